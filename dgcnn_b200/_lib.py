@@ -1,0 +1,126 @@
+"""Build and load ``libdgcnn_b200.so`` -- the C-ABI shared library declared in
+``include/dgcnn_b200.h`` -- and bind it with ctypes.
+
+There is NO CPU fallback: if the library cannot be loaded every operator raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from ctypes import c_char_p, c_int32, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC_DIR = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "lib" / "libdgcnn_b200.so"
+INCLUDE_DIR = PKG_DIR.parent / "include"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only; no PTX for other archs
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+# name -> (restype, argtypes); mirrors include/dgcnn_b200.h one to one
+SIGNATURES = {
+    "dgcnn_abi_version": (c_int32, []),
+    "dgcnn_status_string": (c_char_p, [c_int32]),
+    "dgcnn_build_graph_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "dgcnn_build_graph": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                    c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
+    "dgcnn_graph_ptr": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dgcnn_graph_conv_fwd": (c_int32, [c_void_p, c_int64, c_int32,
+                                       c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p,
+                                       c_void_p, c_int64, c_int32,
+                                       c_int64, c_int32, c_int32, c_void_p]),
+    "dgcnn_graph_conv_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "dgcnn_graph_conv_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64,
+                                       c_void_p, c_int64, c_int32,
+                                       c_void_p, c_void_p, c_void_p,
+                                       c_void_p,
+                                       c_void_p, c_int64, c_int32,
+                                       c_void_p, c_void_p, c_int32,
+                                       c_int64, c_int32, c_int32,
+                                       c_void_p, c_size_t, c_void_p]),
+    "dgcnn_sort_pool_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "dgcnn_sort_pool_fwd": (c_int32, [c_void_p, c_int64, c_int32,
+                                      c_void_p, c_int64, c_int64, c_int32,
+                                      c_int64, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
+    "dgcnn_sort_pool_bwd": (c_int32, [c_void_p, c_void_p, c_int64,
+                                      c_int32, c_int32, c_void_p, c_int64, c_int64,
+                                      c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def sources():
+    return sorted(CSRC_DIR.glob("*.cu"))
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    built = LIB_PATH.stat().st_mtime
+    deps = list(CSRC_DIR.glob("*.cu")) + list(CSRC_DIR.glob("*.cuh")) + list(INCLUDE_DIR.glob("*.h"))
+    return any(p.stat().st_mtime > built for p in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc-compile every kernel for sm_100a into one in-tree shared library."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("dgcnn_b200: nvcc not found; cannot build libdgcnn_b200.so")
+    LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
+    tmp = LIB_PATH.with_suffix(f".tmp{os.getpid()}.so")
+    cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE_DIR), "-o", str(tmp), *map(str, sources())]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        tmp.unlink(missing_ok=True)
+        raise RuntimeError(f"dgcnn_b200: nvcc failed\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def load_library() -> ctypes.CDLL:
+    """Load (building first if the sources are newer) and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _stale():
+            try:
+                build_library()
+            except RuntimeError:
+                if not LIB_PATH.exists():
+                    raise
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError = header/library mismatch: loud
+            fn.restype, fn.argtypes = restype, argtypes
+        if lib.dgcnn_abi_version() != 1:
+            raise RuntimeError("dgcnn_b200: ABI version mismatch between _lib.py and the library")
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load_library().dgcnn_status_string(status).decode()
+        raise RuntimeError(f"dgcnn_b200: {what} failed: {msg} ({status})")

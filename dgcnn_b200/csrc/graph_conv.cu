@@ -1,0 +1,391 @@
+// K1 / K3 -- per-layer graph convolution, forward and backward, for ANY graph
+// size and any channel widths up to 128 (the fused per-graph kernels in
+// graph_stack.cu cover the model's fixed 32/32/32/1 stack when graphs fit a CTA).
+//
+// Reference call sites: model.py:30-33 torch.tanh(self.convN(x, edge_index)),
+// i.e. PyG GCNConv.forward = lin -> propagate(gather, scale, scatter_add) -> +bias.
+// PyG materialises three [E+N, Cout] temporaries per layer and scatters with
+// atomics; here one warp owns one target row, walks its CSR segment once,
+// accumulates in registers in a fixed order (deterministic), applies the
+// D^-1/2 scales, the [Cin x Cout] projection, the bias and the tanh before the
+// single store -- straight into the layer's column slice of the [N,97] buffer.
+//
+// Aggregate-first ((A_hat X) W^T instead of A_hat (X W^T)) is used because it
+// lets the projection stay row-local; both orders agree to fp32 rounding.
+//
+// The same kernel runs the backward aggregation: with `swap_coef` the row/column
+// scales trade places (A_hat^T), the "features" are dpre = dy*(1-y^2), and the
+// row-local matrix is W itself (dx = dh W) instead of W^T.
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int kConvThreads = 256;
+constexpr int kMaxChannels = 128;
+
+struct AggParams {
+    const float* feat;   // [N, fin] rows gathered
+    int64_t ldf;
+    int fin;
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* dis;
+    const float* mat;    // global [cout, cin] weight
+    int mat_transposed;  // 1: smem[k*fout+c] = mat[c*fin+k] (forward); 0: smem = mat (backward)
+    const float* bias;   // [fout] or null
+    float* agg_out;      // optional [N, fin] dense copy of the aggregated rows (dh)
+    float* out;          // optional [N, fout] (ld = ldo)
+    int64_t ldo;
+    int fout;
+    int accumulate;      // out += instead of out =
+    int act;
+    int norm;
+    int swap_coef;       // 0: forward (A_hat), 1: backward (A_hat^T)
+    int64_t n;
+};
+
+__device__ __forceinline__ void load_matrix(const AggParams& p, float* smat, float* sbias) {
+    const int total = p.fin * p.fout;
+    if (p.out) {
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            if (p.mat_transposed) {
+                int c = idx / p.fin, k = idx - c * p.fin;  // mat[c][k], c < fout, k < fin
+                smat[k * p.fout + c] = p.mat[idx];
+            } else {
+                smat[idx] = p.mat[idx];                     // mat[k][c] with k < fin, c < fout
+            }
+        }
+        for (int c = threadIdx.x; c < p.fout; c += blockDim.x) sbias[c] = p.bias ? p.bias[c] : 0.0f;
+    }
+    __syncthreads();
+}
+
+// channel-parallel: lane l owns input channels l, l+32, ... (CPL of them)
+template <int CPL>
+__global__ void __launch_bounds__(kConvThreads) gc_aggregate_chan(AggParams p) {
+    extern __shared__ float smem[];
+    float* smat = smem;
+    float* sbias = smem + p.fin * p.fout;
+    load_matrix(p, smat, sbias);
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (kConvThreads / 32);
+    for (int64_t row = (int64_t)blockIdx.x * (kConvThreads / 32) + (threadIdx.x >> 5); row < p.n;
+         row += warps) {
+        const float di = p.dis[row];
+        const float self_c = p.swap_coef ? row_coef(di, p.norm) : col_coef(di, p.norm);
+        const float scale = p.swap_coef ? col_coef(di, p.norm) : row_coef(di, p.norm);
+        float agg[CPL];
+        const float* fi = p.feat + row * p.ldf;
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            int k = lane + 32 * r;
+            agg[r] = (k < p.fin) ? self_c * fi[k] : 0.0f;
+        }
+        const int beg = p.rowptr[row], end = p.rowptr[row + 1];
+        for (int base = beg; base < end; base += 32) {
+            int e = base + lane;
+            int j = 0;
+            float cj = 0.0f;
+            if (e < end) {
+                j = p.col[e];
+                float dj = p.dis[j];
+                cj = p.swap_coef ? row_coef(dj, p.norm) : col_coef(dj, p.norm);
+            }
+            const int cnt = min(32, end - base);
+#pragma unroll 4
+            for (int t = 0; t < cnt; ++t) {
+                int jj = __shfl_sync(DGCNN_FULL_MASK, j, t);
+                float cc = __shfl_sync(DGCNN_FULL_MASK, cj, t);
+                const float* fj = p.feat + (int64_t)jj * p.ldf;
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) {
+                    int k = lane + 32 * r;
+                    if (k < p.fin) agg[r] = fmaf(cc, fj[k], agg[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            agg[r] *= scale;
+            int k = lane + 32 * r;
+            if (p.agg_out && k < p.fin) p.agg_out[row * p.fin + k] = agg[r];
+        }
+        if (!p.out) continue;
+        float acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int c = lane + 32 * q;
+            acc[q] = (c < p.fout) ? sbias[c] : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            for (int kk = 0; kk < 32; ++kk) {
+                int k = 32 * r + kk;
+                if (k >= p.fin) break;
+                float a = __shfl_sync(DGCNN_FULL_MASK, agg[r], kk);
+                const float* mrow = smat + k * p.fout;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int c = lane + 32 * q;
+                    if (c < p.fout) acc[q] = fmaf(a, mrow[c], acc[q]);
+                }
+            }
+        }
+        float* orow = p.out + row * p.ldo;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int c = lane + 32 * q;
+            if (c < p.fout) {
+                float v = p.act == DGCNN_ACT_TANH ? tanhf(acc[q]) : acc[q];
+                orow[c] = p.accumulate ? orow[c] + v : v;
+            }
+        }
+    }
+}
+
+// edge-parallel: for narrow rows (fin <= FINP <= 8) the lanes split the
+// neighbours instead of the channels and combine with warp-shuffle partial sums
+template <int FINP>
+__global__ void __launch_bounds__(kConvThreads) gc_aggregate_edge(AggParams p) {
+    extern __shared__ float smem[];
+    float* smat = smem;
+    float* sbias = smem + p.fin * p.fout;
+    load_matrix(p, smat, sbias);
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (kConvThreads / 32);
+    for (int64_t row = (int64_t)blockIdx.x * (kConvThreads / 32) + (threadIdx.x >> 5); row < p.n;
+         row += warps) {
+        const float di = p.dis[row];
+        const float self_c = p.swap_coef ? row_coef(di, p.norm) : col_coef(di, p.norm);
+        const float scale = p.swap_coef ? col_coef(di, p.norm) : row_coef(di, p.norm);
+        float agg[FINP];
+#pragma unroll
+        for (int k = 0; k < FINP; ++k) agg[k] = 0.0f;
+        const int beg = p.rowptr[row], end = p.rowptr[row + 1];
+        for (int e = beg + lane; e < end; e += 32) {
+            int j = p.col[e];
+            float dj = p.dis[j];
+            float cj = p.swap_coef ? row_coef(dj, p.norm) : col_coef(dj, p.norm);
+            const float* fj = p.feat + (int64_t)j * p.ldf;
+#pragma unroll
+            for (int k = 0; k < FINP; ++k)
+                if (k < p.fin) agg[k] = fmaf(cj, fj[k], agg[k]);
+        }
+        const float* fi = p.feat + row * p.ldf;
+#pragma unroll
+        for (int k = 0; k < FINP; ++k) {
+            float s = warp_sum(agg[k]);
+            agg[k] = (k < p.fin) ? scale * fmaf(self_c, fi[k], s) : 0.0f;
+            if (p.agg_out && k < p.fin && lane == 0) p.agg_out[row * p.fin + k] = agg[k];
+        }
+        if (!p.out) continue;
+        float* orow = p.out + row * p.ldo;
+        for (int c = lane; c < p.fout; c += 32) {
+            float acc = sbias[c];
+#pragma unroll
+            for (int k = 0; k < FINP; ++k)
+                if (k < p.fin) acc = fmaf(agg[k], smat[k * p.fout + c], acc);
+            float v = p.act == DGCNN_ACT_TANH ? tanhf(acc) : acc;
+            orow[c] = p.accumulate ? orow[c] + v : v;
+        }
+    }
+}
+
+static int launch_aggregate(const AggParams& p, cudaStream_t st) {
+    size_t smem = p.out ? sizeof(float) * ((size_t)p.fin * p.fout + p.fout) : 0;
+    int grid = grid_for(p.n, kConvThreads / 32, 8);
+#define DGCNN_LAUNCH_AGG(KERNEL)                                                              \
+    do {                                                                                      \
+        if (smem > 48 * 1024 &&                                                               \
+            cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                 (int)smem) != cudaSuccess)                                   \
+            return DGCNN_ERR_CUDA;                                                            \
+        KERNEL<<<grid, kConvThreads, smem, st>>>(p);                                          \
+    } while (0)
+    if (p.fin <= 1) DGCNN_LAUNCH_AGG(gc_aggregate_edge<1>);
+    else if (p.fin <= 2) DGCNN_LAUNCH_AGG(gc_aggregate_edge<2>);
+    else if (p.fin <= 4) DGCNN_LAUNCH_AGG(gc_aggregate_edge<4>);
+    else if (p.fin <= 8) DGCNN_LAUNCH_AGG(gc_aggregate_edge<8>);
+    else if (p.fin <= 32) DGCNN_LAUNCH_AGG(gc_aggregate_chan<1>);
+    else if (p.fin <= 64) DGCNN_LAUNCH_AGG(gc_aggregate_chan<2>);
+    else if (p.fin <= 96) DGCNN_LAUNCH_AGG(gc_aggregate_chan<3>);
+    else DGCNN_LAUNCH_AGG(gc_aggregate_chan<4>);
+#undef DGCNN_LAUNCH_AGG
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
+// ---- backward, step A: dpre = dy * act'(y), db = column sums -------------------
+// block = (CX, 256/CX): x indexes the channel, y a row inside the block's slab
+__global__ void __launch_bounds__(256)
+gc_bwd_dpre(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy,
+            int cout, int64_t n, int act, float* __restrict__ dpre, float* __restrict__ db) {
+    __shared__ float red[256];
+    const int c = threadIdx.x;
+    const int rows_per_block = blockDim.y;
+    float part = 0.0f;
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.y; row < n;
+         row += (int64_t)gridDim.x * rows_per_block) {
+        if (c < cout) {
+            float g = dy[row * lddy + c];
+            if (act == DGCNN_ACT_TANH) {
+                float v = y[row * ldy + c];
+                g *= 1.0f - v * v;
+            }
+            dpre[row * cout + c] = g;
+            part += g;
+        }
+    }
+    if (!db) return;
+    red[threadIdx.y * blockDim.x + c] = part;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cout) {
+        float s = 0.0f;
+        for (int r = 0; r < rows_per_block; ++r) s += red[r * blockDim.x + c];
+        atomicAdd(&db[c], s);
+    }
+}
+
+// ---- backward, step C: dw[c][k] = sum_i dh[i][c] * x[i][k] -----------------------
+// grid (row slabs, output tiles of 1024): each CTA keeps 4 outputs per thread in
+// registers while it strides over 32-row slabs staged in shared memory
+constexpr int kDwRows = 32;
+__global__ void __launch_bounds__(256)
+gc_bwd_dw(const float* __restrict__ dh, const float* __restrict__ x, int64_t ldx, int cin, int cout,
+          int64_t n, float* __restrict__ dw) {
+    extern __shared__ float smem[];
+    float* sdh = smem;                   // [kDwRows][cout]
+    float* sx = smem + kDwRows * cout;   // [kDwRows][cin]
+    const int total = cin * cout;
+    int oc[4], ok[4];
+    float acc[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        int o = blockIdx.y * 1024 + m * 256 + threadIdx.x;
+        oc[m] = (o < total) ? o / cin : -1;
+        ok[m] = (o < total) ? o - oc[m] * cin : 0;
+        acc[m] = 0.0f;
+    }
+    const int64_t slabs = ceil_div(n, kDwRows);
+    for (int64_t slab = blockIdx.x; slab < slabs; slab += gridDim.x) {
+        const int64_t r0 = slab * kDwRows;
+        const int rows = (int)min((int64_t)kDwRows, n - r0);
+        for (int idx = threadIdx.x; idx < rows * cout; idx += 256) sdh[idx] = dh[r0 * cout + idx];
+        for (int idx = threadIdx.x; idx < rows * cin; idx += 256) {
+            int r = idx / cin, k = idx - r * cin;
+            sx[idx] = x[(r0 + r) * ldx + k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            if (oc[m] >= 0) {
+                float a = acc[m];
+                for (int r = 0; r < rows; ++r) a = fmaf(sdh[r * cout + oc[m]], sx[r * cin + ok[m]], a);
+                acc[m] = a;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        if (oc[m] >= 0) atomicAdd(&dw[oc[m] * cin + ok[m]], acc[m]);
+}
+
+struct BwdWorkspace {
+    float* dpre;
+    float* dh;
+    size_t bytes;
+};
+
+__host__ inline BwdWorkspace carve_bwd_workspace(void* base, int64_t n, int cout) {
+    BwdWorkspace w;
+    size_t each = align_up(sizeof(float) * (size_t)n * (size_t)cout, 256);
+    char* p = static_cast<char*>(base);
+    w.dpre = reinterpret_cast<float*>(p);
+    w.dh = reinterpret_cast<float*>(p ? p + each : nullptr);
+    w.bytes = 2 * each;
+    return w;
+}
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+extern "C" int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin, const int32_t* rowptr,
+                                    const int32_t* col, const float* dis, const float* weight,
+                                    const float* bias, float* y, int64_t ldy, int32_t cout,
+                                    int64_t num_nodes, int32_t norm, int32_t act, void* stream) {
+    if (num_nodes < 0 || cin < 1 || cout < 1 || ldx < cin || ldy < cout)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (norm != DGCNN_NORM_SYM && norm != DGCNN_NORM_RW) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (act != DGCNN_ACT_NONE && act != DGCNN_ACT_TANH) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (cin > kMaxChannels || cout > kMaxChannels) return DGCNN_ERR_UNSUPPORTED;
+    if (num_nodes == 0) return DGCNN_OK;
+    if (!x || !rowptr || !dis || !weight || !y) return DGCNN_ERR_INVALID_ARGUMENT;
+    AggParams p{};
+    p.feat = x; p.ldf = ldx; p.fin = cin;
+    p.rowptr = rowptr; p.col = col; p.dis = dis;
+    p.mat = weight; p.mat_transposed = 1; p.bias = bias;
+    p.agg_out = nullptr; p.out = y; p.ldo = ldy; p.fout = cout;
+    p.accumulate = 0; p.act = act; p.norm = norm; p.swap_coef = 0; p.n = num_nodes;
+    return launch_aggregate(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t dgcnn_graph_conv_bwd_workspace_bytes(int64_t num_nodes, int32_t cin, int32_t cout) {
+    (void)cin;
+    if (num_nodes < 0 || cout < 1) return 0;
+    return carve_bwd_workspace(nullptr, num_nodes, cout).bytes + 256;
+}
+
+extern "C" int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy,
+                                    const float* x, int64_t ldx, int32_t cin,
+                                    const int32_t* rowptr_t, const int32_t* col_t, const float* dis,
+                                    const float* weight, float* dx, int64_t lddx,
+                                    int32_t accumulate_dx, float* dw, float* db, int32_t cout,
+                                    int64_t num_nodes, int32_t norm, int32_t act, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    const int64_t n = num_nodes;
+    if (n < 0 || cin < 1 || cout < 1 || ldx < cin || lddy < cout) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (norm != DGCNN_NORM_SYM && norm != DGCNN_NORM_RW) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (act != DGCNN_ACT_NONE && act != DGCNN_ACT_TANH) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (act == DGCNN_ACT_TANH && (!y || ldy < cout) && n > 0) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (cin > kMaxChannels || cout > kMaxChannels) return DGCNN_ERR_UNSUPPORTED;
+    if (!dw || (dx && lddx < cin)) return DGCNN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cin * cout, st) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    if (db && cudaMemsetAsync(db, 0, sizeof(float) * (size_t)cout, st) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    if (n == 0) return DGCNN_OK;
+    if (!dy || !x || !rowptr_t || !dis || !weight) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < dgcnn_graph_conv_bwd_workspace_bytes(n, cin, cout))
+        return DGCNN_ERR_WORKSPACE;
+    uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    BwdWorkspace w = carve_bwd_workspace(reinterpret_cast<void*>(aligned), n, cout);
+
+    // A: dpre, db
+    int cx = (int)next_pow2((uint32_t)cout);
+    dim3 block_a(cx, 256 / cx);
+    gc_bwd_dpre<<<grid_for(n, block_a.y, 8), block_a, 0, st>>>(dy, lddy, y, ldy, cout, n, act, w.dpre,
+                                                               db);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+
+    // B: dh = A_hat^T dpre (kept dense for step C), dx (+)= dh W
+    AggParams p{};
+    p.feat = w.dpre; p.ldf = cout; p.fin = cout;
+    p.rowptr = rowptr_t; p.col = col_t; p.dis = dis;
+    p.mat = weight; p.mat_transposed = 0; p.bias = nullptr;
+    p.agg_out = w.dh; p.out = dx; p.ldo = lddx; p.fout = cin;
+    p.accumulate = accumulate_dx; p.act = DGCNN_ACT_NONE; p.norm = norm; p.swap_coef = 1; p.n = n;
+    int rc = launch_aggregate(p, st);
+    if (rc != DGCNN_OK) return rc;
+
+    // C: dw = dh^T x
+    dim3 grid_c((unsigned)grid_for(ceil_div(n, kDwRows), 1, 2), (unsigned)ceil_div(cin * cout, 1024));
+    size_t smem_c = sizeof(float) * kDwRows * (size_t)(cin + cout);
+    gc_bwd_dw<<<grid_c, 256, smem_c, st>>>(w.dh, x, ldx, cin, cout, n, dw);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}

@@ -1,0 +1,196 @@
+// K2 / K4 -- SortPooling forward and backward.
+//
+// Reference call site: model.py:17,35  self.sort_pool = SortAggregation(k=30);
+// x = self.sort_pool(x, batch).  PyG's SortAggregation.forward scatters x into a
+// dense [B, Nmax, D] tensor padded with (x.min()-1), sorts every padded row of
+// length Nmax on the last channel, gathers ALL B*Nmax rows, slices/pads to k and
+// finally overwrites the fill value with 0.  Here one CTA owns one graph: it
+// sorts that graph's n_g keys only (64-bit key|index composites, bitonic network
+// in shared memory), then copies just the min(n_g,k) winning rows and zero-fills
+// the rest.  No dense detour, no host sync, and the permutation is emitted for
+// the backward scatter.
+//
+// Order contract (pinned by the oracle with stable=True):
+// descending key, ties by ascending node index, -0.0 == +0.0, NaN first.
+#include "common.cuh"
+
+namespace dgcnn {
+
+// float -> uint32 whose ASCENDING order is the contract's DESCENDING key order
+__host__ __device__ __forceinline__ uint32_t descending_key_bits(float v) {
+    uint32_t b;
+#ifdef __CUDA_ARCH__
+    b = __float_as_uint(v);
+#else
+    union { float f; uint32_t u; } cvt; cvt.f = v; b = cvt.u;
+#endif
+    if ((b & 0x7fffffffu) > 0x7f800000u) return 0u;           // NaN sorts first
+    if (b == 0x80000000u) b = 0u;                              // -0.0 == +0.0
+    uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u); // ascending-order map
+    return ~asc;
+}
+
+constexpr uint64_t kPadComposite = ~0ull;  // sorts after every real element
+
+__device__ __forceinline__ void bitonic_sort_block(uint64_t* buf, uint32_t p) {
+    for (uint32_t size = 2; size <= p; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (p >> 1); t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
+                uint32_t hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t a = buf[lo], b = buf[hi];
+                if ((a > b) == up) {
+                    buf[lo] = b;
+                    buf[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// one CTA per graph (grid-stride). smem_cap = composites that fit the dynamic
+// shared buffer; larger graphs sort in the global workspace slice [2*base, 2*base+P)
+__global__ void __launch_bounds__(1024)
+sp_fwd_kernel(const float* __restrict__ x, int64_t ldx, int d,
+                              const int32_t* __restrict__ gptr, int64_t num_graphs, int k,
+                              float* __restrict__ out, int32_t* __restrict__ perm,
+                              uint64_t* __restrict__ workspace, uint32_t smem_cap) {
+    extern __shared__ uint64_t sbuf[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int64_t g = blockIdx.x; g < num_graphs; g += gridDim.x) {
+        const int base = gptr[g];
+        const int n = gptr[g + 1] - base;
+        const int keep = min(n, k);
+        if (n > 1) {
+            const uint32_t p = next_pow2((uint32_t)n);
+            uint64_t* buf = (p <= smem_cap) ? sbuf : workspace + 2 * (int64_t)base;
+            __syncthreads();  // previous graph's readers are done with sbuf
+            for (uint32_t t = threadIdx.x; t < p; t += blockDim.x) {
+                uint64_t c = kPadComposite;
+                if (t < (uint32_t)n) {
+                    float key = x[(int64_t)(base + t) * ldx + (d - 1)];
+                    c = ((uint64_t)descending_key_bits(key) << 32) | t;
+                }
+                buf[t] = c;
+            }
+            bitonic_sort_block(buf, p);
+            // warp per output row: gather the winners
+            for (int r = warp; r < keep; r += nwarps) {
+                int srcrow = base + (int)(uint32_t)(buf[r] & 0xffffffffu);
+                const float* xr = x + (int64_t)srcrow * ldx;
+                float* orow = out + ((int64_t)g * k + r) * d;
+                for (int c = lane; c < d; c += 32) orow[c] = xr[c];
+                if (lane == 0) perm[g * k + r] = srcrow;
+            }
+        } else if (n == 1) {
+            const float* xr = x + (int64_t)base * ldx;
+            float* orow = out + (int64_t)g * k * d;
+            if (keep == 1) {
+                for (int c = threadIdx.x; c < d; c += blockDim.x) orow[c] = xr[c];
+                if (threadIdx.x == 0) perm[g * k] = base;
+            }
+        }
+        // zero padding for rows keep..k-1 (contiguous)
+        float* pad = out + ((int64_t)g * k + keep) * d;
+        const int64_t pad_elems = (int64_t)(k - keep) * d;
+        for (int64_t i = threadIdx.x; i < pad_elems; i += blockDim.x) pad[i] = 0.0f;
+        for (int r = keep + threadIdx.x; r < k; r += blockDim.x) perm[g * k + r] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sp_bwd_zero(float* __restrict__ dx, int64_t lddx, int d, int64_t n) {
+    int64_t total = n * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / d;
+        dx[r * lddx + (i - r * d)] = 0.0f;
+    }
+}
+
+// warp per pooled row: dx[perm] = dout
+__global__ void __launch_bounds__(256)
+sp_bwd_scatter(const float* __restrict__ dout, const int32_t* __restrict__ perm, int64_t rows, int d,
+               float* __restrict__ dx, int64_t lddx, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+         r += warps) {
+        int p = perm[r];
+        if (p < 0 || p >= n) continue;
+        const float* g = dout + r * d;
+        float* o = dx + (int64_t)p * lddx;
+        for (int c = lane; c < d; c += 32) o[c] = g[c];
+    }
+}
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+extern "C" size_t dgcnn_sort_pool_workspace_bytes(int64_t num_nodes, int64_t num_graphs) {
+    (void)num_graphs;
+    if (num_nodes < 0) return 0;
+    // fallback sort buffer for graphs too large for shared memory: next_pow2(n_g) <= 2 n_g
+    return sizeof(uint64_t) * 2 * (size_t)num_nodes + 256;
+}
+
+extern "C" int dgcnn_sort_pool_fwd(const float* x, int64_t ldx, int32_t d, const int32_t* gptr,
+                                   int64_t num_nodes, int64_t num_graphs, int32_t k,
+                                   int64_t max_nodes_hint, float* out,
+                                   int32_t* perm, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+    if (num_graphs < 0 || num_nodes < 0 || d < 1 || k < 1 || ldx < d)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_graphs == 0) return DGCNN_OK;
+    if (!gptr || !out || !perm || (num_nodes > 0 && !x)) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_graphs * (int64_t)k >= INT32_MAX || num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < dgcnn_sort_pool_workspace_bytes(num_nodes, num_graphs))
+        return DGCNN_ERR_WORKSPACE;
+    uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+
+    // shared sort buffer: sized from the hint, 64 KB (8192 nodes) when unknown,
+    // never above 128 KB (16384 nodes) so that at least one CTA/SM stays resident
+    uint32_t cap = 8192;
+    if (max_nodes_hint > 0) {
+        cap = next_pow2((uint32_t)(max_nodes_hint > 16384 ? 16384 : max_nodes_hint));
+        if (cap < 64) cap = 64;
+    }
+    size_t smem = sizeof(uint64_t) * cap;
+    int threads = cap >= 2048 ? 1024 : (cap >= 512 ? 256 : 128);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(sp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    int grid = (int)(num_graphs < 8 * DGCNN_NUM_SMS ? num_graphs : 8 * DGCNN_NUM_SMS);
+    sp_fwd_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, d, gptr, num_graphs, k, out, perm, reinterpret_cast<uint64_t*>(aligned), cap);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
+extern "C" int dgcnn_sort_pool_bwd(const float* dout, const int32_t* perm, int64_t num_graphs,
+                                   int32_t k, int32_t d, float* dx, int64_t lddx, int64_t num_nodes,
+                                   void* stream) {
+    if (num_graphs < 0 || num_nodes < 0 || d < 1 || k < 1 || lddx < d)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_nodes == 0) return DGCNN_OK;
+    if (!dx) return DGCNN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (lddx == d) {
+        if (cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)num_nodes * d, st) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+    } else {
+        sp_bwd_zero<<<grid_for(num_nodes * d, 256, 8), 256, 0, st>>>(dx, lddx, d, num_nodes);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
+    if (num_graphs == 0) return DGCNN_OK;
+    if (!dout || !perm) return DGCNN_ERR_INVALID_ARGUMENT;
+    int64_t rows = num_graphs * k;
+    sp_bwd_scatter<<<grid_for(rows, 8, 8), 256, 0, st>>>(dout, perm, rows, d, dx, lddx, num_nodes);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}

@@ -1,0 +1,68 @@
+"""Graph-sharded data parallelism: one process per GPU, every rank
+runs the hot path on its own slice of the batch's graphs with replicated
+parameters, and ONE all-reduce on a flat fp32 gradient bucket closes the step.
+
+The reference has no distributed code (single device, train.py:75-79); this is
+the one collective the build adds.  Graphs are independent block-diagonal
+components in both GraphConv and SortPool (model.py:30-35 never mixes graphs),
+so no data-path collective exists -- only the gradient sum.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_bounds", "GradBucket"]
+
+
+def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
+    """Split graphs ``0..len(costs)`` into ``world_size`` CONTIGUOUS slices of nearly
+    equal total cost (cost ~ nodes + edges of a graph; counts alone skew badly on
+    D&D-like size tails).  Returns [(lo, hi)] per rank; slices may be empty."""
+    n = len(costs)
+    total = float(sum(costs))
+    bounds, lo, acc = [], 0, 0.0
+    for r in range(world_size):
+        target = total * (r + 1) / world_size
+        hi = lo
+        while hi < n and (acc + costs[hi] <= target or hi == lo and n - hi > world_size - r - 1
+                          and acc + 0.5 * costs[hi] <= target):
+            acc += costs[hi]
+            hi += 1
+        if r == world_size - 1:
+            hi = n
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+class GradBucket:
+    """All parameter gradients as views into ONE flat fp32 buffer, plus ``extra``
+    trailing slots for step scalars (loss sum, correct count) so that they ride
+    the same collective.  ``p.grad`` aliases the bucket: autograd accumulates in
+    place, the all-reduce needs no gather/scatter copies."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 2):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucket needs at least one trainable parameter")
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total + extra, dtype=torch.float32, device=dev)
+        self.extra = self.flat[total:]
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce(self, global_batch: int, group=None) -> None:
+        """Sum over ranks, then turn the summed (not averaged) local NLL gradients into
+        the gradient of the GLOBAL-batch mean loss.  Scalars in ``extra`` stay sums."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat[: self.flat.numel() - self.extra.numel()].mul_(1.0 / float(global_batch))

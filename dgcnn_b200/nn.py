@@ -1,0 +1,301 @@
+"""Host-side mirror of the Module API the reference's model.py consumes.
+
+Same names, argument meaning, parameter names and error behaviour as the PyG
+classes the reference imports (model.py:5-6), backed by the sm_100a kernels:
+
+    GCNConv(in, out)         (alias GraphConvolution)   model.py:13-16, 30-33
+    SortAggregation(k)       (alias SortPool)           model.py:17, 35
+    remove_self_loops(ei)                               model.py:28
+    Model(num_features, num_classes, k=30)              model.py:9-45
+
+State-dict keys are PyG's (``convN.lin.weight [Cout,Cin]``, ``convN.bias``), so
+the reference's ``epochs/*.pth`` (train.py:129) load unchanged.  CUDA only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Union
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import ops
+from .ops import ACT_NONE, ACT_TANH, NORM_RW, NORM_SYM, Graph
+
+__all__ = ["GCNConv", "GraphConvolution", "SortAggregation", "SortPool", "Model",
+           "remove_self_loops", "graph_conv_stack", "classifier_in_features"]
+
+
+def remove_self_loops(edge_index: Tensor, edge_attr: Optional[Tensor] = None):
+    """model.py:28.  Kept for drop-in compatibility; ``Model`` does not need it
+    because K0 drops loops while it builds the CSR."""
+    keep = edge_index[0] != edge_index[1]
+    return edge_index[:, keep], (None if edge_attr is None else edge_attr[keep])
+
+
+def _norm_id(norm: Union[int, str]) -> int:
+    if norm in (NORM_SYM, "sym"):
+        return NORM_SYM
+    if norm in (NORM_RW, "rw"):
+        return NORM_RW
+    raise ValueError(f"norm must be 'sym' or 'rw', got {norm!r}")
+
+
+# ----------------------------------------------------------------------------------
+# autograd glue
+# ----------------------------------------------------------------------------------
+class _GraphConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph: Graph, norm: int, act: int):
+        x = x if x.stride(-1) == 1 else x.contiguous()
+        out = torch.empty(x.size(0), weight.size(0), dtype=torch.float32, device=x.device)
+        ops.graph_conv_fwd(x, graph.rowptr, graph.col, graph.dis, weight, bias, norm, act, out)
+        ctx.graph, ctx.norm, ctx.act = graph, norm, act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, out if act == ACT_TANH else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        g = ctx.graph
+        if g.rowptr_t is None:
+            raise RuntimeError("dgcnn_b200: graph was built with transpose=False; no backward")
+        dy = dy if dy.stride(-1) == 1 and dy.dim() == 2 else dy.contiguous()
+        dx = (torch.empty(x.shape, dtype=x.dtype, device=x.device)
+              if ctx.needs_input_grad[0] else None)
+        dw, db = ops.graph_conv_bwd(dy, y, x, g.rowptr_t, g.col_t, g.dis, weight, ctx.norm, ctx.act,
+                                    dx, False, need_db=ctx.has_bias)
+        return dx, dw, db, None, None, None
+
+
+class _SortPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gptr, k: int, max_nodes: int):
+        x = x if x.stride(-1) == 1 else x.contiguous()
+        out, perm = ops.sort_pool_fwd(x, gptr, k, max_nodes)
+        ctx.save_for_backward(perm)
+        ctx.n, ctx.d = x.size(0), x.size(1)
+        ctx.mark_non_differentiable(perm)
+        return out, perm
+
+    @staticmethod
+    def backward(ctx, dout, _dperm):
+        (perm,) = ctx.saved_tensors
+        return ops.sort_pool_bwd(dout.contiguous().view(perm.size(0), -1), perm, ctx.n), None, None, None
+
+
+class _StackFn(torch.autograd.Function):
+    """model.py:28-35 as ONE autograd node: L x tanh(GCNConv) written in place into
+    the concatenated [N, sum(Cout)] buffer, then SortPooling.  Backward scatters the
+    pooled gradient into a [N, sum(Cout)] gradient buffer and walks the layers in
+    reverse, each one adding its input gradient into the previous layer's slice."""
+
+    @staticmethod
+    def forward(ctx, x, graph: Graph, k: int, norm: int, *params):
+        weights, biases = params[0::2], params[1::2]
+        x = x if x.stride(-1) == 1 else x.contiguous()
+        n = x.size(0)
+        widths = [w.size(0) for w in weights]
+        offs = [0]
+        for c in widths:
+            offs.append(offs[-1] + c)
+        xcat = torch.empty(n, offs[-1], dtype=torch.float32, device=x.device)
+        h = x
+        for l, (w, b) in enumerate(zip(weights, biases)):
+            out = xcat[:, offs[l]:offs[l + 1]]
+            ops.graph_conv_fwd(h, graph.rowptr, graph.col, graph.dis, w, b, norm, ACT_TANH, out)
+            h = out
+        pooled, perm = ops.sort_pool_fwd(xcat, graph.gptr, k, graph.max_nodes)
+        ctx.graph, ctx.norm, ctx.offs = graph, norm, offs
+        ctx.has_bias = [b is not None for b in biases]
+        ctx.save_for_backward(x, xcat, perm, *weights)
+        ctx.mark_non_differentiable(perm)
+        ctx.set_materialize_grads(False)
+        return pooled, xcat, perm
+
+    @staticmethod
+    def backward(ctx, dpooled, dxcat_in, _dperm):
+        x, xcat, perm, *weights = ctx.saved_tensors
+        g, offs, norm = ctx.graph, ctx.offs, ctx.norm
+        if g.rowptr_t is None:
+            raise RuntimeError("dgcnn_b200: graph was built with transpose=False; no backward")
+        n = xcat.size(0)
+        if dpooled is not None:
+            dxcat = ops.sort_pool_bwd(dpooled.contiguous().view(perm.size(0), -1), perm, n)
+            if dxcat_in is not None:
+                dxcat = dxcat + dxcat_in
+        elif dxcat_in is not None:
+            dxcat = dxcat_in.clone()
+        else:
+            dxcat = torch.zeros_like(xcat)
+        grads = []
+        nl = len(weights)
+        for l in range(nl - 1, -1, -1):
+            ysl = slice(offs[l], offs[l + 1])
+            if l > 0:
+                xsl = slice(offs[l - 1], offs[l])
+                xin, dx, acc = xcat[:, xsl], dxcat[:, xsl], True
+            else:
+                xin = x
+                dx = (torch.empty(x.shape, dtype=x.dtype, device=x.device)
+                      if ctx.needs_input_grad[0] else None)
+                acc = False
+            dw, db = ops.graph_conv_bwd(dxcat[:, ysl], xcat[:, ysl], xin, g.rowptr_t, g.col_t, g.dis,
+                                        weights[l], norm, ACT_TANH, dx, acc,
+                                        need_db=ctx.has_bias[l])
+            grads.append((dw, db))
+            if l == 0:
+                dx0 = dx
+        flat = []
+        for dw, db in reversed(grads):
+            flat += [dw, db]
+        return (dx0, None, None, None, *flat)
+
+
+def graph_conv_stack(x: Tensor, graph: Graph, weights: Sequence[Tensor], biases: Sequence[Tensor],
+                     k: int, norm: int = NORM_SYM):
+    """Functional form of model.py:28-35 -> (pooled [B,k*D], x_cat [N,D], perm [B,k])."""
+    if graph.gptr is None:
+        raise ValueError("dgcnn_b200: graph was built without `batch`; SortPooling needs gptr")
+    params = []
+    for w, b in zip(weights, biases):
+        params += [w, b]
+    return _StackFn.apply(x, graph, int(k), int(norm), *params)
+
+
+# ----------------------------------------------------------------------------------
+# Modules
+# ----------------------------------------------------------------------------------
+class _Lin(nn.Module):
+    """PyG's ``Linear(in, out, bias=False, weight_initializer='glorot')`` -- only the
+    parameter container; the product is done inside the fused kernel."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.weight.size(0) + self.weight.size(1)))
+        with torch.no_grad():
+            self.weight.uniform_(-a, a)
+
+
+class GCNConv(nn.Module):
+    """``GCNConv(in_channels, out_channels)`` as model.py:13-16 constructs it (PyG
+    defaults: symmetric norm, self loops added, bias).  ``forward(x, edge_index)``
+    accepts the int64 ``[2,E]`` tensor of the reference or a prebuilt ``Graph``."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True,
+                 norm: Union[int, str] = "sym"):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.norm = _norm_id(norm)
+        self.lin = _Lin(in_channels, out_channels)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x: Tensor, edge_index: Union[Tensor, Graph], act: int = ACT_NONE) -> Tensor:
+        graph = edge_index if isinstance(edge_index, Graph) else ops.build_graph(
+            edge_index, None, x.size(0), 0, transpose=torch.is_grad_enabled())
+        return _GraphConvFn.apply(x, self.lin.weight, self.bias, graph, self.norm, act)
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}"
+
+
+class SortAggregation(nn.Module):
+    """``SortAggregation(k)`` as model.py:17 constructs it; ``forward(x, index)`` takes
+    the non-decreasing graph id per node (model.py:35).  ``dim_size`` (PyG's name for
+    the number of graphs) avoids the ``index.max()`` host sync PyG also pays."""
+
+    def __init__(self, k: int):
+        super().__init__()
+        self.k = k
+
+    def forward(self, x: Tensor, index: Optional[Tensor] = None, ptr: Optional[Tensor] = None,
+                dim_size: Optional[int] = None, graph: Optional[Graph] = None,
+                return_perm: bool = False):
+        if graph is not None and graph.gptr is not None:
+            gptr, max_nodes = graph.gptr, graph.max_nodes
+        else:
+            if index is None:
+                raise ValueError("SortAggregation needs `index` (graph id per node)")
+            if dim_size is None:
+                dim_size = int(index.max()) + 1 if index.numel() else 0   # sync, like PyG
+            gptr, max_nodes = ops.graph_ptr(index, dim_size), 0
+        out, perm = _SortPoolFn.apply(x, gptr, self.k, max_nodes)
+        return (out, perm) if return_perm else out
+
+    def extra_repr(self):
+        return f"k={self.k}"
+
+
+GraphConvolution = GCNConv
+SortPool = SortAggregation
+
+
+def classifier_in_features(k: int) -> int:
+    """352 for the reference's k=30 (model.py:21): conv5 -> k, pool -> k//2, conv6 -> -4."""
+    return 32 * (k // 2 - 4)
+
+
+class Model(nn.Module):
+    """model.py:9-45 with ``k`` a parameter (the reference hard-codes 30 and 352)."""
+
+    def __init__(self, num_features: int, num_classes: int, k: int = 30,
+                 norm: Union[int, str] = "sym"):
+        super().__init__()
+        if k // 2 - 4 < 1:
+            raise ValueError("k too small for conv6 (kernel 5 after the 2x max-pool)")
+        self.conv1 = GCNConv(num_features, 32, norm=norm)
+        self.conv2 = GCNConv(32, 32, norm=norm)
+        self.conv3 = GCNConv(32, 32, norm=norm)
+        self.conv4 = GCNConv(32, 1, norm=norm)
+        self.sort_pool = SortAggregation(k=k)
+        self.conv5 = nn.Conv1d(1, 16, 97, 97)
+        self.conv6 = nn.Conv1d(16, 32, 5, 1)
+        self.pool = nn.MaxPool1d(2, 2)
+        self.classifier_1 = nn.Linear(classifier_in_features(k), 128)
+        self.drop_out = nn.Dropout(0.5)
+        self.classifier_2 = nn.Linear(128, num_classes)
+        self.relu = nn.ReLU(inplace=True)
+
+    # -- hot path: model.py:27-35 -----------------------------------------------------
+    def build_graph(self, data) -> Graph:
+        cached = getattr(data, "_dgcnn_graph", None)
+        if cached is not None:
+            return cached
+        num_graphs = getattr(data, "num_graphs", None)
+        if num_graphs is None:
+            num_graphs = int(data.batch.max()) + 1                    # sync, like PyG
+        return ops.build_graph(data.edge_index, data.batch, data.x.size(0), int(num_graphs),
+                               transpose=torch.is_grad_enabled(),
+                               max_nodes=int(getattr(data, "max_nodes", 0) or 0))
+
+    def hot_path(self, x: Tensor, graph: Graph):
+        convs = (self.conv1, self.conv2, self.conv3, self.conv4)
+        return graph_conv_stack(x, graph, [c.lin.weight for c in convs], [c.bias for c in convs],
+                                self.sort_pool.k, self.conv1.norm)
+
+    # -- dense tail: model.py:36-43 (stock torch) -------------------------------------
+    def tail(self, pooled: Tensor) -> Tensor:
+        h = pooled.view(pooled.size(0), 1, pooled.size(-1))
+        h = self.pool(self.relu(self.conv5(h)))
+        h = self.relu(self.conv6(h))
+        h = h.view(h.size(0), -1)
+        h = self.drop_out(self.relu(self.classifier_1(h)))
+        return F.log_softmax(self.classifier_2(h), dim=-1)
+
+    def forward(self, data) -> Tensor:
+        pooled, _, _ = self.hot_path(data.x, self.build_graph(data))
+        return self.tail(pooled)

@@ -1,0 +1,259 @@
+"""Operator layer: torch tensors in, C-ABI calls out (``include/dgcnn_b200.h``).
+
+Every function here validates dtype / device / layout, allocates outputs and
+scratch through torch's caching allocator (no sync), and launches on torch's
+current CUDA stream -- so the ops compose with streams and CUDA-graph capture.
+The same functions are registered as ``torch.ops.dgcnn_b200.*`` (CUDA dispatch
+key only: a CPU tensor raises, there is no CPU path).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+NORM_SYM, NORM_RW = 0, 1
+ACT_NONE, ACT_TANH = 0, 1
+GRAPH_BAD_EDGE, GRAPH_BAD_BATCH = 1, 2
+
+
+def _require_cuda(t: Tensor, name: str, dtype: torch.dtype) -> None:
+    if not isinstance(t, Tensor):
+        raise TypeError(f"dgcnn_b200: {name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"dgcnn_b200: {name} is on {t.device}; the hot path is CUDA-only "
+                           "(there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"dgcnn_b200: {name} must be {dtype}, got {t.dtype}")
+
+
+def _rows(t: Tensor, name: str) -> int:
+    """Leading dimension (in elements) of a 2-D row-major, possibly column-sliced, tensor."""
+    if t.dim() != 2 or (t.size(1) > 1 and t.stride(1) != 1):
+        raise ValueError(f"dgcnn_b200: {name} must be 2-D with unit column stride, got "
+                         f"shape {tuple(t.shape)} strides {t.stride()}")
+    if t.size(0) <= 1:
+        return max(int(t.stride(0)), int(t.size(1)))
+    return int(t.stride(0))
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+@dataclass
+class Graph:
+    """Device-resident batched graph shared by all layers of one forward/backward:
+    int32 CSR by target (``rowptr/col``), its transpose (``rowptr_t/col_t``),
+    ``dis = (1+in_degree)^-1/2`` and per-graph node offsets ``gptr``."""
+    rowptr: Tensor
+    col: Tensor
+    rowptr_t: Optional[Tensor]
+    col_t: Optional[Tensor]
+    dis: Tensor
+    gptr: Optional[Tensor]
+    status: Tensor
+    num_nodes: int
+    num_graphs: int
+    max_nodes: int = 0       # largest graph if known on the host, else 0
+
+    def check(self) -> None:
+        """Host-syncing validation of the device-side status word (debug / tests)."""
+        s = int(self.status.item())
+        if s & GRAPH_BAD_EDGE:
+            raise ValueError("dgcnn_b200: edge_index holds node ids outside [0, num_nodes)")
+        if s & GRAPH_BAD_BATCH:
+            raise ValueError("dgcnn_b200: batch must be non-decreasing with ids in [0, num_graphs)")
+
+
+def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num_graphs: int = 0,
+                transpose: bool = True, max_nodes: int = 0) -> Graph:
+    """K0 (model.py:28 + gcn_norm prologue + to_dense_batch offsets), once per batch."""
+    lib = _lib.load_library()
+    _require_cuda(edge_index, "edge_index", torch.int64)
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("dgcnn_b200: edge_index must be [2, E]")
+    edge_index = edge_index.contiguous()
+    dev = edge_index.device
+    n, e, b = int(num_nodes), int(edge_index.size(1)), int(num_graphs)
+    if batch is not None:
+        _require_cuda(batch, "batch", torch.int64)
+        batch = batch.contiguous()
+        if batch.numel() != n:
+            raise ValueError("dgcnn_b200: batch must have one entry per node")
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n + 1, **i32)
+    col = torch.empty(max(e, 1), **i32)
+    rowptr_t = torch.empty(n + 1, **i32) if transpose else None
+    col_t = torch.empty(max(e, 1), **i32) if transpose else None
+    dis = torch.empty(n, dtype=torch.float32, device=dev)
+    gptr = torch.empty(b + 1, **i32) if batch is not None else None
+    status = torch.zeros(1, **i32)
+    wbytes = lib.dgcnn_build_graph_workspace_bytes(n, e)
+    ws = _workspace(wbytes, dev)
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_build_graph(_ptr(edge_index), e, _ptr(batch), n, b,
+                                   _ptr(rowptr), _ptr(col), _ptr(rowptr_t), _ptr(col_t),
+                                   _ptr(dis), _ptr(gptr), _ptr(status),
+                                   _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "build_graph")
+    return Graph(rowptr, col, rowptr_t, col_t, dis, gptr, status, n, b, int(max_nodes))
+
+
+def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
+    lib = _lib.load_library()
+    _require_cuda(batch, "batch", torch.int64)
+    batch = batch.contiguous()
+    gptr = torch.empty(int(num_graphs) + 1, dtype=torch.int32, device=batch.device)
+    with torch.cuda.device(batch.device):
+        rc = lib.dgcnn_graph_ptr(_ptr(batch), batch.numel(), int(num_graphs), _ptr(gptr), None,
+                                 _stream())
+    _lib.check(rc, "graph_ptr")
+    return gptr
+
+
+def graph_conv_fwd(x: Tensor, rowptr: Tensor, col: Tensor, dis: Tensor, weight: Tensor,
+                   bias: Optional[Tensor], norm: int, act: int, out: Tensor) -> None:
+    """K1: ``out[:] = act(A_hat x W^T + b)`` in one launch; ``out`` may be a column
+    slice of the concatenated buffer (model.py:30-34)."""
+    lib = _lib.load_library()
+    _require_cuda(x, "x", torch.float32)
+    _require_cuda(out, "out", torch.float32)
+    _require_cuda(weight, "weight", torch.float32)
+    _require_cuda(rowptr, "rowptr", torch.int32)
+    _require_cuda(col, "col", torch.int32)
+    _require_cuda(dis, "dis", torch.float32)
+    n, cin = x.shape
+    cout = weight.size(0)
+    if weight.shape != (cout, cin) or out.shape != (n, cout) or rowptr.numel() != n + 1:
+        raise ValueError("dgcnn_b200: graph_conv_fwd shape mismatch")
+    weight = weight.contiguous()
+    if bias is not None:
+        _require_cuda(bias, "bias", torch.float32)
+        bias = bias.contiguous()
+    with torch.cuda.device(x.device):
+        rc = lib.dgcnn_graph_conv_fwd(_ptr(x), _rows(x, "x"), cin, _ptr(rowptr), _ptr(col),
+                                      _ptr(dis), _ptr(weight), _ptr(bias), _ptr(out),
+                                      _rows(out, "out"), cout, n, int(norm), int(act), _stream())
+    _lib.check(rc, "graph_conv_fwd")
+
+
+def graph_conv_bwd(dy: Tensor, y: Optional[Tensor], x: Tensor, rowptr_t: Tensor, col_t: Tensor,
+                   dis: Tensor, weight: Tensor, norm: int, act: int, dx: Optional[Tensor],
+                   accumulate: bool, need_db: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+    """K3: returns (dw, db); writes / accumulates dx in place when given."""
+    lib = _lib.load_library()
+    _require_cuda(dy, "dy", torch.float32)
+    _require_cuda(x, "x", torch.float32)
+    _require_cuda(weight, "weight", torch.float32)
+    _require_cuda(rowptr_t, "rowptr_t", torch.int32)
+    n, cin = x.shape
+    cout = weight.size(0)
+    if dy.shape != (n, cout) or weight.shape != (cout, cin):
+        raise ValueError("dgcnn_b200: graph_conv_bwd shape mismatch")
+    if act == ACT_TANH:
+        _require_cuda(y, "y", torch.float32)
+    if dx is not None:
+        _require_cuda(dx, "dx", torch.float32)
+        if dx.shape != (n, cin):
+            raise ValueError("dgcnn_b200: dx shape mismatch")
+    weight = weight.contiguous()
+    dw = torch.empty_like(weight)
+    db = torch.empty(cout, dtype=torch.float32, device=x.device) if need_db else None
+    ws = _workspace(lib.dgcnn_graph_conv_bwd_workspace_bytes(n, cin, cout), x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.dgcnn_graph_conv_bwd(
+            _ptr(dy), _rows(dy, "dy"), _ptr(y), _rows(y, "y") if y is not None else 0,
+            _ptr(x), _rows(x, "x"), cin, _ptr(rowptr_t), _ptr(col_t), _ptr(dis), _ptr(weight),
+            _ptr(dx), _rows(dx, "dx") if dx is not None else 0, int(bool(accumulate)),
+            _ptr(dw), _ptr(db), cout, n, int(norm), int(act), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "graph_conv_bwd")
+    return dw, db
+
+
+def sort_pool_fwd(x: Tensor, gptr: Tensor, k: int, max_nodes: int = 0) -> Tuple[Tensor, Tensor]:
+    """K2: (out [B, k*D] f32, perm [B, k] i32) -- model.py:35."""
+    lib = _lib.load_library()
+    _require_cuda(x, "x", torch.float32)
+    _require_cuda(gptr, "gptr", torch.int32)
+    n, d = x.shape
+    b = gptr.numel() - 1
+    out = torch.empty(b, int(k) * d, dtype=torch.float32, device=x.device)
+    perm = torch.empty(b, int(k), dtype=torch.int32, device=x.device)
+    ws = _workspace(lib.dgcnn_sort_pool_workspace_bytes(n, b), x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.dgcnn_sort_pool_fwd(_ptr(x), _rows(x, "x"), d, _ptr(gptr), n, b, int(k),
+                                     int(max_nodes), _ptr(out), _ptr(perm), _ptr(ws), ws.numel(),
+                                     _stream())
+    _lib.check(rc, "sort_pool_fwd")
+    return out, perm
+
+
+def sort_pool_bwd(dout: Tensor, perm: Tensor, num_nodes: int, out: Optional[Tensor] = None) -> Tensor:
+    """K4: dx [N, D] with dx[perm[g,r]] = dout[g,r], zero elsewhere."""
+    lib = _lib.load_library()
+    _require_cuda(dout, "dout", torch.float32)
+    _require_cuda(perm, "perm", torch.int32)
+    b, k = perm.shape
+    d = dout.numel() // max(b * k, 1) if b * k else (out.size(1) if out is not None else 1)
+    dout = dout.contiguous()
+    if out is None:
+        out = torch.empty(int(num_nodes), d, dtype=torch.float32, device=dout.device)
+    with torch.cuda.device(dout.device):
+        rc = lib.dgcnn_sort_pool_bwd(_ptr(dout), _ptr(perm), b, k, d, _ptr(out), _rows(out, "dx"),
+                                     int(num_nodes), _stream())
+    _lib.check(rc, "sort_pool_bwd")
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# torch.ops.dgcnn_b200.* registration.  CUDA key only.
+# ---------------------------------------------------------------------------------
+_torch_lib = None
+
+
+def register_torch_ops() -> None:
+    global _torch_lib
+    if _torch_lib is not None:
+        return
+    lib = torch.library.Library("dgcnn_b200", "DEF")
+    lib.define("build_graph(Tensor edge_index, Tensor batch, int num_graphs, bool transpose) -> "
+               "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
+    lib.define("graph_conv_fwd(Tensor x, Tensor rowptr, Tensor col, Tensor dis, Tensor weight, "
+               "Tensor? bias, int norm, int act, Tensor(a!) out) -> ()")
+    lib.define("graph_conv_bwd(Tensor dy, Tensor? y, Tensor x, Tensor rowptr_t, Tensor col_t, "
+               "Tensor dis, Tensor weight, int norm, int act, Tensor(a!)? dx, bool accumulate) -> "
+               "(Tensor, Tensor)")
+    lib.define("sort_pool_fwd(Tensor x, Tensor gptr, int k, int max_nodes) -> (Tensor, Tensor)")
+    lib.define("sort_pool_bwd(Tensor dout, Tensor perm, int num_nodes) -> Tensor")
+
+    def _build(edge_index, batch, num_graphs, transpose):
+        g = build_graph(edge_index, batch, batch.numel(), num_graphs, transpose)
+        empty = torch.empty(0, dtype=torch.int32, device=edge_index.device)
+        return (g.rowptr, g.col, g.rowptr_t if transpose else empty,
+                g.col_t if transpose else empty, g.dis, g.gptr, g.status)
+
+    def _conv_bwd(dy, y, x, rowptr_t, col_t, dis, weight, norm, act, dx, accumulate):
+        return graph_conv_bwd(dy, y, x, rowptr_t, col_t, dis, weight, norm, act, dx, accumulate)
+
+    lib.impl("build_graph", _build, "CUDA")
+    lib.impl("graph_conv_fwd", graph_conv_fwd, "CUDA")
+    lib.impl("graph_conv_bwd", _conv_bwd, "CUDA")
+    lib.impl("sort_pool_fwd", sort_pool_fwd, "CUDA")
+    lib.impl("sort_pool_bwd", lambda dout, perm, n: sort_pool_bwd(dout, perm, n), "CUDA")
+    _torch_lib = lib
+
+
+register_torch_ops()

@@ -1,0 +1,160 @@
+/*
+ * dgcnn_b200 -- C ABI of the B200-native DGCNN hot path.
+ *
+ * The reference (leftthomas/DGCNN) has no FFI layer: its hot path is the PyG
+ * Module API that model.py consumes.  Each entry point below replaces the
+ * arithmetic behind one of those call sites (cited per function); the Python
+ * mirror of the Module API (dgcnn_b200/nn.py) binds them with ctypes, exactly as
+ * INTEGRATION.md shows for a maintainer of the reference.
+ *
+ * Rules that hold for EVERY function:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the
+ *     current CUDA device unless the name says `host`;
+ *   - returns DGCNN_OK (0) or a negative dgcnn_status; never throws, never
+ *     allocates, never synchronises, launches only on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - the caller owns every buffer; scratch space is sized by the matching
+ *     *_workspace_bytes() query (pure host arithmetic, no CUDA call);
+ *   - safe under CUDA-graph stream capture; re-entrant and thread-safe;
+ *   - features are fp32 row-major with an explicit leading dimension (`ld*`,
+ *     in floats) so a layer can read/write its column slice of the
+ *     concatenated [N,97] buffer in place (model.py:34 needs no copy);
+ *   - indices are int64 at the boundary the reference defines
+ *     (edge_index, batch) and int32 inside (CSR, gptr, perm).
+ */
+#ifndef DGCNN_B200_H_
+#define DGCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGCNN_B200_ABI_VERSION 1
+
+typedef enum dgcnn_status {
+    DGCNN_OK = 0,
+    DGCNN_ERR_INVALID_ARGUMENT = -1, /* null pointer, negative size, bad enum            */
+    DGCNN_ERR_UNSUPPORTED = -2,      /* size outside what the kernels cover (see each fn) */
+    DGCNN_ERR_WORKSPACE = -3,        /* workspace smaller than *_workspace_bytes()        */
+    DGCNN_ERR_CUDA = -4              /* a launch failed; cudaGetLastError was consumed    */
+} dgcnn_status;
+
+/* GCNConv normalisation.  SYM is what the reference computes (PyG GCNConv
+ * default, model.py:13-16); RW is the AAAI-18 paper's D^-1 (A+I). */
+typedef enum dgcnn_norm { DGCNN_NORM_SYM = 0, DGCNN_NORM_RW = 1 } dgcnn_norm;
+
+/* Activation fused behind the convolution: NONE for a bare GCNConv call,
+ * TANH for model.py:30-33's torch.tanh(convN(...)). */
+typedef enum dgcnn_act { DGCNN_ACT_NONE = 0, DGCNN_ACT_TANH = 1 } dgcnn_act;
+
+/* Bits OR-ed by the kernels into the optional device word `status`
+ * (graph validation happens on the device, without a host sync). */
+#define DGCNN_GRAPH_BAD_EDGE 1    /* an edge_index entry outside [0, N)      */
+#define DGCNN_GRAPH_BAD_BATCH 2   /* batch not non-decreasing / outside [0,B) */
+
+int dgcnn_abi_version(void);
+const char* dgcnn_status_string(int status);
+
+/* ------------------------------------------------------------------------
+ * K0  graph build.  Replaces, once per batch instead of once per layer:
+ *   model.py:28       remove_self_loops(edge_index)
+ *   model.py:30-33 -> GCNConv.forward -> gcn_norm (PyG nn/conv/gcn_conv.py):
+ *                     add_remaining_self_loops, in-degree scatter, deg^-1/2
+ *   model.py:35    -> SortAggregation -> to_dense_batch's per-graph offsets
+ *
+ * edge_index [2,E] int64 (row 0 = source j, row 1 = target i), any order,
+ * self loops and duplicates allowed (loops dropped, duplicates kept: PyG counts
+ * multi-edges in both the degree and the sum).  batch [N] int64 non-decreasing.
+ *
+ * Outputs:
+ *   rowptr  [N+1], col  [E]  CSR by TARGET: col = sources of row i, ascending
+ *   rowptr_t[N+1], col_t[E]  CSR by SOURCE (the transpose, for backward);
+ *                            pass both NULL to skip
+ *   dis     [N]   (1 + in_degree)^-1/2     (the implicit self loop is the +1)
+ *   gptr    [B+1] node offset of every graph (empty graphs allowed)
+ *   status  optional device int32, OR-ed with DGCNN_GRAPH_* on bad input
+ * Only the first rowptr[N] entries of col are meaningful.
+ * Limits: N, E < 2^31.
+ * ------------------------------------------------------------------------ */
+size_t dgcnn_build_graph_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges,
+                      const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
+                      int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
+                      float* dis, int32_t* gptr, int32_t* status,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* gptr alone (SortAggregation called without a graph: model.py:35's `batch`). */
+int dgcnn_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
+                    int32_t* gptr, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K1  fused graph convolution, forward.  One launch replaces
+ *   model.py:30-33  torch.tanh(self.convN(x, edge_index))
+ * i.e. PyG GCNConv.forward (lin -> propagate: gather, scale, scatter-add ->
+ * + bias) followed by tanh, and -- through (y, ldy) -- model.py:34's cat.
+ *
+ *   y[i, :] = act( r_i * sum_{j in in(i) U {i}} c_j * x[j, :] @ W^T + b )
+ *   SYM: r = c = dis          RW: r = dis^2, c = 1
+ *
+ * weight [cout, cin] row-major (PyG's lin.weight), bias [cout] or NULL.
+ * Limits: 1 <= cin, cout <= 128.
+ * ------------------------------------------------------------------------ */
+int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin,
+                         const int32_t* rowptr, const int32_t* col, const float* dis,
+                         const float* weight, const float* bias,
+                         float* y, int64_t ldy, int32_t cout,
+                         int64_t num_nodes, int32_t norm, int32_t act, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K3  graph convolution, backward (autograd of model.py:30-33, train.py:40).
+ *   dpre = dy * (1 - y^2)   (act = TANH; y is the forward OUTPUT)
+ *   db   = sum_i dpre[i]           dh = A_hat^T dpre  (walks rowptr_t/col_t)
+ *   dw   = dh^T x                  dx = dh W
+ * dx may be NULL (first layer).  accumulate_dx != 0 adds into dx instead of
+ * overwriting it (lets a layer add its input gradient on top of the pooled
+ * gradient already sitting in that slice of the [N,97] gradient buffer).
+ * dw [cout,cin] and db [cout] (db may be NULL) are overwritten.
+ * ------------------------------------------------------------------------ */
+size_t dgcnn_graph_conv_bwd_workspace_bytes(int64_t num_nodes, int32_t cin, int32_t cout);
+int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy,
+                         const float* x, int64_t ldx, int32_t cin,
+                         const int32_t* rowptr_t, const int32_t* col_t, const float* dis,
+                         const float* weight,
+                         float* dx, int64_t lddx, int32_t accumulate_dx,
+                         float* dw, float* db, int32_t cout,
+                         int64_t num_nodes, int32_t norm, int32_t act,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K2  SortPooling, forward.  Replaces model.py:35 self.sort_pool(x, batch)
+ * (PyG SortAggregation.forward: to_dense_batch, sort on the last channel,
+ * gather, truncate / pad to k rows, fill -> 0) without the dense [B,Nmax,D]
+ * detour.
+ *
+ * Per graph g: order its rows by x[:, d-1] DESCENDING, ties by ascending node
+ * index (torch.sort(stable=True)), -0.0 == +0.0, NaN first; copy the first
+ * min(n_g, k) rows to out[g, r, :], zero the rest;
+ * perm[g, r] = global node index of that row, or -1 for a padded row.
+ * out [B, k*d] fp32, perm [B, k] int32.
+ * max_nodes_hint: the largest graph in the batch if the caller knows it
+ * (sizes the shared-memory sort buffer), <= 0 if unknown.
+ * ------------------------------------------------------------------------ */
+size_t dgcnn_sort_pool_workspace_bytes(int64_t num_nodes, int64_t num_graphs);
+int dgcnn_sort_pool_fwd(const float* x, int64_t ldx, int32_t d,
+                        const int32_t* gptr, int64_t num_nodes, int64_t num_graphs, int32_t k,
+                        int64_t max_nodes_hint, float* out, int32_t* perm,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* K4  SortPooling, backward: dx[perm[g,r], :] = dout[g, r, :], every other row
+ * of dx[0:N, 0:d] is zeroed (truncated nodes get no gradient from the pool). */
+int dgcnn_sort_pool_bwd(const float* dout, const int32_t* perm, int64_t num_graphs,
+                        int32_t k, int32_t d, float* dx, int64_t lddx, int64_t num_nodes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGCNN_B200_H_ */

@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Benchmark of the DGCNN hot path (BASELINE.json: graphs/sec DGCNN fwd+bwd on
+COLLAB-synth at 1/2/4/8 B200; GraphConv HBM GB/s as % of the measured peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one training step of the reference's loop (train.py:35-42) on one
+COLLAB-shaped synthetic batch of 512 graphs per GPU: graph build (K0), 4x fused
+GraphConv + SortPool forward, dense tail, NLL, backward through everything, the
+single gradient all-reduce when N > 1, Adam.  Prints ONE JSON line on rank 0.
+
+`value`      graphs/s with the batch (x, edge_index, batch) already resident in HBM
+`e2e`        the same step through the public API from pinned HOST buffers, the H2D
+             copy and the D2H loss read inside the timed region
+`roofline`   the dominant kernel, timed alone with CUDA events, against MEASURED_PEAKS
+`cpu_baseline` / `--impl reference`   the CPU oracle restatement of the reference's
+             path (PyG itself is not installable here), timed on this host's cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.nn.functional as F
+
+METRIC = "graphs_per_sec_fwd_bwd"
+UNIT = "graphs/s"
+WORKLOAD = "collab"          # BASELINE.json configs[3]: the config the metric is quoted on
+RING = 4                     # distinct pre-built batches cycled through the timed steps
+L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------
+# clocks: sampled on a thread DURING the timed region (pynvml; nvidia-smi as a fallback)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                getter = getattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    self.nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = getter(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# algorithmic bytes (fp32 features, int32 CSR)
+# --------------------------------------------------------------------------------------
+def layer_bytes(n, e, cin, cout):
+    return 4 * (n + 1) + 4 * e + 4 * n + 4 * n * cin + 4 * cin * cout + 4 * cout + 4 * n * cout
+
+
+def sortpool_bytes(n, b, k, d=97):
+    return 4 * n * d + 4 * (b + 1) + 4 * b * k * d + 4 * b * k
+
+
+def forward_bytes(n, e, b, f, k):
+    dims = [(f, 32), (32, 32), (32, 32), (32, 1)]
+    return sum(layer_bytes(n, e, ci, co) for ci, co in dims) + sortpool_bytes(n, b, k)
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference's own path, all host threads
+# --------------------------------------------------------------------------------------
+def cpu_reference_step_fn(cfg, batch):
+    from oracle import dgcnn_oracle as orc      # the one place bench.py touches oracle/
+    torch.manual_seed(324)
+    model = orc.OracleModel(cfg.num_features, cfg.num_classes, cfg.k).train()
+    opt = torch.optim.Adam(model.parameters())
+
+    def step():
+        logp = model(batch)
+        loss = F.nll_loss(logp, batch.y)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return float(loss.detach())
+    return step
+
+
+def time_cpu(cfg, batch, seconds, warmup=1):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_reference_step_fn(cfg, batch)
+    for _ in range(warmup):
+        step()
+    t0, n = time.perf_counter(), 0
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or n >= 200:
+            break
+    return batch.num_graphs * n / el, n, el
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dgcnn_b200.synth import CONFIGS, make_batch
+    cfg = CONFIGS[args.workload]
+    batch = make_batch(args.workload, seed=324)
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_reference_step_fn(cfg, batch)
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    budget = 150.0                                  # keep the whole arm within a few minutes
+    if first * (args.steps + args.warmup) > budget:
+        keep = max(16, int(batch.num_graphs * budget / (first * (args.steps + args.warmup))))
+        batch = make_batch(args.workload, seed=324, num_graphs=keep)   # bounded sample
+        step = cpu_reference_step_fn(cfg, batch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = batch.num_graphs * args.steps / el
+    sample = (f"{args.steps} train steps (fwd+NLL+bwd+Adam) on one {args.workload}-synth batch of "
+              f"{batch.num_graphs} graphs, N={batch.num_nodes}, E={batch.num_edges}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}-synth bs{batch.num_graphs} k{cfg.k}",
+                   "nodes": batch.num_nodes, "edges": batch.num_edges,
+                   "note": "CPU oracle restatement of model.py:26-45 + train.py:35-42 "
+                           "(torch_geometric is not installable here); rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    import dgcnn_b200 as dg
+    from dgcnn_b200 import ops
+    from dgcnn_b200.synth import CONFIGS, make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = CONFIGS[args.workload]
+    # weak scaling: every rank owns RING distinct batches of cfg.batch_size graphs
+    host_batches = [make_batch(args.workload, seed=324 + 1000 * rank + i).pin_memory()
+                    for i in range(RING)]
+    for hb in host_batches:
+        hb.max_nodes = int((hb.ptr[1:] - hb.ptr[:-1]).max())
+    dev_batches = []
+    for hb in host_batches:
+        db = hb.to(dev)
+        db.max_nodes = hb.max_nodes
+        dev_batches.append(db)
+    graphs_per_step = cfg.batch_size
+    global_batch = graphs_per_step * world
+
+    torch.manual_seed(324)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(dev).train()
+    bucket = dg.GradBucket(model.parameters(), extra=2)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, foreach=True)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def train_step(data):
+        bucket.zero_()
+        logp = model(data)
+        loss = F.nll_loss(logp, data.y, reduction="sum")
+        loss.backward()
+        bucket.extra[0].copy_(loss.detach())
+        bucket.all_reduce(global_batch)
+        opt.step()
+        return loss
+
+    # ---- launch census on one eager step ------------------------------------------
+    before = ops.launches_total()
+    train_step(dev_batches[0])
+    torch.cuda.synchronize()
+    launches_per_step = ops.launches_total() - before
+
+    # ---- optional CUDA-graph capture: one graph per ring slot ---------------------
+    use_graph = not args.no_graph
+    graphs, static_loss = [], []
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for db in dev_batches:
+                    train_step(db)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            pool = None
+            for db in dev_batches:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    static_loss.append(train_step(db))
+                pool = g.pool()
+                graphs.append(g)
+        except Exception as exc:                       # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed ({exc!r}); timing eagerly", file=sys.stderr)
+            use_graph, graphs = False, []
+            torch.cuda.synchronize()
+
+    def run_slot(i):
+        if use_graph:
+            graphs[i % RING].replay()
+        else:
+            train_step(dev_batches[i % RING])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, L2 flushed before each, CUDA events ----
+    for i in range(max(args.warmup, 3)):
+        flush.zero_()
+        run_slot(i)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()                              # evict the batch / weights from L2
+            starts[i].record()
+            run_slot(i)
+            stops[i].record()
+        barrier()
+        wall = time.perf_counter() - wall0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = global_batch * args.steps / (total_ms / 1e3)
+
+    # ---- end to end from pinned host buffers (public API, eager) ------------------
+    def e2e_step(hb):
+        data = hb.to(dev, non_blocking=True)
+        data.max_nodes = hb.max_nodes
+        loss = train_step(data)
+        return float(loss.item())                      # D2H read of the step's result
+
+    e2e_steps = max(5, min(args.steps, 20))
+    for i in range(3):
+        e2e_step(host_batches[i % RING])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(host_batches[i % RING])
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = global_batch * e2e_steps / float(e2e_s.item())
+    h2d_bytes = host_batches[0].nbytes()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: forward hot path and its dominant kernel, each timed alone ----
+    peak, peak_kind = measured_peaks()
+    db0 = dev_batches[0]
+    n, e = db0.num_nodes, db0.num_edges
+    model.eval()
+    with torch.no_grad():
+        g0 = model.build_graph(db0)
+        convs = (model.conv1, model.conv2, model.conv3, model.conv4)
+
+        def timed(fn, reps=20):
+            times = []
+            for _ in range(3):
+                fn()
+            for _ in range(reps):
+                flush.zero_()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b_.record()
+                torch.cuda.synchronize()
+                times.append(a.elapsed_time(b_))
+            return statistics.mean(times) * 1e-3
+
+        t_fwd = timed(lambda: model.hot_path(db0.x, g0))
+        xcat = torch.empty(n, 97, device=dev)
+        ops.graph_conv_fwd(db0.x, g0.rowptr, g0.col, g0.dis, convs[0].lin.weight, convs[0].bias,
+                           0, 1, xcat[:, 0:32])
+        t_l2 = timed(lambda: ops.graph_conv_fwd(xcat[:, 0:32], g0.rowptr, g0.col, g0.dis,
+                                                convs[1].lin.weight, convs[1].bias, 0, 1,
+                                                xcat[:, 32:64]))
+        t_k0 = timed(lambda: model.build_graph(db0))
+    a_fwd = forward_bytes(n, e, cfg.batch_size, cfg.num_features, cfg.k)
+    a_l2 = layer_bytes(n, e, 32, 32)
+    roofline = {"bound": "hbm", "kernel": "gc_aggregate_chan<1> (GraphConv 32->32 forward, layer 2)",
+                "achieved": a_l2 / t_l2 / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": a_l2 / t_l2 / 1e9 / peak, "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes": a_l2, "launch_us": t_l2 * 1e6}
+    hot_fwd = {"what": "GraphConv x4 + SortPool forward (A_fwd, SURVEY 8d)", "algorithmic_bytes": a_fwd,
+               "us": t_fwd * 1e6, "achieved_GBps": a_fwd / t_fwd / 1e9,
+               "frac_of_peak": a_fwd / t_fwd / 1e9 / peak, "graph_build_us": t_k0 * 1e6}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cb = make_batch(args.workload, seed=324)
+        v, nsteps, el = time_cpu(cfg, cb, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{nsteps} train steps in {el:.1f} s on one {args.workload}-synth batch "
+                         f"({cb.num_graphs} graphs, N={cb.num_nodes}, E={cb.num_edges}), "
+                         "CPU oracle restatement, all host threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-synth bs{cfg.batch_size}/GPU k{cfg.k} "
+                               f"F{cfg.num_features} (BASELINE.json configs[3])",
+                   "nodes_per_batch": n, "edges_per_batch": e, "global_batch": global_batch,
+                   "step": "K0 graph build + GraphConv x4 + SortPool + dense tail + NLL + backward "
+                           "+ grad all-reduce (N>1) + Adam",
+                   "l2": f"flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every timed step; "
+                         f"ring of {RING} distinct batches",
+                   "cuda_graph": use_graph, "parallelism": f"dp{world} (graph-sharded)",
+                   "wall_s_incl_flush": wall},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                "note": "pinned host batch -> H2D -> Model(data) -> NLL -> backward -> Adam -> loss.item()"},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": roofline,
+        "hot_path_fwd": hot_fwd,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

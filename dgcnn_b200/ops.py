@@ -20,6 +20,15 @@ NORM_SYM, NORM_RW = 0, 1
 ACT_NONE, ACT_TANH = 0, 1
 GRAPH_BAD_EDGE, GRAPH_BAD_BATCH = 1, 2
 
+# kernels launched by this process through the C ABI (memsets not counted); bench.py
+# reads it to report `gpu_launches`.  Keyed by entry point.
+LAUNCHES = {"build_graph": 0, "graph_ptr": 0, "graph_conv_fwd": 0, "graph_conv_bwd": 0,
+            "sort_pool_fwd": 0, "sort_pool_bwd": 0}
+
+
+def launches_total() -> int:
+    return sum(LAUNCHES.values())
+
 
 def _require_cuda(t: Tensor, name: str, dtype: torch.dtype) -> None:
     if not isinstance(t, Tensor):
@@ -109,6 +118,7 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
                                    _ptr(dis), _ptr(gptr), _ptr(status),
                                    _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "build_graph")
+    LAUNCHES["build_graph"] += 6 if e > 0 else 4
     return Graph(rowptr, col, rowptr_t, col_t, dis, gptr, status, n, b, int(max_nodes))
 
 
@@ -121,6 +131,7 @@ def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
         rc = lib.dgcnn_graph_ptr(_ptr(batch), batch.numel(), int(num_graphs), _ptr(gptr), None,
                                  _stream())
     _lib.check(rc, "graph_ptr")
+    LAUNCHES["graph_ptr"] += 1
     return gptr
 
 
@@ -148,6 +159,7 @@ def graph_conv_fwd(x: Tensor, rowptr: Tensor, col: Tensor, dis: Tensor, weight: 
                                       _ptr(dis), _ptr(weight), _ptr(bias), _ptr(out),
                                       _rows(out, "out"), cout, n, int(norm), int(act), _stream())
     _lib.check(rc, "graph_conv_fwd")
+    LAUNCHES["graph_conv_fwd"] += 1 if n > 0 else 0
 
 
 def graph_conv_bwd(dy: Tensor, y: Optional[Tensor], x: Tensor, rowptr_t: Tensor, col_t: Tensor,
@@ -180,6 +192,7 @@ def graph_conv_bwd(dy: Tensor, y: Optional[Tensor], x: Tensor, rowptr_t: Tensor,
             _ptr(dx), _rows(dx, "dx") if dx is not None else 0, int(bool(accumulate)),
             _ptr(dw), _ptr(db), cout, n, int(norm), int(act), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "graph_conv_bwd")
+    LAUNCHES["graph_conv_bwd"] += 3 if n > 0 else 0
     return dw, db
 
 
@@ -198,6 +211,7 @@ def sort_pool_fwd(x: Tensor, gptr: Tensor, k: int, max_nodes: int = 0) -> Tuple[
                                      int(max_nodes), _ptr(out), _ptr(perm), _ptr(ws), ws.numel(),
                                      _stream())
     _lib.check(rc, "sort_pool_fwd")
+    LAUNCHES["sort_pool_fwd"] += 1 if b > 0 else 0
     return out, perm
 
 
@@ -215,6 +229,7 @@ def sort_pool_bwd(dout: Tensor, perm: Tensor, num_nodes: int, out: Optional[Tens
         rc = lib.dgcnn_sort_pool_bwd(_ptr(dout), _ptr(perm), b, k, d, _ptr(out), _rows(out, "dx"),
                                      int(num_nodes), _stream())
     _lib.check(rc, "sort_pool_bwd")
+    LAUNCHES["sort_pool_bwd"] += (1 if b > 0 else 0) + (1 if out.stride(0) != d and num_nodes > 0 else 0)
     return out
 
 

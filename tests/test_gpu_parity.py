@@ -1,0 +1,501 @@
+"""GPU parity tests: every CUDA entry point of include/dgcnn_b200.h, called through
+the ctypes binding (dgcnn_b200.ops), against the CPU oracle on the same seeded
+inputs, the committed golden vectors, and size-independent properties.
+
+Tolerances (north_star): fp32 features within 1e-5 absolute of the oracle (outputs
+are tanh-bounded); permutation indices and CSR arrays bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import dgcnn_b200 as dg
+from dgcnn_b200 import ops
+from dgcnn_b200.synth import CONFIGS, collate, make_batch, make_graphs
+from oracle import dgcnn_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+ATOL = 1e-5
+DEV = "cuda:0"
+# the dense tail is stock torch: keep cuDNN/cuBLAS in true fp32 so that the end-to-end
+# comparison against the float64 oracle measures OUR kernels, not TF32 rounding
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+# ------------------------------------------------------------------ helpers
+def ref_csr(edge_index: np.ndarray, n: int):
+    src, dst = edge_index
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    o = np.lexsort((src, dst))
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=n))]).astype(np.int32)
+    ot = np.lexsort((dst, src))
+    rowptr_t = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=n))]).astype(np.int32)
+    indeg = np.bincount(dst, minlength=n)
+    dis = (1.0 / np.sqrt((indeg + 1).astype(np.float32))).astype(np.float32)
+    return rowptr, src[o].astype(np.int32), rowptr_t, dst[ot].astype(np.int32), dis
+
+
+def random_multigraph(rng, sizes, avg_deg=4.0, loops=True):
+    """Block-diagonal directed multigraph: duplicates, self loops, isolated nodes,
+    edges in random order."""
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    srcs, dsts = [], []
+    for g, n in enumerate(sizes):
+        if n == 0:
+            continue
+        m = int(avg_deg * n)
+        s = rng.randint(0, n, size=m) + ptr[g]
+        d = rng.randint(0, n, size=m) + ptr[g]
+        if not loops:
+            ok = s != d
+            s, d = s[ok], d[ok]
+        srcs.append(s)
+        dsts.append(d)
+    src = np.concatenate(srcs) if srcs else np.zeros(0, np.int64)
+    dst = np.concatenate(dsts) if dsts else np.zeros(0, np.int64)
+    p = rng.permutation(src.size)
+    ei = np.stack([src[p], dst[p]]).astype(np.int64)
+    batch = np.repeat(np.arange(len(sizes)), sizes).astype(np.int64)
+    return ei, batch, int(ptr[-1])
+
+
+def gpu_graph(ei, batch, n, b, **kw):
+    return ops.build_graph(torch.from_numpy(ei).to(DEV), torch.from_numpy(batch).to(DEV), n, b, **kw)
+
+
+def assert_perm_matches(perm_gpu, perm_ref, keys64, gptr, k, tol=1e-5):
+    """perm must equal the oracle's wherever the oracle's neighbouring sorted keys are
+    further apart than the fp32 tolerance (near-ties may legitimately swap)."""
+    perm_gpu, perm_ref = np.asarray(perm_gpu), np.asarray(perm_ref)
+    assert ((perm_gpu < 0) == (perm_ref < 0)).all()
+    bad = 0
+    for g in range(perm_ref.shape[0]):
+        n = gptr[g + 1] - gptr[g]
+        if n == 0:
+            continue
+        ks = np.sort(keys64[gptr[g]:gptr[g + 1]])[::-1]
+        for r in range(min(n, k)):
+            if perm_gpu[g, r] == perm_ref[g, r]:
+                continue
+            near = (r > 0 and abs(ks[r] - ks[r - 1]) < tol) or (r + 1 < n and abs(ks[r] - ks[r + 1]) < tol)
+            assert near, f"graph {g} rank {r}: {perm_gpu[g, r]} vs {perm_ref[g, r]} without a near-tie"
+            bad += 1
+    return bad
+
+
+# ------------------------------------------------------------------ K0
+@pytest.mark.parametrize("sizes", [[5, 0, 7, 1, 0], [2048], [2047, 1], [4096, 100], [1], [0, 0, 3],
+                                   list(range(0, 60)), [30000, 20000, 15000]])
+def test_build_graph_matches_reference_csr(sizes):
+    rng = np.random.RandomState(len(sizes) + sum(sizes))
+    ei, batch, n = random_multigraph(rng, sizes, avg_deg=5.0)
+    b = len(sizes)
+    g = gpu_graph(ei, batch, n, b)
+    g.check()
+    rowptr, col, rowptr_t, col_t, dis = ref_csr(ei, n)
+    e = int(rowptr[-1])
+    np.testing.assert_array_equal(g.rowptr.cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(g.col.cpu().numpy()[:e], col)
+    np.testing.assert_array_equal(g.rowptr_t.cpu().numpy(), rowptr_t)
+    np.testing.assert_array_equal(g.col_t.cpu().numpy()[:e], col_t)
+    np.testing.assert_allclose(g.dis.cpu().numpy(), dis, rtol=2e-7, atol=0)
+    np.testing.assert_array_equal(g.gptr.cpu().numpy(), np.concatenate([[0], np.cumsum(sizes)]))
+
+
+def test_build_graph_heavy_rows_and_no_edges():
+    # star: one row of degree 5000 (rank sort beyond one warp chunk), plus an edgeless graph
+    n = 5001
+    src = np.arange(1, n, dtype=np.int64)
+    ei = np.stack([np.concatenate([src, np.zeros(n - 1, np.int64)]),
+                   np.concatenate([np.zeros(n - 1, np.int64), src])])
+    ei = ei[:, np.random.RandomState(0).permutation(ei.shape[1])]
+    batch = np.zeros(n, np.int64)
+    g = gpu_graph(ei, batch, n, 1)
+    rowptr, col, rowptr_t, col_t, dis = ref_csr(ei, n)
+    np.testing.assert_array_equal(g.rowptr.cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(g.col.cpu().numpy()[:rowptr[-1]], col)
+    np.testing.assert_array_equal(g.col_t.cpu().numpy()[:rowptr[-1]], col_t)
+    g2 = gpu_graph(np.zeros((2, 0), np.int64), np.zeros(4, np.int64), 4, 1, transpose=False)
+    assert g2.rowptr.cpu().tolist() == [0] * 5 and g2.dis.cpu().tolist() == [1.0] * 4
+    assert g2.rowptr_t is None
+
+
+def test_build_graph_flags_bad_input():
+    ei = torch.tensor([[0, 9], [1, 0]], device=DEV)
+    g = ops.build_graph(ei, torch.tensor([0, 0, 0], device=DEV), 3, 1)
+    with pytest.raises(ValueError, match="edge_index"):
+        g.check()
+    g = ops.build_graph(torch.tensor([[0], [1]], device=DEV), torch.tensor([1, 0, 0], device=DEV), 3, 2)
+    with pytest.raises(ValueError, match="batch"):
+        g.check()
+
+
+def test_synthetic_batches_build():
+    for name in ("mutag", "proteins", "dd", "collab"):
+        b = make_batch(name)
+        g = ops.build_graph(b.edge_index.to(DEV), b.batch.to(DEV), b.num_nodes, b.num_graphs)
+        g.check()
+        rowptr, col, rowptr_t, col_t, dis = ref_csr(b.edge_index.numpy(), b.num_nodes)
+        np.testing.assert_array_equal(g.rowptr.cpu().numpy(), rowptr)
+        np.testing.assert_array_equal(g.col.cpu().numpy()[:rowptr[-1]], col)
+        # symmetric inputs: the transpose equals the matrix
+        np.testing.assert_array_equal(g.rowptr_t.cpu().numpy(), rowptr)
+        np.testing.assert_array_equal(g.col_t.cpu().numpy()[:rowptr[-1]], col)
+        np.testing.assert_array_equal(g.gptr.cpu().numpy(), b.ptr.numpy().astype(np.int32))
+
+
+# ------------------------------------------------------------------ K1 / K3
+DIMS = [(1, 32), (2, 5), (5, 32), (8, 32), (3, 7), (19, 32), (32, 32), (32, 1), (38, 32), (90, 32),
+        (64, 64), (128, 128), (100, 3), (33, 40)]
+
+
+def conv_case(seed, cin, cout, sizes=(17, 1, 0, 40, 9), avg_deg=3.0):
+    rng = np.random.RandomState(seed)
+    ei, batch, n = random_multigraph(rng, list(sizes), avg_deg)
+    x = rng.randn(n, cin).astype(np.float32)
+    w = (rng.randn(cout, cin) / np.sqrt(cin)).astype(np.float32)
+    b = (rng.randn(cout) * 0.1).astype(np.float32)
+    return ei, batch, n, x, w, b
+
+
+@pytest.mark.parametrize("cin,cout", DIMS)
+@pytest.mark.parametrize("norm", [0, 1])
+@pytest.mark.parametrize("act", [0, 1])
+def test_graph_conv_forward(cin, cout, norm, act):
+    ei, batch, n, x, w, b = conv_case(cin * 131 + cout, cin, cout)
+    g = gpu_graph(ei, batch, n, 5)
+    # x and out live inside wider buffers (column slices), like the [N,97] concat buffer
+    xbuf = torch.zeros(n, cin + 3, device=DEV)
+    xbuf[:, 2:2 + cin] = torch.from_numpy(x).to(DEV)
+    obuf = torch.full((n, cout + 5), 7.0, device=DEV)
+    ops.graph_conv_fwd(xbuf[:, 2:2 + cin], g.rowptr, g.col, g.dis, torch.from_numpy(w).to(DEV),
+                       torch.from_numpy(b).to(DEV), norm, act, obuf[:, 1:1 + cout])
+    ref = orc.gcn_conv(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(w),
+                       torch.from_numpy(b), norm)
+    ref64 = orc.gcn_conv(torch.from_numpy(x).double(), torch.from_numpy(ei),
+                         torch.from_numpy(w).double(), torch.from_numpy(b).double(), norm)
+    if act:
+        ref, ref64 = torch.tanh(ref), torch.tanh(ref64)
+    got = obuf[:, 1:1 + cout].cpu()
+    scale = max(1.0, float(ref64.abs().max()))
+    assert (got - ref).abs().max().item() <= ATOL * scale
+    assert (got.double() - ref64).abs().max().item() <= ATOL * scale
+    # nothing outside the slice was touched
+    assert (obuf[:, 0] == 7.0).all() and (obuf[:, 1 + cout:] == 7.0).all()
+
+
+def test_graph_conv_forward_without_bias_and_via_torch_ops():
+    ei, batch, n, x, w, b = conv_case(5, 32, 32)
+    g = gpu_graph(ei, batch, n, 5)
+    out = torch.empty(n, 32, device=DEV)
+    torch.ops.dgcnn_b200.graph_conv_fwd(torch.from_numpy(x).to(DEV), g.rowptr, g.col, g.dis,
+                                        torch.from_numpy(w).to(DEV), None, 0, 0, out)
+    ref = orc.gcn_conv(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(w), None)
+    assert (out.cpu() - ref).abs().max().item() <= ATOL
+
+
+@pytest.mark.parametrize("cin,cout", DIMS)
+@pytest.mark.parametrize("norm", [0, 1])
+def test_graph_conv_backward(cin, cout, norm):
+    ei, batch, n, x, w, b = conv_case(cin * 17 + cout + 1, cin, cout)
+    g = gpu_graph(ei, batch, n, 5)
+    rng = np.random.RandomState(1)
+    dy = rng.randn(n, cout).astype(np.float32)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    bt = torch.from_numpy(b).double().requires_grad_(True)
+    y64 = torch.tanh(orc.gcn_conv(xt, torch.from_numpy(ei), wt, bt, norm))
+    y64.backward(torch.from_numpy(dy).double())
+
+    xd, wd = torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV)
+    yd = torch.empty(n, cout, device=DEV)
+    ops.graph_conv_fwd(xd, g.rowptr, g.col, g.dis, wd, torch.from_numpy(b).to(DEV), norm, 1, yd)
+    dx0 = torch.from_numpy(rng.randn(n, cin).astype(np.float32)).to(DEV)
+    dx = dx0.clone()
+    dw, db = ops.graph_conv_bwd(torch.from_numpy(dy).to(DEV), yd, xd, g.rowptr_t, g.col_t, g.dis, wd,
+                                norm, 1, dx, True)
+    for got, ref in ((dx - dx0, xt.grad), (dw, wt.grad), (db, bt.grad)):
+        scale = max(1.0, float(ref.abs().max()))
+        assert (got.cpu().double() - ref).abs().max().item() <= 2e-5 * scale
+    # overwrite mode, no db, no dx
+    dx2 = torch.full((n, cin), 3.0, device=DEV)
+    dw2, none = ops.graph_conv_bwd(torch.from_numpy(dy).to(DEV), yd, xd, g.rowptr_t, g.col_t, g.dis, wd,
+                                   norm, 1, dx2, False, need_db=False)
+    assert none is None
+    assert (dx2.cpu().double() - xt.grad).abs().max().item() <= 2e-5 * max(1.0, float(xt.grad.abs().max()))
+    dw3, _ = ops.graph_conv_bwd(torch.from_numpy(dy).to(DEV), yd, xd, g.rowptr_t, g.col_t, g.dis, wd,
+                                norm, 1, None, False)
+    assert (dw3 - dw2).abs().max().item() <= 1e-4 * max(1.0, float(dw2.abs().max()))
+
+
+def test_gcnconv_module_autograd_matches_oracle():
+    ei, batch, n, x, w, b = conv_case(77, 19, 32, sizes=(25, 30))
+    torch.manual_seed(0)
+    conv = dg.GCNConv(19, 32).to(DEV)
+    assert set(conv.state_dict()) == {"lin.weight", "bias"}
+    with torch.no_grad():
+        conv.bias.uniform_(-0.1, 0.1)
+    xd = torch.from_numpy(x).to(DEV).requires_grad_(True)
+    out = conv(xd, torch.from_numpy(ei).to(DEV))
+    out.square().sum().backward()
+    xr = torch.from_numpy(x).requires_grad_(True)
+    wr = conv.lin.weight.detach().cpu().requires_grad_(True)
+    br = conv.bias.detach().cpu().requires_grad_(True)
+    ref = orc.gcn_conv(xr, torch.from_numpy(ei), wr, br)
+    ref.square().sum().backward()
+    assert (out.detach().cpu() - ref.detach()).abs().max().item() <= ATOL * max(1, ref.abs().max().item())
+    for got, want in ((xd.grad, xr.grad), (conv.lin.weight.grad, wr.grad), (conv.bias.grad, br.grad)):
+        assert (got.cpu() - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+
+
+# ------------------------------------------------------------------ K2 / K4
+def test_sort_pool_golden_cases_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "sortpool_cases.npz"))
+    x = torch.from_numpy(z["x"]).to(DEV)
+    gptr = ops.graph_ptr(torch.from_numpy(z["batch"]).to(DEV), int(z["num_graphs"]))
+    out, perm = ops.sort_pool_fwd(x, gptr, int(z["k"]))
+    np.testing.assert_array_equal(perm.cpu().numpy(), z["perm"])
+    np.testing.assert_array_equal(out.cpu().numpy(), z["out"])
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("k", [1, 7, 30, 200])
+@pytest.mark.parametrize("hint", [0, 16, 5000])
+def test_sort_pool_random_bit_exact(seed, k, hint):
+    """ragged sizes with empty graphs and many exact ties; hint=16 forces graphs larger
+    than the shared buffer through the global-memory sort path."""
+    rng = np.random.RandomState(seed)
+    sizes = list(rng.randint(0, 90, size=12)) + [1, 0, 300, 1025]
+    n = int(np.sum(sizes))
+    d = 97
+    xbuf = rng.randn(n, d + 3).astype(np.float32)
+    xbuf[:, d - 1] = np.round(xbuf[:, d - 1], 1)
+    xbuf[::17, d - 1] = -0.0
+    batch = np.repeat(np.arange(len(sizes)), sizes).astype(np.int64)
+    xg = torch.from_numpy(xbuf).to(DEV)[:, :d]
+    gptr = ops.graph_ptr(torch.from_numpy(batch).to(DEV), len(sizes))
+    out, perm = ops.sort_pool_fwd(xg, gptr, k, hint)
+    ro, rp = orc.sort_aggregation(torch.from_numpy(xbuf[:, :d].copy()), torch.from_numpy(batch), k,
+                                  len(sizes), return_perm=True)
+    np.testing.assert_array_equal(perm.cpu().numpy(), rp.numpy())
+    np.testing.assert_array_equal(out.cpu().numpy(), ro.numpy())
+
+
+def test_sort_pool_giant_graph_and_nan():
+    rng = np.random.RandomState(3)
+    sizes = [20000, 5, 5748]
+    n, d, k = sum(sizes), 4, 291
+    x = rng.randn(n, d).astype(np.float32)
+    x[123, -1] = np.nan
+    x[20003, -1] = np.inf
+    batch = np.repeat(np.arange(3), sizes).astype(np.int64)
+    gptr = ops.graph_ptr(torch.from_numpy(batch).to(DEV), 3)
+    for hint in (0, 20000, 5748):
+        out, perm = ops.sort_pool_fwd(torch.from_numpy(x).to(DEV), gptr, k, hint)
+        ro, rp = orc.sort_aggregation(torch.from_numpy(x), torch.from_numpy(batch), k, 3, return_perm=True)
+        np.testing.assert_array_equal(perm.cpu().numpy(), rp.numpy())
+        assert perm[0, 0].item() == 123
+        np.testing.assert_array_equal(out.cpu().numpy(), ro.numpy())
+
+
+def test_sort_pool_backward_and_module():
+    rng = np.random.RandomState(9)
+    sizes = [3, 0, 50, 12]
+    n, d, k = sum(sizes), 97, 10
+    x = rng.randn(n, d).astype(np.float32)
+    batch = np.repeat(np.arange(4), sizes).astype(np.int64)
+    pool = dg.SortAggregation(k)
+    assert dg.SortPool is dg.SortAggregation and pool.k == k
+    xd = torch.from_numpy(x).to(DEV).requires_grad_(True)
+    out = pool(xd, torch.from_numpy(batch).to(DEV))          # B inferred from index.max(), like PyG
+    cot = torch.from_numpy(rng.randn(4, k * d).astype(np.float32))
+    (out * cot.to(DEV)).sum().backward()
+    xr = torch.from_numpy(x).requires_grad_(True)
+    (orc.sort_aggregation(xr, torch.from_numpy(batch), k) * cot).sum().backward()
+    np.testing.assert_array_equal(xd.grad.cpu().numpy(), xr.grad.numpy())
+    # strided destination (ld > d) through the raw op
+    perm = pool(xd, torch.from_numpy(batch).to(DEV), return_perm=True)[1]
+    buf = torch.full((n, d + 4), 5.0, device=DEV)
+    ops.sort_pool_bwd(cot.to(DEV), perm, n, out=buf[:, :d])
+    np.testing.assert_array_equal(buf[:, :d].cpu().numpy(), xr.grad.numpy())
+    assert (buf[:, d:] == 5.0).all()
+
+
+# ------------------------------------------------------------------ stack + model
+def run_stack(z, norm, k, b):
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    ws = [dev(z[f"w{i}"]).requires_grad_(True) for i in range(1, 5)]
+    bs = [dev(z[f"b{i}"]).requires_grad_(True) for i in range(1, 5)]
+    x = dev(z["x"]).requires_grad_(True)
+    g = ops.build_graph(dev(z["edge_index"]), dev(z["batch"]), x.size(0), b)
+    pooled, xcat, perm = dg.graph_conv_stack(x, g, ws, bs, k, norm)
+    return x, ws, bs, g, pooled, xcat, perm
+
+
+@pytest.mark.parametrize("name", ["hand_sym", "hand_rw", "mutag6_sym", "proteins5_sym"])
+def test_stack_against_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    norm, k, b = int(z["norm"]), int(z["k"]), int(z["num_graphs"])
+    x, ws, bs, g, pooled, xcat, perm = run_stack(z, norm, k, b)
+    assert np.abs(xcat.detach().cpu().numpy() - z["xcat_f32"]).max() <= ATOL
+    assert np.abs(xcat.detach().cpu().numpy() - z["xcat_f64"]).max() <= ATOL
+    gptr = g.gptr.cpu().numpy()
+    swaps = assert_perm_matches(perm.cpu().numpy(), z["perm_f64"], z["xcat_f64"][:, -1], gptr, k)
+    if swaps == 0:
+        assert np.abs(pooled.detach().cpu().numpy() - z["pooled_f64"]).max() <= ATOL
+        (pooled * torch.from_numpy(z["cotangent"]).to(DEV)).sum().backward()
+        pairs = [(x.grad, z["dx_f64"])]
+        pairs += [(ws[i].grad, z[f"dw{i+1}_f64"]) for i in range(4)]
+        pairs += [(bs[i].grad, z[f"db{i+1}_f64"]) for i in range(4)]
+        for got, want in pairs:
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.abs(got.cpu().numpy() - want).max() <= 3e-5 * scale
+
+
+def load_into(model, oracle_model):
+    model.load_state_dict(oracle_model.state_dict())     # identical key names
+    return model
+
+
+@pytest.mark.parametrize("name,count", [("mutag", 50), ("proteins", 128), ("dd", 64), ("collab", 96)])
+def test_model_forward_backward_matches_oracle(name, count):
+    cfg = CONFIGS[name]
+    batch = make_batch(name, num_graphs=count, tie_free=True)
+    torch.manual_seed(324)
+    ref = orc.OracleModel(cfg.num_features, cfg.num_classes, cfg.k).double().eval()
+    with torch.no_grad():
+        for c in (ref.conv1, ref.conv2, ref.conv3, ref.conv4):
+            c.bias.uniform_(-0.1, 0.1)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k)
+    model.load_state_dict({k_: v.float() for k_, v in ref.state_dict().items()})
+    model = model.to(DEV).eval()
+    data = batch.to(DEV)
+    data.max_nodes = int((batch.ptr[1:] - batch.ptr[:-1]).max())
+
+    g = model.build_graph(data)
+    pooled, xcat, perm = model.hot_path(data.x, g)
+    rx, rpool = ref.hot_path(batch.x.double(), batch.edge_index, batch.batch, count)
+    assert (xcat.detach().cpu().double() - rx.detach()).abs().max().item() <= ATOL
+    _, rperm = orc.sort_aggregation(rx.detach(), batch.batch, cfg.k, count, return_perm=True)
+    swaps = assert_perm_matches(perm.cpu().numpy(), rperm.numpy(), rx.detach().numpy()[:, -1],
+                                batch.ptr.numpy(), cfg.k)
+    if swaps:
+        pytest.skip(f"{swaps} near-tie rank swaps: pooled layout differs legitimately")
+    assert (pooled.detach().cpu().double() - rpool.detach()).abs().max().item() <= ATOL
+
+    out = model(data)
+    rout = ref(batch_to_double(batch))
+    assert (out.detach().cpu().double() - rout.detach()).abs().max().item() <= 1e-4
+    torch.nn.functional.nll_loss(out, data.y).backward()
+    torch.nn.functional.nll_loss(rout, batch.y).backward()
+    rp = dict(ref.named_parameters())
+    for pname, p in model.named_parameters():
+        want = rp[pname].grad
+        scale = max(1e-3, float(want.abs().max()))
+        err = (p.grad.cpu().double() - want).abs().max().item()
+        assert err <= 2e-3 * scale, f"{pname}: {err} vs scale {scale}"
+
+
+def batch_to_double(b):
+    return dg.GraphBatch(b.x.double(), b.edge_index, b.batch, b.ptr, b.y, b.num_graphs)
+
+
+def test_full_size_collab_properties():
+    """BASELINE config 4 at full size (512 graphs, ~2.4M edges): determinism,
+    sortedness of the pooled keys, batch-of-1 == batched, and direct oracle parity."""
+    cfg = CONFIGS["collab"]
+    batch = make_batch("collab")
+    torch.manual_seed(324)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    data = batch.to(DEV)
+    g = model.build_graph(data)
+    with torch.no_grad():
+        pooled, xcat, perm = model.hot_path(data.x, g)
+        pooled2, xcat2, perm2 = model.hot_path(data.x, model.build_graph(data))
+    assert torch.equal(xcat, xcat2) and torch.equal(perm, perm2) and torch.equal(pooled, pooled2)
+    keys = pooled.view(cfg.batch_size, cfg.k, 97)[:, :, -1]
+    valid = perm >= 0
+    both = valid[:, 1:] & valid[:, :-1]
+    assert (keys[:, :-1][both] >= keys[:, 1:][both]).all()
+    assert (pooled.view(cfg.batch_size, cfg.k, 97)[~valid] == 0).all()
+    # every valid perm entry points into its own graph and is unique
+    gp = g.gptr.long()
+    lo, hi = gp[:-1].view(-1, 1), gp[1:].view(-1, 1)
+    assert ((perm >= lo) & (perm < hi))[valid].all()
+    assert valid.sum(1).tolist() == torch.minimum(hi - lo, torch.tensor(cfg.k, device=DEV)).view(-1).tolist()
+    # gathered rows equal x_cat rows
+    assert torch.equal(pooled.view(-1, 97)[valid.view(-1)], xcat[perm[valid].long()])
+    # oracle parity on x_cat
+    ws = [c.lin.weight.detach().cpu() for c in (model.conv1, model.conv2, model.conv3, model.conv4)]
+    bs = [c.bias.detach().cpu() for c in (model.conv1, model.conv2, model.conv3, model.conv4)]
+    ref = orc.graph_conv_stack(batch.x, batch.edge_index, ws, bs)
+    assert (xcat.cpu() - ref).abs().max().item() <= ATOL
+    # batch-of-1 == batched for a few graphs
+    graphs = make_graphs(cfg, cfg.batch_size, 324)
+    for gi in (0, 17, 511):
+        one = collate([graphs[gi]]).to(DEV)
+        with torch.no_grad():
+            _, x1, _ = model.hot_path(one.x, model.build_graph(one))
+        lo_i, hi_i = int(batch.ptr[gi]), int(batch.ptr[gi + 1])
+        assert (x1 - xcat[lo_i:hi_i]).abs().max().item() <= 1e-6
+
+
+def test_permutation_equivariance():
+    """Relabelling nodes inside each graph leaves the pooled output unchanged
+    (tie-free features), up to fp32 summation order."""
+    cfg = CONFIGS["proteins"]
+    graphs = make_graphs(cfg, 16, seed=2, tie_free=True)
+    rng = np.random.RandomState(0)
+    shuffled = []
+    for gr in graphs:
+        n = gr["x"].shape[0]
+        p = rng.permutation(n)                 # new id of old node i is p[i]
+        inv = np.argsort(p)
+        ei = p[gr["edge_index"]]
+        o = np.lexsort((ei[1], ei[0]))
+        shuffled.append({"x": gr["x"][inv], "edge_index": ei[:, o], "y": gr["y"]})
+    torch.manual_seed(1)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    with torch.no_grad():
+        a = collate(graphs).to(DEV)
+        b = collate(shuffled).to(DEV)
+        pa, _, _ = model.hot_path(a.x, model.build_graph(a))
+        pb, _, _ = model.hot_path(b.x, model.build_graph(b))
+    assert (pa - pb).abs().max().item() <= 1e-5
+
+
+def test_cuda_graph_capture_replays_bit_identically():
+    cfg = CONFIGS["mutag"]
+    batch = make_batch("mutag").to(DEV)
+    torch.manual_seed(0)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    g = model.build_graph(batch)
+    with torch.no_grad():
+        eager, _, _ = model.hot_path(batch.x, g)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            model.hot_path(batch.x, g)
+        torch.cuda.current_stream().wait_stream(s)
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            g2 = model.build_graph(batch)
+            captured, _, _ = model.hot_path(batch.x, g2)
+        captured.zero_()
+        cg.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ops.sort_pool_fwd(torch.zeros(3, 4), torch.zeros(2, dtype=torch.int32), 2)
+    m = dg.Model(8, 2)
+    with pytest.raises((RuntimeError, TypeError)):
+        m(make_batch("mutag", num_graphs=3))

@@ -77,8 +77,11 @@ def test_no_cpu_fallback():
                               None, 0, 0, torch.zeros(2, 2))
     with pytest.raises(NotImplementedError):
         torch.ops.dgcnn_b200.sort_pool_bwd(torch.zeros(1, 4), torch.zeros(1, 2, dtype=torch.int32), 3)
+    import subprocess
     import sys
-    assert not any(m.startswith("oracle") for m in sys.modules if "dgcnn_b200" in sys.modules), \
+    code = ("import sys; sys.path.insert(0, %r); import dgcnn_b200; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)" % ROOT)
+    assert subprocess.run([sys.executable, "-c", code]).returncode == 0, \
         "importing the product must not import the oracle"
 
 

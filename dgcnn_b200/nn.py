@@ -23,7 +23,7 @@ from torch import Tensor, nn
 from . import ops
 from .ops import ACT_NONE, ACT_TANH, NORM_RW, NORM_SYM, Graph
 
-__all__ = ["GCNConv", "GraphConvolution", "SortAggregation", "SortPool", "Model",
+__all__ = ["set_fused", "fused_enabled", "GCNConv", "GraphConvolution", "SortAggregation", "SortPool", "Model",
            "remove_self_loops", "graph_conv_stack", "classifier_in_features"]
 
 
@@ -32,6 +32,20 @@ def remove_self_loops(edge_index: Tensor, edge_attr: Optional[Tensor] = None):
     because K0 drops loops while it builds the CSR."""
     keep = edge_index[0] != edge_index[1]
     return edge_index[:, keep], (None if edge_attr is None else edge_attr[keep])
+
+
+_FUSED = True
+
+
+def set_fused(enabled: bool) -> None:
+    """Enable/disable the one-launch fused stack kernels (the per-layer kernels are
+    always available; tests use this to cross-check the two CUDA paths)."""
+    global _FUSED
+    _FUSED = bool(enabled)
+
+
+def fused_enabled() -> bool:
+    return _FUSED
 
 
 def _norm_id(norm: Union[int, str]) -> int:
@@ -101,13 +115,18 @@ class _StackFn(torch.autograd.Function):
         offs = [0]
         for c in widths:
             offs.append(offs[-1] + c)
-        xcat = torch.empty(n, offs[-1], dtype=torch.float32, device=x.device)
-        h = x
-        for l, (w, b) in enumerate(zip(weights, biases)):
-            out = xcat[:, offs[l]:offs[l + 1]]
-            ops.graph_conv_fwd(h, graph.rowptr, graph.col, graph.dis, w, b, norm, ACT_TANH, out)
-            h = out
-        pooled, perm = ops.sort_pool_fwd(xcat, graph.gptr, k, graph.max_nodes)
+        fused = (fused_enabled() and widths == [32, 32, 32, 1] and x.size(1) <= 128
+                 and ops.stack_fwd_supported(x.size(1), graph.max_nodes))
+        if fused:          # KS: one launch, one CTA per graph, everything in shared memory
+            pooled, xcat, perm = ops.stack_fwd(x, graph, weights, biases, k, norm)
+        else:              # K1 x L + K2: any widths, any graph size
+            xcat = torch.empty(n, offs[-1], dtype=torch.float32, device=x.device)
+            h = x
+            for l, (w, b) in enumerate(zip(weights, biases)):
+                out = xcat[:, offs[l]:offs[l + 1]]
+                ops.graph_conv_fwd(h, graph.rowptr, graph.col, graph.dis, w, b, norm, ACT_TANH, out)
+                h = out
+            pooled, perm = ops.sort_pool_fwd(xcat, graph.gptr, k, graph.max_nodes)
         ctx.graph, ctx.norm, ctx.offs = graph, norm, offs
         ctx.has_bias = [b is not None for b in biases]
         ctx.save_for_backward(x, xcat, perm, *weights)

@@ -23,7 +23,7 @@ GRAPH_BAD_EDGE, GRAPH_BAD_BATCH = 1, 2
 # kernels launched by this process through the C ABI (memsets not counted); bench.py
 # reads it to report `gpu_launches`.  Keyed by entry point.
 LAUNCHES = {"build_graph": 0, "graph_ptr": 0, "graph_conv_fwd": 0, "graph_conv_bwd": 0,
-            "sort_pool_fwd": 0, "sort_pool_bwd": 0}
+            "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0}
 
 
 def launches_total() -> int:
@@ -231,6 +231,44 @@ def sort_pool_bwd(dout: Tensor, perm: Tensor, num_nodes: int, out: Optional[Tens
     _lib.check(rc, "sort_pool_bwd")
     LAUNCHES["sort_pool_bwd"] += (1 if b > 0 else 0) + (1 if out.stride(0) != d and num_nodes > 0 else 0)
     return out
+
+
+def stack_fwd_supported(num_features: int, max_nodes: int) -> bool:
+    """Can the one-launch fused forward (KS) hold the largest graph in shared memory?"""
+    if max_nodes <= 0:
+        return False
+    return bool(_lib.load_library().dgcnn_stack_fwd_supported(int(num_features), int(max_nodes)))
+
+
+def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
+              ) -> Tuple[Tensor, Tensor, Tensor]:
+    """KS: model.py:28-35 in one launch -> (pooled [B,k*97], xcat [N,97], perm [B,k])."""
+    lib = _lib.load_library()
+    _require_cuda(x, "x", torch.float32)
+    n, f = x.shape
+    if len(weights) != 4 or [tuple(w.shape) for w in weights] != [(32, f), (32, 32), (32, 32), (1, 32)]:
+        raise ValueError("dgcnn_b200: stack_fwd needs the model's F->32->32->32->1 weights")
+    if graph.gptr is None:
+        raise ValueError("dgcnn_b200: stack_fwd needs a graph built with `batch`")
+    ws = [w.contiguous() for w in weights]
+    bs = [None if b is None else b.contiguous() for b in biases]
+    for t in ws + [b for b in bs if b is not None]:
+        _require_cuda(t, "parameter", torch.float32)
+    b = graph.num_graphs
+    xcat = torch.empty(n, 97, dtype=torch.float32, device=x.device)
+    pooled = torch.empty(b, int(k) * 97, dtype=torch.float32, device=x.device)
+    perm = torch.empty(b, int(k), dtype=torch.int32, device=x.device)
+    wsp = _workspace(lib.dgcnn_stack_fwd_workspace_bytes(), x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.dgcnn_stack_fwd(_ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr), _ptr(graph.col),
+                                 _ptr(graph.dis), _ptr(graph.gptr), n, b, int(graph.max_nodes),
+                                 _ptr(ws[0]), _ptr(bs[0]), _ptr(ws[1]), _ptr(bs[1]),
+                                 _ptr(ws[2]), _ptr(bs[2]), _ptr(ws[3]), _ptr(bs[3]),
+                                 _ptr(xcat), 97, _ptr(pooled), _ptr(perm), int(k), int(norm),
+                                 _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
+    _lib.check(rc, "stack_fwd")
+    LAUNCHES["stack_fwd"] += 1 if b > 0 else 0
+    return pooled, xcat, perm
 
 
 # ---------------------------------------------------------------------------------

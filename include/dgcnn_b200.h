@@ -154,6 +154,29 @@ int dgcnn_sort_pool_bwd(const float* dout, const int32_t* perm, int64_t num_grap
                         int32_t k, int32_t d, float* dx, int64_t lddx, int64_t num_nodes,
                         void* stream);
 
+/* ------------------------------------------------------------------------
+ * KS  fused forward of the whole hot path, model.py:28-35, in ONE launch for the
+ * model's fixed widths (F -> 32 -> 32 -> 32 -> 1, model.py:13-16):
+ *   xcat [N,97] = cat(tanh(conv1..4))  and  (pooled [B,k*97], perm [B,k]) =
+ *   SortAggregation(k)(xcat) -- same contracts as K1 and K2 above.
+ * One CTA per graph; adjacency, features and sort keys stay in shared memory
+ * (see dgcnn_b200/csrc/graph_stack.cu).  Needs the size of the largest graph
+ * (`max_nodes`, known on the host from the batch's ptr): graphs must fit the
+ * shared-memory budget, which dgcnn_stack_fwd_supported() reports (1/0, pure host
+ * arithmetic).  When it returns 0 use K1 x 4 + K2.
+ * w1 [32,F], w2/w3 [32,32], w4 [1,32] row-major; biases may be NULL.
+ * ------------------------------------------------------------------------ */
+int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes);
+size_t dgcnn_stack_fwd_workspace_bytes(void);
+int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
+                    const int32_t* rowptr, const int32_t* col, const float* dis,
+                    const int32_t* gptr, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                    const float* w1, const float* b1, const float* w2, const float* b2,
+                    const float* w3, const float* b3, const float* w4, const float* b4,
+                    float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
+                    int32_t norm, int32_t* status,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

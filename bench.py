@@ -362,14 +362,25 @@ def main():
         convs = (model.conv1, model.conv2, model.conv3, model.conv4)
 
         def timed(fn, reps=20):
-            times = []
-            for _ in range(3):
+            """Mean device time of fn(): captured once in a CUDA graph and replayed, so that
+            Python/ctypes launch overhead never sits between the two events; L2 is flushed
+            (untimed) before every replay."""
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
                 fn()
+            times = []
             for _ in range(reps):
                 flush.zero_()
                 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                fn()
+                g.replay()
                 b_.record()
                 torch.cuda.synchronize()
                 times.append(a.elapsed_time(b_))

@@ -57,7 +57,7 @@ struct StackFwdParams {
 
 // shared-memory carve-up, in 4-byte words; every region starts 16-byte aligned
 struct StackLayout {
-    int w1t, w2t, w3t, w4, b1, b2, b3, colsum, red, bufA, bufB, bm, cs, rs, v, key, order, total;
+    int w1t, w2t, w3t, w4, b1, b2, b3, colsum, red, bufA, bufB, bm, cs, rs, v, key, order, rp, total;
 };
 
 __host__ __device__ inline int al4(int v) { return (v + 3) & ~3; }
@@ -83,6 +83,7 @@ __host__ __device__ inline StackLayout stack_layout(int f, int nmax, int nwarps)
     L.v = o; o += al4(nmax);
     L.key = o; o += al4(nmax);
     L.order = o; o += al4(nmax);
+    L.rp = o; o += al4(nmax + 1);
     L.total = o;
     return L;
 }
@@ -101,8 +102,8 @@ __device__ __forceinline__ float f4_get(const float4& a, int i) {
 template <bool PROJECT, bool EMIT_H4>
 __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float* __restrict__ out,
                                             const uint32_t* __restrict__ bm, int wpr, int n, bool dup,
-                                            const int32_t* __restrict__ rowptr_g,
-                                            const int32_t* __restrict__ col, int base,
+                                            const int* __restrict__ rp,
+                                            const int32_t* __restrict__ col_g, int base,
                                             const float* __restrict__ rs, const float* __restrict__ colsum,
                                             const float* __restrict__ wt, const float* __restrict__ bias,
                                             const float* __restrict__ w4s, const float* __restrict__ cs,
@@ -119,7 +120,7 @@ __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float*
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
             if (!dup) {
-                const int cnt = rowptr_g[i + 1] - rowptr_g[i] + 1;   // neighbours + self
+                const int cnt = rp[i + 1] - rp[i] + 1;               // neighbours + self
                 const bool comp = 2 * cnt > n;
                 const uint32_t* brow = bm + i * wpr;
                 for (int t = 0; t < wpr; ++t) {
@@ -141,8 +142,8 @@ __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float*
                 }
             } else {
                 acc = in4[i * 8 + q];                                  // the self loop
-                for (int e = rowptr_g[i]; e < rowptr_g[i + 1]; ++e)
-                    acc = f4_add(acc, in4[(col[e] - base) * 8 + q]);
+                for (int e = rp[i]; e < rp[i + 1]; ++e)
+                    acc = f4_add(acc, in4[(col_g[e] - base) * 8 + q]);
             }
             const float r = rs[i];
             acc = make_float4(acc.x * r, acc.y * r, acc.z * r, acc.w * r);
@@ -178,15 +179,15 @@ __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float*
 // One warp per row: s_i = sum_{j in N(i) U {i}} val[j]  (val pre-scaled by c_j)
 __device__ __forceinline__ float scalar_row_sum(const float* __restrict__ val,
                                                 const uint32_t* __restrict__ brow, int wpr, bool dup,
-                                                const int32_t* __restrict__ rowptr_g,
-                                                const int32_t* __restrict__ col, int base, int i) {
+                                                const int* __restrict__ rp,
+                                                const int32_t* __restrict__ col_g, int base, int i) {
     const int lane = threadIdx.x & 31;
     float s = 0.f;
     if (!dup) {
         for (int t = 0; t < wpr; ++t)
             if ((brow[t] >> lane) & 1u) s += val[t * 32 + lane];
     } else {
-        for (int e = rowptr_g[i] + lane; e < rowptr_g[i + 1]; e += 32) s += val[col[e] - base];
+        for (int e = rp[i] + lane; e < rp[i + 1]; e += 32) s += val[col_g[e] - base];
         if (lane == 0) s += val[i];
     }
     return warp_sum(s);
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
     uint32_t* bm = reinterpret_cast<uint32_t*>(sm + L.bm);
     float* cs = sm + L.cs;  float* rs = sm + L.rs;  float* v = sm + L.v;  float* key = sm + L.key;
     int* order = reinterpret_cast<int*>(sm + L.order);
+    int* rp = reinterpret_cast<int*>(sm + L.rp);
     const int f = p.f, nmax = p.nmax;
     const float b4 = p.b4 ? p.b4[0] : 0.f;
 
@@ -247,28 +249,51 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
         if (n == 0) { __syncthreads(); continue; }
 
         const int wpr = (n + 31) >> 5;
-        const int32_t* rowptr_g = p.rowptr + base;
+        const int e0 = p.rowptr[base];
+        const int32_t* col_g = p.col + e0;
         float* xc = p.xcat + (int64_t)base * p.ldc;
 
-        // ---- phase 0: clear bitmap, per-node coefficients -----------------------
+        // ---- phase 0: clear bitmap, per-node coefficients, local row pointers -----
         for (int idx = tid; idx < n * wpr; idx += nthreads) bm[idx] = 0u;
         for (int j = tid; j < n; j += nthreads) {
             const float d = p.dis[base + j];
             cs[j] = col_coef(d, p.norm);
             rs[j] = row_coef(d, p.norm);
         }
+        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
         __syncthreads();
 
-        // ---- phase 1: adjacency bitmap from the CSR (one warp per row) ------------
+        // ---- phase 1: adjacency bitmap from the CSR ---------------------------------
+        // The graph's col segment is contiguous: stage it in ONE cooperative, coalesced
+        // sweep (all loads in flight at once) as 16-bit local ids in the two feature
+        // buffers, which are still free.  Building from global row by row instead costs
+        // a DRAM round trip per 32 edges per warp and dominated the kernel.
+        const int eg = rp[n];
+        uint16_t* cl = reinterpret_cast<uint16_t*>(bufA);              // bufA and bufB are adjacent
+        const bool staged = eg <= 2 * kHid * 2 * nmax;                 // uint16 slots in both buffers
+        if (staged) {
+            for (int idx = tid; idx < eg; idx += nthreads) {
+                const unsigned j = (unsigned)(col_g[idx] - base);
+                if (j >= (unsigned)n && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_EDGE);
+                cl[idx] = j < (unsigned)n ? (uint16_t)j : (uint16_t)0xffff;
+            }
+            __syncthreads();
+        }
         for (int i = warp; i < n; i += nwarps) {
             uint32_t* brow = bm + i * wpr;
-            const int beg = rowptr_g[i], end = rowptr_g[i + 1];
-            for (int e0 = beg; e0 < end; e0 += 32) {
-                const int e = e0 + lane;
-                int j = (e < end) ? p.col[e] - base : -1;
-                if (e < end && (unsigned)j >= (unsigned)n) {    // edge leaving its graph
-                    if (p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_EDGE);
-                    j = -1;
+            const int beg = rp[i], end = rp[i + 1];
+            for (int c0 = beg; c0 < end; c0 += 32) {
+                const int e = c0 + lane;
+                int j = -1;
+                if (e < end) {
+                    if (staged) {
+                        const unsigned t = cl[e];
+                        j = t == 0xffffu ? -1 : (int)t;
+                    } else {
+                        const unsigned t = (unsigned)(col_g[e] - base);
+                        if (t >= (unsigned)n) { if (p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_EDGE); }
+                        else j = (int)t;
+                    }
                 }
                 const bool valid = j >= 0;
                 const int word = valid ? (j >> 5) : -1;
@@ -300,8 +325,8 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
                 const float r = rs[i];
                 float acc = b1s[lane];
                 for (int k = 0; k < f; ++k) {
-                    const float a = r * scalar_row_sum(xs + k * nmax, bm + i * wpr, wpr, dup, rowptr_g,
-                                                       p.col, base, i);
+                    const float a = r * scalar_row_sum(xs + k * nmax, bm + i * wpr, wpr, dup, rp,
+                                                       col_g, base, i);
                     acc = fmaf(a, w1t[k * kHid + lane], acc);
                 }
                 bufA[i * kHid + lane] = tanhf(acc);
@@ -327,7 +352,7 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
                 }
                 __syncthreads();
             }
-            aggregate32<false, false>(bufB, bufA, bm, wpr, n, dup, rowptr_g, p.col, base, rs, colsum,
+            aggregate32<false, false>(bufB, bufA, bm, wpr, n, dup, rp, col_g, base, rs, colsum,
                                       nullptr, b1s, nullptr, nullptr, nullptr);
         }
         __syncthreads();
@@ -358,10 +383,10 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
                 __syncthreads();
             }
             if (layer == 1)
-                aggregate32<true, false>(bin, bout, bm, wpr, n, dup, rowptr_g, p.col, base, rs, colsum,
+                aggregate32<true, false>(bin, bout, bm, wpr, n, dup, rp, col_g, base, rs, colsum,
                                          w2t, b2s, nullptr, nullptr, nullptr);
             else
-                aggregate32<true, true>(bin, bout, bm, wpr, n, dup, rowptr_g, p.col, base, rs, colsum,
+                aggregate32<true, true>(bin, bout, bm, wpr, n, dup, rp, col_g, base, rs, colsum,
                                         w3t, b3s, w4s, cs, v);
             __syncthreads();
         }
@@ -370,7 +395,7 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
         for (int j = warp; j < n; j += nwarps)
             xc[(int64_t)j * p.ldc + 2 * kHid + lane] = bufA[j * kHid + lane];
         for (int i = warp; i < n; i += nwarps) {
-            const float s = scalar_row_sum(v, bm + i * wpr, wpr, dup, rowptr_g, p.col, base, i);
+            const float s = scalar_row_sum(v, bm + i * wpr, wpr, dup, rp, col_g, base, i);
             if (lane == 0) {
                 const float x4 = tanhf(fmaf(rs[i], s, b4));
                 key[i] = x4;
@@ -402,13 +427,13 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
         __syncthreads();
 
         // ---- gather the k winners (rows of x_cat this CTA just wrote: L2 hits) ------------
-        for (int r = warp; r < keep; r += nwarps) {
-            const int src = order[r];
-            const float* xr = xc + (int64_t)src * p.ldc;
-            float* orow = pooled_g + (int64_t)r * kCat;
-            for (int c = lane; c < kCat; c += 32) orow[c] = xr[c];
-            if (lane == 0) perm_g[r] = base + src;
+        // flat index over keep*97 elements: contiguous writes, row-contiguous reads, and
+        // several independent loads in flight per thread
+        for (int idx = tid; idx < keep * kCat; idx += nthreads) {
+            const int r = idx / kCat, c = idx - r * kCat;
+            pooled_g[idx] = xc[(int64_t)order[r] * p.ldc + c];
         }
+        for (int r = tid; r < keep; r += nthreads) perm_g[r] = base + order[r];
         __syncthreads();   // shared buffers are reused by the next graph
     }
 }

@@ -1,7 +1,8 @@
 """dgcnn_b200 -- B200-native (sm_100a) DGCNN hot path: fused graph convolutions and
 SortPooling behind the Module API of leftthomas/DGCNN's model.py.  CUDA only."""
 from .ops import (ACT_NONE, ACT_TANH, NORM_RW, NORM_SYM, Graph, build_graph, graph_conv_bwd,
-                  graph_conv_fwd, graph_ptr, sort_pool_bwd, sort_pool_fwd, stack_fwd, stack_fwd_supported)
+                  graph_conv_fwd, graph_ptr, sort_pool_bwd, sort_pool_fwd, stack_bwd, stack_bwd_supported, stack_fwd,
+                  stack_fwd_supported)
 from .nn import (GCNConv, GraphConvolution, Model, SortAggregation, SortPool,
                  classifier_in_features, fused_enabled, graph_conv_stack, remove_self_loops,
                  set_fused)

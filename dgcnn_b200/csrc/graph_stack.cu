@@ -30,17 +30,10 @@
 // detected while the bitmap is built and take a CSR-walking path in the same kernel.
 // Graphs larger than the shared-memory budget are not handled here: the host picks
 // the per-layer kernels (graph_conv.cu + sort_pool.cu) for such batches.
-#include "common.cuh"
+#include "graph_stack.cuh"
 #include "sort_key.cuh"
 
 namespace dgcnn {
-
-constexpr int kHid = 32;            // hidden width, model.py:13-15
-constexpr int kCat = 3 * kHid + 1;  // 97, model.py:19 (Conv1d kernel/stride 97)
-constexpr int kStackMaxThreads = 512;
-constexpr int kSmallF = 8;          // layer 1 aggregates first when F <= 8
-constexpr int kMaxF = 128;
-constexpr int kSmemBudget = 227 * 1024;
 
 struct StackFwdParams {
     const float* x; int64_t ldx; int f;
@@ -60,7 +53,6 @@ struct StackLayout {
     int w1t, w2t, w3t, w4, b1, b2, b3, colsum, red, bufA, bufB, bm, cs, rs, v, key, order, rp, total;
 };
 
-__host__ __device__ inline int al4(int v) { return (v + 3) & ~3; }
 
 __host__ __device__ inline StackLayout stack_layout(int f, int nmax, int nwarps) {
     StackLayout L;
@@ -81,18 +73,11 @@ __host__ __device__ inline StackLayout stack_layout(int f, int nmax, int nwarps)
     L.cs = o; o += al4(nmax);
     L.rs = o; o += al4(nmax);
     L.v = o; o += al4(nmax);
-    L.key = o; o += al4(nmax);
-    L.order = o; o += al4(nmax);
+    L.key = L.rs;     // x_4 overwrites r_i in place (same index, same thread, layer 4)
+    L.order = L.cs;   // c_j is dead once layer 3 has emitted v
     L.rp = o; o += al4(nmax + 1);
     L.total = o;
     return L;
-}
-
-__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
-    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-}
-__device__ __forceinline__ float f4_get(const float4& a, int i) {
-    return i == 0 ? a.x : (i == 1 ? a.y : (i == 2 ? a.z : a.w));
 }
 
 // 32-wide aggregation of one layer, float4 layout (lane = 8*group + q; group -> row,
@@ -119,50 +104,13 @@ __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float*
         const bool active = i < n;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
-            if (!dup) {
-                const int cnt = rp[i + 1] - rp[i] + 1;               // neighbours + self
-                const bool comp = 2 * cnt > n;
-                const uint32_t* brow = bm + i * wpr;
-                for (int t = 0; t < wpr; ++t) {
-                    uint32_t w = brow[t];
-                    if (comp) {
-                        w = ~w;
-                        if (t == wpr - 1) w &= tailmask;
-                    }
-                    const float4* src = in4 + (t * 32) * 8 + q;
-                    while (w) {
-                        const int b = __ffs(w) - 1;
-                        w &= w - 1;
-                        acc = f4_add(acc, src[b * 8]);
-                    }
-                }
-                if (comp) {
-                    const float4 s = reinterpret_cast<const float4*>(colsum)[q];
-                    acc = make_float4(s.x - acc.x, s.y - acc.y, s.z - acc.z, s.w - acc.w);
-                }
-            } else {
-                acc = in4[i * 8 + q];                                  // the self loop
-                for (int e = rp[i]; e < rp[i + 1]; ++e)
-                    acc = f4_add(acc, in4[(col_g[e] - base) * 8 + q]);
-            }
+            acc = gather_row32(in4, bm, wpr, n, dup, rp, col_g, base, colsum, i, q, tailmask);
             const float r = rs[i];
             acc = make_float4(acc.x * r, acc.y * r, acc.z * r, acc.w * r);
         }
         float4 y;
-        if (PROJECT) {
-            y = bias4;
-#pragma unroll
-            for (int k = 0; k < kHid; ++k) {
-                const float a = __shfl_sync(DGCNN_FULL_MASK, f4_get(acc, k & 3), (lane & 24) + (k >> 2));
-                const float4 w = wt4[k * 8 + q];
-                y.x = fmaf(a, w.x, y.x);
-                y.y = fmaf(a, w.y, y.y);
-                y.z = fmaf(a, w.z, y.z);
-                y.w = fmaf(a, w.w, y.w);
-            }
-        } else {
-            y = f4_add(acc, bias4);
-        }
+        if (PROJECT) y = project32(acc, bias4, wt4, lane, q);
+        else y = f4_add(acc, bias4);
         y = make_float4(tanhf(y.x), tanhf(y.y), tanhf(y.z), tanhf(y.w));
         if (active) reinterpret_cast<float4*>(out)[i * 8 + q] = y;
         if (EMIT_H4) {
@@ -176,24 +124,7 @@ __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float*
     }
 }
 
-// One warp per row: s_i = sum_{j in N(i) U {i}} val[j]  (val pre-scaled by c_j)
-__device__ __forceinline__ float scalar_row_sum(const float* __restrict__ val,
-                                                const uint32_t* __restrict__ brow, int wpr, bool dup,
-                                                const int* __restrict__ rp,
-                                                const int32_t* __restrict__ col_g, int base, int i) {
-    const int lane = threadIdx.x & 31;
-    float s = 0.f;
-    if (!dup) {
-        for (int t = 0; t < wpr; ++t)
-            if ((brow[t] >> lane) & 1u) s += val[t * 32 + lane];
-    } else {
-        for (int e = rp[i] + lane; e < rp[i + 1]; e += 32) s += val[col_g[e] - base];
-        if (lane == 0) s += val[i];
-    }
-    return warp_sum(s);
-}
-
-__global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwdParams p) {
+__global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwdParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_graph;
     __shared__ int s_dup;
@@ -268,47 +199,8 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
         // sweep (all loads in flight at once) as 16-bit local ids in the two feature
         // buffers, which are still free.  Building from global row by row instead costs
         // a DRAM round trip per 32 edges per warp and dominated the kernel.
-        const int eg = rp[n];
-        uint16_t* cl = reinterpret_cast<uint16_t*>(bufA);              // bufA and bufB are adjacent
-        const bool staged = eg <= 2 * kHid * 2 * nmax;                 // uint16 slots in both buffers
-        if (staged) {
-            for (int idx = tid; idx < eg; idx += nthreads) {
-                const unsigned j = (unsigned)(col_g[idx] - base);
-                if (j >= (unsigned)n && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_EDGE);
-                cl[idx] = j < (unsigned)n ? (uint16_t)j : (uint16_t)0xffff;
-            }
-            __syncthreads();
-        }
-        for (int i = warp; i < n; i += nwarps) {
-            uint32_t* brow = bm + i * wpr;
-            const int beg = rp[i], end = rp[i + 1];
-            for (int c0 = beg; c0 < end; c0 += 32) {
-                const int e = c0 + lane;
-                int j = -1;
-                if (e < end) {
-                    if (staged) {
-                        const unsigned t = cl[e];
-                        j = t == 0xffffu ? -1 : (int)t;
-                    } else {
-                        const unsigned t = (unsigned)(col_g[e] - base);
-                        if (t >= (unsigned)n) { if (p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_EDGE); }
-                        else j = (int)t;
-                    }
-                }
-                const bool valid = j >= 0;
-                const int word = valid ? (j >> 5) : -1;
-                const uint32_t bit = valid ? (1u << (j & 31)) : 0u;
-                const uint32_t peers = __match_any_sync(DGCNN_FULL_MASK, word);
-                const uint32_t val = __reduce_or_sync(peers, bit);
-                if (valid && lane == __ffs(peers) - 1) {
-                    const uint32_t old = brow[word];
-                    if ((old & val) || __popc(val) != __popc(peers)) s_dup = 1;   // multigraph
-                    brow[word] = old | val;
-                }
-                __syncwarp();
-            }
-            if (lane == 0) brow[i >> 5] |= 1u << (i & 31);       // the added self loop
-        }
+        build_bitmap(col_g, base, n, wpr, nmax, rp, bm, reinterpret_cast<uint16_t*>(bufA), &s_dup,
+                     p.status);
         __syncthreads();
         const bool dup = s_dup != 0;
 
@@ -441,13 +333,6 @@ __global__ void __launch_bounds__(kStackMaxThreads, 1) stack_fwd_kernel(StackFwd
 }  // namespace dgcnn
 
 using namespace dgcnn;
-
-static int stack_threads_for(int nmax) { return nmax <= 64 ? 128 : (nmax <= 160 ? 256 : 512); }
-
-static int stack_nmax_for(int64_t max_nodes) {
-    int64_t r = (max_nodes + 31) / 32 * 32;
-    return (int)(r < 32 ? 32 : r);
-}
 
 extern "C" int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes) {
     if (num_features < 1 || num_features > kMaxF || max_nodes < 1 || max_nodes > 4096) return 0;

@@ -1,0 +1,162 @@
+// Device helpers shared by the fused per-graph kernels (graph_stack.cu forward,
+// graph_stack_bwd.cu backward): shared-memory adjacency bitmap, the 8-lanes-per-row
+// float4 gather with the complement trick, the 32x32 row-local projection.
+#pragma once
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int kHid = 32;            // hidden width, model.py:13-15
+constexpr int kCat = 3 * kHid + 1;  // 97, model.py:19 (Conv1d kernel/stride 97)
+constexpr int kStackMaxThreads = 512;
+constexpr int kSmallF = 8;          // layer 1 aggregates first when F <= 8
+constexpr int kMaxF = 128;
+constexpr int kSmemBudget = 227 * 1024;
+
+
+__host__ __device__ inline int al4(int v) { return (v + 3) & ~3; }
+
+inline int stack_threads_for(int nmax) { return nmax <= 64 ? 128 : (nmax <= 160 ? 256 : 512); }
+
+inline int stack_nmax_for(int64_t max_nodes) {
+    int64_t r = (max_nodes + 31) / 32 * 32;
+    return (int)(r < 32 ? 32 : r);
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float f4_get(const float4& a, int i) {
+    return i == 0 ? a.x : (i == 1 ? a.y : (i == 2 ? a.z : a.w));
+}
+
+// Sum of the (pre-scaled) feature rows of N(i) U {i}, float4 layout: the caller's lane
+// holds channels 4q..4q+3 of row i.  Dense rows walk the complement of the bitmap row
+// and subtract from the column sum; multigraphs (dup) walk the CSR instead.
+__device__ __forceinline__ float4 gather_row32(const float4* __restrict__ in4,
+                                               const uint32_t* __restrict__ bm, int wpr, int n,
+                                               bool dup, const int* __restrict__ rp,
+                                               const int32_t* __restrict__ col_g, int base,
+                                               const float* __restrict__ colsum, int i, int q,
+                                               uint32_t tailmask) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!dup) {
+        const int cnt = rp[i + 1] - rp[i] + 1;               // neighbours + self
+        const bool comp = 2 * cnt > n;
+        const uint32_t* brow = bm + i * wpr;
+        for (int t = 0; t < wpr; ++t) {
+            uint32_t w = brow[t];
+            if (comp) {
+                w = ~w;
+                if (t == wpr - 1) w &= tailmask;
+            }
+            const float4* src = in4 + (t * 32) * 8 + q;
+            while (w) {
+                const int b = __ffs(w) - 1;
+                w &= w - 1;
+                acc = f4_add(acc, src[b * 8]);
+            }
+        }
+        if (comp) {
+            const float4 s = reinterpret_cast<const float4*>(colsum)[q];
+            acc = make_float4(s.x - acc.x, s.y - acc.y, s.z - acc.z, s.w - acc.w);
+        }
+    } else {
+        acc = in4[i * 8 + q];                                  // the self loop
+        for (int e = rp[i]; e < rp[i + 1]; ++e)
+            acc = f4_add(acc, in4[(col_g[e] - base) * 8 + q]);
+    }
+    return acc;
+}
+
+// y[4q..4q+3] = init + sum_k a_k * M[k][4q..4q+3] for the row held by this 8-lane group
+// (a_k lives in lane (k>>2) of the group, component k&3).  Must be executed by the
+// whole warp: it shuffles with the full mask.
+__device__ __forceinline__ float4 project32(const float4& acc, float4 init,
+                                            const float4* __restrict__ m4, int lane, int q) {
+    float4 y = init;
+#pragma unroll
+    for (int k = 0; k < kHid; ++k) {
+        const float a = __shfl_sync(DGCNN_FULL_MASK, f4_get(acc, k & 3), (lane & 24) + (k >> 2));
+        const float4 w = m4[k * 8 + q];
+        y.x = fmaf(a, w.x, y.x);
+        y.y = fmaf(a, w.y, y.y);
+        y.z = fmaf(a, w.z, y.z);
+        y.w = fmaf(a, w.w, y.w);
+    }
+    return y;
+}
+
+// One warp per row: s_i = sum_{j in N(i) U {i}} val[j]  (val pre-scaled by c_j)
+__device__ __forceinline__ float scalar_row_sum(const float* __restrict__ val,
+                                                const uint32_t* __restrict__ brow, int wpr, bool dup,
+                                                const int* __restrict__ rp,
+                                                const int32_t* __restrict__ col_g, int base, int i) {
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    if (!dup) {
+        for (int t = 0; t < wpr; ++t)
+            if ((brow[t] >> lane) & 1u) s += val[t * 32 + lane];
+    } else {
+        for (int e = rp[i] + lane; e < rp[i + 1]; e += 32) s += val[col_g[e] - base];
+        if (lane == 0) s += val[i];
+    }
+    return warp_sum(s);
+}
+
+// Adjacency bitmap (plus the self loop) of one graph from its CSR segment.  The segment
+// is contiguous, so it is first staged in ONE cooperative coalesced sweep -- every load
+// in flight at once -- as 16-bit local ids in `cl` (the two feature buffers, still free).
+// Building from global memory row by row costs a DRAM round trip per 32 edges per warp,
+// which dominated the first version of the kernel.  Sets *s_dup for multigraphs.
+// bm must be zeroed and rp filled (and a __syncthreads passed) before the call; the
+// caller synchronises after it.
+__device__ __forceinline__ void build_bitmap(const int32_t* __restrict__ col_g, int base, int n,
+                                             int wpr, int nmax, const int* __restrict__ rp,
+                                             uint32_t* __restrict__ bm, uint16_t* __restrict__ cl,
+                                             int* s_dup, int32_t* status) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int eg = rp[n];
+    const bool staged = eg <= 2 * kHid * 2 * nmax;                 // uint16 slots in both buffers
+    if (staged) {
+        for (int idx = tid; idx < eg; idx += nthreads) {
+            const unsigned j = (unsigned)(col_g[idx] - base);
+            if (j >= (unsigned)n && status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE);
+            cl[idx] = j < (unsigned)n ? (uint16_t)j : (uint16_t)0xffff;
+        }
+        __syncthreads();
+    }
+    for (int i = warp; i < n; i += nwarps) {
+        uint32_t* brow = bm + i * wpr;
+        const int beg = rp[i], end = rp[i + 1];
+        for (int c0 = beg; c0 < end; c0 += 32) {
+            const int e = c0 + lane;
+            int j = -1;
+            if (e < end) {
+                if (staged) {
+                    const unsigned t = cl[e];
+                    j = t == 0xffffu ? -1 : (int)t;
+                } else {
+                    const unsigned t = (unsigned)(col_g[e] - base);
+                    if (t >= (unsigned)n) { if (status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE); }
+                    else j = (int)t;
+                }
+            }
+            const bool valid = j >= 0;
+            const int word = valid ? (j >> 5) : -1;
+            const uint32_t bit = valid ? (1u << (j & 31)) : 0u;
+            const uint32_t peers = __match_any_sync(DGCNN_FULL_MASK, word);
+            const uint32_t val = __reduce_or_sync(peers, bit);
+            if (valid && lane == __ffs(peers) - 1) {
+                const uint32_t old = brow[word];
+                if ((old & val) || __popc(val) != __popc(peers)) *s_dup = 1;   // multigraph
+                brow[word] = old | val;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) brow[i >> 5] |= 1u << (i & 31);           // the added self loop
+    }
+}
+
+}  // namespace dgcnn

@@ -127,7 +127,7 @@ class _StackFn(torch.autograd.Function):
                 ops.graph_conv_fwd(h, graph.rowptr, graph.col, graph.dis, w, b, norm, ACT_TANH, out)
                 h = out
             pooled, perm = ops.sort_pool_fwd(xcat, graph.gptr, k, graph.max_nodes)
-        ctx.graph, ctx.norm, ctx.offs = graph, norm, offs
+        ctx.graph, ctx.norm, ctx.offs, ctx.k, ctx.fused = graph, norm, offs, k, fused
         ctx.has_bias = [b is not None for b in biases]
         ctx.save_for_backward(x, xcat, perm, *weights)
         ctx.mark_non_differentiable(perm)
@@ -141,6 +141,15 @@ class _StackFn(torch.autograd.Function):
         if g.rowptr_t is None:
             raise RuntimeError("dgcnn_b200: graph was built with transpose=False; no backward")
         n = xcat.size(0)
+        if (ctx.fused and fused_enabled() and dpooled is not None and dxcat_in is None
+                and not ctx.needs_input_grad[0]
+                and ops.stack_bwd_supported(x.size(1), g.max_nodes)):
+            # KSB: pooled gradient -> parameter gradients, one CTA per graph, two launches
+            pairs = ops.stack_bwd(dpooled, perm, xcat, x, g, weights, ctx.k, norm)
+            flat = []
+            for (dw, db), hb in zip(pairs, ctx.has_bias):
+                flat += [dw, db if hb else None]
+            return (None, None, None, None, *flat)
         if dpooled is not None:
             dxcat = ops.sort_pool_bwd(dpooled.contiguous().view(perm.size(0), -1), perm, n)
             if dxcat_in is not None:

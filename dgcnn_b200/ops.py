@@ -23,7 +23,7 @@ GRAPH_BAD_EDGE, GRAPH_BAD_BATCH = 1, 2
 # kernels launched by this process through the C ABI (memsets not counted); bench.py
 # reads it to report `gpu_launches`.  Keyed by entry point.
 LAUNCHES = {"build_graph": 0, "graph_ptr": 0, "graph_conv_fwd": 0, "graph_conv_bwd": 0,
-            "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0}
+            "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0, "stack_bwd": 0}
 
 
 def launches_total() -> int:
@@ -269,6 +269,47 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
     _lib.check(rc, "stack_fwd")
     LAUNCHES["stack_fwd"] += 1 if b > 0 else 0
     return pooled, xcat, perm
+
+
+def stack_bwd_supported(num_features: int, max_nodes: int) -> bool:
+    if max_nodes <= 0:
+        return False
+    return bool(_lib.load_library().dgcnn_stack_bwd_supported(int(num_features), int(max_nodes)))
+
+
+def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Graph, weights,
+              k: int, norm: int):
+    """KSB: gradients of the eight GraphConv parameters from d(pooled), two launches.
+    Returns [(dw1, db1), ..., (dw4, db4)] as views of one flat buffer."""
+    lib = _lib.load_library()
+    for t, name in ((dpooled, "dpooled"), (xcat, "xcat"), (x, "x")):
+        _require_cuda(t, name, torch.float32)
+    _require_cuda(perm, "perm", torch.int32)
+    if graph.rowptr_t is None or graph.gptr is None:
+        raise ValueError("dgcnn_b200: stack_bwd needs a graph built with batch and transpose=True")
+    n, f = x.shape
+    b = graph.num_graphs
+    dpooled = dpooled.contiguous()
+    ws = [w.contiguous() for w in weights]
+    total = int(lib.dgcnn_stack_num_params(f))
+    grads = torch.empty(total, dtype=torch.float32, device=x.device)
+    wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f), x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.dgcnn_stack_bwd(_ptr(dpooled), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
+                                 _ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr_t), _ptr(graph.col_t),
+                                 _ptr(graph.dis), _ptr(graph.gptr), n, b, int(graph.max_nodes),
+                                 _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm), _ptr(grads),
+                                 _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
+    _lib.check(rc, "stack_bwd")
+    LAUNCHES["stack_bwd"] += 2 if (b > 0 and n > 0) else 0
+    out, o = [], 0
+    for cout, cin in ((32, f), (32, 32), (32, 32), (1, 32)):
+        dw = grads[o:o + cout * cin].view(cout, cin)
+        o += cout * cin
+        db = grads[o:o + cout]
+        o += cout
+        out.append((dw, db))
+    return out
 
 
 # ---------------------------------------------------------------------------------

@@ -177,6 +177,28 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                     int32_t norm, int32_t* status,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * KSB  fused backward of the hot path (autograd of model.py:28-35, train.py:40),
+ * companion of dgcnn_stack_fwd: from the gradient of `pooled` to the gradients of
+ * the eight GraphConv parameters, one CTA per graph, two launches (per-CTA partial
+ * sums + an ordered reduction: deterministic, no float atomics).
+ *   grads: flat [dgcnn_stack_num_params(F)] in PyG parameter order
+ *     conv1.lin.weight [32,F] | conv1.bias [32] | conv2.lin.weight [32,32] | conv2.bias
+ *     | conv3.lin.weight | conv3.bias | conv4.lin.weight [1,32] | conv4.bias [1]
+ * Walks the CSR by SOURCE (rowptr_t/col_t).  The gradient w.r.t. x is not produced
+ * (use K3/K4 when it is needed).
+ * ------------------------------------------------------------------------ */
+int dgcnn_stack_bwd_supported(int32_t num_features, int64_t max_nodes);
+int64_t dgcnn_stack_num_params(int32_t num_features);
+size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features);
+int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
+                    const float* xcat, int64_t ldc, const float* x, int64_t ldx,
+                    int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
+                    const float* dis, const int32_t* gptr, int64_t num_nodes, int64_t num_graphs,
+                    int64_t max_nodes, const float* w2, const float* w3, const float* w4,
+                    int32_t norm, float* grads, int32_t* status,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -451,6 +451,68 @@ def test_fused_stack_forward_matches_oracle_and_per_layer(case):
     np.testing.assert_array_equal(pooled.detach().cpu().numpy(), ro.numpy())
 
 
+@pytest.mark.parametrize("case", STACK_CASES, ids=[c[0] for c in STACK_CASES])
+def test_fused_stack_backward_matches_oracle_and_per_layer(case):
+    """KSB (two launches) against float64 autograd of the oracle and against K3/K4.  The
+    oracle continues from OUR permutation (validated bit-exact above) so that near-tied
+    keys cannot turn a legitimate rank swap into a gradient mismatch."""
+    name, sizes, f, avg_deg, simple, k, norm = case
+    rng = np.random.RandomState(zlib.crc32(name.encode()) % (2 ** 31))
+    z, n = stack_inputs(rng, sizes, f, avg_deg, loops=True)
+    if simple:
+        z["edge_index"] = dedup_symmetric(z["edge_index"])
+    b = len(sizes)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    g = ops.build_graph(dev(z["edge_index"]), dev(z["batch"]), n, b, max_nodes=max_graph(z["batch"], b))
+    cot = torch.from_numpy(rng.randn(b, k * 97).astype(np.float32))
+
+    def run(fused_flag):
+        dg.set_fused(fused_flag)
+        try:
+            ws = [dev(z[f"w{i}"]).requires_grad_(True) for i in range(1, 5)]
+            bs = [dev(z[f"b{i}"]).requires_grad_(True) for i in range(1, 5)]
+            before = ops.LAUNCHES["stack_bwd"]
+            pooled, xcat, perm = dg.graph_conv_stack(dev(z["x"]), g, ws, bs, k, norm)
+            (pooled * cot.to(DEV)).sum().backward()
+            assert (ops.LAUNCHES["stack_bwd"] - before == 2) == fused_flag
+            return [w.grad.cpu() for w in ws], [b_.grad.cpu() for b_ in bs], perm.cpu().long()
+        finally:
+            dg.set_fused(True)
+
+    dws, dbs, perm = run(True)
+    dws_l, dbs_l, perm_l = run(False)
+    assert torch.equal(perm, perm_l)
+    wr = [torch.from_numpy(z[f"w{i}"]).double().requires_grad_(True) for i in range(1, 5)]
+    br = [torch.from_numpy(z[f"b{i}"]).double().requires_grad_(True) for i in range(1, 5)]
+    rx = orc.graph_conv_stack(torch.from_numpy(z["x"]).double(), torch.from_numpy(z["edge_index"]),
+                              wr, br, norm)
+    rpool = torch.where((perm >= 0).unsqueeze(-1), rx[perm.clamp(min=0)], rx.new_zeros(()))
+    (rpool.reshape(b, k * 97) * cot.double()).sum().backward()
+    for got, got_l, want in zip(dws + dbs, dws_l + dbs_l, [w.grad for w in wr] + [b_.grad for b_ in br]):
+        scale = max(1.0, float(want.abs().max()))
+        err = (got.double() - want).abs().max().item()
+        err_l = (got_l.double() - want).abs().max().item()
+        assert err <= 3e-5 * scale, f"fused {err:.3e} (per-layer {err_l:.3e}) scale {scale:.2e}"
+        assert err_l <= 3e-5 * scale
+
+
+def test_fused_backward_is_deterministic():
+    cfg = CONFIGS["collab"]
+    batch = make_batch("collab", num_graphs=200)
+    data = batch.to(DEV)
+    data.max_nodes = int((batch.ptr[1:] - batch.ptr[:-1]).max())
+    torch.manual_seed(3)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    grads = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        torch.nn.functional.nll_loss(model(data), data.y).backward()
+        grads.append([p.grad.clone() for p in (model.conv1.lin.weight, model.conv2.lin.weight,
+                                               model.conv3.bias, model.conv4.lin.weight)])
+    for a, b_ in zip(*grads):
+        assert torch.equal(a, b_)
+
+
 def load_into(model, oracle_model):
     model.load_state_dict(oracle_model.state_dict())     # identical key names (SURVEY D2)
     return model

@@ -7,12 +7,21 @@
 // batch -> offsets part of to_dense_batch (model.py:35).  Done ONCE per batch;
 // all four layers, forward and backward, share the result.
 //
-// Pipeline (all on `stream`, no host sync, no allocation):
-//   memset degrees -> count (+gptr) -> 3-phase exclusive scan (+dis) -> fill
-//   (atomic cursor, order arbitrary) -> per-row rank sort (ascending source id).
-// The row sort makes the CSR canonical: duplicates are equal values, so the
-// result -- and therefore every later floating-point summation order -- is
-// bit-reproducible run to run although the fill uses atomics.
+// Two pipelines, chosen ON THE DEVICE (no host sync, no allocation):
+//
+//  fast   edge_index already strictly sorted by (src,dst), loop-free and symmetric --
+//         exactly what TUDataset/PyG batches look like.  Then the CSR
+//         by source is the edge list itself (row pointers = run boundaries), and by
+//         symmetry it is also the CSR by target.  k0_fast_build writes it in one
+//         streaming pass and checks order; k0_fast_verify checks symmetry with a
+//         binary search per edge and derives dis.  Any violation sets a device flag.
+//
+//  generic  memset degrees -> count -> 3-phase exclusive scan (+dis) -> fill (atomic
+//         cursor, order arbitrary) -> per-row rank sort (ascending source id).  Always
+//         launched, but every kernel returns at once unless the flag is set.
+//         The row sort makes the CSR canonical: duplicates are equal values, so the
+//         result -- and every later floating-point summation order -- is
+//         bit-reproducible run to run although the fill uses atomics.
 #include "common.cuh"
 
 namespace dgcnn {
@@ -22,6 +31,7 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
 
 struct BuildWorkspace {
+    int32_t* flags;  // bit 0: input is not in the fast-path form, run the generic pipeline
     int32_t* indeg;
     int32_t* outdeg;
     int32_t* bsum;   // [2][nb]
@@ -41,7 +51,8 @@ __host__ inline BuildWorkspace carve_build_workspace(void* base, int64_t n, int6
         off += align_up(bytes, 256);
         return q;
     };
-    // indeg and outdeg are adjacent so that one memset clears both
+    // flags, indeg and outdeg are adjacent so that one memset clears all three
+    w.flags = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
     w.indeg = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)n));
     w.outdeg = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)n));
     w.bsum = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * 2 * (size_t)w.nb));
@@ -80,7 +91,8 @@ __global__ void __launch_bounds__(256)
 k0_count(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0,
          const int64_t* __restrict__ batch, int64_t n, int64_t num_graphs,
          int32_t* __restrict__ indeg, int32_t* __restrict__ outdeg,
-         int32_t* __restrict__ gptr, int32_t* status) {
+         int32_t* __restrict__ gptr, int32_t* status, const int32_t* gate) {
+    if (gate && !(*gate & 1)) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t e = tid; e < e0; e += stride) {
@@ -114,8 +126,9 @@ __device__ __forceinline__ int block_sum_256(int v, int* smem /*[8]*/) {
 // phase 1: per-tile sums.  grid (nb, 1 or 2); y selects in- or out-degrees
 __global__ void __launch_bounds__(kScanThreads)
 k0_scan_reduce(const int32_t* __restrict__ indeg, const int32_t* __restrict__ outdeg, int64_t n,
-               int32_t* __restrict__ bsum, int64_t nb) {
+               int32_t* __restrict__ bsum, int64_t nb, const int32_t* gate) {
     __shared__ int red[kScanThreads / 32];
+    if (gate && !(*gate & 1)) return;
     const int32_t* deg = blockIdx.y ? outdeg : indeg;
     int64_t base = (int64_t)blockIdx.x * kScanTile;
     int v = 0;
@@ -130,9 +143,10 @@ k0_scan_reduce(const int32_t* __restrict__ indeg, const int32_t* __restrict__ ou
 
 // phase 2: exclusive scan of the tile sums, one CTA per array
 __global__ void __launch_bounds__(1024)
-k0_scan_top(int32_t* __restrict__ bsum, int64_t nb) {
+k0_scan_top(int32_t* __restrict__ bsum, int64_t nb, const int32_t* gate) {
     __shared__ int wsum[32];
     __shared__ int carry_s;
+    if (gate && !(*gate & 1)) return;
     int32_t* a = bsum + blockIdx.x * nb;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
@@ -171,8 +185,9 @@ k0_scan_top(int32_t* __restrict__ bsum, int64_t nb) {
 __global__ void __launch_bounds__(kScanThreads)
 k0_scan_apply(const int32_t* __restrict__ indeg, const int32_t* __restrict__ outdeg, int64_t n,
               const int32_t* __restrict__ bsum, int64_t nb, int32_t* __restrict__ rowptr,
-              int32_t* __restrict__ rowptr_t, float* __restrict__ dis) {
+              int32_t* __restrict__ rowptr_t, float* __restrict__ dis, const int32_t* gate) {
     __shared__ int wsum[kScanThreads / 32];
+    if (gate && !(*gate & 1)) return;
     const bool transposed = blockIdx.y != 0;
     const int32_t* deg = transposed ? outdeg : indeg;
     int32_t* out = transposed ? rowptr_t : rowptr;
@@ -213,7 +228,8 @@ __global__ void __launch_bounds__(256)
 k0_fill(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0, int64_t n,
         const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowptr_t,
         int32_t* __restrict__ indeg, int32_t* __restrict__ outdeg,
-        int32_t* __restrict__ tmp_in, int32_t* __restrict__ tmp_out) {
+        int32_t* __restrict__ tmp_in, int32_t* __restrict__ tmp_out, const int32_t* gate) {
+    if (gate && !(*gate & 1)) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e0; e += stride) {
         int64_t s = src[e], d = dst[e];
@@ -232,7 +248,8 @@ k0_fill(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_
 __global__ void __launch_bounds__(256)
 k0_sort_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowptr_t, int64_t n,
              const int32_t* __restrict__ tmp_in, const int32_t* __restrict__ tmp_out,
-             int32_t* __restrict__ col, int32_t* __restrict__ col_t) {
+             int32_t* __restrict__ col, int32_t* __restrict__ col_t, const int32_t* gate) {
+    if (gate && !(*gate & 1)) return;
     const bool transposed = blockIdx.y != 0;
     const int32_t* rp = transposed ? rowptr_t : rowptr;
     const int32_t* in = transposed ? tmp_out : tmp_in;
@@ -262,6 +279,75 @@ k0_sort_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ row
             }
             if (t < deg) out[beg + rank] = v;
         }
+    }
+}
+
+// ---- fast path ---------------------------------------------------------------------
+// One streaming pass: col/col_t = targets in input order, row pointers = run boundaries
+// of the source column, graph offsets; flags bit 0 is raised on anything that is not a
+// strictly (src,dst)-sorted, loop-free, in-range edge list.  e == e0 is the sentinel that
+// closes the trailing (edge-free) rows.
+__global__ void __launch_bounds__(256)
+k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0,
+              const int64_t* __restrict__ batch, int64_t n, int64_t num_graphs,
+              int32_t* __restrict__ rowptr, int32_t* __restrict__ col,
+              int32_t* __restrict__ rowptr_t, int32_t* __restrict__ col_t,
+              int32_t* __restrict__ gptr, int32_t* flags, int32_t* status) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t e = tid; e <= e0; e += stride) {
+        int64_t s = n, d = 0;
+        if (e < e0) {
+            s = src[e];
+            d = dst[e];
+            if ((uint64_t)s >= (uint64_t)n || (uint64_t)d >= (uint64_t)n) {
+                if (status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE);
+                atomicOr(flags, 1);
+                continue;
+            }
+            col[e] = (int32_t)d;
+            if (col_t) col_t[e] = (int32_t)d;
+            if (s == d) atomicOr(flags, 1);
+        }
+        int64_t ps = -1, pd = -1;
+        if (e > 0) {
+            ps = src[e - 1];
+            pd = dst[e - 1];
+            if ((uint64_t)ps >= (uint64_t)n) { atomicOr(flags, 1); continue; }
+        }
+        if (e < e0 && !(ps < s || (ps == s && pd < d))) atomicOr(flags, 1);   // not strictly sorted
+        if (ps < s) {
+            for (int64_t r = ps + 1; r <= s; ++r) {
+                rowptr[r] = (int32_t)e;
+                if (rowptr_t) rowptr_t[r] = (int32_t)e;
+            }
+        }
+    }
+    if (gptr)
+        for (int64_t i = tid; i <= n; i += stride)
+            graph_ptr_body(batch, n, num_graphs, gptr, status, i);
+}
+
+// symmetry: every edge (s,d) must find s in row d (rows are sorted: binary search);
+// dis from the row lengths (in-degree == out-degree once symmetric)
+__global__ void __launch_bounds__(256)
+k0_fast_verify(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0, int64_t n,
+               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+               float* __restrict__ dis, int32_t* flags) {
+    if (*flags & 1) return;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < n; i += stride)
+        dis[i] = 1.0f / sqrtf((float)(rowptr[i + 1] - rowptr[i] + 1));
+    for (int64_t e = tid; e < e0; e += stride) {
+        const int32_t s = (int32_t)src[e];
+        const int64_t d = dst[e];
+        int lo = rowptr[d], hi = rowptr[d + 1];
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (col[mid] < s) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= rowptr[d + 1] || col[lo] != s) { atomicOr(flags, 1); return; }
     }
 }
 
@@ -307,29 +393,40 @@ extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, c
     const int64_t* src = edge_index;
     const int64_t* dst = edge_index + e0;
 
-    size_t deg_span = (size_t)((char*)w.outdeg - (char*)w.indeg) + sizeof(int32_t) * (size_t)n;
-    if (cudaMemsetAsync(w.indeg, 0, deg_span, st) != cudaSuccess) return DGCNN_ERR_CUDA;
+    size_t clear_span = (size_t)((char*)w.outdeg - (char*)w.flags) + sizeof(int32_t) * (size_t)n;
+    if (cudaMemsetAsync(w.flags, 0, clear_span, st) != cudaSuccess) return DGCNN_ERR_CUDA;
 
-    int64_t work = e0 > n + 1 ? e0 : n + 1;
+    // fast path (sorted + symmetric input), verified on the device
+    int64_t work = e0 + 1 > n + 1 ? e0 + 1 : n + 1;
+    k0_fast_build<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, batch, n, num_graphs, rowptr,
+                                                          col, rowptr_t, col_t, gptr, w.flags, status);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    k0_fast_verify<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, n, rowptr, col, dis, w.flags);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+
+    // generic path: every kernel returns immediately unless the flag was raised
+    const int32_t* gate = w.flags;
     k0_count<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, batch, n, num_graphs, w.indeg,
-                                                     transposed ? w.outdeg : nullptr, gptr, status);
+                                                     transposed ? w.outdeg : nullptr, nullptr, status,
+                                                     gate);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
 
     dim3 scan_grid((unsigned)w.nb, transposed ? 2 : 1);
-    k0_scan_reduce<<<scan_grid, kScanThreads, 0, st>>>(w.indeg, w.outdeg, n, w.bsum, w.nb);
+    k0_scan_reduce<<<scan_grid, kScanThreads, 0, st>>>(w.indeg, w.outdeg, n, w.bsum, w.nb, gate);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    k0_scan_top<<<transposed ? 2 : 1, 1024, 0, st>>>(w.bsum, w.nb);
+    k0_scan_top<<<transposed ? 2 : 1, 1024, 0, st>>>(w.bsum, w.nb, gate);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     k0_scan_apply<<<scan_grid, kScanThreads, 0, st>>>(w.indeg, w.outdeg, n, w.bsum, w.nb, rowptr,
-                                                      rowptr_t, dis);
+                                                      rowptr_t, dis, gate);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
 
     if (e0 > 0) {
         k0_fill<<<grid_for(e0, 256, 8), 256, 0, st>>>(src, dst, e0, n, rowptr, rowptr_t, w.indeg,
-                                                      w.outdeg, w.tmp_in, w.tmp_out);
+                                                      w.outdeg, w.tmp_in, w.tmp_out, gate);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         dim3 sort_grid((unsigned)grid_for(n, 8, 8), transposed ? 2 : 1);
-        k0_sort_rows<<<sort_grid, 256, 0, st>>>(rowptr, rowptr_t, n, w.tmp_in, w.tmp_out, col, col_t);
+        k0_sort_rows<<<sort_grid, 256, 0, st>>>(rowptr, rowptr_t, n, w.tmp_in, w.tmp_out, col, col_t,
+                                                gate);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     return DGCNN_OK;

@@ -118,7 +118,7 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
                                    _ptr(dis), _ptr(gptr), _ptr(status),
                                    _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "build_graph")
-    LAUNCHES["build_graph"] += 6 if e > 0 else 4
+    LAUNCHES["build_graph"] += 8 if e > 0 else 6
     return Graph(rowptr, col, rowptr_t, col_t, dis, gptr, status, n, b, int(max_nodes))
 
 

@@ -479,34 +479,43 @@ def test_fused_stack_backward_matches_oracle_and_per_layer(case):
         finally:
             dg.set_fused(True)
 
-    dws, dbs, perm = run(True)
-    dws_l, dbs_l, perm_l = run(False)
-    assert torch.equal(perm, perm_l)
-    wr = [torch.from_numpy(z[f"w{i}"]).double().requires_grad_(True) for i in range(1, 5)]
-    br = [torch.from_numpy(z[f"b{i}"]).double().requires_grad_(True) for i in range(1, 5)]
-    rx = orc.graph_conv_stack(torch.from_numpy(z["x"]).double(), torch.from_numpy(z["edge_index"]),
-                              wr, br, norm)
-    rpool = torch.where((perm >= 0).unsqueeze(-1), rx[perm.clamp(min=0)], rx.new_zeros(()))
-    (rpool.reshape(b, k * 97) * cot.double()).sum().backward()
-    for got, got_l, want in zip(dws + dbs, dws_l + dbs_l, [w.grad for w in wr] + [b_.grad for b_ in br]):
-        scale = max(1.0, float(want.abs().max()))
-        err = (got.double() - want).abs().max().item()
-        err_l = (got_l.double() - want).abs().max().item()
-        assert err <= 3e-5 * scale, f"fused {err:.3e} (per-layer {err_l:.3e}) scale {scale:.2e}"
-        assert err_l <= 3e-5 * scale
+    def oracle_grads(perm):
+        wr = [torch.from_numpy(z[f"w{i}"]).double().requires_grad_(True) for i in range(1, 5)]
+        br = [torch.from_numpy(z[f"b{i}"]).double().requires_grad_(True) for i in range(1, 5)]
+        rx = orc.graph_conv_stack(torch.from_numpy(z["x"]).double(), torch.from_numpy(z["edge_index"]),
+                                  wr, br, norm)
+        rpool = torch.where((perm >= 0).unsqueeze(-1), rx[perm.clamp(min=0)], rx.new_zeros(()))
+        (rpool.reshape(b, k * 97) * cot.double()).sum().backward()
+        return [w.grad for w in wr] + [b_.grad for b_ in br]
+
+    # the two CUDA paths round x_4 differently, so exactly tied keys may rank differently:
+    # each path is compared with the oracle continued from ITS OWN permutation
+    for fused_flag in (True, False):
+        dws, dbs, perm = run(fused_flag)
+        for got, want in zip(dws + dbs, oracle_grads(perm)):
+            scale = max(1.0, float(want.abs().max()))
+            err = (got.double() - want).abs().max().item()
+            assert err <= 3e-5 * scale, f"fused={fused_flag}: {err:.3e} scale {scale:.2e}"
 
 
 def test_fused_backward_is_deterministic():
+    """Same inputs, same cotangent -> bit-identical parameter gradients (fixed graph->CTA
+    assignment, ordered reduction, no float atomics).  The cotangent is fixed rather than
+    taken through the dense tail because cuDNN's wgrad is not bit-reproducible."""
     cfg = CONFIGS["collab"]
     batch = make_batch("collab", num_graphs=200)
     data = batch.to(DEV)
     data.max_nodes = int((batch.ptr[1:] - batch.ptr[:-1]).max())
     torch.manual_seed(3)
     model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    cot = torch.randn(200, cfg.k * 97, device=DEV)
     grads = []
     for _ in range(2):
         model.zero_grad(set_to_none=True)
-        torch.nn.functional.nll_loss(model(data), data.y).backward()
+        before = ops.LAUNCHES["stack_bwd"]
+        pooled, _, _ = model.hot_path(data.x, model.build_graph(data))
+        (pooled * cot).sum().backward()
+        assert ops.LAUNCHES["stack_bwd"] - before == 2
         grads.append([p.grad.clone() for p in (model.conv1.lin.weight, model.conv2.lin.weight,
                                                model.conv3.bias, model.conv4.lin.weight)])
     for a, b_ in zip(*grads):

@@ -35,19 +35,6 @@
 
 namespace dgcnn {
 
-struct StackFwdParams {
-    const float* x; int64_t ldx; int f;
-    const int32_t* rowptr; const int32_t* col; const float* dis; const int32_t* gptr;
-    int num_graphs;
-    const float* w1; const float* b1; const float* w2; const float* b2;
-    const float* w3; const float* b3; const float* w4; const float* b4;
-    float* xcat; int64_t ldc;
-    float* pooled; int32_t* perm; int k;
-    int norm; int nmax;
-    int32_t* counter;   // work queue head, zeroed by the host wrapper
-    int32_t* status;    // optional
-};
-
 // shared-memory carve-up, in 4-byte words; every region starts 16-byte aligned
 struct StackLayout {
     int w1t, w2t, w3t, w4, b1, b2, b3, colsum, red, bufA, bufB, bm, cs, rs, v, key, order, rp, total;
@@ -334,40 +321,23 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwd
 
 using namespace dgcnn;
 
-extern "C" int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes) {
+int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes) {
     if (num_features < 1 || num_features > kMaxF || max_nodes < 1 || max_nodes > 4096) return 0;
     const int nmax = stack_nmax_for(max_nodes);
     const StackLayout L = stack_layout(num_features, nmax, stack_threads_for(nmax) / 32);
     return (size_t)L.total * 4 + 64 <= (size_t)kSmemBudget ? 1 : 0;
 }
 
-extern "C" size_t dgcnn_stack_fwd_workspace_bytes(void) { return 256; }
-
-extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
-                               const int32_t* rowptr, const int32_t* col, const float* dis,
-                               const int32_t* gptr, int64_t num_nodes, int64_t num_graphs,
-                               int64_t max_nodes,
-                               const float* w1, const float* b1, const float* w2, const float* b2,
-                               const float* w3, const float* b3, const float* w4, const float* b4,
-                               float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
-                               int32_t norm, int32_t* status, void* workspace, size_t workspace_bytes,
-                               void* stream) {
-    if (num_nodes < 0 || num_graphs < 0 || k < 1 || num_features < 1 || ldx < num_features ||
-        ldc < kCat)
-        return DGCNN_ERR_INVALID_ARGUMENT;
-    if (norm != DGCNN_NORM_SYM && norm != DGCNN_NORM_RW) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (num_graphs == 0) return DGCNN_OK;
-    if (!dgcnn_stack_fwd_supported(num_features, max_nodes)) return DGCNN_ERR_UNSUPPORTED;
-    if (num_graphs >= INT32_MAX || num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
-    if (!rowptr || !dis || !gptr || !w1 || !w2 || !w3 || !w4 || !xcat || !pooled || !perm ||
-        (num_nodes > 0 && !x))
-        return DGCNN_ERR_INVALID_ARGUMENT;
-    if (!workspace || workspace_bytes < dgcnn_stack_fwd_workspace_bytes()) return DGCNN_ERR_WORKSPACE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    uintptr_t aligned = ((uintptr_t)workspace + 127) & ~(uintptr_t)127;
-    int32_t* counter = reinterpret_cast<int32_t*>(aligned);
-    if (cudaMemsetAsync(counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
-
+// FMA-gather variant of dgcnn_stack_fwd (argument checks and the work-queue reset are
+// done by the dispatcher in graph_stack_mma.cu)
+int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const int32_t* rowptr,
+                        const int32_t* col, const float* dis, const int32_t* gptr, int64_t num_nodes,
+                        int64_t num_graphs, int64_t max_nodes, const float* w1, const float* b1,
+                        const float* w2, const float* b2, const float* w3, const float* b3,
+                        const float* w4, const float* b4, float* xcat, int64_t ldc, float* pooled,
+                        int32_t* perm, int32_t k, int32_t norm, int32_t* status, int32_t* counter,
+                        cudaStream_t st) {
+    (void)num_nodes;
     StackFwdParams p{};
     p.x = x; p.ldx = ldx; p.f = num_features;
     p.rowptr = rowptr; p.col = col; p.dis = dis; p.gptr = gptr; p.num_graphs = (int)num_graphs;

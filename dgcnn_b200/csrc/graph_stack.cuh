@@ -14,6 +14,20 @@ constexpr int kMaxF = 128;
 constexpr int kSmemBudget = 227 * 1024;
 
 
+struct StackFwdParams {
+    const float* x; int64_t ldx; int f;
+    const int32_t* rowptr; const int32_t* col; const float* dis; const int32_t* gptr;
+    int num_graphs;
+    const float* w1; const float* b1; const float* w2; const float* b2;
+    const float* w3; const float* b3; const float* w4; const float* b4;
+    float* xcat; int64_t ldc;
+    float* pooled; int32_t* perm; int k;
+    int norm; int nmax;
+    int32_t* counter;   // work queue head, zeroed by the host wrapper
+    int32_t* status;    // optional
+};
+
+
 __host__ __device__ inline int al4(int v) { return (v + 3) & ~3; }
 
 inline int stack_threads_for(int nmax) { return nmax <= 64 ? 128 : (nmax <= 160 ? 256 : 512); }

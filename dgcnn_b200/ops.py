@@ -8,6 +8,7 @@ key only: a CPU tensor raises, there is no CPU path).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -18,7 +19,10 @@ from . import _lib
 
 NORM_SYM, NORM_RW = 0, 1
 ACT_NONE, ACT_TANH = 0, 1
-GRAPH_BAD_EDGE, GRAPH_BAD_BATCH = 1, 2
+GRAPH_BAD_EDGE, GRAPH_BAD_BATCH, GRAPH_RANGE = 1, 2, 4
+STACK_MMA, STACK_FMA = 0, 1
+# implementation of the fused forward; tests flip it to cross-check the two kernels
+STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower() == "fma" else STACK_MMA
 
 # kernels launched by this process through the C ABI (memsets not counted); bench.py
 # reads it to report `gpu_launches`.  Keyed by entry point.
@@ -85,6 +89,9 @@ class Graph:
             raise ValueError("dgcnn_b200: edge_index holds node ids outside [0, num_nodes)")
         if s & GRAPH_BAD_BATCH:
             raise ValueError("dgcnn_b200: batch must be non-decreasing with ids in [0, num_graphs)")
+        if s & GRAPH_RANGE:
+            raise ValueError("dgcnn_b200: projected input features exceed the fp16 split range "
+                             "(|c_j * x_j W1^T| > 6e4); use the FMA variant or the per-layer path")
 
 
 def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num_graphs: int = 0,
@@ -265,7 +272,7 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
                                  _ptr(ws[0]), _ptr(bs[0]), _ptr(ws[1]), _ptr(bs[1]),
                                  _ptr(ws[2]), _ptr(bs[2]), _ptr(ws[3]), _ptr(bs[3]),
                                  _ptr(xcat), 97, _ptr(pooled), _ptr(perm), int(k), int(norm),
-                                 _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
+                                 int(STACK_VARIANT), _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
     _lib.check(rc, "stack_fwd")
     LAUNCHES["stack_fwd"] += 1 if b > 0 else 0
     return pooled, xcat, perm

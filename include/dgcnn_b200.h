@@ -54,6 +54,11 @@ typedef enum dgcnn_act { DGCNN_ACT_NONE = 0, DGCNN_ACT_TANH = 1 } dgcnn_act;
  * (graph validation happens on the device, without a host sync). */
 #define DGCNN_GRAPH_BAD_EDGE 1    /* an edge_index entry outside [0, N)      */
 #define DGCNN_GRAPH_BAD_BATCH 2   /* batch not non-decreasing / outside [0,B) */
+#define DGCNN_GRAPH_RANGE 4       /* a projected feature exceeded the fp16 split range */
+
+/* Implementations of the fused forward (dgcnn_stack_fwd `variant`). */
+#define DGCNN_STACK_MMA 0         /* tensor-core aggregation + projection (default)    */
+#define DGCNN_STACK_FMA 1         /* fp32 FMA gather through shared memory            */
 
 int dgcnn_abi_version(void);
 const char* dgcnn_status_string(int status);
@@ -160,7 +165,7 @@ int dgcnn_sort_pool_bwd(const float* dout, const int32_t* perm, int64_t num_grap
  *   xcat [N,97] = cat(tanh(conv1..4))  and  (pooled [B,k*97], perm [B,k]) =
  *   SortAggregation(k)(xcat) -- same contracts as K1 and K2 above.
  * One CTA per graph; adjacency, features and sort keys stay in shared memory
- * (see dgcnn_b200/csrc/graph_stack.cu).  Needs the size of the largest graph
+ * (see dgcnn_b200/csrc/graph_stack_mma.cu and graph_stack.cu for the two variants).  Needs the size of the largest graph
  * (`max_nodes`, known on the host from the batch's ptr): graphs must fit the
  * shared-memory budget, which dgcnn_stack_fwd_supported() reports (1/0, pure host
  * arithmetic).  When it returns 0 use K1 x 4 + K2.
@@ -174,7 +179,7 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                     const float* w1, const float* b1, const float* w2, const float* b2,
                     const float* w3, const float* b3, const float* w4, const float* b4,
                     float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
-                    int32_t norm, int32_t* status,
+                    int32_t norm, int32_t variant, int32_t* status,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------

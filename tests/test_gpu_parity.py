@@ -342,12 +342,16 @@ def test_sort_pool_backward_and_module():
 
 
 # ------------------------------------------------------------------ stack + model
-@pytest.fixture(params=[True, False], ids=["fused", "per-layer"])
+@pytest.fixture(params=["fused-mma", "fused-fma", "per-layer"])
 def fused(request):
-    """Both CUDA implementations of the hot path: the one-launch fused stack kernel
-    (graph_stack.cu) and the per-layer kernels (graph_conv.cu + sort_pool.cu)."""
-    dg.set_fused(request.param)
+    """All CUDA implementations of the hot path: the one-launch fused stack kernel in its
+    tensor-core (graph_stack_mma.cu) and FMA-gather (graph_stack.cu) variants, and the
+    per-layer kernels (graph_conv.cu + sort_pool.cu)."""
+    dg.set_fused(request.param != "per-layer")
+    old = ops.STACK_VARIANT
+    ops.STACK_VARIANT = ops.STACK_FMA if request.param == "fused-fma" else ops.STACK_MMA
     yield request.param
+    ops.STACK_VARIANT = old
     dg.set_fused(True)
 
 
@@ -423,21 +427,26 @@ STACK_CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", ["mma", "fma"])
 @pytest.mark.parametrize("case", STACK_CASES, ids=[c[0] for c in STACK_CASES])
-def test_fused_stack_forward_matches_oracle_and_per_layer(case):
+def test_fused_stack_forward_matches_oracle_and_per_layer(case, variant):
     name, sizes, f, avg_deg, simple, k, norm = case
     rng = np.random.RandomState(zlib.crc32(name.encode()) % (2 ** 31))
     z, n = stack_inputs(rng, sizes, f, avg_deg, loops=True)
     if simple:
         z["edge_index"] = dedup_symmetric(z["edge_index"])
     b = len(sizes)
-    dg.set_fused(True)
-    x, ws, bs, g, pooled, xcat, perm = run_stack(z, norm, k, b)
     dg.set_fused(False)
     try:
         _, _, _, _, pooled_l, xcat_l, perm_l = run_stack(z, norm, k, b)
     finally:
         dg.set_fused(True)
+    old = ops.STACK_VARIANT
+    ops.STACK_VARIANT = ops.STACK_FMA if variant == "fma" else ops.STACK_MMA
+    try:
+        x, ws, bs, g, pooled, xcat, perm = run_stack(z, norm, k, b)
+    finally:
+        ops.STACK_VARIANT = old
     ref = orc.graph_conv_stack(torch.from_numpy(z["x"]).double(), torch.from_numpy(z["edge_index"]),
                                [torch.from_numpy(z[f"w{i}"]).double() for i in range(1, 5)],
                                [torch.from_numpy(z[f"b{i}"]).double() for i in range(1, 5)], norm)

@@ -31,7 +31,7 @@ SIGNATURES = {
     "dgcnn_build_graph_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dgcnn_build_graph": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                     c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
     "dgcnn_graph_ptr": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "dgcnn_graph_conv_fwd": (c_int32, [c_void_p, c_int64, c_int32,
@@ -57,7 +57,7 @@ SIGNATURES = {
     "dgcnn_stack_fwd_workspace_bytes": (c_size_t, []),
     "dgcnn_stack_fwd": (c_int32, [c_void_p, c_int64, c_int32,
                                   c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_int64, c_int64, c_int64,
+                                  c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int32,
@@ -69,7 +69,7 @@ SIGNATURES = {
     "dgcnn_stack_bwd": (c_int32, [c_void_p, c_void_p, c_int32,
                                   c_void_p, c_int64, c_void_p, c_int64,
                                   c_int32, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_int64, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_int64, c_void_p, c_void_p, c_void_p,
                                   c_int32, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),

@@ -328,6 +328,29 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
             graph_ptr_body(batch, n, num_graphs, gptr, status, i);
 }
 
+// Processing order for the per-graph kernels: graphs by DESCENDING size (longest first
+// keeps the tail of the dynamic work queue short).  One CTA, rank sort over <= 4096 sizes.
+constexpr int kMaxOrderGraphs = 4096;
+__global__ void __launch_bounds__(1024)
+k0_graph_order(const int32_t* __restrict__ gptr, int num_graphs, int32_t* __restrict__ gorder) {
+    __shared__ int sizes[kMaxOrderGraphs];
+    if (num_graphs > kMaxOrderGraphs) {
+        for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) gorder[g] = g;
+        return;
+    }
+    for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) sizes[g] = gptr[g + 1] - gptr[g];
+    __syncthreads();
+    for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) {
+        const int mine = sizes[g];
+        int rank = 0;
+        for (int h = 0; h < num_graphs; ++h) {
+            const int other = sizes[h];
+            rank += (other > mine) || (other == mine && h < g);
+        }
+        gorder[rank] = g;
+    }
+}
+
 // symmetry: every edge (s,d) must find s in row d (rows are sorted: binary search);
 // dis from the row lengths (in-degree == out-degree once symmetric)
 __global__ void __launch_bounds__(256)
@@ -375,7 +398,7 @@ extern "C" int dgcnn_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t 
 extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, const int64_t* batch,
                                  int64_t num_nodes, int64_t num_graphs, int32_t* rowptr,
                                  int32_t* col, int32_t* rowptr_t, int32_t* col_t, float* dis,
-                                 int32_t* gptr, int32_t* status, void* workspace,
+                                 int32_t* gptr, int32_t* gorder, int32_t* status, void* workspace,
                                  size_t workspace_bytes, void* stream) {
     const int64_t n = num_nodes, e0 = num_edges;
     if (n < 0 || e0 < 0 || num_graphs < 0 || !rowptr || !dis) return DGCNN_ERR_INVALID_ARGUMENT;
@@ -383,6 +406,7 @@ extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, c
     if (rowptr_t && e0 > 0 && !col_t) return DGCNN_ERR_INVALID_ARGUMENT;
     if (!rowptr_t && col_t) return DGCNN_ERR_INVALID_ARGUMENT;
     if (gptr && n > 0 && !batch) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (gorder && !gptr) return DGCNN_ERR_INVALID_ARGUMENT;
     if (n >= INT32_MAX || e0 >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < dgcnn_build_graph_workspace_bytes(n, e0))
         return DGCNN_ERR_WORKSPACE;
@@ -403,6 +427,10 @@ extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, c
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     k0_fast_verify<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, n, rowptr, col, dis, w.flags);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (gorder && num_graphs > 0) {
+        k0_graph_order<<<1, 1024, 0, st>>>(gptr, (int)num_graphs, gorder);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
 
     // generic path: every kernel returns immediately unless the flag was raised
     const int32_t* gate = w.flags;

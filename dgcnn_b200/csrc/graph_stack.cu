@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwd
     for (;;) {
         if (tid == 0) { s_graph = atomicAdd(p.counter, 1); s_dup = 0; }
         __syncthreads();
-        const int g = s_graph;
-        if (g >= p.num_graphs) break;
+        if (s_graph >= p.num_graphs) break;
+        const int g = p.gorder ? p.gorder[s_graph] : s_graph;
         const int base = p.gptr[g];
         int n = p.gptr[g + 1] - base;
         if (n > nmax) {                       // host promised this cannot happen
@@ -308,9 +308,24 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwd
         // ---- gather the k winners (rows of x_cat this CTA just wrote: L2 hits) ------------
         // flat index over keep*97 elements: contiguous writes, row-contiguous reads, and
         // several independent loads in flight per thread
-        for (int idx = tid; idx < keep * kCat; idx += nthreads) {
-            const int r = idx / kCat, c = idx - r * kCat;
-            pooled_g[idx] = xc[(int64_t)order[r] * p.ldc + c];
+        {
+            const int total = keep * kCat;
+            for (int i0 = tid; i0 < total; i0 += nthreads * 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = i0 + u * nthreads;
+                    if (idx < total) {
+                        const int r = idx / kCat, c = idx - r * kCat;
+                        v[u] = xc[(int64_t)order[r] * p.ldc + c];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = i0 + u * nthreads;
+                    if (idx < total) pooled_g[idx] = v[u];
+                }
+            }
         }
         for (int r = tid; r < keep; r += nthreads) perm_g[r] = base + order[r];
         __syncthreads();   // shared buffers are reused by the next graph
@@ -331,8 +346,9 @@ int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes) {
 // FMA-gather variant of dgcnn_stack_fwd (argument checks and the work-queue reset are
 // done by the dispatcher in graph_stack_mma.cu)
 int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const int32_t* rowptr,
-                        const int32_t* col, const float* dis, const int32_t* gptr, int64_t num_nodes,
-                        int64_t num_graphs, int64_t max_nodes, const float* w1, const float* b1,
+                        const int32_t* col, const float* dis, const int32_t* gptr, const int32_t* gorder,
+                        int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w1,
+                        const float* b1,
                         const float* w2, const float* b2, const float* w3, const float* b3,
                         const float* w4, const float* b4, float* xcat, int64_t ldc, float* pooled,
                         int32_t* perm, int32_t k, int32_t norm, int32_t* status, int32_t* counter,
@@ -344,7 +360,7 @@ int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.w4 = w4; p.b4 = b4;
     p.xcat = xcat; p.ldc = ldc; p.pooled = pooled; p.perm = perm; p.k = k;
     p.norm = norm; p.nmax = stack_nmax_for(max_nodes);
-    p.counter = counter; p.status = status;
+    p.gorder = gorder; p.counter = counter; p.status = status;
 
     const int threads = stack_threads_for(p.nmax);
     const size_t smem = (size_t)stack_layout(p.f, p.nmax, threads / 32).total * 4;

@@ -27,7 +27,7 @@ struct StackBwdParams {
     const float* xcat; int64_t ldc;
     const float* x; int64_t ldx; int f;
     const int32_t* rowptr_t; const int32_t* col_t; const float* dis; const int32_t* gptr;
-    int num_graphs;
+    const int32_t* gorder; int num_graphs;
     const float* w2; const float* w3; const float* w4;
     int norm; int nmax;
     float* partials;     // [gridDim.x][P]
@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_bwd_kernel(StackBwd
     const int dww = nwarps >= 8 ? 4 : nwarps;
     const bool split = nwarps >= 8;
 
-    for (int g = blockIdx.x; g < p.num_graphs; g += gridDim.x) {     // fixed order: deterministic
+    for (int gq = blockIdx.x; gq < p.num_graphs; gq += gridDim.x) {  // fixed order: deterministic
+        const int g = p.gorder ? p.gorder[gq] : gq;
         const int base = p.gptr[g];
         int n = p.gptr[g + 1] - base;
         if (n > nmax) {
@@ -348,8 +349,8 @@ extern "C" size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features) {
 extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                                const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                                int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
-                               const float* dis, const int32_t* gptr, int64_t num_nodes,
-                               int64_t num_graphs, int64_t max_nodes, const float* w2,
+                               const float* dis, const int32_t* gptr, const int32_t* gorder,
+                               int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w2,
                                const float* w3, const float* w4, int32_t norm, float* grads,
                                int32_t* status, void* workspace, size_t workspace_bytes,
                                void* stream) {
@@ -373,7 +374,7 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
     StackBwdParams p{};
     p.dpooled = dpooled; p.perm = perm; p.k = k; p.xcat = xcat; p.ldc = ldc;
     p.x = x; p.ldx = ldx; p.f = num_features;
-    p.rowptr_t = rowptr_t; p.col_t = col_t; p.dis = dis; p.gptr = gptr; p.num_graphs = (int)num_graphs;
+    p.rowptr_t = rowptr_t; p.col_t = col_t; p.dis = dis; p.gptr = gptr; p.gorder = gorder; p.num_graphs = (int)num_graphs;
     p.w2 = w2; p.w3 = w3; p.w4 = w4; p.norm = norm; p.nmax = stack_nmax_for(max_nodes);
     p.partials = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     p.status = status;

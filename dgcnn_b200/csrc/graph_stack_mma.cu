@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) stack_fwd_mma_kernel(StackFwdP
     for (;;) {
         if (tid == 0) { s_graph = atomicAdd(p.counter, 1); s_dup = 0; }
         __syncthreads();
-        const int gi = s_graph;
-        if (gi >= p.num_graphs) break;
+        if (s_graph >= p.num_graphs) break;
+        const int gi = p.gorder ? p.gorder[s_graph] : s_graph;
         const int base = p.gptr[gi];
         int n = p.gptr[gi + 1] - base;
         if (n > nmax) {
@@ -456,9 +456,24 @@ __global__ void __launch_bounds__(kMmaThreads, 2) stack_fwd_mma_kernel(StackFwdP
         __syncthreads();
 
         // ---- gather the k winners (rows of x_cat this CTA just wrote: L2 hits) ------------
-        for (int idx = tid; idx < keep * kCat; idx += nthreads) {
-            const int r = idx / kCat, c = idx - r * kCat;
-            pooled_g[idx] = xc[(int64_t)order[r] * p.ldc + c];
+        {
+            const int total = keep * kCat;
+            for (int i0 = tid; i0 < total; i0 += nthreads * 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = i0 + u * nthreads;
+                    if (idx < total) {
+                        const int r = idx / kCat, c = idx - r * kCat;
+                        v[u] = xc[(int64_t)order[r] * p.ldc + c];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = i0 + u * nthreads;
+                    if (idx < total) pooled_g[idx] = v[u];
+                }
+            }
         }
         for (int r = tid; r < keep; r += nthreads) perm_g[r] = base + order[r];
         __syncthreads();
@@ -471,8 +486,9 @@ using namespace dgcnn;
 
 // implemented in graph_stack.cu (FMA gather variant)
 int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const int32_t* rowptr,
-                        const int32_t* col, const float* dis, const int32_t* gptr, int64_t num_nodes,
-                        int64_t num_graphs, int64_t max_nodes, const float* w1, const float* b1,
+                        const int32_t* col, const float* dis, const int32_t* gptr, const int32_t* gorder,
+                        int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w1,
+                        const float* b1,
                         const float* w2, const float* b2, const float* w3, const float* b3,
                         const float* w4, const float* b4, float* xcat, int64_t ldc, float* pooled,
                         int32_t* perm, int32_t k, int32_t norm, int32_t* status, int32_t* counter,
@@ -493,8 +509,8 @@ extern "C" size_t dgcnn_stack_fwd_workspace_bytes(void) { return 256; }
 
 extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                                const int32_t* rowptr, const int32_t* col, const float* dis,
-                               const int32_t* gptr, int64_t num_nodes, int64_t num_graphs,
-                               int64_t max_nodes,
+                               const int32_t* gptr, const int32_t* gorder, int64_t num_nodes,
+                               int64_t num_graphs, int64_t max_nodes,
                                const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* w3, const float* b3, const float* w4, const float* b4,
                                float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
@@ -519,7 +535,7 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     int32_t* counter = reinterpret_cast<int32_t*>(aligned);
     if (cudaMemsetAsync(counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
     if (variant == DGCNN_STACK_FMA)
-        return dgcnn_stack_fwd_fma(x, ldx, num_features, rowptr, col, dis, gptr, num_nodes, num_graphs,
+        return dgcnn_stack_fwd_fma(x, ldx, num_features, rowptr, col, dis, gptr, gorder, num_nodes, num_graphs,
                                    max_nodes, w1, b1, w2, b2, w3, b3, w4, b4, xcat, ldc, pooled, perm, k,
                                    norm, status, counter, st);
 
@@ -529,7 +545,7 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.w4 = w4; p.b4 = b4;
     p.xcat = xcat; p.ldc = ldc; p.pooled = pooled; p.perm = perm; p.k = k;
     p.norm = norm; p.nmax = stack_nmax_for(max_nodes);
-    p.counter = counter; p.status = status;
+    p.gorder = gorder; p.counter = counter; p.status = status;
     const size_t smem = (size_t)mma_layout(p.f, p.nmax).total;
     if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)

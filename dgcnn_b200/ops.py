@@ -77,6 +77,7 @@ class Graph:
     col_t: Optional[Tensor]
     dis: Tensor
     gptr: Optional[Tensor]
+    gorder: Optional[Tensor]   # graph ids by descending size (work order of the per-graph kernels)
     status: Tensor
     num_nodes: int
     num_graphs: int
@@ -116,17 +117,18 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
     col_t = torch.empty(max(e, 1), **i32) if transpose else None
     dis = torch.empty(n, dtype=torch.float32, device=dev)
     gptr = torch.empty(b + 1, **i32) if batch is not None else None
+    gorder = torch.empty(max(b, 1), **i32) if batch is not None else None
     status = torch.zeros(1, **i32)
     wbytes = lib.dgcnn_build_graph_workspace_bytes(n, e)
     ws = _workspace(wbytes, dev)
     with torch.cuda.device(dev):
         rc = lib.dgcnn_build_graph(_ptr(edge_index), e, _ptr(batch), n, b,
                                    _ptr(rowptr), _ptr(col), _ptr(rowptr_t), _ptr(col_t),
-                                   _ptr(dis), _ptr(gptr), _ptr(status),
+                                   _ptr(dis), _ptr(gptr), _ptr(gorder), _ptr(status),
                                    _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "build_graph")
-    LAUNCHES["build_graph"] += 8 if e > 0 else 6
-    return Graph(rowptr, col, rowptr_t, col_t, dis, gptr, status, n, b, int(max_nodes))
+    LAUNCHES["build_graph"] += (8 if e > 0 else 6) + (1 if batch is not None and b > 0 else 0)
+    return Graph(rowptr, col, rowptr_t, col_t, dis, gptr, gorder, status, n, b, int(max_nodes))
 
 
 def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
@@ -268,8 +270,8 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
     wsp = _workspace(lib.dgcnn_stack_fwd_workspace_bytes(), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_fwd(_ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr), _ptr(graph.col),
-                                 _ptr(graph.dis), _ptr(graph.gptr), n, b, int(graph.max_nodes),
-                                 _ptr(ws[0]), _ptr(bs[0]), _ptr(ws[1]), _ptr(bs[1]),
+                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder), n, b,
+                                 int(graph.max_nodes), _ptr(ws[0]), _ptr(bs[0]), _ptr(ws[1]), _ptr(bs[1]),
                                  _ptr(ws[2]), _ptr(bs[2]), _ptr(ws[3]), _ptr(bs[3]),
                                  _ptr(xcat), 97, _ptr(pooled), _ptr(perm), int(k), int(norm),
                                  int(STACK_VARIANT), _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
@@ -304,8 +306,8 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_bwd(_ptr(dpooled), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
                                  _ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr_t), _ptr(graph.col_t),
-                                 _ptr(graph.dis), _ptr(graph.gptr), n, b, int(graph.max_nodes),
-                                 _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm), _ptr(grads),
+                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder), n, b,
+                                 int(graph.max_nodes), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm), _ptr(grads),
                                  _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
     _lib.check(rc, "stack_bwd")
     LAUNCHES["stack_bwd"] += 2 if (b > 0 and n > 0) else 0
@@ -331,7 +333,7 @@ def register_torch_ops() -> None:
         return
     lib = torch.library.Library("dgcnn_b200", "DEF")
     lib.define("build_graph(Tensor edge_index, Tensor batch, int num_graphs, bool transpose) -> "
-               "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
+               "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
     lib.define("graph_conv_fwd(Tensor x, Tensor rowptr, Tensor col, Tensor dis, Tensor weight, "
                "Tensor? bias, int norm, int act, Tensor(a!) out) -> ()")
     lib.define("graph_conv_bwd(Tensor dy, Tensor? y, Tensor x, Tensor rowptr_t, Tensor col_t, "
@@ -344,7 +346,7 @@ def register_torch_ops() -> None:
         g = build_graph(edge_index, batch, batch.numel(), num_graphs, transpose)
         empty = torch.empty(0, dtype=torch.int32, device=edge_index.device)
         return (g.rowptr, g.col, g.rowptr_t if transpose else empty,
-                g.col_t if transpose else empty, g.dis, g.gptr, g.status)
+                g.col_t if transpose else empty, g.dis, g.gptr, g.gorder, g.status)
 
     def _conv_bwd(dy, y, x, rowptr_t, col_t, dis, weight, norm, act, dx, accumulate):
         return graph_conv_bwd(dy, y, x, rowptr_t, col_t, dis, weight, norm, act, dx, accumulate)

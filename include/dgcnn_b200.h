@@ -80,6 +80,8 @@ const char* dgcnn_status_string(int status);
  *                            pass both NULL to skip
  *   dis     [N]   (1 + in_degree)^-1/2     (the implicit self loop is the +1)
  *   gptr    [B+1] node offset of every graph (empty graphs allowed)
+ *   gorder  [B]   optional: graph ids by descending size, the order in which the
+ *                 per-graph kernels (KS, KSB) drain their work queue
  *   status  optional device int32, OR-ed with DGCNN_GRAPH_* on bad input
  * Only the first rowptr[N] entries of col are meaningful.
  * Limits: N, E < 2^31.
@@ -88,7 +90,7 @@ size_t dgcnn_build_graph_workspace_bytes(int64_t num_nodes, int64_t num_edges);
 int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges,
                       const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
                       int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
-                      float* dis, int32_t* gptr, int32_t* status,
+                      float* dis, int32_t* gptr, int32_t* gorder, int32_t* status,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* gptr alone (SortAggregation called without a graph: model.py:35's `batch`). */
@@ -175,7 +177,8 @@ int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes);
 size_t dgcnn_stack_fwd_workspace_bytes(void);
 int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                     const int32_t* rowptr, const int32_t* col, const float* dis,
-                    const int32_t* gptr, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                    const int32_t* gptr, const int32_t* gorder, int64_t num_nodes,
+                    int64_t num_graphs, int64_t max_nodes,
                     const float* w1, const float* b1, const float* w2, const float* b2,
                     const float* w3, const float* b3, const float* w4, const float* b4,
                     float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
@@ -199,7 +202,8 @@ size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features);
 int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                     const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                     int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
-                    const float* dis, const int32_t* gptr, int64_t num_nodes, int64_t num_graphs,
+                    const float* dis, const int32_t* gptr, const int32_t* gorder,
+                    int64_t num_nodes, int64_t num_graphs,
                     int64_t max_nodes, const float* w2, const float* w3, const float* w4,
                     int32_t norm, float* grads, int32_t* status,
                     void* workspace, size_t workspace_bytes, void* stream);

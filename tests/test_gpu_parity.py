@@ -107,6 +107,33 @@ def test_build_graph_matches_reference_csr(sizes):
     np.testing.assert_array_equal(g.col_t.cpu().numpy()[:e], col_t)
     np.testing.assert_allclose(g.dis.cpu().numpy(), dis, rtol=2e-7, atol=0)
     np.testing.assert_array_equal(g.gptr.cpu().numpy(), np.concatenate([[0], np.cumsum(sizes)]))
+    # gorder: graph ids by descending size, ties by id
+    want = sorted(range(b), key=lambda i: (-sizes[i], i))
+    assert g.gorder.cpu().tolist() == want
+
+
+def test_build_graph_fast_path_equals_generic_path():
+    """A sorted symmetric edge list takes the streaming fast path; shuffling the same
+    edges forces the generic count/scan/fill/sort path.  Both must give the same CSR."""
+    for name in ("proteins", "collab"):
+        b = make_batch(name, num_graphs=40)
+        ei = b.edge_index
+        perm = torch.randperm(ei.size(1), generator=torch.Generator().manual_seed(0))
+        g1 = ops.build_graph(ei.to(DEV), b.batch.to(DEV), b.num_nodes, b.num_graphs)
+        g2 = ops.build_graph(ei[:, perm].contiguous().to(DEV), b.batch.to(DEV), b.num_nodes, b.num_graphs)
+        e = ei.size(1)
+        for a, c in ((g1.rowptr, g2.rowptr), (g1.col[:e], g2.col[:e]), (g1.rowptr_t, g2.rowptr_t),
+                     (g1.col_t[:e], g2.col_t[:e]), (g1.dis, g2.dis), (g1.gptr, g2.gptr)):
+            assert torch.equal(a, c)
+        # one missing reverse edge (asymmetric) must fall back and still be right
+        ei3 = ei[:, 1:].contiguous()
+        g3 = ops.build_graph(ei3.to(DEV), b.batch.to(DEV), b.num_nodes, b.num_graphs)
+        rowptr, col, rowptr_t, col_t, dis = ref_csr(ei3.numpy(), b.num_nodes)
+        np.testing.assert_array_equal(g3.rowptr.cpu().numpy(), rowptr)
+        np.testing.assert_array_equal(g3.col.cpu().numpy()[:rowptr[-1]], col)
+        np.testing.assert_array_equal(g3.rowptr_t.cpu().numpy(), rowptr_t)
+        np.testing.assert_array_equal(g3.col_t.cpu().numpy()[:rowptr[-1]], col_t)
+        np.testing.assert_allclose(g3.dis.cpu().numpy(), dis, rtol=2e-7)
 
 
 def test_build_graph_heavy_rows_and_no_edges():

@@ -33,6 +33,10 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
+    "dgcnn_graph_bitmap_words": (c_int64, [c_int64, c_int64, c_int64]),
+    "dgcnn_build_bitmaps": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32,
+                                      c_void_p]),
     "dgcnn_graph_ptr": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "dgcnn_graph_conv_fwd": (c_int32, [c_void_p, c_int64, c_int32,
                                        c_void_p, c_void_p, c_void_p,
@@ -57,7 +61,8 @@ SIGNATURES = {
     "dgcnn_stack_fwd_workspace_bytes": (c_size_t, []),
     "dgcnn_stack_fwd": (c_int32, [c_void_p, c_int64, c_int32,
                                   c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int64, c_int64, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int32,
@@ -69,7 +74,9 @@ SIGNATURES = {
     "dgcnn_stack_bwd": (c_int32, [c_void_p, c_void_p, c_int32,
                                   c_void_p, c_int64, c_void_p, c_int64,
                                   c_int32, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                  c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int64, c_int64,
                                   c_int64, c_void_p, c_void_p, c_void_p,
                                   c_int32, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),

@@ -95,6 +95,7 @@ k0_count(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64
     if (gate && !(*gate & 1)) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0 && gate && status) atomicOr(status, DGCNN_GRAPH_GENERIC);   // not proven symmetric
     for (int64_t e = tid; e < e0; e += stride) {
         int64_t s = src[e], d = dst[e];
         if ((uint64_t)s >= (uint64_t)n || (uint64_t)d >= (uint64_t)n) {

@@ -114,7 +114,6 @@ __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float*
 __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwdParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_graph;
-    __shared__ int s_dup;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const StackLayout L = stack_layout(p.f, p.nmax, nwarps);
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwd
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) { s_graph = atomicAdd(p.counter, 1); s_dup = 0; }
+        if (tid == 0) s_graph = atomicAdd(p.counter, 1);
         __syncthreads();
         if (s_graph >= p.num_graphs) break;
         const int g = p.gorder ? p.gorder[s_graph] : s_graph;
@@ -166,30 +165,22 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwd
         for (int r = keep + tid; r < p.k; r += nthreads) perm_g[r] = -1;
         if (n == 0) { __syncthreads(); continue; }
 
-        const int wpr = (n + 31) >> 5;
-        const int e0 = p.rowptr[base];
+        const int wpr = (n + 31) >> 5;                   // == ceil(round16(n) / 32), K0b's row stride
+        const bool dup = (p.gflags[g] & 1) != 0;         // multigraph: walk the CSR instead
+        const int e0 = dup ? p.rowptr[base] : 0;
         const int32_t* col_g = p.col + e0;
         float* xc = p.xcat + (int64_t)base * p.ldc;
 
-        // ---- phase 0: clear bitmap, per-node coefficients, local row pointers -----
-        for (int idx = tid; idx < n * wpr; idx += nthreads) bm[idx] = 0u;
+        // ---- phase 0: adjacency bitmap (from K0b), per-node coefficients ----------------
+        load_bitmap(p.bitmap + p.bmoff[g], bm, n * wpr, tid, nthreads);
         for (int j = tid; j < n; j += nthreads) {
             const float d = p.dis[base + j];
             cs[j] = col_coef(d, p.norm);
             rs[j] = row_coef(d, p.norm);
         }
-        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
+        if (dup)
+            for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
         __syncthreads();
-
-        // ---- phase 1: adjacency bitmap from the CSR ---------------------------------
-        // The graph's col segment is contiguous: stage it in ONE cooperative, coalesced
-        // sweep (all loads in flight at once) as 16-bit local ids in the two feature
-        // buffers, which are still free.  Building from global row by row instead costs
-        // a DRAM round trip per 32 edges per warp and dominated the kernel.
-        build_bitmap(col_g, base, n, wpr, nmax, rp, bm, reinterpret_cast<uint16_t*>(bufA), &s_dup,
-                     p.status);
-        __syncthreads();
-        const bool dup = s_dup != 0;
 
         // ---- layer 1: F -> 32 --------------------------------------------------------
         if (f <= kSmallF) {
@@ -347,6 +338,7 @@ int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes) {
 // done by the dispatcher in graph_stack_mma.cu)
 int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const int32_t* rowptr,
                         const int32_t* col, const float* dis, const int32_t* gptr, const int32_t* gorder,
+                        const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
                         int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w1,
                         const float* b1,
                         const float* w2, const float* b2, const float* w3, const float* b3,
@@ -357,6 +349,7 @@ int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const
     StackFwdParams p{};
     p.x = x; p.ldx = ldx; p.f = num_features;
     p.rowptr = rowptr; p.col = col; p.dis = dis; p.gptr = gptr; p.num_graphs = (int)num_graphs;
+    p.bitmap = bitmap; p.bmoff = bmoff; p.gflags = gflags;
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.w4 = w4; p.b4 = b4;
     p.xcat = xcat; p.ldc = ldc; p.pooled = pooled; p.perm = perm; p.k = k;
     p.norm = norm; p.nmax = stack_nmax_for(max_nodes);

@@ -17,6 +17,7 @@ constexpr int kSmemBudget = 227 * 1024;
 struct StackFwdParams {
     const float* x; int64_t ldx; int f;
     const int32_t* rowptr; const int32_t* col; const float* dis; const int32_t* gptr;
+    const uint32_t* bitmap; const int32_t* bmoff; const int32_t* gflags;   // K0b (graph_bitmap.cu)
     int num_graphs;
     const float* w1; const float* b1; const float* w2; const float* b2;
     const float* w3; const float* b3; const float* w4; const float* b4;
@@ -56,9 +57,10 @@ __device__ __forceinline__ float4 gather_row32(const float4* __restrict__ in4,
                                                uint32_t tailmask) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!dup) {
-        const int cnt = rp[i + 1] - rp[i] + 1;               // neighbours + self
-        const bool comp = 2 * cnt > n;
         const uint32_t* brow = bm + i * wpr;
+        int cnt = 0;                                         // neighbours + self
+        for (int t = 0; t < wpr; ++t) cnt += __popc(brow[t]);
+        const bool comp = 2 * cnt > n;
         for (int t = 0; t < wpr; ++t) {
             uint32_t w = brow[t];
             if (comp) {
@@ -119,72 +121,22 @@ __device__ __forceinline__ float scalar_row_sum(const float* __restrict__ val,
     return warp_sum(s);
 }
 
-// Adjacency bitmap (plus the self loop) of one graph from its CSR segment.  The segment
-// is contiguous, so it is first staged in ONE cooperative coalesced sweep -- every load
-// in flight at once -- as 16-bit local ids in `cl` (the two feature buffers, still free).
-// Building from global memory row by row costs a DRAM round trip per 32 edges per warp,
-// which dominated the first version of the kernel.  Sets *s_dup for multigraphs.
-// bm must be zeroed and rp filled (and a __syncthreads passed) before the call; the
-// caller synchronises after it.
-__device__ __forceinline__ void build_bitmap(const int32_t* __restrict__ col_g, int base, int n,
-                                             int wpr, int nmax, const int* __restrict__ rp,
-                                             uint32_t* __restrict__ bm, uint16_t* __restrict__ cl,
-                                             int* s_dup, int32_t* status) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-    const int eg = rp[n];
-    const bool staged = eg <= 2 * kHid * 2 * nmax;                 // uint16 slots in both buffers
-    if (staged) {
-        // 8 independent coalesced loads in flight per thread: the sweep costs a couple of
-        // DRAM round trips instead of one per element
-        for (int i0 = tid; i0 < eg; i0 += nthreads * 8) {
-            int v[8];
+// Fetch one graph's adjacency bitmap (built once per batch by K0b, graph_bitmap.cu) into
+// shared memory: np*wpr contiguous words, coalesced, several loads in flight per thread.
+__device__ __forceinline__ void load_bitmap(const uint32_t* __restrict__ gbm, uint32_t* __restrict__ bm,
+                                            int words, int tid, int nthreads) {
+    for (int i0 = tid; i0 < words; i0 += nthreads * 4) {
+        uint32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int idx = i0 + u * nthreads;
-                v[u] = idx < eg ? col_g[idx] : base;
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + u * nthreads;
+            v[u] = idx < words ? gbm[idx] : 0u;
+        }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int idx = i0 + u * nthreads;
-                if (idx < eg) {
-                    const unsigned j = (unsigned)(v[u] - base);
-                    if (j >= (unsigned)n && status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE);
-                    cl[idx] = j < (unsigned)n ? (uint16_t)j : (uint16_t)0xffff;
-                }
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + u * nthreads;
+            if (idx < words) bm[idx] = v[u];
         }
-        __syncthreads();
-    }
-    for (int i = warp; i < n; i += nwarps) {
-        uint32_t* brow = bm + i * wpr;
-        const int beg = rp[i], end = rp[i + 1];
-        for (int c0 = beg; c0 < end; c0 += 32) {
-            const int e = c0 + lane;
-            int j = -1;
-            if (e < end) {
-                if (staged) {
-                    const unsigned t = cl[e];
-                    j = t == 0xffffu ? -1 : (int)t;
-                } else {
-                    const unsigned t = (unsigned)(col_g[e] - base);
-                    if (t >= (unsigned)n) { if (status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE); }
-                    else j = (int)t;
-                }
-            }
-            const bool valid = j >= 0;
-            const int word = valid ? (j >> 5) : -1;
-            const uint32_t bit = valid ? (1u << (j & 31)) : 0u;
-            const uint32_t peers = __match_any_sync(DGCNN_FULL_MASK, word);
-            const uint32_t val = __reduce_or_sync(peers, bit);
-            if (valid && lane == __ffs(peers) - 1) {
-                const uint32_t old = brow[word];
-                if ((old & val) || __popc(val) != __popc(peers)) *s_dup = 1;   // multigraph
-                brow[word] = old | val;
-            }
-            __syncwarp();
-        }
-        if (lane == 0) brow[i >> 5] |= 1u << (i & 31);           // the added self loop
     }
 }
 

@@ -28,6 +28,9 @@ struct StackBwdParams {
     const float* x; int64_t ldx; int f;
     const int32_t* rowptr_t; const int32_t* col_t; const float* dis; const int32_t* gptr;
     const int32_t* gorder; int num_graphs;
+    // K0b bitmaps: of A_hat (used when the batch was proven symmetric) and of A_hat^T
+    const uint32_t* bitmap; const int32_t* bmoff; const int32_t* gflags;
+    const uint32_t* bitmap_t; const int32_t* bmoff_t; const int32_t* gflags_t;
     const float* w2; const float* w3; const float* w4;
     int norm; int nmax;
     float* partials;     // [gridDim.x][P]
@@ -87,7 +90,6 @@ __device__ __forceinline__ float reduce_rows(const float* red, int nwarps, int c
 
 __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_bwd_kernel(StackBwdParams p) {
     extern __shared__ __align__(16) float sm[];
-    __shared__ int s_dup;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const int grp = lane >> 3, q = lane & 7;
@@ -109,6 +111,12 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_bwd_kernel(StackBwd
     for (int idx = tid; idx < G.total; idx += nthreads) sacc[idx] = 0.f;
     __syncthreads();
 
+    // A_hat^T: the forward bitmap when K0 proved the batch symmetric, else the transposed one
+    const bool use_t = p.status && (*p.status & DGCNN_GRAPH_GENERIC) && p.bitmap_t;
+    const uint32_t* gbm = use_t ? p.bitmap_t : p.bitmap;
+    const int32_t* gbo = use_t ? p.bmoff_t : p.bmoff;
+    const int32_t* gfl = use_t ? p.gflags_t : p.gflags;
+
     // dW tile workers: the first DWW warps own the 32x32 outputs as 4(c) x 2(k) tiles while
     // the other warps run the row-local projection; with 4 warps everybody does both in turn
     const int dww = nwarps >= 8 ? 4 : nwarps;
@@ -125,7 +133,8 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_bwd_kernel(StackBwd
         if (n == 0) continue;
         const int keep = min(n, p.k);
         const int wpr = (n + 31) >> 5;
-        const int e0 = p.rowptr_t[base];
+        const bool dup = (gfl[g] & 1) != 0;
+        const int e0 = dup ? p.rowptr_t[base] : 0;
         const int32_t* col_g = p.col_t + e0;
         const float* xc = p.xcat + (int64_t)base * p.ldc;
         const float* dp = p.dpooled + (int64_t)g * p.k * kCat;
@@ -133,25 +142,22 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_bwd_kernel(StackBwd
         const uint32_t tailmask = (n & 31) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
 
         // ---- phase 0 ------------------------------------------------------------------
-        if (tid == 0) s_dup = 0;
-        for (int idx = tid; idx < n * wpr; idx += nthreads) bm[idx] = 0u;
+        load_bitmap(gbm + gbo[g], bm, n * wpr, tid, nthreads);
         for (int j = tid; j < n; j += nthreads) {
             const float d = p.dis[base + j];
             cs[j] = col_coef(d, p.norm);
             rs[j] = row_coef(d, p.norm);
             rank[j] = -1;
         }
-        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr_t[base + j] - e0;
+        if (dup)
+            for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr_t[base + j] - e0;
         __syncthreads();
         // rank[node] = pooled row that took this node (the inverse of perm), -1 if truncated
         for (int r = tid; r < keep; r += nthreads) {
             const int node = perm_g[r] - base;
             if ((unsigned)node < (unsigned)n) rank[node] = r;
         }
-        build_bitmap(col_g, base, n, wpr, nmax, rp, bm, reinterpret_cast<uint16_t*>(bufA), &s_dup,
-                     p.status);
         __syncthreads();
-        const bool dup = s_dup != 0;
 
         // ---- layer 4 (32 -> 1) -----------------------------------------------------------
         {
@@ -350,6 +356,9 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
                                const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                                int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
                                const float* dis, const int32_t* gptr, const int32_t* gorder,
+                               const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                               const uint32_t* bitmap_t, const int32_t* bmoff_t,
+                               const int32_t* gflags_t,
                                int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w2,
                                const float* w3, const float* w4, int32_t norm, float* grads,
                                int32_t* status, void* workspace, size_t workspace_bytes,
@@ -366,6 +375,8 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
     }
     if (!dgcnn_stack_bwd_supported(num_features, max_nodes)) return DGCNN_ERR_UNSUPPORTED;
     if (num_graphs >= INT32_MAX || num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
+    if (!bitmap || !bmoff || !gflags || !status) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (max_nodes > 1024) return DGCNN_ERR_UNSUPPORTED;
     if (!dpooled || !perm || !xcat || !x || !rowptr_t || !dis || !gptr || !w2 || !w3 || !w4)
         return DGCNN_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < dgcnn_stack_bwd_workspace_bytes(num_features))
@@ -375,6 +386,8 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
     p.dpooled = dpooled; p.perm = perm; p.k = k; p.xcat = xcat; p.ldc = ldc;
     p.x = x; p.ldx = ldx; p.f = num_features;
     p.rowptr_t = rowptr_t; p.col_t = col_t; p.dis = dis; p.gptr = gptr; p.gorder = gorder; p.num_graphs = (int)num_graphs;
+    p.bitmap = bitmap; p.bmoff = bmoff; p.gflags = gflags;
+    p.bitmap_t = bitmap_t; p.bmoff_t = bmoff_t; p.gflags_t = gflags_t;
     p.w2 = w2; p.w3 = w3; p.w4 = w4; p.norm = norm; p.nmax = stack_nmax_for(max_nodes);
     p.partials = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     p.status = status;

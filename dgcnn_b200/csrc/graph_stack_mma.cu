@@ -250,7 +250,6 @@ __device__ __forceinline__ void mma_layer(const __half* __restrict__ in_pl, cons
 __global__ void __launch_bounds__(kMmaThreads, 2) stack_fwd_mma_kernel(StackFwdParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int s_graph;
-    __shared__ int s_dup;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const int f = p.f, nmax = p.nmax;
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) stack_fwd_mma_kernel(StackFwdP
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) { s_graph = atomicAdd(p.counter, 1); s_dup = 0; }
+        if (tid == 0) s_graph = atomicAdd(p.counter, 1);
         __syncthreads();
         if (s_graph >= p.num_graphs) break;
         const int gi = p.gorder ? p.gorder[s_graph] : s_graph;
@@ -312,25 +311,21 @@ __global__ void __launch_bounds__(kMmaThreads, 2) stack_fwd_mma_kernel(StackFwdP
 
         const int np = (n + 15) & ~15;                   // rows/columns padded to the MMA tile
         const int wpr = (np + 31) >> 5;
-        const int e0 = p.rowptr[base];
+        const bool dup = (p.gflags[gi] & 1) != 0;        // multigraph: walk the CSR instead
+        const int e0 = dup ? p.rowptr[base] : 0;
         const int32_t* col_g = p.col + e0;
         float* xc = p.xcat + (int64_t)base * p.ldc;
 
-        // ---- phase 0 ------------------------------------------------------------------
-        for (int idx = tid; idx < np * wpr; idx += nthreads) bm[idx] = 0u;
+        // ---- phase 0: adjacency bitmap (from K0b), per-node coefficients ----------------
+        load_bitmap(p.bitmap + p.bmoff[gi], bm, np * wpr, tid, nthreads);
         for (int j = tid; j < np; j += nthreads) {
             const float d = j < n ? p.dis[base + j] : 0.f;
             cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
             rs[j] = j < n ? row_coef(d, p.norm) : 0.f;
         }
-        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
+        if (dup)
+            for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
         __syncthreads();
-
-        // ---- phase 1: bitmap (col segment staged through the still-free plane buffers) ----
-        build_bitmap(col_g, base, n, wpr, nmax, rp, bm, reinterpret_cast<uint16_t*>(PA), &s_dup,
-                     p.status);
-        __syncthreads();
-        const bool dup = s_dup != 0;
 
         // ---- layer 1: F -> 32 (FMA pipe: arbitrary input range, tiny work) -----------------
         if (f <= kSmallF) {
@@ -487,6 +482,7 @@ using namespace dgcnn;
 // implemented in graph_stack.cu (FMA gather variant)
 int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const int32_t* rowptr,
                         const int32_t* col, const float* dis, const int32_t* gptr, const int32_t* gorder,
+                        const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
                         int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w1,
                         const float* b1,
                         const float* w2, const float* b2, const float* w3, const float* b3,
@@ -509,8 +505,9 @@ extern "C" size_t dgcnn_stack_fwd_workspace_bytes(void) { return 256; }
 
 extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                                const int32_t* rowptr, const int32_t* col, const float* dis,
-                               const int32_t* gptr, const int32_t* gorder, int64_t num_nodes,
-                               int64_t num_graphs, int64_t max_nodes,
+                               const int32_t* gptr, const int32_t* gorder,
+                               const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                               int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                                const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* w3, const float* b3, const float* w4, const float* b4,
                                float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
@@ -526,6 +523,8 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     if (variant == DGCNN_STACK_MMA ? !mma_supported(num_features, max_nodes)
                                    : !dgcnn_stack_fwd_fma_supported(num_features, max_nodes))
         return DGCNN_ERR_UNSUPPORTED;
+    if (!bitmap || !bmoff || !gflags) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (max_nodes > 1024) return DGCNN_ERR_UNSUPPORTED;
     if (!rowptr || !dis || !gptr || !w1 || !w2 || !w3 || !w4 || !xcat || !pooled || !perm ||
         (num_nodes > 0 && !x))
         return DGCNN_ERR_INVALID_ARGUMENT;
@@ -535,13 +534,15 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     int32_t* counter = reinterpret_cast<int32_t*>(aligned);
     if (cudaMemsetAsync(counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
     if (variant == DGCNN_STACK_FMA)
-        return dgcnn_stack_fwd_fma(x, ldx, num_features, rowptr, col, dis, gptr, gorder, num_nodes, num_graphs,
+        return dgcnn_stack_fwd_fma(x, ldx, num_features, rowptr, col, dis, gptr, gorder, bitmap, bmoff,
+                                   gflags, num_nodes, num_graphs,
                                    max_nodes, w1, b1, w2, b2, w3, b3, w4, b4, xcat, ldc, pooled, perm, k,
                                    norm, status, counter, st);
 
     StackFwdParams p{};
     p.x = x; p.ldx = ldx; p.f = num_features;
     p.rowptr = rowptr; p.col = col; p.dis = dis; p.gptr = gptr; p.num_graphs = (int)num_graphs;
+    p.bitmap = bitmap; p.bmoff = bmoff; p.gflags = gflags;
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.w4 = w4; p.b4 = b4;
     p.xcat = xcat; p.ldc = ldc; p.pooled = pooled; p.perm = perm; p.k = k;
     p.norm = norm; p.nmax = stack_nmax_for(max_nodes);

@@ -19,7 +19,8 @@ from . import _lib
 
 NORM_SYM, NORM_RW = 0, 1
 ACT_NONE, ACT_TANH = 0, 1
-GRAPH_BAD_EDGE, GRAPH_BAD_BATCH, GRAPH_RANGE = 1, 2, 4
+GRAPH_BAD_EDGE, GRAPH_BAD_BATCH, GRAPH_RANGE, GRAPH_GENERIC = 1, 2, 4, 8
+BITMAP_MAX_NODES = 1024
 STACK_MMA, STACK_FMA = 0, 1
 # implementation of the fused forward; tests flip it to cross-check the two kernels
 STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower() == "fma" else STACK_MMA
@@ -27,7 +28,8 @@ STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower(
 # kernels launched by this process through the C ABI (memsets not counted); bench.py
 # reads it to report `gpu_launches`.  Keyed by entry point.
 LAUNCHES = {"build_graph": 0, "graph_ptr": 0, "graph_conv_fwd": 0, "graph_conv_bwd": 0,
-            "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0, "stack_bwd": 0}
+            "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0, "stack_bwd": 0,
+            "build_bitmaps": 0}
 
 
 def launches_total() -> int:
@@ -82,6 +84,13 @@ class Graph:
     num_nodes: int
     num_graphs: int
     max_nodes: int = 0       # largest graph if known on the host, else 0
+    # K0b: per-graph adjacency bitmaps for the fused kernels (only when max_nodes is known)
+    bitmap: Optional[Tensor] = None
+    bmoff: Optional[Tensor] = None
+    gflags: Optional[Tensor] = None
+    bitmap_t: Optional[Tensor] = None
+    bmoff_t: Optional[Tensor] = None
+    gflags_t: Optional[Tensor] = None
 
     def check(self) -> None:
         """Host-syncing validation of the device-side status word (debug / tests)."""
@@ -128,7 +137,36 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
                                    _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "build_graph")
     LAUNCHES["build_graph"] += (8 if e > 0 else 6) + (1 if batch is not None and b > 0 else 0)
-    return Graph(rowptr, col, rowptr_t, col_t, dis, gptr, gorder, status, n, b, int(max_nodes))
+    graph = Graph(rowptr, col, rowptr_t, col_t, dis, gptr, gorder, status, n, b, int(max_nodes))
+    if batch is not None and b > 0 and 0 < int(max_nodes) <= BITMAP_MAX_NODES:
+        _build_bitmaps(graph, transpose)
+    return graph
+
+
+def _build_bitmaps(graph: Graph, transpose: bool) -> None:
+    """K0b: adjacency bitmaps of A_hat (and of A_hat^T unless K0 proved symmetry)."""
+    lib = _lib.load_library()
+    dev = graph.rowptr.device
+    n, b, mx = graph.num_nodes, graph.num_graphs, graph.max_nodes
+    words = int(lib.dgcnn_graph_bitmap_words(n, b, mx))
+    i32 = dict(dtype=torch.int32, device=dev)
+
+    def run(rowptr, col, gate):
+        bitmap = torch.empty(words, **i32)
+        bmoff = torch.empty(b + 1, **i32)
+        gflags = torch.empty(b, **i32)
+        with torch.cuda.device(dev):
+            rc = lib.dgcnn_build_bitmaps(_ptr(rowptr), _ptr(col), _ptr(graph.gptr), n, b, mx,
+                                         _ptr(bitmap), words, _ptr(bmoff), _ptr(gflags),
+                                         _ptr(graph.status) if gate else None, GRAPH_GENERIC,
+                                         _stream())
+        _lib.check(rc, "build_bitmaps")
+        LAUNCHES["build_bitmaps"] += 2
+        return bitmap, bmoff, gflags
+
+    graph.bitmap, graph.bmoff, graph.gflags = run(graph.rowptr, graph.col, False)
+    if transpose and graph.rowptr_t is not None:
+        graph.bitmap_t, graph.bmoff_t, graph.gflags_t = run(graph.rowptr_t, graph.col_t, True)
 
 
 def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
@@ -244,7 +282,7 @@ def sort_pool_bwd(dout: Tensor, perm: Tensor, num_nodes: int, out: Optional[Tens
 
 def stack_fwd_supported(num_features: int, max_nodes: int) -> bool:
     """Can the one-launch fused forward (KS) hold the largest graph in shared memory?"""
-    if max_nodes <= 0:
+    if max_nodes <= 0 or max_nodes > BITMAP_MAX_NODES:
         return False
     return bool(_lib.load_library().dgcnn_stack_fwd_supported(int(num_features), int(max_nodes)))
 
@@ -257,8 +295,8 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
     n, f = x.shape
     if len(weights) != 4 or [tuple(w.shape) for w in weights] != [(32, f), (32, 32), (32, 32), (1, 32)]:
         raise ValueError("dgcnn_b200: stack_fwd needs the model's F->32->32->32->1 weights")
-    if graph.gptr is None:
-        raise ValueError("dgcnn_b200: stack_fwd needs a graph built with `batch`")
+    if graph.gptr is None or graph.bitmap is None:
+        raise ValueError("dgcnn_b200: stack_fwd needs a graph built with `batch` and `max_nodes`")
     ws = [w.contiguous() for w in weights]
     bs = [None if b is None else b.contiguous() for b in biases]
     for t in ws + [b for b in bs if b is not None]:
@@ -270,7 +308,8 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
     wsp = _workspace(lib.dgcnn_stack_fwd_workspace_bytes(), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_fwd(_ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr), _ptr(graph.col),
-                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder), n, b,
+                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder),
+                                 _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags), n, b,
                                  int(graph.max_nodes), _ptr(ws[0]), _ptr(bs[0]), _ptr(ws[1]), _ptr(bs[1]),
                                  _ptr(ws[2]), _ptr(bs[2]), _ptr(ws[3]), _ptr(bs[3]),
                                  _ptr(xcat), 97, _ptr(pooled), _ptr(perm), int(k), int(norm),
@@ -281,7 +320,7 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
 
 
 def stack_bwd_supported(num_features: int, max_nodes: int) -> bool:
-    if max_nodes <= 0:
+    if max_nodes <= 0 or max_nodes > BITMAP_MAX_NODES:
         return False
     return bool(_lib.load_library().dgcnn_stack_bwd_supported(int(num_features), int(max_nodes)))
 
@@ -294,8 +333,9 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     for t, name in ((dpooled, "dpooled"), (xcat, "xcat"), (x, "x")):
         _require_cuda(t, name, torch.float32)
     _require_cuda(perm, "perm", torch.int32)
-    if graph.rowptr_t is None or graph.gptr is None:
-        raise ValueError("dgcnn_b200: stack_bwd needs a graph built with batch and transpose=True")
+    if graph.rowptr_t is None or graph.gptr is None or graph.bitmap is None:
+        raise ValueError("dgcnn_b200: stack_bwd needs a graph built with batch, max_nodes and "
+                         "transpose=True")
     n, f = x.shape
     b = graph.num_graphs
     dpooled = dpooled.contiguous()
@@ -306,7 +346,9 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_bwd(_ptr(dpooled), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
                                  _ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr_t), _ptr(graph.col_t),
-                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder), n, b,
+                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder),
+                                 _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags),
+                                 _ptr(graph.bitmap_t), _ptr(graph.bmoff_t), _ptr(graph.gflags_t), n, b,
                                  int(graph.max_nodes), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm), _ptr(grads),
                                  _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
     _lib.check(rc, "stack_bwd")

@@ -55,6 +55,8 @@ typedef enum dgcnn_act { DGCNN_ACT_NONE = 0, DGCNN_ACT_TANH = 1 } dgcnn_act;
 #define DGCNN_GRAPH_BAD_EDGE 1    /* an edge_index entry outside [0, N)      */
 #define DGCNN_GRAPH_BAD_BATCH 2   /* batch not non-decreasing / outside [0,B) */
 #define DGCNN_GRAPH_RANGE 4       /* a projected feature exceeded the fp16 split range */
+#define DGCNN_GRAPH_GENERIC 8     /* (informational) input was not a sorted symmetric edge list:
+                                     K0 took the generic path, A_hat^T != A_hat may hold */
 
 /* Implementations of the fused forward (dgcnn_stack_fwd `variant`). */
 #define DGCNN_STACK_MMA 0         /* tensor-core aggregation + projection (default)    */
@@ -92,6 +94,22 @@ int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges,
                       int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
                       float* dis, int32_t* gptr, int32_t* gorder, int32_t* status,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K0b  per-graph adjacency bitmaps (with GCNConv's self loop) for the fused per-graph
+ * kernels KS / KSB, built once per batch from a CSR of K0 (call it a second time with
+ * rowptr_t/col_t for A_hat^T; gate_word/gate_mask let that call be skipped ON THE DEVICE
+ * when K0 proved the batch symmetric: pass K0's status word and DGCNN_GRAPH_GENERIC).
+ *   bitmap  uint32[dgcnn_graph_bitmap_words(N, B, max_nodes)]; graph g owns
+ *           np_g * ceil(np_g/32) words at bmoff[g], np_g = n_g rounded up to 16
+ *   bmoff   int32[B+1];  gflags int32[B]: bit 0 duplicate edges, bit 1 no bitmap (too large)
+ * max_nodes: largest graph in the batch (host knowledge); capped at 1024.
+ * ------------------------------------------------------------------------ */
+int64_t dgcnn_graph_bitmap_words(int64_t num_nodes, int64_t num_graphs, int64_t max_nodes);
+int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col, const int32_t* gptr,
+                        int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                        uint32_t* bitmap, int64_t bitmap_words, int32_t* bmoff, int32_t* gflags,
+                        const int32_t* gate_word, int32_t gate_mask, void* stream);
 
 /* gptr alone (SortAggregation called without a graph: model.py:35's `batch`). */
 int dgcnn_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
@@ -177,8 +195,9 @@ int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes);
 size_t dgcnn_stack_fwd_workspace_bytes(void);
 int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                     const int32_t* rowptr, const int32_t* col, const float* dis,
-                    const int32_t* gptr, const int32_t* gorder, int64_t num_nodes,
-                    int64_t num_graphs, int64_t max_nodes,
+                    const int32_t* gptr, const int32_t* gorder,
+                    const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                    int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                     const float* w1, const float* b1, const float* w2, const float* b2,
                     const float* w3, const float* b3, const float* w4, const float* b4,
                     float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
@@ -203,6 +222,8 @@ int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                     const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                     int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
                     const float* dis, const int32_t* gptr, const int32_t* gorder,
+                    const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                    const uint32_t* bitmap_t, const int32_t* bmoff_t, const int32_t* gflags_t,
                     int64_t num_nodes, int64_t num_graphs,
                     int64_t max_nodes, const float* w2, const float* w3, const float* w4,
                     int32_t norm, float* grads, int32_t* status,

@@ -136,6 +136,42 @@ def test_build_graph_fast_path_equals_generic_path():
         np.testing.assert_allclose(g3.dis.cpu().numpy(), dis, rtol=2e-7)
 
 
+def test_bitmaps_match_the_adjacency():
+    """K0b: bit (r,c) of graph g  <=>  edge c->r or r == c; duplicates flagged per graph;
+    the transposed bitmap is only built when the input is not a sorted symmetric list."""
+    rng = np.random.RandomState(5)
+    sizes = [5, 0, 33, 64, 1, 100, 17]
+    ei, batch, n = random_multigraph(rng, sizes, avg_deg=3.0)
+    b = len(sizes)
+    mx = max(sizes)
+    g = gpu_graph(ei, batch, n, b, max_nodes=mx)
+    assert int(g.status.item()) & ops.GRAPH_GENERIC
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    for bitmap, bmoff, gflags, rows, cols in ((g.bitmap, g.bmoff, g.gflags, ei[1], ei[0]),
+                                              (g.bitmap_t, g.bmoff_t, g.gflags_t, ei[0], ei[1])):
+        bm, off, fl = bitmap.cpu().numpy().view(np.uint32), bmoff.cpu().numpy(), gflags.cpu().numpy()
+        for gi, ng in enumerate(sizes):
+            npad = (ng + 15) // 16 * 16
+            wpr = (npad + 31) // 32
+            assert off[gi + 1] - off[gi] == npad * wpr
+            dense = np.zeros((npad, wpr * 32), dtype=bool)
+            sel = (batch[rows] == gi) & (rows != cols)
+            dense[rows[sel] - ptr[gi], cols[sel] - ptr[gi]] = True
+            dense[np.arange(ng), np.arange(ng)] = True
+            words = bm[off[gi]:off[gi + 1]].reshape(npad, wpr)
+            got = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(npad, -1)
+            np.testing.assert_array_equal(got, dense)
+            pairs = np.stack([rows[sel], cols[sel]], 1)
+            has_dup = len(np.unique(pairs, axis=0)) != len(pairs)
+            assert bool(fl[gi] & 1) == has_dup
+    # sorted symmetric input: proven symmetric on the device, transposed bitmap left empty
+    bt = make_batch("proteins", num_graphs=20)
+    g2 = ops.build_graph(bt.edge_index.to(DEV), bt.batch.to(DEV), bt.num_nodes, 20,
+                         max_nodes=int((bt.ptr[1:] - bt.ptr[:-1]).max()))
+    assert not int(g2.status.item()) & ops.GRAPH_GENERIC
+    assert int(g2.bitmap_t.abs().sum()) == 0 and int(g2.bitmap.abs().sum()) > 0
+
+
 def test_build_graph_heavy_rows_and_no_edges():
     # star: one row of degree 5000 (rank sort beyond one warp chunk), plus an edgeless graph
     n = 5001

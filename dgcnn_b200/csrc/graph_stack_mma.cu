@@ -28,38 +28,77 @@
 
 namespace dgcnn {
 
-constexpr int kMmaThreads = 256;
 constexpr int kWPad = 40;   // row stride (halfs) of the 32x32 weight planes: conflict-free
 
-// shared-memory carve-up in BYTES; every region is 16-byte aligned
-struct MmaLayout {
-    int w2p, w3p, w1t, misc, PA, PB, vpl, bm, xs, cs, rs, rp, total;
-    int S;      // plane row stride in halfs: padded node count + 8
-    int nmaxp;  // nmax rounded up to 16
+// A TEAM is the set of threads working on one graph: 1, 2 or 4 "quads" of 128 threads of
+// the 512-thread CTA.  Big graphs get the whole CTA (16 warps, the whole SM: they are the
+// critical path of the launch); small graphs run four at a time, one per quad, each with
+// its own named barrier and its own slice of the dynamic shared memory.  Graphs arrive in
+// descending size (gorder), so a group only ever splits, never merges.
+constexpr int kCtaThreads = 512;
+constexpr int kQuadThreads = 128;
+constexpr int kQuads = kCtaThreads / kQuadThreads;
+
+struct Team {
+    int tid, nthreads, warp, nwarps, lane;
+    int bar;                 // named barrier id (1 + first quad of the group)
+    unsigned char* smem;     // the group's slice of dynamic shared memory
+    __device__ __forceinline__ void sync() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
+    }
 };
 
 __host__ __device__ inline int al16(int v) { return (v + 15) & ~15; }
 
-__host__ __device__ inline MmaLayout mma_layout(int f, int nmax) {
-    MmaLayout L;
-    L.nmaxp = (nmax + 15) & ~15;
-    L.S = L.nmaxp + 8;
-    const int wpr = (L.nmaxp + 31) >> 5;
+// CTA-wide region: weights, shared by all teams.  Byte offsets, 16-byte aligned.
+struct SharedLayout { int w2p, w3p, w1t, misc, total; };
+
+__host__ __device__ inline SharedLayout shared_layout(int f) {
+    SharedLayout L;
     int o = 0;
     L.w2p = o; o += 2 * kHid * kWPad * 2;
     L.w3p = o; o += 2 * kHid * kWPad * 2;
     L.w1t = o; o += al16(f * kHid * 4);
     L.misc = o; o += 4 * kHid * 4;                       // w4, b1, b2, b3
+    L.total = o;
+    return L;
+}
+
+// Per-graph region, sized by the graph's own padded node count np (multiple of 16).
+struct TeamLayout {
+    int PA, PB, vpl, bm, xs, cs, rs, rp, total;
+    int S;      // plane row stride in halfs: np + 8
+};
+
+__host__ __device__ inline TeamLayout team_layout(int f, int np) {
+    TeamLayout L;
+    L.S = np + 8;
+    const int wpr = (np + 31) >> 5;
+    int o = 0;
     L.PA = o; o += 2 * kHid * L.S * 2;                   // hi and lo planes [32][S] fp16
     L.PB = o; o += 2 * kHid * L.S * 2;
     L.vpl = o; o += al16(2 * L.S * 2);                   // layer-4 input: hi and lo [S]
-    L.bm = o; o += al16(L.nmaxp * wpr * 4);
-    L.xs = o; o += (f <= kSmallF) ? al16(f * L.nmaxp * 4) : 0;
-    L.cs = o; o += al16(L.nmaxp * 4);
-    L.rs = o; o += al16(L.nmaxp * 4);
-    L.rp = o; o += al16((L.nmaxp + 1) * 4);
+    L.bm = o; o += al16(np * wpr * 4);
+    L.xs = o; o += (f <= kSmallF) ? al16(f * np * 4) : 0;
+    L.cs = o; o += al16(np * 4);
+    L.rs = o; o += al16(np * 4);
+    L.rp = o; o += al16((np + 1) * 4);
     L.total = o;
     return L;
+}
+
+// bytes of one quad's slice when the CTA takes (almost) all of the SM's shared memory
+__host__ __device__ inline int quad_bytes(int f) {
+    return ((kSmemBudget - 1024 - shared_layout(f).total) / kQuads) & ~15;
+}
+
+// quads a graph of n nodes is given: enough warps for its 16-row tiles, enough memory
+__host__ __device__ inline int quads_needed(int f, int n) {
+    const int np = (n + 15) & ~15, tiles = np >> 4;
+    int q = tiles <= 4 ? 1 : (tiles <= 8 ? 2 : 4);
+    const int need = team_layout(f, np < 16 ? 16 : np).total, qb = quad_bytes(f);
+    while (q < kQuads && need > q * qb) q <<= 1;
+    return q;
 }
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -117,8 +156,8 @@ __device__ __forceinline__ void mma_layer(const __half* __restrict__ in_pl, cons
                                           const int* __restrict__ rp, const int32_t* __restrict__ col_g,
                                           int base, const float* __restrict__ cs,
                                           const float* __restrict__ rs, float* __restrict__ xo,
-                                          int64_t ldc) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+                                          int64_t ldc, const Team& tm) {
+    const int lane = tm.lane, warp = tm.warp, nwarps = tm.nwarps;
     const int g = lane >> 2, t = lane & 3;
     const int tiles = (n + 15) >> 4;
     const uint32_t* in32[2] = {reinterpret_cast<const uint32_t*>(in_pl),
@@ -247,19 +286,51 @@ __device__ __forceinline__ void mma_layer(const __half* __restrict__ in_pl, cons
     }
 }
 
-__global__ void __launch_bounds__(kMmaThreads, 2) stack_fwd_mma_kernel(StackFwdParams p) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ int s_graph;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-    const int f = p.f, nmax = p.nmax;
-    const MmaLayout L = mma_layout(f, nmax);
+// team-wide bitonic sort of 64-bit composites (p = power of two >= 2)
+__device__ __forceinline__ void bitonic_sort_team(uint64_t* buf, uint32_t p, const Team& tm) {
+    for (uint32_t size = 2; size <= p; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            tm.sync();
+            for (uint32_t t = tm.tid; t < (p >> 1); t += tm.nthreads) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = buf[lo], b = buf[hi];
+                if ((a > b) == up) { buf[lo] = b; buf[hi] = a; }
+            }
+        }
+    }
+    tm.sync();
+}
+
+// model.py:28-35 for ONE graph, executed by one team
+__device__ __forceinline__ void process_graph(const StackFwdParams& p, const Team& tm, int gi,
+                                              const unsigned char* shraw) {
+    const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
+    const int nthreads = tm.nthreads, nwarps = tm.nwarps;
+    const int f = p.f;
+    const SharedLayout SL = shared_layout(f);
+    const __half* w2p = reinterpret_cast<const __half*>(shraw + SL.w2p);
+    const __half* w3p = reinterpret_cast<const __half*>(shraw + SL.w3p);
+    const float* w1t = reinterpret_cast<const float*>(shraw + SL.w1t);
+    const float* w4s = reinterpret_cast<const float*>(shraw + SL.misc);
+    const float* b1s = w4s + kHid;  const float* b2s = b1s + kHid;  const float* b3s = b2s + kHid;
+    const float b4 = p.b4 ? p.b4[0] : 0.f;
+
+    const int base = p.gptr[gi];
+    const int n = p.gptr[gi + 1] - base;
+    const int keep = min(n, p.k);
+    float* pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
+    int32_t* perm_g = p.perm + (int64_t)gi * p.k;
+    for (int idx = keep * kCat + tid; idx < p.k * kCat; idx += nthreads) pooled_g[idx] = 0.f;
+    for (int r = keep + tid; r < p.k; r += nthreads) perm_g[r] = -1;
+    if (n == 0) return;
+
+    const int np = (n + 15) & ~15;                   // rows/columns padded to the MMA tile
+    const int wpr = (np + 31) >> 5;
+    const TeamLayout L = team_layout(f, np);
     const int S = L.S;
-    __half* w2p = reinterpret_cast<__half*>(smraw + L.w2p);
-    __half* w3p = reinterpret_cast<__half*>(smraw + L.w3p);
-    float* w1t = reinterpret_cast<float*>(smraw + L.w1t);
-    float* w4s = reinterpret_cast<float*>(smraw + L.misc);
-    float* b1s = w4s + kHid;  float* b2s = b1s + kHid;  float* b3s = b2s + kHid;
+    unsigned char* smraw = tm.smem;
     __half* PA = reinterpret_cast<__half*>(smraw + L.PA);
     __half* PB = reinterpret_cast<__half*>(smraw + L.PB);
     __half* vpl = reinterpret_cast<__half*>(smraw + L.vpl);
@@ -270,208 +341,239 @@ __global__ void __launch_bounds__(kMmaThreads, 2) stack_fwd_mma_kernel(StackFwdP
     float* key = rs;                                    // x_4 overwrites r_i in place
     int* order = reinterpret_cast<int*>(cs);            // c_j is dead after layer 3
     int* rp = reinterpret_cast<int*>(smraw + L.rp);
-    const float b4 = p.b4 ? p.b4[0] : 0.f;
 
-    // weights once per CTA: W1 transposed fp32 (layer 1 stays on the FMA pipe),
-    // W2/W3 as hi/lo fp16 planes [cout][cin] = the MMA "col" operand of y = agg @ W^T
-    for (int idx = tid; idx < f * kHid; idx += nthreads) {
-        int c = idx / f, k = idx - c * f;
-        w1t[k * kHid + c] = p.w1[idx];
+    const bool dup = (p.gflags[gi] & 1) != 0;        // multigraph: walk the CSR instead
+    const int e0 = dup ? p.rowptr[base] : 0;
+    const int32_t* col_g = p.col + e0;
+    float* xc = p.xcat + (int64_t)base * p.ldc;
+
+    // ---- phase 0: adjacency bitmap (from K0b), per-node coefficients, layer-1 input ------
+    load_bitmap(p.bitmap + p.bmoff[gi], bm, np * wpr, tid, nthreads);
+    for (int j = tid; j < np; j += nthreads) {
+        const float d = j < n ? p.dis[base + j] : 0.f;
+        cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
+        rs[j] = j < n ? row_coef(d, p.norm) : 0.f;
     }
-    for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
-        const int c = idx >> 5, k = idx & 31;
-        store_split(w2p, w2p + kHid * kWPad, c * kWPad + k, p.w2[idx]);
-        store_split(w3p, w3p + kHid * kWPad, c * kWPad + k, p.w3[idx]);
+    if (dup)
+        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
+    tm.sync();
+
+    // ---- layer 1: F -> 32 (FMA pipe: arbitrary input range, tiny work) -----------------
+    if (f <= kSmallF) {
+        for (int idx = tid; idx < n * f; idx += nthreads) {
+            int j = idx / f, k = idx - j * f;
+            xs[k * np + j] = cs[j] * p.x[(int64_t)(base + j) * p.ldx + k];
+        }
+        // padding columns of the output planes must be finite zeros (0 * NaN = NaN)
+        for (int idx = tid; idx < (np - n) * kHid; idx += nthreads) {
+            const int c = idx / (np - n), j = n + idx - c * (np - n);
+            PA[c * S + j] = __float2half_rn(0.f);
+            PA[kHid * S + c * S + j] = __float2half_rn(0.f);
+        }
+        tm.sync();
+        for (int i = warp; i < n; i += nwarps) {
+            const float r = rs[i];
+            float acc = b1s[lane];
+            for (int k = 0; k < f; ++k) {
+                const float a = r * scalar_row_sum(xs + k * np, bm + i * wpr, wpr, dup, rp, col_g, base, i);
+                acc = fmaf(a, w1t[k * kHid + lane], acc);
+            }
+            const float y = tanhf(acc);
+            xc[(int64_t)i * p.ldc + lane] = y;
+            store_split(PA, PA + kHid * S, lane * S + i, cs[i] * y);
+        }
+    } else {
+        // project first: c_j * (x_j W1^T) as planes in PB, then aggregate on the tensor cores
+        for (int j = warp; j < np; j += nwarps) {
+            float acc = 0.f;
+            if (j < n) {
+                const float* xr = p.x + (int64_t)(base + j) * p.ldx;
+                for (int k = 0; k < f; ++k) acc = fmaf(xr[k], w1t[k * kHid + lane], acc);
+                acc *= cs[j];
+                if (fabsf(acc) > 6.0e4f && p.status) atomicOr(p.status, DGCNN_GRAPH_RANGE);
+            }
+            store_split(PB, PB + kHid * S, lane * S + j, acc);
+        }
+        tm.sync();
+        mma_layer<false, false>(PB, nullptr, b1s, PA, nullptr, nullptr, bm, wpr, n, S, dup, rp, col_g,
+                                base, cs, rs, xc, p.ldc, tm);
     }
-    if (tid < kHid) {
-        w4s[tid] = p.w4[tid];
-        b1s[tid] = p.b1 ? p.b1[tid] : 0.f;
-        b2s[tid] = p.b2 ? p.b2[tid] : 0.f;
-        b3s[tid] = p.b3 ? p.b3[tid] : 0.f;
+    tm.sync();
+
+    // ---- layers 2 and 3 on the tensor cores ------------------------------------------
+    mma_layer<true, false>(PA, w2p, b2s, PB, nullptr, nullptr, bm, wpr, n, S, dup, rp, col_g, base, cs,
+                           rs, xc + kHid, p.ldc, tm);
+    tm.sync();
+    mma_layer<true, true>(PB, w3p, b3s, nullptr, vpl, w4s, bm, wpr, n, S, dup, rp, col_g, base, cs, rs,
+                          xc + 2 * kHid, p.ldc, tm);
+    tm.sync();
+
+    // ---- layer 4: 32 -> 1, already projected into v: one 8-wide MMA column ---------------
+    {
+        const int g = lane >> 2, t = lane & 3;
+        const int tiles = np >> 4;
+        const uint32_t* v32[2] = {reinterpret_cast<const uint32_t*>(vpl),
+                                  reinterpret_cast<const uint32_t*>(vpl + S)};
+        for (int mt = warp; mt < tiles; mt += nwarps) {
+            const int row0 = mt * 16 + g, row1 = row0 + 8;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!dup) {
+                for (int kt = 0; kt < tiles; ++kt) {
+                    uint32_t a[4];
+                    if (!adj_fragment(bm, wpr, row0, kt, t, a)) continue;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                        const int idx = (kt * 16 + 2 * t) >> 1;
+                        const uint32_t b0 = g == 0 ? v32[pl][idx] : 0u;
+                        const uint32_t b1 = g == 0 ? v32[pl][idx + 4] : 0u;
+                        mma_f16(acc, a, b0, b1);
+                    }
+                }
+            } else if (t == 0) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int row = half ? row1 : row0;
+                    if (row >= n) continue;
+                    float s = 0.f;
+                    for (int e = rp[row] - 1; e < rp[row + 1]; ++e) {
+                        const int j = e < rp[row] ? row : col_g[e] - base;
+                        s += __half2float(vpl[j]) + __half2float(vpl[S + j]);
+                    }
+                    acc[2 * half] = s;
+                }
+            }
+            if (t == 0) {                                  // column 0 of the tile lives in t == 0
+                if (row0 < n) {
+                    const float x4 = tanhf(fmaf(rs[row0], acc[0], b4));
+                    key[row0] = x4;
+                    xc[(int64_t)row0 * p.ldc + 3 * kHid] = x4;
+                }
+                if (row1 < n) {
+                    const float x4 = tanhf(fmaf(rs[row1], acc[2], b4));
+                    key[row1] = x4;
+                    xc[(int64_t)row1 * p.ldc + 3 * kHid] = x4;
+                }
+            }
+        }
     }
-    __syncthreads();
+    tm.sync();
+
+    // ---- SortPool: order by x_4 descending, ties by node index -----------------------
+    uint64_t* comp = reinterpret_cast<uint64_t*>(PA);
+    if (n <= 256) {
+        for (int j = tid; j < n; j += nthreads)
+            comp[j] = ((uint64_t)descending_key_bits(key[j]) << 32) | (uint32_t)j;
+        tm.sync();
+        for (int i = tid; i < n; i += nthreads) {
+            const uint64_t mine = comp[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += comp[j] < mine;
+            if (rank < keep) order[rank] = i;
+        }
+    } else {
+        const uint32_t pw = next_pow2((uint32_t)n);
+        for (uint32_t j = tid; j < pw; j += nthreads)
+            comp[j] = (j < (uint32_t)n) ? (((uint64_t)descending_key_bits(key[j]) << 32) | j) : ~0ull;
+        bitonic_sort_team(comp, pw, tm);
+        for (int r = tid; r < keep; r += nthreads) order[r] = (int)(uint32_t)(comp[r] & 0xffffffffu);
+    }
+    tm.sync();
+
+    // ---- gather the k winners (rows of x_cat this team just wrote: L2 hits) ------------
+    {
+        const int total = keep * kCat;
+        for (int i0 = tid; i0 < total; i0 += nthreads * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0 + u * nthreads;
+                if (idx < total) {
+                    const int r = idx / kCat, c = idx - r * kCat;
+                    v[u] = xc[(int64_t)order[r] * p.ldc + c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0 + u * nthreads;
+                if (idx < total) pooled_g[idx] = v[u];
+            }
+        }
+    }
+    for (int r = tid; r < keep; r += nthreads) perm_g[r] = base + order[r];
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ int s_item[kQuads];
+    const int f = p.f;
+    const SharedLayout SL = shared_layout(f);
+    {   // weights once per CTA: W1 transposed fp32 (layer 1 stays on the FMA pipe), W2/W3 as
+        // hi/lo fp16 planes [cout][cin] = the MMA "col" operand of y = agg @ W^T
+        const int tid = threadIdx.x, nthreads = blockDim.x;
+        __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
+        __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
+        float* w1t = reinterpret_cast<float*>(smraw + SL.w1t);
+        float* w4s = reinterpret_cast<float*>(smraw + SL.misc);
+        for (int idx = tid; idx < f * kHid; idx += nthreads) {
+            int c = idx / f, k = idx - c * f;
+            w1t[k * kHid + c] = p.w1[idx];
+        }
+        for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
+            const int c = idx >> 5, k = idx & 31;
+            store_split(w2p, w2p + kHid * kWPad, c * kWPad + k, p.w2[idx]);
+            store_split(w3p, w3p + kHid * kWPad, c * kWPad + k, p.w3[idx]);
+        }
+        if (tid < kHid) {
+            w4s[tid] = p.w4[tid];
+            w4s[kHid + tid] = p.b1 ? p.b1[tid] : 0.f;
+            w4s[2 * kHid + tid] = p.b2 ? p.b2[tid] : 0.f;
+            w4s[3 * kHid + tid] = p.b3 ? p.b3[tid] : 0.f;
+        }
+        __syncthreads();
+    }
+
+    const int quad = threadIdx.x / kQuadThreads;
+    const int qb = quad_bytes(f);
+    unsigned char* team_base = smraw + al16(SL.total);
+    const bool can_split = p.gorder != nullptr;     // descending sizes: a group only ever splits
+    int first = 0, nq = kQuads;                      // my group = quads [first, first + nq)
 
     for (;;) {
-        if (tid == 0) s_graph = atomicAdd(p.counter, 1);
-        __syncthreads();
-        if (s_graph >= p.num_graphs) break;
-        const int gi = p.gorder ? p.gorder[s_graph] : s_graph;
-        const int base = p.gptr[gi];
-        int n = p.gptr[gi + 1] - base;
-        if (n > nmax) {
-            if (tid == 0 && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_BATCH);
-            n = 0;
+        Team tm;
+        tm.tid = threadIdx.x - first * kQuadThreads;
+        tm.nthreads = nq * kQuadThreads;
+        tm.warp = tm.tid >> 5;
+        tm.nwarps = tm.nthreads >> 5;
+        tm.lane = threadIdx.x & 31;
+        tm.bar = 1 + first;
+        tm.smem = team_base + (size_t)first * qb;
+
+        if (tm.tid == 0) s_item[first] = atomicAdd(p.counter, 1);
+        tm.sync();
+        int q = s_item[first];
+        tm.sync();                                   // everyone has read the slot
+        if (q >= p.num_graphs) break;
+        const int gi = p.gorder ? p.gorder[q] : q;
+        const int n = p.gptr[gi + 1] - p.gptr[gi];
+        if (n > p.nmax) {                            // host promised this cannot happen
+            if (tm.tid == 0 && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_BATCH);
+            continue;
         }
-        const int keep = min(n, p.k);
-        float* pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
-        int32_t* perm_g = p.perm + (int64_t)gi * p.k;
-        for (int idx = keep * kCat + tid; idx < p.k * kCat; idx += nthreads) pooled_g[idx] = 0.f;
-        for (int r = keep + tid; r < p.k; r += nthreads) perm_g[r] = -1;
-        if (n == 0) { __syncthreads(); continue; }
-
-        const int np = (n + 15) & ~15;                   // rows/columns padded to the MMA tile
-        const int wpr = (np + 31) >> 5;
-        const bool dup = (p.gflags[gi] & 1) != 0;        // multigraph: walk the CSR instead
-        const int e0 = dup ? p.rowptr[base] : 0;
-        const int32_t* col_g = p.col + e0;
-        float* xc = p.xcat + (int64_t)base * p.ldc;
-
-        // ---- phase 0: adjacency bitmap (from K0b), per-node coefficients ----------------
-        load_bitmap(p.bitmap + p.bmoff[gi], bm, np * wpr, tid, nthreads);
-        for (int j = tid; j < np; j += nthreads) {
-            const float d = j < n ? p.dis[base + j] : 0.f;
-            cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
-            rs[j] = j < n ? row_coef(d, p.norm) : 0.f;
+        if (can_split) {
+            const int need = quads_needed(f, n);
+            bool refetch = false;
+            while (need < nq) {                      // the lower half keeps the graph,
+                nq >>= 1;                            // the upper half fetches its own
+                if (quad >= first + nq) { first += nq; refetch = true; break; }
+            }
+            if (refetch) continue;
+            tm.tid = threadIdx.x - first * kQuadThreads;
+            tm.nthreads = nq * kQuadThreads;
+            tm.warp = tm.tid >> 5;
+            tm.nwarps = tm.nthreads >> 5;
         }
-        if (dup)
-            for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
-        __syncthreads();
-
-        // ---- layer 1: F -> 32 (FMA pipe: arbitrary input range, tiny work) -----------------
-        if (f <= kSmallF) {
-            for (int idx = tid; idx < n * f; idx += nthreads) {
-                int j = idx / f, k = idx - j * f;
-                xs[k * L.nmaxp + j] = cs[j] * p.x[(int64_t)(base + j) * p.ldx + k];
-            }
-            // padding columns of the output planes must be finite zeros (0 * NaN = NaN)
-            for (int idx = tid; idx < (np - n) * kHid; idx += nthreads) {
-                const int c = idx / (np - n), j = n + idx - c * (np - n);
-                PA[c * S + j] = __float2half_rn(0.f);
-                PA[kHid * S + c * S + j] = __float2half_rn(0.f);
-            }
-            __syncthreads();
-            for (int i = warp; i < n; i += nwarps) {
-                const float r = rs[i];
-                float acc = b1s[lane];
-                for (int k = 0; k < f; ++k) {
-                    const float a = r * scalar_row_sum(xs + k * L.nmaxp, bm + i * wpr, wpr, dup, rp,
-                                                       col_g, base, i);
-                    acc = fmaf(a, w1t[k * kHid + lane], acc);
-                }
-                const float y = tanhf(acc);
-                xc[(int64_t)i * p.ldc + lane] = y;
-                store_split(PA, PA + kHid * S, lane * S + i, cs[i] * y);
-            }
-        } else {
-            // project first: c_j * (x_j W1^T) as planes in PB, then aggregate on the tensor cores
-            for (int j = warp; j < np; j += nwarps) {
-                float acc = 0.f;
-                if (j < n) {
-                    const float* xr = p.x + (int64_t)(base + j) * p.ldx;
-                    for (int k = 0; k < f; ++k) acc = fmaf(xr[k], w1t[k * kHid + lane], acc);
-                    acc *= cs[j];
-                    if (fabsf(acc) > 6.0e4f && p.status) atomicOr(p.status, DGCNN_GRAPH_RANGE);
-                }
-                store_split(PB, PB + kHid * S, lane * S + j, acc);
-            }
-            __syncthreads();
-            mma_layer<false, false>(PB, nullptr, b1s, PA, nullptr, nullptr, bm, wpr, n, S, dup, rp, col_g,
-                                    base, cs, rs, xc, p.ldc);
-        }
-        __syncthreads();
-
-        // ---- layers 2 and 3 on the tensor cores ------------------------------------------
-        mma_layer<true, false>(PA, w2p, b2s, PB, nullptr, nullptr, bm, wpr, n, S, dup, rp, col_g, base, cs,
-                               rs, xc + kHid, p.ldc);
-        __syncthreads();
-        mma_layer<true, true>(PB, w3p, b3s, nullptr, vpl, w4s, bm, wpr, n, S, dup, rp, col_g, base, cs,
-                              rs, xc + 2 * kHid, p.ldc);
-        __syncthreads();
-
-        // ---- layer 4: 32 -> 1, already projected into v: one 8-wide MMA column ---------------
-        {
-            const int g = lane >> 2, t = lane & 3;
-            const int tiles = np >> 4;
-            const uint32_t* v32[2] = {reinterpret_cast<const uint32_t*>(vpl),
-                                      reinterpret_cast<const uint32_t*>(vpl + S)};
-            for (int mt = warp; mt < tiles; mt += nwarps) {
-                const int row0 = mt * 16 + g, row1 = row0 + 8;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!dup) {
-                    for (int kt = 0; kt < tiles; ++kt) {
-                        uint32_t a[4];
-                        if (!adj_fragment(bm, wpr, row0, kt, t, a)) continue;
-#pragma unroll
-                        for (int pl = 0; pl < 2; ++pl) {
-                            const int idx = (kt * 16 + 2 * t) >> 1;
-                            const uint32_t b0 = g == 0 ? v32[pl][idx] : 0u;
-                            const uint32_t b1 = g == 0 ? v32[pl][idx + 4] : 0u;
-                            mma_f16(acc, a, b0, b1);
-                        }
-                    }
-                } else if (t == 0) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int row = half ? row1 : row0;
-                        if (row >= n) continue;
-                        float s = 0.f;
-                        for (int e = rp[row] - 1; e < rp[row + 1]; ++e) {
-                            const int j = e < rp[row] ? row : col_g[e] - base;
-                            s += __half2float(vpl[j]) + __half2float(vpl[S + j]);
-                        }
-                        acc[2 * half] = s;
-                    }
-                }
-                if (t == 0) {                                  // column 0 of the tile lives in t == 0
-                    if (row0 < n) {
-                        const float x4 = tanhf(fmaf(rs[row0], acc[0], b4));
-                        key[row0] = x4;
-                        xc[(int64_t)row0 * p.ldc + 3 * kHid] = x4;
-                    }
-                    if (row1 < n) {
-                        const float x4 = tanhf(fmaf(rs[row1], acc[2], b4));
-                        key[row1] = x4;
-                        xc[(int64_t)row1 * p.ldc + 3 * kHid] = x4;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- SortPool: order by x_4 descending, ties by node index -----------------------
-        uint64_t* comp = reinterpret_cast<uint64_t*>(PA);
-        if (n <= 256) {
-            for (int j = tid; j < n; j += nthreads)
-                comp[j] = ((uint64_t)descending_key_bits(key[j]) << 32) | (uint32_t)j;
-            __syncthreads();
-            for (int i = tid; i < n; i += nthreads) {
-                const uint64_t mine = comp[i];
-                int rank = 0;
-                for (int j = 0; j < n; ++j) rank += comp[j] < mine;
-                if (rank < keep) order[rank] = i;
-            }
-        } else {
-            const uint32_t pw = next_pow2((uint32_t)n);
-            for (uint32_t j = tid; j < pw; j += nthreads)
-                comp[j] = (j < (uint32_t)n)
-                              ? (((uint64_t)descending_key_bits(key[j]) << 32) | j) : ~0ull;
-            bitonic_sort_block(comp, pw);
-            for (int r = tid; r < keep; r += nthreads) order[r] = (int)(uint32_t)(comp[r] & 0xffffffffu);
-        }
-        __syncthreads();
-
-        // ---- gather the k winners (rows of x_cat this CTA just wrote: L2 hits) ------------
-        {
-            const int total = keep * kCat;
-            for (int i0 = tid; i0 < total; i0 += nthreads * 8) {
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int idx = i0 + u * nthreads;
-                    if (idx < total) {
-                        const int r = idx / kCat, c = idx - r * kCat;
-                        v[u] = xc[(int64_t)order[r] * p.ldc + c];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int idx = i0 + u * nthreads;
-                    if (idx < total) pooled_g[idx] = v[u];
-                }
-            }
-        }
-        for (int r = tid; r < keep; r += nthreads) perm_g[r] = base + order[r];
-        __syncthreads();
+        process_graph(p, tm, gi, smraw);
+        tm.sync();                                   // the slice is reused by the next graph
     }
 }
 
@@ -492,9 +594,9 @@ int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const
 int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes);
 
 static int mma_supported(int32_t f, int64_t max_nodes) {
-    if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 4096) return 0;
-    const MmaLayout L = mma_layout(f, stack_nmax_for(max_nodes));
-    return (size_t)L.total + 64 <= (size_t)kSmemBudget ? 1 : 0;
+    if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
+    const int np = (int)((max_nodes + 15) / 16 * 16);
+    return team_layout(f, np).total <= kQuads * quad_bytes(f) ? 1 : 0;
 }
 
 extern "C" int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes) {
@@ -545,19 +647,16 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     p.bitmap = bitmap; p.bmoff = bmoff; p.gflags = gflags;
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.w4 = w4; p.b4 = b4;
     p.xcat = xcat; p.ldc = ldc; p.pooled = pooled; p.perm = perm; p.k = k;
-    p.norm = norm; p.nmax = stack_nmax_for(max_nodes);
+    p.norm = norm; p.nmax = (int)max_nodes;
     p.gorder = gorder; p.counter = counter; p.status = status;
-    const size_t smem = (size_t)mma_layout(p.f, p.nmax).total;
+    // one CTA per SM with (almost) all of its shared memory: 4 quad slices + the weights
+    const size_t smem = (size_t)al16(shared_layout(p.f).total) + (size_t)kQuads * quad_bytes(p.f);
     if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stack_fwd_mma_kernel, kMmaThreads,
-                                                      smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    int64_t grid = (int64_t)per_sm * DGCNN_NUM_SMS;
+    int64_t grid = DGCNN_NUM_SMS;
     if (grid > num_graphs) grid = num_graphs;
-    stack_fwd_mma_kernel<<<(unsigned)grid, kMmaThreads, smem, st>>>(p);
+    stack_fwd_mma_kernel<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

@@ -335,21 +335,40 @@ static int stack_bwd_grid(int f, int nmax, int threads, size_t smem, int64_t num
 
 using namespace dgcnn;
 
-extern "C" int dgcnn_stack_bwd_supported(int32_t num_features, int64_t max_nodes) {
-    if (num_features < 1 || num_features > kMaxF || max_nodes < 1 || max_nodes > 4096) return 0;
+// tensor-core variant, graph_stack_bwd_mma.cu
+int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes);
+size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs);
+int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
+                        int64_t ldc, const float* x, int64_t ldx, int32_t f, const int32_t* rowptr_t,
+                        const int32_t* col_t, const float* dis, const int32_t* gptr,
+                        const int32_t* gorder, const uint32_t* bitmap, const int32_t* bmoff,
+                        const int32_t* gflags, const uint32_t* bitmap_t, const int32_t* bmoff_t,
+                        const int32_t* gflags_t, int64_t num_graphs, int64_t max_nodes, const float* w2,
+                        const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
+                        void* workspace, cudaStream_t st);
+
+static int fma_bwd_supported(int32_t num_features, int64_t max_nodes) {
+    if (num_features < 1 || num_features > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
     const int nmax = stack_nmax_for(max_nodes);
     const StackBwdLayout L = stack_bwd_layout(num_features, nmax, stack_threads_for(nmax) / 32);
     return (size_t)L.total * 4 + 64 <= (size_t)kSmemBudget ? 1 : 0;
+}
+
+extern "C" int dgcnn_stack_bwd_supported(int32_t num_features, int64_t max_nodes) {
+    return dgcnn_stack_bwd_mma_supported(num_features, max_nodes);
 }
 
 extern "C" int64_t dgcnn_stack_num_params(int32_t num_features) {
     return num_features < 1 ? 0 : grad_offsets(num_features).total;
 }
 
-extern "C" size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features) {
+extern "C" size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features, int64_t num_graphs) {
     if (num_features < 1) return 0;
-    // one partial gradient vector per CTA; at most 8 CTAs per SM are ever launched
-    return sizeof(float) * (size_t)grad_offsets(num_features).total * 8 * DGCNN_NUM_SMS + 256;
+    // FMA variant: one partial gradient vector per CTA (at most 8 CTAs per SM);
+    // tensor-core variant: one per graph
+    const size_t fma = sizeof(float) * (size_t)grad_offsets(num_features).total * 8 * DGCNN_NUM_SMS + 256;
+    const size_t mma = dgcnn_stack_bwd_mma_workspace_bytes(num_features, num_graphs);
+    return fma > mma ? fma : mma;
 }
 
 extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
@@ -360,8 +379,8 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
                                const uint32_t* bitmap_t, const int32_t* bmoff_t,
                                const int32_t* gflags_t,
                                int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w2,
-                               const float* w3, const float* w4, int32_t norm, float* grads,
-                               int32_t* status, void* workspace, size_t workspace_bytes,
+                               const float* w3, const float* w4, int32_t norm, int32_t variant,
+                               float* grads, int32_t* status, void* workspace, size_t workspace_bytes,
                                void* stream) {
     if (num_nodes < 0 || num_graphs < 0 || k < 1 || num_features < 1 || ldx < num_features ||
         ldc < kCat || !grads)
@@ -373,14 +392,21 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
         if (cudaMemsetAsync(grads, 0, sizeof(float) * G.total, st) != cudaSuccess) return DGCNN_ERR_CUDA;
         return DGCNN_OK;
     }
-    if (!dgcnn_stack_bwd_supported(num_features, max_nodes)) return DGCNN_ERR_UNSUPPORTED;
+    if (variant != DGCNN_STACK_MMA && variant != DGCNN_STACK_FMA) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (variant == DGCNN_STACK_MMA ? !dgcnn_stack_bwd_mma_supported(num_features, max_nodes)
+                                   : !fma_bwd_supported(num_features, max_nodes))
+        return DGCNN_ERR_UNSUPPORTED;
     if (num_graphs >= INT32_MAX || num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
     if (!bitmap || !bmoff || !gflags || !status) return DGCNN_ERR_INVALID_ARGUMENT;
     if (max_nodes > 1024) return DGCNN_ERR_UNSUPPORTED;
     if (!dpooled || !perm || !xcat || !x || !rowptr_t || !dis || !gptr || !w2 || !w3 || !w4)
         return DGCNN_ERR_INVALID_ARGUMENT;
-    if (!workspace || workspace_bytes < dgcnn_stack_bwd_workspace_bytes(num_features))
+    if (!workspace || workspace_bytes < dgcnn_stack_bwd_workspace_bytes(num_features, num_graphs))
         return DGCNN_ERR_WORKSPACE;
+    if (variant == DGCNN_STACK_MMA)
+        return dgcnn_stack_bwd_mma(dpooled, perm, k, xcat, ldc, x, ldx, num_features, rowptr_t, col_t, dis,
+                                   gptr, gorder, bitmap, bmoff, gflags, bitmap_t, bmoff_t, gflags_t,
+                                   num_graphs, max_nodes, w2, w3, w4, norm, grads, status, workspace, st);
 
     StackBwdParams p{};
     p.dpooled = dpooled; p.perm = perm; p.k = k; p.xcat = xcat; p.ldc = ldc;

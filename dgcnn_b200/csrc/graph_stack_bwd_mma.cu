@@ -1,0 +1,597 @@
+// Tensor-core version of the fused backward (autograd of model.py:28-35, train.py:40),
+// the mirror image of graph_stack_mma.cu.  One TEAM (1, 2 or 4 quads of a 512-thread CTA)
+// per graph; per layer l = 4..1:
+//
+//   dpre = dy * (1 - y^2)            row-local, db += column sums
+//   dh   = c_i * (A_hat^T . r dpre)  mma.sync: A^T from the bitmap (exact 0/1 fp16),
+//                                    r*dpre split hi/lo into fp16 planes
+//   dx   = dh W (+ pooled gradient)  mma.sync straight from the accumulator fragments
+//   dW  += dh^T x_in                 mma.sync: dh planes [c][node] x x_in planes [k][node]
+//
+// Gradients span many orders of magnitude, so each graph picks a power-of-two scale from
+// the largest pooled gradient it receives (exact to apply and to undo) before anything is
+// split into fp16 hi/lo pairs; a graph whose pooled gradient is all zero is skipped.
+//
+// Determinism without float atomics and without a fixed graph->CTA assignment: every graph
+// writes ITS OWN parameter-gradient vector to HBM; a second kernel sums the B vectors in
+// graph order.  (B x 2.2k floats = 4.5 MB on COLLAB-synth bs512.)
+#include "graph_mma.cuh"
+
+namespace dgcnn {
+
+struct StackBwdMmaParams {
+    const float* dpooled; const int32_t* perm; int k;
+    const float* xcat; int64_t ldc;
+    const float* x; int64_t ldx; int f;
+    const int32_t* rowptr_t; const int32_t* col_t; const float* dis; const int32_t* gptr;
+    const int32_t* gorder; int num_graphs;
+    const uint32_t* bitmap; const int32_t* bmoff; const int32_t* gflags;
+    const uint32_t* bitmap_t; const int32_t* bmoff_t; const int32_t* gflags_t;
+    const float* w2; const float* w3; const float* w4;
+    int norm; int nmax;
+    float* partials;     // [num_graphs][P]
+    int32_t* counter;
+    int32_t* status;
+};
+
+struct GradOffsetsM { int w1, b1, w2, b2, w3, b3, w4, b4, total; };
+
+__host__ __device__ inline GradOffsetsM grad_offsets_m(int f) {
+    GradOffsetsM g;
+    int o = 0;
+    g.w1 = o; o += kHid * f;
+    g.b1 = o; o += kHid;
+    g.w2 = o; o += kHid * kHid;
+    g.b2 = o; o += kHid;
+    g.w3 = o; o += kHid * kHid;
+    g.b3 = o; o += kHid;
+    g.w4 = o; o += kHid;
+    g.b4 = o; o += 1;
+    g.total = o;
+    return g;
+}
+
+// CTA-wide: W2^T, W3^T hi/lo planes [k][c] (B operand of dx = dh W), w4
+struct BwdShared { int w2p, w3p, w4, total; };
+__host__ __device__ inline BwdShared bwd_shared_layout() {
+    BwdShared L;
+    int o = 0;
+    L.w2p = o; o += 2 * kHid * kWPad * 2;
+    L.w3p = o; o += 2 * kHid * kWPad * 2;
+    L.w4 = o; o += kHid * 4;
+    L.total = o;
+    return L;
+}
+
+// per graph (bytes)
+struct BwdTeamLayout { int G, P, DH, PX, vpl, bm, cs, rs, hv, rank, rp, red, sacc, total; int S; };
+__host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np) {
+    BwdTeamLayout L;
+    L.S = np + 8;
+    const int wpr = (np + 31) >> 5;
+    int o = 0;
+    L.G = o; o += np * kHid * 4;                         // fp32 gradient w.r.t. the layer output
+    L.P = o; o += 2 * kHid * L.S * 2;                    // hi/lo planes of r * dpre * scale
+    L.DH = o; o += 2 * kHid * L.S * 2;                   // hi/lo planes of dh * scale
+    L.PX = o; o += 2 * kHid * L.S * 2;                   // hi/lo planes of x_in
+    L.vpl = o; o += al16(2 * L.S * 2);
+    L.bm = o; o += al16(np * wpr * 4);
+    L.cs = o; o += al16(np * 4);
+    L.rs = o; o += al16(np * 4);
+    L.hv = o; o += al16(np * 4);
+    L.rank = o; o += al16(np * 4);
+    L.rp = o; o += al16((np + 1) * 4);
+    L.red = o; o += (kCtaThreads / 32) * kHid * 4;
+    L.sacc = o; o += al16(grad_offsets_m(f).total * 4);
+    L.total = o;
+    return L;
+}
+
+__host__ __device__ inline int bwd_quad_bytes() {
+    return ((kSmemBudget - 1024 - bwd_shared_layout().total) / kQuads) & ~15;
+}
+
+__host__ __device__ inline int bwd_quads_needed(int f, int n) {
+    const int np = (n + 15) & ~15, tiles = np >> 4;
+    int q = tiles <= 4 ? 1 : (tiles <= 8 ? 2 : 4);
+    const int need = bwd_team_layout(f, np < 16 ? 16 : np).total, qb = bwd_quad_bytes();
+    while (q < kQuads && need > q * qb) q <<= 1;
+    return q;
+}
+
+// sum red[w][c] over the team's warps (c < 32)
+__device__ __forceinline__ float reduce_rows_t(const float* red, int nwarps, int c) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[w * kHid + c];
+    return s;
+}
+
+// dh tile(s) = c_i * (A_hat^T . P) for every 16-row tile owned by this warp; then
+//   - dh planes (still scaled) for the dW product,
+//   - if wp: dx = dh W via the fragments, unscaled, + pooled gradient of the slice -> Gout
+__device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, const __half* __restrict__ wp,
+                                              __half* __restrict__ DH, float* __restrict__ Gout,
+                                              const uint32_t* __restrict__ bm, int wpr, int n, int S,
+                                              bool dup, const int* __restrict__ rp,
+                                              const int32_t* __restrict__ col_g, int base,
+                                              const float* __restrict__ cs, const int* __restrict__ rank,
+                                              const float* __restrict__ dp, int offx, float inv_scale,
+                                              const Team& tm) {
+    const int lane = tm.lane, warp = tm.warp, nwarps = tm.nwarps;
+    const int g = lane >> 2, t = lane & 3;
+    const int tiles = (n + 15) >> 4;
+    const uint32_t* in32[2] = {reinterpret_cast<const uint32_t*>(P),
+                               reinterpret_cast<const uint32_t*>(P + kHid * S)};
+    for (int mt = warp; mt < tiles; mt += nwarps) {
+        const int row0 = mt * 16 + g, row1 = row0 + 8;
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        if (!dup) {
+            for (int kt = 0; kt < tiles; ++kt) {
+                uint32_t a[4];
+                if (!adj_fragment(bm, wpr, row0, kt, t, a)) continue;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int idx = ((nt * 8 + g) * S + kt * 16 + 2 * t) >> 1;
+                        mma_f16(acc[nt], a, in32[pl][idx], in32[pl][idx + 4]);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = half ? row1 : row0;
+                if (row >= n) continue;
+                for (int e = rp[row] - 1; e < rp[row + 1]; ++e) {
+                    const int j = e < rp[row] ? row : col_g[e] - base;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int idx = (nt * 8 + 2 * t + q) * S + j;
+                            acc[nt][2 * half + q] += __half2float(P[idx]) + __half2float(P[kHid * S + idx]);
+                        }
+                }
+            }
+        }
+        const float c0 = cs[row0], c1 = cs[row1];                        // 0 on padding rows
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            acc[nt][0] *= c0; acc[nt][1] *= c0; acc[nt][2] *= c1; acc[nt][3] *= c1;
+        }
+        {   // dh planes [channel][node] (scaled), the A operand of dW = dh^T x_in
+            __half* oh = DH;
+            __half* ol = DH + kHid * S;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int ch = nt * 8 + 2 * t + q;
+                    store_split(oh, ol, ch * S + row0, acc[nt][q]);
+                    store_split(oh, ol, ch * S + row1, acc[nt][2 + q]);
+                }
+        }
+        if (wp) {
+            float y[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) y[nt][0] = y[nt][1] = y[nt][2] = y[nt][3] = 0.f;
+            const uint32_t* wh = reinterpret_cast<const uint32_t*>(wp);
+            const uint32_t* wl = reinterpret_cast<const uint32_t*>(wp + kHid * kWPad);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                uint32_t ah[4], al[4];
+                split2(acc[2 * kk][0], acc[2 * kk][1], ah[0], al[0]);
+                split2(acc[2 * kk][2], acc[2 * kk][3], ah[1], al[1]);
+                split2(acc[2 * kk + 1][0], acc[2 * kk + 1][1], ah[2], al[2]);
+                split2(acc[2 * kk + 1][2], acc[2 * kk + 1][3], ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int widx = ((nt * 8 + g) * kWPad + kk * 16 + 2 * t) >> 1;
+                    const uint32_t h0 = wh[widx], h1 = wh[widx + 4];
+                    const uint32_t l0 = wl[widx], l1 = wl[widx + 4];
+                    mma_f16(y[nt], ah, h0, h1);
+                    mma_f16(y[nt], al, h0, h1);
+                    mma_f16(y[nt], ah, l0, l1);
+                }
+            }
+            // unscale, add the pooled gradient of x_in's slice, store as the next layer's G
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = half ? row1 : row0;
+                if (row >= n) continue;
+                const int r = rank[row];
+                const float* gp = r >= 0 ? dp + r * kCat + offx + 2 * t : nullptr;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    float v0 = y[nt][2 * half] * inv_scale, v1 = y[nt][2 * half + 1] * inv_scale;
+                    if (gp) { v0 += gp[nt * 8]; v1 += gp[nt * 8 + 1]; }
+                    *reinterpret_cast<float2*>(Gout + row * kHid + nt * 8 + 2 * t) = make_float2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, const Team& tm, int gi,
+                                                  const unsigned char* shraw, const uint32_t* gbm,
+                                                  const int32_t* gbo, const int32_t* gfl) {
+    const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
+    const int nthreads = tm.nthreads, nwarps = tm.nwarps;
+    const int f = p.f;
+    const GradOffsetsM GO = grad_offsets_m(f);
+    const BwdShared SL = bwd_shared_layout();
+    const __half* w2p = reinterpret_cast<const __half*>(shraw + SL.w2p);
+    const __half* w3p = reinterpret_cast<const __half*>(shraw + SL.w3p);
+    const float* w4s = reinterpret_cast<const float*>(shraw + SL.w4);
+    float* out = p.partials + (int64_t)gi * GO.total;
+
+    const int base = p.gptr[gi];
+    const int n = p.gptr[gi + 1] - base;
+    if (n == 0) {
+        for (int idx = tid; idx < GO.total; idx += nthreads) out[idx] = 0.f;
+        return;
+    }
+    const int keep = min(n, p.k);
+    const int np = (n + 15) & ~15;
+    const int wpr = (np + 31) >> 5;
+    const int tiles = np >> 4;
+    const BwdTeamLayout L = bwd_team_layout(f, np);
+    const int S = L.S;
+    unsigned char* sm = tm.smem;
+    float* G = reinterpret_cast<float*>(sm + L.G);
+    __half* P = reinterpret_cast<__half*>(sm + L.P);
+    __half* DH = reinterpret_cast<__half*>(sm + L.DH);
+    __half* PX = reinterpret_cast<__half*>(sm + L.PX);
+    __half* vpl = reinterpret_cast<__half*>(sm + L.vpl);
+    uint32_t* bm = reinterpret_cast<uint32_t*>(sm + L.bm);
+    float* cs = reinterpret_cast<float*>(sm + L.cs);
+    float* rs = reinterpret_cast<float*>(sm + L.rs);
+    float* hv = reinterpret_cast<float*>(sm + L.hv);
+    int* rank = reinterpret_cast<int*>(sm + L.rank);
+    int* rp = reinterpret_cast<int*>(sm + L.rp);
+    float* red0 = reinterpret_cast<float*>(sm + L.red);
+    float* sacc = reinterpret_cast<float*>(sm + L.sacc);
+
+    const bool dup = (gfl[gi] & 1) != 0;
+    const int e0 = dup ? p.rowptr_t[base] : 0;
+    const int32_t* col_g = p.col_t + e0;
+    const float* xc = p.xcat + (int64_t)base * p.ldc;
+    const float* dp = p.dpooled + (int64_t)gi * p.k * kCat;
+    const int32_t* perm_g = p.perm + (int64_t)gi * p.k;
+
+    // ---- phase 0: bitmap, coefficients, inverse permutation, gradient scale -----------------
+    load_bitmap(gbm + gbo[gi], bm, np * wpr, tid, nthreads);
+    for (int j = tid; j < np; j += nthreads) {
+        const float d = j < n ? p.dis[base + j] : 0.f;
+        cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
+        rs[j] = j < n ? row_coef(d, p.norm) : 0.f;
+        rank[j] = -1;
+    }
+    if (dup)
+        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr_t[base + j] - e0;
+    for (int idx = tid; idx < GO.total; idx += nthreads) sacc[idx] = 0.f;
+    float amax = 0.f;
+    for (int idx = tid; idx < keep * kCat; idx += nthreads) amax = fmaxf(amax, fabsf(dp[idx]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(DGCNN_FULL_MASK, amax, o));
+    if (lane == 0) red0[warp] = amax;
+    tm.sync();
+    for (int r = tid; r < keep; r += nthreads) {
+        const int node = perm_g[r] - base;
+        if ((unsigned)node < (unsigned)n) rank[node] = r;
+    }
+    amax = 0.f;
+    for (int w = 0; w < nwarps; ++w) amax = fmaxf(amax, red0[w]);
+    tm.sync();
+    if (!(amax > 0.f) || !(amax < 3.0e38f)) {
+        // nothing flows into this graph (or the gradient is not finite: propagate as zeros
+        // would hide it, so write NaN-free zeros only for the exact-zero case)
+        const float fillv = amax > 0.f ? amax * 0.f + (amax - amax) : 0.f;   // NaN if inf/nan
+        for (int idx = tid; idx < GO.total; idx += nthreads) out[idx] = fillv;
+        return;
+    }
+    // power-of-two scale: max |pooled gradient| -> about 2^6, leaving 2^9 of head room
+    int ex;
+    frexpf(amax, &ex);
+    const float scale = ldexpf(1.f, 6 - ex), inv_scale = ldexpf(1.f, ex - 6);
+
+    // ---- layer 4 (32 -> 1) --------------------------------------------------------------------
+    {
+        float dbp = 0.f;
+        for (int i = tid; i < np; i += nthreads) {
+            float v = 0.f;
+            if (i < n) {
+                const float y = xc[(int64_t)i * p.ldc + 3 * kHid];
+                const float gy = rank[i] >= 0 ? dp[rank[i] * kCat + 3 * kHid] : 0.f;
+                const float d = gy * (1.f - y * y);
+                dbp += d;
+                v = rs[i] * d * scale;
+            }
+            store_split(vpl, vpl + S, i, v);
+        }
+        dbp = warp_sum(dbp);
+        if (lane == 0) red0[warp] = dbp;
+    }
+    tm.sync();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < nwarps; ++w) s += red0[w];
+        sacc[GO.b4] = s;
+    }
+    {
+        const int g = lane >> 2, t = lane & 3;
+        const uint32_t* v32[2] = {reinterpret_cast<const uint32_t*>(vpl),
+                                  reinterpret_cast<const uint32_t*>(vpl + S)};
+        for (int mt = warp; mt < tiles; mt += nwarps) {
+            const int row0 = mt * 16 + g, row1 = row0 + 8;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!dup) {
+                for (int kt = 0; kt < tiles; ++kt) {
+                    uint32_t a[4];
+                    if (!adj_fragment(bm, wpr, row0, kt, t, a)) continue;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                        const int idx = (kt * 16 + 2 * t) >> 1;
+                        const uint32_t b0 = g == 0 ? v32[pl][idx] : 0u;
+                        const uint32_t b1 = g == 0 ? v32[pl][idx + 4] : 0u;
+                        mma_f16(acc, a, b0, b1);
+                    }
+                }
+            } else if (t == 0) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int row = half ? row1 : row0;
+                    if (row >= n) continue;
+                    float s = 0.f;
+                    for (int e = rp[row] - 1; e < rp[row + 1]; ++e) {
+                        const int j = e < rp[row] ? row : col_g[e] - base;
+                        s += __half2float(vpl[j]) + __half2float(vpl[S + j]);
+                    }
+                    acc[2 * half] = s;
+                }
+            }
+            if (t == 0) {
+                hv[row0] = cs[row0] * acc[0] * inv_scale;      // dh4
+                hv[row1] = cs[row1] * acc[2] * inv_scale;
+            }
+        }
+    }
+    tm.sync();
+    {   // dW4[k] += sum_i dh4[i] x3[i][k];  G3[i][k] = dh4[i] w4[k] + pooled gradient of x3
+        float dwp = 0.f;
+        const float w4k = w4s[lane];
+        for (int i = warp; i < n; i += nwarps) {
+            const float h = hv[i];
+            dwp = fmaf(h, xc[(int64_t)i * p.ldc + 2 * kHid + lane], dwp);
+            const int r = rank[i];
+            const float gp = r >= 0 ? dp[r * kCat + 2 * kHid + lane] : 0.f;
+            G[i * kHid + lane] = fmaf(h, w4k, gp);
+        }
+        red0[warp * kHid + lane] = dwp;
+    }
+    tm.sync();
+    if (tid < kHid) sacc[GO.w4 + tid] = reduce_rows_t(red0, nwarps, tid);
+    tm.sync();
+
+    // ---- layers 3, 2, 1 -------------------------------------------------------------------------
+#pragma unroll 1
+    for (int layer = 3; layer >= 1; --layer) {
+        const int offy = (layer - 1) * kHid;
+        const int offx = (layer - 2) * kHid;             // slice of x_in (layers 3 and 2)
+        // A: P planes <- r * dpre * scale, db; PX planes <- x_in (for dW)
+        {
+            float dbp = 0.f;
+            __half* ph = P;  __half* pl = P + kHid * S;
+            __half* xh = PX; __half* xl = PX + kHid * S;
+            for (int i = warp; i < np; i += nwarps) {
+                float sc = 0.f, xv = 0.f;
+                if (i < n) {
+                    const float y = xc[(int64_t)i * p.ldc + offy + lane];
+                    const float d = G[i * kHid + lane] * (1.f - y * y);
+                    dbp += d;
+                    sc = rs[i] * d * scale;
+                    if (layer >= 2) xv = xc[(int64_t)i * p.ldc + offx + lane];
+                }
+                store_split(ph, pl, lane * S + i, sc);
+                if (layer >= 2) store_split(xh, xl, lane * S + i, xv);
+            }
+            red0[warp * kHid + lane] = dbp;
+        }
+        tm.sync();
+        if (tid < kHid) {
+            const int ob = layer == 3 ? GO.b3 : (layer == 2 ? GO.b2 : GO.b1);
+            sacc[ob + tid] = reduce_rows_t(red0, nwarps, tid);
+        }
+        // B: dh planes, and G <- dx (layers 3, 2)
+        bwd_mma_layer(P, layer == 3 ? w3p : (layer == 2 ? w2p : nullptr), DH, G, bm, wpr, n, S, dup, rp,
+                      col_g, base, cs, rank, dp, offx, inv_scale, tm);
+        tm.sync();
+        // C: parameter gradient of the layer
+        if (layer >= 2) {
+            // dW[c][k] = sum_i dh[i][c] x_in[i][k]: 8 output tiles (2 x 4), one per warp
+            const int ow = layer == 3 ? GO.w3 : GO.w2;
+            const int g = lane >> 2, t = lane & 3;
+            const uint32_t* dh32[2] = {reinterpret_cast<const uint32_t*>(DH),
+                                       reinterpret_cast<const uint32_t*>(DH + kHid * S)};
+            const uint32_t* px32[2] = {reinterpret_cast<const uint32_t*>(PX),
+                                       reinterpret_cast<const uint32_t*>(PX + kHid * S)};
+            for (int tile = warp; tile < 8; tile += nwarps) {
+                const int mc = tile >> 2, nk = tile & 3;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int kt = 0; kt < tiles; ++kt) {
+                    const int ia = ((16 * mc + g) * S + kt * 16 + 2 * t) >> 1;
+                    const int ib = ((8 * nk + g) * S + kt * 16 + 2 * t) >> 1;
+                    uint32_t ah[4], al[4];
+                    ah[0] = dh32[0][ia]; ah[1] = dh32[0][ia + 4 * S]; ah[2] = dh32[0][ia + 4];
+                    ah[3] = dh32[0][ia + 4 * S + 4];
+                    al[0] = dh32[1][ia]; al[1] = dh32[1][ia + 4 * S]; al[2] = dh32[1][ia + 4];
+                    al[3] = dh32[1][ia + 4 * S + 4];
+                    const uint32_t bh0 = px32[0][ib], bh1 = px32[0][ib + 4];
+                    const uint32_t bl0 = px32[1][ib], bl1 = px32[1][ib + 4];
+                    mma_f16(acc, ah, bh0, bh1);
+                    mma_f16(acc, al, bh0, bh1);
+                    mma_f16(acc, ah, bl0, bl1);
+                }
+                float* o = sacc + ow + (16 * mc + g) * kHid + 8 * nk + 2 * t;
+                o[0] = acc[0] * inv_scale; o[1] = acc[1] * inv_scale;
+                o[8 * kHid] = acc[2] * inv_scale; o[8 * kHid + 1] = acc[3] * inv_scale;
+            }
+        } else {
+            // dW1[c][k] = sum_i dh[i][c] x0[i][k], k < F (any F): FMA, dh rebuilt from its planes
+            const __half* dhh = DH;
+            const __half* dhl = DH + kHid * S;
+            for (int o = tid; o < kHid * f; o += nthreads) {
+                const int c = o & 31, k = o >> 5;
+                const float* xr = p.x + (int64_t)base * p.ldx + k;
+                float a0 = 0.f;
+                for (int i = 0; i < n; ++i) {
+                    const float dh = __half2float(dhh[c * S + i]) + __half2float(dhl[c * S + i]);
+                    a0 = fmaf(dh, xr[(int64_t)i * p.ldx], a0);
+                }
+                sacc[GO.w1 + c * f + k] = a0 * inv_scale;
+            }
+        }
+        tm.sync();
+    }
+
+    // this graph's parameter-gradient vector
+    for (int idx = tid; idx < GO.total; idx += nthreads) out[idx] = sacc[idx];
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdMmaParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ int s_item[kQuads];
+    const BwdShared SL = bwd_shared_layout();
+    {
+        const int tid = threadIdx.x, nthreads = blockDim.x;
+        __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
+        __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
+        float* w4s = reinterpret_cast<float*>(smraw + SL.w4);
+        // transposed planes [k][c]: the "col" operand of dx[k] = sum_c dh[c] W[c][k]
+        for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
+            const int c = idx >> 5, k = idx & 31;
+            store_split(w2p, w2p + kHid * kWPad, k * kWPad + c, p.w2[idx]);
+            store_split(w3p, w3p + kHid * kWPad, k * kWPad + c, p.w3[idx]);
+        }
+        if (tid < kHid) w4s[tid] = p.w4[tid];
+        __syncthreads();
+    }
+    // A_hat^T: the forward bitmap when K0 proved the batch symmetric, else the transposed one
+    const bool use_t = p.status && (*p.status & DGCNN_GRAPH_GENERIC) && p.bitmap_t;
+    const uint32_t* gbm = use_t ? p.bitmap_t : p.bitmap;
+    const int32_t* gbo = use_t ? p.bmoff_t : p.bmoff;
+    const int32_t* gfl = use_t ? p.gflags_t : p.gflags;
+
+    const int quad = threadIdx.x / kQuadThreads;
+    const int qb = bwd_quad_bytes();
+    unsigned char* team_base = smraw + al16(SL.total);
+    const bool can_split = p.gorder != nullptr;
+    int first = 0, nq = kQuads;
+
+    for (;;) {
+        Team tm;
+        tm.tid = threadIdx.x - first * kQuadThreads;
+        tm.nthreads = nq * kQuadThreads;
+        tm.warp = tm.tid >> 5;
+        tm.nwarps = tm.nthreads >> 5;
+        tm.lane = threadIdx.x & 31;
+        tm.bar = 1 + first;
+        tm.smem = team_base + (size_t)first * qb;
+
+        if (tm.tid == 0) s_item[first] = atomicAdd(p.counter, 1);
+        tm.sync();
+        const int q = s_item[first];
+        tm.sync();
+        if (q >= p.num_graphs) break;
+        const int gi = p.gorder ? p.gorder[q] : q;
+        const int n = p.gptr[gi + 1] - p.gptr[gi];
+        if (n > p.nmax) {
+            if (tm.tid == 0 && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_BATCH);
+            continue;
+        }
+        if (can_split) {
+            const int need = bwd_quads_needed(p.f, n);
+            bool refetch = false;
+            while (need < nq) {
+                nq >>= 1;
+                if (quad >= first + nq) { first += nq; refetch = true; break; }
+            }
+            if (refetch) continue;
+            tm.tid = threadIdx.x - first * kQuadThreads;
+            tm.nthreads = nq * kQuadThreads;
+            tm.warp = tm.tid >> 5;
+            tm.nwarps = tm.nthreads >> 5;
+        }
+        bwd_process_graph(p, tm, gi, smraw, gbm, gbo, gfl);
+        tm.sync();
+    }
+}
+
+// grads[o] = sum over graphs, in graph order (deterministic)
+__global__ void __launch_bounds__(256)
+stack_bwd_reduce_graphs(const float* __restrict__ partials, int parts, int total,
+                        float* __restrict__ grads) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = 0;
+    for (; b + 3 < parts; b += 4) {
+        s0 += partials[(int64_t)b * total + o];
+        s1 += partials[(int64_t)(b + 1) * total + o];
+        s2 += partials[(int64_t)(b + 2) * total + o];
+        s3 += partials[(int64_t)(b + 3) * total + o];
+    }
+    for (; b < parts; ++b) s0 += partials[(int64_t)b * total + o];
+    grads[o] = (s0 + s1) + (s2 + s3);
+}
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes) {
+    if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
+    const int np = (int)((max_nodes + 15) / 16 * 16);
+    return bwd_team_layout(f, np).total <= kQuads * bwd_quad_bytes() ? 1 : 0;
+}
+
+size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs) {
+    return sizeof(float) * (size_t)grad_offsets_m(f).total * (size_t)(num_graphs > 0 ? num_graphs : 1) + 512;
+}
+
+int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
+                        int64_t ldc, const float* x, int64_t ldx, int32_t f, const int32_t* rowptr_t,
+                        const int32_t* col_t, const float* dis, const int32_t* gptr,
+                        const int32_t* gorder, const uint32_t* bitmap, const int32_t* bmoff,
+                        const int32_t* gflags, const uint32_t* bitmap_t, const int32_t* bmoff_t,
+                        const int32_t* gflags_t, int64_t num_graphs, int64_t max_nodes, const float* w2,
+                        const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
+                        void* workspace, cudaStream_t st) {
+    StackBwdMmaParams p{};
+    p.dpooled = dpooled; p.perm = perm; p.k = k; p.xcat = xcat; p.ldc = ldc;
+    p.x = x; p.ldx = ldx; p.f = f;
+    p.rowptr_t = rowptr_t; p.col_t = col_t; p.dis = dis; p.gptr = gptr; p.gorder = gorder;
+    p.num_graphs = (int)num_graphs;
+    p.bitmap = bitmap; p.bmoff = bmoff; p.gflags = gflags;
+    p.bitmap_t = bitmap_t; p.bmoff_t = bmoff_t; p.gflags_t = gflags_t;
+    p.w2 = w2; p.w3 = w3; p.w4 = w4; p.norm = norm; p.nmax = (int)max_nodes;
+    uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    p.counter = reinterpret_cast<int32_t*>(aligned);
+    p.partials = reinterpret_cast<float*>(aligned + 256);
+    p.status = status;
+    if (cudaMemsetAsync(p.counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
+    const size_t smem = (size_t)al16(bwd_shared_layout().total) + (size_t)kQuads * bwd_quad_bytes();
+    if (cudaFuncSetAttribute(stack_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    int64_t grid = DGCNN_NUM_SMS;
+    if (grid > num_graphs) grid = num_graphs;
+    stack_bwd_mma_kernel<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const int total = grad_offsets_m(f).total;
+    stack_bwd_reduce_graphs<<<(total + 255) / 256, 256, 0, st>>>(p.partials, (int)num_graphs, total, grads);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}

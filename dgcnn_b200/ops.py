@@ -342,14 +342,15 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     ws = [w.contiguous() for w in weights]
     total = int(lib.dgcnn_stack_num_params(f))
     grads = torch.empty(total, dtype=torch.float32, device=x.device)
-    wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f), x.device)
+    wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f, b), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_bwd(_ptr(dpooled), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
                                  _ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr_t), _ptr(graph.col_t),
                                  _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder),
                                  _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags),
                                  _ptr(graph.bitmap_t), _ptr(graph.bmoff_t), _ptr(graph.gflags_t), n, b,
-                                 int(graph.max_nodes), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm), _ptr(grads),
+                                 int(graph.max_nodes), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm),
+                                 int(STACK_VARIANT), _ptr(grads),
                                  _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
     _lib.check(rc, "stack_bwd")
     LAUNCHES["stack_bwd"] += 2 if (b > 0 and n > 0) else 0

@@ -207,8 +207,9 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
 /* ------------------------------------------------------------------------
  * KSB  fused backward of the hot path (autograd of model.py:28-35, train.py:40),
  * companion of dgcnn_stack_fwd: from the gradient of `pooled` to the gradients of
- * the eight GraphConv parameters, one CTA per graph, two launches (per-CTA partial
- * sums + an ordered reduction: deterministic, no float atomics).
+ * the eight GraphConv parameters, one thread team per graph, two launches (per-graph
+ * partial gradient vectors + a reduction in graph order: deterministic, no float
+ * atomics).  `variant` as for dgcnn_stack_fwd.
  *   grads: flat [dgcnn_stack_num_params(F)] in PyG parameter order
  *     conv1.lin.weight [32,F] | conv1.bias [32] | conv2.lin.weight [32,32] | conv2.bias
  *     | conv3.lin.weight | conv3.bias | conv4.lin.weight [1,32] | conv4.bias [1]
@@ -217,7 +218,7 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
  * ------------------------------------------------------------------------ */
 int dgcnn_stack_bwd_supported(int32_t num_features, int64_t max_nodes);
 int64_t dgcnn_stack_num_params(int32_t num_features);
-size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features);
+size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features, int64_t num_graphs);
 int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                     const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                     int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
@@ -226,7 +227,7 @@ int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                     const uint32_t* bitmap_t, const int32_t* bmoff_t, const int32_t* gflags_t,
                     int64_t num_nodes, int64_t num_graphs,
                     int64_t max_nodes, const float* w2, const float* w3, const float* w4,
-                    int32_t norm, float* grads, int32_t* status,
+                    int32_t norm, int32_t variant, float* grads, int32_t* status,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

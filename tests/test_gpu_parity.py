@@ -525,8 +525,9 @@ def test_fused_stack_forward_matches_oracle_and_per_layer(case, variant):
     np.testing.assert_array_equal(pooled.detach().cpu().numpy(), ro.numpy())
 
 
+@pytest.mark.parametrize("variant", ["mma", "fma"])
 @pytest.mark.parametrize("case", STACK_CASES, ids=[c[0] for c in STACK_CASES])
-def test_fused_stack_backward_matches_oracle_and_per_layer(case):
+def test_fused_stack_backward_matches_oracle_and_per_layer(case, variant):
     """KSB (two launches) against float64 autograd of the oracle and against K3/K4.  The
     oracle continues from OUR permutation (validated bit-exact above) so that near-tied
     keys cannot turn a legitimate rank swap into a gradient mismatch."""
@@ -542,6 +543,8 @@ def test_fused_stack_backward_matches_oracle_and_per_layer(case):
 
     def run(fused_flag):
         dg.set_fused(fused_flag)
+        old_variant = ops.STACK_VARIANT
+        ops.STACK_VARIANT = ops.STACK_FMA if variant == "fma" else ops.STACK_MMA
         try:
             ws = [dev(z[f"w{i}"]).requires_grad_(True) for i in range(1, 5)]
             bs = [dev(z[f"b{i}"]).requires_grad_(True) for i in range(1, 5)]
@@ -551,6 +554,7 @@ def test_fused_stack_backward_matches_oracle_and_per_layer(case):
             assert (ops.LAUNCHES["stack_bwd"] - before == 2) == fused_flag
             return [w.grad.cpu() for w in ws], [b_.grad.cpu() for b_ in bs], perm.cpu().long()
         finally:
+            ops.STACK_VARIANT = old_variant
             dg.set_fused(True)
 
     def oracle_grads(perm):

@@ -529,22 +529,32 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdM
     }
 }
 
-// grads[o] = sum over graphs, in graph order (deterministic)
+// grads[o] = sum over graphs (deterministic: fixed partition, fixed order).  Block =
+// 32 outputs x 8 graph lanes: lane y sums graphs y, y+8, ... (coalesced 128 B rows), then
+// the 8 lane sums are added in order.
 __global__ void __launch_bounds__(256)
 stack_bwd_reduce_graphs(const float* __restrict__ partials, int parts, int total,
                         float* __restrict__ grads) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= total) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int b = 0;
-    for (; b + 3 < parts; b += 4) {
-        s0 += partials[(int64_t)b * total + o];
-        s1 += partials[(int64_t)(b + 1) * total + o];
-        s2 += partials[(int64_t)(b + 2) * total + o];
-        s3 += partials[(int64_t)(b + 3) * total + o];
+    __shared__ float red[8][33];
+    const int ox = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + ox;
+    float s0 = 0.f, s1 = 0.f;
+    if (o < total) {
+        int b = gy;
+        for (; b + 8 < parts; b += 16) {
+            s0 += partials[(int64_t)b * total + o];
+            s1 += partials[(int64_t)(b + 8) * total + o];
+        }
+        if (b < parts) s0 += partials[(int64_t)b * total + o];
     }
-    for (; b < parts; ++b) s0 += partials[(int64_t)b * total + o];
-    grads[o] = (s0 + s1) + (s2 + s3);
+    red[gy][ox] = s0 + s1;
+    __syncthreads();
+    if (gy == 0 && o < total) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][ox];
+        grads[o] = s;
+    }
 }
 
 }  // namespace dgcnn
@@ -591,7 +601,7 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     stack_bwd_mma_kernel<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int total = grad_offsets_m(f).total;
-    stack_bwd_reduce_graphs<<<(total + 255) / 256, 256, 0, st>>>(p.partials, (int)num_graphs, total, grads);
+    stack_bwd_reduce_graphs<<<(total + 31) / 32, 256, 0, st>>>(p.partials, (int)num_graphs, total, grads);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

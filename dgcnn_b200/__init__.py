@@ -5,8 +5,9 @@ from .ops import (ACT_NONE, ACT_TANH, NORM_RW, NORM_SYM, Graph, build_graph, gra
                   stack_fwd_supported)
 from .nn import (GCNConv, GraphConvolution, Model, SortAggregation, SortPool,
                  classifier_in_features, fused_enabled, graph_conv_stack, remove_self_loops,
-                 set_fused)
+                 set_fused, set_custom_tail, custom_tail_enabled)
 from .synth import CONFIGS, GraphBatch, collate, make_batch, make_graphs
 from .dp import GradBucket, shard_bounds
+from .optim import FlatAdam
 
 __version__ = "0.1.0"

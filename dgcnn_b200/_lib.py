@@ -10,7 +10,7 @@ import os
 import shutil
 import subprocess
 import threading
-from ctypes import c_char_p, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -80,6 +80,14 @@ SIGNATURES = {
                                   c_int64, c_void_p, c_void_p, c_void_p,
                                   c_int32, c_int32, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
+    "dgcnn_tail_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "dgcnn_tail_fwd": (c_int32, [c_void_p, c_int64, c_int32] + [c_void_p] * 8 +
+                       [c_int32, c_int32, c_uint64, c_void_p] + [c_void_p] * 6 +
+                       [c_void_p, c_size_t, c_void_p]),
+    "dgcnn_tail_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32] + [c_void_p] * 4 + [c_int32] +
+                       [c_void_p] * 6 + [c_void_p] * 9 + [c_void_p, c_size_t, c_void_p]),
+    "dgcnn_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_float, c_float, c_float, c_float, c_void_p]),
     "dgcnn_sort_pool_bwd": (c_int32, [c_void_p, c_void_p, c_int64,
                                       c_int32, c_int32, c_void_p, c_int64, c_int64,
                                       c_void_p]),

@@ -1,0 +1,646 @@
+// KT -- the dense tail of the model, model.py:36-43, forward and backward, plus a flat Adam
+// (train.py:41).  SURVEY.md 8f rows N2/N3: the callers either side of the graph hot path.
+//
+//   pooled [B, k*97] --view--> [B,1,k*97]
+//   conv5  Conv1d(1,16,97,97) + ReLU      model.py:19,37   (kernel == stride: a per-row 97->16 linear)
+//   pool   MaxPool1d(2,2)                 model.py:20,38
+//   conv6  Conv1d(16,32,5,1) + ReLU       model.py:19,39
+//   fc1    Linear(32*(k/2-4),128) + ReLU  model.py:21,41
+//   drop   Dropout(0.5)                   model.py:22,42
+//   fc2    Linear(128,C) + log_softmax    model.py:23,43
+//
+// Stock torch runs this as ~60 small launches (cuDNN implicit-GEMM convolutions, layout
+// shuffles, separate bias/ReLU/pool kernels, cuBLAS SIMT GEMMs picked for the wrong shape)
+// that cost 5x the graph kernels once those are fused.  Here: 5 forward and 9 backward
+// launches of plain fp32 FMA kernels, every reduction in a fixed order (no float atomics).
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int kC5 = 16, kKW = 97, kC6 = 32, kK6 = 5, kFc = 128;
+
+// ------------------------------------------------------------------------------------------
+// conv5 + ReLU + MaxPool(2,2): one warp per pair of pooled rows (2j, 2j+1 are adjacent in
+// memory: 194 contiguous floats).  lane = (row, channel).  h1[b][c][j], arg[b][c][j] = 0/1
+// the winning row, 2 when the max is not positive (ReLU dead: no gradient).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tail_c5_fwd(const float* __restrict__ pooled, int64_t B, int k, int L1, const float* __restrict__ w5,
+            const float* __restrict__ b5, float* __restrict__ h1, uint8_t* __restrict__ arg) {
+    __shared__ float w5t[kKW * kC5];
+    __shared__ float sb[kC5];
+    __shared__ float sx[8][2 * kKW + 2];
+    for (int idx = threadIdx.x; idx < kKW * kC5; idx += 256) {
+        int c = idx / kKW, i = idx - c * kKW;
+        w5t[i * kC5 + c] = w5[idx];
+    }
+    if (threadIdx.x < kC5) sb[threadIdx.x] = b5[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rowsel = lane >> 4, c = lane & 15;
+    const int64_t pairs = B * L1;
+    for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += (int64_t)gridDim.x * 8) {
+        const int64_t b = pr / L1;
+        const int j = (int)(pr - b * L1);
+        const float* src = pooled + (b * k + 2 * j) * kKW;
+        for (int idx = lane; idx < 2 * kKW; idx += 32) sx[warp][idx] = src[idx];
+        __syncwarp();
+        const float* xr = sx[warp] + rowsel * kKW;
+        float acc = sb[c];
+#pragma unroll 4
+        for (int i = 0; i < kKW; ++i) acc = fmaf(w5t[i * kC5 + c], xr[i], acc);
+        const float zr = fmaxf(acc, 0.f);
+        const float other = __shfl_xor_sync(DGCNN_FULL_MASK, zr, 16);
+        if (rowsel == 0) {
+            const float m = fmaxf(zr, other);
+            const int64_t o = (b * kC5 + c) * L1 + j;
+            h1[o] = m;
+            arg[o] = (uint8_t)(m <= 0.f ? 2 : (zr >= other ? 0 : 1));
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conv6 + ReLU: one CTA per graph; lane = output channel, a warp walks output positions.
+// h2 is written flattened as torch's x.view(B,-1) sees it: [b][o * L2 + t].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tail_c6_fwd(const float* __restrict__ h1, int64_t B, int L1, const float* __restrict__ w6,
+            const float* __restrict__ b6, float* __restrict__ h2) {
+    extern __shared__ float sm[];
+    float* w6t = sm;                         // [(c*5+d)][o]
+    float* sb = sm + kC5 * kK6 * kC6;        // [32]
+    float* h1s = sb + kC6;                   // [16][L1]
+    const int L2 = L1 - (kK6 - 1);
+    for (int idx = threadIdx.x; idx < kC6 * kC5 * kK6; idx += 256) {
+        int o = idx / (kC5 * kK6), r = idx - o * (kC5 * kK6);
+        w6t[r * kC6 + o] = w6[idx];
+    }
+    if (threadIdx.x < kC6) sb[threadIdx.x] = b6[threadIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) h1s[idx] = h1[b * kC5 * L1 + idx];
+        __syncthreads();
+        for (int t = warp; t < L2; t += 8) {
+            float acc = sb[lane];
+#pragma unroll
+            for (int c = 0; c < kC5; ++c)
+#pragma unroll
+                for (int d = 0; d < kK6; ++d)
+                    acc = fmaf(w6t[(c * kK6 + d) * kC6 + lane], h1s[c * L1 + t + d], acc);
+            h2[b * kC6 * L2 + lane * L2 + t] = fmaxf(acc, 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 GEMM  C[m][n] = sum_k A(m,k) * Bm(k,n)  on the FMA pipe, 32 x 128 tiles, 256 threads,
+// 2 x 8 outputs per thread with interleaved ownership (conflict-free scalar shared loads for
+// every operand layout).  A_KM: A is stored [k][m] (else [m][k]); B_KN: Bm is stored [k][n]
+// (else [n][k]).  blockIdx.z splits K; each split writes its own [M][N] slab of C (the
+// caller adds the slabs in order).  RELU_MASK: C *= (mask > 0), the ReLU backward.
+// ------------------------------------------------------------------------------------------
+template <bool A_KM, bool B_KN, bool RELU_MASK>
+__global__ void __launch_bounds__(256)
+gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm, int64_t ldb,
+         float* __restrict__ C, int M, int N, int K, int kchunk, const float* __restrict__ mask) {
+    constexpr int BM = 32, BN = 128, BK = 32, BMP = BM + 1, BNP = BN + 1;
+    __shared__ float As[BK * BMP];
+    __shared__ float Bs[BK * BNP];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    float acc[2][8];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        // A tile -> As[kk][m]
+#pragma unroll
+        for (int r = 0; r < (BM * BK) / 256; ++r) {
+            const int idx = threadIdx.x + 256 * r;
+            int kk, m;
+            if (A_KM) { kk = idx / BM; m = idx - kk * BM; } else { m = idx / BK; kk = idx - m * BK; }
+            const int gm = m0 + m, gk = k0 + kk;
+            float v = 0.f;
+            if (gm < M && gk < kend) v = A_KM ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+            As[kk * BMP + m] = v;
+        }
+        // B tile -> Bs[kk][n]
+#pragma unroll
+        for (int r = 0; r < (BN * BK) / 256; ++r) {
+            const int idx = threadIdx.x + 256 * r;
+            int kk, n;
+            if (B_KN) { kk = idx / BN; n = idx - kk * BN; } else { n = idx / BK; kk = idx - n * BK; }
+            const int gn = n0 + n, gk = k0 + kk;
+            float v = 0.f;
+            if (gn < N && gk < kend) v = B_KN ? Bm[(int64_t)gk * ldb + gn] : Bm[(int64_t)gn * ldb + gk];
+            Bs[kk * BNP + n] = v;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < BK; ++kk) {
+            const float a0 = As[kk * BMP + ty], a1 = As[kk * BMP + ty + 16];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float bv = Bs[kk * BNP + tx + 16 * q];
+                acc[0][q] = fmaf(a0, bv, acc[0][q]);
+                acc[1][q] = fmaf(a1, bv, acc[1][q]);
+            }
+        }
+        __syncthreads();
+    }
+    float* out = C + (int64_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int gm = m0 + ty + 16 * p;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int gn = n0 + tx + 16 * q;
+            if (gn >= N) continue;
+            float v = acc[p][q];
+            if (RELU_MASK) v = mask[(int64_t)gm * N + gn] > 0.f ? v : 0.f;
+            out[(int64_t)gm * N + gn] = v;
+        }
+    }
+}
+
+// 32-bit mix (murmur3 finaliser) of (seed, offset, index): one dropout decision per element
+__device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t offset, uint32_t idx) {
+    uint32_t h = (uint32_t)seed ^ (uint32_t)(seed >> 32) ^ ((uint32_t)offset * 0x9E3779B9u) ^
+                 (uint32_t)(offset >> 32);
+    h ^= idx * 0x85EBCA6Bu + 0x7F4A7C15u;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+// fc1 epilogue: sum the split-K slabs in order, + bias, ReLU, Dropout(0.5) when training.
+// keep[b][j] = 0 dropped (or ReLU dead), else the multiplier applied (1 or 2) as uint8.
+__global__ void __launch_bounds__(256)
+tail_fc1_epilogue(const float* __restrict__ slabs, int splits, int64_t total, const float* __restrict__ bias,
+                  int training, uint64_t seed, const int64_t* __restrict__ rng_offset,
+                  float* __restrict__ h3, uint8_t* __restrict__ keep) {
+    const uint64_t off = (training && rng_offset) ? (uint64_t)*rng_offset : 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        float s = bias[i % kFc];
+        for (int sp = 0; sp < splits; ++sp) s += slabs[(int64_t)sp * total + i];
+        s = fmaxf(s, 0.f);
+        uint8_t kp = s > 0.f ? 1 : 0;
+        if (training) {
+            if (mix32(seed, off, (uint32_t)i) & 0x80000000u) { s *= 2.f; kp = kp ? 2 : 0; }
+            else { s = 0.f; kp = 0; }
+        }
+        h3[i] = s;
+        keep[i] = kp;
+    }
+}
+
+// fc2 + log_softmax: one warp per graph (C <= 32); the last block bumps the dropout offset
+__global__ void __launch_bounds__(256)
+tail_fc2_lsm_fwd(const float* __restrict__ h3, int64_t B, int C, const float* __restrict__ w2,
+                 const float* __restrict__ b2, float* __restrict__ logp, int64_t* rng_offset) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+        const float* hr = h3 + b * kFc;
+        float mylogit = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            float s = 0.f;
+            for (int j = lane; j < kFc; j += 32) s = fmaf(hr[j], w2[c * kFc + j], s);
+            s = warp_sum(s) + b2[c];
+            if (lane == c) mylogit = s;
+        }
+        float mx = mylogit;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(DGCNN_FULL_MASK, mx, o));
+        const float e = lane < C ? expf(mylogit - mx) : 0.f;
+        const float lse = mx + logf(warp_sum(e));
+        if (lane < C) logp[b * C + lane] = mylogit - lse;
+    }
+    if (rng_offset && blockIdx.x == 0 && threadIdx.x == 0) *rng_offset += 1;
+}
+
+// ---- backward -----------------------------------------------------------------------------
+// fc2 / log_softmax backward, single CTA: dlogit = dlogp - softmax * sum(dlogp);
+// dz3 = (dlogit W2) * keep;  dW2 = dlogit^T h3;  db2;  db_fc1 = column sums of dz3.
+__global__ void __launch_bounds__(1024)
+tail_fc2_bwd(const float* __restrict__ dlogp, const float* __restrict__ logp, const float* __restrict__ h3,
+             const uint8_t* __restrict__ keep, int64_t B, int C, const float* __restrict__ w2,
+             float* __restrict__ dlogit_ws, float* __restrict__ dz3, float* __restrict__ dw2,
+             float* __restrict__ db2, float* __restrict__ dbf1) {
+    const int tid = threadIdx.x;
+    // 1. dlogit [B][C] into workspace
+    for (int64_t b = tid; b < B; b += 1024) {
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += dlogp[b * C + c];
+        for (int c = 0; c < C; ++c)
+            dlogit_ws[b * C + c] = dlogp[b * C + c] - expf(logp[b * C + c]) * sum;
+    }
+    __syncthreads();
+    // 2. dz3[b][j]
+    for (int64_t i = tid; i < B * kFc; i += 1024) {
+        const int64_t b = i / kFc;
+        const int j = (int)(i - b * kFc);
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(dlogit_ws[b * C + c], w2[c * kFc + j], s);
+        dz3[i] = s * (float)keep[i];
+    }
+    __syncthreads();
+    // 3. dW2[c][j], db2[c], dbf1[j]: one output per thread, batch summed in order
+    for (int o = tid; o < C * kFc + C + kFc; o += 1024) {
+        float s = 0.f;
+        if (o < C * kFc) {
+            const int c = o / kFc, j = o - c * kFc;
+            for (int64_t b = 0; b < B; ++b) s = fmaf(dlogit_ws[b * C + c], h3[b * kFc + j], s);
+            dw2[o] = s;
+        } else if (o < C * kFc + C) {
+            const int c = o - C * kFc;
+            for (int64_t b = 0; b < B; ++b) s += dlogit_ws[b * C + c];
+            db2[c] = s;
+        } else {
+            const int j = o - C * kFc - C;
+            for (int64_t b = 0; b < B; ++b) s += dz3[b * kFc + j];
+            dbf1[j] = s;
+        }
+    }
+}
+
+// conv6 backward w.r.t. its input: dh1[b][c][s] = sum_{o,d} dz2[b][o][s-d] W6[o][c][d]
+__global__ void __launch_bounds__(256)
+tail_c6_bwd_input(const float* __restrict__ dz2, int64_t B, int L1, const float* __restrict__ w6,
+                  float* __restrict__ dh1) {
+    extern __shared__ float sm[];
+    float* w6c = sm;                         // [(o*5+d)][c]
+    float* dzs = sm + kC6 * kK6 * kC5;       // [32][L2]
+    const int L2 = L1 - (kK6 - 1);
+    for (int idx = threadIdx.x; idx < kC6 * kC5 * kK6; idx += 256) {
+        int o = idx / (kC5 * kK6), r = idx - o * (kC5 * kK6);
+        int c = r / kK6, d = r - c * kK6;
+        w6c[(o * kK6 + d) * kC5 + c] = w6[idx];
+    }
+    const int c = threadIdx.x & 15, srow = threadIdx.x >> 4;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) dzs[idx] = dz2[b * kC6 * L2 + idx];
+        __syncthreads();
+        for (int s = srow; s < L1; s += 16) {
+            float acc = 0.f;
+            for (int o = 0; o < kC6; ++o)
+#pragma unroll
+                for (int d = 0; d < kK6; ++d) {
+                    const int t = s - d;
+                    if (t >= 0 && t < L2) acc = fmaf(dzs[o * L2 + t], w6c[(o * kK6 + d) * kC5 + c], acc);
+                }
+            dh1[(b * kC5 + c) * L1 + s] = acc;
+        }
+    }
+}
+
+// conv6 weight/bias gradient: persistent CTAs, thread-owned outputs, per-CTA partial vector
+// [2560 + 32] written to `partials[blockIdx.x]`
+__global__ void __launch_bounds__(256)
+tail_c6_bwd_weight(const float* __restrict__ dz2, const float* __restrict__ h1, int64_t B, int L1,
+                   float* __restrict__ partials) {
+    extern __shared__ float sm[];
+    const int L2 = L1 - (kK6 - 1);
+    float* dzs = sm;                 // [32][L2]
+    float* h1s = sm + kC6 * L2;      // [16][L1]
+    constexpr int NW = kC6 * kC5 * kK6;   // 2560
+    float acc[NW / 256];
+#pragma unroll
+    for (int m = 0; m < NW / 256; ++m) acc[m] = 0.f;
+    float accb = 0.f;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) dzs[idx] = dz2[b * kC6 * L2 + idx];
+        for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) h1s[idx] = h1[b * kC5 * L1 + idx];
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < NW / 256; ++m) {
+            const int o = threadIdx.x + 256 * m;
+            const int oc = o / (kC5 * kK6), r = o - oc * (kC5 * kK6);
+            const int c = r / kK6, d = r - c * kK6;
+            const float* dr = dzs + oc * L2;
+            const float* hr = h1s + c * L1 + d;
+            float a = acc[m];
+            for (int t = 0; t < L2; ++t) a = fmaf(dr[t], hr[t], a);
+            acc[m] = a;
+        }
+        if (threadIdx.x < kC6) {
+            const float* dr = dzs + threadIdx.x * L2;
+            for (int t = 0; t < L2; ++t) accb += dr[t];
+        }
+    }
+    float* out = partials + (int64_t)blockIdx.x * (NW + kC6);
+#pragma unroll
+    for (int m = 0; m < NW / 256; ++m) out[threadIdx.x + 256 * m] = acc[m];
+    if (threadIdx.x < kC6) out[NW + threadIdx.x] = accb;
+}
+
+// conv5 / pool / ReLU backward w.r.t. pooled: one warp per row pair
+__global__ void __launch_bounds__(256)
+tail_c5_bwd_input(const float* __restrict__ dh1, const uint8_t* __restrict__ arg, int64_t B, int k, int L1,
+                  const float* __restrict__ w5, float* __restrict__ dpooled) {
+    __shared__ float w5s[kC5 * kKW];
+    __shared__ float zv[8][kC5];
+    __shared__ int za[8][kC5];
+    for (int idx = threadIdx.x; idx < kC5 * kKW; idx += 256) w5s[idx] = w5[idx];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t pairs = B * L1;
+    for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += (int64_t)gridDim.x * 8) {
+        const int64_t b = pr / L1;
+        const int j = (int)(pr - b * L1);
+        if (lane < kC5) {
+            const int64_t o = (b * kC5 + lane) * L1 + j;
+            zv[warp][lane] = dh1[o];
+            za[warp][lane] = arg[o];
+        }
+        __syncwarp();
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < kC5; ++c) {
+            const int r = za[warp][c];
+            if (r > 1) continue;                       // ReLU dead
+            const float v = zv[warp][c];
+            const float* wr = w5s + c * kKW;
+            if (r == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { int i = lane + 32 * q; if (i < kKW) a0[q] = fmaf(v, wr[i], a0[q]); }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { int i = lane + 32 * q; if (i < kKW) a1[q] = fmaf(v, wr[i], a1[q]); }
+            }
+        }
+        float* dst = dpooled + (b * k + 2 * j) * kKW;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int i = lane + 32 * q;
+            if (i < kKW) { dst[i] = a0[q]; dst[kKW + i] = a1[q]; }
+        }
+        __syncwarp();
+    }
+    // an odd k leaves the last row outside every pooling window: zero gradient
+    if ((k & 1) && blockIdx.x == 0)
+        for (int64_t idx = threadIdx.x; idx < B * kKW; idx += 256) {
+            const int64_t b = idx / kKW;
+            dpooled[(b * k + (k - 1)) * kKW + (idx - b * kKW)] = 0.f;
+        }
+}
+
+// conv5 weight/bias gradient: persistent CTAs, thread-owned outputs (16*97 + 16), 8 pairs
+// staged per iteration; per-CTA partials
+__global__ void __launch_bounds__(256)
+tail_c5_bwd_weight(const float* __restrict__ dh1, const uint8_t* __restrict__ arg,
+                   const float* __restrict__ pooled, int64_t B, int k, int L1,
+                   float* __restrict__ partials) {
+    constexpr int PB = 8;                                   // pairs per stage
+    __shared__ float sx[PB][2 * kKW + 2];
+    __shared__ float zv[PB][kC5];
+    __shared__ int za[PB][kC5];
+    constexpr int NW = kC5 * kKW;                           // 1552
+    constexpr int PER = (NW + 255) / 256;                   // 7
+    float acc[PER];
+#pragma unroll
+    for (int m = 0; m < PER; ++m) acc[m] = 0.f;
+    float accb = 0.f;
+    const int64_t pairs = B * L1;
+    const int64_t stages = (pairs + PB - 1) / PB;
+    for (int64_t st = blockIdx.x; st < stages; st += gridDim.x) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < PB * 2 * kKW; idx += 256) {
+            const int pp = idx / (2 * kKW), i = idx - pp * (2 * kKW);
+            const int64_t pr = st * PB + pp;
+            float v = 0.f;
+            if (pr < pairs) {
+                const int64_t b = pr / L1;
+                const int j = (int)(pr - b * L1);
+                v = pooled[(b * k + 2 * j) * kKW + i];
+            }
+            sx[pp][i] = v;
+        }
+        if (threadIdx.x < PB * kC5) {
+            const int pp = threadIdx.x / kC5, c = threadIdx.x - pp * kC5;
+            const int64_t pr = st * PB + pp;
+            float v = 0.f;
+            int a = 2;
+            if (pr < pairs) {
+                const int64_t b = pr / L1;
+                const int j = (int)(pr - b * L1);
+                const int64_t o = (b * kC5 + c) * L1 + j;
+                v = dh1[o];
+                a = arg[o];
+            }
+            zv[pp][c] = v;
+            za[pp][c] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < PER; ++m) {
+            const int o = threadIdx.x + 256 * m;
+            if (o >= NW) break;
+            const int c = o / kKW, i = o - c * kKW;
+            float a = acc[m];
+#pragma unroll
+            for (int pp = 0; pp < PB; ++pp) {
+                const int r = za[pp][c];
+                if (r < 2) a = fmaf(zv[pp][c], sx[pp][r * kKW + i], a);
+            }
+            acc[m] = a;
+        }
+        if (threadIdx.x < kC5) {
+#pragma unroll
+            for (int pp = 0; pp < PB; ++pp)
+                if (za[pp][threadIdx.x] < 2) accb += zv[pp][threadIdx.x];
+        }
+    }
+    float* out = partials + (int64_t)blockIdx.x * (NW + kC5);
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+        const int o = threadIdx.x + 256 * m;
+        if (o < NW) out[o] = acc[m];
+    }
+    if (threadIdx.x < kC5) out[NW + threadIdx.x] = accb;
+}
+
+// out[o] = sum_p partials[p][o] in order; optionally split over two destinations
+__global__ void __launch_bounds__(256)
+tail_reduce_partials(const float* __restrict__ partials, int parts, int total, int split_at,
+                     float* __restrict__ out_a, float* __restrict__ out_b) {
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= total) return;
+    float s = 0.f;
+    for (int p = 0; p < parts; ++p) s += partials[(int64_t)p * total + o];
+    if (o < split_at) out_a[o] = s; else out_b[o - split_at] = s;
+}
+
+// Adam on flat buffers (torch.optim.Adam defaults semantics, train.py:99): the step counter
+// lives on the device so that the whole step can be replayed from a CUDA graph.
+__global__ void __launch_bounds__(256)
+adam_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+          int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps) {
+    const int64_t t = *step + 1;
+    const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const float gi = g[i];
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    }
+}
+__global__ void adam_bump(int64_t* step) { *step += 1; }
+
+struct TailDims { int L1, L2, D1; };
+__host__ inline TailDims tail_dims(int k) {
+    TailDims d;
+    d.L1 = k / 2;
+    d.L2 = d.L1 - (kK6 - 1);
+    d.D1 = kC6 * d.L2;
+    return d;
+}
+constexpr int kFc1Splits = 8;
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+extern "C" size_t dgcnn_tail_workspace_bytes(int64_t num_graphs, int32_t k, int32_t num_classes) {
+    if (num_graphs < 0 || k < 10 || num_classes < 1) return 0;
+    const TailDims d = tail_dims(k);
+    size_t fwd = sizeof(float) * (size_t)kFc1Splits * num_graphs * kFc;
+    size_t bwd = sizeof(float) * ((size_t)num_graphs * num_classes            // dlogit
+                                  + (size_t)num_graphs * kFc                   // dz3
+                                  + (size_t)num_graphs * d.D1                  // dz2
+                                  + (size_t)num_graphs * kC5 * d.L1            // dh1
+                                  + (size_t)2 * DGCNN_NUM_SMS * (kC6 * kC5 * kK6 + kC6)
+                                  + (size_t)2 * DGCNN_NUM_SMS * (kC5 * kKW + kC5));
+    return (fwd > bwd ? fwd : bwd) + 1024;
+}
+
+extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k, const float* w5,
+                              const float* b5, const float* w6, const float* b6, const float* wf1,
+                              const float* bf1, const float* wf2, const float* bf2, int32_t num_classes,
+                              int32_t training, uint64_t seed, int64_t* rng_offset, float* h1,
+                              uint8_t* arg, float* h2, float* h3, uint8_t* keep, float* logp,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    const int64_t B = num_graphs;
+    if (B < 0 || k < 10 || num_classes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_classes > 32) return DGCNN_ERR_UNSUPPORTED;
+    if (B == 0) return DGCNN_OK;
+    if (!pooled || !w5 || !b5 || !w6 || !b6 || !wf1 || !bf1 || !wf2 || !bf2 || !h1 || !arg || !h2 ||
+        !h3 || !keep || !logp)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < dgcnn_tail_workspace_bytes(B, k, num_classes))
+        return DGCNN_ERR_WORKSPACE;
+    const TailDims d = tail_dims(k);
+    if (B * (int64_t)d.D1 >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* slabs = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+
+    tail_c5_fwd<<<grid_for(B * d.L1, 8, 8), 256, 0, st>>>(pooled, B, k, d.L1, w5, b5, h1, arg);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const size_t smem6 = sizeof(float) * (kC5 * kK6 * kC6 + kC6 + kC5 * d.L1);
+    if (smem6 > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    tail_c6_fwd<<<grid_for(B, 1, 4), 256, smem6, st>>>(h1, B, d.L1, w6, b6, h2);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    // fc1: [B, D1] x Wf1^T [D1, 128], split-K slabs
+    const int kchunk = (int)ceil_div(ceil_div(d.D1, kFc1Splits), 32) * 32;
+    const int splits = (int)ceil_div(d.D1, kchunk);
+    dim3 g1(1, (unsigned)ceil_div(B, 32), (unsigned)splits);
+    gemm_f32<false, false, false><<<g1, 256, 0, st>>>(h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
+                                                      nullptr);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    tail_fc1_epilogue<<<grid_for(B * kFc, 256, 4), 256, 0, st>>>(slabs, splits, B * kFc, bf1, training, seed,
+                                                                 rng_offset, h3, keep);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    tail_fc2_lsm_fwd<<<grid_for(B, 8, 2), 256, 0, st>>>(h3, B, num_classes, wf2, bf2, logp,
+                                                        training ? rng_offset : nullptr);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
+extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, int32_t k,
+                              const float* w5, const float* w6, const float* wf1, const float* wf2,
+                              int32_t num_classes, const float* h1, const uint8_t* arg, const float* h2,
+                              const float* h3, const uint8_t* keep, const float* logp, float* dpooled,
+                              float* dw5, float* db5, float* dw6, float* db6, float* dwf1, float* dbf1,
+                              float* dwf2, float* dbf2, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    const int64_t B = num_graphs;
+    if (B < 0 || k < 10 || num_classes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_classes > 32) return DGCNN_ERR_UNSUPPORTED;
+    if (!dw5 || !db5 || !dw6 || !db6 || !dwf1 || !dbf1 || !dwf2 || !dbf2) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < dgcnn_tail_workspace_bytes(B, k, num_classes))
+        return DGCNN_ERR_WORKSPACE;
+    const TailDims d = tail_dims(k);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B == 0) {
+        cudaMemsetAsync(dw5, 0, sizeof(float) * kC5 * kKW, st);  cudaMemsetAsync(db5, 0, sizeof(float) * kC5, st);
+        cudaMemsetAsync(dw6, 0, sizeof(float) * kC6 * kC5 * kK6, st);  cudaMemsetAsync(db6, 0, sizeof(float) * kC6, st);
+        cudaMemsetAsync(dwf1, 0, sizeof(float) * kFc * d.D1, st);  cudaMemsetAsync(dbf1, 0, sizeof(float) * kFc, st);
+        cudaMemsetAsync(dwf2, 0, sizeof(float) * num_classes * kFc, st);
+        cudaMemsetAsync(dbf2, 0, sizeof(float) * num_classes, st);
+        return DGCNN_OK;
+    }
+    if (!dlogp || !pooled || !w5 || !w6 || !wf1 || !wf2 || !h1 || !arg || !h2 || !h3 || !keep || !logp ||
+        !dpooled)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    float* ws = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* dlogit = ws;                         ws += B * num_classes;
+    float* dz3 = ws;                            ws += B * kFc;
+    float* dz2 = ws;                            ws += B * (int64_t)d.D1;
+    float* dh1 = ws;                            ws += B * (int64_t)kC5 * d.L1;
+    float* part6 = ws;                          ws += 2 * DGCNN_NUM_SMS * (kC6 * kC5 * kK6 + kC6);
+    float* part5 = ws;
+
+    tail_fc2_bwd<<<1, 1024, 0, st>>>(dlogp, logp, h3, keep, B, num_classes, wf2, dlogit, dz3, dwf2, dbf2, dbf1);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    // dz2 = (dz3 Wf1) * (h2 > 0):  [B,128] x [128,D1]
+    dim3 ga((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(B, 32), 1);
+    gemm_f32<false, true, true><<<ga, 256, 0, st>>>(dz3, kFc, wf1, d.D1, dz2, (int)B, d.D1, kFc, kFc, h2);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    // dWf1 = dz3^T h2:  [128,B] x [B,D1]
+    dim3 gb((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(kFc, 32), 1);
+    gemm_f32<true, true, false><<<gb, 256, 0, st>>>(dz3, kFc, h2, d.D1, dwf1, kFc, d.D1, (int)B, (int)B, nullptr);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * d.L2);
+    const size_t smem_w = sizeof(float) * (kC6 * d.L2 + kC5 * d.L1);
+    if (smem_in > 48 * 1024 || smem_w > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    tail_c6_bwd_input<<<grid_for(B, 1, 4), 256, smem_in, st>>>(dz2, B, d.L1, w6, dh1);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const int parts6 = grid_for(B, 1, 2);
+    tail_c6_bwd_weight<<<parts6, 256, smem_w, st>>>(dz2, h1, B, d.L1, part6);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const int n6 = kC6 * kC5 * kK6;
+    tail_reduce_partials<<<(n6 + kC6 + 255) / 256, 256, 0, st>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    tail_c5_bwd_input<<<grid_for(B * d.L1, 8, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const int parts5 = grid_for(ceil_div(B * d.L1, 8), 1, 2);
+    tail_c5_bwd_weight<<<parts5, 256, 0, st>>>(dh1, arg, pooled, B, k, d.L1, part5);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const int n5 = kC5 * kKW;
+    tail_reduce_partials<<<(n5 + kC5 + 255) / 256, 256, 0, st>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
+extern "C" int dgcnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                               int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps,
+                               void* stream) {
+    if (n < 0 || !step) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DGCNN_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq) return DGCNN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    adam_flat<<<grid_for(n, 256, 4), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1,
+                                                   beta2, eps);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    adam_bump<<<1, 1, 0, st>>>(step);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}

@@ -23,7 +23,7 @@ from torch import Tensor, nn
 from . import ops
 from .ops import ACT_NONE, ACT_TANH, NORM_RW, NORM_SYM, Graph
 
-__all__ = ["set_fused", "fused_enabled", "GCNConv", "GraphConvolution", "SortAggregation", "SortPool", "Model",
+__all__ = ["set_fused", "fused_enabled", "set_custom_tail", "custom_tail_enabled", "GCNConv", "GraphConvolution", "SortAggregation", "SortPool", "Model",
            "remove_self_loops", "graph_conv_stack", "classifier_in_features"]
 
 
@@ -35,6 +35,18 @@ def remove_self_loops(edge_index: Tensor, edge_attr: Optional[Tensor] = None):
 
 
 _FUSED = True
+_CUSTOM_TAIL = True
+
+
+def set_custom_tail(enabled: bool) -> None:
+    """Use the hand-written dense-tail kernels (KT) instead of stock torch for model.py:36-43."""
+    global _CUSTOM_TAIL
+    _CUSTOM_TAIL = bool(enabled)
+
+
+def custom_tail_enabled() -> bool:
+    return _CUSTOM_TAIL
+
 
 
 def set_fused(enabled: bool) -> None:
@@ -98,6 +110,23 @@ class _SortPoolFn(torch.autograd.Function):
     def backward(ctx, dout, _dperm):
         (perm,) = ctx.saved_tensors
         return ops.sort_pool_bwd(dout.contiguous().view(perm.size(0), -1), perm, ctx.n), None, None, None
+
+
+class _TailFn(torch.autograd.Function):
+    """model.py:36-43 as one autograd node backed by the KT kernels."""
+
+    @staticmethod
+    def forward(ctx, pooled, k, training, seed, rng_offset, *params):
+        logp, saved = ops.tail_fwd(pooled, k, params, training, seed, rng_offset)
+        ctx.k = k
+        ctx.save_for_backward(logp, *saved, *params)
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        logp, pooled, h1, arg, h2, h3, keep, *params = ctx.saved_tensors
+        dpooled, grads = ops.tail_bwd(dlogp, logp, (pooled, h1, arg, h2, h3, keep), ctx.k, params)
+        return (dpooled if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
 
 
 class _StackFn(torch.autograd.Function):
@@ -297,6 +326,9 @@ class Model(nn.Module):
         self.drop_out = nn.Dropout(0.5)
         self.classifier_2 = nn.Linear(128, num_classes)
         self.relu = nn.ReLU(inplace=True)
+        # dropout stream of the hand-written tail: counter hash of (seed, offset, element)
+        self._tail_seed = int(torch.initial_seed())
+        self.register_buffer("_tail_rng_offset", torch.zeros(1, dtype=torch.int64), persistent=False)
 
     # -- hot path: model.py:27-35 -----------------------------------------------------
     def build_graph(self, data) -> Graph:
@@ -317,6 +349,12 @@ class Model(nn.Module):
 
     # -- dense tail: model.py:36-43 (stock torch) -------------------------------------
     def tail(self, pooled: Tensor) -> Tensor:
+        if custom_tail_enabled() and pooled.is_cuda and self.classifier_2.out_features <= 32:
+            params = (self.conv5.weight, self.conv5.bias, self.conv6.weight, self.conv6.bias,
+                      self.classifier_1.weight, self.classifier_1.bias,
+                      self.classifier_2.weight, self.classifier_2.bias)
+            return _TailFn.apply(pooled, self.sort_pool.k, self.training, self._tail_seed,
+                                 self._tail_rng_offset, *params)
         h = pooled.view(pooled.size(0), 1, pooled.size(-1))
         h = self.pool(self.relu(self.conv5(h)))
         h = self.relu(self.conv6(h))

@@ -29,7 +29,7 @@ STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower(
 # reads it to report `gpu_launches`.  Keyed by entry point.
 LAUNCHES = {"build_graph": 0, "graph_ptr": 0, "graph_conv_fwd": 0, "graph_conv_bwd": 0,
             "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0, "stack_bwd": 0,
-            "build_bitmaps": 0}
+            "build_bitmaps": 0, "tail_fwd": 0, "tail_bwd": 0, "adam_step": 0}
 
 
 def launches_total() -> int:
@@ -362,6 +362,85 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
         o += cout
         out.append((dw, db))
     return out
+
+
+def tail_fwd(pooled: Tensor, k: int, params, training: bool, seed: int, rng_offset: Optional[Tensor]):
+    """KT forward (model.py:36-43) -> (logp [B,C], saved tensors for tail_bwd)."""
+    lib = _lib.load_library()
+    _require_cuda(pooled, "pooled", torch.float32)
+    w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
+    for t in (w5, b5, w6, b6, wf1, bf1, wf2, bf2):
+        _require_cuda(t, "parameter", torch.float32)
+    pooled = pooled.contiguous()
+    b = pooled.size(0)
+    k = int(k)
+    l1 = k // 2
+    d1 = 32 * (l1 - 4)
+    c = wf2.size(0)
+    if pooled.numel() != b * k * 97 or tuple(wf1.shape) != (128, d1) or w5.numel() != 16 * 97 \
+            or w6.numel() != 32 * 16 * 5 or wf2.size(1) != 128:
+        raise ValueError("dgcnn_b200: tail_fwd shape mismatch")
+    dev = pooled.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    u8 = dict(dtype=torch.uint8, device=dev)
+    h1 = torch.empty(b, 16, l1, **f32)
+    arg = torch.empty(b, 16, l1, **u8)
+    h2 = torch.empty(b, d1, **f32)
+    h3 = torch.empty(b, 128, **f32)
+    keep = torch.empty(b, 128, **u8)
+    logp = torch.empty(b, c, **f32)
+    ws = _workspace(lib.dgcnn_tail_workspace_bytes(b, k, c), dev)
+    if training and rng_offset is None:
+        raise ValueError("dgcnn_b200: training-mode tail needs the device rng_offset counter")
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_tail_fwd(_ptr(pooled), b, k, _ptr(w5), _ptr(b5), _ptr(w6), _ptr(b6), _ptr(wf1),
+                                _ptr(bf1), _ptr(wf2), _ptr(bf2), c, int(bool(training)),
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(rng_offset), _ptr(h1), _ptr(arg),
+                                _ptr(h2), _ptr(h3), _ptr(keep), _ptr(logp), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "tail_fwd")
+    LAUNCHES["tail_fwd"] += 5 if b > 0 else 0
+    return logp, (pooled, h1, arg, h2, h3, keep)
+
+
+def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params):
+    """KT backward -> (dpooled, [dw5, db5, dw6, db6, dwf1, dbf1, dwf2, dbf2])."""
+    lib = _lib.load_library()
+    pooled, h1, arg, h2, h3, keep = saved
+    w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
+    _require_cuda(dlogp, "dlogp", torch.float32)
+    dlogp = dlogp.contiguous()
+    b, c = logp.shape
+    dev = pooled.device
+    dpooled = torch.empty_like(pooled)
+    grads = [torch.empty_like(p) for p in (w5, b5, w6, b6, wf1, bf1, wf2, bf2)]
+    ws = _workspace(lib.dgcnn_tail_workspace_bytes(b, int(k), c), dev)
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_tail_bwd(_ptr(dlogp), _ptr(pooled), b, int(k), _ptr(w5), _ptr(w6), _ptr(wf1),
+                                _ptr(wf2), c, _ptr(h1), _ptr(arg), _ptr(h2), _ptr(h3), _ptr(keep),
+                                _ptr(logp), _ptr(dpooled), *[_ptr(g) for g in grads], _ptr(ws), ws.numel(),
+                                _stream())
+    _lib.check(rc, "tail_bwd")
+    LAUNCHES["tail_bwd"] += 9 if b > 0 else 0
+    return dpooled, grads
+
+
+def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: Tensor,
+              lr: float, beta1: float, beta2: float, eps: float) -> None:
+    """Flat Adam update (train.py:41); `step` is a device int64 counter bumped by the call."""
+    lib = _lib.load_library()
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _require_cuda(t, name, torch.float32)
+        if not t.is_contiguous():
+            raise ValueError(f"dgcnn_b200: {name} must be contiguous")
+    _require_cuda(step, "step", torch.int64)
+    n = params.numel()
+    if not (grads.numel() >= n and exp_avg.numel() == n and exp_avg_sq.numel() == n):
+        raise ValueError("dgcnn_b200: adam_step size mismatch")
+    with torch.cuda.device(params.device):
+        rc = lib.dgcnn_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), n,
+                                 _ptr(step), float(lr), float(beta1), float(beta2), float(eps), _stream())
+    _lib.check(rc, "adam_step")
+    LAUNCHES["adam_step"] += 2 if n > 0 else 0
 
 
 # ---------------------------------------------------------------------------------

@@ -230,6 +230,41 @@ int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                     int32_t norm, int32_t variant, float* grads, int32_t* status,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * KT  dense tail, model.py:36-43: view -> conv5 Conv1d(1,16,97,97) +
+ * ReLU -> MaxPool1d(2,2) -> conv6 Conv1d(16,32,5,1) + ReLU -> flatten -> fc1 Linear(.,128) +
+ * ReLU -> Dropout(0.5) -> fc2 Linear(128,C) -> log_softmax.  Parameter layouts are torch's
+ * (conv5.weight [16,1,97], conv6.weight [32,16,5], Linear.weight [out,in]).
+ * Saved for backward (caller-owned): h1 [B,16,k/2], arg uint8 [B,16,k/2], h2 [B,32*(k/2-4)],
+ * h3 [B,128], keep uint8 [B,128].  Dropout decisions come from a counter hash of
+ * (seed, *rng_offset, element); the forward increments *rng_offset (device int64) so that a
+ * CUDA-graph replay draws a fresh mask.  training == 0: no dropout, rng_offset unused.
+ * Limits: num_classes <= 32, k <= ~700 (shared-memory tiles).
+ * ------------------------------------------------------------------------ */
+size_t dgcnn_tail_workspace_bytes(int64_t num_graphs, int32_t k, int32_t num_classes);
+int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k,
+                   const float* w5, const float* b5, const float* w6, const float* b6,
+                   const float* wf1, const float* bf1, const float* wf2, const float* bf2,
+                   int32_t num_classes, int32_t training, uint64_t seed, int64_t* rng_offset,
+                   float* h1, uint8_t* arg, float* h2, float* h3, uint8_t* keep, float* logp,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* autograd of the above (train.py:40): dlogp [B,C] -> dpooled [B,k*97] and the eight
+ * parameter gradients (overwritten).  Deterministic: every reduction runs in a fixed order. */
+int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, int32_t k,
+                   const float* w5, const float* w6, const float* wf1, const float* wf2,
+                   int32_t num_classes,
+                   const float* h1, const uint8_t* arg, const float* h2, const float* h3,
+                   const uint8_t* keep, const float* logp,
+                   float* dpooled, float* dw5, float* db5, float* dw6, float* db6,
+                   float* dwf1, float* dbf1, float* dwf2, float* dbf2,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adam (train.py:41,99: torch.optim.Adam defaults) on flat fp32 buffers;
+ * `step` is a device int64 counter, incremented by the call. */
+int dgcnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

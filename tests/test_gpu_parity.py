@@ -716,6 +716,101 @@ def test_permutation_equivariance():
     assert (pa - pb).abs().max().item() <= 1e-5
 
 
+# ------------------------------------------------------------------ dense tail + Adam (8f N2/N3)
+@pytest.mark.parametrize("b,k,c", [(37, 30, 2), (64, 130, 3), (5, 61, 2), (3, 291, 2)])
+def test_dense_tail_matches_torch(b, k, c):
+    """KT (model.py:36-43) forward and backward against the stock-torch tail in float64 on
+    the CPU (the reference's own op sequence), eval mode so that dropout is the identity."""
+    torch.manual_seed(b * 1000 + k)
+    ref = orc.OracleModel(7, c, k).double().eval()
+    model = dg.Model(7, c, k)
+    model.load_state_dict({n_: v.float() for n_, v in ref.state_dict().items()})
+    model = model.to(DEV).eval()
+    pooled = torch.randn(b, k * 97)
+    pooled[:, ::5] = 0.0                                     # zeros like real zero padding
+    cot = torch.randn(b, c)
+    pd = pooled.to(DEV).requires_grad_(True)
+    dg.set_custom_tail(True)
+    before = ops.LAUNCHES["tail_fwd"]
+    out = model.tail(pd)
+    assert ops.LAUNCHES["tail_fwd"] - before == 5
+    (out * cot.to(DEV)).sum().backward()
+    pr = pooled.double().requires_grad_(True)
+    rout = ref.tail(pr)
+    (rout * cot.double()).sum().backward()
+    assert (out.detach().cpu().double() - rout.detach()).abs().max().item() <= 2e-5
+    scale = max(1.0, float(pr.grad.abs().max()))
+    assert (pd.grad.cpu().double() - pr.grad).abs().max().item() <= 2e-5 * scale
+    rp = dict(ref.named_parameters())
+    for name, p_ in model.named_parameters():
+        if name.startswith(("conv5", "conv6", "classifier")):
+            want = rp[name].grad
+            scale = max(1.0, float(want.abs().max()))
+            err = (p_.grad.cpu().double() - want).abs().max().item()
+            assert err <= 5e-5 * scale, f"{name}: {err:.3e} (scale {scale:.2e})"
+    # and against the stock torch tail on the GPU
+    dg.set_custom_tail(False)
+    try:
+        with torch.no_grad():
+            tout = model.tail(pd.detach())
+    finally:
+        dg.set_custom_tail(True)
+    assert (out.detach() - tout).abs().max().item() <= 1e-4
+
+
+def test_dense_tail_dropout_and_graph_replay():
+    torch.manual_seed(0)
+    model = dg.Model(5, 2, 60).to(DEV).train()
+    pooled = torch.randn(256, 60 * 97, device=DEV)
+    _, saved = ops.tail_fwd(pooled, 60, (model.conv5.weight, model.conv5.bias, model.conv6.weight,
+                                        model.conv6.bias, model.classifier_1.weight, model.classifier_1.bias,
+                                        model.classifier_2.weight, model.classifier_2.bias), True, 123,
+                            model._tail_rng_offset)
+    h3, keep = saved[4], saved[5]
+    alive = (keep > 0).float().mean().item()
+    assert int(keep.max()) == 2 and set(keep.unique().tolist()) <= {0, 2}
+    assert 0.15 < alive < 0.5                      # P(kept) = 0.5 times P(ReLU alive)
+    assert torch.equal(h3 > 0, keep > 0)
+    a = model.tail(pooled)
+    b_ = model.tail(pooled)
+    assert not torch.equal(a, b_)                  # the offset advanced: a fresh mask
+    assert int(model._tail_rng_offset.item()) == 3
+    model.eval()
+    assert torch.equal(model.tail(pooled), model.tail(pooled))
+    model.train()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        model.tail(pooled)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = model.tail(pooled)
+    g.replay()
+    first = out.clone()
+    g.replay()
+    assert not torch.equal(first, out)             # replays draw new masks too
+
+
+def test_flat_adam_matches_torch_adam():
+    torch.manual_seed(1)
+    m1 = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 3)).to(DEV)
+    m2 = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 3)).to(DEV)
+    m2.load_state_dict(m1.state_dict())
+    ref = torch.optim.Adam(m1.parameters(), lr=1e-3)
+    bucket = dg.GradBucket(m2.parameters(), extra=2)
+    opt = dg.FlatAdam(m2, bucket, lr=1e-3)
+    x = torch.randn(32, 13, device=DEV)
+    for it in range(6):
+        for m, o in ((m1, ref), (m2, opt)):
+            o.zero_grad()
+            (m(x) ** 2).sum().backward()
+            o.step()
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert (p1 - p2).abs().max().item() <= 2e-6
+    assert int(opt.step_count.item()) == 6
+
+
 def test_cuda_graph_capture_replays_bit_identically():
     cfg = CONFIGS["mutag"]
     batch = make_batch("mutag").to(DEV)

@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--autograd", action="store_true",
+                    help="step through torch autograd (Model + GradBucket + FlatAdam) instead of FusedTrainer")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -245,19 +247,30 @@ def main():
 
     torch.manual_seed(324)
     model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(dev).train()
-    bucket = dg.GradBucket(model.parameters(), extra=2)
-    opt = dg.FlatAdam(model, bucket, lr=1e-3)        # train.py:99 Adam defaults, one flat kernel
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    fused_step = not args.autograd
+    if fused_step:
+        # train.py:35-45 as a straight launch sequence (dgcnn_b200/trainer.py): no autograd,
+        # gradients written in place into one flat buffer, one all-reduce, flat Adam
+        trainer = dg.FusedTrainer(model, lr=1e-3)
+        if not trainer.supported(dev_batches[0]):
+            fused_step = False
+    if fused_step:
+        def train_step(data):
+            return trainer.step(data, global_batch)[0]
+    else:
+        bucket = dg.GradBucket(model.parameters(), extra=2)
+        opt = dg.FlatAdam(model, bucket, lr=1e-3)    # train.py:99 Adam defaults, one flat kernel
 
-    def train_step(data):
-        bucket.zero_()
-        logp = model(data)
-        loss = F.nll_loss(logp, data.y, reduction="sum")
-        loss.backward()
-        bucket.extra[0].copy_(loss.detach())
-        bucket.all_reduce(global_batch)
-        opt.step()
-        return loss
+        def train_step(data):
+            bucket.zero_()
+            logp = model(data)
+            loss = F.nll_loss(logp, data.y, reduction="sum")
+            loss.backward()
+            bucket.extra[0].copy_(loss.detach())
+            bucket.all_reduce(global_batch)
+            opt.step()
+            return loss
 
     # ---- launch census on one eager step ------------------------------------------
     before = ops.launches_total()
@@ -460,7 +473,7 @@ def main():
                            "+ grad all-reduce (N>1) + Adam (all hand-written kernels except NLL)",
                    "l2": f"flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every timed step; "
                          f"ring of {RING} distinct batches",
-                   "cuda_graph": use_graph, "parallelism": f"dp{world} (graph-sharded)",
+                   "cuda_graph": use_graph, "fused_trainer": fused_step, "parallelism": f"dp{world} (graph-sharded)",
                    "wall_s_incl_flush": wall},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,

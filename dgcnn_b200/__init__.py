@@ -9,5 +9,6 @@ from .nn import (GCNConv, GraphConvolution, Model, SortAggregation, SortPool,
 from .synth import CONFIGS, GraphBatch, collate, make_batch, make_graphs
 from .dp import GradBucket, shard_bounds
 from .optim import FlatAdam
+from .trainer import FusedTrainer
 
 __version__ = "0.1.0"

@@ -224,47 +224,64 @@ tail_fc2_lsm_fwd(const float* __restrict__ h3, int64_t B, int C, const float* __
 }
 
 // ---- backward -----------------------------------------------------------------------------
-// fc2 / log_softmax backward, single CTA: dlogit = dlogp - softmax * sum(dlogp);
-// dz3 = (dlogit W2) * keep;  dW2 = dlogit^T h3;  db2;  db_fc1 = column sums of dz3.
-__global__ void __launch_bounds__(1024)
-tail_fc2_bwd(const float* __restrict__ dlogp, const float* __restrict__ logp, const float* __restrict__ h3,
-             const uint8_t* __restrict__ keep, int64_t B, int C, const float* __restrict__ w2,
-             float* __restrict__ dlogit_ws, float* __restrict__ dz3, float* __restrict__ dw2,
-             float* __restrict__ db2, float* __restrict__ dbf1) {
-    const int tid = threadIdx.x;
-    // 1. dlogit [B][C] into workspace
-    for (int64_t b = tid; b < B; b += 1024) {
-        float sum = 0.f;
-        for (int c = 0; c < C; ++c) sum += dlogp[b * C + c];
-        for (int c = 0; c < C; ++c)
-            dlogit_ws[b * C + c] = dlogp[b * C + c] - expf(logp[b * C + c]) * sum;
-    }
-    __syncthreads();
-    // 2. dz3[b][j]
-    for (int64_t i = tid; i < B * kFc; i += 1024) {
-        const int64_t b = i / kFc;
-        const int j = (int)(i - b * kFc);
-        float s = 0.f;
-        for (int c = 0; c < C; ++c) s = fmaf(dlogit_ws[b * C + c], w2[c * kFc + j], s);
-        dz3[i] = s * (float)keep[i];
-    }
-    __syncthreads();
-    // 3. dW2[c][j], db2[c], dbf1[j]: one output per thread, batch summed in order
-    for (int o = tid; o < C * kFc + C + kFc; o += 1024) {
-        float s = 0.f;
-        if (o < C * kFc) {
-            const int c = o / kFc, j = o - c * kFc;
-            for (int64_t b = 0; b < B; ++b) s = fmaf(dlogit_ws[b * C + c], h3[b * kFc + j], s);
-            dw2[o] = s;
-        } else if (o < C * kFc + C) {
-            const int c = o - C * kFc;
-            for (int64_t b = 0; b < B; ++b) s += dlogit_ws[b * C + c];
-            db2[c] = s;
-        } else {
-            const int j = o - C * kFc - C;
-            for (int64_t b = 0; b < B; ++b) s += dz3[b * kFc + j];
-            dbf1[j] = s;
+// fc2 / log_softmax backward, part A (one warp per graph):
+//   dlogit = dlogp - softmax * sum(dlogp);   dz3 = (dlogit W2) * keep
+__global__ void __launch_bounds__(256)
+tail_fc2_bwd_rows(const float* __restrict__ dlogp, const float* __restrict__ logp,
+                  const uint8_t* __restrict__ keep, int64_t B, int C, const float* __restrict__ w2,
+                  float* __restrict__ dlogit, float* __restrict__ dz3) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+        const float g = lane < C ? dlogp[b * C + lane] : 0.f;
+        const float sum = warp_sum(g);
+        const float dl = lane < C ? g - expf(logp[b * C + lane]) * sum : 0.f;
+        if (lane < C) dlogit[b * C + lane] = dl;
+        float acc[kFc / 32];
+#pragma unroll
+        for (int q = 0; q < kFc / 32; ++q) acc[q] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float dc = __shfl_sync(DGCNN_FULL_MASK, dl, c);
+#pragma unroll
+            for (int q = 0; q < kFc / 32; ++q) acc[q] = fmaf(dc, w2[c * kFc + lane + 32 * q], acc[q]);
         }
+#pragma unroll
+        for (int q = 0; q < kFc / 32; ++q) {
+            const int64_t i = b * kFc + lane + 32 * q;
+            dz3[i] = acc[q] * (float)keep[i];
+        }
+    }
+}
+
+// part B: dW2[c][j] = sum_b dlogit[b][c] h3[b][j], db2[c] = sum_b dlogit, dbf1[j] = sum_b dz3.
+// Block = 32 outputs x 8 batch lanes, batch lanes combined in order (deterministic).
+__global__ void __launch_bounds__(256)
+tail_fc2_bwd_params(const float* __restrict__ dlogit, const float* __restrict__ h3,
+                    const float* __restrict__ dz3, int64_t B, int C, float* __restrict__ dw2,
+                    float* __restrict__ db2, float* __restrict__ dbf1) {
+    __shared__ float red[8][33];
+    const int ox = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + ox;
+    const int total = C * kFc + C + kFc;
+    float s = 0.f;
+    if (o < C * kFc) {
+        const int c = o / kFc, j = o - c * kFc;
+        for (int64_t b = gy; b < B; b += 8) s = fmaf(dlogit[b * C + c], h3[b * kFc + j], s);
+    } else if (o < C * kFc + C) {
+        const int c = o - C * kFc;
+        for (int64_t b = gy; b < B; b += 8) s += dlogit[b * C + c];
+    } else if (o < total) {
+        const int j = o - C * kFc - C;
+        for (int64_t b = gy; b < B; b += 8) s += dz3[b * kFc + j];
+    }
+    red[gy][ox] = s;
+    __syncthreads();
+    if (gy == 0 && o < total) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t += red[y][ox];
+        if (o < C * kFc) dw2[o] = t;
+        else if (o < C * kFc + C) db2[o - C * kFc] = t;
+        else dbf1[o - C * kFc - C] = t;
     }
 }
 
@@ -299,8 +316,8 @@ tail_c6_bwd_input(const float* __restrict__ dz2, int64_t B, int L1, const float*
     }
 }
 
-// conv6 weight/bias gradient: persistent CTAs, thread-owned outputs, per-CTA partial vector
-// [2560 + 32] written to `partials[blockIdx.x]`
+// conv6 weight/bias gradient: one CTA per graph, thread-owned outputs, one partial vector
+// [2560 + 32] per graph (summed in graph order by tail_reduce_partials)
 __global__ void __launch_bounds__(256)
 tail_c6_bwd_weight(const float* __restrict__ dz2, const float* __restrict__ h1, int64_t B, int L1,
                    float* __restrict__ partials) {
@@ -309,35 +326,30 @@ tail_c6_bwd_weight(const float* __restrict__ dz2, const float* __restrict__ h1, 
     float* dzs = sm;                 // [32][L2]
     float* h1s = sm + kC6 * L2;      // [16][L1]
     constexpr int NW = kC6 * kC5 * kK6;   // 2560
-    float acc[NW / 256];
+    const int64_t b = blockIdx.x;
+    for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) dzs[idx] = dz2[b * kC6 * L2 + idx];
+    for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) h1s[idx] = h1[b * kC5 * L1 + idx];
+    __syncthreads();
+    float* out = partials + b * (NW + kC6);
 #pragma unroll
-    for (int m = 0; m < NW / 256; ++m) acc[m] = 0.f;
-    float accb = 0.f;
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) dzs[idx] = dz2[b * kC6 * L2 + idx];
-        for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) h1s[idx] = h1[b * kC5 * L1 + idx];
-        __syncthreads();
-#pragma unroll
-        for (int m = 0; m < NW / 256; ++m) {
-            const int o = threadIdx.x + 256 * m;
-            const int oc = o / (kC5 * kK6), r = o - oc * (kC5 * kK6);
-            const int c = r / kK6, d = r - c * kK6;
-            const float* dr = dzs + oc * L2;
-            const float* hr = h1s + c * L1 + d;
-            float a = acc[m];
-            for (int t = 0; t < L2; ++t) a = fmaf(dr[t], hr[t], a);
-            acc[m] = a;
-        }
-        if (threadIdx.x < kC6) {
-            const float* dr = dzs + threadIdx.x * L2;
-            for (int t = 0; t < L2; ++t) accb += dr[t];
-        }
+    for (int m = 0; m < NW / 256; ++m) {
+        const int o = threadIdx.x + 256 * m;
+        const int oc = o / (kC5 * kK6), r = o - oc * (kC5 * kK6);
+        const int c = r / kK6, d = r - c * kK6;
+        const float* dr = dzs + oc * L2;
+        const float* hr = h1s + c * L1 + d;
+        float a0 = 0.f, a1 = 0.f;
+        int t = 0;
+        for (; t + 1 < L2; t += 2) { a0 = fmaf(dr[t], hr[t], a0); a1 = fmaf(dr[t + 1], hr[t + 1], a1); }
+        if (t < L2) a0 = fmaf(dr[t], hr[t], a0);
+        out[o] = a0 + a1;
     }
-    float* out = partials + (int64_t)blockIdx.x * (NW + kC6);
-#pragma unroll
-    for (int m = 0; m < NW / 256; ++m) out[threadIdx.x + 256 * m] = acc[m];
-    if (threadIdx.x < kC6) out[NW + threadIdx.x] = accb;
+    if (threadIdx.x < kC6) {
+        const float* dr = dzs + threadIdx.x * L2;
+        float a = 0.f;
+        for (int t = 0; t < L2; ++t) a += dr[t];
+        out[NW + threadIdx.x] = a;
+    }
 }
 
 // conv5 / pool / ReLU backward w.r.t. pooled: one warp per row pair
@@ -390,102 +402,100 @@ tail_c5_bwd_input(const float* __restrict__ dh1, const uint8_t* __restrict__ arg
         }
 }
 
-// conv5 weight/bias gradient: persistent CTAs, thread-owned outputs (16*97 + 16), 8 pairs
-// staged per iteration; per-CTA partials
+// conv5 weight/bias gradient.  Every warp streams its own row pairs (warp-private staging, no
+// CTA barrier in the loop) and keeps ALL 16 x 97 outputs in registers (lane owns columns
+// lane, lane+32, lane+64, lane+96 of every channel); the 8 warps of a CTA are then added in
+// order and the CTA writes one partial vector [1552 + 16].
 __global__ void __launch_bounds__(256)
 tail_c5_bwd_weight(const float* __restrict__ dh1, const uint8_t* __restrict__ arg,
                    const float* __restrict__ pooled, int64_t B, int k, int L1,
                    float* __restrict__ partials) {
-    constexpr int PB = 8;                                   // pairs per stage
-    __shared__ float sx[PB][2 * kKW + 2];
-    __shared__ float zv[PB][kC5];
-    __shared__ int za[PB][kC5];
     constexpr int NW = kC5 * kKW;                           // 1552
-    constexpr int PER = (NW + 255) / 256;                   // 7
-    float acc[PER];
+    __shared__ float sx[8][2 * kKW + 2];
+    __shared__ float zv[8][kC5];
+    __shared__ int win[8][kC5];
+    __shared__ float red[NW + kC5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[kC5][4];
 #pragma unroll
-    for (int m = 0; m < PER; ++m) acc[m] = 0.f;
+    for (int c = 0; c < kC5; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
     float accb = 0.f;
     const int64_t pairs = B * L1;
-    const int64_t stages = (pairs + PB - 1) / PB;
-    for (int64_t st = blockIdx.x; st < stages; st += gridDim.x) {
+    for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += (int64_t)gridDim.x * 8) {
+        const int64_t b = pr / L1;
+        const int j = (int)(pr - b * L1);
+        const float* src = pooled + (b * k + 2 * j) * kKW;
+        for (int idx = lane; idx < 2 * kKW; idx += 32) sx[warp][idx] = src[idx];
+        if (lane < kC5) {
+            const int64_t o = (b * kC5 + lane) * L1 + j;
+            const int a = arg[o];                       // 0/1 winning row, 2 = ReLU dead
+            const float v = a < 2 ? dh1[o] : 0.f;
+            zv[warp][lane] = v;
+            win[warp][lane] = a < 2 ? a : 0;            // dead channels contribute v = 0
+            accb += v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < kC5; ++c) {
+            const float v = zv[warp][c];
+            const float* xr = sx[warp] + win[warp][c] * kKW;
+            acc[c][0] = fmaf(v, xr[lane], acc[c][0]);
+            acc[c][1] = fmaf(v, xr[lane + 32], acc[c][1]);
+            acc[c][2] = fmaf(v, xr[lane + 64], acc[c][2]);
+            if (lane == 0) acc[c][3] = fmaf(v, xr[96], acc[c][3]);
+        }
+        __syncwarp();
+    }
+    // ordered combine of the 8 warps
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int c = 0; c < kC5; ++c) {
+                float* r = red + c * kKW;
+                r[lane] = (w == 0 ? 0.f : r[lane]) + acc[c][0];
+                r[lane + 32] = (w == 0 ? 0.f : r[lane + 32]) + acc[c][1];
+                r[lane + 64] = (w == 0 ? 0.f : r[lane + 64]) + acc[c][2];
+                if (lane == 0) r[96] = (w == 0 ? 0.f : r[96]) + acc[c][3];
+            }
+            if (lane < kC5) red[NW + lane] = (w == 0 ? 0.f : red[NW + lane]) + accb;
+        }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < PB * 2 * kKW; idx += 256) {
-            const int pp = idx / (2 * kKW), i = idx - pp * (2 * kKW);
-            const int64_t pr = st * PB + pp;
-            float v = 0.f;
-            if (pr < pairs) {
-                const int64_t b = pr / L1;
-                const int j = (int)(pr - b * L1);
-                v = pooled[(b * k + 2 * j) * kKW + i];
-            }
-            sx[pp][i] = v;
-        }
-        if (threadIdx.x < PB * kC5) {
-            const int pp = threadIdx.x / kC5, c = threadIdx.x - pp * kC5;
-            const int64_t pr = st * PB + pp;
-            float v = 0.f;
-            int a = 2;
-            if (pr < pairs) {
-                const int64_t b = pr / L1;
-                const int j = (int)(pr - b * L1);
-                const int64_t o = (b * kC5 + c) * L1 + j;
-                v = dh1[o];
-                a = arg[o];
-            }
-            zv[pp][c] = v;
-            za[pp][c] = a;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int m = 0; m < PER; ++m) {
-            const int o = threadIdx.x + 256 * m;
-            if (o >= NW) break;
-            const int c = o / kKW, i = o - c * kKW;
-            float a = acc[m];
-#pragma unroll
-            for (int pp = 0; pp < PB; ++pp) {
-                const int r = za[pp][c];
-                if (r < 2) a = fmaf(zv[pp][c], sx[pp][r * kKW + i], a);
-            }
-            acc[m] = a;
-        }
-        if (threadIdx.x < kC5) {
-#pragma unroll
-            for (int pp = 0; pp < PB; ++pp)
-                if (za[pp][threadIdx.x] < 2) accb += zv[pp][threadIdx.x];
-        }
     }
     float* out = partials + (int64_t)blockIdx.x * (NW + kC5);
-#pragma unroll
-    for (int m = 0; m < PER; ++m) {
-        const int o = threadIdx.x + 256 * m;
-        if (o < NW) out[o] = acc[m];
-    }
-    if (threadIdx.x < kC5) out[NW + threadIdx.x] = accb;
+    for (int o = threadIdx.x; o < NW + kC5; o += 256) out[o] = red[o];
 }
 
-// out[o] = sum_p partials[p][o] in order; optionally split over two destinations
+// out[o] = sum_p partials[p][o] (fixed partition and order: deterministic); block = 32 outputs
+// x 8 partial lanes; optionally split over two destinations
 __global__ void __launch_bounds__(256)
 tail_reduce_partials(const float* __restrict__ partials, int parts, int total, int split_at,
                      float* __restrict__ out_a, float* __restrict__ out_b) {
-    const int o = blockIdx.x * 256 + threadIdx.x;
-    if (o >= total) return;
+    __shared__ float red[8][33];
+    const int ox = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + ox;
     float s = 0.f;
-    for (int p = 0; p < parts; ++p) s += partials[(int64_t)p * total + o];
-    if (o < split_at) out_a[o] = s; else out_b[o - split_at] = s;
+    if (o < total)
+        for (int p = gy; p < parts; p += 8) s += partials[(int64_t)p * total + o];
+    red[gy][ox] = s;
+    __syncthreads();
+    if (gy == 0 && o < total) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t += red[y][ox];
+        if (o < split_at) out_a[o] = t; else out_b[o - split_at] = t;
+    }
 }
 
 // Adam on flat buffers (torch.optim.Adam defaults semantics, train.py:99): the step counter
 // lives on the device so that the whole step can be replayed from a CUDA graph.
 __global__ void __launch_bounds__(256)
 adam_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-          int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps) {
+          int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale) {
     const int64_t t = *step + 1;
     const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const float gi = g[i];
+        const float gi = g[i] * grad_scale;
         const float mi = beta1 * m[i] + (1.f - beta1) * gi;
         const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
         m[i] = mi;
@@ -494,6 +504,37 @@ adam_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict_
     }
 }
 __global__ void adam_bump(int64_t* step) { *step += 1; }
+
+// NLL (train.py:39,44-45) on log-probabilities, single CTA: stats[0] = -sum_b logp[b][y_b],
+// stats[1] = #{argmax == y};  dlogp[b][c] = -grad_scale at c == y_b, else 0.
+__global__ void __launch_bounds__(1024)
+nll_sum_kernel(const float* __restrict__ logp, const int64_t* __restrict__ y, int64_t B, int C,
+               float grad_scale, float* __restrict__ stats, float* __restrict__ dlogp) {
+    __shared__ float sl[32], sc[32];
+    float loss = 0.f, correct = 0.f;
+    for (int64_t b = threadIdx.x; b < B; b += 1024) {
+        const int yb = (int)y[b];
+        int best = 0;
+        float bv = logp[b * C];
+        for (int c = 0; c < C; ++c) {
+            const float v = logp[b * C + c];
+            if (v > bv) { bv = v; best = c; }
+            if (dlogp) dlogp[b * C + c] = c == yb ? -grad_scale : 0.f;
+        }
+        if (yb >= 0 && yb < C) loss -= logp[b * C + yb];
+        correct += best == yb ? 1.f : 0.f;
+    }
+    loss = warp_sum(loss);
+    correct = warp_sum(correct);
+    if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = loss; sc[threadIdx.x >> 5] = correct; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c2 = 0.f;
+        for (int w = 0; w < 32; ++w) { a += sl[w]; c2 += sc[w]; }
+        stats[0] = a;
+        stats[1] = c2;
+    }
+}
 
 struct TailDims { int L1, L2, D1; };
 __host__ inline TailDims tail_dims(int k) {
@@ -504,6 +545,7 @@ __host__ inline TailDims tail_dims(int k) {
     return d;
 }
 constexpr int kFc1Splits = 8;
+constexpr int kDwSplits = 4;
 
 }  // namespace dgcnn
 
@@ -517,8 +559,9 @@ extern "C" size_t dgcnn_tail_workspace_bytes(int64_t num_graphs, int32_t k, int3
                                   + (size_t)num_graphs * kFc                   // dz3
                                   + (size_t)num_graphs * d.D1                  // dz2
                                   + (size_t)num_graphs * kC5 * d.L1            // dh1
-                                  + (size_t)2 * DGCNN_NUM_SMS * (kC6 * kC5 * kK6 + kC6)
-                                  + (size_t)2 * DGCNN_NUM_SMS * (kC5 * kKW + kC5));
+                                  + (size_t)num_graphs * (kC6 * kC5 * kK6 + kC6)   // conv6 partials
+                                  + (size_t)4 * DGCNN_NUM_SMS * (kC5 * kKW + kC5)   // conv5 partials
+                                  + (size_t)kDwSplits * kFc * d.D1);                // dWf1 slabs
     return (fwd > bwd ? fwd : bwd) + 1024;
 }
 
@@ -595,52 +638,74 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
     float* dz3 = ws;                            ws += B * kFc;
     float* dz2 = ws;                            ws += B * (int64_t)d.D1;
     float* dh1 = ws;                            ws += B * (int64_t)kC5 * d.L1;
-    float* part6 = ws;                          ws += 2 * DGCNN_NUM_SMS * (kC6 * kC5 * kK6 + kC6);
-    float* part5 = ws;
+    float* part6 = ws;                          ws += B * (kC6 * kC5 * kK6 + kC6);
+    float* part5 = ws;                          ws += 4 * DGCNN_NUM_SMS * (kC5 * kKW + kC5);
+    float* slabw = ws;
 
-    tail_fc2_bwd<<<1, 1024, 0, st>>>(dlogp, logp, h3, keep, B, num_classes, wf2, dlogit, dz3, dwf2, dbf2, dbf1);
+    tail_fc2_bwd_rows<<<grid_for(B, 8, 4), 256, 0, st>>>(dlogp, logp, keep, B, num_classes, wf2, dlogit, dz3);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    tail_fc2_bwd_params<<<(num_classes * kFc + num_classes + kFc + 31) / 32, 256, 0, st>>>(
+        dlogit, h3, dz3, B, num_classes, dwf2, dbf2, dbf1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dz2 = (dz3 Wf1) * (h2 > 0):  [B,128] x [128,D1]
     dim3 ga((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(B, 32), 1);
     gemm_f32<false, true, true><<<ga, 256, 0, st>>>(dz3, kFc, wf1, d.D1, dz2, (int)B, d.D1, kFc, kFc, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dWf1 = dz3^T h2:  [128,B] x [B,D1]
-    dim3 gb((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(kFc, 32), 1);
-    gemm_f32<true, true, false><<<gb, 256, 0, st>>>(dz3, kFc, h2, d.D1, dwf1, kFc, d.D1, (int)B, (int)B, nullptr);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    {   // split over the batch, slabs summed in order
+        const int kchunk = (int)ceil_div(ceil_div(B, kDwSplits), 32) * 32;
+        const int splits = (int)ceil_div(B, kchunk);
+        dim3 gb((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(kFc, 32), (unsigned)splits);
+        gemm_f32<true, true, false><<<gb, 256, 0, st>>>(dz3, kFc, h2, d.D1, slabw, kFc, d.D1, (int)B, kchunk,
+                                                        nullptr);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+        const int total = kFc * d.D1;
+        tail_reduce_partials<<<(total + 31) / 32, 256, 0, st>>>(slabw, splits, total, total, dwf1, dwf1);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
     const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * d.L2);
     const size_t smem_w = sizeof(float) * (kC6 * d.L2 + kC5 * d.L1);
     if (smem_in > 48 * 1024 || smem_w > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
     tail_c6_bwd_input<<<grid_for(B, 1, 4), 256, smem_in, st>>>(dz2, B, d.L1, w6, dh1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const int parts6 = grid_for(B, 1, 2);
+    const int parts6 = (int)B;
     tail_c6_bwd_weight<<<parts6, 256, smem_w, st>>>(dz2, h1, B, d.L1, part6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int n6 = kC6 * kC5 * kK6;
-    tail_reduce_partials<<<(n6 + kC6 + 255) / 256, 256, 0, st>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
+    tail_reduce_partials<<<(n6 + kC6 + 31) / 32, 256, 0, st>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     tail_c5_bwd_input<<<grid_for(B * d.L1, 8, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const int parts5 = grid_for(ceil_div(B * d.L1, 8), 1, 2);
+    const int parts5 = grid_for(ceil_div(B * d.L1, 8), 1, 4);
     tail_c5_bwd_weight<<<parts5, 256, 0, st>>>(dh1, arg, pooled, B, k, d.L1, part5);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int n5 = kC5 * kKW;
-    tail_reduce_partials<<<(n5 + kC5 + 255) / 256, 256, 0, st>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
+    tail_reduce_partials<<<(n5 + kC5 + 31) / 32, 256, 0, st>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }
 
 extern "C" int dgcnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps,
-                               void* stream) {
+                               float grad_scale, void* stream) {
     if (n < 0 || !step) return DGCNN_ERR_INVALID_ARGUMENT;
     if (n == 0) return DGCNN_OK;
     if (!params || !grads || !exp_avg || !exp_avg_sq) return DGCNN_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     adam_flat<<<grid_for(n, 256, 4), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1,
-                                                   beta2, eps);
+                                                   beta2, eps, grad_scale);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     adam_bump<<<1, 1, 0, st>>>(step);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
+extern "C" int dgcnn_nll_sum(const float* logp, const int64_t* y, int64_t num_graphs, int32_t num_classes,
+                             float grad_scale, float* stats, float* dlogp, void* stream) {
+    if (num_graphs < 0 || num_classes < 1 || !stats) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_graphs > 0 && (!logp || !y)) return DGCNN_ERR_INVALID_ARGUMENT;
+    nll_sum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(logp, y, num_graphs, num_classes,
+                                                                     grad_scale, stats, dlogp);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

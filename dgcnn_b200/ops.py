@@ -29,7 +29,7 @@ STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower(
 # reads it to report `gpu_launches`.  Keyed by entry point.
 LAUNCHES = {"build_graph": 0, "graph_ptr": 0, "graph_conv_fwd": 0, "graph_conv_bwd": 0,
             "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0, "stack_bwd": 0,
-            "build_bitmaps": 0, "tail_fwd": 0, "tail_bwd": 0, "adam_step": 0}
+            "build_bitmaps": 0, "tail_fwd": 0, "tail_bwd": 0, "adam_step": 0, "nll_sum": 0}
 
 
 def launches_total() -> int:
@@ -326,7 +326,7 @@ def stack_bwd_supported(num_features: int, max_nodes: int) -> bool:
 
 
 def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Graph, weights,
-              k: int, norm: int):
+              k: int, norm: int, out: Optional[Tensor] = None):
     """KSB: gradients of the eight GraphConv parameters from d(pooled), two launches.
     Returns [(dw1, db1), ..., (dw4, db4)] as views of one flat buffer."""
     lib = _lib.load_library()
@@ -341,7 +341,9 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     dpooled = dpooled.contiguous()
     ws = [w.contiguous() for w in weights]
     total = int(lib.dgcnn_stack_num_params(f))
-    grads = torch.empty(total, dtype=torch.float32, device=x.device)
+    grads = out if out is not None else torch.empty(total, dtype=torch.float32, device=x.device)
+    if grads.numel() != total or not grads.is_contiguous():
+        raise ValueError("dgcnn_b200: stack_bwd out buffer mismatch")
     wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f, b), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_bwd(_ptr(dpooled), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
@@ -402,8 +404,9 @@ def tail_fwd(pooled: Tensor, k: int, params, training: bool, seed: int, rng_offs
     return logp, (pooled, h1, arg, h2, h3, keep)
 
 
-def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params):
-    """KT backward -> (dpooled, [dw5, db5, dw6, db6, dwf1, dbf1, dwf2, dbf2])."""
+def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params, out_grads=None):
+    """KT backward -> (dpooled, [dw5, db5, dw6, db6, dwf1, dbf1, dwf2, dbf2]); `out_grads`
+    lets the caller have the eight gradients written in place (e.g. into a flat bucket)."""
     lib = _lib.load_library()
     pooled, h1, arg, h2, h3, keep = saved
     w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
@@ -412,7 +415,11 @@ def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params):
     b, c = logp.shape
     dev = pooled.device
     dpooled = torch.empty_like(pooled)
-    grads = [torch.empty_like(p) for p in (w5, b5, w6, b6, wf1, bf1, wf2, bf2)]
+    grads = list(out_grads) if out_grads is not None else \
+        [torch.empty_like(p) for p in (w5, b5, w6, b6, wf1, bf1, wf2, bf2)]
+    for g_, p_ in zip(grads, (w5, b5, w6, b6, wf1, bf1, wf2, bf2)):
+        if g_.numel() != p_.numel() or not g_.is_contiguous():
+            raise ValueError("dgcnn_b200: tail_bwd out_grads mismatch")
     ws = _workspace(lib.dgcnn_tail_workspace_bytes(b, int(k), c), dev)
     with torch.cuda.device(dev):
         rc = lib.dgcnn_tail_bwd(_ptr(dlogp), _ptr(pooled), b, int(k), _ptr(w5), _ptr(w6), _ptr(wf1),
@@ -420,12 +427,31 @@ def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params):
                                 _ptr(logp), _ptr(dpooled), *[_ptr(g) for g in grads], _ptr(ws), ws.numel(),
                                 _stream())
     _lib.check(rc, "tail_bwd")
-    LAUNCHES["tail_bwd"] += 9 if b > 0 else 0
+    LAUNCHES["tail_bwd"] += 12 if b > 0 else 0
     return dpooled, grads
 
 
+def nll_sum(logp: Tensor, y: Tensor, grad_scale: float = 1.0, want_grad: bool = True, stats=None):
+    """stats[0] = -sum_b logp[b, y_b] (train.py:39 with reduction='sum'), stats[1] = #correct
+    (train.py:45); optionally d(stats[0]*grad_scale)/dlogp.  One launch."""
+    lib = _lib.load_library()
+    _require_cuda(logp, "logp", torch.float32)
+    _require_cuda(y, "y", torch.int64)
+    logp, y = logp.contiguous(), y.contiguous()
+    b, c = logp.shape
+    if stats is None:
+        stats = torch.empty(2, dtype=torch.float32, device=logp.device)
+    dlogp = torch.empty_like(logp) if want_grad else None
+    with torch.cuda.device(logp.device):
+        rc = lib.dgcnn_nll_sum(_ptr(logp), _ptr(y), b, c, float(grad_scale), _ptr(stats), _ptr(dlogp),
+                               _stream())
+    _lib.check(rc, "nll_sum")
+    LAUNCHES["nll_sum"] = LAUNCHES.get("nll_sum", 0) + 1
+    return stats, dlogp
+
+
 def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: Tensor,
-              lr: float, beta1: float, beta2: float, eps: float) -> None:
+              lr: float, beta1: float, beta2: float, eps: float, grad_scale: float = 1.0) -> None:
     """Flat Adam update (train.py:41); `step` is a device int64 counter bumped by the call."""
     lib = _lib.load_library()
     for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
@@ -438,7 +464,8 @@ def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor
         raise ValueError("dgcnn_b200: adam_step size mismatch")
     with torch.cuda.device(params.device):
         rc = lib.dgcnn_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), n,
-                                 _ptr(step), float(lr), float(beta1), float(beta2), float(eps), _stream())
+                                 _ptr(step), float(lr), float(beta1), float(beta2), float(eps),
+                                 float(grad_scale), _stream())
     _lib.check(rc, "adam_step")
     LAUNCHES["adam_step"] += 2 if n > 0 else 0
 

@@ -1,0 +1,103 @@
+"""One training step of the reference loop, train.py:35-45, as a straight launch sequence.
+
+    data.to(device) -> model(data) -> NLL -> backward -> Adam.step -> zero_grad -> loss/acc
+
+The reference (and the autograd path of this package) pays for an autograd graph, ~16
+gradient-accumulation kernels into ``p.grad`` and a multi-launch optimizer per step.
+``FusedTrainer`` calls the hand-written kernels directly, with every gradient written in
+place into ONE flat buffer that the single all-reduce and the flat Adam consume:
+
+    K0 (+K0b) -> KS -> KT forward -> NLL -> KT backward -> KSB -> [all-reduce] -> Adam
+
+14 parameter tensors stay ordinary ``nn.Parameter``s (views of the flat buffers), so
+``state_dict()``/checkpoints (train.py:129) are unchanged.  CUDA-graph capturable: no host
+sync, step counter and dropout offset live on the device.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .nn import Model
+
+__all__ = ["FusedTrainer"]
+
+
+class FusedTrainer:
+    def __init__(self, model: Model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 group=None):
+        convs = (model.conv1, model.conv2, model.conv3, model.conv4)
+        self.model = model
+        self.group = group
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        # flat order = KSB's gradient layout for the graph convolutions, then the dense tail
+        self.stack_params = []
+        for c in convs:
+            if c.bias is None:
+                raise ValueError("FusedTrainer needs GCNConv layers with bias (the reference's)")
+            self.stack_params += [c.lin.weight, c.bias]
+        self.tail_params = [model.conv5.weight, model.conv5.bias, model.conv6.weight, model.conv6.bias,
+                            model.classifier_1.weight, model.classifier_1.bias,
+                            model.classifier_2.weight, model.classifier_2.bias]
+        self.params = self.stack_params + self.tail_params
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedTrainer: the model must live on a CUDA device")
+        n = sum(p.numel() for p in self.params)
+        self.num_params = n
+        self.num_stack = sum(p.numel() for p in self.stack_params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n + 2, dtype=torch.float32, device=dev)   # + loss sum, #correct
+        self.stats = self.grad[n:]
+        off = 0
+        self.tail_grad_views = []
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                view = self.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                gview = self.grad[off:off + p.numel()].view_as(p)
+                p.grad = gview
+                if i >= len(self.stack_params):
+                    self.tail_grad_views.append(gview)
+                off += p.numel()
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def supported(self, data) -> bool:
+        """The fused kernels need the largest graph of the batch (host knowledge)."""
+        mx = int(getattr(data, "max_nodes", 0) or 0)
+        f = data.x.size(1)
+        return (ops.stack_fwd_supported(f, mx) and ops.stack_bwd_supported(f, mx)
+                and self.model.classifier_2.out_features <= 32)
+
+    def step(self, data, global_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimisation step on `data`; returns the device tensor
+        [sum of NLL over the (global) batch, number of correct predictions]."""
+        m = self.model
+        if not self.supported(data):
+            raise RuntimeError("FusedTrainer.step: batch not supported by the fused kernels "
+                               "(set data.max_nodes; graphs must fit shared memory)")
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        graph = m.build_graph(data)
+        weights = self.stack_params[0::2]
+        biases = self.stack_params[1::2]
+        k, norm = m.sort_pool.k, m.conv1.norm
+        pooled, xcat, perm = ops.stack_fwd(data.x, graph, weights, biases, k, norm)
+        logp, saved = ops.tail_fwd(pooled, k, self.tail_params, m.training, m._tail_seed,
+                                   m._tail_rng_offset)
+        _, dlogp = ops.nll_sum(logp, data.y, 1.0, True, stats=self.stats)
+        dpooled, _ = ops.tail_bwd(dlogp, logp, saved, k, self.tail_params, out_grads=self.tail_grad_views)
+        ops.stack_bwd(dpooled, perm, xcat, data.x, graph, weights, k, norm,
+                      out=self.grad[:self.num_stack])
+        if world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+        if global_batch is None:
+            global_batch = graph.num_graphs * world
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                      self.betas[0], self.betas[1], self.eps, grad_scale=1.0 / float(global_batch))
+        return self.stats

@@ -260,10 +260,16 @@ int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, 
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* Adam (train.py:41,99: torch.optim.Adam defaults) on flat fp32 buffers;
- * `step` is a device int64 counter, incremented by the call. */
+ * `step` is a device int64 counter, incremented by the call; gradients are multiplied by
+ * grad_scale first (1/B_global after a summed all-reduce). */
 int dgcnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps,
-                    void* stream);
+                    float grad_scale, void* stream);
+
+/* NLL on log-probabilities (train.py:39,44-45): stats[0] = -sum_b logp[b, y_b], stats[1] =
+ * number of correct argmax predictions; dlogp (optional) [B,C] = d(stats[0] * grad_scale). */
+int dgcnn_nll_sum(const float* logp, const int64_t* y, int64_t num_graphs, int32_t num_classes,
+                  float grad_scale, float* stats, float* dlogp, void* stream);
 
 #ifdef __cplusplus
 }

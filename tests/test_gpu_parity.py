@@ -811,6 +811,40 @@ def test_flat_adam_matches_torch_adam():
     assert int(opt.step_count.item()) == 6
 
 
+def test_fused_trainer_matches_autograd_training():
+    """train.py:35-45: three optimisation steps through FusedTrainer (no autograd, flat
+    buffers, in-place gradients) equal three steps of Model + F.nll_loss + torch Adam."""
+    cfg = CONFIGS["proteins"]
+    batches = []
+    for i in range(3):
+        hb = make_batch("proteins", seed=10 + i, num_graphs=48)
+        d = hb.to(DEV)
+        d.max_nodes = int((hb.ptr[1:] - hb.ptr[:-1]).max())
+        batches.append(d)
+    torch.manual_seed(5)
+    m1 = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    m2 = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    m2.load_state_dict(m1.state_dict())
+    m2._tail_seed = m1._tail_seed
+    ref_opt = torch.optim.Adam(m1.parameters(), lr=1e-3)
+    trainer = dg.FusedTrainer(m2, lr=1e-3)
+    assert set(m2.state_dict()) == set(m1.state_dict())
+    for d in batches:
+        ref_opt.zero_grad()
+        logp = m1(d)
+        loss = torch.nn.functional.nll_loss(logp, d.y)          # mean, like train.py:39
+        loss.backward()
+        ref_opt.step()
+        stats = trainer.step(d)
+        assert abs(stats[0].item() / d.num_graphs - loss.item()) <= 1e-5 * max(1.0, abs(loss.item()))
+        assert stats[1].item() == float((logp.argmax(1) == d.y).sum())
+    p1 = dict(m1.named_parameters())
+    for name, p_ in m2.named_parameters():
+        err = (p_ - p1[name]).abs().max().item()
+        assert err <= 3e-6, f"{name}: {err:.3e}"
+    assert int(trainer.step_count.item()) == 3
+
+
 def test_cuda_graph_capture_replays_bit_identically():
     cfg = CONFIGS["mutag"]
     batch = make_batch("mutag").to(DEV)

@@ -355,7 +355,10 @@ static int fma_bwd_supported(int32_t num_features, int64_t max_nodes) {
 }
 
 extern "C" int dgcnn_stack_bwd_supported(int32_t num_features, int64_t max_nodes) {
-    return dgcnn_stack_bwd_mma_supported(num_features, max_nodes);
+    // 1: the tensor-core variant fits; 2: only the FMA variant fits (it needs less shared
+    // memory per node); 0: neither
+    if (dgcnn_stack_bwd_mma_supported(num_features, max_nodes)) return 1;
+    return fma_bwd_supported(num_features, max_nodes) ? 2 : 0;
 }
 
 extern "C" int64_t dgcnn_stack_num_params(int32_t num_features) {

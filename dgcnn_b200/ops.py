@@ -320,9 +320,20 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
 
 
 def stack_bwd_supported(num_features: int, max_nodes: int) -> bool:
+    return _stack_bwd_variant(num_features, max_nodes) is not None
+
+
+def _stack_bwd_variant(num_features: int, max_nodes: int):
+    """Which KSB implementation can hold the largest graph: the configured one if it fits,
+    else the FMA variant (smaller shared-memory footprint per node), else None."""
     if max_nodes <= 0 or max_nodes > BITMAP_MAX_NODES:
-        return False
-    return bool(_lib.load_library().dgcnn_stack_bwd_supported(int(num_features), int(max_nodes)))
+        return None
+    code = int(_lib.load_library().dgcnn_stack_bwd_supported(int(num_features), int(max_nodes)))
+    if code == 0:
+        return None
+    if code == 1 and STACK_VARIANT == STACK_MMA:
+        return STACK_MMA
+    return STACK_FMA
 
 
 def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Graph, weights,

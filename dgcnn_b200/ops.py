@@ -363,7 +363,7 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
                                  _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags),
                                  _ptr(graph.bitmap_t), _ptr(graph.bmoff_t), _ptr(graph.gflags_t), n, b,
                                  int(graph.max_nodes), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm),
-                                 int(STACK_VARIANT), _ptr(grads),
+                                 int(_stack_bwd_variant(f, graph.max_nodes)), _ptr(grads),
                                  _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
     _lib.check(rc, "stack_bwd")
     LAUNCHES["stack_bwd"] += 2 if (b > 0 and n > 0) else 0

@@ -20,44 +20,86 @@ namespace dgcnn {
 constexpr int kC5 = 16, kKW = 97, kC6 = 32, kK6 = 5, kFc = 128;
 
 // ------------------------------------------------------------------------------------------
-// conv5 + ReLU + MaxPool(2,2): one warp per pair of pooled rows (2j, 2j+1 are adjacent in
-// memory: 194 contiguous floats).  lane = (row, channel).  h1[b][c][j], arg[b][c][j] = 0/1
-// the winning row, 2 when the max is not positive (ReLU dead: no gradient).
+// conv5 + ReLU + MaxPool(2,2).  A pooled row pair (2j, 2j+1) is 194 contiguous floats; a CTA
+// stages 64 pairs in shared memory and every thread owns one pair x 4 channels (both rows,
+// so the pooling max stays in registers): 3 shared loads per 8 FMAs.  h1[b][c][j];
+// arg[b][c][j] = 0/1 the winning row, 2 when the max is not positive (ReLU dead).
 // ------------------------------------------------------------------------------------------
+constexpr int kC5Pairs = 64;                       // row pairs staged per CTA iteration
+constexpr int kC5Row = 2 * kKW;                    // one pair = 194 contiguous floats
+constexpr size_t kC5StageBytes = sizeof(float) * (kC5Pairs * kC5Row + kKW * kC5 + kC5);
+
+// stage `count` row pairs starting at pair index pr0 into xs[pp][194]; warp w copies pairs
+// w, w+8, ...; all 7 loads of a lane are issued before the first store
+__device__ __forceinline__ void c5_stage_pairs(const float* __restrict__ pooled, int64_t pr0, int count,
+                                               int k, int L1, float* __restrict__ xs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int pp = warp; pp < kC5Pairs; pp += 8) {
+        float v[7];
+        const bool live = pp < count;
+        const int64_t pr = pr0 + pp;
+        const int64_t b = live ? pr / L1 : 0;
+        const int j = live ? (int)(pr - b * L1) : 0;
+        const float* src = pooled + (b * k + 2 * j) * kKW;
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            const int i = lane + 32 * u;
+            v[u] = (live && i < kC5Row) ? src[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            const int i = lane + 32 * u;
+            if (i < kC5Row) xs[pp * kC5Row + i] = v[u];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 tail_c5_fwd(const float* __restrict__ pooled, int64_t B, int k, int L1, const float* __restrict__ w5,
             const float* __restrict__ b5, float* __restrict__ h1, uint8_t* __restrict__ arg) {
-    __shared__ float w5t[kKW * kC5];
-    __shared__ float sb[kC5];
-    __shared__ float sx[8][2 * kKW + 2];
+    extern __shared__ __align__(16) float c5sm[];
+    float* xs = c5sm;                                   // [64][194]
+    float* w5t = xs + kC5Pairs * kC5Row;                // [97][16]
+    float* sb = w5t + kKW * kC5;                        // [16]
     for (int idx = threadIdx.x; idx < kKW * kC5; idx += 256) {
         int c = idx / kKW, i = idx - c * kKW;
         w5t[i * kC5 + c] = w5[idx];
     }
     if (threadIdx.x < kC5) sb[threadIdx.x] = b5[threadIdx.x];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rowsel = lane >> 4, c = lane & 15;
+    const int pp = threadIdx.x >> 2, cg = threadIdx.x & 3;      // pair in the stage, channels 4cg..4cg+3
     const int64_t pairs = B * L1;
-    for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += (int64_t)gridDim.x * 8) {
-        const int64_t b = pr / L1;
-        const int j = (int)(pr - b * L1);
-        const float* src = pooled + (b * k + 2 * j) * kKW;
-        for (int idx = lane; idx < 2 * kKW; idx += 32) sx[warp][idx] = src[idx];
-        __syncwarp();
-        const float* xr = sx[warp] + rowsel * kKW;
-        float acc = sb[c];
+    for (int64_t pr0 = (int64_t)blockIdx.x * kC5Pairs; pr0 < pairs; pr0 += (int64_t)gridDim.x * kC5Pairs) {
+        const int count = (int)min((int64_t)kC5Pairs, pairs - pr0);
+        __syncthreads();
+        c5_stage_pairs(pooled, pr0, count, k, L1, xs);
+        __syncthreads();
+        const float* x0 = xs + pp * kC5Row;
+        const float* x1 = x0 + kKW;
+        float a0[4], a1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a0[q] = a1[q] = sb[4 * cg + q];
 #pragma unroll 4
-        for (int i = 0; i < kKW; ++i) acc = fmaf(w5t[i * kC5 + c], xr[i], acc);
-        const float zr = fmaxf(acc, 0.f);
-        const float other = __shfl_xor_sync(DGCNN_FULL_MASK, zr, 16);
-        if (rowsel == 0) {
-            const float m = fmaxf(zr, other);
-            const int64_t o = (b * kC5 + c) * L1 + j;
-            h1[o] = m;
-            arg[o] = (uint8_t)(m <= 0.f ? 2 : (zr >= other ? 0 : 1));
+        for (int i = 0; i < kKW; ++i) {
+            const float4 w = *reinterpret_cast<const float4*>(w5t + i * kC5 + 4 * cg);
+            const float u0 = x0[i], u1 = x1[i];
+            a0[0] = fmaf(w.x, u0, a0[0]); a0[1] = fmaf(w.y, u0, a0[1]);
+            a0[2] = fmaf(w.z, u0, a0[2]); a0[3] = fmaf(w.w, u0, a0[3]);
+            a1[0] = fmaf(w.x, u1, a1[0]); a1[1] = fmaf(w.y, u1, a1[1]);
+            a1[2] = fmaf(w.z, u1, a1[2]); a1[3] = fmaf(w.w, u1, a1[3]);
         }
-        __syncwarp();
+        if (pp < count) {
+            const int64_t pr = pr0 + pp;
+            const int64_t b = pr / L1;
+            const int j = (int)(pr - b * L1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float z0 = fmaxf(a0[q], 0.f), z1 = fmaxf(a1[q], 0.f);
+                const float m = fmaxf(z0, z1);
+                const int64_t o = (b * kC5 + 4 * cg + q) * L1 + j;
+                h1[o] = m;
+                arg[o] = (uint8_t)(m <= 0.f ? 2 : (z0 >= z1 ? 0 : 1));
+            }
+        }
     }
 }
 
@@ -71,8 +113,9 @@ tail_c6_fwd(const float* __restrict__ h1, int64_t B, int L1, const float* __rest
     extern __shared__ float sm[];
     float* w6t = sm;                         // [(c*5+d)][o]
     float* sb = sm + kC5 * kK6 * kC6;        // [32]
-    float* h1s = sb + kC6;                   // [16][L1]
+    float* h1s = sb + kC6;                   // [16][L1 + 8] (zero tail: windows may run past L1)
     const int L2 = L1 - (kK6 - 1);
+    const int L1P = L1 + 8;
     for (int idx = threadIdx.x; idx < kC6 * kC5 * kK6; idx += 256) {
         int o = idx / (kC5 * kK6), r = idx - o * (kC5 * kK6);
         w6t[r * kC6 + o] = w6[idx];
@@ -81,23 +124,41 @@ tail_c6_fwd(const float* __restrict__ h1, int64_t B, int L1, const float* __rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
-        for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) h1s[idx] = h1[b * kC5 * L1 + idx];
+        for (int idx = threadIdx.x; idx < kC5 * L1P; idx += 256) {
+            const int c = idx / L1P, t = idx - c * L1P;
+            h1s[idx] = t < L1 ? h1[(b * kC5 + c) * L1 + t] : 0.f;
+        }
         __syncthreads();
-        for (int t = warp; t < L2; t += 8) {
-            float acc = sb[lane];
+        // lane = output channel; a warp owns runs of 8 consecutive positions and slides a
+        // 5-wide window over each input channel: 17 shared loads per 40 FMAs
+        for (int t0 = warp * 8; t0 < L2; t0 += 64) {
+            float acc[8];
 #pragma unroll
-            for (int c = 0; c < kC5; ++c)
+            for (int u = 0; u < 8; ++u) acc[u] = sb[lane];
+#pragma unroll 2
+            for (int c = 0; c < kC5; ++c) {
+                float w[kK6];
 #pragma unroll
-                for (int d = 0; d < kK6; ++d)
-                    acc = fmaf(w6t[(c * kK6 + d) * kC6 + lane], h1s[c * L1 + t + d], acc);
-            h2[b * kC6 * L2 + lane * L2 + t] = fmaxf(acc, 0.f);
+                for (int d = 0; d < kK6; ++d) w[d] = w6t[(c * kK6 + d) * kC6 + lane];
+                const float* hr = h1s + c * L1P + t0;
+                float win[kK6 + 7];
+#pragma unroll
+                for (int u = 0; u < kK6 + 7; ++u) win[u] = hr[u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int d = 0; d < kK6; ++d) acc[u] = fmaf(w[d], win[u + d], acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < L2) h2[b * kC6 * L2 + lane * L2 + t0 + u] = fmaxf(acc[u], 0.f);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// fp32 GEMM  C[m][n] = sum_k A(m,k) * Bm(k,n)  on the FMA pipe, 32 x 128 tiles, 256 threads,
-// 2 x 8 outputs per thread with interleaved ownership (conflict-free scalar shared loads for
+// fp32 GEMM  C[m][n] = sum_k A(m,k) * Bm(k,n)  on the FMA pipe, 64 x 128 tiles, 256 threads,
+// 4 x 8 outputs per thread with interleaved ownership (conflict-free scalar shared loads for
 // every operand layout).  A_KM: A is stored [k][m] (else [m][k]); B_KN: Bm is stored [k][n]
 // (else [n][k]).  blockIdx.z splits K; each split writes its own [M][N] slab of C (the
 // caller adds the slabs in order).  RELU_MASK: C *= (mask > 0), the ReLU backward.
@@ -106,15 +167,15 @@ template <bool A_KM, bool B_KN, bool RELU_MASK>
 __global__ void __launch_bounds__(256)
 gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm, int64_t ldb,
          float* __restrict__ C, int M, int N, int K, int kchunk, const float* __restrict__ mask) {
-    constexpr int BM = 32, BN = 128, BK = 32, BMP = BM + 1, BNP = BN + 1;
+    constexpr int BM = 64, BN = 128, BK = 16, BMP = BM + 1, BNP = BN + 1;
     __shared__ float As[BK * BMP];
     __shared__ float Bs[BK * BNP];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
-    float acc[2][8];
+    float acc[4][8];
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
@@ -141,21 +202,23 @@ gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
             Bs[kk * BNP + n] = v;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int kk = 0; kk < BK; ++kk) {
-            const float a0 = As[kk * BMP + ty], a1 = As[kk * BMP + ty + 16];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float bv = Bs[kk * BNP + tx + 16 * q];
-                acc[0][q] = fmaf(a0, bv, acc[0][q]);
-                acc[1][q] = fmaf(a1, bv, acc[1][q]);
-            }
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], bv[8];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a[p] = As[kk * BMP + ty + 16 * p];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) bv[q] = Bs[kk * BNP + tx + 16 * q];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(a[p], bv[q], acc[p][q]);
         }
         __syncthreads();
     }
     float* out = C + (int64_t)blockIdx.z * M * N;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < 4; ++p) {
         const int gm = m0 + ty + 16 * p;
         if (gm >= M) continue;
 #pragma unroll
@@ -285,71 +348,97 @@ tail_fc2_bwd_params(const float* __restrict__ dlogit, const float* __restrict__ 
     }
 }
 
-// conv6 backward w.r.t. its input: dh1[b][c][s] = sum_{o,d} dz2[b][o][s-d] W6[o][c][d]
+// conv6 backward w.r.t. its input: dh1[b][c][s] = sum_{o,d} dz2[b][o][s-d] W6[o][c][d].
+// One CTA per graph; thread = (input channel c, run of 5 positions), sliding window over dz2.
 __global__ void __launch_bounds__(256)
 tail_c6_bwd_input(const float* __restrict__ dz2, int64_t B, int L1, const float* __restrict__ w6,
                   float* __restrict__ dh1) {
     extern __shared__ float sm[];
     float* w6c = sm;                         // [(o*5+d)][c]
-    float* dzs = sm + kC6 * kK6 * kC5;       // [32][L2]
     const int L2 = L1 - (kK6 - 1);
+    const int LZ = L2 + 2 * (kK6 - 1) + 8;   // dz row with 4 zeros in front, zeros behind
+    float* dzs = sm + kC6 * kK6 * kC5;       // [32][LZ]
     for (int idx = threadIdx.x; idx < kC6 * kC5 * kK6; idx += 256) {
         int o = idx / (kC5 * kK6), r = idx - o * (kC5 * kK6);
         int c = r / kK6, d = r - c * kK6;
         w6c[(o * kK6 + d) * kC5 + c] = w6[idx];
     }
-    const int c = threadIdx.x & 15, srow = threadIdx.x >> 4;
+    const int c = threadIdx.x & 15, run = threadIdx.x >> 4;     // 16 runs
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
-        for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) dzs[idx] = dz2[b * kC6 * L2 + idx];
+        for (int idx = threadIdx.x; idx < kC6 * LZ; idx += 256) {
+            const int o = idx / LZ, t = idx - o * LZ - (kK6 - 1);
+            dzs[idx] = (t >= 0 && t < L2) ? dz2[(b * kC6 + o) * L2 + t] : 0.f;
+        }
         __syncthreads();
-        for (int s = srow; s < L1; s += 16) {
-            float acc = 0.f;
-            for (int o = 0; o < kC6; ++o)
+        for (int s0 = run * 5; s0 < L1; s0 += 80) {
+            float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int o = 0; o < kC6; ++o) {
+                float w[kK6];
 #pragma unroll
-                for (int d = 0; d < kK6; ++d) {
-                    const int t = s - d;
-                    if (t >= 0 && t < L2) acc = fmaf(dzs[o * L2 + t], w6c[(o * kK6 + d) * kC5 + c], acc);
-                }
-            dh1[(b * kC5 + c) * L1 + s] = acc;
+                for (int d = 0; d < kK6; ++d) w[d] = w6c[(o * kK6 + d) * kC5 + c];
+                // dz[o][s - d] for s = s0..s0+4, d = 0..4  ->  padded index s - d + 4
+                const float* dr = dzs + o * LZ + s0;
+                float win[9];
+#pragma unroll
+                for (int u = 0; u < 9; ++u) win[u] = dr[u];
+#pragma unroll
+                for (int u = 0; u < 5; ++u)
+#pragma unroll
+                    for (int d = 0; d < kK6; ++d) acc[u] = fmaf(win[u + 4 - d], w[d], acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+                if (s0 + u < L1) dh1[(b * kC5 + c) * L1 + s0 + u] = acc[u];
         }
     }
 }
 
-// conv6 weight/bias gradient: one CTA per graph, thread-owned outputs, one partial vector
-// [2560 + 32] per graph (summed in graph order by tail_reduce_partials)
+// conv6 weight/bias gradient: persistent CTAs; thread = (pair of output channels, input
+// channel) owns all 5 taps (10 outputs) and slides a 5-wide window over h1 while it walks
+// dz2: 3 shared loads per 10 FMAs.  One partial vector [2560 + 32] per CTA.
 __global__ void __launch_bounds__(256)
 tail_c6_bwd_weight(const float* __restrict__ dz2, const float* __restrict__ h1, int64_t B, int L1,
                    float* __restrict__ partials) {
     extern __shared__ float sm[];
     const int L2 = L1 - (kK6 - 1);
+    const int L1P = L1 | 1;          // odd row stride: the 16 channel rows hit distinct banks
     float* dzs = sm;                 // [32][L2]
-    float* h1s = sm + kC6 * L2;      // [16][L1]
+    float* h1s = sm + kC6 * L2;      // [16][L1P]
     constexpr int NW = kC6 * kC5 * kK6;   // 2560
-    const int64_t b = blockIdx.x;
-    for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) dzs[idx] = dz2[b * kC6 * L2 + idx];
-    for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) h1s[idx] = h1[b * kC5 * L1 + idx];
-    __syncthreads();
-    float* out = partials + b * (NW + kC6);
+    const int c = threadIdx.x & 15, op = threadIdx.x >> 4;     // output channels 2op, 2op+1
+    float a0[kK6] = {0.f, 0.f, 0.f, 0.f, 0.f}, a1[kK6] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float sb0 = 0.f, sb1 = 0.f;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) dzs[idx] = dz2[b * kC6 * L2 + idx];
+        for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) {
+            const int cc = idx / L1, t = idx - cc * L1;
+            h1s[cc * L1P + t] = h1[b * kC5 * L1 + idx];
+        }
+        __syncthreads();
+        const float* d0 = dzs + (2 * op) * L2;
+        const float* d1 = d0 + L2;
+        const float* hr = h1s + c * L1P;
+        float w0 = hr[0], w1 = hr[1], w2 = hr[2], w3 = hr[3];
+        for (int t = 0; t < L2; ++t) {
+            const float w4 = hr[t + 4];
+            const float z0 = d0[t], z1 = d1[t];
+            a0[0] = fmaf(z0, w0, a0[0]); a0[1] = fmaf(z0, w1, a0[1]); a0[2] = fmaf(z0, w2, a0[2]);
+            a0[3] = fmaf(z0, w3, a0[3]); a0[4] = fmaf(z0, w4, a0[4]);
+            a1[0] = fmaf(z1, w0, a1[0]); a1[1] = fmaf(z1, w1, a1[1]); a1[2] = fmaf(z1, w2, a1[2]);
+            a1[3] = fmaf(z1, w3, a1[3]); a1[4] = fmaf(z1, w4, a1[4]);
+            if (c == 0) { sb0 += z0; sb1 += z1; }
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+        }
+    }
+    float* out = partials + (int64_t)blockIdx.x * (NW + kC6);
 #pragma unroll
-    for (int m = 0; m < NW / 256; ++m) {
-        const int o = threadIdx.x + 256 * m;
-        const int oc = o / (kC5 * kK6), r = o - oc * (kC5 * kK6);
-        const int c = r / kK6, d = r - c * kK6;
-        const float* dr = dzs + oc * L2;
-        const float* hr = h1s + c * L1 + d;
-        float a0 = 0.f, a1 = 0.f;
-        int t = 0;
-        for (; t + 1 < L2; t += 2) { a0 = fmaf(dr[t], hr[t], a0); a1 = fmaf(dr[t + 1], hr[t + 1], a1); }
-        if (t < L2) a0 = fmaf(dr[t], hr[t], a0);
-        out[o] = a0 + a1;
+    for (int d = 0; d < kK6; ++d) {
+        out[((2 * op) * kC5 + c) * kK6 + d] = a0[d];
+        out[((2 * op + 1) * kC5 + c) * kK6 + d] = a1[d];
     }
-    if (threadIdx.x < kC6) {
-        const float* dr = dzs + threadIdx.x * L2;
-        float a = 0.f;
-        for (int t = 0; t < L2; ++t) a += dr[t];
-        out[NW + threadIdx.x] = a;
-    }
+    if (c == 0) { out[NW + 2 * op] = sb0; out[NW + 2 * op + 1] = sb1; }
 }
 
 // conv5 / pool / ReLU backward w.r.t. pooled: one warp per row pair
@@ -402,67 +491,56 @@ tail_c5_bwd_input(const float* __restrict__ dh1, const uint8_t* __restrict__ arg
         }
 }
 
-// conv5 weight/bias gradient.  Every warp streams its own row pairs (warp-private staging, no
-// CTA barrier in the loop) and keeps ALL 16 x 97 outputs in registers (lane owns columns
-// lane, lane+32, lane+64, lane+96 of every channel); the 8 warps of a CTA are then added in
-// order and the CTA writes one partial vector [1552 + 16].
+// conv5 weight/bias gradient: persistent CTAs stage 64 row pairs at a time (coalesced, all
+// loads in flight) and every thread owns 7 of the 16 x 97 outputs across the whole sweep:
+// thread = (channel c, column group ig), columns ig + 16 q.  Only the row that won the
+// pooling (arg) contributes.  One partial vector [1552 + 16] per CTA.
 __global__ void __launch_bounds__(256)
 tail_c5_bwd_weight(const float* __restrict__ dh1, const uint8_t* __restrict__ arg,
                    const float* __restrict__ pooled, int64_t B, int k, int L1,
                    float* __restrict__ partials) {
     constexpr int NW = kC5 * kKW;                           // 1552
-    __shared__ float sx[8][2 * kKW + 2];
-    __shared__ float zv[8][kC5];
-    __shared__ int win[8][kC5];
-    __shared__ float red[NW + kC5];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float acc[kC5][4];
-#pragma unroll
-    for (int c = 0; c < kC5; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    extern __shared__ __align__(16) float c5sm[];
+    float* xs = c5sm;                                       // [64][194]
+    float* zv = xs + kC5Pairs * kC5Row;                     // [64][16]
+    int* win = reinterpret_cast<int*>(zv + kC5Pairs * kC5); // [64][16]
+    const int c = threadIdx.x & 15, ig = threadIdx.x >> 4;
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float accb = 0.f;
     const int64_t pairs = B * L1;
-    for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += (int64_t)gridDim.x * 8) {
-        const int64_t b = pr / L1;
-        const int j = (int)(pr - b * L1);
-        const float* src = pooled + (b * k + 2 * j) * kKW;
-        for (int idx = lane; idx < 2 * kKW; idx += 32) sx[warp][idx] = src[idx];
-        if (lane < kC5) {
-            const int64_t o = (b * kC5 + lane) * L1 + j;
-            const int a = arg[o];                       // 0/1 winning row, 2 = ReLU dead
-            const float v = a < 2 ? dh1[o] : 0.f;
-            zv[warp][lane] = v;
-            win[warp][lane] = a < 2 ? a : 0;            // dead channels contribute v = 0
-            accb += v;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < kC5; ++c) {
-            const float v = zv[warp][c];
-            const float* xr = sx[warp] + win[warp][c] * kKW;
-            acc[c][0] = fmaf(v, xr[lane], acc[c][0]);
-            acc[c][1] = fmaf(v, xr[lane + 32], acc[c][1]);
-            acc[c][2] = fmaf(v, xr[lane + 64], acc[c][2]);
-            if (lane == 0) acc[c][3] = fmaf(v, xr[96], acc[c][3]);
-        }
-        __syncwarp();
-    }
-    // ordered combine of the 8 warps
-    for (int w = 0; w < 8; ++w) {
-        if (warp == w) {
-#pragma unroll
-            for (int c = 0; c < kC5; ++c) {
-                float* r = red + c * kKW;
-                r[lane] = (w == 0 ? 0.f : r[lane]) + acc[c][0];
-                r[lane + 32] = (w == 0 ? 0.f : r[lane + 32]) + acc[c][1];
-                r[lane + 64] = (w == 0 ? 0.f : r[lane + 64]) + acc[c][2];
-                if (lane == 0) r[96] = (w == 0 ? 0.f : r[96]) + acc[c][3];
+    for (int64_t pr0 = (int64_t)blockIdx.x * kC5Pairs; pr0 < pairs; pr0 += (int64_t)gridDim.x * kC5Pairs) {
+        const int count = (int)min((int64_t)kC5Pairs, pairs - pr0);
+        __syncthreads();
+        c5_stage_pairs(pooled, pr0, count, k, L1, xs);
+        for (int idx = threadIdx.x; idx < kC5Pairs * kC5; idx += 256) {
+            const int pp = idx >> 4, cc = idx & 15;
+            float v = 0.f;
+            int a = 0;
+            if (pp < count) {
+                const int64_t pr = pr0 + pp;
+                const int64_t b = pr / L1;
+                const int j = (int)(pr - b * L1);
+                const int64_t o = (b * kC5 + cc) * L1 + j;
+                a = arg[o];
+                v = a < 2 ? dh1[o] : 0.f;
+                a = a < 2 ? a : 0;
             }
-            if (lane < kC5) red[NW + lane] = (w == 0 ? 0.f : red[NW + lane]) + accb;
+            zv[idx] = v;
+            win[idx] = a;
         }
         __syncthreads();
+        for (int pp = 0; pp < count; ++pp) {
+            const float v = zv[pp * kC5 + c];
+            const float* xr = xs + pp * kC5Row + win[pp * kC5 + c] * kKW + ig;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[q] = fmaf(v, xr[16 * q], acc[q]);
+            if (ig == 0) { acc[6] = fmaf(v, xr[96], acc[6]); accb += v; }
+        }
     }
     float* out = partials + (int64_t)blockIdx.x * (NW + kC5);
-    for (int o = threadIdx.x; o < NW + kC5; o += 256) out[o] = red[o];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) out[c * kKW + ig + 16 * q] = acc[q];
+    if (ig == 0) { out[c * kKW + 96] = acc[6]; out[NW + c] = accb; }
 }
 
 // out[o] = sum_p partials[p][o] (fixed partition and order: deterministic); block = 32 outputs
@@ -544,7 +622,7 @@ __host__ inline TailDims tail_dims(int k) {
     d.D1 = kC6 * d.L2;
     return d;
 }
-constexpr int kFc1Splits = 8;
+constexpr int kFc1Splits = 16;
 constexpr int kDwSplits = 4;
 
 }  // namespace dgcnn
@@ -585,16 +663,20 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* slabs = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 
-    tail_c5_fwd<<<grid_for(B * d.L1, 8, 8), 256, 0, st>>>(pooled, B, k, d.L1, w5, b5, h1, arg);
+    if (cudaFuncSetAttribute(tail_c5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kC5StageBytes) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    tail_c5_fwd<<<grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st>>>(pooled, B, k, d.L1, w5, b5, h1,
+                                                                             arg);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const size_t smem6 = sizeof(float) * (kC5 * kK6 * kC6 + kC6 + kC5 * d.L1);
+    const size_t smem6 = sizeof(float) * (kC5 * kK6 * kC6 + kC6 + kC5 * (d.L1 + 8));
     if (smem6 > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
     tail_c6_fwd<<<grid_for(B, 1, 4), 256, smem6, st>>>(h1, B, d.L1, w6, b6, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // fc1: [B, D1] x Wf1^T [D1, 128], split-K slabs
-    const int kchunk = (int)ceil_div(ceil_div(d.D1, kFc1Splits), 32) * 32;
+    const int kchunk = (int)ceil_div(ceil_div(d.D1, kFc1Splits), 16) * 16;
     const int splits = (int)ceil_div(d.D1, kchunk);
-    dim3 g1(1, (unsigned)ceil_div(B, 32), (unsigned)splits);
+    dim3 g1(1, (unsigned)ceil_div(B, 64), (unsigned)splits);
     gemm_f32<false, false, false><<<g1, 256, 0, st>>>(h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
                                                       nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
@@ -648,14 +730,14 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
         dlogit, h3, dz3, B, num_classes, dwf2, dbf2, dbf1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dz2 = (dz3 Wf1) * (h2 > 0):  [B,128] x [128,D1]
-    dim3 ga((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(B, 32), 1);
+    dim3 ga((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(B, 64), 1);
     gemm_f32<false, true, true><<<ga, 256, 0, st>>>(dz3, kFc, wf1, d.D1, dz2, (int)B, d.D1, kFc, kFc, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dWf1 = dz3^T h2:  [128,B] x [B,D1]
     {   // split over the batch, slabs summed in order
-        const int kchunk = (int)ceil_div(ceil_div(B, kDwSplits), 32) * 32;
+        const int kchunk = (int)ceil_div(ceil_div(B, kDwSplits), 16) * 16;
         const int splits = (int)ceil_div(B, kchunk);
-        dim3 gb((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(kFc, 32), (unsigned)splits);
+        dim3 gb((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(kFc, 64), (unsigned)splits);
         gemm_f32<true, true, false><<<gb, 256, 0, st>>>(dz3, kFc, h2, d.D1, slabw, kFc, d.D1, (int)B, kchunk,
                                                         nullptr);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
@@ -663,12 +745,12 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
         tail_reduce_partials<<<(total + 31) / 32, 256, 0, st>>>(slabw, splits, total, total, dwf1, dwf1);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
-    const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * d.L2);
-    const size_t smem_w = sizeof(float) * (kC6 * d.L2 + kC5 * d.L1);
+    const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * (d.L2 + 2 * (kK6 - 1) + 8));
+    const size_t smem_w = sizeof(float) * (kC6 * d.L2 + kC5 * (d.L1 | 1));
     if (smem_in > 48 * 1024 || smem_w > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
     tail_c6_bwd_input<<<grid_for(B, 1, 4), 256, smem_in, st>>>(dz2, B, d.L1, w6, dh1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const int parts6 = (int)B;
+    const int parts6 = grid_for(B, 1, 2);
     tail_c6_bwd_weight<<<parts6, 256, smem_w, st>>>(dz2, h1, B, d.L1, part6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int n6 = kC6 * kC5 * kK6;
@@ -676,8 +758,12 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     tail_c5_bwd_input<<<grid_for(B * d.L1, 8, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const int parts5 = grid_for(ceil_div(B * d.L1, 8), 1, 4);
-    tail_c5_bwd_weight<<<parts5, 256, 0, st>>>(dh1, arg, pooled, B, k, d.L1, part5);
+    const size_t smem5 = sizeof(float) * (kC5Pairs * kC5Row + 2 * kC5Pairs * kC5);
+    if (cudaFuncSetAttribute(tail_c5_bwd_weight, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem5) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    const int parts5 = grid_for(B * d.L1, kC5Pairs, 2);
+    tail_c5_bwd_weight<<<parts5, 256, smem5, st>>>(dh1, arg, pooled, B, k, d.L1, part5);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int n5 = kC5 * kKW;
     tail_reduce_partials<<<(n5 + kC5 + 31) / 32, 256, 0, st>>>(part5, parts5, n5 + kC5, n5, dw5, db5);

@@ -841,7 +841,7 @@ def test_fused_trainer_matches_autograd_training():
     p1 = dict(m1.named_parameters())
     for name, p_ in m2.named_parameters():
         err = (p_ - p1[name]).abs().max().item()
-        assert err <= 3e-6, f"{name}: {err:.3e}"
+        assert err <= 1e-5, f"{name}: {err:.3e}"
     assert int(trainer.step_count.item()) == 3
 
 

@@ -337,14 +337,14 @@ using namespace dgcnn;
 
 // tensor-core variant, graph_stack_bwd_mma.cu
 int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes);
-size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs);
+size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_t num_nodes);
 int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
                         int64_t ldc, const float* x, int64_t ldx, int32_t f, const int32_t* rowptr_t,
                         const int32_t* col_t, const float* dis, const int32_t* gptr,
                         const int32_t* gorder, const uint32_t* bitmap, const int32_t* bmoff,
                         const int32_t* gflags, const uint32_t* bitmap_t, const int32_t* bmoff_t,
-                        const int32_t* gflags_t, int64_t num_graphs, int64_t max_nodes, const float* w2,
-                        const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
+                        const int32_t* gflags_t, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                        const float* w2, const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
                         void* workspace, cudaStream_t st);
 
 static int fma_bwd_supported(int32_t num_features, int64_t max_nodes) {
@@ -365,12 +365,13 @@ extern "C" int64_t dgcnn_stack_num_params(int32_t num_features) {
     return num_features < 1 ? 0 : grad_offsets(num_features).total;
 }
 
-extern "C" size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features, int64_t num_graphs) {
+extern "C" size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features, int64_t num_graphs,
+                                                  int64_t num_nodes) {
     if (num_features < 1) return 0;
     // FMA variant: one partial gradient vector per CTA (at most 8 CTAs per SM);
     // tensor-core variant: one per graph
     const size_t fma = sizeof(float) * (size_t)grad_offsets(num_features).total * 8 * DGCNN_NUM_SMS + 256;
-    const size_t mma = dgcnn_stack_bwd_mma_workspace_bytes(num_features, num_graphs);
+    const size_t mma = dgcnn_stack_bwd_mma_workspace_bytes(num_features, num_graphs, num_nodes);
     return fma > mma ? fma : mma;
 }
 
@@ -404,12 +405,12 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
     if (max_nodes > 1024) return DGCNN_ERR_UNSUPPORTED;
     if (!dpooled || !perm || !xcat || !x || !rowptr_t || !dis || !gptr || !w2 || !w3 || !w4)
         return DGCNN_ERR_INVALID_ARGUMENT;
-    if (!workspace || workspace_bytes < dgcnn_stack_bwd_workspace_bytes(num_features, num_graphs))
+    if (!workspace || workspace_bytes < dgcnn_stack_bwd_workspace_bytes(num_features, num_graphs, num_nodes))
         return DGCNN_ERR_WORKSPACE;
     if (variant == DGCNN_STACK_MMA)
         return dgcnn_stack_bwd_mma(dpooled, perm, k, xcat, ldc, x, ldx, num_features, rowptr_t, col_t, dis,
                                    gptr, gorder, bitmap, bmoff, gflags, bitmap_t, bmoff_t, gflags_t,
-                                   num_graphs, max_nodes, w2, w3, w4, norm, grads, status, workspace, st);
+                                   num_nodes, num_graphs, max_nodes, w2, w3, w4, norm, grads, status, workspace, st);
 
     StackBwdParams p{};
     p.dpooled = dpooled; p.perm = perm; p.k = k; p.xcat = xcat; p.ldc = ldc;

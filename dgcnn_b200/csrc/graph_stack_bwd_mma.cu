@@ -6,7 +6,7 @@
 //   dh   = c_i * (A_hat^T . r dpre)  mma.sync: A^T from the bitmap (exact 0/1 fp16),
 //                                    r*dpre split hi/lo into fp16 planes
 //   dx   = dh W (+ pooled gradient)  mma.sync straight from the accumulator fragments
-//   dW  += dh^T x_in                 mma.sync: dh planes [c][node] x x_in planes [k][node]
+//   dW  += dh^T x_in                 mma.sync: dh planes [c][node] x x_in (from x_cat, split in registers)
 //
 // Gradients span many orders of magnitude, so each graph picks a power-of-two scale from
 // the largest pooled gradient it receives (exact to apply and to undo) before anything is
@@ -30,6 +30,7 @@ struct StackBwdMmaParams {
     const float* w2; const float* w3; const float* w4;
     int norm; int nmax;
     float* partials;     // [num_graphs][P]
+    float* gws;          // [N][32] fp32: gradient w.r.t. the current layer's output (L2-resident)
     int32_t* counter;
     int32_t* status;
 };
@@ -64,16 +65,14 @@ __host__ __device__ inline BwdShared bwd_shared_layout() {
 }
 
 // per graph (bytes)
-struct BwdTeamLayout { int G, P, DH, PX, vpl, bm, cs, rs, hv, rank, rp, red, sacc, total; int S; };
+struct BwdTeamLayout { int P, DH, vpl, bm, cs, rs, hv, rank, rp, red, sacc, total; int S; };
 __host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np) {
     BwdTeamLayout L;
     L.S = np + 8;
     const int wpr = (np + 31) >> 5;
     int o = 0;
-    L.G = o; o += np * kHid * 4;                         // fp32 gradient w.r.t. the layer output
     L.P = o; o += 2 * kHid * L.S * 2;                    // hi/lo planes of r * dpre * scale
     L.DH = o; o += 2 * kHid * L.S * 2;                   // hi/lo planes of dh * scale
-    L.PX = o; o += 2 * kHid * L.S * 2;                   // hi/lo planes of x_in
     L.vpl = o; o += al16(2 * L.S * 2);
     L.bm = o; o += al16(np * wpr * 4);
     L.cs = o; o += al16(np * 4);
@@ -240,10 +239,9 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     const BwdTeamLayout L = bwd_team_layout(f, np);
     const int S = L.S;
     unsigned char* sm = tm.smem;
-    float* G = reinterpret_cast<float*>(sm + L.G);
+    float* G = p.gws + (int64_t)base * kHid;             // this graph's rows
     __half* P = reinterpret_cast<__half*>(sm + L.P);
     __half* DH = reinterpret_cast<__half*>(sm + L.DH);
-    __half* PX = reinterpret_cast<__half*>(sm + L.PX);
     __half* vpl = reinterpret_cast<__half*>(sm + L.vpl);
     uint32_t* bm = reinterpret_cast<uint32_t*>(sm + L.bm);
     float* cs = reinterpret_cast<float*>(sm + L.cs);
@@ -380,22 +378,19 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     for (int layer = 3; layer >= 1; --layer) {
         const int offy = (layer - 1) * kHid;
         const int offx = (layer - 2) * kHid;             // slice of x_in (layers 3 and 2)
-        // A: P planes <- r * dpre * scale, db; PX planes <- x_in (for dW)
+        // A: P planes <- r * dpre * scale, db
         {
             float dbp = 0.f;
             __half* ph = P;  __half* pl = P + kHid * S;
-            __half* xh = PX; __half* xl = PX + kHid * S;
             for (int i = warp; i < np; i += nwarps) {
-                float sc = 0.f, xv = 0.f;
+                float sc = 0.f;
                 if (i < n) {
                     const float y = xc[(int64_t)i * p.ldc + offy + lane];
                     const float d = G[i * kHid + lane] * (1.f - y * y);
                     dbp += d;
                     sc = rs[i] * d * scale;
-                    if (layer >= 2) xv = xc[(int64_t)i * p.ldc + offx + lane];
                 }
                 store_split(ph, pl, lane * S + i, sc);
-                if (layer >= 2) store_split(xh, xl, lane * S + i, xv);
             }
             red0[warp * kHid + lane] = dbp;
         }
@@ -410,29 +405,42 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         tm.sync();
         // C: parameter gradient of the layer
         if (layer >= 2) {
-            // dW[c][k] = sum_i dh[i][c] x_in[i][k]: 8 output tiles (2 x 4), one per warp
+            // dW[c][k] = sum_i dh[i][c] x_in[i][k]: 8 output tiles (2 x 4), one per warp.
+            // A = dh planes [c][node]; B = x_in straight from x_cat in HBM/L2 (fp32, split
+            // hi/lo in registers; the next k-tile's four values are fetched ahead)
             const int ow = layer == 3 ? GO.w3 : GO.w2;
             const int g = lane >> 2, t = lane & 3;
             const uint32_t* dh32[2] = {reinterpret_cast<const uint32_t*>(DH),
                                        reinterpret_cast<const uint32_t*>(DH + kHid * S)};
-            const uint32_t* px32[2] = {reinterpret_cast<const uint32_t*>(PX),
-                                       reinterpret_cast<const uint32_t*>(PX + kHid * S)};
             for (int tile = warp; tile < 8; tile += nwarps) {
                 const int mc = tile >> 2, nk = tile & 3;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* xcol = xc + offx + 8 * nk + g;          // feature column of this lane
+                auto fetch = [&](int kt, float (&v)[4]) {
+                    const int i0 = kt * 16 + 2 * t;
+                    v[0] = i0 < n ? xcol[(int64_t)i0 * p.ldc] : 0.f;
+                    v[1] = i0 + 1 < n ? xcol[(int64_t)(i0 + 1) * p.ldc] : 0.f;
+                    v[2] = i0 + 8 < n ? xcol[(int64_t)(i0 + 8) * p.ldc] : 0.f;
+                    v[3] = i0 + 9 < n ? xcol[(int64_t)(i0 + 9) * p.ldc] : 0.f;
+                };
+                float cur[4], nxt[4];
+                fetch(0, cur);
                 for (int kt = 0; kt < tiles; ++kt) {
+                    if (kt + 1 < tiles) fetch(kt + 1, nxt);
                     const int ia = ((16 * mc + g) * S + kt * 16 + 2 * t) >> 1;
-                    const int ib = ((8 * nk + g) * S + kt * 16 + 2 * t) >> 1;
                     uint32_t ah[4], al[4];
                     ah[0] = dh32[0][ia]; ah[1] = dh32[0][ia + 4 * S]; ah[2] = dh32[0][ia + 4];
                     ah[3] = dh32[0][ia + 4 * S + 4];
                     al[0] = dh32[1][ia]; al[1] = dh32[1][ia + 4 * S]; al[2] = dh32[1][ia + 4];
                     al[3] = dh32[1][ia + 4 * S + 4];
-                    const uint32_t bh0 = px32[0][ib], bh1 = px32[0][ib + 4];
-                    const uint32_t bl0 = px32[1][ib], bl1 = px32[1][ib + 4];
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split2(cur[0], cur[1], bh0, bl0);
+                    split2(cur[2], cur[3], bh1, bl1);
                     mma_f16(acc, ah, bh0, bh1);
                     mma_f16(acc, al, bh0, bh1);
                     mma_f16(acc, ah, bl0, bl1);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
                 }
                 float* o = sacc + ow + (16 * mc + g) * kHid + 8 * nk + 2 * t;
                 o[0] = acc[0] * inv_scale; o[1] = acc[1] * inv_scale;
@@ -567,8 +575,9 @@ int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes) {
     return bwd_team_layout(f, np).total <= kQuads * bwd_quad_bytes() ? 1 : 0;
 }
 
-size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs) {
-    return sizeof(float) * (size_t)grad_offsets_m(f).total * (size_t)(num_graphs > 0 ? num_graphs : 1) + 512;
+size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_t num_nodes) {
+    return sizeof(float) * ((size_t)grad_offsets_m(f).total * (size_t)(num_graphs > 0 ? num_graphs : 1) +
+                            (size_t)(num_nodes > 0 ? num_nodes : 0) * kHid) + 1024;
 }
 
 int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
@@ -576,7 +585,8 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
                         const int32_t* col_t, const float* dis, const int32_t* gptr,
                         const int32_t* gorder, const uint32_t* bitmap, const int32_t* bmoff,
                         const int32_t* gflags, const uint32_t* bitmap_t, const int32_t* bmoff_t,
-                        const int32_t* gflags_t, int64_t num_graphs, int64_t max_nodes, const float* w2,
+                        const int32_t* gflags_t, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                        const float* w2,
                         const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
                         void* workspace, cudaStream_t st) {
     StackBwdMmaParams p{};
@@ -590,6 +600,9 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     p.counter = reinterpret_cast<int32_t*>(aligned);
     p.partials = reinterpret_cast<float*>(aligned + 256);
+    p.gws = reinterpret_cast<float*>(
+        ((uintptr_t)(p.partials + (size_t)grad_offsets_m(f).total * (size_t)num_graphs) + 255) &
+        ~(uintptr_t)255);
     p.status = status;
     if (cudaMemsetAsync(p.counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
     const size_t smem = (size_t)al16(bwd_shared_layout().total) + (size_t)kQuads * bwd_quad_bytes();

@@ -355,7 +355,7 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     grads = out if out is not None else torch.empty(total, dtype=torch.float32, device=x.device)
     if grads.numel() != total or not grads.is_contiguous():
         raise ValueError("dgcnn_b200: stack_bwd out buffer mismatch")
-    wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f, b), x.device)
+    wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f, b, n), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_bwd(_ptr(dpooled), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
                                  _ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr_t), _ptr(graph.col_t),

@@ -218,7 +218,8 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
  * ------------------------------------------------------------------------ */
 int dgcnn_stack_bwd_supported(int32_t num_features, int64_t max_nodes);  /* 0 no, 1 MMA, 2 FMA only */
 int64_t dgcnn_stack_num_params(int32_t num_features);
-size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features, int64_t num_graphs);
+size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features, int64_t num_graphs,
+                                       int64_t num_nodes);
 int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                     const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                     int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,

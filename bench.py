@@ -379,10 +379,11 @@ def main():
     h2d_bytes = host_batches[0].nbytes()
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        # Nothing collective happens after this point.  Tearing down an NCCL communicator whose
+        # kernels live inside captured CUDA graphs can block forever: leave without ceremony.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
     # ---- roofline: forward hot path and its dominant kernel, each timed alone ----
     peak, peak_kind = measured_peaks()
@@ -487,8 +488,9 @@ def main():
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)                                   # see the note at the rank != 0 exit
 
 
 if __name__ == "__main__":

@@ -34,9 +34,11 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
     "dgcnn_graph_bitmap_words": (c_int64, [c_int64, c_int64, c_int64]),
+    "dgcnn_graph_fragmap_words": (c_int64, [c_int64, c_int64, c_int64]),
     "dgcnn_build_bitmaps": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
-                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32,
-                                      c_void_p]),
+                                      c_void_p, c_int64, c_void_p, c_void_p,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int32, c_void_p]),
     "dgcnn_graph_ptr": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "dgcnn_graph_conv_fwd": (c_int32, [c_void_p, c_int64, c_int32,
                                        c_void_p, c_void_p, c_void_p,
@@ -59,9 +61,11 @@ SIGNATURES = {
                                       c_void_p, c_size_t, c_void_p]),
     "dgcnn_stack_fwd_supported": (c_int32, [c_int32, c_int64]),
     "dgcnn_stack_fwd_workspace_bytes": (c_size_t, []),
+    "dgcnn_stack_fwd_set_trace": (None, [c_void_p]),
     "dgcnn_stack_fwd": (c_int32, [c_void_p, c_int64, c_int32,
                                   c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int64, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p,
@@ -151,7 +155,7 @@ def load_library() -> ctypes.CDLL:
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(lib, name)      # AttributeError = header/library mismatch: loud
             fn.restype, fn.argtypes = restype, argtypes
-        if lib.dgcnn_abi_version() != 1:
+        if lib.dgcnn_abi_version() != 2:
             raise RuntimeError("dgcnn_b200: ABI version mismatch between _lib.py and the library")
         _lib = lib
     return _lib

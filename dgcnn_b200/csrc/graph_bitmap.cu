@@ -24,48 +24,117 @@ __device__ __forceinline__ int bitmap_words_of(int n, int max_nodes) {
     return np * ((np + 31) >> 5);
 }
 
-// exclusive scan of the per-graph word counts, one CTA
+__device__ __forceinline__ int fragmap_words_of(int n, int max_nodes) {
+    if (n <= 0 || n > max_nodes) return 0;
+    const int t = (n + 15) >> 4;
+    return t * ((t + 3) >> 2) * 32;
+}
+
+// exclusive scans of the per-graph word counts (row bitmap | fragment map), one CTA; the two
+// running sums travel packed in one 64-bit integer
 __global__ void __launch_bounds__(1024)
 k0b_offsets(const int32_t* __restrict__ gptr, int num_graphs, int max_nodes,
-            int32_t* __restrict__ bmoff, int32_t* __restrict__ gflags) {
-    __shared__ int wsum[32];
-    __shared__ int carry_s;
+            int32_t* __restrict__ bmoff, int32_t* __restrict__ fgoff, int32_t* __restrict__ gflags,
+            const int32_t* __restrict__ gorder, int4* __restrict__ gdesc) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x == 0) carry_s = 0ull;
     __syncthreads();
     for (int c0 = 0; c0 < num_graphs; c0 += 1024) {
         const int g = c0 + threadIdx.x;
-        int v = 0;
+        unsigned long long v = 0ull;
         if (g < num_graphs) {
             const int n = gptr[g + 1] - gptr[g];
-            v = bitmap_words_of(n, max_nodes);
+            v = (unsigned long long)(unsigned)bitmap_words_of(n, max_nodes) |
+                ((unsigned long long)(unsigned)fragmap_words_of(n, max_nodes) << 32);
             gflags[g] = (n > max_nodes) ? 2 : 0;
         }
-        int inc = v;
+        unsigned long long inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int u = __shfl_up_sync(DGCNN_FULL_MASK, inc, o);
+            unsigned long long u = __shfl_up_sync(DGCNN_FULL_MASK, inc, o);
             if (lane >= o) inc += u;
         }
         if (lane == 31) wsum[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            int w = wsum[lane], winc = w;
+            unsigned long long w = wsum[lane], winc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(DGCNN_FULL_MASK, winc, o);
+                unsigned long long u = __shfl_up_sync(DGCNN_FULL_MASK, winc, o);
                 if (lane >= o) winc += u;
             }
             wsum[lane] = winc - w;
         }
         __syncthreads();
-        const int excl = carry_s + wsum[warp] + inc - v;
-        if (g < num_graphs) bmoff[g] = excl;
+        const unsigned long long excl = carry_s + wsum[warp] + inc - v;
+        if (g < num_graphs) {
+            bmoff[g] = (int)(unsigned)(excl & 0xffffffffull);
+            if (fgoff) fgoff[g] = (int)(unsigned)(excl >> 32);
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) bmoff[num_graphs] = carry_s;
+    if (threadIdx.x == 0) {
+        bmoff[num_graphs] = (int)(unsigned)(carry_s & 0xffffffffull);
+        if (fgoff) fgoff[num_graphs] = (int)(unsigned)(carry_s >> 32);
+    }
+    if (gdesc && fgoff) {
+        // work descriptors in processing order: one 16-byte load tells a team all it needs
+        __syncthreads();
+        for (int q = threadIdx.x; q < num_graphs; q += 1024) {
+            const int g = gorder ? gorder[q] : q;
+            const int b0 = gptr[g];
+            gdesc[q] = make_int4(g, b0, gptr[g + 1] - b0, fgoff[g]);
+        }
+    }
+}
+
+// Fragment-major copy of the row bitmaps for the tensor-core kernels (graph_stack_mma.cu):
+// graph g with T = np/16 row tiles and G = ceil(T/4) column groups owns T*G*32 words at
+// fragmap + fgoff[g]; word (mt, grp, lane = 4*gq + t) holds, for the four 16x16 blocks
+// kt = 4*grp + q, the lane's m16k16 A-fragment bits: pair m = 4q + i at bit m (even column)
+// and bit 16 + m (odd column), i = 0: (row gq, cols 2t..), 1: (row gq+8, cols 2t..),
+// 2: (row gq, cols 2t+8..), 3: (row gq+8, cols 2t+8..).  One warp per (mt, grp) unit.
+__global__ void __launch_bounds__(256)
+k0b_fragments(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ bmoff,
+              const int32_t* __restrict__ fgoff, const int32_t* __restrict__ gptr, int num_graphs,
+              uint32_t* __restrict__ fragmap, const int32_t* gate_word, int gate_mask) {
+    if (gate_word && !(*gate_word & gate_mask)) return;
+    const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+    const int units = fgoff[num_graphs] >> 5;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += warps) {
+        int lo = 0, hi = num_graphs;                 // last g with fgoff[g] <= 32 u
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (fgoff[mid] <= (u << 5)) lo = mid; else hi = mid;
+        }
+        const int g = lo, n = gptr[g + 1] - gptr[g];
+        const int np = (n + 15) & ~15, wpr = (np + 31) >> 5, T = np >> 4, G = (T + 3) >> 2;
+        const int local = u - (fgoff[g] >> 5);
+        const int mt = local / G, grp = local - mt * G;
+        const uint32_t* r0 = bitmap + bmoff[g] + (int64_t)(mt * 16 + gq) * wpr;
+        const uint32_t* r1 = r0 + 8 * wpr;
+        const int w0 = 2 * grp, w1 = 2 * grp + 1;
+        const unsigned long long row0 = (unsigned long long)r0[w0] |
+                                        ((unsigned long long)(w1 < wpr ? r0[w1] : 0u) << 32);
+        const unsigned long long row1 = (unsigned long long)r1[w0] |
+                                        ((unsigned long long)(w1 < wpr ? r1[w1] : 0u) << 32);
+        uint32_t out = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned long long src = (i & 1) ? row1 : row0;
+                const int col = q * 16 + 2 * t + 8 * (i >> 1);
+                const uint32_t two = (uint32_t)(src >> col) & 3u;
+                out |= ((two & 1u) << (4 * q + i)) | ((two >> 1) << (16 + 4 * q + i));
+            }
+        fragmap[fgoff[g] + (local << 5) + lane] = out;
+    }
 }
 
 // one warp per node row
@@ -137,11 +206,20 @@ extern "C" int64_t dgcnn_graph_bitmap_words(int64_t num_nodes, int64_t num_graph
     return (num_nodes + 15 * num_graphs) * ((npmax + 31) / 32) + 32;
 }
 
+extern "C" int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_graphs, int64_t max_nodes) {
+    if (num_nodes < 0 || num_graphs < 0 || max_nodes < 1) return 0;
+    if (max_nodes > 1024) max_nodes = 1024;
+    const int64_t tmax = (max_nodes + 15) / 16;
+    // sum_g T_g * G_g * 32 <= (N/16 + B) * G_max * 32
+    return (num_nodes / 16 + num_graphs) * ((tmax + 3) / 4) * 32 + 32;
+}
+
 extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col, const int32_t* gptr,
                                    int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                                    uint32_t* bitmap, int64_t bitmap_words, int32_t* bmoff,
-                                   int32_t* gflags, const int32_t* gate_word, int32_t gate_mask,
-                                   void* stream) {
+                                   int32_t* gflags, uint32_t* fragmap, int64_t fragmap_words,
+                                   int32_t* fgoff, const int32_t* gorder, int32_t* gdesc,
+                                   const int32_t* gate_word, int32_t gate_mask, void* stream) {
     if (num_nodes < 0 || num_graphs < 0 || max_nodes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_graphs == 0) return DGCNN_OK;
     if (!rowptr || !gptr || !bitmap || !bmoff || !gflags) return DGCNN_ERR_INVALID_ARGUMENT;
@@ -152,13 +230,27 @@ extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * (size_t)need, st) != cudaSuccess)
         return DGCNN_ERR_CUDA;
-    k0b_offsets<<<1, 1024, 0, st>>>(gptr, (int)num_graphs, (int)max_nodes, bmoff, gflags);
+    if (fragmap) {
+        if (!fgoff) return DGCNN_ERR_INVALID_ARGUMENT;
+        const int64_t fneed = dgcnn_graph_fragmap_words(num_nodes, num_graphs, max_nodes);
+        if (fragmap_words < fneed || fneed >= INT32_MAX) return DGCNN_ERR_WORKSPACE;
+    }
+    if (gdesc && (!fragmap || ((uintptr_t)gdesc & 15))) return DGCNN_ERR_INVALID_ARGUMENT;
+    k0b_offsets<<<1, 1024, 0, st>>>(gptr, (int)num_graphs, (int)max_nodes, bmoff,
+                                    fragmap ? fgoff : nullptr, gflags, gorder,
+                                    reinterpret_cast<int4*>(gdesc));
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (num_nodes > 0) {
         k0b_fill<<<grid_for(num_nodes, 8, 8), 256, 0, st>>>(rowptr, col, gptr, (int)num_graphs, num_nodes,
                                                             (int)max_nodes, bmoff, bitmap, gflags,
                                                             gate_word, gate_mask);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
+        if (fragmap) {
+            const int64_t units = dgcnn_graph_fragmap_words(num_nodes, num_graphs, max_nodes) / 32;
+            k0b_fragments<<<grid_for(units, 8, 8), 256, 0, st>>>(bitmap, bmoff, fgoff, gptr, (int)num_graphs,
+                                                                 fragmap, gate_word, gate_mask);
+            DGCNN_RETURN_IF_LAUNCH_FAILED();
+        }
     }
     return DGCNN_OK;
 }

@@ -18,6 +18,8 @@ struct StackFwdParams {
     const float* x; int64_t ldx; int f;
     const int32_t* rowptr; const int32_t* col; const float* dis; const int32_t* gptr;
     const uint32_t* bitmap; const int32_t* bmoff; const int32_t* gflags;   // K0b (graph_bitmap.cu)
+    const uint32_t* fragmap; const int32_t* fgoff;                          // K0b, fragment-major copy
+    const int32_t* gdesc;   // K0b: {graph, first node, nodes, fgoff} per graph, descending size
     int num_graphs;
     const float* w1; const float* b1; const float* w2; const float* b2;
     const float* w3; const float* b3; const float* w4; const float* b4;
@@ -27,6 +29,7 @@ struct StackFwdParams {
     const int32_t* gorder;  // optional processing order (largest graphs first), else natural
     int32_t* counter;   // work queue head, zeroed by the host wrapper
     int32_t* status;    // optional
+    int64_t* trace;     // optional debug timeline, [num_graphs][16] (dgcnn_stack_fwd_set_trace)
 };
 
 

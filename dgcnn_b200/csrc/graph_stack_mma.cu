@@ -1,31 +1,43 @@
-// Tensor-core version of the fused forward (model.py:28-35 in one launch; see
-// graph_stack.cu for the data flow).  Same bitmap-in-shared-memory design, but the
-// aggregations  A_hat . H  and the 32x32 projections run on the tensor cores:
+// KS, tensor-core variant: the fused forward of model.py:28-35 in ONE launch
+// (remove_self_loops + 4 x tanh(GCNConv) + cat + SortAggregation), one thread team per graph.
 //
-//   * A (adjacency + self loop) is 0/1, hence EXACT in fp16.  Its m16k16 fragments are
-//     expanded from the bitmap directly into registers (a few shifts and masks per
-//     k-tile); all-zero 16x16 blocks are skipped, so sparse graphs stay cheap.
-//   * H must keep fp32 accuracy (1e-5 parity bar): every value is split as
-//     h = hi + lo with hi = fp16(h), lo = fp16(h - hi)  (22 mantissa bits; inputs are
-//     tanh outputs times c_j <= 1, so no range problem), stored as two fp16 planes
-//     [channel][node] in shared memory, and multiplied in two MMAs that accumulate in
-//     fp32.  The products are exact; only the fp32 accumulation rounds.
-//   * the projection (r_i * agg) @ W^T reuses the accumulator fragments as A operands
-//     (C layout of two n-tiles == A layout of one k-tile), split hi/lo in registers,
-//     against hi/lo planes of W:  hi*hi + lo*hi + hi*lo  (the lo*lo term is < 2^-22).
+// Data flow per graph (n nodes, np = n rounded up to 16, T = np/16 row tiles):
 //
-// mma.sync (register fragments) is used on purpose, not tcgen05: the operands are
-// generated in registers from a bitmap for graphs of ~30-500 nodes; tcgen05 needs
-// shared-memory operand tiles of M >= 64/128 rows in descriptor layouts plus a TMEM
-// round trip per tile, which would waste most of each tile on 75-node graphs.
+//   adjacency   A_hat = A + I is 0/1.  K0b ships it in FRAGMENT-MAJOR form (graph_bitmap.cu):
+//               for every 16-row tile and every group of four 16-column blocks one 32-bit word
+//               per lane, in which the lane's eight m16k16 A-fragment bits of each block sit
+//               at bit m (low half) and 16+m (high half).  A fragment register is then
+//               rotate + mask:  rotl(w, 14-m) & 0x40004000  = two fp16 values in {0, 2.0}
+//               (the factor 2 is folded into the row coefficient).  8 ALU per 16x16 block.
+//   features    must keep fp32 accuracy (1e-5 parity bar): every value is split h = hi + lo,
+//               hi = fp16(h), lo = fp16(h - hi) (22 mantissa bits), stored [node][hi 32|lo 32|pad 8]
+//               halfs in shared memory (144 B rows: conflict-free for ldmatrix and for the
+//               packed half2 epilogue stores).  B fragments come from ldmatrix.x4.trans.
+//               Products 0/2 x fp16 are exact, only the fp32 accumulation rounds.
+//   projection  (r_i agg) @ W^T reuses the accumulator fragments as A operands (C layout of
+//               two n-tiles == A layout of one k-tile), split hi/lo in registers, against
+//               hi/lo planes of W (ldmatrix):  hi*hi + lo*hi + hi*lo.
+//   layer 1     F <= 8: aggregate first -- one 8-wide n-tile holds all features, scaled per
+//               graph by a power of two so that the split never leaves the fp16 range --
+//               then an fp32 FMA projection F -> 32.  F > 8: project first (FMA), aggregate
+//               on the tensor cores.
+//   layer 4     32 -> 1: v = c_i (x_3 . w4) is emitted by layer 3's epilogue; one MMA column.
+//   SortPool    64-bit (key, index) composites, rank sort (n <= 256) or bitonic; the k winners
+//               are copied row by row (one warp per row) from x_cat (L2 hits) into `pooled`.
 //
-// Instruction count per graph drops ~5x against the FMA gather version
-// (profiles/r01_stack_fwd_fma.md), which was issue-bound.
+// mma.sync (register fragments) is used on purpose, not tcgen05: the operands are generated
+// in registers from a bitmap for graphs of ~30-500 nodes; tcgen05 needs shared-memory operand
+// tiles of M >= 64/128 rows in descriptor layouts plus a TMEM round trip per tile, which
+// would waste most of each tile on 75-node graphs.  The kernel is bound by issue slots and
+// latency, not by the tensor pipe (profiles/).
 #include "graph_mma.cuh"
 #include "sort_key.cuh"
 
 namespace dgcnn {
 
+constexpr int kRowH = 72;                  // halfs per node row of a feature plane pair
+constexpr int kRowB = kRowH * 2;           // 144 bytes
+constexpr int kRankSortMax = 640;          // rank sort (one pass, no barriers) up to this many nodes
 
 // CTA-wide region: weights, shared by all teams.  Byte offsets, 16-byte aligned.
 struct SharedLayout { int w2p, w3p, w1t, misc, total; };
@@ -33,30 +45,34 @@ struct SharedLayout { int w2p, w3p, w1t, misc, total; };
 __host__ __device__ inline SharedLayout shared_layout(int f) {
     SharedLayout L;
     int o = 0;
-    L.w2p = o; o += 2 * kHid * kWPad * 2;
+    L.w2p = o; o += 2 * kHid * kWPad * 2;                // [plane][cout][kWPad] fp16
     L.w3p = o; o += 2 * kHid * kWPad * 2;
-    L.w1t = o; o += al16(f * kHid * 4);
+    L.w1t = o; o += al16(f * kHid * 4);                  // [F][32] fp32
     L.misc = o; o += 4 * kHid * 4;                       // w4, b1, b2, b3
     L.total = o;
     return L;
 }
 
+__host__ __device__ inline int frag_words(int np) {     // fragment-major adjacency of one graph
+    const int t = np >> 4;
+    return t * ((t + 3) >> 2) * 32;
+}
+
 // Per-graph region, sized by the graph's own padded node count np (multiple of 16).
 struct TeamLayout {
-    int PA, PB, vpl, bm, xs, cs, rs, rp, total;
-    int S;      // plane row stride in halfs: np + 8
+    int PA, PB, vpl, fbm, xs, cs, rs, rp, total;
+    int S;      // row stride (halfs) of the single-column planes (vpl, xs): np + 8
 };
 
 __host__ __device__ inline TeamLayout team_layout(int f, int np) {
     TeamLayout L;
     L.S = np + 8;
-    const int wpr = (np + 31) >> 5;
     int o = 0;
-    L.PA = o; o += 2 * kHid * L.S * 2;                   // hi and lo planes [32][S] fp16
-    L.PB = o; o += 2 * kHid * L.S * 2;
+    L.PA = o; o += np * kRowB;
+    L.PB = o; o += np * kRowB;
     L.vpl = o; o += al16(2 * L.S * 2);                   // layer-4 input: hi and lo [S]
-    L.bm = o; o += al16(np * wpr * 4);
-    L.xs = o; o += (f <= kSmallF) ? al16(f * np * 4) : 0;
+    L.fbm = o; o += frag_words(np) * 4;
+    L.xs = o; o += (f <= kSmallF) ? al16(2 * f * L.S * 2) : 0;   // layer-1 input planes [2][F][S]
     L.cs = o; o += al16(np * 4);
     L.rs = o; o += al16(np * 4);
     L.rp = o; o += al16((np + 1) * 4);
@@ -78,230 +94,410 @@ __host__ __device__ inline int quads_needed(int f, int n) {
     return q;
 }
 
-// One 32-wide layer on the tensor cores for every 16-row tile owned by this warp.
-//   in_pl   hi/lo planes [32][S] of c_j * x_{l-1}
-//   PROJECT y = tanh((r_i agg) @ W^T + b) with W's hi/lo planes wp, else y = tanh(r_i agg + b)
-//   out_pl  (optional) hi/lo planes of c_i * y for the next layer
-//   EMIT_V  also v = c_i * (y . w4) as hi/lo fp16 into vpl (layer 4's input)
-template <bool PROJECT, bool EMIT_V>
-__device__ __forceinline__ void mma_layer(const __half* __restrict__ in_pl, const __half* __restrict__ wp,
-                                          const float* __restrict__ bias, __half* __restrict__ out_pl,
-                                          __half* __restrict__ vpl, const float* __restrict__ w4s,
-                                          const uint32_t* __restrict__ bm, int wpr, int n, int S, bool dup,
-                                          const int* __restrict__ rp, const int32_t* __restrict__ col_g,
-                                          int base, const float* __restrict__ cs,
-                                          const float* __restrict__ rs, float* __restrict__ xo,
-                                          int64_t ldc, const Team& tm) {
-    const int lane = tm.lane, warp = tm.warp, nwarps = tm.nwarps;
-    const int g = lane >> 2, t = lane & 3;
-    const int tiles = (n + 15) >> 4;
-    const uint32_t* in32[2] = {reinterpret_cast<const uint32_t*>(in_pl),
-                               reinterpret_cast<const uint32_t*>(in_pl + kHid * S)};
-    for (int mt = warp; mt < tiles; mt += nwarps) {
-        const int row0 = mt * 16 + g, row1 = row0 + 8;
-        float acc[4][4];
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                          uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+
+// tanh for the hidden layers: (1 - t) / (1 + t), t = 2^(-2 log2(e) |v|); two MUFU ops, no
+// branch.  Absolute error <= ~1.5e-7 (ex2.approx is 2^-22 relative), NaN propagates.
+// The sort key (layer 4) uses tanhf.
+__device__ __forceinline__ float tanh_hidden(float v) {
+    float t, r;
+    const float a = fabsf(v) * -2.885390081777927f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+    return copysignf((1.0f - t) * r, v);
+}
+
+// A-fragment registers of block q (0..3) of a fragment-major adjacency word
+__device__ __forceinline__ void adj_regs(uint32_t w, int q, uint32_t (&a)[4]) {
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        if (!dup) {
-            for (int kt = 0; kt < tiles; ++kt) {
-                uint32_t a[4];
-                if (!adj_fragment(bm, wpr, row0, kt, t, a)) continue;       // empty 16x16 block
+    for (int i = 0; i < 4; ++i)
+        a[i] = __funnelshift_l(w, w, (14 - (4 * q + i)) & 31) & 0x40004000u;
+}
+
+// packed hi / lo halves of (x0, x1), x0 in the low half
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Optional per-graph timeline (debug hook dgcnn_stack_fwd_set_trace): clock64 at phase ends.
+#define KS_TRACE(slot) do { if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ int64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (int64_t)t;
+}
+
+struct GraphCtx {
+    int n, np, T, G, S, base;
+    bool dup;
+    const uint32_t* fbm;            // shared: fragment-major adjacency
+    const int* rp;                  // shared: local row pointers (multigraphs only)
+    const int32_t* col_g;           // global: CSR columns of this graph (multigraphs only)
+    const float* cs;                // shared: c_j (0 on padding)
+    const float* rs;                // shared: 0.5 * r_i (0 on padding); 0.5 undoes A = {0, 2}
+};
+
+// mma.sync without `volatile`: a pure function of its operands, so that ptxas may interleave
+// the MMAs of one block with the ldmatrix of the next (the loops below are latency-bound).
+__device__ __forceinline__ void mma_fp16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// one 16x16 adjacency block (q-th of its word) times the 16x32 hi and lo feature blocks
+__device__ __forceinline__ void block32(uint32_t w, int q, uint32_t addr, float (&acc)[4][4]) {
+    uint32_t a[4];
 #pragma unroll
-                for (int pl = 0; pl < 2; ++pl) {
+    for (int i = 0; i < 4; ++i)
+        a[i] = __funnelshift_l(w, w, (14 - (4 * q + i)) & 31) & 0x40004000u;
+    uint32_t b[4][4];
+    ldsm_x4_t(addr, b[0][0], b[0][1], b[0][2], b[0][3]);              // hi, channels 0..15
+    ldsm_x4_t(addr + 32, b[1][0], b[1][1], b[1][2], b[1][3]);         // hi, channels 16..31
+    ldsm_x4_t(addr + 64, b[2][0], b[2][1], b[2][2], b[2][3]);         // lo, channels 0..15
+    ldsm_x4_t(addr + 96, b[3][0], b[3][1], b[3][2], b[3][3]);         // lo, channels 16..31
+    mma_fp16(acc[0], a, b[0][0], b[0][1]);
+    mma_fp16(acc[1], a, b[0][2], b[0][3]);
+    mma_fp16(acc[2], a, b[1][0], b[1][1]);
+    mma_fp16(acc[3], a, b[1][2], b[1][3]);
+    mma_fp16(acc[0], a, b[2][0], b[2][1]);
+    mma_fp16(acc[1], a, b[2][2], b[2][3]);
+    mma_fp16(acc[2], a, b[3][0], b[3][1]);
+    mma_fp16(acc[3], a, b[3][2], b[3][3]);
+}
+
+// Sum over N(i) U {i} of the 32-wide rows of a plane pair, for the 16-row tile mt of this
+// warp: acc[nt][..] in the m16n8 C layout, value = 2 * sum (both paths).
+// Full groups of four blocks run branch-free (one big basic block: loads and MMAs overlap);
+// a group whose four blocks are all empty is skipped, which is what sparse graphs need.
+__device__ __forceinline__ void aggregate32(const GraphCtx& c, const __half* __restrict__ in_pl, int mt,
+                                            int lane, float (&acc)[4][4]) {
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        const int idx = ((nt * 8 + g) * S + kt * 16 + 2 * t) >> 1;
-                        mma_f16(acc[nt], a, in32[pl][idx], in32[pl][idx + 4]);
-                    }
+    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    if (!c.dup) {
+        const uint32_t lane_off = (((lane & 7) + ((lane >> 3) & 1) * 8) * kRowH + (lane >> 4) * 8) * 2;
+        uint32_t addr = smem_u32(in_pl) + lane_off;
+        const uint32_t* fb = c.fbm + mt * c.G * 32 + lane;
+        uint32_t w = fb[0];
+        for (int grp = 0; grp < c.G; ++grp, addr += 64 * kRowB) {
+            const uint32_t wn = grp + 1 < c.G ? fb[(grp + 1) * 32] : 0u;
+            const int nb = c.T - grp * 4;
+            if (__any_sync(DGCNN_FULL_MASK, w != 0u)) {
+                if (nb >= 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) block32(w, q, addr + q * 16 * kRowB, acc);
+                } else {
+#pragma unroll 1
+                    for (int q = 0; q < nb; ++q) block32(w, q, addr + q * 16 * kRowB, acc);
                 }
             }
-        } else {
-            // multigraph: duplicates have no bitmap encoding (PyG counts them): walk the CSR
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int row = half ? row1 : row0;
-                if (row >= n) continue;
-                for (int e = rp[row] - 1; e < rp[row + 1]; ++e) {
-                    const int j = e < rp[row] ? row : col_g[e] - base;       // first the self loop
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int idx = (nt * 8 + 2 * t + q) * S + j;
-                            acc[nt][2 * half + q] += __half2float(in_pl[idx]) +
-                                                     __half2float(in_pl[kHid * S + idx]);
-                        }
-                }
-            }
+            w = wn;
         }
-        const float r0 = rs[row0], r1 = rs[row1];                           // 0 on padding rows
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            acc[nt][0] *= r0; acc[nt][1] *= r0; acc[nt][2] *= r1; acc[nt][3] *= r1;
-        }
-        float y[4][4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const float bx = bias[nt * 8 + 2 * t], by = bias[nt * 8 + 2 * t + 1];
-            y[nt][0] = bx; y[nt][1] = by; y[nt][2] = bx; y[nt][3] = by;
-        }
-        if (PROJECT) {
-            const uint32_t* wh = reinterpret_cast<const uint32_t*>(wp);
-            const uint32_t* wl = reinterpret_cast<const uint32_t*>(wp + kHid * kWPad);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                uint32_t ah[4], al[4];
-                split2(acc[2 * kk][0], acc[2 * kk][1], ah[0], al[0]);
-                split2(acc[2 * kk][2], acc[2 * kk][3], ah[1], al[1]);
-                split2(acc[2 * kk + 1][0], acc[2 * kk + 1][1], ah[2], al[2]);
-                split2(acc[2 * kk + 1][2], acc[2 * kk + 1][3], ah[3], al[3]);
+    } else {
+        // multigraph: duplicates have no bitmap encoding (PyG counts them): walk the CSR
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int row = mt * 16 + g + 8 * half;
+            if (row >= c.n) continue;
+            for (int e = c.rp[row] - 1; e < c.rp[row + 1]; ++e) {
+                const int j = e < c.rp[row] ? row : c.col_g[e] - c.base;  // first the self loop
+                const __half2* r2 = reinterpret_cast<const __half2*>(in_pl + j * kRowH);
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
-                    const int widx = ((nt * 8 + g) * kWPad + kk * 16 + 2 * t) >> 1;
-                    const uint32_t h0 = wh[widx], h1 = wh[widx + 4];
-                    const uint32_t l0 = wl[widx], l1 = wl[widx + 4];
-                    mma_f16(y[nt], ah, h0, h1);
-                    mma_f16(y[nt], al, h0, h1);
-                    mma_f16(y[nt], ah, l0, l1);
+                    const float2 h = __half22float2(r2[nt * 4 + t]);
+                    const float2 l = __half22float2(r2[16 + nt * 4 + t]);
+                    if (half == 0) { acc[nt][0] += 2.f * (h.x + l.x); acc[nt][1] += 2.f * (h.y + l.y); }
+                    else           { acc[nt][2] += 2.f * (h.x + l.x); acc[nt][3] += 2.f * (h.y + l.y); }
                 }
-            }
-        } else {
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                y[nt][0] += acc[nt][0]; y[nt][1] += acc[nt][1];
-                y[nt][2] += acc[nt][2]; y[nt][3] += acc[nt][3];
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            y[nt][0] = tanhf(y[nt][0]); y[nt][1] = tanhf(y[nt][1]);
-            y[nt][2] = tanhf(y[nt][2]); y[nt][3] = tanhf(y[nt][3]);
-        }
-        // x_l to HBM (its slice of x_cat)
-        if (row0 < n) {
-            float* o = xo + (int64_t)row0 * ldc + 2 * t;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) { o[nt * 8] = y[nt][0]; o[nt * 8 + 1] = y[nt][1]; }
-        }
-        if (row1 < n) {
-            float* o = xo + (int64_t)row1 * ldc + 2 * t;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) { o[nt * 8] = y[nt][2]; o[nt * 8 + 1] = y[nt][3]; }
-        }
-        const float c0 = cs[row0], c1 = cs[row1];                           // 0 on padding rows
-        if (out_pl) {
-            __half* oh = out_pl;
-            __half* ol = out_pl + kHid * S;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int ch = nt * 8 + 2 * t + q;
-                    store_split(oh, ol, ch * S + row0, c0 * y[nt][q]);
-                    store_split(oh, ol, ch * S + row1, c1 * y[nt][2 + q]);
-                }
-        }
-        if (EMIT_V) {
-            float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const float wa = w4s[nt * 8 + 2 * t], wb = w4s[nt * 8 + 2 * t + 1];
-                p0 = fmaf(y[nt][0], wa, fmaf(y[nt][1], wb, p0));
-                p1 = fmaf(y[nt][2], wa, fmaf(y[nt][3], wb, p1));
-            }
-            p0 += __shfl_xor_sync(DGCNN_FULL_MASK, p0, 1);
-            p0 += __shfl_xor_sync(DGCNN_FULL_MASK, p0, 2);
-            p1 += __shfl_xor_sync(DGCNN_FULL_MASK, p1, 1);
-            p1 += __shfl_xor_sync(DGCNN_FULL_MASK, p1, 2);
-            if (t == 0) {
-                store_split(vpl, vpl + S, row0, c0 * p0);
-                store_split(vpl, vpl + S, row1, c1 * p1);
             }
         }
     }
 }
 
+__device__ __forceinline__ void block8(uint32_t w, int q, const uint32_t* __restrict__ hi32,
+                                       const uint32_t* __restrict__ lo32, bool live, float (&acc)[4]) {
+    uint32_t a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        a[i] = __funnelshift_l(w, w, (14 - (4 * q + i)) & 31) & 0x40004000u;
+    const uint32_t h0 = live ? hi32[q * 8] : 0u, h1 = live ? hi32[q * 8 + 4] : 0u;
+    const uint32_t l0 = live ? lo32[q * 8] : 0u, l1 = live ? lo32[q * 8 + 4] : 0u;
+    mma_fp16(acc, a, h0, h1);
+    mma_fp16(acc, a, l0, l1);
+}
+
+// Same for single-column-per-feature planes [F' <= 8][S] (hi at pl, lo at pl + lo_off):
+// feature f of the tile's rows lands in column f of one 8-wide n-tile.
+__device__ __forceinline__ void aggregate8(const GraphCtx& c, const __half* __restrict__ pl, int lo_off,
+                                           int nf, int mt, int lane, float (&acc)[4]) {
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    const int g = lane >> 2, t = lane & 3;
+    if (!c.dup) {
+        const uint32_t* hi32 = reinterpret_cast<const uint32_t*>(pl + g * c.S) + t;
+        const uint32_t* lo32 = reinterpret_cast<const uint32_t*>(pl + lo_off + g * c.S) + t;
+        const bool live = g < nf;
+        const uint32_t* fb = c.fbm + mt * c.G * 32 + lane;
+        uint32_t w = fb[0];
+        float acc2[4] = {0.f, 0.f, 0.f, 0.f};               // second chain: halves the MMA dependency depth
+        for (int grp = 0; grp < c.G; ++grp, hi32 += 32, lo32 += 32) {
+            const uint32_t wn = grp + 1 < c.G ? fb[(grp + 1) * 32] : 0u;
+            const int nb = c.T - grp * 4;
+            if (__any_sync(DGCNN_FULL_MASK, w != 0u)) {
+                if (nb >= 4) {
+                    block8(w, 0, hi32, lo32, live, acc);
+                    block8(w, 1, hi32, lo32, live, acc2);
+                    block8(w, 2, hi32, lo32, live, acc);
+                    block8(w, 3, hi32, lo32, live, acc2);
+                } else {
+#pragma unroll 1
+                    for (int q = 0; q < nb; ++q) block8(w, q, hi32, lo32, live, acc);
+                }
+            }
+            w = wn;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += acc2[i];
+    } else {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int row = mt * 16 + g + 8 * half;
+            if (row >= c.n) continue;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int f = 2 * t + u;
+                if (f >= nf) continue;
+                float s = 0.f;
+                for (int e = c.rp[row] - 1; e < c.rp[row + 1]; ++e) {
+                    const int j = e < c.rp[row] ? row : c.col_g[e] - c.base;
+                    s += __half2float(pl[f * c.S + j]) + __half2float(pl[lo_off + f * c.S + j]);
+                }
+                acc[2 * half + u] = 2.f * s;
+            }
+        }
+    }
+}
+
+// y += (acc) @ W^T on the tensor cores; acc already scaled by r_i.  wp: [plane][32][kWPad].
+__device__ __forceinline__ void project32(const float (&acc)[4][4], const __half* __restrict__ wp,
+                                          int lane, float (&y)[4][4]) {
+    const int j = lane >> 3;
+    const uint32_t wbase = smem_u32(wp) +
+        (uint32_t)(((j >> 1) * kHid * kWPad + (lane & 7) * kWPad + (j & 1) * 8) * 2);
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        uint32_t ah[4], al[4];
+        split_pair(acc[2 * kk][0], acc[2 * kk][1], ah[0], al[0]);
+        split_pair(acc[2 * kk][2], acc[2 * kk][3], ah[1], al[1]);
+        split_pair(acc[2 * kk + 1][0], acc[2 * kk + 1][1], ah[2], al[2]);
+        split_pair(acc[2 * kk + 1][2], acc[2 * kk + 1][3], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t h0, h1, l0, l1;
+            ldsm_x4(wbase + (uint32_t)((nt * 8 * kWPad + kk * 16) * 2), h0, h1, l0, l1);
+            mma_fp16(y[nt], ah, h0, h1);
+            mma_fp16(y[nt], al, h0, h1);
+            mma_fp16(y[nt], ah, l0, l1);
+        }
+    }
+}
+
+// tanh, x_l slice of x_cat to HBM, c_i * x_l as hi/lo planes for the next layer (out_pl),
+// and v = c_i (x_l . w4) for layer 4 (vpl).  y holds the pre-activations (C layout).
+__device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][4], int mt, int lane,
+                                               float* __restrict__ xo, int64_t ldc, bool vec2,
+                                               __half* __restrict__ out_pl, __half* __restrict__ vpl,
+                                               const float* __restrict__ w4s) {
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = mt * 16 + g, row1 = row0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        y[nt][0] = tanh_hidden(y[nt][0]); y[nt][1] = tanh_hidden(y[nt][1]);
+        y[nt][2] = tanh_hidden(y[nt][2]); y[nt][3] = tanh_hidden(y[nt][3]);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int row = half ? row1 : row0;
+        if (row < c.n) {
+            float* o = xo + (int64_t)row * ldc + 2 * t;
+            if (vec2) {
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    *reinterpret_cast<float2*>(o + nt * 8) = make_float2(y[nt][2 * half], y[nt][2 * half + 1]);
+            } else {
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) { o[nt * 8] = y[nt][2 * half]; o[nt * 8 + 1] = y[nt][2 * half + 1]; }
+            }
+        }
+    }
+    const float c0 = c.cs[row0], c1 = c.cs[row1];                         // 0 on padding rows
+    if (out_pl) {
+        uint32_t* o0 = reinterpret_cast<uint32_t*>(out_pl + row0 * kRowH) + t;
+        uint32_t* o1 = reinterpret_cast<uint32_t*>(out_pl + row1 * kRowH) + t;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t hi, lo;
+            split_pair(c0 * y[nt][0], c0 * y[nt][1], hi, lo);
+            o0[nt * 4] = hi; o0[16 + nt * 4] = lo;
+            split_pair(c1 * y[nt][2], c1 * y[nt][3], hi, lo);
+            o1[nt * 4] = hi; o1[16 + nt * 4] = lo;
+        }
+    }
+    if (vpl) {
+        float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float2 w = *reinterpret_cast<const float2*>(w4s + nt * 8 + 2 * t);
+            p0 = fmaf(y[nt][0], w.x, fmaf(y[nt][1], w.y, p0));
+            p1 = fmaf(y[nt][2], w.x, fmaf(y[nt][3], w.y, p1));
+        }
+        p0 += __shfl_xor_sync(DGCNN_FULL_MASK, p0, 1);
+        p0 += __shfl_xor_sync(DGCNN_FULL_MASK, p0, 2);
+        p1 += __shfl_xor_sync(DGCNN_FULL_MASK, p1, 1);
+        p1 += __shfl_xor_sync(DGCNN_FULL_MASK, p1, 2);
+        if (t == 0) {
+            store_split(vpl, vpl + c.S, row0, c0 * p0);
+            store_split(vpl, vpl + c.S, row1, c1 * p1);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_bias(const float* __restrict__ bias, int t, float (&y)[4][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const float2 b = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * t);
+        y[nt][0] = b.x; y[nt][1] = b.y; y[nt][2] = b.x; y[nt][3] = b.y;
+    }
+}
+
+// One entry of a CTA's pass: a graph, the warps that work on it, its slice of shared memory.
+constexpr int kMaxTeams = 8;
+struct PlanEntry { int gi, base, n, fgoff, warp0, nwarps, smem_off, pad; };
+
+// rough latency (cycles) of one layer of a T-tile graph on w warps: rounds x (blocks + epilogue)
+__device__ __forceinline__ int layer_latency(int T, int w) { return ((T + w - 1) / w) * (T * 64 + 1200); }
+
 // model.py:28-35 for ONE graph, executed by one team
-__device__ __forceinline__ void process_graph(const StackFwdParams& p, const Team& tm, int gi,
+__device__ __forceinline__ void process_graph(const StackFwdParams& p, const Team& tm, const PlanEntry& e,
                                               const unsigned char* shraw) {
     const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
     const int nthreads = tm.nthreads, nwarps = tm.nwarps;
     const int f = p.f;
+    const bool small_f = f <= kSmallF;
     const SharedLayout SL = shared_layout(f);
     const __half* w2p = reinterpret_cast<const __half*>(shraw + SL.w2p);
     const __half* w3p = reinterpret_cast<const __half*>(shraw + SL.w3p);
     const float* w1t = reinterpret_cast<const float*>(shraw + SL.w1t);
     const float* w4s = reinterpret_cast<const float*>(shraw + SL.misc);
-    const float* b1s = w4s + kHid;  const float* b2s = b1s + kHid;  const float* b3s = b2s + kHid;
+    const float* b1s = w4s + kHid;                       // b1, b2, b3 contiguous
     const float b4 = p.b4 ? p.b4[0] : 0.f;
 
-    const int base = p.gptr[gi];
-    const int n = p.gptr[gi + 1] - base;
+    const int gi = e.gi, base = e.base, n = e.n;
     const int keep = min(n, p.k);
-    float* pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
-    int32_t* perm_g = p.perm + (int64_t)gi * p.k;
-    for (int idx = keep * kCat + tid; idx < p.k * kCat; idx += nthreads) pooled_g[idx] = 0.f;
-    for (int r = keep + tid; r < p.k; r += nthreads) perm_g[r] = -1;
+    float* __restrict__ pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
+    int32_t* __restrict__ perm_g = p.perm + (int64_t)gi * p.k;
     if (n == 0) return;
+    if (p.trace && tm.tid == 0) {
+        uint32_t smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[(int64_t)gi * 16 + 15] = ((int64_t)smid << 32) | (uint32_t)(tm.nthreads | (n << 12));
+        p.trace[(int64_t)gi * 16 + 9] = global_ns();
+    }
+    KS_TRACE(0);
 
-    const int np = (n + 15) & ~15;                   // rows/columns padded to the MMA tile
-    const int wpr = (np + 31) >> 5;
+    GraphCtx c;
+    c.n = n; c.np = (n + 15) & ~15; c.T = c.np >> 4; c.G = (c.T + 3) >> 2; c.base = base;
+    const int np = c.np;
     const TeamLayout L = team_layout(f, np);
+    c.S = L.S;
     const int S = L.S;
     unsigned char* smraw = tm.smem;
     __half* PA = reinterpret_cast<__half*>(smraw + L.PA);
     __half* PB = reinterpret_cast<__half*>(smraw + L.PB);
     __half* vpl = reinterpret_cast<__half*>(smraw + L.vpl);
-    uint32_t* bm = reinterpret_cast<uint32_t*>(smraw + L.bm);
-    float* xs = reinterpret_cast<float*>(smraw + L.xs);
+    uint32_t* fbm = reinterpret_cast<uint32_t*>(smraw + L.fbm);
+    __half* xs = reinterpret_cast<__half*>(smraw + L.xs);
     float* cs = reinterpret_cast<float*>(smraw + L.cs);
     float* rs = reinterpret_cast<float*>(smraw + L.rs);
     float* key = rs;                                    // x_4 overwrites r_i in place
     int* order = reinterpret_cast<int*>(cs);            // c_j is dead after layer 3
     int* rp = reinterpret_cast<int*>(smraw + L.rp);
+    float* stage = reinterpret_cast<float*>(PB);        // layer-1 inputs c_j x_j, fp32 [n][f] (F <= 8)
+    float* wmax = reinterpret_cast<float*>(vpl);        // per-warp max |c_j x_j|
+    c.fbm = fbm; c.cs = cs; c.rs = rs; c.rp = rp;
 
-    const bool dup = (p.gflags[gi] & 1) != 0;        // multigraph: walk the CSR instead
-    const int e0 = dup ? p.rowptr[base] : 0;
-    const int32_t* col_g = p.col + e0;
     float* xc = p.xcat + (int64_t)base * p.ldc;
+    const bool vec2 = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.xcat) & 7) == 0);
+    const bool pad4 = ((p.ldc & 3) == 0) && p.ldc >= 100 && ((reinterpret_cast<uintptr_t>(p.xcat) & 15) == 0);
+    const int g = lane >> 2, t = lane & 3;
 
-    // ---- phase 0: adjacency bitmap (from K0b), per-node coefficients, layer-1 input ------
-    load_bitmap(p.bitmap + p.bmoff[gi], bm, np * wpr, tid, nthreads);
+    // ---- phase 0, one DRAM round trip: adjacency fragments (K0b), coefficients, inputs ----
+    c.dup = (p.gflags[gi] & 1) != 0;                 // multigraph: walk the CSR instead
+    load_bitmap(p.fragmap + e.fgoff, fbm, frag_words(np), tid, nthreads);
     for (int j = tid; j < np; j += nthreads) {
         const float d = j < n ? p.dis[base + j] : 0.f;
         cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
-        rs[j] = j < n ? row_coef(d, p.norm) : 0.f;
+        rs[j] = j < n ? 0.5f * row_coef(d, p.norm) : 0.f;
     }
-    if (dup)
-        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
-    tm.sync();
-
-    // ---- layer 1: F -> 32 (FMA pipe: arbitrary input range, tiny work) -----------------
-    if (f <= kSmallF) {
+    if (small_f) {
+        float m = 0.f;
         for (int idx = tid; idx < n * f; idx += nthreads) {
-            int j = idx / f, k = idx - j * f;
-            xs[k * np + j] = cs[j] * p.x[(int64_t)(base + j) * p.ldx + k];
+            const int j = idx / f, k = idx - j * f;
+            const float v = col_coef(p.dis[base + j], p.norm) * p.x[(int64_t)(base + j) * p.ldx + k];
+            stage[idx] = v;
+            m = fmaxf(m, fabsf(v));                  // NaN-ignoring: a NaN flows through hi/lo instead
         }
-        // padding columns of the output planes must be finite zeros (0 * NaN = NaN)
-        for (int idx = tid; idx < (np - n) * kHid; idx += nthreads) {
-            const int c = idx / (np - n), j = n + idx - c * (np - n);
-            PA[c * S + j] = __float2half_rn(0.f);
-            PA[kHid * S + c * S + j] = __float2half_rn(0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(DGCNN_FULL_MASK, m, o));
+        if (lane == 0) wmax[warp] = m;
+    }
+    int e0 = 0;
+    if (c.dup) {
+        e0 = p.rowptr[base];
+        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
+    }
+    c.col_g = p.col + e0;
+    tm.sync();
+    KS_TRACE(1);
+
+    float pow2 = 1.f;
+    if (small_f) {
+        // layer-1 inputs scaled by a power of two just below their maximum, so that the
+        // fp16 hi/lo split keeps 22 bits relative to the graph's own range: values in (-2, 2)
+        float m = 0.f;
+        for (int w = 0; w < nwarps; ++w) m = fmaxf(m, wmax[w]);
+        uint32_t eb = __float_as_uint(m) & 0x7F800000u;
+        if (eb == 0u || eb >= 0x7E800000u) {
+            if (eb >= 0x7E800000u && tid == 0 && p.status) atomicOr(p.status, DGCNN_GRAPH_RANGE);
+            eb = 0x3F800000u;
         }
-        tm.sync();
-        for (int i = warp; i < n; i += nwarps) {
-            const float r = rs[i];
-            float acc = b1s[lane];
-            for (int k = 0; k < f; ++k) {
-                const float a = r * scalar_row_sum(xs + k * np, bm + i * wpr, wpr, dup, rp, col_g, base, i);
-                acc = fmaf(a, w1t[k * kHid + lane], acc);
-            }
-            const float y = tanhf(acc);
-            xc[(int64_t)i * p.ldc + lane] = y;
-            store_split(PA, PA + kHid * S, lane * S + i, cs[i] * y);
+        pow2 = __uint_as_float(eb);
+        const float inv = __uint_as_float(0x7F000000u - eb);
+        for (int idx = tid; idx < f * S; idx += nthreads) {
+            const int k = idx / S, j = idx - k * S;
+            store_split(xs, xs + f * S, idx, j < n ? stage[j * f + k] * inv : 0.f);
         }
     } else {
-        // project first: c_j * (x_j W1^T) as planes in PB, then aggregate on the tensor cores
+        // F > 8: project first (FMA), c_j (x_j W1^T) as planes in PB
         for (int j = warp; j < np; j += nwarps) {
             float acc = 0.f;
             if (j < n) {
@@ -310,83 +506,117 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
                 acc *= cs[j];
                 if (fabsf(acc) > 6.0e4f && p.status) atomicOr(p.status, DGCNN_GRAPH_RANGE);
             }
-            store_split(PB, PB + kHid * S, lane * S + j, acc);
+            store_split(PB + j * kRowH, PB + j * kRowH + kHid, lane, acc);
+        }
+    }
+    tm.sync();
+    KS_TRACE(2);
+
+    // ---- layers 1..3: aggregate on the tensor cores, project, tanh ------------------------
+#pragma unroll 1
+    for (int layer = 0; layer < 3; ++layer) {
+        const __half* in_pl = layer == 1 ? PA : PB;
+        __half* out_pl = layer == 0 ? PA : (layer == 1 ? PB : nullptr);
+        const __half* wp = layer == 1 ? w2p : w3p;
+        const float* bias = b1s + layer * kHid;
+        float* xo = xc + layer * kHid;
+#pragma unroll 1
+        for (int mt = warp; mt < c.T; mt += nwarps) {
+            float y[4][4];
+            load_bias(bias, t, y);
+            if (layer == 0 && small_f) {
+                float a4[4];
+                aggregate8(c, xs, f * S, f, mt, lane, a4);
+                const float r0 = rs[mt * 16 + g] * pow2, r1 = rs[mt * 16 + g + 8] * pow2;
+                a4[0] *= r0; a4[1] *= r0; a4[2] *= r1; a4[3] *= r1;
+                for (int k = 0; k < f; ++k) {
+                    const int src = (lane & ~3) | (k >> 1);
+                    const float v0 = __shfl_sync(DGCNN_FULL_MASK, (k & 1) ? a4[1] : a4[0], src);
+                    const float v1 = __shfl_sync(DGCNN_FULL_MASK, (k & 1) ? a4[3] : a4[2], src);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const float2 w = *reinterpret_cast<const float2*>(w1t + k * kHid + nt * 8 + 2 * t);
+                        y[nt][0] = fmaf(v0, w.x, y[nt][0]); y[nt][1] = fmaf(v0, w.y, y[nt][1]);
+                        y[nt][2] = fmaf(v1, w.x, y[nt][2]); y[nt][3] = fmaf(v1, w.y, y[nt][3]);
+                    }
+                }
+            } else {
+                float acc[4][4];
+                aggregate32(c, in_pl, mt, lane, acc);
+                const float r0 = rs[mt * 16 + g], r1 = rs[mt * 16 + g + 8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    acc[nt][0] *= r0; acc[nt][1] *= r0; acc[nt][2] *= r1; acc[nt][3] *= r1;
+                }
+                if (layer == 0) {
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        y[nt][0] += acc[nt][0]; y[nt][1] += acc[nt][1];
+                        y[nt][2] += acc[nt][2]; y[nt][3] += acc[nt][3];
+                    }
+                } else {
+                    project32(acc, wp, lane, y);
+                }
+            }
+            layer_epilogue(c, y, mt, lane, xo, p.ldc, vec2, out_pl, layer == 2 ? vpl : nullptr, w4s);
         }
         tm.sync();
-        mma_layer<false, false>(PB, nullptr, b1s, PA, nullptr, nullptr, bm, wpr, n, S, dup, rp, col_g,
-                                base, cs, rs, xc, p.ldc, tm);
+        KS_TRACE(3 + layer);
     }
-    tm.sync();
 
-    // ---- layers 2 and 3 on the tensor cores ------------------------------------------
-    mma_layer<true, false>(PA, w2p, b2s, PB, nullptr, nullptr, bm, wpr, n, S, dup, rp, col_g, base, cs,
-                           rs, xc + kHid, p.ldc, tm);
-    tm.sync();
-    mma_layer<true, true>(PB, w3p, b3s, nullptr, vpl, w4s, bm, wpr, n, S, dup, rp, col_g, base, cs, rs,
-                          xc + 2 * kHid, p.ldc, tm);
-    tm.sync();
-
-    // ---- layer 4: 32 -> 1, already projected into v: one 8-wide MMA column ---------------
-    {
-        const int g = lane >> 2, t = lane & 3;
-        const int tiles = np >> 4;
-        const uint32_t* v32[2] = {reinterpret_cast<const uint32_t*>(vpl),
-                                  reinterpret_cast<const uint32_t*>(vpl + S)};
-        for (int mt = warp; mt < tiles; mt += nwarps) {
-            const int row0 = mt * 16 + g, row1 = row0 + 8;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (!dup) {
-                for (int kt = 0; kt < tiles; ++kt) {
-                    uint32_t a[4];
-                    if (!adj_fragment(bm, wpr, row0, kt, t, a)) continue;
+    // ---- layer 4: 32 -> 1, already projected into v: one MMA column -------------------
+    for (int mt = warp; mt < c.T; mt += nwarps) {
+        float a4[4];
+        aggregate8(c, vpl, S, 1, mt, lane, a4);
+        if (t == 0) {                                  // column 0 of the tile lives in t == 0
 #pragma unroll
-                    for (int pl = 0; pl < 2; ++pl) {
-                        const int idx = (kt * 16 + 2 * t) >> 1;
-                        const uint32_t b0 = g == 0 ? v32[pl][idx] : 0u;
-                        const uint32_t b1 = g == 0 ? v32[pl][idx + 4] : 0u;
-                        mma_f16(acc, a, b0, b1);
-                    }
-                }
-            } else if (t == 0) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int row = half ? row1 : row0;
-                    if (row >= n) continue;
-                    float s = 0.f;
-                    for (int e = rp[row] - 1; e < rp[row + 1]; ++e) {
-                        const int j = e < rp[row] ? row : col_g[e] - base;
-                        s += __half2float(vpl[j]) + __half2float(vpl[S + j]);
-                    }
-                    acc[2 * half] = s;
-                }
-            }
-            if (t == 0) {                                  // column 0 of the tile lives in t == 0
-                if (row0 < n) {
-                    const float x4 = tanhf(fmaf(rs[row0], acc[0], b4));
-                    key[row0] = x4;
-                    xc[(int64_t)row0 * p.ldc + 3 * kHid] = x4;
-                }
-                if (row1 < n) {
-                    const float x4 = tanhf(fmaf(rs[row1], acc[2], b4));
-                    key[row1] = x4;
-                    xc[(int64_t)row1 * p.ldc + 3 * kHid] = x4;
+            for (int half = 0; half < 2; ++half) {
+                const int row = mt * 16 + g + 8 * half;
+                if (row < n) {
+                    const float x4 = tanhf(fmaf(rs[row], a4[2 * half], b4));
+                    key[row] = x4;
+                    float* o = xc + (int64_t)row * p.ldc + 3 * kHid;
+                    // padded rows (ldc >= 100, 16-byte aligned): write the pad too, so that no
+                    // 32-byte sector of x_cat is left partially written (a later read of such a
+                    // sector has to be filled from DRAM)
+                    if (pad4) *reinterpret_cast<float4*>(o) = make_float4(x4, 0.f, 0.f, 0.f);
+                    else *o = x4;
                 }
             }
         }
     }
     tm.sync();
+    KS_TRACE(6);
 
     // ---- SortPool: order by x_4 descending, ties by node index -----------------------
     uint64_t* comp = reinterpret_cast<uint64_t*>(PA);
-    if (n <= 256) {
+    if (n <= kRankSortMax) {
         for (int j = tid; j < n; j += nthreads)
             comp[j] = ((uint64_t)descending_key_bits(key[j]) << 32) | (uint32_t)j;
         tm.sync();
-        for (int i = tid; i < n; i += nthreads) {
-            const uint64_t mine = comp[i];
+        // rank = number of smaller composites; `parts` lanes share one element (interleaved j)
+        int parts = 1;
+        while (parts < 32 && n * parts * 2 <= nthreads) parts <<= 1;
+        const int lp = 31 - __clz(parts);
+        for (int it0 = 0; it0 < n * parts; it0 += nthreads) {
+            const int item = it0 + tid;
+            const int i = item >> lp, part = item & (parts - 1);
+            const bool live = i < n;
+            const uint64_t mine = live ? comp[i] : 0ull;
             int rank = 0;
-            for (int j = 0; j < n; ++j) rank += comp[j] < mine;
-            if (rank < keep) order[rank] = i;
+            if (live) {
+                int j = part;
+                for (; j + 7 * parts < n; j += 8 * parts) {          // eight independent loads in flight
+                    uint64_t o[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) o[u] = comp[j + u * parts];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) rank += o[u] < mine;
+                }
+                for (; j < n; j += parts) rank += comp[j] < mine;
+            }
+            for (int o = parts >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(DGCNN_FULL_MASK, rank, o);
+            if (live && part == 0 && rank < keep) order[rank] = i;
         }
     } else {
         const uint32_t pw = next_pow2((uint32_t)n);
@@ -396,102 +626,189 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
         for (int r = tid; r < keep; r += nthreads) order[r] = (int)(uint32_t)(comp[r] & 0xffffffffu);
     }
     tm.sync();
+    KS_TRACE(7);
 
-    // ---- gather the k winners (rows of x_cat this team just wrote: L2 hits) ------------
+    // ---- the k winners, one warp per row (rows of x_cat this team just wrote: L2 hits);
+    //      sixteen rows in flight per warp, loads unconditional (clamped) so they all overlap:
+    //      the copy is pure L2 latency ------------------------------------------------------
     {
-        const int total = keep * kCat;
-        for (int i0 = tid; i0 < total; i0 += nthreads * 8) {
-            float v[8];
+        const float* __restrict__ xsrc = xc;
+        constexpr int R = 16;
+        for (int r0 = warp * R; r0 < keep; r0 += nwarps * R) {
+            float v[R][3], v96;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int idx = i0 + u * nthreads;
-                if (idx < total) {
-                    const int r = idx / kCat, c = idx - r * kCat;
-                    v[u] = xc[(int64_t)order[r] * p.ldc + c];
+            for (int u = 0; u < R; ++u) {
+                const float* src = xsrc + (int64_t)order[min(r0 + u, keep - 1)] * p.ldc;
+                v[u][0] = src[lane]; v[u][1] = src[32 + lane]; v[u][2] = src[64 + lane];
+            }
+            v96 = xsrc[(int64_t)order[min(r0 + (lane & (R - 1)), keep - 1)] * p.ldc + 96];
+            if (p.trace && r0 == 0) {
+                if (tm.tid == 0) p.trace[(int64_t)gi * 16 + 12] = clock64();
+                float sum = v96;
+#pragma unroll
+                for (int u = 0; u < R; ++u) sum += v[u][0] + v[u][1] + v[u][2];
+                if (sum == 1.2345e-30f) p.trace[(int64_t)gi * 16 + 14] = 1;   // consume the loads
+                if (tm.tid == 0) p.trace[(int64_t)gi * 16 + 13] = clock64();
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                if (r0 + u < keep) {
+                    float* dst = pooled_g + (r0 + u) * kCat;
+                    dst[lane] = v[u][0]; dst[32 + lane] = v[u][1]; dst[64 + lane] = v[u][2];
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int idx = i0 + u * nthreads;
-                if (idx < total) pooled_g[idx] = v[u];
-            }
+            if (lane < R && r0 + lane < keep) pooled_g[(r0 + lane) * kCat + 96] = v96;
         }
     }
     for (int r = tid; r < keep; r += nthreads) perm_g[r] = base + order[r];
+    KS_TRACE(8);
+    if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + 10] = global_ns();
 }
 
+// cost of a graph in "16x16 adjacency blocks": T^2 blocks per layer plus a per-row-tile
+// share (projection, epilogue, sort, copy) worth ~19 blocks
+__device__ __forceinline__ int graph_cost(int n) {
+    const int T = (max(n, 1) + 15) >> 4;
+    return T * (T + 19);
+}
+
+// The CTA's graphs.  The batch arrives in descending size (gdesc, written by K0b).  Graphs
+// that alone cost more than an SM's fair share of the batch get an SM to themselves; the rest
+// is dealt to the remaining CTAs boustrophedon-wise (s, 2S-1-s, 2S+s, ...), so that every SM
+// holds one graph of each size class.  Up to kMaxTeams of a CTA's graphs run CONCURRENTLY,
+// each on its own warps (more warps for more tiles), named barrier and slice of shared
+// memory: the per-graph work is a chain of short latency-bound phases, and the only way to
+// fill the SM is to overlap the chains of different graphs.
 __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ int s_item[kQuads];
+    __shared__ PlanEntry s_plan[kMaxTeams];
+    __shared__ int s_count;
+    const int64_t cta_t0 = p.trace ? global_ns() : 0;
     const int f = p.f;
     const SharedLayout SL = shared_layout(f);
-    {   // weights once per CTA: W1 transposed fp32 (layer 1 stays on the FMA pipe), W2/W3 as
-        // hi/lo fp16 planes [cout][cin] = the MMA "col" operand of y = agg @ W^T
-        const int tid = threadIdx.x, nthreads = blockDim.x;
-        __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
-        __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
-        float* w1t = reinterpret_cast<float*>(smraw + SL.w1t);
-        float* w4s = reinterpret_cast<float*>(smraw + SL.misc);
-        for (int idx = tid; idx < f * kHid; idx += nthreads) {
-            int c = idx / f, k = idx - c * f;
-            w1t[k * kHid + c] = p.w1[idx];
-        }
-        for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
-            const int c = idx >> 5, k = idx & 31;
-            store_split(w2p, w2p + kHid * kWPad, c * kWPad + k, p.w2[idx]);
-            store_split(w3p, w3p + kHid * kWPad, c * kWPad + k, p.w3[idx]);
-        }
-        if (tid < kHid) {
-            w4s[tid] = p.w4[tid];
-            w4s[kHid + tid] = p.b1 ? p.b1[tid] : 0.f;
-            w4s[2 * kHid + tid] = p.b2 ? p.b2[tid] : 0.f;
-            w4s[3 * kHid + tid] = p.b3 ? p.b3[tid] : 0.f;
-        }
-        __syncthreads();
-    }
-
-    const int quad = threadIdx.x / kQuadThreads;
-    const int qb = quad_bytes(f);
     unsigned char* team_base = smraw + al16(SL.total);
-    const bool can_split = p.gorder != nullptr;     // descending sizes: a group only ever splits
-    int first = 0, nq = kQuads;                      // my group = quads [first, first + nq)
+    const int budget = kQuads * quad_bytes(f);
+    const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
+    constexpr int kWarps = kCtaThreads / 32;
+    const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);      // {graph, base, n, fgoff}
+    int next = 0;                                    // items of this CTA consumed so far
+    int excl = 0;                                    // graphs with an SM of their own (warp 0 only)
 
-    for (;;) {
-        Team tm;
-        tm.tid = threadIdx.x - first * kQuadThreads;
-        tm.nthreads = nq * kQuadThreads;
-        tm.warp = tm.tid >> 5;
-        tm.nwarps = tm.nthreads >> 5;
-        tm.lane = threadIdx.x & 31;
-        tm.bar = 1 + first;
-        tm.smem = team_base + (size_t)first * qb;
-
-        if (tm.tid == 0) s_item[first] = atomicAdd(p.counter, 1);
-        tm.sync();
-        int q = s_item[first];
-        tm.sync();                                   // everyone has read the slot
-        if (q >= p.num_graphs) break;
-        const int gi = p.gorder ? p.gorder[q] : q;
-        const int n = p.gptr[gi + 1] - p.gptr[gi];
-        if (n > p.nmax) {                            // host promised this cannot happen
-            if (tm.tid == 0 && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_BATCH);
-            continue;
-        }
-        if (can_split) {
-            const int need = quads_needed(f, n);
-            bool refetch = false;
-            while (need < nq) {                      // the lower half keeps the graph,
-                nq >>= 1;                            // the upper half fetches its own
-                if (quad >= first + nq) { first += nq; refetch = true; break; }
+    for (int pass = 0;; ++pass) {
+        if (warp_id == 0) {
+            if (pass == 0 && B > nsm) {
+                // fair share of one SM ~ (B / S) x mean cost; the median stands in for the mean
+                const int nmed = gdesc[B >> 1].z;
+                const int cand = (lane < 8 && lane < B) ? gdesc[lane].z : 0;
+                const int share = (int)(((int64_t)graph_cost(nmed) * B * 5) / (4 * nsm));
+                const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && graph_cost(cand) > share);
+                excl = min(__ffs(~big) - 1, nsm / 2);               // leading run (sizes descend)
             }
-            if (refetch) continue;
-            tm.tid = threadIdx.x - first * kQuadThreads;
-            tm.nthreads = nq * kQuadThreads;
-            tm.warp = tm.tid >> 5;
-            tm.nwarps = tm.nthreads >> 5;
+            excl = __shfl_sync(DGCNN_FULL_MASK, excl, 0);
+            // lane j proposes the CTA's item next + j
+            const int item = next + lane;
+            int pos;
+            if (sm < excl) {
+                pos = item == 0 ? sm : B;
+            } else {
+                const int s2 = sm - excl, n2 = nsm - excl;
+                pos = excl + item * n2 + ((item & 1) ? n2 - 1 - s2 : s2);
+            }
+            const bool valid = lane < kMaxTeams && pos < B;
+            int4 d = make_int4(0, 0, 0, 0);
+            if (valid) d = gdesc[pos];
+            const int n = d.z, np = max(16, (n + 15) & ~15), T = np >> 4;
+            const int need = valid ? team_layout(f, np).total : 0;
+            int incl = need;
+#pragma unroll
+            for (int o = 1; o < kMaxTeams; o <<= 1) {
+                const int u = __shfl_up_sync(DGCNN_FULL_MASK, incl, o);
+                if (lane >= o) incl += u;
+            }
+            // members = the leading items that fit together (the first one always does: host check)
+            const uint32_t fit = __ballot_sync(DGCNN_FULL_MASK, valid && (incl <= budget || lane == 0));
+            const int count = __ffs(~fit) - 1;
+            const bool member = lane < count;
+            // warps: one each, the spare ones to whoever has the longest layer
+            int w = member ? 1 : 0;
+            for (int spare = kWarps - count; spare > 0 && count > 0; --spare) {
+                const uint32_t lat = (member && w < T) ? (uint32_t)layer_latency(T, w) : 0u;
+                const uint32_t best = __reduce_max_sync(DGCNN_FULL_MASK, (lat << 5) | (uint32_t)(31 - lane));
+                if ((best >> 5) == 0u) break;
+                if (lane == 31 - (int)(best & 31u)) ++w;
+            }
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < kMaxTeams; o <<= 1) {
+                const int u = __shfl_up_sync(DGCNN_FULL_MASK, winc, o);
+                if (lane >= o) winc += u;
+            }
+            if (member) {
+                PlanEntry e;
+                e.gi = d.x; e.base = d.y; e.n = n; e.fgoff = d.w;
+                e.warp0 = winc - w; e.nwarps = w; e.smem_off = incl - need; e.pad = 0;
+                s_plan[lane] = e;
+            }
+            if (lane == 0) s_count = count;
+        } else if (pass == 0) {
+            // meanwhile the other warps stage the weights: W1 transposed fp32 (F -> 32 stays on
+            // the FMA pipe), W2/W3 as hi/lo fp16 planes [cout][cin] = the MMA "col" operand
+            const int tid = threadIdx.x - 32, nthreads = kCtaThreads - 32;
+            __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
+            __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
+            float* w1t = reinterpret_cast<float*>(smraw + SL.w1t);
+            float* w4s = reinterpret_cast<float*>(smraw + SL.misc);
+            for (int idx = tid; idx < f * kHid; idx += nthreads) {
+                int c = idx / f, k = idx - c * f;
+                w1t[k * kHid + c] = p.w1[idx];
+            }
+            for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
+                const int c = idx >> 5, k = idx & 31;
+                store_split(w2p, w2p + kHid * kWPad, c * kWPad + k, p.w2[idx]);
+                store_split(w3p, w3p + kHid * kWPad, c * kWPad + k, p.w3[idx]);
+            }
+            if (tid < kHid) {
+                w4s[tid] = p.w4[tid];
+                w4s[kHid + tid] = p.b1 ? p.b1[tid] : 0.f;
+                w4s[2 * kHid + tid] = p.b2 ? p.b2[tid] : 0.f;
+                w4s[3 * kHid + tid] = p.b3 ? p.b3[tid] : 0.f;
+            }
         }
-        process_graph(p, tm, gi, smraw);
-        tm.sync();                                   // the slice is reused by the next graph
+        __syncthreads();                             // the plan (and, first time, the weights)
+        const int count = s_count;
+        if (count == 0) break;
+        // rows of `pooled` past each graph's last node: zeros (PyG's fill trick), perm -1.
+        // Done by the whole CTA: a one-warp team would spend longer on this than on its graph.
+        for (int j = 0; j < count; ++j) {
+            const int gi = s_plan[j].gi, keep = min(s_plan[j].n, p.k);
+            float* pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
+            int32_t* perm_g = p.perm + (int64_t)gi * p.k;
+            for (int idx = keep * kCat + threadIdx.x; idx < p.k * kCat; idx += kCtaThreads) pooled_g[idx] = 0.f;
+            for (int r = keep + threadIdx.x; r < p.k; r += kCtaThreads) perm_g[r] = -1;
+        }
+        int mine = -1;
+        for (int j = 0; j < count; ++j)
+            if (warp_id >= s_plan[j].warp0 && warp_id < s_plan[j].warp0 + s_plan[j].nwarps) mine = j;
+        if (mine >= 0) {
+            const PlanEntry e = s_plan[mine];
+            if (e.n > p.nmax) {                      // host promised this cannot happen
+                if (threadIdx.x == e.warp0 * 32 && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_BATCH);
+            } else {
+                Team tm;
+                tm.tid = threadIdx.x - e.warp0 * 32;
+                tm.nthreads = e.nwarps * 32;
+                tm.warp = tm.tid >> 5;
+                tm.nwarps = e.nwarps;
+                tm.lane = lane;
+                tm.bar = 1 + mine;
+                tm.smem = team_base + e.smem_off;
+                if (p.trace && tm.tid == 0) p.trace[(int64_t)e.gi * 16 + 11] = cta_t0;
+                process_graph(p, tm, e, smraw);
+            }
+        }
+        __syncthreads();                             // shared memory is re-carved by the next pass
+        next += count;
     }
 }
 
@@ -511,6 +828,9 @@ int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const
                         cudaStream_t st);
 int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes);
 
+static int64_t* g_trace = nullptr;
+extern "C" void dgcnn_stack_fwd_set_trace(int64_t* device_buffer) { g_trace = device_buffer; }
+
 static int mma_supported(int32_t f, int64_t max_nodes) {
     if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
     const int np = (int)((max_nodes + 15) / 16 * 16);
@@ -527,6 +847,7 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
                                const int32_t* rowptr, const int32_t* col, const float* dis,
                                const int32_t* gptr, const int32_t* gorder,
                                const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                               const uint32_t* fragmap, const int32_t* fgoff, const int32_t* gdesc,
                                int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                                const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* w3, const float* b3, const float* w4, const float* b4,
@@ -544,6 +865,7 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
                                    : !dgcnn_stack_fwd_fma_supported(num_features, max_nodes))
         return DGCNN_ERR_UNSUPPORTED;
     if (!bitmap || !bmoff || !gflags) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (variant == DGCNN_STACK_MMA && (!fragmap || !fgoff || !gdesc)) return DGCNN_ERR_INVALID_ARGUMENT;
     if (max_nodes > 1024) return DGCNN_ERR_UNSUPPORTED;
     if (!rowptr || !dis || !gptr || !w1 || !w2 || !w3 || !w4 || !xcat || !pooled || !perm ||
         (num_nodes > 0 && !x))
@@ -552,21 +874,24 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uintptr_t aligned = ((uintptr_t)workspace + 127) & ~(uintptr_t)127;
     int32_t* counter = reinterpret_cast<int32_t*>(aligned);
-    if (cudaMemsetAsync(counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
-    if (variant == DGCNN_STACK_FMA)
+    if (variant == DGCNN_STACK_FMA) {
+        if (cudaMemsetAsync(counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
         return dgcnn_stack_fwd_fma(x, ldx, num_features, rowptr, col, dis, gptr, gorder, bitmap, bmoff,
                                    gflags, num_nodes, num_graphs,
                                    max_nodes, w1, b1, w2, b2, w3, b3, w4, b4, xcat, ldc, pooled, perm, k,
                                    norm, status, counter, st);
+    }
 
     StackFwdParams p{};
     p.x = x; p.ldx = ldx; p.f = num_features;
     p.rowptr = rowptr; p.col = col; p.dis = dis; p.gptr = gptr; p.num_graphs = (int)num_graphs;
     p.bitmap = bitmap; p.bmoff = bmoff; p.gflags = gflags;
+    p.fragmap = fragmap; p.fgoff = fgoff;
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.w4 = w4; p.b4 = b4;
     p.xcat = xcat; p.ldc = ldc; p.pooled = pooled; p.perm = perm; p.k = k;
     p.norm = norm; p.nmax = (int)max_nodes;
-    p.gorder = gorder; p.counter = counter; p.status = status;
+    p.gdesc = gdesc; p.counter = counter; p.status = status;
+    p.trace = g_trace;
     // one CTA per SM with (almost) all of its shared memory: 4 quad slices + the weights
     const size_t smem = (size_t)al16(shared_layout(p.f).total) + (size_t)kQuads * quad_bytes(p.f);
     if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -22,6 +22,7 @@ ACT_NONE, ACT_TANH = 0, 1
 GRAPH_BAD_EDGE, GRAPH_BAD_BATCH, GRAPH_RANGE, GRAPH_GENERIC = 1, 2, 4, 8
 BITMAP_MAX_NODES = 1024
 STACK_MMA, STACK_FMA = 0, 1
+XCAT_LD = 100     # row stride (floats) of the x_cat buffer the fused forward allocates
 # implementation of the fused forward; tests flip it to cross-check the two kernels
 STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower() == "fma" else STACK_MMA
 
@@ -91,6 +92,9 @@ class Graph:
     bitmap_t: Optional[Tensor] = None
     bmoff_t: Optional[Tensor] = None
     gflags_t: Optional[Tensor] = None
+    fragmap: Optional[Tensor] = None      # fragment-major copy of `bitmap` (tensor-core kernels)
+    fgoff: Optional[Tensor] = None
+    gdesc: Optional[Tensor] = None        # {graph, first node, nodes, fgoff} in work order
 
     def check(self) -> None:
         """Host-syncing validation of the device-side status word (debug / tests)."""
@@ -151,22 +155,30 @@ def _build_bitmaps(graph: Graph, transpose: bool) -> None:
     words = int(lib.dgcnn_graph_bitmap_words(n, b, mx))
     i32 = dict(dtype=torch.int32, device=dev)
 
-    def run(rowptr, col, gate):
+    fwords = int(lib.dgcnn_graph_fragmap_words(n, b, mx))
+
+    def run(rowptr, col, gate, frag):
         bitmap = torch.empty(words, **i32)
         bmoff = torch.empty(b + 1, **i32)
         gflags = torch.empty(b, **i32)
+        fragmap = torch.empty(fwords, **i32) if frag else None
+        fgoff = torch.empty(b + 1, **i32) if frag else None
+        gdesc = torch.empty(b, 4, **i32) if frag else None
         with torch.cuda.device(dev):
             rc = lib.dgcnn_build_bitmaps(_ptr(rowptr), _ptr(col), _ptr(graph.gptr), n, b, mx,
                                          _ptr(bitmap), words, _ptr(bmoff), _ptr(gflags),
+                                         _ptr(fragmap), fwords if frag else 0, _ptr(fgoff),
+                                         _ptr(graph.gorder), _ptr(gdesc),
                                          _ptr(graph.status) if gate else None, GRAPH_GENERIC,
                                          _stream())
         _lib.check(rc, "build_bitmaps")
-        LAUNCHES["build_bitmaps"] += 2
-        return bitmap, bmoff, gflags
+        LAUNCHES["build_bitmaps"] += 3 if frag else 2
+        return bitmap, bmoff, gflags, fragmap, fgoff, gdesc
 
-    graph.bitmap, graph.bmoff, graph.gflags = run(graph.rowptr, graph.col, False)
+    graph.bitmap, graph.bmoff, graph.gflags, graph.fragmap, graph.fgoff, graph.gdesc = \
+        run(graph.rowptr, graph.col, False, True)
     if transpose and graph.rowptr_t is not None:
-        graph.bitmap_t, graph.bmoff_t, graph.gflags_t = run(graph.rowptr_t, graph.col_t, True)
+        graph.bitmap_t, graph.bmoff_t, graph.gflags_t, _, _, _ = run(graph.rowptr_t, graph.col_t, True, False)
 
 
 def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
@@ -302,17 +314,19 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
     for t in ws + [b for b in bs if b is not None]:
         _require_cuda(t, "parameter", torch.float32)
     b = graph.num_graphs
-    xcat = torch.empty(n, 97, dtype=torch.float32, device=x.device)
+    # rows padded to 100 floats (16-byte aligned rows: vector stores in KS); callers see [N,97]
+    xcat = torch.empty(n, XCAT_LD, dtype=torch.float32, device=x.device)[:, :97]
     pooled = torch.empty(b, int(k) * 97, dtype=torch.float32, device=x.device)
     perm = torch.empty(b, int(k), dtype=torch.int32, device=x.device)
     wsp = _workspace(lib.dgcnn_stack_fwd_workspace_bytes(), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_fwd(_ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr), _ptr(graph.col),
                                  _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder),
-                                 _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags), n, b,
+                                 _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags),
+                                 _ptr(graph.fragmap), _ptr(graph.fgoff), _ptr(graph.gdesc), n, b,
                                  int(graph.max_nodes), _ptr(ws[0]), _ptr(bs[0]), _ptr(ws[1]), _ptr(bs[1]),
                                  _ptr(ws[2]), _ptr(bs[2]), _ptr(ws[3]), _ptr(bs[3]),
-                                 _ptr(xcat), 97, _ptr(pooled), _ptr(perm), int(k), int(norm),
+                                 _ptr(xcat), XCAT_LD, _ptr(pooled), _ptr(perm), int(k), int(norm),
                                  int(STACK_VARIANT), _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
     _lib.check(rc, "stack_fwd")
     LAUNCHES["stack_fwd"] += 1 if b > 0 else 0

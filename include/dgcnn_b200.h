@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DGCNN_B200_ABI_VERSION 1
+#define DGCNN_B200_ABI_VERSION 2
 
 typedef enum dgcnn_status {
     DGCNN_OK = 0,
@@ -106,9 +106,20 @@ int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges,
  * max_nodes: largest graph in the batch (host knowledge); capped at 1024.
  * ------------------------------------------------------------------------ */
 int64_t dgcnn_graph_bitmap_words(int64_t num_nodes, int64_t num_graphs, int64_t max_nodes);
+/* Optional second copy in FRAGMENT-MAJOR order for the tensor-core kernels (fragmap may be
+ * NULL): graph g with T = np_g/16 row tiles and G = ceil(T/4) column groups owns T*G*32
+ * words at fgoff[g]; word (mt, grp, lane) packs the lane's mma.m16n8k16 A-fragment bits of
+ * the four 16x16 blocks kt = 4 grp + q (layout: dgcnn_b200/csrc/graph_bitmap.cu).
+ *   fragmap uint32[dgcnn_graph_fragmap_words(N, B, max_nodes)];  fgoff int32[B+1]
+ * gdesc (optional, needs fragmap; 16-byte aligned int32[4*B]): work descriptors
+ *   {graph, first node, nodes, fgoff[graph]} in the order of gorder (K0: descending size;
+ *   NULL = natural order) -- what the tensor-core KS kernel reads to deal graphs to SMs. */
+int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_graphs, int64_t max_nodes);
 int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col, const int32_t* gptr,
                         int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                         uint32_t* bitmap, int64_t bitmap_words, int32_t* bmoff, int32_t* gflags,
+                        uint32_t* fragmap, int64_t fragmap_words, int32_t* fgoff,
+                        const int32_t* gorder, int32_t* gdesc,
                         const int32_t* gate_word, int32_t gate_mask, void* stream);
 
 /* gptr alone (SortAggregation called without a graph: model.py:35's `batch`). */
@@ -192,11 +203,17 @@ int dgcnn_sort_pool_bwd(const float* dout, const int32_t* perm, int64_t num_grap
  * w1 [32,F], w2/w3 [32,32], w4 [1,32] row-major; biases may be NULL.
  * ------------------------------------------------------------------------ */
 int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes);
+/* Debug hook (not thread-safe, off by default): when set to a device buffer of
+ * int64[num_graphs][16], the tensor-core KS kernel records clock64() at the end of each of
+ * its phases per graph (slots 0-8) and (smid << 32 | team threads | n << 12) in slot 15.
+ * Pass NULL to switch it off.  Used by scripts/trace_stack_fwd.py. */
+void dgcnn_stack_fwd_set_trace(int64_t* device_buffer);
 size_t dgcnn_stack_fwd_workspace_bytes(void);
 int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                     const int32_t* rowptr, const int32_t* col, const float* dis,
                     const int32_t* gptr, const int32_t* gorder,
                     const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                    const uint32_t* fragmap, const int32_t* fgoff, const int32_t* gdesc,
                     int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                     const float* w1, const float* b1, const float* w2, const float* b2,
                     const float* w3, const float* b3, const float* w4, const float* b4,

@@ -166,6 +166,28 @@ def test_bitmaps_match_the_adjacency():
             pairs = np.stack([rows[sel], cols[sel]], 1)
             has_dup = len(np.unique(pairs, axis=0)) != len(pairs)
             assert bool(fl[gi] & 1) == has_dup
+            if bitmap is g.bitmap:
+                # fragment-major copy (tensor-core kernels): word (mt, grp, lane) carries the
+                # lane's m16k16 A-fragment bits of blocks kt = 4 grp + q
+                fm = g.fragmap.cpu().numpy().view(np.uint32)
+                fo = g.fgoff.cpu().numpy()
+                tiles = npad // 16
+                groups = (tiles + 3) // 4
+                assert fo[gi + 1] - fo[gi] == tiles * groups * 32
+                want = np.zeros((tiles, groups, 32), dtype=np.uint32)
+                full = np.zeros((npad, groups * 64), dtype=bool)
+                full[:, :dense.shape[1]] = dense[:, :groups * 64]
+                for lane in range(32):
+                    gq, t = lane >> 2, lane & 3
+                    for q in range(4):
+                        for i in range(4):
+                            r = np.arange(tiles) * 16 + gq + 8 * (i & 1)
+                            for grp in range(groups):
+                                c = grp * 64 + q * 16 + 2 * t + 8 * (i >> 1)
+                                m = 4 * q + i
+                                want[:, grp, lane] |= (full[r, c].astype(np.uint32) << m) | \
+                                                      (full[r, c + 1].astype(np.uint32) << (16 + m))
+                np.testing.assert_array_equal(fm[fo[gi]:fo[gi + 1]].reshape(tiles, groups, 32), want)
     # sorted symmetric input: proven symmetric on the device, transposed bitmap left empty
     bt = make_batch("proteins", num_graphs=20)
     g2 = ops.build_graph(bt.edge_index.to(DEV), bt.batch.to(DEV), bt.num_nodes, 20,

@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/dgcnn_b200.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert lib.dgcnn_abi_version() == 1
+    assert lib.dgcnn_abi_version() == 2
     assert lib.dgcnn_status_string(0) == b"ok"
     assert b"workspace" in lib.dgcnn_status_string(-3)
 

@@ -31,12 +31,13 @@ SIGNATURES = {
     "dgcnn_build_graph_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dgcnn_build_graph": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                     c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_void_p, c_size_t, c_void_p]),
     "dgcnn_graph_bitmap_words": (c_int64, [c_int64, c_int64, c_int64]),
     "dgcnn_graph_fragmap_words": (c_int64, [c_int64, c_int64, c_int64]),
-    "dgcnn_build_bitmaps": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
-                                      c_void_p, c_int64, c_void_p, c_void_p,
+    "dgcnn_build_bitmaps": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_int64, c_int64,
+                                      c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int32, c_void_p]),
     "dgcnn_graph_ptr": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),

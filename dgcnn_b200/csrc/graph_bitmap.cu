@@ -35,7 +35,7 @@ __device__ __forceinline__ int fragmap_words_of(int n, int max_nodes) {
 __global__ void __launch_bounds__(1024)
 k0b_offsets(const int32_t* __restrict__ gptr, int num_graphs, int max_nodes,
             int32_t* __restrict__ bmoff, int32_t* __restrict__ fgoff, int32_t* __restrict__ gflags,
-            const int32_t* __restrict__ gorder, int4* __restrict__ gdesc) {
+            int32_t* __restrict__ gflags_t, const int32_t* __restrict__ gorder, int4* __restrict__ gdesc) {
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -49,6 +49,7 @@ k0b_offsets(const int32_t* __restrict__ gptr, int num_graphs, int max_nodes,
             v = (unsigned long long)(unsigned)bitmap_words_of(n, max_nodes) |
                 ((unsigned long long)(unsigned)fragmap_words_of(n, max_nodes) << 32);
             gflags[g] = (n > max_nodes) ? 2 : 0;
+            if (gflags_t) gflags_t[g] = (n > max_nodes) ? 2 : 0;
         }
         unsigned long long inc = v;
 #pragma unroll
@@ -92,76 +93,48 @@ k0b_offsets(const int32_t* __restrict__ gptr, int num_graphs, int max_nodes,
     }
 }
 
-// Fragment-major copy of the row bitmaps for the tensor-core kernels (graph_stack_mma.cu):
-// graph g with T = np/16 row tiles and G = ceil(T/4) column groups owns T*G*32 words at
-// fragmap + fgoff[g]; word (mt, grp, lane = 4*gq + t) holds, for the four 16x16 blocks
-// kt = 4*grp + q, the lane's m16k16 A-fragment bits: pair m = 4q + i at bit m (even column)
-// and bit 16 + m (odd column), i = 0: (row gq, cols 2t..), 1: (row gq+8, cols 2t..),
-// 2: (row gq, cols 2t+8..), 3: (row gq+8, cols 2t+8..).  One warp per (mt, grp) unit.
+// One warp per node row; blockIdx.y = 1 builds the bitmap of A_hat^T from the CSR by source
+// (skipped on the device when K0 proved the batch symmetric: gate_word / gate_mask).
+// Lane l accumulates word l of the row (wpr <= 32 for n <= 1024).  The columns of a CSR row
+// ascend, so the lanes of a 32-edge chunk that hit the same word are handled together:
+// leader by leader, one ballot + one OR-reduction per distinct word.
 __global__ void __launch_bounds__(256)
-k0b_fragments(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ bmoff,
-              const int32_t* __restrict__ fgoff, const int32_t* __restrict__ gptr, int num_graphs,
-              uint32_t* __restrict__ fragmap, const int32_t* gate_word, int gate_mask) {
-    if (gate_word && !(*gate_word & gate_mask)) return;
-    const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
-    const int units = fgoff[num_graphs] >> 5;
-    const int warps = gridDim.x * (blockDim.x >> 5);
-    for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += warps) {
-        int lo = 0, hi = num_graphs;                 // last g with fgoff[g] <= 32 u
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (fgoff[mid] <= (u << 5)) lo = mid; else hi = mid;
-        }
-        const int g = lo, n = gptr[g + 1] - gptr[g];
-        const int np = (n + 15) & ~15, wpr = (np + 31) >> 5, T = np >> 4, G = (T + 3) >> 2;
-        const int local = u - (fgoff[g] >> 5);
-        const int mt = local / G, grp = local - mt * G;
-        const uint32_t* r0 = bitmap + bmoff[g] + (int64_t)(mt * 16 + gq) * wpr;
-        const uint32_t* r1 = r0 + 8 * wpr;
-        const int w0 = 2 * grp, w1 = 2 * grp + 1;
-        const unsigned long long row0 = (unsigned long long)r0[w0] |
-                                        ((unsigned long long)(w1 < wpr ? r0[w1] : 0u) << 32);
-        const unsigned long long row1 = (unsigned long long)r1[w0] |
-                                        ((unsigned long long)(w1 < wpr ? r1[w1] : 0u) << 32);
-        uint32_t out = 0u;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const unsigned long long src = (i & 1) ? row1 : row0;
-                const int col = q * 16 + 2 * t + 8 * (i >> 1);
-                const uint32_t two = (uint32_t)(src >> col) & 3u;
-                out |= ((two & 1u) << (4 * q + i)) | ((two >> 1) << (16 + 4 * q + i));
-            }
-        fragmap[fgoff[g] + (local << 5) + lane] = out;
-    }
-}
-
-// one warp per node row
-__global__ void __launch_bounds__(256)
-k0b_fill(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-         const int32_t* __restrict__ gptr, int num_graphs, int64_t n_nodes, int max_nodes,
-         const int32_t* __restrict__ bmoff, uint32_t* __restrict__ bitmap,
-         int32_t* __restrict__ gflags, const int32_t* gate_word, int gate_mask) {
-    if (gate_word && !(*gate_word & gate_mask)) return;
+k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
+         const int32_t* __restrict__ rowptr1, const int32_t* __restrict__ col1,
+         const int32_t* __restrict__ gptr, const int64_t* __restrict__ batch, int num_graphs,
+         int64_t n_nodes, int max_nodes, const int32_t* __restrict__ bmoff,
+         uint32_t* __restrict__ bitmap0, uint32_t* __restrict__ bitmap1,
+         int32_t* __restrict__ gflags0, int32_t* __restrict__ gflags1,
+         const int32_t* gate_word, int gate_mask) {
+    const bool second = blockIdx.y != 0;
+    if (second && gate_word && !(*gate_word & gate_mask)) return;
+    const int32_t* __restrict__ rowptr = second ? rowptr1 : rowptr0;
+    const int32_t* __restrict__ col = second ? col1 : col0;
+    uint32_t* __restrict__ bitmap = second ? bitmap1 : bitmap0;
+    int32_t* __restrict__ gflags = second ? gflags1 : gflags0;
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_nodes;
          i += warps) {
-        // graph of node i: last g with gptr[g] <= i
-        int lo = 0, hi = num_graphs;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (gptr[mid] <= i) lo = mid; else hi = mid;
+        const int beg = rowptr[i], end = rowptr[i + 1];
+        int g;
+        if (batch) {
+            g = (int)batch[i];
+        } else {                                     // graph of node i: last g with gptr[g] <= i
+            int lo = 0, hi = num_graphs;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (gptr[mid] <= i) lo = mid; else hi = mid;
+            }
+            g = lo;
         }
-        const int g = lo, base = gptr[g], n = gptr[g + 1] - base;
-        if (n > max_nodes) continue;
+        if ((unsigned)g >= (unsigned)num_graphs) continue;   // K0 flags a bad batch vector
+        const int base = gptr[g], n = gptr[g + 1] - base;
+        if (n > max_nodes || i < base || i >= (int64_t)base + n) continue;
         const int np = (n + 15) & ~15, wpr = (np + 31) >> 5;
         const int r = (int)(i - base);
         uint32_t* brow = bitmap + bmoff[g] + (int64_t)r * wpr;
-        const int beg = rowptr[i], end = rowptr[i + 1];
         bool dup = false;
-        // a warp owns the row: accumulate one word per lane (wpr <= 32 for n <= 1024)
         uint32_t mine = 0;            // lane l holds word l of the row
         for (int c0 = beg; c0 < end; c0 += 32) {
             const int e = c0 + lane;
@@ -172,25 +145,65 @@ k0b_fill(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
             }
             const int word = j >= 0 ? (j >> 5) : -1;
             const uint32_t bit = j >= 0 ? (1u << (j & 31)) : 0u;
-            const uint32_t peers = __match_any_sync(DGCNN_FULL_MASK, word);
-            const uint32_t val = __reduce_or_sync(peers, bit);
-            if (j >= 0 && __popc(val) != __popc(peers)) dup = true;   // same bit twice in this chunk
-            // hand each distinct word to the lane that owns it
 #pragma unroll 1
-            for (uint32_t todo = __ballot_sync(DGCNN_FULL_MASK, j >= 0 && lane == __ffs(peers) - 1); todo;
-                 todo &= todo - 1) {
-                const int src = __ffs(todo) - 1;
-                const int w = __shfl_sync(DGCNN_FULL_MASK, word, src);
-                const uint32_t v = __shfl_sync(DGCNN_FULL_MASK, val, src);
+            for (uint32_t todo = __ballot_sync(DGCNN_FULL_MASK, j >= 0); todo;) {
+                const int w = __shfl_sync(DGCNN_FULL_MASK, word, __ffs(todo) - 1);
+                const uint32_t peers = __ballot_sync(DGCNN_FULL_MASK, word == w);
+                const uint32_t val = __reduce_or_sync(DGCNN_FULL_MASK, word == w ? bit : 0u);
+                if (__popc(val) != __popc(peers)) dup = true;          // same bit twice in this chunk
                 if (lane == w) {
-                    if (mine & v) dup = true;                          // bit already set by an earlier chunk
-                    mine |= v;
+                    if (mine & val) dup = true;                        // bit already set by an earlier chunk
+                    mine |= val;
                 }
+                todo &= ~peers;
             }
         }
         if (lane == (r >> 5)) mine |= 1u << (r & 31);                  // the self loop
         if (lane < wpr) brow[lane] = mine;
         if (__any_sync(DGCNN_FULL_MASK, dup) && lane == 0) atomicOr(&gflags[g], 1);
+    }
+}
+
+// Fragment-major copy of the row bitmaps for the tensor-core kernels (graph_stack_mma.cu):
+// graph g with T = np/16 row tiles and G = ceil(T/4) column groups owns T*G*32 words at
+// fragmap + fgoff[g]; word (mt, grp, lane = 4*gq + t) holds, for the four 16x16 blocks
+// kt = 4*grp + q, the lane's m16k16 A-fragment bits: pair m = 4q + i at bit m (even column)
+// and bit 16 + m (odd column), i = 0: (row gq, cols 2t..), 1: (row gq+8, cols 2t..),
+// 2: (row gq, cols 2t+8..), 3: (row gq+8, cols 2t+8..).  One CTA per graph (descriptor
+// order), one warp per (mt, grp) unit.
+__global__ void __launch_bounds__(256)
+k0b_fragments(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ bmoff,
+              const int4* __restrict__ gdesc, int num_graphs, int max_nodes,
+              uint32_t* __restrict__ fragmap) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+    for (int q = blockIdx.x; q < num_graphs; q += gridDim.x) {
+        const int4 d = gdesc[q];                     // {graph, first node, nodes, fgoff}
+        const int n = d.z;
+        if (n <= 0 || n > max_nodes) continue;
+        const int np = (n + 15) & ~15, wpr = (np + 31) >> 5, T = np >> 4, G = (T + 3) >> 2;
+        const uint32_t* bm = bitmap + bmoff[d.x];
+        uint32_t* out = fragmap + d.w;
+        for (int u = threadIdx.x >> 5; u < T * G; u += blockDim.x >> 5) {
+            const int mt = u / G, grp = u - mt * G;
+            const uint32_t* r0 = bm + (int64_t)(mt * 16 + gq) * wpr;
+            const uint32_t* r1 = r0 + 8 * wpr;
+            const int w0 = 2 * grp, w1 = 2 * grp + 1;
+            const unsigned long long row0 = (unsigned long long)r0[w0] |
+                                            ((unsigned long long)(w1 < wpr ? r0[w1] : 0u) << 32);
+            const unsigned long long row1 = (unsigned long long)r1[w0] |
+                                            ((unsigned long long)(w1 < wpr ? r1[w1] : 0u) << 32);
+            uint32_t o = 0u;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned long long src = (i & 1) ? row1 : row0;
+                    const int c = qq * 16 + 2 * t + 8 * (i >> 1);
+                    const uint32_t two = (uint32_t)(src >> c) & 3u;
+                    o |= ((two & 1u) << (4 * qq + i)) | ((two >> 1) << (16 + 4 * qq + i));
+                }
+            out[(u << 5) + lane] = o;
+        }
     }
 }
 
@@ -214,41 +227,56 @@ extern "C" int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_grap
     return (num_nodes / 16 + num_graphs) * ((tmax + 3) / 4) * 32 + 32;
 }
 
-extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col, const int32_t* gptr,
+extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
+                                   const int32_t* rowptr_t, const int32_t* col_t,
+                                   const int32_t* gptr, const int64_t* batch,
                                    int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
-                                   uint32_t* bitmap, int64_t bitmap_words, int32_t* bmoff,
-                                   int32_t* gflags, uint32_t* fragmap, int64_t fragmap_words,
-                                   int32_t* fgoff, const int32_t* gorder, int32_t* gdesc,
+                                   uint32_t* bitmap, uint32_t* bitmap_t, int64_t bitmap_words,
+                                   int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,
+                                   uint32_t* fragmap, int64_t fragmap_words, int32_t* fgoff,
+                                   const int32_t* gorder, int32_t* gdesc,
                                    const int32_t* gate_word, int32_t gate_mask, void* stream) {
     if (num_nodes < 0 || num_graphs < 0 || max_nodes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_graphs == 0) return DGCNN_OK;
     if (!rowptr || !gptr || !bitmap || !bmoff || !gflags) return DGCNN_ERR_INVALID_ARGUMENT;
+    const bool transposed = bitmap_t != nullptr;
+    if (transposed && (!rowptr_t || !gflags_t)) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_nodes >= INT32_MAX || num_graphs >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
     if (max_nodes > 1024) max_nodes = 1024;          // a row must fit one word per lane
     const int64_t need = dgcnn_graph_bitmap_words(num_nodes, num_graphs, max_nodes);
     if (bitmap_words < need || need >= INT32_MAX) return DGCNN_ERR_WORKSPACE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * (size_t)need, st) != cudaSuccess)
-        return DGCNN_ERR_CUDA;
     if (fragmap) {
         if (!fgoff) return DGCNN_ERR_INVALID_ARGUMENT;
         const int64_t fneed = dgcnn_graph_fragmap_words(num_nodes, num_graphs, max_nodes);
         if (fragmap_words < fneed || fneed >= INT32_MAX) return DGCNN_ERR_WORKSPACE;
     }
     if (gdesc && (!fragmap || ((uintptr_t)gdesc & 15))) return DGCNN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // padding rows / bits must be zero; one memset when the two bitmaps are adjacent
+    if (transposed && bitmap_t == bitmap + need) {
+        if (cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * 2 * (size_t)need, st) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+    } else {
+        if (cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * (size_t)need, st) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+        if (transposed &&
+            cudaMemsetAsync(bitmap_t, 0, sizeof(uint32_t) * (size_t)need, st) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+    }
     k0b_offsets<<<1, 1024, 0, st>>>(gptr, (int)num_graphs, (int)max_nodes, bmoff,
-                                    fragmap ? fgoff : nullptr, gflags, gorder,
+                                    fragmap ? fgoff : nullptr, gflags, gflags_t, gorder,
                                     reinterpret_cast<int4*>(gdesc));
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (num_nodes > 0) {
-        k0b_fill<<<grid_for(num_nodes, 8, 8), 256, 0, st>>>(rowptr, col, gptr, (int)num_graphs, num_nodes,
-                                                            (int)max_nodes, bmoff, bitmap, gflags,
-                                                            gate_word, gate_mask);
+        dim3 grid((unsigned)grid_for(num_nodes, 8, 8), transposed ? 2 : 1);
+        k0b_fill<<<grid, 256, 0, st>>>(rowptr, col, rowptr_t, col_t, gptr, batch, (int)num_graphs,
+                                       num_nodes, (int)max_nodes, bmoff, bitmap, bitmap_t, gflags,
+                                       gflags_t, gate_word, gate_mask);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
-        if (fragmap) {
-            const int64_t units = dgcnn_graph_fragmap_words(num_nodes, num_graphs, max_nodes) / 32;
-            k0b_fragments<<<grid_for(units, 8, 8), 256, 0, st>>>(bitmap, bmoff, fgoff, gptr, (int)num_graphs,
-                                                                 fragmap, gate_word, gate_mask);
+        if (fragmap && gdesc) {
+            k0b_fragments<<<grid_for(num_graphs, 1, 8), 256, 0, st>>>(
+                bitmap, bmoff, reinterpret_cast<const int4*>(gdesc), (int)num_graphs, (int)max_nodes,
+                fragmap);
             DGCNN_RETURN_IF_LAUNCH_FAILED();
         }
     }

@@ -13,16 +13,21 @@
 //         exactly what TUDataset/PyG batches look like.  Then the CSR
 //         by source is the edge list itself (row pointers = run boundaries), and by
 //         symmetry it is also the CSR by target.  k0_fast_build writes it in one
-//         streaming pass and checks order; k0_fast_verify checks symmetry with a
-//         binary search per edge and derives dis.  Any violation sets a device flag.
+//         streaming pass, checks order and fingerprints symmetry; k0_finalize derives
+//         dis, the verdict and the graph order.  Any violation sets a device flag.
 //
 //  generic  memset degrees -> count -> 3-phase exclusive scan (+dis) -> fill (atomic
-//         cursor, order arbitrary) -> per-row rank sort (ascending source id).  Always
-//         launched, but every kernel returns at once unless the flag is set.
+//         cursor, order arbitrary) -> per-row rank sort (ascending source id): ONE
+//         cooperative launch with grid barriers between the phases, always issued, which
+//         returns at once unless the flag is set.
 //         The row sort makes the CSR canonical: duplicates are equal values, so the
 //         result -- and every later floating-point summation order -- is
 //         bit-reproducible run to run although the fill uses atomics.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dgcnn {
 
@@ -32,6 +37,7 @@ constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
 
 struct BuildWorkspace {
     int32_t* flags;  // bit 0: input is not in the fast-path form, run the generic pipeline
+                     // (flags + 2, + 4: two 64-bit symmetry fingerprints, see k0_fast_build)
     int32_t* indeg;
     int32_t* outdeg;
     int32_t* bsum;   // [2][nb]
@@ -52,7 +58,7 @@ __host__ inline BuildWorkspace carve_build_workspace(void* base, int64_t n, int6
         return q;
     };
     // flags, indeg and outdeg are adjacent so that one memset clears all three
-    w.flags = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
+    w.flags = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * 8));
     w.indeg = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)n));
     w.outdeg = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)n));
     w.bsum = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * 2 * (size_t)w.nb));
@@ -87,30 +93,6 @@ k0_graph_ptr(const int64_t* __restrict__ batch, int64_t n, int64_t num_graphs,
         graph_ptr_body(batch, n, num_graphs, gptr, status, i);
 }
 
-__global__ void __launch_bounds__(256)
-k0_count(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0,
-         const int64_t* __restrict__ batch, int64_t n, int64_t num_graphs,
-         int32_t* __restrict__ indeg, int32_t* __restrict__ outdeg,
-         int32_t* __restrict__ gptr, int32_t* status, const int32_t* gate) {
-    if (gate && !(*gate & 1)) return;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid == 0 && gate && status) atomicOr(status, DGCNN_GRAPH_GENERIC);   // not proven symmetric
-    for (int64_t e = tid; e < e0; e += stride) {
-        int64_t s = src[e], d = dst[e];
-        if ((uint64_t)s >= (uint64_t)n || (uint64_t)d >= (uint64_t)n) {
-            if (status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE);
-            continue;
-        }
-        if (s == d) continue;  // remove_self_loops; the +1 in dis re-adds exactly one loop
-        atomicAdd(&indeg[d], 1);
-        if (outdeg) atomicAdd(&outdeg[s], 1);
-    }
-    if (gptr)
-        for (int64_t i = tid; i <= n; i += stride)
-            graph_ptr_body(batch, n, num_graphs, gptr, status, i);
-}
-
 __device__ __forceinline__ int block_sum_256(int v, int* smem /*[8]*/) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DGCNN_FULL_MASK, v, o);
@@ -124,157 +106,168 @@ __device__ __forceinline__ int block_sum_256(int v, int* smem /*[8]*/) {
     return t;
 }
 
-// phase 1: per-tile sums.  grid (nb, 1 or 2); y selects in- or out-degrees
-__global__ void __launch_bounds__(kScanThreads)
-k0_scan_reduce(const int32_t* __restrict__ indeg, const int32_t* __restrict__ outdeg, int64_t n,
-               int32_t* __restrict__ bsum, int64_t nb, const int32_t* gate) {
-    __shared__ int red[kScanThreads / 32];
-    if (gate && !(*gate & 1)) return;
-    const int32_t* deg = blockIdx.y ? outdeg : indeg;
-    int64_t base = (int64_t)blockIdx.x * kScanTile;
-    int v = 0;
-#pragma unroll
-    for (int q = 0; q < kScanItems; ++q) {
-        int64_t i = base + q * kScanThreads + threadIdx.x;
-        if (i < n) v += deg[i];
-    }
-    int t = block_sum_256(v, red);
-    if (threadIdx.x == 0) bsum[blockIdx.y * nb + blockIdx.x] = t;
-}
+// ---- generic path in ONE launch -------------------------------------------------------
+// count -> tile sums -> top scan -> apply (+dis) -> fill -> row sort, separated by grid-wide
+// barriers (cooperative launch: every CTA is resident).  When the fast path succeeded -- the
+// normal case -- the flag is clear and every thread leaves at once: one empty launch instead
+// of six.
+struct GenericArgs {
+    const int64_t* src; const int64_t* dst; int64_t e0;
+    const int64_t* batch; int64_t n; int64_t num_graphs;
+    int32_t* indeg; int32_t* outdeg; int32_t* bsum; int64_t nb;
+    int32_t* rowptr; int32_t* rowptr_t; float* dis;
+    int32_t* tmp_in; int32_t* tmp_out; int32_t* col; int32_t* col_t;
+    int32_t* status; const int32_t* gate;
+};
 
-// phase 2: exclusive scan of the tile sums, one CTA per array
-__global__ void __launch_bounds__(1024)
-k0_scan_top(int32_t* __restrict__ bsum, int64_t nb, const int32_t* gate) {
-    __shared__ int wsum[32];
+__global__ void __launch_bounds__(kScanThreads)
+k0_generic(GenericArgs a) {
+    __shared__ int red[kScanThreads / 32];
     __shared__ int carry_s;
-    if (gate && !(*gate & 1)) return;
-    int32_t* a = bsum + blockIdx.x * nb;
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t c0 = 0; c0 < nb; c0 += 1024) {
-        int64_t i = c0 + threadIdx.x;
-        int v = (i < nb) ? a[i] : 0;
-        int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int u = __shfl_up_sync(DGCNN_FULL_MASK, inc, o);
-            if (lane >= o) inc += u;
+    if (!(*a.gate & 1)) return;
+    cg::grid_group grid = cg::this_grid();
+    const bool transposed = a.rowptr_t != nullptr;
+    const int nwhich = transposed ? 2 : 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // 1. degrees (self loops dropped: the +1 in dis re-adds exactly one loop per node)
+    if (tid == 0 && a.status) atomicOr(a.status, DGCNN_GRAPH_GENERIC);      // not proven symmetric
+    for (int64_t e = tid; e < a.e0; e += stride) {
+        const int64_t s = a.src[e], d = a.dst[e];
+        if ((uint64_t)s >= (uint64_t)a.n || (uint64_t)d >= (uint64_t)a.n) {
+            if (a.status) atomicOr(a.status, DGCNN_GRAPH_BAD_EDGE);
+            continue;
         }
-        if (lane == 31) wsum[warp] = inc;
+        if (s == d) continue;
+        atomicAdd(&a.indeg[d], 1);
+        if (transposed) atomicAdd(&a.outdeg[s], 1);
+    }
+    grid.sync();
+
+    // 2. per-tile sums
+    for (int64_t job = blockIdx.x; job < a.nb * nwhich; job += gridDim.x) {
+        const int which = (int)(job / a.nb);
+        const int64_t tile = job - which * a.nb;
+        const int32_t* deg = which ? a.outdeg : a.indeg;
+        const int64_t base = tile * kScanTile;
+        int v = 0;
+#pragma unroll
+        for (int q = 0; q < kScanItems; ++q) {
+            const int64_t i = base + q * kScanThreads + threadIdx.x;
+            if (i < a.n) v += deg[i];
+        }
+        const int t = block_sum_256(v, red);
+        if (threadIdx.x == 0) a.bsum[which * a.nb + tile] = t;
+    }
+    grid.sync();
+
+    // 3. exclusive scan of the tile sums: one CTA per array
+    if ((int)blockIdx.x < nwhich) {
+        int32_t* arr = a.bsum + blockIdx.x * a.nb;
+        if (threadIdx.x == 0) carry_s = 0;
         __syncthreads();
-        if (warp == 0) {
-            int w = wsum[lane], winc = w;
+        for (int64_t c0 = 0; c0 < a.nb; c0 += kScanThreads) {
+            const int64_t i = c0 + threadIdx.x;
+            const int v = (i < a.nb) ? arr[i] : 0;
+            int inc = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(DGCNN_FULL_MASK, winc, o);
-                if (lane >= o) winc += u;
+                const int u = __shfl_up_sync(DGCNN_FULL_MASK, inc, o);
+                if (lane >= o) inc += u;
             }
-            wsum[lane] = winc - w;  // exclusive warp offsets
-        }
-        __syncthreads();
-        int carry = carry_s;
-        int excl = carry + wsum[warp] + inc - v;
-        if (i < nb) a[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl + v;
-        __syncthreads();
-    }
-}
-
-// phase 3: per-tile exclusive scan + tile offset -> rowptr[0..n]; also dis
-__global__ void __launch_bounds__(kScanThreads)
-k0_scan_apply(const int32_t* __restrict__ indeg, const int32_t* __restrict__ outdeg, int64_t n,
-              const int32_t* __restrict__ bsum, int64_t nb, int32_t* __restrict__ rowptr,
-              int32_t* __restrict__ rowptr_t, float* __restrict__ dis, const int32_t* gate) {
-    __shared__ int wsum[kScanThreads / 32];
-    if (gate && !(*gate & 1)) return;
-    const bool transposed = blockIdx.y != 0;
-    const int32_t* deg = transposed ? outdeg : indeg;
-    int32_t* out = transposed ? rowptr_t : rowptr;
-    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-    int v[kScanItems];
-    int tsum = 0;
+            if (lane == 31) red[warp] = inc;
+            __syncthreads();
+            int woff = 0;
 #pragma unroll
-    for (int q = 0; q < kScanItems; ++q) {
-        int64_t i = base + q;
-        v[q] = (i < n) ? deg[i] : 0;
-        tsum += v[q];
-    }
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(DGCNN_FULL_MASK, inc, o);
-        if (lane >= o) inc += u;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    int woff = 0;
-#pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) woff += (w < warp) ? wsum[w] : 0;
-    int run = bsum[blockIdx.y * nb + blockIdx.x] + woff + inc - tsum;
-#pragma unroll
-    for (int q = 0; q < kScanItems; ++q) {
-        int64_t i = base + q;
-        if (i <= n) out[i] = run;  // i == n receives the grand total
-        if (!transposed && i < n) dis[i] = 1.0f / sqrtf((float)(v[q] + 1));
-        run += v[q];
-    }
-}
-
-// scatter sources (targets) into their rows; the degree counters double as
-// reverse cursors, so they end at zero
-__global__ void __launch_bounds__(256)
-k0_fill(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0, int64_t n,
-        const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowptr_t,
-        int32_t* __restrict__ indeg, int32_t* __restrict__ outdeg,
-        int32_t* __restrict__ tmp_in, int32_t* __restrict__ tmp_out, const int32_t* gate) {
-    if (gate && !(*gate & 1)) return;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e0; e += stride) {
-        int64_t s = src[e], d = dst[e];
-        if ((uint64_t)s >= (uint64_t)n || (uint64_t)d >= (uint64_t)n || s == d) continue;
-        int p = atomicSub(&indeg[d], 1) - 1;
-        tmp_in[rowptr[d] + p] = (int32_t)s;
-        if (rowptr_t) {
-            int q = atomicSub(&outdeg[s], 1) - 1;
-            tmp_out[rowptr_t[s] + q] = (int32_t)d;
+            for (int w = 0; w < kScanThreads / 32; ++w) woff += (w < warp) ? red[w] : 0;
+            const int excl = carry_s + woff + inc - v;
+            if (i < a.nb) arr[i] = excl;
+            __syncthreads();
+            if (threadIdx.x == kScanThreads - 1) carry_s = excl + v;
+            __syncthreads();
         }
     }
-}
+    grid.sync();
 
-// one warp per row: rank sort (ascending value, ties by position) from tmp to col.
-// O(deg^2 / 32) shuffles per row; degrees here are tens to a few hundred.
-__global__ void __launch_bounds__(256)
-k0_sort_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowptr_t, int64_t n,
-             const int32_t* __restrict__ tmp_in, const int32_t* __restrict__ tmp_out,
-             int32_t* __restrict__ col, int32_t* __restrict__ col_t, const int32_t* gate) {
-    if (gate && !(*gate & 1)) return;
-    const bool transposed = blockIdx.y != 0;
-    const int32_t* rp = transposed ? rowptr_t : rowptr;
-    const int32_t* in = transposed ? tmp_out : tmp_in;
-    int32_t* out = transposed ? col_t : col;
-    int lane = threadIdx.x & 31;
-    int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n;
-         row += warps) {
-        int beg = rp[row], deg = rp[row + 1] - beg;
+    // 4. per-tile exclusive scan + tile offset -> rowptr[0..n]; also dis
+    for (int64_t job = blockIdx.x; job < a.nb * nwhich; job += gridDim.x) {
+        const int which = (int)(job / a.nb);
+        const int64_t tile = job - which * a.nb;
+        const int32_t* deg = which ? a.outdeg : a.indeg;
+        int32_t* out = which ? a.rowptr_t : a.rowptr;
+        const int64_t base = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+        int v[kScanItems];
+        int tsum = 0;
+#pragma unroll
+        for (int q = 0; q < kScanItems; ++q) {
+            const int64_t i = base + q;
+            v[q] = (i < a.n) ? deg[i] : 0;
+            tsum += v[q];
+        }
+        int inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(DGCNN_FULL_MASK, inc, o);
+            if (lane >= o) inc += u;
+        }
+        __syncthreads();                               // red[] may still be read by the previous job
+        if (lane == 31) red[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) woff += (w < warp) ? red[w] : 0;
+        int run = a.bsum[which * a.nb + tile] + woff + inc - tsum;
+#pragma unroll
+        for (int q = 0; q < kScanItems; ++q) {
+            const int64_t i = base + q;
+            if (i <= a.n) out[i] = run;                // i == n receives the grand total
+            if (!which && i < a.n) a.dis[i] = 1.0f / sqrtf((float)(v[q] + 1));
+            run += v[q];
+        }
+    }
+    grid.sync();
+
+    // 5. scatter sources (targets) into their rows; the degree counters double as reverse
+    //    cursors, so they end at zero
+    for (int64_t e = tid; e < a.e0; e += stride) {
+        const int64_t s = a.src[e], d = a.dst[e];
+        if ((uint64_t)s >= (uint64_t)a.n || (uint64_t)d >= (uint64_t)a.n || s == d) continue;
+        const int p = atomicSub(&a.indeg[d], 1) - 1;
+        a.tmp_in[a.rowptr[d] + p] = (int32_t)s;
+        if (transposed) {
+            const int q = atomicSub(&a.outdeg[s], 1) - 1;
+            a.tmp_out[a.rowptr_t[s] + q] = (int32_t)d;
+        }
+    }
+    grid.sync();
+
+    // 6. one warp per row: rank sort (ascending value, ties by position) from tmp to col.
+    //    O(deg^2 / 32) shuffles per row; makes the CSR canonical (bit-reproducible sums)
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; job < a.n * nwhich; job += warps) {
+        const int which = job >= a.n;
+        const int64_t row = which ? job - a.n : job;
+        const int32_t* rp = which ? a.rowptr_t : a.rowptr;
+        const int32_t* in = which ? a.tmp_out : a.tmp_in;
+        int32_t* out = which ? a.col_t : a.col;
+        const int beg = rp[row], deg = rp[row + 1] - beg;
         if (deg <= 0) continue;
         if (deg == 1) {
             if (lane == 0) out[beg] = in[beg];
             continue;
         }
         for (int t0 = 0; t0 < deg; t0 += 32) {
-            int t = t0 + lane;
-            int v = (t < deg) ? in[beg + t] : 0x7fffffff;
+            const int t = t0 + lane;
+            const int v = (t < deg) ? in[beg + t] : 0x7fffffff;
             int rank = 0;
             for (int c0 = 0; c0 < deg; c0 += 32) {
-                int idx = c0 + lane;
-                int u = (idx < deg) ? in[beg + idx] : 0x7fffffff;
-                int lim = min(32, deg - c0);
+                const int idx = c0 + lane;
+                const int u = (idx < deg) ? in[beg + idx] : 0x7fffffff;
+                const int lim = min(32, deg - c0);
                 for (int s = 0; s < lim; ++s) {
-                    int uu = __shfl_sync(DGCNN_FULL_MASK, u, s);
+                    const int uu = __shfl_sync(DGCNN_FULL_MASK, u, s);
                     rank += (uu < v) || (uu == v && (c0 + s) < t);
                 }
             }
@@ -284,18 +277,36 @@ k0_sort_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ row
 }
 
 // ---- fast path ---------------------------------------------------------------------
+// 32-bit mixes of an ORDERED pair; two independent ones feed the symmetry fingerprints
+__device__ __forceinline__ uint32_t pair_mix(uint32_t a, uint32_t b, uint32_t k1, uint32_t k2) {
+    uint32_t h = (a * k1) ^ __funnelshift_l(b * k2, b * k2, 15);
+    h *= 0xC2B2AE3Du; h ^= h >> 16;
+    h *= 0x27D4EB2Fu; h ^= h >> 15;
+    return h;
+}
+
 // One streaming pass: col/col_t = targets in input order, row pointers = run boundaries
 // of the source column, graph offsets; flags bit 0 is raised on anything that is not a
 // strictly (src,dst)-sorted, loop-free, in-range edge list.  e == e0 is the sentinel that
 // closes the trailing (edge-free) rows.
+//
+// Symmetry (needed for "CSR by source == CSR by target") is checked in the same pass by
+// fingerprinting: a strictly sorted list has no duplicates, so it is symmetric iff the
+// multisets {(s,d)} and {(d,s)} are equal, and two independent sums
+//   F_i = sum_e [ mix_i(s,d) - mix_i(d,s) ]   (mod 2^64)
+// are both zero when they are; a non-symmetric list passes with probability ~2^-64.
+// k0_finalize raises the flag when either sum is non-zero.  (The exact check, one binary
+// search per edge, is k0_fast_verify: `exact_verify` of dgcnn_build_graph.)
 __global__ void __launch_bounds__(256)
 k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0,
               const int64_t* __restrict__ batch, int64_t n, int64_t num_graphs,
               int32_t* __restrict__ rowptr, int32_t* __restrict__ col,
               int32_t* __restrict__ rowptr_t, int32_t* __restrict__ col_t,
               int32_t* __restrict__ gptr, int32_t* flags, int32_t* status) {
+    __shared__ unsigned long long red[2][8];
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long f0 = 0ull, f1 = 0ull;
     for (int64_t e = tid; e <= e0; e += stride) {
         int64_t s = n, d = 0;
         if (e < e0) {
@@ -309,6 +320,11 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
             col[e] = (int32_t)d;
             if (col_t) col_t[e] = (int32_t)d;
             if (s == d) atomicOr(flags, 1);
+            const uint32_t a = (uint32_t)s, b = (uint32_t)d;
+            f0 += (unsigned long long)pair_mix(a, b, 0x9E3779B1u, 0x85EBCA77u);
+            f0 -= (unsigned long long)pair_mix(b, a, 0x9E3779B1u, 0x85EBCA77u);
+            f1 += (unsigned long long)pair_mix(a, b, 0x165667B1u, 0xD3A2646Du);
+            f1 -= (unsigned long long)pair_mix(b, a, 0x165667B1u, 0xD3A2646Du);
         }
         int64_t ps = -1, pd = -1;
         if (e > 0) {
@@ -324,45 +340,84 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
             }
         }
     }
+    // block-level sums of the fingerprints, one atomic pair per CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        f0 += __shfl_xor_sync(DGCNN_FULL_MASK, f0, o);
+        f1 += __shfl_xor_sync(DGCNN_FULL_MASK, f1, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = f0; red[1][warp] = f1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned long long t = 0ull;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        if (t) atomicAdd(reinterpret_cast<unsigned long long*>(flags + 2) + threadIdx.x, t);
+    }
     if (gptr)
         for (int64_t i = tid; i <= n; i += stride)
             graph_ptr_body(batch, n, num_graphs, gptr, status, i);
 }
 
-// Processing order for the per-graph kernels: graphs by DESCENDING size (longest first
-// keeps the tail of the dynamic work queue short).  One CTA, rank sort over <= 4096 sizes.
+// After the streaming pass: dis from the row lengths (in-degree == out-degree once the
+// list is symmetric), the fingerprint verdict, and the processing order of the graphs.
+// Block 0 owns the verdict and the order; all blocks share the dis sweep.
 constexpr int kMaxOrderGraphs = 4096;
 __global__ void __launch_bounds__(1024)
-k0_graph_order(const int32_t* __restrict__ gptr, int num_graphs, int32_t* __restrict__ gorder) {
+k0_finalize(int64_t n, const int32_t* __restrict__ rowptr, float* __restrict__ dis, int32_t* flags,
+            int check_fingerprints, const int32_t* __restrict__ gptr, int num_graphs,
+            int32_t* __restrict__ gorder) {
     __shared__ int sizes[kMaxOrderGraphs];
-    if (num_graphs > kMaxOrderGraphs) {
-        for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) gorder[g] = g;
-        return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && check_fingerprints) {
+        const unsigned long long* fp = reinterpret_cast<const unsigned long long*>(flags + 2);
+        if (fp[0] != 0ull || fp[1] != 0ull) atomicOr(flags, 1);
     }
-    for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) sizes[g] = gptr[g + 1] - gptr[g];
-    __syncthreads();
-    for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) {
-        const int mine = sizes[g];
-        int rank = 0;
-        for (int h = 0; h < num_graphs; ++h) {
-            const int other = sizes[h];
-            rank += (other > mine) || (other == mine && h < g);
+    // graphs by DESCENDING size, ties by index: rank sort.  The first `ob` blocks each rank a
+    // slice of the graphs against all sizes, `parts` threads per graph.
+    const int ob = min((int)gridDim.x, 32);
+    if (gorder && num_graphs > 0 && (int)blockIdx.x < ob) {
+        if (num_graphs > kMaxOrderGraphs) {
+            if (blockIdx.x == 0)
+                for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) gorder[g] = g;
+        } else {
+            for (int g = threadIdx.x; g < num_graphs; g += blockDim.x) sizes[g] = gptr[g + 1] - gptr[g];
+            __syncthreads();
+            const int chunk = (num_graphs + ob - 1) / ob;
+            const int g0 = blockIdx.x * chunk, g1 = min(num_graphs, g0 + chunk);
+            const int cnt = max(g1 - g0, 0);
+            int parts = 1;
+            while (parts < 32 && cnt * parts * 2 <= (int)blockDim.x) parts <<= 1;
+            const int lp = 31 - __clz(parts);
+            for (int it0 = 0; it0 < cnt * parts; it0 += blockDim.x) {
+                const int item = it0 + threadIdx.x;
+                const int g = g0 + (item >> lp), part = item & (parts - 1);
+                const bool live = g < g1;
+                const int mine = live ? sizes[g] : 0;
+                int rank = 0;
+                if (live)
+                    for (int h = part; h < num_graphs; h += parts) {
+                        const int other = sizes[h];
+                        rank += (other > mine) || (other == mine && h < g);
+                    }
+                for (int o = parts >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(DGCNN_FULL_MASK, rank, o);
+                if (live && part == 0) gorder[rank] = g;
+            }
         }
-        gorder[rank] = g;
     }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dis[i] = 1.0f / sqrtf((float)(rowptr[i + 1] - rowptr[i] + 1));
 }
 
-// symmetry: every edge (s,d) must find s in row d (rows are sorted: binary search);
-// dis from the row lengths (in-degree == out-degree once symmetric)
+// exact symmetry check (optional): every edge (s,d) must find s in row d (rows are sorted:
+// binary search)
 __global__ void __launch_bounds__(256)
 k0_fast_verify(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0, int64_t n,
-               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-               float* __restrict__ dis, int32_t* flags) {
+               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int32_t* flags) {
     if (*flags & 1) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int64_t i = tid; i < n; i += stride)
-        dis[i] = 1.0f / sqrtf((float)(rowptr[i + 1] - rowptr[i] + 1));
     for (int64_t e = tid; e < e0; e += stride) {
         const int32_t s = (int32_t)src[e];
         const int64_t d = dst[e];
@@ -399,8 +454,9 @@ extern "C" int dgcnn_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t 
 extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, const int64_t* batch,
                                  int64_t num_nodes, int64_t num_graphs, int32_t* rowptr,
                                  int32_t* col, int32_t* rowptr_t, int32_t* col_t, float* dis,
-                                 int32_t* gptr, int32_t* gorder, int32_t* status, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+                                 int32_t* gptr, int32_t* gorder, int32_t* status,
+                                 int32_t exact_verify, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
     const int64_t n = num_nodes, e0 = num_edges;
     if (n < 0 || e0 < 0 || num_graphs < 0 || !rowptr || !dis) return DGCNN_ERR_INVALID_ARGUMENT;
     if (e0 > 0 && (!edge_index || !col)) return DGCNN_ERR_INVALID_ARGUMENT;
@@ -426,37 +482,37 @@ extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, c
     k0_fast_build<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, batch, n, num_graphs, rowptr,
                                                           col, rowptr_t, col_t, gptr, w.flags, status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    k0_fast_verify<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, n, rowptr, col, dis, w.flags);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-    if (gorder && num_graphs > 0) {
-        k0_graph_order<<<1, 1024, 0, st>>>(gptr, (int)num_graphs, gorder);
+    if (exact_verify) {
+        k0_fast_verify<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, n, rowptr, col, w.flags);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
-
-    // generic path: every kernel returns immediately unless the flag was raised
-    const int32_t* gate = w.flags;
-    k0_count<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, batch, n, num_graphs, w.indeg,
-                                                     transposed ? w.outdeg : nullptr, nullptr, status,
-                                                     gate);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-
-    dim3 scan_grid((unsigned)w.nb, transposed ? 2 : 1);
-    k0_scan_reduce<<<scan_grid, kScanThreads, 0, st>>>(w.indeg, w.outdeg, n, w.bsum, w.nb, gate);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-    k0_scan_top<<<transposed ? 2 : 1, 1024, 0, st>>>(w.bsum, w.nb, gate);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-    k0_scan_apply<<<scan_grid, kScanThreads, 0, st>>>(w.indeg, w.outdeg, n, w.bsum, w.nb, rowptr,
-                                                      rowptr_t, dis, gate);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-
-    if (e0 > 0) {
-        k0_fill<<<grid_for(e0, 256, 8), 256, 0, st>>>(src, dst, e0, n, rowptr, rowptr_t, w.indeg,
-                                                      w.outdeg, w.tmp_in, w.tmp_out, gate);
-        DGCNN_RETURN_IF_LAUNCH_FAILED();
-        dim3 sort_grid((unsigned)grid_for(n, 8, 8), transposed ? 2 : 1);
-        k0_sort_rows<<<sort_grid, 256, 0, st>>>(rowptr, rowptr_t, n, w.tmp_in, w.tmp_out, col, col_t,
-                                                gate);
-        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    int fin_grid = grid_for(n + 1, 1024, 1);
+    if (gorder && num_graphs > 16) {                 // enough CTAs to rank the graphs in parallel
+        const int want = (int)((num_graphs + 15) / 16 < 32 ? (num_graphs + 15) / 16 : 32);
+        if (fin_grid < want) fin_grid = want;
     }
+    k0_finalize<<<fin_grid, 1024, 0, st>>>(n, rowptr, dis, w.flags, exact_verify ? 0 : 1, gptr,
+                                           gorder ? (int)num_graphs : 0, gorder);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+
+    // generic path: one cooperative launch that returns at once unless the flag was raised
+    GenericArgs ga;
+    ga.src = src; ga.dst = dst; ga.e0 = e0; ga.batch = batch; ga.n = n; ga.num_graphs = num_graphs;
+    ga.indeg = w.indeg; ga.outdeg = transposed ? w.outdeg : nullptr; ga.bsum = w.bsum; ga.nb = w.nb;
+    ga.rowptr = rowptr; ga.rowptr_t = rowptr_t; ga.dis = dis;
+    ga.tmp_in = w.tmp_in; ga.tmp_out = w.tmp_out; ga.col = col; ga.col_t = col_t;
+    ga.status = status; ga.gate = w.flags;
+    static int coop_blocks = 0;                      // co-resident CTAs per SM, queried once
+    if (coop_blocks == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0_generic, kScanThreads, 0) != cudaSuccess ||
+            per_sm < 1)
+            return DGCNN_ERR_CUDA;
+        coop_blocks = per_sm > 4 ? 4 : per_sm;
+    }
+    void* args[] = {&ga};
+    if (cudaLaunchCooperativeKernel((const void*)k0_generic, dim3(DGCNN_NUM_SMS * coop_blocks),
+                                    dim3(kScanThreads), args, 0, st) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
     return DGCNN_OK;
 }

@@ -22,6 +22,9 @@ ACT_NONE, ACT_TANH = 0, 1
 GRAPH_BAD_EDGE, GRAPH_BAD_BATCH, GRAPH_RANGE, GRAPH_GENERIC = 1, 2, 4, 8
 BITMAP_MAX_NODES = 1024
 STACK_MMA, STACK_FMA = 0, 1
+# K0 proves the symmetry of a sorted edge list with 2 x 64-bit multiset fingerprints; set
+# DGCNN_EXACT_SYMMETRY=1 for the exact (one binary search per edge) check instead
+EXACT_SYMMETRY_CHECK = os.environ.get("DGCNN_EXACT_SYMMETRY", "0") == "1"
 XCAT_LD = 100     # row stride (floats) of the x_cat buffer the fused forward allocates
 # implementation of the fused forward; tests flip it to cross-check the two kernels
 STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower() == "fma" else STACK_MMA
@@ -138,47 +141,47 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
         rc = lib.dgcnn_build_graph(_ptr(edge_index), e, _ptr(batch), n, b,
                                    _ptr(rowptr), _ptr(col), _ptr(rowptr_t), _ptr(col_t),
                                    _ptr(dis), _ptr(gptr), _ptr(gorder), _ptr(status),
-                                   _ptr(ws), ws.numel(), _stream())
+                                   int(EXACT_SYMMETRY_CHECK), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "build_graph")
-    LAUNCHES["build_graph"] += (8 if e > 0 else 6) + (1 if batch is not None and b > 0 else 0)
+    LAUNCHES["build_graph"] += 3 + (1 if EXACT_SYMMETRY_CHECK else 0)
     graph = Graph(rowptr, col, rowptr_t, col_t, dis, gptr, gorder, status, n, b, int(max_nodes))
     if batch is not None and b > 0 and 0 < int(max_nodes) <= BITMAP_MAX_NODES:
-        _build_bitmaps(graph, transpose)
+        _build_bitmaps(graph, transpose, batch)
     return graph
 
 
-def _build_bitmaps(graph: Graph, transpose: bool) -> None:
-    """K0b: adjacency bitmaps of A_hat (and of A_hat^T unless K0 proved symmetry)."""
+def _build_bitmaps(graph: Graph, transpose: bool, batch: Optional[Tensor] = None) -> None:
+    """K0b: adjacency bitmaps of A_hat (and of A_hat^T unless K0 proved symmetry), the
+    fragment-major copy for the tensor-core kernels and the work descriptors; one call."""
     lib = _lib.load_library()
     dev = graph.rowptr.device
     n, b, mx = graph.num_nodes, graph.num_graphs, graph.max_nodes
     words = int(lib.dgcnn_graph_bitmap_words(n, b, mx))
-    i32 = dict(dtype=torch.int32, device=dev)
-
     fwords = int(lib.dgcnn_graph_fragmap_words(n, b, mx))
-
-    def run(rowptr, col, gate, frag):
-        bitmap = torch.empty(words, **i32)
-        bmoff = torch.empty(b + 1, **i32)
-        gflags = torch.empty(b, **i32)
-        fragmap = torch.empty(fwords, **i32) if frag else None
-        fgoff = torch.empty(b + 1, **i32) if frag else None
-        gdesc = torch.empty(b, 4, **i32) if frag else None
-        with torch.cuda.device(dev):
-            rc = lib.dgcnn_build_bitmaps(_ptr(rowptr), _ptr(col), _ptr(graph.gptr), n, b, mx,
-                                         _ptr(bitmap), words, _ptr(bmoff), _ptr(gflags),
-                                         _ptr(fragmap), fwords if frag else 0, _ptr(fgoff),
-                                         _ptr(graph.gorder), _ptr(gdesc),
-                                         _ptr(graph.status) if gate else None, GRAPH_GENERIC,
-                                         _stream())
-        _lib.check(rc, "build_bitmaps")
-        LAUNCHES["build_bitmaps"] += 3 if frag else 2
-        return bitmap, bmoff, gflags, fragmap, fgoff, gdesc
-
-    graph.bitmap, graph.bmoff, graph.gflags, graph.fragmap, graph.fgoff, graph.gdesc = \
-        run(graph.rowptr, graph.col, False, True)
-    if transpose and graph.rowptr_t is not None:
-        graph.bitmap_t, graph.bmoff_t, graph.gflags_t, _, _, _ = run(graph.rowptr_t, graph.col_t, True, False)
+    i32 = dict(dtype=torch.int32, device=dev)
+    transpose = transpose and graph.rowptr_t is not None
+    both = torch.empty((2 if transpose else 1) * words, **i32)
+    graph.bitmap = both[:words]
+    graph.bitmap_t = both[words:] if transpose else None
+    graph.bmoff = torch.empty(b + 1, **i32)
+    graph.bmoff_t = graph.bmoff if transpose else None          # same sizes, same offsets
+    graph.gflags = torch.empty(b, **i32)
+    graph.gflags_t = torch.empty(b, **i32) if transpose else None
+    graph.fragmap = torch.empty(fwords, **i32)
+    graph.fgoff = torch.empty(b + 1, **i32)
+    graph.gdesc = torch.empty(b, 4, **i32)
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_build_bitmaps(_ptr(graph.rowptr), _ptr(graph.col),
+                                     _ptr(graph.rowptr_t) if transpose else None,
+                                     _ptr(graph.col_t) if transpose else None,
+                                     _ptr(graph.gptr), _ptr(batch), n, b, mx,
+                                     _ptr(graph.bitmap), _ptr(graph.bitmap_t), words,
+                                     _ptr(graph.bmoff), _ptr(graph.gflags), _ptr(graph.gflags_t),
+                                     _ptr(graph.fragmap), fwords, _ptr(graph.fgoff),
+                                     _ptr(graph.gorder), _ptr(graph.gdesc),
+                                     _ptr(graph.status), GRAPH_GENERIC, _stream())
+    _lib.check(rc, "build_bitmaps")
+    LAUNCHES["build_bitmaps"] += 3
 
 
 def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:

@@ -86,6 +86,11 @@ const char* dgcnn_status_string(int status);
  *                 per-graph kernels (KS, KSB) drain their work queue
  *   status  optional device int32, OR-ed with DGCNN_GRAPH_* on bad input
  * Only the first rowptr[N] entries of col are meaningful.
+ * Fast path: a strictly (src,dst)-sorted, loop-free, SYMMETRIC list (what TUDataset/PyG
+ * batches are) is converted in one streaming pass; symmetry is established by two 64-bit
+ * multiset fingerprints of {(s,d)} vs {(d,s)} (false accept ~2^-64), or, with
+ * exact_verify != 0, by one binary search per edge (slower, exact).  Anything else takes
+ * the generic count/scan/fill/sort pipeline; the choice is made on the device.
  * Limits: N, E < 2^31.
  * ------------------------------------------------------------------------ */
 size_t dgcnn_build_graph_workspace_bytes(int64_t num_nodes, int64_t num_edges);
@@ -93,13 +98,15 @@ int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges,
                       const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
                       int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
                       float* dis, int32_t* gptr, int32_t* gorder, int32_t* status,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      int32_t exact_verify, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * K0b  per-graph adjacency bitmaps (with GCNConv's self loop) for the fused per-graph
- * kernels KS / KSB, built once per batch from a CSR of K0 (call it a second time with
- * rowptr_t/col_t for A_hat^T; gate_word/gate_mask let that call be skipped ON THE DEVICE
- * when K0 proved the batch symmetric: pass K0's status word and DGCNN_GRAPH_GENERIC).
+ * kernels KS / KSB, built once per batch from the CSRs of K0: `bitmap` from rowptr/col and,
+ * when bitmap_t is given, `bitmap_t` (A_hat^T) from rowptr_t/col_t -- that half is skipped ON
+ * THE DEVICE when K0 proved the batch symmetric (gate_word/gate_mask: pass K0's status word
+ * and DGCNN_GRAPH_GENERIC; a skipped bitmap_t stays all-zero).  Both share bmoff.
+ * batch (optional, the reference's int64 [N] vector) saves a search per node row.
  *   bitmap  uint32[dgcnn_graph_bitmap_words(N, B, max_nodes)]; graph g owns
  *           np_g * ceil(np_g/32) words at bmoff[g], np_g = n_g rounded up to 16
  *   bmoff   int32[B+1];  gflags int32[B]: bit 0 duplicate edges, bit 1 no bitmap (too large)
@@ -115,9 +122,12 @@ int64_t dgcnn_graph_bitmap_words(int64_t num_nodes, int64_t num_graphs, int64_t 
  *   {graph, first node, nodes, fgoff[graph]} in the order of gorder (K0: descending size;
  *   NULL = natural order) -- what the tensor-core KS kernel reads to deal graphs to SMs. */
 int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_graphs, int64_t max_nodes);
-int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col, const int32_t* gptr,
+int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
+                        const int32_t* rowptr_t, const int32_t* col_t,
+                        const int32_t* gptr, const int64_t* batch,
                         int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
-                        uint32_t* bitmap, int64_t bitmap_words, int32_t* bmoff, int32_t* gflags,
+                        uint32_t* bitmap, uint32_t* bitmap_t, int64_t bitmap_words,
+                        int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,
                         uint32_t* fragmap, int64_t fragmap_words, int32_t* fgoff,
                         const int32_t* gorder, int32_t* gdesc,
                         const int32_t* gate_word, int32_t gate_mask, void* stream);

@@ -50,9 +50,15 @@ def timed(fn):
 with torch.enable_grad():                       # training-mode graph: also A_hat^T for backward
     g0 = model.build_graph(data)
     t_k0 = timed(lambda: model.build_graph(data))
+    t_k0a = timed(lambda: ops.build_graph(data.edge_index, data.batch, data.x.size(0), hb.num_graphs,
+                                          transpose=True, max_nodes=0))
+    t_k0n = timed(lambda: ops.build_graph(data.edge_index, data.batch, data.x.size(0), hb.num_graphs,
+                                          transpose=False, max_nodes=data.max_nodes))
 with torch.no_grad():
     print("workload", name, "N", hb.num_nodes, "E", hb.num_edges, "max_nodes", data.max_nodes)
     print("K0 build_graph  us mean/min: %.1f %.1f" % t_k0)
+    print("   K0 only (no bitmaps)     : %.1f %.1f" % t_k0a)
+    print("   K0 + K0b, no transpose   : %.1f %.1f" % t_k0n)
     print("KS hot_path fwd us mean/min: %.1f %.1f" % timed(lambda: model.hot_path(data.x, g0)))
     pooled, xcat, perm = model.hot_path(data.x, g0)
     dp = torch.randn_like(pooled)

@@ -63,8 +63,8 @@ def test_argument_validation_without_touching_cuda():
     assert lib.dgcnn_graph_conv_fwd(None, 8, 8, None, None, None, None, None, None, 32, 32, 5, 0, 0, None) == INVALID
     assert lib.dgcnn_graph_conv_fwd(None, 8, 8, None, None, None, None, None, None, 32, 32, 0, 0, 0, None) == 0
     # K0: missing workspace
-    assert lib.dgcnn_build_graph(1, 4, 1, 3, 1, 1, 1, None, None, 1, 1, None, None, None, 0, None) == WORKSPACE
-    assert lib.dgcnn_build_graph(None, -1, None, 3, 1, None, None, None, None, None, None, None, None, None, 0, None) == INVALID
+    assert lib.dgcnn_build_graph(1, 4, 1, 3, 1, 1, 1, None, None, 1, 1, None, None, 0, None, 0, None) == WORKSPACE
+    assert lib.dgcnn_build_graph(None, -1, None, 3, 1, None, None, None, None, None, None, None, None, 0, None, 0, None) == INVALID
     # K2: k < 1
     assert lib.dgcnn_sort_pool_fwd(None, 97, 97, None, 10, 2, 0, 0, None, None, None, 0, None) == INVALID
     assert lib.dgcnn_sort_pool_fwd(None, 97, 97, None, 0, 0, 30, 0, None, None, None, 0, None) == 0

@@ -74,12 +74,13 @@ SIGNATURES = {
                                   c_int32, c_int32, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "dgcnn_stack_bwd_supported": (c_int32, [c_int32, c_int64]),
+    "dgcnn_stack_bwd_set_trace": (None, [c_void_p]),
     "dgcnn_stack_num_params": (c_int64, [c_int32]),
     "dgcnn_stack_bwd_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64]),
     "dgcnn_stack_bwd": (c_int32, [c_void_p, c_void_p, c_int32,
                                   c_void_p, c_int64, c_void_p, c_int64,
                                   c_int32, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int64,
                                   c_int64, c_void_p, c_void_p, c_void_p,

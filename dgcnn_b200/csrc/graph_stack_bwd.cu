@@ -341,7 +341,8 @@ size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_
 int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
                         int64_t ldc, const float* x, int64_t ldx, int32_t f, const int32_t* rowptr_t,
                         const int32_t* col_t, const float* dis, const int32_t* gptr,
-                        const int32_t* gorder, const uint32_t* bitmap, const int32_t* bmoff,
+                        const int32_t* gorder, const int32_t* gdesc, const uint32_t* fragmap,
+                        const uint32_t* bitmap, const int32_t* bmoff,
                         const int32_t* gflags, const uint32_t* bitmap_t, const int32_t* bmoff_t,
                         const int32_t* gflags_t, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                         const float* w2, const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
@@ -379,6 +380,7 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
                                const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                                int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
                                const float* dis, const int32_t* gptr, const int32_t* gorder,
+                               const int32_t* gdesc, const uint32_t* fragmap,
                                const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
                                const uint32_t* bitmap_t, const int32_t* bmoff_t,
                                const int32_t* gflags_t,
@@ -409,7 +411,7 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
         return DGCNN_ERR_WORKSPACE;
     if (variant == DGCNN_STACK_MMA)
         return dgcnn_stack_bwd_mma(dpooled, perm, k, xcat, ldc, x, ldx, num_features, rowptr_t, col_t, dis,
-                                   gptr, gorder, bitmap, bmoff, gflags, bitmap_t, bmoff_t, gflags_t,
+                                   gptr, gorder, gdesc, fragmap, bitmap, bmoff, gflags, bitmap_t, bmoff_t, gflags_t,
                                    num_nodes, num_graphs, max_nodes, w2, w3, w4, norm, grads, status, workspace, st);
 
     StackBwdParams p{};

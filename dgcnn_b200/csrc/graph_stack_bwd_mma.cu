@@ -25,6 +25,8 @@ struct StackBwdMmaParams {
     const float* x; int64_t ldx; int f;
     const int32_t* rowptr_t; const int32_t* col_t; const float* dis; const int32_t* gptr;
     const int32_t* gorder; int num_graphs;
+    const int32_t* gdesc;            // K0b work descriptors {graph, first node, nodes, fgoff}
+    const uint32_t* fragmap;         // K0b fragment-major A_hat (== A_hat^T when K0 proved symmetry)
     const uint32_t* bitmap; const int32_t* bmoff; const int32_t* gflags;
     const uint32_t* bitmap_t; const int32_t* bmoff_t; const int32_t* gflags_t;
     const float* w2; const float* w3; const float* w4;
@@ -33,7 +35,9 @@ struct StackBwdMmaParams {
     float* gws;          // [N][32] fp32: gradient w.r.t. the current layer's output (L2-resident)
     int32_t* counter;
     int32_t* status;
+    int64_t* trace;      // optional debug timeline [num_graphs][16] (dgcnn_stack_bwd_set_trace)
 };
+#define KSB_TRACE(slot) do { if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
 
 struct GradOffsetsM { int w1, b1, w2, b2, w3, b3, w4, b4, total; };
 
@@ -53,13 +57,14 @@ __host__ __device__ inline GradOffsetsM grad_offsets_m(int f) {
 }
 
 // CTA-wide: W2^T, W3^T hi/lo planes [k][c] (B operand of dx = dh W), w4
-struct BwdShared { int w2p, w3p, w4, total; };
-__host__ __device__ inline BwdShared bwd_shared_layout() {
+struct BwdShared { int w2p, w3p, w4, acc, total; };
+__host__ __device__ inline BwdShared bwd_shared_layout(int f) {
     BwdShared L;
     int o = 0;
     L.w2p = o; o += 2 * kHid * kWPad * 2;
     L.w3p = o; o += 2 * kHid * kWPad * 2;
     L.w4 = o; o += kHid * 4;
+    L.acc = o; o += al16(grad_offsets_m(f).total * 4);   // the CTA's running parameter-gradient sum
     L.total = o;
     return L;
 }
@@ -74,7 +79,10 @@ __host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np) {
     L.P = o; o += 2 * kHid * L.S * 2;                    // hi/lo planes of r * dpre * scale
     L.DH = o; o += 2 * kHid * L.S * 2;                   // hi/lo planes of dh * scale
     L.vpl = o; o += al16(2 * L.S * 2);
-    L.bm = o; o += al16(np * wpr * 4);
+    {
+        const int plain = np * wpr * 4, frag = frag_words(np) * 4;
+        L.bm = o; o += al16(plain > frag ? plain : frag);
+    }
     L.cs = o; o += al16(np * 4);
     L.rs = o; o += al16(np * 4);
     L.hv = o; o += al16(np * 4);
@@ -86,14 +94,14 @@ __host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np) {
     return L;
 }
 
-__host__ __device__ inline int bwd_quad_bytes() {
-    return ((kSmemBudget - 1024 - bwd_shared_layout().total) / kQuads) & ~15;
+__host__ __device__ inline int bwd_quad_bytes(int f) {
+    return ((kSmemBudget - 1024 - bwd_shared_layout(f).total) / kQuads) & ~15;
 }
 
 __host__ __device__ inline int bwd_quads_needed(int f, int n) {
     const int np = (n + 15) & ~15, tiles = np >> 4;
     int q = tiles <= 4 ? 1 : (tiles <= 8 ? 2 : 4);
-    const int need = bwd_team_layout(f, np < 16 ? 16 : np).total, qb = bwd_quad_bytes();
+    const int need = bwd_team_layout(f, np < 16 ? 16 : np).total, qb = bwd_quad_bytes(f);
     while (q < kQuads && need > q * qb) q <<= 1;
     return q;
 }
@@ -110,7 +118,7 @@ __device__ __forceinline__ float reduce_rows_t(const float* red, int nwarps, int
 //   - if wp: dx = dh W via the fragments, unscaled, + pooled gradient of the slice -> Gout
 __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, const __half* __restrict__ wp,
                                               __half* __restrict__ DH, float* __restrict__ Gout,
-                                              const uint32_t* __restrict__ bm, int wpr, int n, int S,
+                                              const uint32_t* __restrict__ bm, bool frag, int wpr, int n, int S,
                                               bool dup, const int* __restrict__ rp,
                                               const int32_t* __restrict__ col_g, int base,
                                               const float* __restrict__ cs, const int* __restrict__ rank,
@@ -126,7 +134,52 @@ __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, cons
         float acc[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        if (!dup) {
+        if (!dup && frag) {
+            // fragment-major adjacency (rotate + mask -> {0, 2.0}), B fragments by ldmatrix from
+            // the [channel][node] planes; full groups of four blocks run branch-free
+            const int G = (tiles + 3) >> 2, j = lane >> 3;
+            uint32_t addr = smem_u32(P) + (uint32_t)((((j >> 1) * 8 + (lane & 7)) * S + (j & 1) * 8) * 2);
+            const uint32_t nt2 = (uint32_t)(16 * S * 2), lo = (uint32_t)(kHid * S * 2);
+            const uint32_t* fb = bm + mt * G * 32 + lane;
+            uint32_t w = fb[0];
+            auto block = [&](int q) {
+                uint32_t a[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    a[i] = __funnelshift_l(w, w, (14 - (4 * q + i)) & 31) & 0x40004000u;
+                const uint32_t ad = addr + (uint32_t)(q * 32);
+                uint32_t b[4][4];
+                ldsm_x4(ad, b[0][0], b[0][1], b[0][2], b[0][3]);                 // hi, channels 0..15
+                ldsm_x4(ad + nt2, b[1][0], b[1][1], b[1][2], b[1][3]);           // hi, channels 16..31
+                ldsm_x4(ad + lo, b[2][0], b[2][1], b[2][2], b[2][3]);            // lo, channels 0..15
+                ldsm_x4(ad + lo + nt2, b[3][0], b[3][1], b[3][2], b[3][3]);      // lo, channels 16..31
+                mma_fp16(acc[0], a, b[0][0], b[0][1]);
+                mma_fp16(acc[1], a, b[0][2], b[0][3]);
+                mma_fp16(acc[2], a, b[1][0], b[1][1]);
+                mma_fp16(acc[3], a, b[1][2], b[1][3]);
+                mma_fp16(acc[0], a, b[2][0], b[2][1]);
+                mma_fp16(acc[1], a, b[2][2], b[2][3]);
+                mma_fp16(acc[2], a, b[3][0], b[3][1]);
+                mma_fp16(acc[3], a, b[3][2], b[3][3]);
+            };
+            for (int grp = 0; grp < G; ++grp, addr += 128) {
+                const uint32_t wn = grp + 1 < G ? fb[(grp + 1) * 32] : 0u;
+                const int nb = tiles - grp * 4;
+                if (__any_sync(DGCNN_FULL_MASK, w != 0u)) {
+                    if (nb >= 4) {
+                        block(0); block(1); block(2); block(3);
+                    } else {
+#pragma unroll 1
+                        for (int q = 0; q < nb; ++q) block(q);
+                    }
+                }
+                w = wn;
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {                      // A was {0, 2}
+                acc[nt][0] *= 0.5f; acc[nt][1] *= 0.5f; acc[nt][2] *= 0.5f; acc[nt][3] *= 0.5f;
+            }
+        } else if (!dup) {
             for (int kt = 0; kt < tiles; ++kt) {
                 uint32_t a[4];
                 if (!adj_fragment(bm, wpr, row0, kt, t, a)) continue;
@@ -214,22 +267,23 @@ __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, cons
 }
 
 __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, const Team& tm, int gi,
-                                                  const unsigned char* shraw, const uint32_t* gbm,
-                                                  const int32_t* gbo, const int32_t* gfl) {
+                                                  int base, int n,
+                                                  int fgoff, const unsigned char* shraw,
+                                                  const uint32_t* gbm, const int32_t* gbo,
+                                                  const int32_t* gfl, bool frag) {
     const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
     const int nthreads = tm.nthreads, nwarps = tm.nwarps;
     const int f = p.f;
     const GradOffsetsM GO = grad_offsets_m(f);
-    const BwdShared SL = bwd_shared_layout();
+    const BwdShared SL = bwd_shared_layout(f);
     const __half* w2p = reinterpret_cast<const __half*>(shraw + SL.w2p);
     const __half* w3p = reinterpret_cast<const __half*>(shraw + SL.w3p);
     const float* w4s = reinterpret_cast<const float*>(shraw + SL.w4);
-    float* out = p.partials + (int64_t)gi * GO.total;
-
-    const int base = p.gptr[gi];
-    const int n = p.gptr[gi + 1] - base;
+    // The team leaves this graph's parameter-gradient vector in `sacc` (every entry is
+    // written exactly once below); the CTA adds the vectors of a pass in team order.
     if (n == 0) {
-        for (int idx = tid; idx < GO.total; idx += nthreads) out[idx] = 0.f;
+        float* sacc0 = reinterpret_cast<float*>(tm.smem + bwd_team_layout(f, 16).sacc);
+        for (int idx = tid; idx < GO.total; idx += nthreads) sacc0[idx] = 0.f;
         return;
     }
     const int keep = min(n, p.k);
@@ -259,8 +313,15 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     const float* dp = p.dpooled + (int64_t)gi * p.k * kCat;
     const int32_t* perm_g = p.perm + (int64_t)gi * p.k;
 
+    if (p.trace && tm.tid == 0) {
+        uint32_t smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[(int64_t)gi * 16 + 15] = ((int64_t)smid << 32) | (uint32_t)(tm.nthreads | (n << 12));
+    }
+    KSB_TRACE(0);
     // ---- phase 0: bitmap, coefficients, inverse permutation, gradient scale -----------------
-    load_bitmap(gbm + gbo[gi], bm, np * wpr, tid, nthreads);
+    if (frag) load_bitmap(p.fragmap + fgoff, bm, frag_words(np), tid, nthreads);
+    else load_bitmap(gbm + gbo[gi], bm, np * wpr, tid, nthreads);
     for (int j = tid; j < np; j += nthreads) {
         const float d = j < n ? p.dis[base + j] : 0.f;
         cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
@@ -269,9 +330,19 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     }
     if (dup)
         for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr_t[base + j] - e0;
-    for (int idx = tid; idx < GO.total; idx += nthreads) sacc[idx] = 0.f;
     float amax = 0.f;
-    for (int idx = tid; idx < keep * kCat; idx += nthreads) amax = fmaxf(amax, fabsf(dp[idx]));
+    {   // eight loads in flight per thread: the sweep is pure memory latency
+        const int total = keep * kCat;
+        int idx = tid;
+        for (; idx + 7 * nthreads < total; idx += 8 * nthreads) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = dp[idx + u * nthreads];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) amax = fmaxf(amax, fabsf(v[u]));
+        }
+        for (; idx < total; idx += nthreads) amax = fmaxf(amax, fabsf(dp[idx]));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(DGCNN_FULL_MASK, amax, o));
     if (lane == 0) red0[warp] = amax;
@@ -287,7 +358,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         // nothing flows into this graph (or the gradient is not finite: propagate as zeros
         // would hide it, so write NaN-free zeros only for the exact-zero case)
         const float fillv = amax > 0.f ? amax * 0.f + (amax - amax) : 0.f;   // NaN if inf/nan
-        for (int idx = tid; idx < GO.total; idx += nthreads) out[idx] = fillv;
+        for (int idx = tid; idx < GO.total; idx += nthreads) sacc[idx] = fillv;
         return;
     }
     // power-of-two scale: max |pooled gradient| -> about 2^6, leaving 2^9 of head room
@@ -295,6 +366,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     frexpf(amax, &ex);
     const float scale = ldexpf(1.f, 6 - ex), inv_scale = ldexpf(1.f, ex - 6);
 
+    KSB_TRACE(1);
     // ---- layer 4 (32 -> 1) --------------------------------------------------------------------
     {
         float dbp = 0.f;
@@ -318,6 +390,21 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         for (int w = 0; w < nwarps; ++w) s += red0[w];
         sacc[GO.b4] = s;
     }
+    if (frag) {
+        GraphCtx c;
+        c.n = n; c.np = np; c.T = tiles; c.G = (tiles + 3) >> 2; c.S = S; c.base = base; c.dup = dup;
+        c.fbm = bm; c.rp = rp; c.col_g = col_g; c.cs = cs; c.rs = rs;
+        const int g = lane >> 2, t = lane & 3;
+        for (int mt = warp; mt < tiles; mt += nwarps) {
+            float a4[4];
+            aggregate8(c, vpl, S, 1, mt, lane, a4);          // 2 x sum (A fragments are {0, 2})
+            if (t == 0) {
+                const int row0 = mt * 16 + g, row1 = row0 + 8;
+                hv[row0] = cs[row0] * a4[0] * (0.5f * inv_scale);      // dh4
+                hv[row1] = cs[row1] * a4[2] * (0.5f * inv_scale);
+            }
+        }
+    } else
     {
         const int g = lane >> 2, t = lane & 3;
         const uint32_t* v32[2] = {reinterpret_cast<const uint32_t*>(vpl),
@@ -360,12 +447,27 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     {   // dW4[k] += sum_i dh4[i] x3[i][k];  G3[i][k] = dh4[i] w4[k] + pooled gradient of x3
         float dwp = 0.f;
         const float w4k = w4s[lane];
-        for (int i = warp; i < n; i += nwarps) {
-            const float h = hv[i];
-            dwp = fmaf(h, xc[(int64_t)i * p.ldc + 2 * kHid + lane], dwp);
-            const int r = rank[i];
-            const float gp = r >= 0 ? dp[r * kCat + 2 * kHid + lane] : 0.f;
-            G[i * kHid + lane] = fmaf(h, w4k, gp);
+        for (int i0 = warp; i0 < n; i0 += 4 * nwarps) {          // four rows in flight per warp
+            float xv[4], gp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nwarps;
+                xv[u] = 0.f; gp[u] = 0.f;
+                if (i < n) {
+                    xv[u] = xc[(int64_t)i * p.ldc + 2 * kHid + lane];
+                    const int r = rank[i];
+                    if (r >= 0) gp[u] = dp[r * kCat + 2 * kHid + lane];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nwarps;
+                if (i < n) {
+                    const float h = hv[i];
+                    dwp = fmaf(h, xv[u], dwp);
+                    G[i * kHid + lane] = fmaf(h, w4k, gp[u]);
+                }
+            }
         }
         red0[warp * kHid + lane] = dwp;
     }
@@ -373,6 +475,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     if (tid < kHid) sacc[GO.w4 + tid] = reduce_rows_t(red0, nwarps, tid);
     tm.sync();
 
+    KSB_TRACE(2);
     // ---- layers 3, 2, 1 -------------------------------------------------------------------------
 #pragma unroll 1
     for (int layer = 3; layer >= 1; --layer) {
@@ -382,15 +485,30 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         {
             float dbp = 0.f;
             __half* ph = P;  __half* pl = P + kHid * S;
-            for (int i = warp; i < np; i += nwarps) {
-                float sc = 0.f;
-                if (i < n) {
-                    const float y = xc[(int64_t)i * p.ldc + offy + lane];
-                    const float d = G[i * kHid + lane] * (1.f - y * y);
-                    dbp += d;
-                    sc = rs[i] * d * scale;
+            for (int i0 = warp; i0 < np; i0 += 4 * nwarps) {     // four rows in flight per warp
+                float yv[4], gv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * nwarps;
+                    yv[u] = 0.f; gv[u] = 0.f;
+                    if (i < n) {
+                        yv[u] = xc[(int64_t)i * p.ldc + offy + lane];
+                        gv[u] = G[i * kHid + lane];
+                    }
                 }
-                store_split(ph, pl, lane * S + i, sc);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * nwarps;
+                    if (i < np) {
+                        float sc = 0.f;
+                        if (i < n) {
+                            const float d = gv[u] * (1.f - yv[u] * yv[u]);
+                            dbp += d;
+                            sc = rs[i] * d * scale;
+                        }
+                        store_split(ph, pl, lane * S + i, sc);
+                    }
+                }
             }
             red0[warp * kHid + lane] = dbp;
         }
@@ -399,10 +517,12 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             const int ob = layer == 3 ? GO.b3 : (layer == 2 ? GO.b2 : GO.b1);
             sacc[ob + tid] = reduce_rows_t(red0, nwarps, tid);
         }
+        KSB_TRACE(3 + 3 * (3 - layer));
         // B: dh planes, and G <- dx (layers 3, 2)
-        bwd_mma_layer(P, layer == 3 ? w3p : (layer == 2 ? w2p : nullptr), DH, G, bm, wpr, n, S, dup, rp,
+        bwd_mma_layer(P, layer == 3 ? w3p : (layer == 2 ? w2p : nullptr), DH, G, bm, frag, wpr, n, S, dup, rp,
                       col_g, base, cs, rank, dp, offx, inv_scale, tm);
         tm.sync();
+        KSB_TRACE(4 + 3 * (3 - layer));
         // C: parameter gradient of the layer
         if (layer >= 2) {
             // dW[c][k] = sum_i dh[i][c] x_in[i][k]: 8 output tiles (2 x 4), one per warp.
@@ -423,24 +543,41 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                     v[2] = i0 + 8 < n ? xcol[(int64_t)(i0 + 8) * p.ldc] : 0.f;
                     v[3] = i0 + 9 < n ? xcol[(int64_t)(i0 + 9) * p.ldc] : 0.f;
                 };
-                float cur[4], nxt[4];
-                fetch(0, cur);
-                for (int kt = 0; kt < tiles; ++kt) {
-                    if (kt + 1 < tiles) fetch(kt + 1, nxt);
-                    const int ia = ((16 * mc + g) * S + kt * 16 + 2 * t) >> 1;
-                    uint32_t ah[4], al[4];
-                    ah[0] = dh32[0][ia]; ah[1] = dh32[0][ia + 4 * S]; ah[2] = dh32[0][ia + 4];
-                    ah[3] = dh32[0][ia + 4 * S + 4];
-                    al[0] = dh32[1][ia]; al[1] = dh32[1][ia + 4 * S]; al[2] = dh32[1][ia + 4];
-                    al[3] = dh32[1][ia + 4 * S + 4];
-                    uint32_t bh0, bl0, bh1, bl1;
-                    split2(cur[0], cur[1], bh0, bl0);
-                    split2(cur[2], cur[3], bh1, bl1);
-                    mma_f16(acc, ah, bh0, bh1);
-                    mma_f16(acc, al, bh0, bh1);
-                    mma_f16(acc, ah, bl0, bl1);
+                // x_in comes from L2: keep four k-tiles (16 loads) in flight per thread
+                constexpr int PF = 4;
+                float buf[PF][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+                for (int u = 0; u < PF; ++u) {
+                    if (u < tiles) fetch(u, buf[u]);
+                    else buf[u][0] = buf[u][1] = buf[u][2] = buf[u][3] = 0.f;
+                }
+                for (int kt0 = 0; kt0 < tiles; kt0 += PF) {
+                    float cur[PF][4];
+#pragma unroll
+                    for (int u = 0; u < PF; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) cur[u][v] = buf[u][v];
+#pragma unroll
+                    for (int u = 0; u < PF; ++u)
+                        if (kt0 + PF + u < tiles) fetch(kt0 + PF + u, buf[u]);
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        const int kt = kt0 + u;
+                        if (kt < tiles) {
+                            const int ia = ((16 * mc + g) * S + kt * 16 + 2 * t) >> 1;
+                            uint32_t ah[4], al[4];
+                            ah[0] = dh32[0][ia]; ah[1] = dh32[0][ia + 4 * S]; ah[2] = dh32[0][ia + 4];
+                            ah[3] = dh32[0][ia + 4 * S + 4];
+                            al[0] = dh32[1][ia]; al[1] = dh32[1][ia + 4 * S]; al[2] = dh32[1][ia + 4];
+                            al[3] = dh32[1][ia + 4 * S + 4];
+                            uint32_t bh0, bl0, bh1, bl1;
+                            split2(cur[u][0], cur[u][1], bh0, bl0);
+                            split2(cur[u][2], cur[u][3], bh1, bl1);
+                            mma_f16(acc, ah, bh0, bh1);
+                            mma_f16(acc, al, bh0, bh1);
+                            mma_f16(acc, ah, bl0, bl1);
+                        }
+                    }
                 }
                 float* o = sacc + ow + (16 * mc + g) * kHid + 8 * nk + 2 * t;
                 o[0] = acc[0] * inv_scale; o[1] = acc[1] * inv_scale;
@@ -454,7 +591,18 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 const int c = o & 31, k = o >> 5;
                 const float* xr = p.x + (int64_t)base * p.ldx + k;
                 float a0 = 0.f;
-                for (int i = 0; i < n; ++i) {
+                int i = 0;
+                for (; i + 8 <= n; i += 8) {                         // eight loads in flight
+                    float xv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) xv[u] = xr[(int64_t)(i + u) * p.ldx];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float dh = __half2float(dhh[c * S + i + u]) + __half2float(dhl[c * S + i + u]);
+                        a0 = fmaf(dh, xv[u], a0);
+                    }
+                }
+                for (; i < n; ++i) {
                     const float dh = __half2float(dhh[c * S + i]) + __half2float(dhl[c * S + i]);
                     a0 = fmaf(dh, xr[(int64_t)i * p.ldx], a0);
                 }
@@ -462,79 +610,89 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             }
         }
         tm.sync();
+        KSB_TRACE(5 + 3 * (3 - layer));
     }
 
-    // this graph's parameter-gradient vector
-    for (int idx = tid; idx < GO.total; idx += nthreads) out[idx] = sacc[idx];
+    KSB_TRACE(12);
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdMmaParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ int s_item[kQuads];
-    const BwdShared SL = bwd_shared_layout();
-    {
-        const int tid = threadIdx.x, nthreads = blockDim.x;
-        __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
-        __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
-        float* w4s = reinterpret_cast<float*>(smraw + SL.w4);
-        // transposed planes [k][c]: the "col" operand of dx[k] = sum_c dh[c] W[c][k]
-        for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
-            const int c = idx >> 5, k = idx & 31;
-            store_split(w2p, w2p + kHid * kWPad, k * kWPad + c, p.w2[idx]);
-            store_split(w3p, w3p + kHid * kWPad, k * kWPad + c, p.w3[idx]);
-        }
-        if (tid < kHid) w4s[tid] = p.w4[tid];
-        __syncthreads();
-    }
+    __shared__ PlanEntry s_plan[kMaxTeams];
+    __shared__ int s_count;
+    const int f = p.f;
+    const BwdShared SL = bwd_shared_layout(f);
+    const int gtotal = grad_offsets_m(f).total;
+    float* cta_acc = reinterpret_cast<float*>(smraw + SL.acc);
+    for (int idx = threadIdx.x; idx < gtotal; idx += kCtaThreads) cta_acc[idx] = 0.f;
     // A_hat^T: the forward bitmap when K0 proved the batch symmetric, else the transposed one
     const bool use_t = p.status && (*p.status & DGCNN_GRAPH_GENERIC) && p.bitmap_t;
     const uint32_t* gbm = use_t ? p.bitmap_t : p.bitmap;
     const int32_t* gbo = use_t ? p.bmoff_t : p.bmoff;
     const int32_t* gfl = use_t ? p.gflags_t : p.gflags;
+    const bool frag = !use_t && p.fragmap != nullptr;   // symmetric batch: A_hat^T == A_hat
 
-    const int quad = threadIdx.x / kQuadThreads;
-    const int qb = bwd_quad_bytes();
     unsigned char* team_base = smraw + al16(SL.total);
-    const bool can_split = p.gorder != nullptr;
-    int first = 0, nq = kQuads;
+    const int budget = kQuads * bwd_quad_bytes(f);
+    const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
+    constexpr int kWarps = kCtaThreads / 32;
+    const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
+    int next = 0, excl = 0;
 
-    for (;;) {
-        Team tm;
-        tm.tid = threadIdx.x - first * kQuadThreads;
-        tm.nthreads = nq * kQuadThreads;
-        tm.warp = tm.tid >> 5;
-        tm.nwarps = tm.nthreads >> 5;
-        tm.lane = threadIdx.x & 31;
-        tm.bar = 1 + first;
-        tm.smem = team_base + (size_t)first * qb;
-
-        if (tm.tid == 0) s_item[first] = atomicAdd(p.counter, 1);
-        tm.sync();
-        const int q = s_item[first];
-        tm.sync();
-        if (q >= p.num_graphs) break;
-        const int gi = p.gorder ? p.gorder[q] : q;
-        const int n = p.gptr[gi + 1] - p.gptr[gi];
-        if (n > p.nmax) {
-            if (tm.tid == 0 && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_BATCH);
-            continue;
-        }
-        if (can_split) {
-            const int need = bwd_quads_needed(p.f, n);
-            bool refetch = false;
-            while (need < nq) {
-                nq >>= 1;
-                if (quad >= first + nq) { first += nq; refetch = true; break; }
+    for (int pass = 0;; ++pass) {
+        if (warp_id == 0) {
+            plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
+                      [f](int np) { return bwd_team_layout(f, np).total; }, s_plan, &s_count);
+        } else if (pass == 0) {
+            const int tid = threadIdx.x - 32, nthreads = kCtaThreads - 32;
+            __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
+            __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
+            float* w4s = reinterpret_cast<float*>(smraw + SL.w4);
+            // transposed planes [k][c]: the "col" operand of dx[k] = sum_c dh[c] W[c][k]
+            for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
+                const int c = idx >> 5, k = idx & 31;
+                store_split(w2p, w2p + kHid * kWPad, k * kWPad + c, p.w2[idx]);
+                store_split(w3p, w3p + kHid * kWPad, k * kWPad + c, p.w3[idx]);
             }
-            if (refetch) continue;
-            tm.tid = threadIdx.x - first * kQuadThreads;
-            tm.nthreads = nq * kQuadThreads;
-            tm.warp = tm.tid >> 5;
-            tm.nwarps = tm.nthreads >> 5;
+            if (tid < kHid) w4s[tid] = p.w4[tid];
         }
-        bwd_process_graph(p, tm, gi, smraw, gbm, gbo, gfl);
-        tm.sync();
+        __syncthreads();                             // the plan (and, first time, the weights)
+        const int count = s_count;
+        if (count == 0) break;
+        int mine = -1;
+        for (int j = 0; j < count; ++j)
+            if (warp_id >= s_plan[j].warp0 && warp_id < s_plan[j].warp0 + s_plan[j].nwarps) mine = j;
+        if (mine >= 0) {
+            const PlanEntry e = s_plan[mine];
+            if (e.n > p.nmax) {                      // host promised this cannot happen
+                if (threadIdx.x == e.warp0 * 32 && p.status) atomicOr(p.status, DGCNN_GRAPH_BAD_BATCH);
+            } else {
+                Team tm;
+                tm.tid = threadIdx.x - e.warp0 * 32;
+                tm.nthreads = e.nwarps * 32;
+                tm.warp = tm.tid >> 5;
+                tm.nwarps = e.nwarps;
+                tm.lane = lane;
+                tm.bar = 1 + mine;
+                tm.smem = team_base + e.smem_off;
+                bwd_process_graph(p, tm, e.gi, e.base, e.n, e.fgoff, smraw, gbm, gbo, gfl, frag);
+            }
+        }
+        __syncthreads();                             // every team's vector is complete
+        // fixed order (pass by pass, team by team) on a static plan: bit-reproducible sums
+        for (int j = 0; j < count; ++j) {
+            const PlanEntry& e = s_plan[j];
+            if (e.n > p.nmax) continue;
+            const int np = max(16, (e.n + 15) & ~15);
+            const float* sacc = reinterpret_cast<const float*>(team_base + e.smem_off +
+                                                               bwd_team_layout(f, np).sacc);
+            for (int idx = threadIdx.x; idx < gtotal; idx += kCtaThreads) cta_acc[idx] += sacc[idx];
+        }
+        next += count;                               // (the next pass syncs before it re-carves)
     }
+    float* out = p.partials + (int64_t)blockIdx.x * gtotal;
+    for (int idx = threadIdx.x; idx < gtotal; idx += kCtaThreads) out[idx] = cta_acc[idx];
 }
 
 // grads[o] = sum over graphs (deterministic: fixed partition, fixed order).  Block =
@@ -569,10 +727,13 @@ stack_bwd_reduce_graphs(const float* __restrict__ partials, int parts, int total
 
 using namespace dgcnn;
 
+static int64_t* g_bwd_trace = nullptr;
+extern "C" void dgcnn_stack_bwd_set_trace(int64_t* device_buffer) { g_bwd_trace = device_buffer; }
+
 int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes) {
     if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
     const int np = (int)((max_nodes + 15) / 16 * 16);
-    return bwd_team_layout(f, np).total <= kQuads * bwd_quad_bytes() ? 1 : 0;
+    return bwd_team_layout(f, np).total <= kQuads * bwd_quad_bytes(f) ? 1 : 0;
 }
 
 size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_t num_nodes) {
@@ -583,7 +744,8 @@ size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_
 int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
                         int64_t ldc, const float* x, int64_t ldx, int32_t f, const int32_t* rowptr_t,
                         const int32_t* col_t, const float* dis, const int32_t* gptr,
-                        const int32_t* gorder, const uint32_t* bitmap, const int32_t* bmoff,
+                        const int32_t* gorder, const int32_t* gdesc, const uint32_t* fragmap,
+                        const uint32_t* bitmap, const int32_t* bmoff,
                         const int32_t* gflags, const uint32_t* bitmap_t, const int32_t* bmoff_t,
                         const int32_t* gflags_t, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                         const float* w2,
@@ -593,6 +755,7 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     p.dpooled = dpooled; p.perm = perm; p.k = k; p.xcat = xcat; p.ldc = ldc;
     p.x = x; p.ldx = ldx; p.f = f;
     p.rowptr_t = rowptr_t; p.col_t = col_t; p.dis = dis; p.gptr = gptr; p.gorder = gorder;
+    p.gdesc = gdesc; p.fragmap = fragmap;
     p.num_graphs = (int)num_graphs;
     p.bitmap = bitmap; p.bmoff = bmoff; p.gflags = gflags;
     p.bitmap_t = bitmap_t; p.bmoff_t = bmoff_t; p.gflags_t = gflags_t;
@@ -604,8 +767,9 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
         ((uintptr_t)(p.partials + (size_t)grad_offsets_m(f).total * (size_t)num_graphs) + 255) &
         ~(uintptr_t)255);
     p.status = status;
-    if (cudaMemsetAsync(p.counter, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
-    const size_t smem = (size_t)al16(bwd_shared_layout().total) + (size_t)kQuads * bwd_quad_bytes();
+    p.trace = g_bwd_trace;
+    if (!gdesc) return DGCNN_ERR_INVALID_ARGUMENT;
+    const size_t smem = (size_t)al16(bwd_shared_layout(f).total) + (size_t)kQuads * bwd_quad_bytes(f);
     if (cudaFuncSetAttribute(stack_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
@@ -614,7 +778,7 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     stack_bwd_mma_kernel<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int total = grad_offsets_m(f).total;
-    stack_bwd_reduce_graphs<<<(total + 31) / 32, 256, 0, st>>>(p.partials, (int)num_graphs, total, grads);
+    stack_bwd_reduce_graphs<<<(total + 31) / 32, 256, 0, st>>>(p.partials, (int)grid, total, grads);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

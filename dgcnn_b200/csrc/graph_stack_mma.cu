@@ -53,11 +53,6 @@ __host__ __device__ inline SharedLayout shared_layout(int f) {
     return L;
 }
 
-__host__ __device__ inline int frag_words(int np) {     // fragment-major adjacency of one graph
-    const int t = np >> 4;
-    return t * ((t + 3) >> 2) * 32;
-}
-
 // Per-graph region, sized by the graph's own padded node count np (multiple of 16).
 struct TeamLayout {
     int PA, PB, vpl, fbm, xs, cs, rs, rp, total;
@@ -94,22 +89,6 @@ __host__ __device__ inline int quads_needed(int f, int n) {
     return q;
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                        uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                          uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-
 // tanh for the hidden layers: (1 - t) / (1 + t), t = 2^(-2 log2(e) |v|); two MUFU ops, no
 // branch.  Absolute error <= ~1.5e-7 (ex2.approx is 2^-22 relative), NaN propagates.
 // The sort key (layer 4) uses tanhf.
@@ -119,13 +98,6 @@ __device__ __forceinline__ float tanh_hidden(float v) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
     return copysignf((1.0f - t) * r, v);
-}
-
-// A-fragment registers of block q (0..3) of a fragment-major adjacency word
-__device__ __forceinline__ void adj_regs(uint32_t w, int q, uint32_t (&a)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        a[i] = __funnelshift_l(w, w, (14 - (4 * q + i)) & 31) & 0x40004000u;
 }
 
 // packed hi / lo halves of (x0, x1), x0 in the low half
@@ -143,25 +115,6 @@ __device__ __forceinline__ int64_t global_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return (int64_t)t;
-}
-
-struct GraphCtx {
-    int n, np, T, G, S, base;
-    bool dup;
-    const uint32_t* fbm;            // shared: fragment-major adjacency
-    const int* rp;                  // shared: local row pointers (multigraphs only)
-    const int32_t* col_g;           // global: CSR columns of this graph (multigraphs only)
-    const float* cs;                // shared: c_j (0 on padding)
-    const float* rs;                // shared: 0.5 * r_i (0 on padding); 0.5 undoes A = {0, 2}
-};
-
-// mma.sync without `volatile`: a pure function of its operands, so that ptxas may interleave
-// the MMAs of one block with the ldmatrix of the next (the loops below are latency-bound).
-__device__ __forceinline__ void mma_fp16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-        "{%0,%1,%2,%3};\n"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // one 16x16 adjacency block (q-th of its word) times the 16x32 hi and lo feature blocks
@@ -229,69 +182,6 @@ __device__ __forceinline__ void aggregate32(const GraphCtx& c, const __half* __r
                     if (half == 0) { acc[nt][0] += 2.f * (h.x + l.x); acc[nt][1] += 2.f * (h.y + l.y); }
                     else           { acc[nt][2] += 2.f * (h.x + l.x); acc[nt][3] += 2.f * (h.y + l.y); }
                 }
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void block8(uint32_t w, int q, const uint32_t* __restrict__ hi32,
-                                       const uint32_t* __restrict__ lo32, bool live, float (&acc)[4]) {
-    uint32_t a[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        a[i] = __funnelshift_l(w, w, (14 - (4 * q + i)) & 31) & 0x40004000u;
-    const uint32_t h0 = live ? hi32[q * 8] : 0u, h1 = live ? hi32[q * 8 + 4] : 0u;
-    const uint32_t l0 = live ? lo32[q * 8] : 0u, l1 = live ? lo32[q * 8 + 4] : 0u;
-    mma_fp16(acc, a, h0, h1);
-    mma_fp16(acc, a, l0, l1);
-}
-
-// Same for single-column-per-feature planes [F' <= 8][S] (hi at pl, lo at pl + lo_off):
-// feature f of the tile's rows lands in column f of one 8-wide n-tile.
-__device__ __forceinline__ void aggregate8(const GraphCtx& c, const __half* __restrict__ pl, int lo_off,
-                                           int nf, int mt, int lane, float (&acc)[4]) {
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    const int g = lane >> 2, t = lane & 3;
-    if (!c.dup) {
-        const uint32_t* hi32 = reinterpret_cast<const uint32_t*>(pl + g * c.S) + t;
-        const uint32_t* lo32 = reinterpret_cast<const uint32_t*>(pl + lo_off + g * c.S) + t;
-        const bool live = g < nf;
-        const uint32_t* fb = c.fbm + mt * c.G * 32 + lane;
-        uint32_t w = fb[0];
-        float acc2[4] = {0.f, 0.f, 0.f, 0.f};               // second chain: halves the MMA dependency depth
-        for (int grp = 0; grp < c.G; ++grp, hi32 += 32, lo32 += 32) {
-            const uint32_t wn = grp + 1 < c.G ? fb[(grp + 1) * 32] : 0u;
-            const int nb = c.T - grp * 4;
-            if (__any_sync(DGCNN_FULL_MASK, w != 0u)) {
-                if (nb >= 4) {
-                    block8(w, 0, hi32, lo32, live, acc);
-                    block8(w, 1, hi32, lo32, live, acc2);
-                    block8(w, 2, hi32, lo32, live, acc);
-                    block8(w, 3, hi32, lo32, live, acc2);
-                } else {
-#pragma unroll 1
-                    for (int q = 0; q < nb; ++q) block8(w, q, hi32, lo32, live, acc);
-                }
-            }
-            w = wn;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] += acc2[i];
-    } else {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int row = mt * 16 + g + 8 * half;
-            if (row >= c.n) continue;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int f = 2 * t + u;
-                if (f >= nf) continue;
-                float s = 0.f;
-                for (int e = c.rp[row] - 1; e < c.rp[row + 1]; ++e) {
-                    const int j = e < c.rp[row] ? row : c.col_g[e] - c.base;
-                    s += __half2float(pl[f * c.S + j]) + __half2float(pl[lo_off + f * c.S + j]);
-                }
-                acc[2 * half + u] = 2.f * s;
             }
         }
     }
@@ -388,13 +278,6 @@ __device__ __forceinline__ void load_bias(const float* __restrict__ bias, int t,
         y[nt][0] = b.x; y[nt][1] = b.y; y[nt][2] = b.x; y[nt][3] = b.y;
     }
 }
-
-// One entry of a CTA's pass: a graph, the warps that work on it, its slice of shared memory.
-constexpr int kMaxTeams = 8;
-struct PlanEntry { int gi, base, n, fgoff, warp0, nwarps, smem_off, pad; };
-
-// rough latency (cycles) of one layer of a T-tile graph on w warps: rounds x (blocks + epilogue)
-__device__ __forceinline__ int layer_latency(int T, int w) { return ((T + w - 1) / w) * (T * 64 + 1200); }
 
 // model.py:28-35 for ONE graph, executed by one team
 __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Team& tm, const PlanEntry& e,
@@ -665,20 +548,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + 10] = global_ns();
 }
 
-// cost of a graph in "16x16 adjacency blocks": T^2 blocks per layer plus a per-row-tile
-// share (projection, epilogue, sort, copy) worth ~19 blocks
-__device__ __forceinline__ int graph_cost(int n) {
-    const int T = (max(n, 1) + 15) >> 4;
-    return T * (T + 19);
-}
-
-// The CTA's graphs.  The batch arrives in descending size (gdesc, written by K0b).  Graphs
-// that alone cost more than an SM's fair share of the batch get an SM to themselves; the rest
-// is dealt to the remaining CTAs boustrophedon-wise (s, 2S-1-s, 2S+s, ...), so that every SM
-// holds one graph of each size class.  Up to kMaxTeams of a CTA's graphs run CONCURRENTLY,
-// each on its own warps (more warps for more tiles), named barrier and slice of shared
-// memory: the per-graph work is a chain of short latency-bound phases, and the only way to
-// fill the SM is to overlap the chains of different graphs.
+// The CTA's graphs and their teams: plan_pass() in graph_mma.cuh.
 __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ PlanEntry s_plan[kMaxTeams];
@@ -697,60 +567,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdP
 
     for (int pass = 0;; ++pass) {
         if (warp_id == 0) {
-            if (pass == 0 && B > nsm) {
-                // fair share of one SM ~ (B / S) x mean cost; the median stands in for the mean
-                const int nmed = gdesc[B >> 1].z;
-                const int cand = (lane < 8 && lane < B) ? gdesc[lane].z : 0;
-                const int share = (int)(((int64_t)graph_cost(nmed) * B * 5) / (4 * nsm));
-                const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && graph_cost(cand) > share);
-                excl = min(__ffs(~big) - 1, nsm / 2);               // leading run (sizes descend)
-            }
-            excl = __shfl_sync(DGCNN_FULL_MASK, excl, 0);
-            // lane j proposes the CTA's item next + j
-            const int item = next + lane;
-            int pos;
-            if (sm < excl) {
-                pos = item == 0 ? sm : B;
-            } else {
-                const int s2 = sm - excl, n2 = nsm - excl;
-                pos = excl + item * n2 + ((item & 1) ? n2 - 1 - s2 : s2);
-            }
-            const bool valid = lane < kMaxTeams && pos < B;
-            int4 d = make_int4(0, 0, 0, 0);
-            if (valid) d = gdesc[pos];
-            const int n = d.z, np = max(16, (n + 15) & ~15), T = np >> 4;
-            const int need = valid ? team_layout(f, np).total : 0;
-            int incl = need;
-#pragma unroll
-            for (int o = 1; o < kMaxTeams; o <<= 1) {
-                const int u = __shfl_up_sync(DGCNN_FULL_MASK, incl, o);
-                if (lane >= o) incl += u;
-            }
-            // members = the leading items that fit together (the first one always does: host check)
-            const uint32_t fit = __ballot_sync(DGCNN_FULL_MASK, valid && (incl <= budget || lane == 0));
-            const int count = __ffs(~fit) - 1;
-            const bool member = lane < count;
-            // warps: one each, the spare ones to whoever has the longest layer
-            int w = member ? 1 : 0;
-            for (int spare = kWarps - count; spare > 0 && count > 0; --spare) {
-                const uint32_t lat = (member && w < T) ? (uint32_t)layer_latency(T, w) : 0u;
-                const uint32_t best = __reduce_max_sync(DGCNN_FULL_MASK, (lat << 5) | (uint32_t)(31 - lane));
-                if ((best >> 5) == 0u) break;
-                if (lane == 31 - (int)(best & 31u)) ++w;
-            }
-            int winc = w;
-#pragma unroll
-            for (int o = 1; o < kMaxTeams; o <<= 1) {
-                const int u = __shfl_up_sync(DGCNN_FULL_MASK, winc, o);
-                if (lane >= o) winc += u;
-            }
-            if (member) {
-                PlanEntry e;
-                e.gi = d.x; e.base = d.y; e.n = n; e.fgoff = d.w;
-                e.warp0 = winc - w; e.nwarps = w; e.smem_off = incl - need; e.pad = 0;
-                s_plan[lane] = e;
-            }
-            if (lane == 0) s_count = count;
+            plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
+                      [f](int np) { return team_layout(f, np).total; }, s_plan, &s_count);
         } else if (pass == 0) {
             // meanwhile the other warps stage the weights: W1 transposed fp32 (F -> 32 stays on
             // the FMA pipe), W2/W3 as hi/lo fp16 planes [cout][cin] = the MMA "col" operand

@@ -376,7 +376,8 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_bwd(_ptr(dpooled), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
                                  _ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr_t), _ptr(graph.col_t),
-                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder),
+                                 _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder), _ptr(graph.gdesc),
+                                 _ptr(graph.fragmap),
                                  _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags),
                                  _ptr(graph.bitmap_t), _ptr(graph.bmoff_t), _ptr(graph.gflags_t), n, b,
                                  int(graph.max_nodes), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), int(norm),

@@ -244,6 +244,10 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
  * (use K3/K4 when it is needed).
  * ------------------------------------------------------------------------ */
 int dgcnn_stack_bwd_supported(int32_t num_features, int64_t max_nodes);  /* 0 no, 1 MMA, 2 FMA only */
+/* Debug hook like dgcnn_stack_fwd_set_trace, for the tensor-core KSB kernel: slots 0-12 =
+ * clock64() at start / after phase 0 / after layer 4 / then (dpre, dh+dx, dW) of layers 3, 2, 1
+ * / end; slot 15 = (smid << 32 | team threads | n << 12). */
+void dgcnn_stack_bwd_set_trace(int64_t* device_buffer);
 int64_t dgcnn_stack_num_params(int32_t num_features);
 size_t dgcnn_stack_bwd_workspace_bytes(int32_t num_features, int64_t num_graphs,
                                        int64_t num_nodes);
@@ -251,6 +255,7 @@ int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
                     const float* xcat, int64_t ldc, const float* x, int64_t ldx,
                     int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
                     const float* dis, const int32_t* gptr, const int32_t* gorder,
+                    const int32_t* gdesc, const uint32_t* fragmap,
                     const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
                     const uint32_t* bitmap_t, const int32_t* bmoff_t, const int32_t* gflags_t,
                     int64_t num_nodes, int64_t num_graphs,

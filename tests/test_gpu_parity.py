@@ -511,6 +511,12 @@ STACK_CASES = [
     ("multigraph-F38-rw", [30, 90], 38, 30.0, False, 20, 1),
     ("rw-norm", [50, 60, 10], 3, 5.0, True, 10, 1),
     ("large-n-480", [480, 100], 4, 20.0, True, 130, 0),
+    # per-CTA plan of the tensor-core kernels (graph_mma.cuh plan_pass): more graphs than one
+    # pass holds (8 teams x 148 CTAs), a giant that gets an SM of its own, and graphs so large
+    # that shared memory, not the team count, ends a pass
+    ("plan-many-small", [1 + (i * 7) % 40 for i in range(1500)], 3, 3.0, True, 10, 0),
+    ("plan-giant-alone", [480] + [12 + (i % 20) for i in range(300)], 2, 5.0, True, 30, 0),
+    ("plan-smem-limited", [280] * 200 + [300] * 100, 1, 4.0, True, 130, 0),
 ]
 
 

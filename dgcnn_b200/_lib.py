@@ -91,7 +91,8 @@ SIGNATURES = {
                        [c_int32, c_int32, c_uint64, c_void_p] + [c_void_p] * 6 +
                        [c_void_p, c_size_t, c_void_p]),
     "dgcnn_tail_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32] + [c_void_p] * 4 + [c_int32] +
-                       [c_void_p] * 6 + [c_void_p] * 9 + [c_void_p, c_size_t, c_void_p]),
+                       [c_void_p] * 6 + [c_void_p] * 9 + [c_int32, c_void_p, c_size_t, c_void_p]),
+    "dgcnn_tail_bwd_join": (c_int32, [c_void_p]),
     "dgcnn_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_float, c_float, c_float, c_float, c_float, c_void_p]),
     "dgcnn_nll_sum": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p,

@@ -13,6 +13,8 @@
 // shuffles, separate bias/ReLU/pool kernels, cuBLAS SIMT GEMMs picked for the wrong shape)
 // that cost 5x the graph kernels once those are fused.  Here: 5 forward and 9 backward
 // launches of plain fp32 FMA kernels, every reduction in a fixed order (no float atomics).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace dgcnn {
@@ -689,15 +691,36 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     return DGCNN_OK;
 }
 
+// Side stream of the parameter-gradient chain of dgcnn_tail_bwd (overlap != 0): one per
+// device, created on first use and kept for the life of the process.
+struct SideStream { cudaStream_t stream; cudaEvent_t ev[3]; cudaEvent_t done; bool ready; };
+static SideStream g_side[64];
+static std::mutex g_side_mutex;
+
+static SideStream* side_stream() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    SideStream& s = g_side[dev];
+    if (!s.ready) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 3; ++i)
+            if (cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ready = true;
+    }
+    return &s;
+}
+
 extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, int32_t k,
                               const float* w5, const float* w6, const float* wf1, const float* wf2,
                               int32_t num_classes, const float* h1, const uint8_t* arg, const float* h2,
                               const float* h3, const uint8_t* keep, const float* logp, float* dpooled,
                               float* dw5, float* db5, float* dw6, float* db6, float* dwf1, float* dbf1,
-                              float* dwf2, float* dbf2, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              float* dwf2, float* dbf2, int32_t overlap, void* workspace,
+                              size_t workspace_bytes, void* stream) {
     const int64_t B = num_graphs;
-    if (B < 0 || k < 10 || num_classes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (B < 0 || k < 10 || num_classes < 1 || overlap < 0 || overlap > 2) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_classes > 32) return DGCNN_ERR_UNSUPPORTED;
     if (!dw5 || !db5 || !dw6 || !db6 || !dwf1 || !dbf1 || !dwf2 || !dbf2) return DGCNN_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < dgcnn_tail_workspace_bytes(B, k, num_classes))
@@ -724,9 +747,23 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
     float* part5 = ws;                          ws += 4 * DGCNN_NUM_SMS * (kC5 * kKW + kC5);
     float* slabw = ws;
 
+    // Two dependency chains: the INPUT gradients (fc2 rows -> fc1 dx -> conv6 dx -> conv5 dx ->
+    // dpooled), which the graph backward is waiting for, and the PARAMETER gradients, which only
+    // the optimizer needs.  With overlap != 0 the second chain runs on the library's side
+    // stream, forked/joined with events (capturable in a CUDA graph).
+    SideStream* side = overlap ? side_stream() : nullptr;
+    if (overlap && !side) return DGCNN_ERR_CUDA;
+    cudaStream_t sw = side ? side->stream : st;      // stream of the parameter-gradient chain
+    auto fork = [&](int i) -> bool {                 // sw waits for everything issued on st so far
+        if (!side) return true;
+        return cudaEventRecord(side->ev[i], st) == cudaSuccess &&
+               cudaStreamWaitEvent(sw, side->ev[i], 0) == cudaSuccess;
+    };
+
     tail_fc2_bwd_rows<<<grid_for(B, 8, 4), 256, 0, st>>>(dlogp, logp, keep, B, num_classes, wf2, dlogit, dz3);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    tail_fc2_bwd_params<<<(num_classes * kFc + num_classes + kFc + 31) / 32, 256, 0, st>>>(
+    if (!fork(0)) return DGCNN_ERR_CUDA;
+    tail_fc2_bwd_params<<<(num_classes * kFc + num_classes + kFc + 31) / 32, 256, 0, sw>>>(
         dlogit, h3, dz3, B, num_classes, dwf2, dbf2, dbf1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dz2 = (dz3 Wf1) * (h2 > 0):  [B,128] x [128,D1]
@@ -738,24 +775,26 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
         const int kchunk = (int)ceil_div(ceil_div(B, kDwSplits), 16) * 16;
         const int splits = (int)ceil_div(B, kchunk);
         dim3 gb((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(kFc, 64), (unsigned)splits);
-        gemm_f32<true, true, false><<<gb, 256, 0, st>>>(dz3, kFc, h2, d.D1, slabw, kFc, d.D1, (int)B, kchunk,
+        gemm_f32<true, true, false><<<gb, 256, 0, sw>>>(dz3, kFc, h2, d.D1, slabw, kFc, d.D1, (int)B, kchunk,
                                                         nullptr);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         const int total = kFc * d.D1;
-        tail_reduce_partials<<<(total + 31) / 32, 256, 0, st>>>(slabw, splits, total, total, dwf1, dwf1);
+        tail_reduce_partials<<<(total + 31) / 32, 256, 0, sw>>>(slabw, splits, total, total, dwf1, dwf1);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * (d.L2 + 2 * (kK6 - 1) + 8));
     const size_t smem_w = sizeof(float) * (kC6 * d.L2 + kC5 * (d.L1 | 1));
     if (smem_in > 48 * 1024 || smem_w > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    if (!fork(1)) return DGCNN_ERR_CUDA;             // dz2 is ready
     tail_c6_bwd_input<<<grid_for(B, 1, 4), 256, smem_in, st>>>(dz2, B, d.L1, w6, dh1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int parts6 = grid_for(B, 1, 2);
-    tail_c6_bwd_weight<<<parts6, 256, smem_w, st>>>(dz2, h1, B, d.L1, part6);
+    tail_c6_bwd_weight<<<parts6, 256, smem_w, sw>>>(dz2, h1, B, d.L1, part6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int n6 = kC6 * kC5 * kK6;
-    tail_reduce_partials<<<(n6 + kC6 + 31) / 32, 256, 0, st>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
+    tail_reduce_partials<<<(n6 + kC6 + 31) / 32, 256, 0, sw>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (!fork(2)) return DGCNN_ERR_CUDA;             // dh1 is ready
     tail_c5_bwd_input<<<grid_for(B * d.L1, 8, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const size_t smem5 = sizeof(float) * (kC5Pairs * kC5Row + 2 * kC5Pairs * kC5);
@@ -763,13 +802,26 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
                              (int)smem5) != cudaSuccess)
         return DGCNN_ERR_CUDA;
     const int parts5 = grid_for(B * d.L1, kC5Pairs, 2);
-    tail_c5_bwd_weight<<<parts5, 256, smem5, st>>>(dh1, arg, pooled, B, k, d.L1, part5);
+    tail_c5_bwd_weight<<<parts5, 256, smem5, sw>>>(dh1, arg, pooled, B, k, d.L1, part5);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int n5 = kC5 * kKW;
-    tail_reduce_partials<<<(n5 + kC5 + 31) / 32, 256, 0, st>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
+    tail_reduce_partials<<<(n5 + kC5 + 31) / 32, 256, 0, sw>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (side) {
+        if (cudaEventRecord(side->done, sw) != cudaSuccess) return DGCNN_ERR_CUDA;
+        if (overlap == 1 && cudaStreamWaitEvent(st, side->done, 0) != cudaSuccess) return DGCNN_ERR_CUDA;
+    }
     return DGCNN_OK;
 }
+
+extern "C" int dgcnn_tail_bwd_join(void* stream) {
+    SideStream* side = side_stream();
+    if (!side) return DGCNN_ERR_CUDA;
+    if (cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), side->done, 0) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    return DGCNN_OK;
+}
+
 
 extern "C" int dgcnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps,

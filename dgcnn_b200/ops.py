@@ -25,6 +25,8 @@ STACK_MMA, STACK_FMA = 0, 1
 # K0 proves the symmetry of a sorted edge list with 2 x 64-bit multiset fingerprints; set
 # DGCNN_EXACT_SYMMETRY=1 for the exact (one binary search per edge) check instead
 EXACT_SYMMETRY_CHECK = os.environ.get("DGCNN_EXACT_SYMMETRY", "0") == "1"
+# parameter gradients of the dense tail on a side stream (set DGCNN_TAIL_OVERLAP=0 to serialise)
+TAIL_OVERLAP = os.environ.get("DGCNN_TAIL_OVERLAP", "1") != "0"
 XCAT_LD = 100     # row stride (floats) of the x_cat buffer the fused forward allocates
 # implementation of the fused forward; tests flip it to cross-check the two kernels
 STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower() == "fma" else STACK_MMA
@@ -433,9 +435,28 @@ def tail_fwd(pooled: Tensor, k: int, params, training: bool, seed: int, rng_offs
     return logp, (pooled, h1, arg, h2, h3, keep)
 
 
-def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params, out_grads=None):
+class PendingTailGrads:
+    """Handle of a dgcnn_tail_bwd whose parameter-gradient chain still runs on the library's
+    side stream: keeps every buffer of the call alive; join() orders the current stream
+    after that chain (event wait, capturable) and releases them."""
+
+    def __init__(self, device, keep):
+        self.device, self._keep = device, keep
+
+    def join(self) -> None:
+        if self._keep is None:
+            return
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load_library().dgcnn_tail_bwd_join(_stream()), "tail_bwd_join")
+        self._keep = None
+
+
+def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params, out_grads=None, defer_join: bool = False):
     """KT backward -> (dpooled, [dw5, db5, dw6, db6, dwf1, dbf1, dwf2, dbf2]); `out_grads`
-    lets the caller have the eight gradients written in place (e.g. into a flat bucket)."""
+    lets the caller have the eight gradients written in place (e.g. into a flat bucket).
+    The parameter gradients are computed on a side stream, concurrently with the chain that
+    produces dpooled; with defer_join the call returns (dpooled, grads, PendingTailGrads) and
+    the caller joins after it has queued more work (the graph backward)."""
     lib = _lib.load_library()
     pooled, h1, arg, h2, h3, keep = saved
     w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
@@ -453,10 +474,14 @@ def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params, out_grads=None)
     with torch.cuda.device(dev):
         rc = lib.dgcnn_tail_bwd(_ptr(dlogp), _ptr(pooled), b, int(k), _ptr(w5), _ptr(w6), _ptr(wf1),
                                 _ptr(wf2), c, _ptr(h1), _ptr(arg), _ptr(h2), _ptr(h3), _ptr(keep),
-                                _ptr(logp), _ptr(dpooled), *[_ptr(g) for g in grads], _ptr(ws), ws.numel(),
+                                _ptr(logp), _ptr(dpooled), *[_ptr(g) for g in grads],
+                                (2 if defer_join else 1) if TAIL_OVERLAP else 0, _ptr(ws), ws.numel(),
                                 _stream())
     _lib.check(rc, "tail_bwd")
     LAUNCHES["tail_bwd"] += 12 if b > 0 else 0
+    if defer_join:
+        keep = (dlogp, logp, saved, grads, ws, dpooled, w5, w6, wf1, wf2) if TAIL_OVERLAP and b > 0 else None
+        return dpooled, grads, PendingTailGrads(dev, keep)
     return dpooled, grads
 
 

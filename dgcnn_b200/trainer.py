@@ -91,9 +91,13 @@ class FusedTrainer:
         logp, saved = ops.tail_fwd(pooled, k, self.tail_params, m.training, m._tail_seed,
                                    m._tail_rng_offset)
         _, dlogp = ops.nll_sum(logp, data.y, 1.0, True, stats=self.stats)
-        dpooled, _ = ops.tail_bwd(dlogp, logp, saved, k, self.tail_params, out_grads=self.tail_grad_views)
+        # the tail's parameter gradients run on a side stream underneath KSB; joined before
+        # the all-reduce / Adam read them
+        dpooled, _, pending = ops.tail_bwd(dlogp, logp, saved, k, self.tail_params,
+                                           out_grads=self.tail_grad_views, defer_join=True)
         ops.stack_bwd(dpooled, perm, xcat, data.x, graph, weights, k, norm,
                       out=self.grad[:self.num_stack])
+        pending.join()
         if world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
         if global_batch is None:

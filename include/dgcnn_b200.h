@@ -289,8 +289,16 @@ int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, 
                    const float* h1, const uint8_t* arg, const float* h2, const float* h3,
                    const uint8_t* keep, const float* logp,
                    float* dpooled, float* dw5, float* db5, float* dw6, float* db6,
-                   float* dwf1, float* dbf1, float* dwf2, float* dbf2,
+                   float* dwf1, float* dbf1, float* dwf2, float* dbf2, int32_t overlap,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* `overlap`: 0 = everything on `stream`.  1 = the parameter-gradient chain (dW/db of fc2, fc1,
+ * conv6, conv5) runs on a side stream owned by the library, concurrently with the
+ * input-gradient chain that produces dpooled, and is joined into `stream` before the call
+ * returns.  2 = as 1 but NOT joined: the caller goes on (e.g. with dgcnn_stack_bwd) and must call
+ * dgcnn_tail_bwd_join(stream) before it reads the eight parameter gradients or releases any
+ * buffer passed to dgcnn_tail_bwd.  Fork and join are event record/wait pairs: capturable in a
+ * CUDA graph.  One side stream per device: with overlap != 0 the call is not re-entrant. */
+int dgcnn_tail_bwd_join(void* stream);
 
 /* Adam (train.py:41,99: torch.optim.Adam defaults) on flat fp32 buffers;
  * `step` is a device int64 counter, incremented by the call; gradients are multiplied by

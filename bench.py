@@ -37,6 +37,9 @@ UNIT = "graphs/s"
 WORKLOAD = "collab"          # BASELINE.json configs[3]: the config the metric is quoted on
 RING = 4                     # distinct pre-built batches cycled through the timed steps
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+# DRAM bytes (read + write) of one stack_fwd_mma_kernel launch on COLLAB-synth bs512, from the
+# ncu --set full capture summarised in profiles/r01_stack_fwd_mma_v2.md (not measurable live)
+KS_NCU_DRAM_BYTES = 1114880 + 128512
 
 
 def parse_args():
@@ -440,8 +443,12 @@ def main():
         roofline = {"bound": "hbm",
                     "kernel": "stack_fwd_kernel (GraphConv x4 + SortPool forward, one launch)",
                     "achieved": a_fwd / t_fwd / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": a_fwd / t_fwd / 1e9 / peak, "traffic": None, "peak_source": peak_kind,
+                    "frac": a_fwd / t_fwd / 1e9 / peak, "traffic": KS_NCU_DRAM_BYTES, "peak_source": peak_kind,
                     "algorithmic_bytes": a_fwd, "launch_us": t_fwd * 1e6,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                      "capture of this kernel on this workload (profiles/r01_stack_fwd_mma_v2.md): "
+                                      "adjacency arrives as K0b bitmaps and the 41 MB of outputs stay in the "
+                                      "126 MB L2, so DRAM traffic is far BELOW the algorithmic bytes",
                     "note": "effective figure on A_fwd = sum of per-layer algorithmic bytes + SortPool "
                             "(SURVEY 8d); the fused kernel's stricter A_stack figure is in hot_path_fwd"}
     else:
@@ -452,7 +459,13 @@ def main():
                "algorithmic_bytes": a_fwd, "us": t_fwd * 1e6, "achieved_GBps": a_fwd / t_fwd / 1e9,
                "frac_of_peak": a_fwd / t_fwd / 1e9 / peak, "a_stack_bytes": a_stack,
                "a_stack_GBps": a_stack / t_fwd / 1e9, "a_stack_frac_of_peak": a_stack / t_fwd / 1e9 / peak,
-               "graph_build_us": t_k0 * 1e6, "per_layer_kernel": per_layer}
+               "graph_build_us": t_k0 * 1e6,
+               "graph_build": {"what": "K0 + K0b: int64 COO -> int32 CSR, dis, bitmaps, fragment maps, work "
+                                       "descriptors (once per batch, shared by 4 layers fwd + bwd)",
+                               "algorithmic_bytes": 24 * e, "us": t_k0 * 1e6,
+                               "achieved_GBps": 24 * e / t_k0 / 1e9,
+                               "frac_of_peak": 24 * e / t_k0 / 1e9 / peak},
+               "per_layer_kernel": per_layer}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -292,8 +292,9 @@ __device__ __forceinline__ uint32_t pair_mix(uint32_t a, uint32_t b, uint32_t k1
 //
 // Symmetry (needed for "CSR by source == CSR by target") is checked in the same pass by
 // fingerprinting: a strictly sorted list has no duplicates, so it is symmetric iff the
-// multisets {(s,d)} and {(d,s)} are equal, and two independent sums
-//   F_i = sum_e [ mix_i(s,d) - mix_i(d,s) ]   (mod 2^64)
+// multiset of upward edges {(s,d): s < d} equals the multiset of reversed downward edges
+// {(d,s): s > d}, and two independent sums
+//   F_i = sum_{s<d} mix_i(s,d) - sum_{s>d} mix_i(d,s)   (mod 2^64)
 // are both zero when they are; a non-symmetric list passes with probability ~2^-64.
 // k0_finalize raises the flag when either sum is non-zero.  (The exact check, one binary
 // search per edge, is k0_fast_verify: `exact_verify` of dgcnn_build_graph.)
@@ -320,11 +321,13 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
             col[e] = (int32_t)d;
             if (col_t) col_t[e] = (int32_t)d;
             if (s == d) atomicOr(flags, 1);
-            const uint32_t a = (uint32_t)s, b = (uint32_t)d;
-            f0 += (unsigned long long)pair_mix(a, b, 0x9E3779B1u, 0x85EBCA77u);
-            f0 -= (unsigned long long)pair_mix(b, a, 0x9E3779B1u, 0x85EBCA77u);
-            f1 += (unsigned long long)pair_mix(a, b, 0x165667B1u, 0xD3A2646Du);
-            f1 -= (unsigned long long)pair_mix(b, a, 0x165667B1u, 0xD3A2646Du);
+            // one evaluation per edge: + mix(lo, hi) for an "upward" edge (s < d), - mix(lo, hi)
+            // for a "downward" one -- the same sums as  sum mix(s,d) - sum mix(d,s)  restricted
+            // to the upward pairs, which is all that symmetry of a duplicate-free list needs
+            const uint32_t lo = (uint32_t)(s < d ? s : d), hi = (uint32_t)(s < d ? d : s);
+            const unsigned long long m0 = pair_mix(lo, hi, 0x9E3779B1u, 0x85EBCA77u);
+            const unsigned long long m1 = pair_mix(lo, hi, 0x165667B1u, 0xD3A2646Du);
+            if (s < d) { f0 += m0; f1 += m1; } else if (s > d) { f0 -= m0; f1 -= m1; }
         }
         int64_t ps = -1, pd = -1;
         if (e > 0) {
@@ -333,8 +336,11 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
             if ((uint64_t)ps >= (uint64_t)n) { atomicOr(flags, 1); continue; }
         }
         if (e < e0 && !(ps < s || (ps == s && pd < d))) atomicOr(flags, 1);   // not strictly sorted
-        if (ps < s) {
-            for (int64_t r = ps + 1; r <= s; ++r) {
+        if (ps < s) {                                  // e opens row s (and any edge-free rows before it)
+            rowptr[s] = (int32_t)e;
+            if (rowptr_t) rowptr_t[s] = (int32_t)e;
+#pragma unroll 1
+            for (int64_t r = ps + 1; r < s; ++r) {
                 rowptr[r] = (int32_t)e;
                 if (rowptr_t) rowptr_t[r] = (int32_t)e;
             }

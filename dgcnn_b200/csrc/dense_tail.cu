@@ -34,7 +34,8 @@ constexpr size_t kC5StageBytes = sizeof(float) * (kC5Pairs * kC5Row + kKW * kC5 
 // stage `count` row pairs starting at pair index pr0 into xs[pp][194]; warp w copies pairs
 // w, w+8, ...; all 7 loads of a lane are issued before the first store
 __device__ __forceinline__ void c5_stage_pairs(const float* __restrict__ pooled, int64_t pr0, int count,
-                                               int k, int L1, float* __restrict__ xs) {
+                                               int k, int L1, float* __restrict__ xs,
+                                               unsigned char* __restrict__ nonzero = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int pp = warp; pp < kC5Pairs; pp += 8) {
         float v[7];
@@ -48,10 +49,16 @@ __device__ __forceinline__ void c5_stage_pairs(const float* __restrict__ pooled,
             const int i = lane + 32 * u;
             v[u] = (live && i < kC5Row) ? src[i] : 0.f;
         }
+        bool any = false;
 #pragma unroll
         for (int u = 0; u < 7; ++u) {
             const int i = lane + 32 * u;
             if (i < kC5Row) xs[pp * kC5Row + i] = v[u];
+            any |= v[u] != 0.f;                       // NaN != 0: a NaN row is not skipped
+        }
+        if (nonzero) {
+            any = __any_sync(DGCNN_FULL_MASK, any);
+            if (lane == 0) nonzero[pp] = any ? 1 : 0;
         }
     }
 }
@@ -63,6 +70,7 @@ tail_c5_fwd(const float* __restrict__ pooled, int64_t B, int k, int L1, const fl
     float* xs = c5sm;                                   // [64][194]
     float* w5t = xs + kC5Pairs * kC5Row;                // [97][16]
     float* sb = w5t + kKW * kC5;                        // [16]
+    __shared__ unsigned char nonzero[kC5Pairs];         // SortPooling pads with all-zero rows: skip them
     for (int idx = threadIdx.x; idx < kKW * kC5; idx += 256) {
         int c = idx / kKW, i = idx - c * kKW;
         w5t[i * kC5 + c] = w5[idx];
@@ -73,15 +81,17 @@ tail_c5_fwd(const float* __restrict__ pooled, int64_t B, int k, int L1, const fl
     for (int64_t pr0 = (int64_t)blockIdx.x * kC5Pairs; pr0 < pairs; pr0 += (int64_t)gridDim.x * kC5Pairs) {
         const int count = (int)min((int64_t)kC5Pairs, pairs - pr0);
         __syncthreads();
-        c5_stage_pairs(pooled, pr0, count, k, L1, xs);
+        c5_stage_pairs(pooled, pr0, count, k, L1, xs, nonzero);
         __syncthreads();
         const float* x0 = xs + pp * kC5Row;
         const float* x1 = x0 + kKW;
         float a0[4], a1[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) a0[q] = a1[q] = sb[4 * cg + q];
+        // a warp covers 8 consecutive pairs: padding pairs are contiguous, so whole warps skip
+        const int iters = __any_sync(DGCNN_FULL_MASK, nonzero[pp] != 0) ? kKW : 0;
 #pragma unroll 4
-        for (int i = 0; i < kKW; ++i) {
+        for (int i = 0; i < iters; ++i) {
             const float4 w = *reinterpret_cast<const float4*>(w5t + i * kC5 + 4 * cg);
             const float u0 = x0[i], u1 = x1[i];
             a0[0] = fmaf(w.x, u0, a0[0]); a0[1] = fmaf(w.y, u0, a0[1]);
@@ -180,30 +190,48 @@ gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
     for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        // A tile -> As[kk][m]
+    // the next k-tile's global loads are issued before the current tile's FMAs (register
+    // double buffer): the loads come from L2 and would otherwise sit exposed between two barriers
+    constexpr int RA = (BM * BK) / 256, RB = (BN * BK) / 256;
+    float ra[RA], rb[RB];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int r = 0; r < (BM * BK) / 256; ++r) {
+        for (int r = 0; r < RA; ++r) {
             const int idx = threadIdx.x + 256 * r;
             int kk, m;
             if (A_KM) { kk = idx / BM; m = idx - kk * BM; } else { m = idx / BK; kk = idx - m * BK; }
             const int gm = m0 + m, gk = k0 + kk;
-            float v = 0.f;
-            if (gm < M && gk < kend) v = A_KM ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
-            As[kk * BMP + m] = v;
+            ra[r] = 0.f;
+            if (gm < M && gk < kend) ra[r] = A_KM ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
         }
-        // B tile -> Bs[kk][n]
 #pragma unroll
-        for (int r = 0; r < (BN * BK) / 256; ++r) {
+        for (int r = 0; r < RB; ++r) {
             const int idx = threadIdx.x + 256 * r;
             int kk, n;
             if (B_KN) { kk = idx / BN; n = idx - kk * BN; } else { n = idx / BK; kk = idx - n * BK; }
             const int gn = n0 + n, gk = k0 + kk;
-            float v = 0.f;
-            if (gn < N && gk < kend) v = B_KN ? Bm[(int64_t)gk * ldb + gn] : Bm[(int64_t)gn * ldb + gk];
-            Bs[kk * BNP + n] = v;
+            rb[r] = 0.f;
+            if (gn < N && gk < kend) rb[r] = B_KN ? Bm[(int64_t)gk * ldb + gn] : Bm[(int64_t)gn * ldb + gk];
+        }
+    };
+    if (kbeg < kend) fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int r = 0; r < RA; ++r) {
+            const int idx = threadIdx.x + 256 * r;
+            int kk, m;
+            if (A_KM) { kk = idx / BM; m = idx - kk * BM; } else { m = idx / BK; kk = idx - m * BK; }
+            As[kk * BMP + m] = ra[r];
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const int idx = threadIdx.x + 256 * r;
+            int kk, n;
+            if (B_KN) { kk = idx / BN; n = idx - kk * BN; } else { n = idx / BK; kk = idx - n * BK; }
+            Bs[kk * BNP + n] = rb[r];
         }
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[4], bv[8];

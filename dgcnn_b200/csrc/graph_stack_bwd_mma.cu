@@ -447,10 +447,10 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     {   // dW4[k] += sum_i dh4[i] x3[i][k];  G3[i][k] = dh4[i] w4[k] + pooled gradient of x3
         float dwp = 0.f;
         const float w4k = w4s[lane];
-        for (int i0 = warp; i0 < n; i0 += 4 * nwarps) {          // four rows in flight per warp
-            float xv[4], gp[4];
+        for (int i0 = warp; i0 < n; i0 += 8 * nwarps) {          // eight rows in flight per warp
+            float xv[8], gp[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u * nwarps;
                 xv[u] = 0.f; gp[u] = 0.f;
                 if (i < n) {
@@ -460,7 +460,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u * nwarps;
                 if (i < n) {
                     const float h = hv[i];
@@ -485,10 +485,10 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         {
             float dbp = 0.f;
             __half* ph = P;  __half* pl = P + kHid * S;
-            for (int i0 = warp; i0 < np; i0 += 4 * nwarps) {     // four rows in flight per warp
-                float yv[4], gv[4];
+            for (int i0 = warp; i0 < np; i0 += 8 * nwarps) {     // eight rows in flight per warp
+                float yv[8], gv[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int i = i0 + u * nwarps;
                     yv[u] = 0.f; gv[u] = 0.f;
                     if (i < n) {
@@ -497,7 +497,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int i = i0 + u * nwarps;
                     if (i < np) {
                         float sc = 0.f;
@@ -526,8 +526,26 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         // C: parameter gradient of the layer
         if (layer >= 2) {
             // dW[c][k] = sum_i dh[i][c] x_in[i][k]: 8 output tiles (2 x 4), one per warp.
-            // A = dh planes [c][node]; B = x_in straight from x_cat in HBM/L2 (fp32, split
-            // hi/lo in registers; the next k-tile's four values are fetched ahead)
+            // A = dh planes [c][node]; B = x_in.  The P planes are dead after the aggregation:
+            // the team copies x_in (its slice of x_cat, from L2, coalesced, every load in
+            // flight) into that space as fp32 [feature][S] -- one round trip instead of one per
+            // k-tile -- and the MMA loop splits it hi/lo in registers.  S = np + 8 makes the
+            // 8-byte fragment loads conflict-free per half-warp.
+            float* xin = reinterpret_cast<float*>(P);
+            for (int i0 = warp; i0 < np; i0 += 8 * nwarps) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * nwarps;
+                    v[u] = i < n ? xc[(int64_t)i * p.ldc + offx + lane] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * nwarps;
+                    if (i < np) xin[lane * S + i] = v[u];
+                }
+            }
+            tm.sync();
             const int ow = layer == 3 ? GO.w3 : GO.w2;
             const int g = lane >> 2, t = lane & 3;
             const uint32_t* dh32[2] = {reinterpret_cast<const uint32_t*>(DH),
@@ -535,78 +553,62 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             for (int tile = warp; tile < 8; tile += nwarps) {
                 const int mc = tile >> 2, nk = tile & 3;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const float* xcol = xc + offx + 8 * nk + g;          // feature column of this lane
-                auto fetch = [&](int kt, float (&v)[4]) {
-                    const int i0 = kt * 16 + 2 * t;
-                    v[0] = i0 < n ? xcol[(int64_t)i0 * p.ldc] : 0.f;
-                    v[1] = i0 + 1 < n ? xcol[(int64_t)(i0 + 1) * p.ldc] : 0.f;
-                    v[2] = i0 + 8 < n ? xcol[(int64_t)(i0 + 8) * p.ldc] : 0.f;
-                    v[3] = i0 + 9 < n ? xcol[(int64_t)(i0 + 9) * p.ldc] : 0.f;
-                };
-                // x_in comes from L2: keep four k-tiles (16 loads) in flight per thread
-                constexpr int PF = 4;
-                float buf[PF][4];
-#pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    if (u < tiles) fetch(u, buf[u]);
-                    else buf[u][0] = buf[u][1] = buf[u][2] = buf[u][3] = 0.f;
-                }
-                for (int kt0 = 0; kt0 < tiles; kt0 += PF) {
-                    float cur[PF][4];
-#pragma unroll
-                    for (int u = 0; u < PF; ++u)
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) cur[u][v] = buf[u][v];
-#pragma unroll
-                    for (int u = 0; u < PF; ++u)
-                        if (kt0 + PF + u < tiles) fetch(kt0 + PF + u, buf[u]);
-#pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        const int kt = kt0 + u;
-                        if (kt < tiles) {
-                            const int ia = ((16 * mc + g) * S + kt * 16 + 2 * t) >> 1;
-                            uint32_t ah[4], al[4];
-                            ah[0] = dh32[0][ia]; ah[1] = dh32[0][ia + 4 * S]; ah[2] = dh32[0][ia + 4];
-                            ah[3] = dh32[0][ia + 4 * S + 4];
-                            al[0] = dh32[1][ia]; al[1] = dh32[1][ia + 4 * S]; al[2] = dh32[1][ia + 4];
-                            al[3] = dh32[1][ia + 4 * S + 4];
-                            uint32_t bh0, bl0, bh1, bl1;
-                            split2(cur[u][0], cur[u][1], bh0, bl0);
-                            split2(cur[u][2], cur[u][3], bh1, bl1);
-                            mma_f16(acc, ah, bh0, bh1);
-                            mma_f16(acc, al, bh0, bh1);
-                            mma_f16(acc, ah, bl0, bl1);
-                        }
-                    }
+                const float* xcol = xin + (8 * nk + g) * S + 2 * t;      // feature column of this lane
+                for (int kt = 0; kt < tiles; ++kt) {
+                    const float2 x01 = *reinterpret_cast<const float2*>(xcol + kt * 16);
+                    const float2 x89 = *reinterpret_cast<const float2*>(xcol + kt * 16 + 8);
+                    const int ia = ((16 * mc + g) * S + kt * 16 + 2 * t) >> 1;
+                    uint32_t ah[4], al[4];
+                    ah[0] = dh32[0][ia]; ah[1] = dh32[0][ia + 4 * S]; ah[2] = dh32[0][ia + 4];
+                    ah[3] = dh32[0][ia + 4 * S + 4];
+                    al[0] = dh32[1][ia]; al[1] = dh32[1][ia + 4 * S]; al[2] = dh32[1][ia + 4];
+                    al[3] = dh32[1][ia + 4 * S + 4];
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split2(x01.x, x01.y, bh0, bl0);
+                    split2(x89.x, x89.y, bh1, bl1);
+                    mma_fp16(acc, ah, bh0, bh1);
+                    mma_fp16(acc, al, bh0, bh1);
+                    mma_fp16(acc, ah, bl0, bl1);
                 }
                 float* o = sacc + ow + (16 * mc + g) * kHid + 8 * nk + 2 * t;
                 o[0] = acc[0] * inv_scale; o[1] = acc[1] * inv_scale;
                 o[8 * kHid] = acc[2] * inv_scale; o[8 * kHid + 1] = acc[3] * inv_scale;
             }
         } else {
-            // dW1[c][k] = sum_i dh[i][c] x0[i][k], k < F (any F): FMA, dh rebuilt from its planes
+            // dW1[c][k] = sum_i dh[i][c] x0[i][k], k < F (any F): FMA, dh rebuilt from its planes.
+            // With few outputs (small F) `parts` lanes share one output and split the rows.
             const __half* dhh = DH;
             const __half* dhl = DH + kHid * S;
-            for (int o = tid; o < kHid * f; o += nthreads) {
+            const int outs = kHid * f;
+            int parts = 1;
+            while (parts < 32 && outs * parts * 2 <= nthreads) parts <<= 1;
+            const int lp = 31 - __clz(parts);
+            for (int it0 = 0; it0 < outs * parts; it0 += nthreads) {
+                const int item = it0 + tid;
+                const int o = item >> lp, part = item & (parts - 1);
+                const bool live = o < outs;
                 const int c = o & 31, k = o >> 5;
-                const float* xr = p.x + (int64_t)base * p.ldx + k;
                 float a0 = 0.f;
-                int i = 0;
-                for (; i + 8 <= n; i += 8) {                         // eight loads in flight
-                    float xv[8];
+                if (live) {
+                    const float* xr = p.x + (int64_t)base * p.ldx + k;
+                    int i = part;
+                    for (; i + 7 * parts < n; i += 8 * parts) {          // eight loads in flight
+                        float xv[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) xv[u] = xr[(int64_t)(i + u) * p.ldx];
+                        for (int u = 0; u < 8; ++u) xv[u] = xr[(int64_t)(i + u * parts) * p.ldx];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float dh = __half2float(dhh[c * S + i + u]) + __half2float(dhl[c * S + i + u]);
-                        a0 = fmaf(dh, xv[u], a0);
+                        for (int u = 0; u < 8; ++u) {
+                            const int ii = c * S + i + u * parts;
+                            a0 = fmaf(__half2float(dhh[ii]) + __half2float(dhl[ii]), xv[u], a0);
+                        }
+                    }
+                    for (; i < n; i += parts) {
+                        const int ii = c * S + i;
+                        a0 = fmaf(__half2float(dhh[ii]) + __half2float(dhl[ii]), xr[(int64_t)i * p.ldx], a0);
                     }
                 }
-                for (; i < n; ++i) {
-                    const float dh = __half2float(dhh[c * S + i]) + __half2float(dhl[c * S + i]);
-                    a0 = fmaf(dh, xr[(int64_t)i * p.ldx], a0);
-                }
-                sacc[GO.w1 + c * f + k] = a0 * inv_scale;
+                for (int q = parts >> 1; q > 0; q >>= 1) a0 += __shfl_xor_sync(DGCNN_FULL_MASK, a0, q);
+                if (live && part == 0) sacc[GO.w1 + c * f + k] = a0 * inv_scale;
             }
         }
         tm.sync();

@@ -408,16 +408,33 @@ def main():
                     fn()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
+            # the two timing events are nodes of the captured graph (external events), right
+            # before and after the kernels of fn(): the graph-launch latency stays outside
+            try:
+                a = torch.cuda.Event(enable_timing=True, external=True)
+                b_ = torch.cuda.Event(enable_timing=True, external=True)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    a.record()
+                    fn()
+                    b_.record()
+                inside = True
+            except Exception:                          # noqa: BLE001  (older torch: events around the replay)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                inside = False
             times = []
             for _ in range(reps):
                 flush.zero_()
-                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                g.replay()
-                b_.record()
+                if inside:
+                    g.replay()
+                else:
+                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    g.replay()
+                    b_.record()
                 torch.cuda.synchronize()
                 times.append(a.elapsed_time(b_))
             return statistics.mean(times) * 1e-3

@@ -84,7 +84,12 @@ constexpr int kMaxTeams = 8;
 struct PlanEntry { int gi, base, n, fgoff, warp0, nwarps, smem_off, pad; };
 
 // rough latency (cycles) of one layer of a T-tile graph on w warps: rounds x (blocks + epilogue)
-__device__ __forceinline__ int layer_latency(int T, int w) { return ((T + w - 1) / w) * (T * 64 + 1200); }
+// (float arithmetic: the plan is a serial chain on one warp, and an integer division by a
+// variable costs ~40 dependent instructions)
+__device__ __forceinline__ int layer_latency(int T, int w) {
+    const int rounds = __float2int_ru(__fdividef((float)T, (float)w) - 1e-4f);
+    return rounds * (T * 64 + 1200);
+}
 
 // cost of a graph in "16x16 adjacency blocks": T^2 blocks per layer plus a per-row-tile
 // share (projection, epilogue, sort, copy) worth ~19 blocks
@@ -102,12 +107,13 @@ __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B,
                                           int& excl, bool first_pass, int budget, int total_warps,
                                           NeedFn need_of, PlanEntry* s_plan, int* s_count) {
     const int lane = threadIdx.x & 31;
+    int4 cand = make_int4(0, 0, 0, 0);                      // the eight largest graphs
     if (first_pass && B > nsm) {
         // fair share of one SM ~ (B / S) x mean cost; the median stands in for the mean
         const int nmed = gdesc[B >> 1].z;
-        const int cand = (lane < 8 && lane < B) ? gdesc[lane].z : 0;
-        const int share = (int)(((int64_t)graph_cost(nmed) * B * 5) / (4 * nsm));
-        const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && graph_cost(cand) > share);
+        if (lane < 8 && lane < B) cand = gdesc[lane];
+        const int share = (int)fminf(1.25f * (float)graph_cost(nmed) * (float)B / (float)nsm, 2.0e9f);
+        const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && graph_cost(cand.z) > share);
         excl = min(__ffs(~big) - 1, nsm / 2);               // leading run (sizes descend)
     }
     excl = __shfl_sync(DGCNN_FULL_MASK, excl, 0);
@@ -122,7 +128,15 @@ __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B,
     }
     const bool valid = lane < kMaxTeams && pos < B;
     int4 d = make_int4(0, 0, 0, 0);
-    if (valid) d = gdesc[pos];
+    if (first_pass && sm < excl) {
+        // a graph with an SM of its own is one of the candidates just loaded: no second round trip
+        const int src = sm & 31;
+        d.x = __shfl_sync(DGCNN_FULL_MASK, cand.x, src); d.y = __shfl_sync(DGCNN_FULL_MASK, cand.y, src);
+        d.z = __shfl_sync(DGCNN_FULL_MASK, cand.z, src); d.w = __shfl_sync(DGCNN_FULL_MASK, cand.w, src);
+        if (!valid) d = make_int4(0, 0, 0, 0);
+    } else if (valid) {
+        d = gdesc[pos];
+    }
     const int n = d.z, np = max(16, (n + 15) & ~15), T = np >> 4;
     const int need = valid ? need_of(np) : 0;
     int incl = need;
@@ -135,9 +149,17 @@ __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B,
     const uint32_t fit = __ballot_sync(DGCNN_FULL_MASK, valid && (incl <= budget || lane == 0));
     const int count = __ffs(~fit) - 1;
     const bool member = lane < count;
-    // warps: one each, the spare ones to whoever has the longest layer
+    // warps: one each plus a share of the rest proportional to the graph's cost (closed form),
+    // then whatever is still spare goes, one at a time, to whoever has the longest layer
     int w = member ? 1 : 0;
-    for (int spare = total_warps - count; spare > 0 && count > 0; --spare) {
+    if (count > 0) {
+        const int cost = member ? graph_cost(n) : 0;
+        const int total = (int)__reduce_add_sync(DGCNN_FULL_MASK, (unsigned)cost);
+        if (member)
+            w = min(T, 1 + (int)((float)(total_warps - count) * (float)cost / (float)max(total, 1) - 1e-3f));
+    }
+    const int used = (int)__reduce_add_sync(DGCNN_FULL_MASK, (unsigned)w);
+    for (int spare = total_warps - used; spare > 0 && count > 0; --spare) {
         const uint32_t lat = (member && w < T) ? (uint32_t)layer_latency(T, w) : 0u;
         const uint32_t best = __reduce_max_sync(DGCNN_FULL_MASK, (lat << 5) | (uint32_t)(31 - lane));
         if ((best >> 5) == 0u) break;

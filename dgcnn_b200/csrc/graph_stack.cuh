@@ -126,17 +126,18 @@ __device__ __forceinline__ float scalar_row_sum(const float* __restrict__ val,
 
 // Fetch one graph's adjacency bitmap (built once per batch by K0b, graph_bitmap.cu) into
 // shared memory: np*wpr contiguous words, coalesced, several loads in flight per thread.
+template <int INFLIGHT = 4>
 __device__ __forceinline__ void load_bitmap(const uint32_t* __restrict__ gbm, uint32_t* __restrict__ bm,
                                             int words, int tid, int nthreads) {
-    for (int i0 = tid; i0 < words; i0 += nthreads * 4) {
-        uint32_t v[4];
+    for (int i0 = tid; i0 < words; i0 += nthreads * INFLIGHT) {
+        uint32_t v[INFLIGHT];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < INFLIGHT; ++u) {
             const int idx = i0 + u * nthreads;
             v[u] = idx < words ? gbm[idx] : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < INFLIGHT; ++u) {
             const int idx = i0 + u * nthreads;
             if (idx < words) bm[idx] = v[u];
         }

@@ -320,7 +320,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     }
     KSB_TRACE(0);
     // ---- phase 0: bitmap, coefficients, inverse permutation, gradient scale -----------------
-    if (frag) load_bitmap(p.fragmap + fgoff, bm, frag_words(np), tid, nthreads);
+    if (frag) load_bitmap<8>(p.fragmap + fgoff, bm, frag_words(np), tid, nthreads);
     else load_bitmap(gbm + gbo[gi], bm, np * wpr, tid, nthreads);
     for (int j = tid; j < np; j += nthreads) {
         const float d = j < n ? p.dis[base + j] : 0.f;

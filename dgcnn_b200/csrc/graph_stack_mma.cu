@@ -335,7 +335,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
 
     // ---- phase 0, one DRAM round trip: adjacency fragments (K0b), coefficients, inputs ----
     c.dup = (p.gflags[gi] & 1) != 0;                 // multigraph: walk the CSR instead
-    load_bitmap(p.fragmap + e.fgoff, fbm, frag_words(np), tid, nthreads);
+    load_bitmap<8>(p.fragmap + e.fgoff, fbm, frag_words(np), tid, nthreads);
     for (int j = tid; j < np; j += nthreads) {
         const float d = j < n ? p.dis[base + j] : 0.f;
         cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
@@ -488,15 +488,18 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
             const uint64_t mine = live ? comp[i] : 0ull;
             int rank = 0;
             if (live) {
-                int j = part;
+                int j = part, r1 = 0, r2 = 0, r3 = 0;                // four independent count chains
                 for (; j + 7 * parts < n; j += 8 * parts) {          // eight independent loads in flight
                     uint64_t o[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] = comp[j + u * parts];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) rank += o[u] < mine;
+                    rank += (o[0] < mine) + (o[4] < mine);
+                    r1 += (o[1] < mine) + (o[5] < mine);
+                    r2 += (o[2] < mine) + (o[6] < mine);
+                    r3 += (o[3] < mine) + (o[7] < mine);
                 }
                 for (; j < n; j += parts) rank += comp[j] < mine;
+                rank += r1 + r2 + r3;
             }
             for (int o = parts >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(DGCNN_FULL_MASK, rank, o);
             if (live && part == 0 && rank < keep) order[rank] = i;
@@ -525,14 +528,6 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
                 v[u][0] = src[lane]; v[u][1] = src[32 + lane]; v[u][2] = src[64 + lane];
             }
             v96 = xsrc[(int64_t)order[min(r0 + (lane & (R - 1)), keep - 1)] * p.ldc + 96];
-            if (p.trace && r0 == 0) {
-                if (tm.tid == 0) p.trace[(int64_t)gi * 16 + 12] = clock64();
-                float sum = v96;
-#pragma unroll
-                for (int u = 0; u < R; ++u) sum += v[u][0] + v[u][1] + v[u][2];
-                if (sum == 1.2345e-30f) p.trace[(int64_t)gi * 16 + 14] = 1;   // consume the loads
-                if (tm.tid == 0) p.trace[(int64_t)gi * 16 + 13] = clock64();
-            }
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 if (r0 + u < keep) {
@@ -554,6 +549,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdP
     __shared__ PlanEntry s_plan[kMaxTeams];
     __shared__ int s_count;
     const int64_t cta_t0 = p.trace ? global_ns() : 0;
+    const int64_t cta_c0 = p.trace ? clock64() : 0;
+    int64_t cta_c1 = 0, cta_c2 = 0;
     const int f = p.f;
     const SharedLayout SL = shared_layout(f);
     unsigned char* team_base = smraw + al16(SL.total);
@@ -577,25 +574,46 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdP
             __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
             float* w1t = reinterpret_cast<float*>(smraw + SL.w1t);
             float* w4s = reinterpret_cast<float*>(smraw + SL.misc);
-            for (int idx = tid; idx < f * kHid; idx += nthreads) {
-                int c = idx / f, k = idx - c * f;
-                w1t[k * kHid + c] = p.w1[idx];
-            }
-            for (int idx = tid; idx < kHid * kHid; idx += nthreads) {
-                const int c = idx >> 5, k = idx & 31;
-                store_split(w2p, w2p + kHid * kWPad, c * kWPad + k, p.w2[idx]);
-                store_split(w3p, w3p + kHid * kWPad, c * kWPad + k, p.w3[idx]);
-            }
-            if (tid < kHid) {
-                w4s[tid] = p.w4[tid];
-                w4s[kHid + tid] = p.b1 ? p.b1[tid] : 0.f;
-                w4s[2 * kHid + tid] = p.b2 ? p.b2[tid] : 0.f;
-                w4s[3 * kHid + tid] = p.b3 ? p.b3[tid] : 0.f;
+            {   // all global loads of a thread are issued before its first store: one round trip
+                constexpr int R = (kHid * kHid + (kCtaThreads - 32) - 1) / (kCtaThreads - 32);
+                float v2[R], v3[R], vb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int idx = tid + r * nthreads;
+                    v2[r] = idx < kHid * kHid ? p.w2[idx] : 0.f;
+                    v3[r] = idx < kHid * kHid ? p.w3[idx] : 0.f;
+                }
+                if (tid < kHid) {
+                    vb[0] = p.w4[tid];
+                    vb[1] = p.b1 ? p.b1[tid] : 0.f;
+                    vb[2] = p.b2 ? p.b2[tid] : 0.f;
+                    vb[3] = p.b3 ? p.b3[tid] : 0.f;
+                }
+                const float w1first = tid < f * kHid ? p.w1[tid] : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int idx = tid + r * nthreads;
+                    if (idx < kHid * kHid) {
+                        const int c = idx >> 5, k = idx & 31;
+                        store_split(w2p, w2p + kHid * kWPad, c * kWPad + k, v2[r]);
+                        store_split(w3p, w3p + kHid * kWPad, c * kWPad + k, v3[r]);
+                    }
+                }
+                if (tid < kHid) {
+                    w4s[tid] = vb[0]; w4s[kHid + tid] = vb[1];
+                    w4s[2 * kHid + tid] = vb[2]; w4s[3 * kHid + tid] = vb[3];
+                }
+                if (tid < f * kHid) { const int c = tid / f, k = tid - c * f; w1t[k * kHid + c] = w1first; }
+                for (int idx = tid + nthreads; idx < f * kHid; idx += nthreads) {
+                    const int c = idx / f, k = idx - c * f;
+                    w1t[k * kHid + c] = p.w1[idx];
+                }
             }
         }
         __syncthreads();                             // the plan (and, first time, the weights)
         const int count = s_count;
         if (count == 0) break;
+        if (p.trace) cta_c1 = clock64();
         // rows of `pooled` past each graph's last node: zeros (PyG's fill trick), perm -1.
         // Done by the whole CTA: a one-warp team would spend longer on this than on its graph.
         for (int j = 0; j < count; ++j) {
@@ -621,7 +639,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdP
                 tm.lane = lane;
                 tm.bar = 1 + mine;
                 tm.smem = team_base + e.smem_off;
-                if (p.trace && tm.tid == 0) p.trace[(int64_t)e.gi * 16 + 11] = cta_t0;
+                if (p.trace && tm.tid == 0) {
+                    cta_c2 = clock64();
+                    p.trace[(int64_t)e.gi * 16 + 11] = cta_t0;
+                    p.trace[(int64_t)e.gi * 16 + 12] = cta_c0;       // CTA entry
+                    p.trace[(int64_t)e.gi * 16 + 13] = cta_c1;       // plan + weights done
+                    p.trace[(int64_t)e.gi * 16 + 14] = cta_c2;       // padding rows zeroed, team starts
+                }
                 process_graph(p, tm, e, smraw);
             }
         }

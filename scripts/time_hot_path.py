@@ -32,16 +32,17 @@ def timed(fn):
             fn()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True, external=True)     # event nodes inside the graph
+    b = torch.cuda.Event(enable_timing=True, external=True)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
+        a.record()
         fn()
+        b.record()
     ts = []
     for _ in range(reps):
         flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
         g.replay()
-        b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
     return statistics.mean(ts), min(ts)

@@ -27,7 +27,8 @@ with torch.no_grad():
     g0 = model.build_graph(data)
     for _ in range(3):
         model.hot_path(data.x, g0)
-    flush.zero_()
+    if os.environ.get("TRACE_WARM", "0") != "1":
+        flush.zero_()                                  # cold L2 (data AND the kernel's instructions)
     lib.dgcnn_stack_fwd_set_trace(trace.data_ptr())
     model.hot_path(data.x, g0)
     torch.cuda.synchronize()
@@ -56,8 +57,11 @@ with open(f"gpurun_out/trace_{name}.txt", "w") as f:
     for gi in late:
         f.write(f"#   late finisher: graph {gi} n {n[gi]} threads {nthr[gi]} sm {smid[gi]} "
                 f"start {t[gi, 9] - ns0} end {t[gi, 10] - ns0} ns\n")
-    f.write(f"# gather detail (cycles, mean): sort_end->loads issued {np.mean(t[:, 12] - t[:, 7]):.0f}, "
-            f"loads issued->arrived {np.mean(t[:, 13] - t[:, 12]):.0f}, arrived->end {np.mean(t[:, 8] - t[:, 13]):.0f}\n")
+    big = int(np.argmax(n))
+    f.write(f"# CTA prologue (cycles, mean | largest graph): entry->plan+weights "
+            f"{np.mean(t[:, 13] - t[:, 12]):.0f} | {t[big, 13] - t[big, 12]}, ->padding zeroed "
+            f"{np.mean(t[:, 14] - t[:, 13]):.0f} | {t[big, 14] - t[big, 13]}, ->graph start "
+            f"{np.mean(t[:, 0] - t[:, 14]):.0f} | {t[big, 0] - t[big, 14]}\n")
     tot = t[:, 8] - t[:, 0]
     f.write(f"# sum over graphs of total cycles: {tot.sum()}  mean {tot.mean():.0f}  max {tot.max()}\n")
     for s in sorted(set(smid.tolist())):

@@ -127,7 +127,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("dgcnn_b200: nvcc not found; cannot build libdgcnn_b200.so")
     LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
     tmp = LIB_PATH.with_suffix(f".tmp{os.getpid()}.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE_DIR), "-o", str(tmp), *map(str, sources())]
+    extra = os.environ.get("DGCNN_NVCC_EXTRA", "").split()      # e.g. -DDGCNN_FWD_THREADS=768 (tuning runs)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(INCLUDE_DIR), "-o", str(tmp), *map(str, sources())]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

@@ -19,6 +19,12 @@
 
 namespace dgcnn {
 
+// threads per CTA of the backward kernel (see DGCNN_FWD_THREADS in graph_stack_mma.cu)
+#ifndef DGCNN_BWD_THREADS
+#define DGCNN_BWD_THREADS 640
+#endif
+constexpr int kBwdThreads = DGCNN_BWD_THREADS;
+
 struct StackBwdMmaParams {
     const float* dpooled; const int32_t* perm; int k;
     const float* xcat; int64_t ldc;
@@ -88,7 +94,7 @@ __host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np) {
     L.hv = o; o += al16(np * 4);
     L.rank = o; o += al16(np * 4);
     L.rp = o; o += al16((np + 1) * 4);
-    L.red = o; o += (kCtaThreads / 32) * kHid * 4;
+    L.red = o; o += (kBwdThreads / 32) * kHid * 4;
     L.sacc = o; o += al16(grad_offsets_m(f).total * 4);
     L.total = o;
     return L;
@@ -618,7 +624,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     KSB_TRACE(12);
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdMmaParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdMmaParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ PlanEntry s_plan[kMaxTeams];
     __shared__ int s_count;
@@ -626,7 +632,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdM
     const BwdShared SL = bwd_shared_layout(f);
     const int gtotal = grad_offsets_m(f).total;
     float* cta_acc = reinterpret_cast<float*>(smraw + SL.acc);
-    for (int idx = threadIdx.x; idx < gtotal; idx += kCtaThreads) cta_acc[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) cta_acc[idx] = 0.f;
     // A_hat^T: the forward bitmap when K0 proved the batch symmetric, else the transposed one
     const bool use_t = p.status && (*p.status & DGCNN_GRAPH_GENERIC) && p.bitmap_t;
     const uint32_t* gbm = use_t ? p.bitmap_t : p.bitmap;
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdM
     const int budget = kQuads * bwd_quad_bytes(f);
     const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
-    constexpr int kWarps = kCtaThreads / 32;
+    constexpr int kWarps = kBwdThreads / 32;
     const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
     int next = 0, excl = 0;
 
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdM
             plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
                       [f](int np) { return bwd_team_layout(f, np).total; }, s_plan, &s_count);
         } else if (pass == 0) {
-            const int tid = threadIdx.x - 32, nthreads = kCtaThreads - 32;
+            const int tid = threadIdx.x - 32, nthreads = kBwdThreads - 32;
             __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
             __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
             float* w4s = reinterpret_cast<float*>(smraw + SL.w4);
@@ -689,12 +695,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_bwd_mma_kernel(StackBwdM
             const int np = max(16, (e.n + 15) & ~15);
             const float* sacc = reinterpret_cast<const float*>(team_base + e.smem_off +
                                                                bwd_team_layout(f, np).sacc);
-            for (int idx = threadIdx.x; idx < gtotal; idx += kCtaThreads) cta_acc[idx] += sacc[idx];
+            for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) cta_acc[idx] += sacc[idx];
         }
         next += count;                               // (the next pass syncs before it re-carves)
     }
     float* out = p.partials + (int64_t)blockIdx.x * gtotal;
-    for (int idx = threadIdx.x; idx < gtotal; idx += kCtaThreads) out[idx] = cta_acc[idx];
+    for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) out[idx] = cta_acc[idx];
 }
 
 // grads[o] = sum over graphs (deterministic: fixed partition, fixed order).  Block =
@@ -777,7 +783,7 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
         return DGCNN_ERR_CUDA;
     int64_t grid = DGCNN_NUM_SMS;
     if (grid > num_graphs) grid = num_graphs;
-    stack_bwd_mma_kernel<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
+    stack_bwd_mma_kernel<<<(unsigned)grid, kBwdThreads, smem, st>>>(p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int total = grad_offsets_m(f).total;
     stack_bwd_reduce_graphs<<<(total + 31) / 32, 256, 0, st>>>(p.partials, (int)grid, total, grads);

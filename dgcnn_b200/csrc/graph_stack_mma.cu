@@ -35,6 +35,13 @@
 
 namespace dgcnn {
 
+// The forward kernel runs FWD_THREADS threads per CTA (default 640 = 20 warps at <= 96
+// registers): the largest graphs of a batch bound the launch, and a 19-tile graph then does
+// one round of row tiles per layer instead of two.
+#ifndef DGCNN_FWD_THREADS
+#define DGCNN_FWD_THREADS 640
+#endif
+constexpr int kFwdThreads = DGCNN_FWD_THREADS;
 constexpr int kRowH = 72;                  // halfs per node row of a feature plane pair
 constexpr int kRowB = kRowH * 2;           // 144 bytes
 constexpr int kRankSortMax = 640;          // rank sort (one pass, no barriers) up to this many nodes
@@ -544,7 +551,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
 }
 
 // The CTA's graphs and their teams: plan_pass() in graph_mma.cuh.
-__global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ PlanEntry s_plan[kMaxTeams];
     __shared__ int s_count;
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdP
     const int budget = kQuads * quad_bytes(f);
     const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
-    constexpr int kWarps = kCtaThreads / 32;
+    constexpr int kWarps = kFwdThreads / 32;
     const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);      // {graph, base, n, fgoff}
     int next = 0;                                    // items of this CTA consumed so far
     int excl = 0;                                    // graphs with an SM of their own (warp 0 only)
@@ -569,13 +576,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdP
         } else if (pass == 0) {
             // meanwhile the other warps stage the weights: W1 transposed fp32 (F -> 32 stays on
             // the FMA pipe), W2/W3 as hi/lo fp16 planes [cout][cin] = the MMA "col" operand
-            const int tid = threadIdx.x - 32, nthreads = kCtaThreads - 32;
+            const int tid = threadIdx.x - 32, nthreads = kFwdThreads - 32;
             __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
             __half* w3p = reinterpret_cast<__half*>(smraw + SL.w3p);
             float* w1t = reinterpret_cast<float*>(smraw + SL.w1t);
             float* w4s = reinterpret_cast<float*>(smraw + SL.misc);
             {   // all global loads of a thread are issued before its first store: one round trip
-                constexpr int R = (kHid * kHid + (kCtaThreads - 32) - 1) / (kCtaThreads - 32);
+                constexpr int R = (kHid * kHid + (kFwdThreads - 32) - 1) / (kFwdThreads - 32);
                 float v2[R], v3[R], vb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -620,8 +627,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) stack_fwd_mma_kernel(StackFwdP
             const int gi = s_plan[j].gi, keep = min(s_plan[j].n, p.k);
             float* pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
             int32_t* perm_g = p.perm + (int64_t)gi * p.k;
-            for (int idx = keep * kCat + threadIdx.x; idx < p.k * kCat; idx += kCtaThreads) pooled_g[idx] = 0.f;
-            for (int r = keep + threadIdx.x; r < p.k; r += kCtaThreads) perm_g[r] = -1;
+            for (int idx = keep * kCat + threadIdx.x; idx < p.k * kCat; idx += kFwdThreads) pooled_g[idx] = 0.f;
+            for (int r = keep + threadIdx.x; r < p.k; r += kFwdThreads) perm_g[r] = -1;
         }
         int mine = -1;
         for (int j = 0; j < count; ++j)
@@ -741,7 +748,7 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
         return DGCNN_ERR_CUDA;
     int64_t grid = DGCNN_NUM_SMS;
     if (grid > num_graphs) grid = num_graphs;
-    stack_fwd_mma_kernel<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
+    stack_fwd_mma_kernel<<<(unsigned)grid, kFwdThreads, smem, st>>>(p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

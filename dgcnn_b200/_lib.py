@@ -95,6 +95,14 @@ SIGNATURES = {
     "dgcnn_tail_bwd_join": (c_int32, [c_void_p]),
     "dgcnn_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_float, c_float, c_float, c_float, c_float, c_void_p]),
+    "dgcnn_allreduce_adam_exchange_bytes": (c_size_t, [c_int64, c_int32]),
+    "dgcnn_exchange_create": (c_int32, [c_int64, c_int32, c_void_p, c_void_p]),
+    "dgcnn_exchange_open": (c_int32, [c_void_p, c_void_p]),
+    "dgcnn_exchange_close": (c_int32, [c_void_p]),
+    "dgcnn_exchange_destroy": (c_int32, [c_void_p]),
+    "dgcnn_allreduce_adam": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                       c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,
+                                       c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "dgcnn_nll_sum": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p,
                                 c_void_p]),
     "dgcnn_sort_pool_bwd": (c_int32, [c_void_p, c_void_p, c_int64,

@@ -1,0 +1,191 @@
+// X1 + N3 -- the step's one collective fused with the optimizer: a one-shot all-reduce of the
+// flat gradient buffer over NVLink / NVSwitch PEER MEMORY followed, in the same kernel, by the
+// flat Adam update (train.py:40-42 across ranks; SURVEY.md 8e: one sum of 0.2-4 MB per step,
+// latency-bound).
+//
+// Every rank owns an exchange buffer that all the others map through CUDA IPC:
+//
+//     [ header: arrival counters of parity 0 / 1, 128 B apart ]
+//     [ parity 0: W slots of n floats, slot r written by rank r ][ parity 1: the same ]
+//
+// PUSH model (remote stores are fire-and-forget, remote loads cost a NVLink round trip each):
+// one launch (G CTAs, all resident) per step e, parity = e & 1:
+//   1. every rank stores its local gradient sums into slot [rank] of EVERY rank's buffer
+//      (its own included), fences to system scope, and adds one arrival per CTA to every
+//      rank's counter (remote atomics);
+//   2. thread 0 of every CTA polls the LOCAL counter until it shows G * W * (e/2 + 1);
+//   3. the W local slots are summed IN RANK ORDER (every rank computes bit-identical sums), the
+//      global sums go back to `grads` (the loss / accuracy scalars ride along), Adam is applied.
+// Two parity regions make one barrier per step enough: a rank pushes step e+2 only after it
+// passed the barrier of step e+1, which every rank joins only after its step-e kernel is over,
+// so nobody still reads the region that step e+2 overwrites.  A poll that does not complete
+// within ~2 s raises DGCNN_COMM_TIMEOUT in `status` instead of hanging the GPU.
+//
+// NCCL costs ~90 us per step here (launch + ring + rank skew); see DESIGN.md for this kernel.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int kArMaxWorld = 16;
+constexpr int kArCtas = 32;
+constexpr int kArThreads = 256;
+constexpr int kArHeaderBytes = 256;
+
+struct AllreduceAdamParams {
+    float* p; float* g; float* m; float* v;
+    int64_t n_params, n_total;
+    const int64_t* step; const int64_t* epoch;
+    float lr, beta1, beta2, eps, grad_scale;
+    unsigned char* exch[kArMaxWorld];
+    int world, rank;
+    int32_t* status;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kArThreads)
+allreduce_adam_kernel(AllreduceAdamParams a) {
+    const int64_t e = *a.epoch;
+    const int parity = (int)(e & 1);
+    const uint32_t target = (uint32_t)(gridDim.x * (uint64_t)a.world * (uint64_t)(e / 2 + 1));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slot = (a.n_total + 31) / 32 * 32;             // floats per slot
+    const int64_t region = (int64_t)parity * a.world * slot;     // floats before this parity's slots
+
+    // 1. push the local sums into slot [rank] of every rank's buffer
+    for (int64_t i = tid; i < a.n_total; i += stride) {
+        const float gi = a.g[i];
+        for (int r = 0; r < a.world; ++r)
+            reinterpret_cast<float*>(a.exch[r] + kArHeaderBytes)[region + (int64_t)a.rank * slot + i] = gi;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int r = 0; r < a.world; ++r)
+            atomicAdd_system(reinterpret_cast<uint32_t*>(a.exch[r] + parity * 128), 1u);
+
+    // 2. wait until every CTA of every rank has arrived at the LOCAL counter
+    if (threadIdx.x == 0) {
+        const uint32_t* cnt = reinterpret_cast<const uint32_t*>(a.exch[a.rank] + parity * 128);
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(cnt) - target) < 0) {
+            if (clock64() - t0 > 4000000000ll) {                  // ~2 s: a peer is gone
+                if (a.status) atomicOr(a.status, DGCNN_COMM_TIMEOUT);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+
+    // 3. sum the local slots in rank order, Adam on the parameters
+    const int64_t t = *a.step + 1;
+    const float bc1 = 1.f - powf(a.beta1, (float)t), bc2 = 1.f - powf(a.beta2, (float)t);
+    const float step_size = a.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    const float* mine = reinterpret_cast<const float*>(a.exch[a.rank] + kArHeaderBytes) + region;
+    for (int64_t i = tid; i < a.n_total; i += stride) {
+        float s = 0.f;
+        for (int r = 0; r < a.world; ++r) s += __ldcv(mine + (int64_t)r * slot + i);
+        a.g[i] = s;
+        if (i < a.n_params) {
+            const float gi = s * a.grad_scale;
+            const float mi = a.beta1 * a.m[i] + (1.f - a.beta1) * gi;
+            const float vi = a.beta2 * a.v[i] + (1.f - a.beta2) * gi * gi;
+            a.m[i] = mi;
+            a.v[i] = vi;
+            a.p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + a.eps);
+        }
+    }
+}
+
+__global__ void allreduce_adam_bump(int64_t* step, int64_t* epoch) { *step += 1; *epoch += 1; }
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+// ---- exchange buffers: set-up calls (these allocate; the per-step call never does) -----------
+// The buffer is a cudaMalloc allocation of its own, so that the IPC handle maps exactly it.
+// A peer opens the handle WITH ITS OWN DEVICE CURRENT: cudaIpcOpenMemHandle then maps the
+// exporter's memory into the importer's context and enables peer access between the two
+// devices (importing it into the exporter's device context of the importing process does not
+// make it visible to kernels of another device).
+static size_t exchange_bytes(int64_t n_total, int world) {
+    return (size_t)kArHeaderBytes + 2 * (size_t)world * sizeof(float) * (size_t)((n_total + 31) / 32 * 32);
+}
+
+extern "C" int dgcnn_exchange_create(int64_t n_total, int32_t world, void** local_ptr, unsigned char* handle64) {
+    if (n_total < 0 || world < 1 || world > kArMaxWorld || !local_ptr || !handle64)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const size_t bytes = exchange_bytes(n_total, world);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return DGCNN_ERR_CUDA;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        cudaFree(p);
+        return DGCNN_ERR_CUDA;
+    }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return DGCNN_ERR_CUDA; }
+    memcpy(handle64, &h, 64);
+    *local_ptr = p;
+    return DGCNN_OK;
+}
+
+extern "C" int dgcnn_exchange_open(const unsigned char* handle64, void** peer_ptr) {
+    if (!handle64 || !peer_ptr) return DGCNN_ERR_INVALID_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return DGCNN_ERR_UNSUPPORTED;
+    }
+    *peer_ptr = p;
+    return DGCNN_OK;
+}
+
+extern "C" int dgcnn_exchange_close(void* peer_ptr) {
+    return (!peer_ptr || cudaIpcCloseMemHandle(peer_ptr) == cudaSuccess) ? DGCNN_OK : DGCNN_ERR_CUDA;
+}
+
+extern "C" int dgcnn_exchange_destroy(void* local_ptr) {
+    return (!local_ptr || cudaFree(local_ptr) == cudaSuccess) ? DGCNN_OK : DGCNN_ERR_CUDA;
+}
+
+extern "C" size_t dgcnn_allreduce_adam_exchange_bytes(int64_t n_total, int32_t world) {
+    if (n_total < 0 || world < 1) return 0;
+    return exchange_bytes(n_total, world);
+}
+
+extern "C" int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                                    int64_t n_params, int64_t n_total, int64_t* step, int64_t* epoch,
+                                    float lr, float beta1, float beta2, float eps, float grad_scale,
+                                    void* const* exchange, int32_t world, int32_t rank, int32_t* status,
+                                    void* stream) {
+    if (n_params < 0 || n_total < n_params || !step || !epoch || !exchange) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (n_total == 0) return DGCNN_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq) return DGCNN_ERR_INVALID_ARGUMENT;
+    AllreduceAdamParams a{};
+    a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq;
+    a.n_params = n_params; a.n_total = n_total; a.step = step; a.epoch = epoch;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
+    for (int r = 0; r < world; ++r) {
+        if (!exchange[r]) return DGCNN_ERR_INVALID_ARGUMENT;
+        a.exch[r] = static_cast<unsigned char*>(exchange[r]);
+    }
+    a.world = world; a.rank = rank; a.status = status;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    allreduce_adam_kernel<<<kArCtas, kArThreads, 0, st>>>(a);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    allreduce_adam_bump<<<1, 1, 0, st>>>(step, epoch);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}

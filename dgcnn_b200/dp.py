@@ -14,7 +14,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "GradBucket"]
+__all__ = ["shard_bounds", "GradBucket", "PeerExchange"]
 
 
 def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
@@ -66,3 +66,53 @@ class GradBucket:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat[: self.flat.numel() - self.extra.numel()].mul_(1.0 / float(global_batch))
+
+
+class PeerExchange:
+    """Exchange buffers of the fused all-reduce + Adam kernel (csrc/allreduce_adam.cu): every
+    rank of ONE node allocates a small device buffer, shares it through CUDA IPC (torch's own
+    storage-sharing handles, exchanged with all_gather_object) and maps the buffers of all its
+    peers, so that the kernel can read the other ranks' gradient sums directly over
+    NVLink / NVSwitch.  `ptrs[r]` is the device pointer of rank r's buffer as seen from this
+    process.  Raises if the ranks cannot map each other's memory (e.g. several nodes): the
+    caller then keeps the NCCL all-reduce."""
+
+    def __init__(self, n_total: int, device: torch.device, group=None):
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group")
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        import ctypes
+        lib = _lib.load_library()
+        self._lib, self.device = lib, device
+        local, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            _lib.check(lib.dgcnn_exchange_create(int(n_total), self.world, ctypes.byref(local), handle), "exchange_create")
+        self.local_ptr = int(local.value)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(handle), group=group)
+        self.ptrs, self.peer_ptrs = [], []
+        for r, h in enumerate(gathered):
+            if r == self.rank:
+                self.ptrs.append(self.local_ptr)
+                continue
+            peer = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            with torch.cuda.device(device):          # OUR device current: mapped for OUR kernels
+                _lib.check(lib.dgcnn_exchange_open(buf, ctypes.byref(peer)), "exchange_open")
+            self.peer_ptrs.append(int(peer.value))
+            self.ptrs.append(int(peer.value))
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        dist.barrier(group=group)
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free the own one (after a barrier: nobody may still poll)."""
+        if self.local_ptr is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self.peer_ptrs:
+                self._lib.dgcnn_exchange_close(p)
+            self._lib.dgcnn_exchange_destroy(self.local_ptr)
+        self.local_ptr, self.peer_ptrs = None, []

@@ -8,6 +8,7 @@ key only: a CPU tensor raises, there is no CPU path).
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -522,6 +523,32 @@ def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor
                                  float(grad_scale), _stream())
     _lib.check(rc, "adam_step")
     LAUNCHES["adam_step"] += 2 if n > 0 else 0
+
+
+def allreduce_adam(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: Tensor,
+                   epoch: Tensor, lr: float, beta1: float, beta2: float, eps: float, grad_scale: float,
+                   exchange_ptrs, rank: int, status: Optional[Tensor] = None) -> None:
+    """X1 + N3: one-shot all-reduce of `grads` over peer memory fused with the flat Adam step
+    (`exchange_ptrs[r]` = device pointer of rank r's exchange buffer, see dp.PeerExchange)."""
+    lib = _lib.load_library()
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _require_cuda(t, name, torch.float32)
+        if not t.is_contiguous():
+            raise ValueError(f"dgcnn_b200: {name} must be contiguous")
+    _require_cuda(step, "step", torch.int64)
+    _require_cuda(epoch, "epoch", torch.int64)
+    n, total = params.numel(), grads.numel()
+    if not (total >= n and exp_avg.numel() == n and exp_avg_sq.numel() == n):
+        raise ValueError("dgcnn_b200: allreduce_adam size mismatch")
+    world = len(exchange_ptrs)
+    table = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p_)) for p_ in exchange_ptrs])
+    with torch.cuda.device(params.device):
+        rc = lib.dgcnn_allreduce_adam(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), n, total,
+                                      _ptr(step), _ptr(epoch), float(lr), float(beta1), float(beta2),
+                                      float(eps), float(grad_scale), table, world, int(rank), _ptr(status),
+                                      _stream())
+    _lib.check(rc, "allreduce_adam")
+    LAUNCHES["adam_step"] += 2
 
 
 # ---------------------------------------------------------------------------------

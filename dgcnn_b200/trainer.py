@@ -15,6 +15,7 @@ sync, step counter and dropout offset live on the device.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -67,6 +68,22 @@ class FusedTrainer:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        # multi-GPU: gradients are summed by the fused peer-memory all-reduce + Adam kernel when
+        # the ranks (one node) can map each other's memory, else by NCCL (DGCNN_ALLREDUCE=nccl)
+        self.exchange = None
+        self.comm_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+                and os.environ.get("DGCNN_ALLREDUCE", "p2p").lower() == "p2p"):
+            try:
+                from .dp import PeerExchange
+                self.exchange = PeerExchange(n + 2, dev, group)
+            except Exception as exc:                                       # noqa: BLE001
+                print(f"[dgcnn_b200] peer-memory all-reduce unavailable ({exc!r}); using NCCL", flush=True)
+            # all ranks must agree, or the collectives no longer match
+            flag = torch.tensor([1.0 if self.exchange is not None else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if float(flag.item()) < 1.0:
+                self.exchange = None
 
     def supported(self, data) -> bool:
         """The fused kernels need the largest graph of the batch (host knowledge)."""
@@ -98,10 +115,16 @@ class FusedTrainer:
         ops.stack_bwd(dpooled, perm, xcat, data.x, graph, weights, k, norm,
                       out=self.grad[:self.num_stack])
         pending.join()
-        if world > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
         if global_batch is None:
             global_batch = graph.num_graphs * world
+        if world > 1 and self.exchange is not None:
+            ops.allreduce_adam(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                               self.exchange.epoch, self.lr, self.betas[0], self.betas[1], self.eps,
+                               1.0 / float(global_batch), self.exchange.ptrs, self.exchange.rank,
+                               self.comm_status)
+            return self.stats
+        if world > 1 and os.environ.get("DGCNN_SKIP_ALLREDUCE", "0") != "1":   # (skip: timing experiments only)
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
                       self.betas[0], self.betas[1], self.eps, grad_scale=1.0 / float(global_batch))
         return self.stats

@@ -55,6 +55,7 @@ typedef enum dgcnn_act { DGCNN_ACT_NONE = 0, DGCNN_ACT_TANH = 1 } dgcnn_act;
 #define DGCNN_GRAPH_BAD_EDGE 1    /* an edge_index entry outside [0, N)      */
 #define DGCNN_GRAPH_BAD_BATCH 2   /* batch not non-decreasing / outside [0,B) */
 #define DGCNN_GRAPH_RANGE 4       /* a projected feature exceeded the fp16 split range */
+#define DGCNN_COMM_TIMEOUT 16     /* dgcnn_allreduce_adam: a peer did not arrive within ~2 s */
 #define DGCNN_GRAPH_GENERIC 8     /* (informational) input was not a sorted symmetric edge list:
                                      K0 took the generic path, A_hat^T != A_hat may hold */
 
@@ -311,6 +312,38 @@ int dgcnn_adam_step(float* params, const float* grads, float* exp_avg, float* ex
  * number of correct argmax predictions; dlogp (optional) [B,C] = d(stats[0] * grad_scale). */
 int dgcnn_nll_sum(const float* logp, const int64_t* y, int64_t num_graphs, int32_t num_classes,
                   float grad_scale, float* stats, float* dlogp, void* stream);
+
+/* ------------------------------------------------------------------------
+ * X1 + N3  multi-GPU step tail: ONE kernel that all-reduces the flat gradient buffer over
+ * NVLink peer memory (one-shot, push: every rank stores its sums into its slot of every rank's
+ * exchange buffer -- mapped through CUDA IPC --, signals an arrival counter per rank, waits on
+ * its own counter and adds its W local slots in rank order: bit-identical on every rank) and
+ * applies the flat Adam update of dgcnn_adam_step.
+ * Replaces, for ranks of one node, dist.all_reduce + optimizer.step (train.py:40-42 in the
+ * data-parallel harness; the reference itself is single-device).
+ *   grads      [n_total]: in = local sums, out = global sums; the first n_params entries
+ *              drive Adam (x grad_scale), the rest (loss sum, #correct) just ride along
+ *   exchange   HOST array of `world` DEVICE pointers, exchange[r] = rank r's buffer
+ *              (dgcnn_exchange_create at [rank], dgcnn_exchange_open of the peers' handles
+ *              elsewhere)
+ *   step, epoch device int64 counters, bumped by the call; epoch must be equal on all ranks
+ *   status     optional; DGCNN_COMM_TIMEOUT if a peer never arrived (no hang)
+ * Every rank must make the same sequence of calls.  Capturable in a CUDA graph.
+ * ------------------------------------------------------------------------ */
+size_t dgcnn_allreduce_adam_exchange_bytes(int64_t n_total, int32_t world);
+/* Set-up of the exchange buffers (these four allocate / map; call them once, outside the step):
+ * create = cudaMalloc + zero + cudaIpcGetMemHandle on the current device (handle64: 64 bytes to
+ * send to the peers); open = cudaIpcOpenMemHandle with the CALLER's device current, which maps
+ * the exporter's buffer for kernels of the caller's device (peer access enabled lazily). */
+int dgcnn_exchange_create(int64_t n_total, int32_t world, void** local_ptr, unsigned char* handle64);
+int dgcnn_exchange_open(const unsigned char* handle64, void** peer_ptr);
+int dgcnn_exchange_close(void* peer_ptr);
+int dgcnn_exchange_destroy(void* local_ptr);
+int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                         int64_t n_params, int64_t n_total, int64_t* step, int64_t* epoch,
+                         float lr, float beta1, float beta2, float eps, float grad_scale,
+                         void* const* exchange, int32_t world, int32_t rank, int32_t* status,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,8 +38,8 @@ WORKLOAD = "collab"          # BASELINE.json configs[3]: the config the metric i
 RING = 4                     # distinct pre-built batches cycled through the timed steps
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
 # DRAM bytes (read + write) of one stack_fwd_mma_kernel launch on COLLAB-synth bs512, from the
-# ncu --set full capture summarised in profiles/r01_stack_fwd_mma_v2.md (not measurable live)
-KS_NCU_DRAM_BYTES = 1114880 + 128512
+# ncu --set full capture summarised in profiles/r01_stack_fwd_mma_v3.md (not measurable live)
+KS_NCU_DRAM_BYTES = 1112064 + 109312
 
 
 def parse_args():
@@ -463,7 +463,7 @@ def main():
                     "frac": a_fwd / t_fwd / 1e9 / peak, "traffic": KS_NCU_DRAM_BYTES, "peak_source": peak_kind,
                     "algorithmic_bytes": a_fwd, "launch_us": t_fwd * 1e6,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                                      "capture of this kernel on this workload (profiles/r01_stack_fwd_mma_v2.md): "
+                                      "capture of this kernel on this workload (profiles/r01_stack_fwd_mma_v3.md): "
                                       "adjacency arrives as K0b bitmaps and the 41 MB of outputs stay in the "
                                       "126 MB L2, so DRAM traffic is far BELOW the algorithmic bytes",
                     "note": "effective figure on A_fwd = sum of per-layer algorithmic bytes + SortPool "

@@ -136,6 +136,44 @@ def test_build_graph_fast_path_equals_generic_path():
         np.testing.assert_allclose(g3.dis.cpu().numpy(), dis, rtol=2e-7)
 
 
+def test_fingerprint_symmetry_check_rejects_asymmetric_sorted_lists(monkeypatch):
+    """K0's fast path proves symmetry with multiset fingerprints.  Sorted, duplicate-free lists
+    that are NOT symmetric -- including ones that keep every in/out degree intact -- must take
+    the generic path and give the reference CSR; the exact binary-search check
+    (DGCNN_EXACT_SYMMETRY=1) must agree on both verdicts."""
+    b = make_batch("proteins", num_graphs=30)
+    ei = b.edge_index.numpy()
+    n = b.num_nodes
+    # a directed 3-cycle a->b->c->a inside graph 0 replaces nothing: add it and keep the order
+    rng = np.random.RandomState(3)
+    cases = {"symmetric": ei}
+    extra = np.array([[0, 1, 2], [1, 2, 0]])            # nodes 0,1,2 belong to graph 0
+    have = set(map(tuple, ei.T.tolist()))
+    add = np.array([e for e in extra.T.tolist() if tuple(e) not in have] or [[0, 3]]).T
+    asym = np.concatenate([ei, add], 1)
+    asym = asym[:, np.lexsort((asym[1], asym[0]))]
+    cases["one-way edges"] = asym
+    # reverse the direction of one existing edge pair: (u,v),(v,u) -> keep only (u,v) twice is a
+    # duplicate, so instead drop (v,u) and add (v,w) for another neighbour w of u: degrees change
+    # little, symmetry breaks
+    drop = int(rng.randint(ei.shape[1]))
+    cases["missing reverse edge"] = np.delete(ei, drop, axis=1)
+    for exact in (False, True):
+        monkeypatch.setattr(ops, "EXACT_SYMMETRY_CHECK", exact)
+        for name, e in cases.items():
+            e = np.ascontiguousarray(e)
+            g = gpu_graph(e, b.batch.numpy(), n, b.num_graphs)
+            generic = bool(int(g.status.item()) & ops.GRAPH_GENERIC)
+            assert generic == (name != "symmetric"), (name, exact)
+            rowptr, col, rowptr_t, col_t, dis = ref_csr(e, n)
+            m = int(rowptr[-1])
+            np.testing.assert_array_equal(g.rowptr.cpu().numpy(), rowptr)
+            np.testing.assert_array_equal(g.col.cpu().numpy()[:m], col)
+            np.testing.assert_array_equal(g.rowptr_t.cpu().numpy(), rowptr_t)
+            np.testing.assert_array_equal(g.col_t.cpu().numpy()[:m], col_t)
+            np.testing.assert_allclose(g.dis.cpu().numpy(), dis, rtol=2e-7)
+
+
 def test_bitmaps_match_the_adjacency():
     """K0b: bit (r,c) of graph g  <=>  edge c->r or r == c; duplicates flagged per graph;
     the transposed bitmap is only built when the input is not a sorted symmetric list."""

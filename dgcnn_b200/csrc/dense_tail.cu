@@ -37,28 +37,37 @@ __device__ __forceinline__ void c5_stage_pairs(const float* __restrict__ pooled,
                                                int k, int L1, float* __restrict__ xs,
                                                unsigned char* __restrict__ nonzero = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int pp = warp; pp < kC5Pairs; pp += 8) {
-        float v[7];
-        const bool live = pp < count;
-        const int64_t pr = pr0 + pp;
-        const int64_t b = live ? pr / L1 : 0;
-        const int j = live ? (int)(pr - b * L1) : 0;
-        const float* src = pooled + (b * k + 2 * j) * kKW;
+    // two pairs (14 loads per lane) in flight per warp: the copy is L2 latency
+    for (int pp0 = warp; pp0 < kC5Pairs; pp0 += 16) {
+        float v[2][7];
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            const int i = lane + 32 * u;
-            v[u] = (live && i < kC5Row) ? src[i] : 0.f;
-        }
-        bool any = false;
+        for (int h = 0; h < 2; ++h) {
+            const int pp = pp0 + 8 * h;
+            const bool live = pp < count;
+            const int64_t pr = pr0 + pp;
+            const int64_t b = live ? pr / L1 : 0;
+            const int j = live ? (int)(pr - b * L1) : 0;
+            const float* src = pooled + (b * k + 2 * j) * kKW;
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            const int i = lane + 32 * u;
-            if (i < kC5Row) xs[pp * kC5Row + i] = v[u];
-            any |= v[u] != 0.f;                       // NaN != 0: a NaN row is not skipped
+            for (int u = 0; u < 7; ++u) {
+                const int i = lane + 32 * u;
+                v[h][u] = (live && i < kC5Row) ? src[i] : 0.f;
+            }
         }
-        if (nonzero) {
-            any = __any_sync(DGCNN_FULL_MASK, any);
-            if (lane == 0) nonzero[pp] = any ? 1 : 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pp = pp0 + 8 * h;
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                const int i = lane + 32 * u;
+                if (i < kC5Row) xs[pp * kC5Row + i] = v[h][u];
+                any |= v[h][u] != 0.f;                    // NaN != 0: a NaN row is not skipped
+            }
+            if (nonzero) {
+                any = __any_sync(DGCNN_FULL_MASK, any);
+                if (lane == 0) nonzero[pp] = any ? 1 : 0;
+            }
         }
     }
 }
@@ -99,17 +108,29 @@ tail_c5_fwd(const float* __restrict__ pooled, int64_t B, int k, int L1, const fl
             a1[0] = fmaf(w.x, u1, a1[0]); a1[1] = fmaf(w.y, u1, a1[1]);
             a1[2] = fmaf(w.z, u1, a1[2]); a1[3] = fmaf(w.w, u1, a1[3]);
         }
-        if (pp < count) {
-            const int64_t pr = pr0 + pp;
-            const int64_t b = pr / L1;
-            const int j = (int)(pr - b * L1);
+        // results go through shared memory (the staged inputs are dead): h1/arg are [b][c][j], so a
+        // thread's 4 channels are L1 floats apart -- written directly they are 2 M scattered 4-byte
+        // and 1-byte stores; re-ordered, each channel's 64 consecutive j are one coalesced run
+        __syncthreads();
+        float* so = xs;                                   // [16][64] maxima
+        unsigned char* sa = reinterpret_cast<unsigned char*>(xs + kC5 * kC5Pairs);   // [16][64] argmax
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float z0 = fmaxf(a0[q], 0.f), z1 = fmaxf(a1[q], 0.f);
-                const float m = fmaxf(z0, z1);
-                const int64_t o = (b * kC5 + 4 * cg + q) * L1 + j;
-                h1[o] = m;
-                arg[o] = (uint8_t)(m <= 0.f ? 2 : (z0 >= z1 ? 0 : 1));
+        for (int q = 0; q < 4; ++q) {
+            const float z0 = fmaxf(a0[q], 0.f), z1 = fmaxf(a1[q], 0.f);
+            const float m = fmaxf(z0, z1);
+            so[(4 * cg + q) * kC5Pairs + pp] = m;
+            sa[(4 * cg + q) * kC5Pairs + pp] = (unsigned char)(m <= 0.f ? 2 : (z0 >= z1 ? 0 : 1));
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kC5 * kC5Pairs; idx += 256) {
+            const int c = idx / kC5Pairs, q = idx - c * kC5Pairs;
+            if (q < count) {
+                const int64_t pr = pr0 + q;
+                const int64_t b = pr / L1;
+                const int j = (int)(pr - b * L1);
+                const int64_t o = (b * kC5 + c) * L1 + j;
+                h1[o] = so[idx];
+                arg[o] = sa[idx];
             }
         }
     }
@@ -128,6 +149,7 @@ tail_c6_fwd(const float* __restrict__ h1, int64_t B, int L1, const float* __rest
     float* h1s = sb + kC6;                   // [16][L1 + 8] (zero tail: windows may run past L1)
     const int L2 = L1 - (kK6 - 1);
     const int L1P = L1 + 8;
+    float* outs = h1s + kC5 * L1P;           // [32][L2] results of this graph
     for (int idx = threadIdx.x; idx < kC6 * kC5 * kK6; idx += 256) {
         int o = idx / (kC5 * kK6), r = idx - o * (kC5 * kK6);
         w6t[r * kC6 + o] = w6[idx];
@@ -163,8 +185,12 @@ tail_c6_fwd(const float* __restrict__ h1, int64_t B, int L1, const float* __rest
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (t0 + u < L2) h2[b * kC6 * L2 + lane * L2 + t0 + u] = fmaxf(acc[u], 0.f);
+                if (t0 + u < L2) outs[lane * L2 + t0 + u] = fmaxf(acc[u], 0.f);
         }
+        // the graph's [32][L2] block is contiguous in h2: one coalesced copy instead of stores
+        // that are L2 floats apart across the lanes of a warp
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kC6 * L2; idx += 256) h2[b * kC6 * L2 + idx] = outs[idx];
     }
 }
 
@@ -388,6 +414,7 @@ tail_c6_bwd_input(const float* __restrict__ dz2, int64_t B, int L1, const float*
     const int L2 = L1 - (kK6 - 1);
     const int LZ = L2 + 2 * (kK6 - 1) + 8;   // dz row with 4 zeros in front, zeros behind
     float* dzs = sm + kC6 * kK6 * kC5;       // [32][LZ]
+    float* outs = dzs + kC6 * LZ;            // [16][L1] results of this graph
     for (int idx = threadIdx.x; idx < kC6 * kC5 * kK6; idx += 256) {
         int o = idx / (kC5 * kK6), r = idx - o * (kC5 * kK6);
         int c = r / kK6, d = r - c * kK6;
@@ -419,8 +446,11 @@ tail_c6_bwd_input(const float* __restrict__ dz2, int64_t B, int L1, const float*
             }
 #pragma unroll
             for (int u = 0; u < 5; ++u)
-                if (s0 + u < L1) dh1[(b * kC5 + c) * L1 + s0 + u] = acc[u];
+                if (s0 + u < L1) outs[c * L1 + s0 + u] = acc[u];
         }
+        // the graph's [16][L1] block is contiguous in dh1: one coalesced copy
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < kC5 * L1; idx += 256) dh1[b * kC5 * L1 + idx] = outs[idx];
     }
 }
 
@@ -476,42 +506,59 @@ __global__ void __launch_bounds__(256)
 tail_c5_bwd_input(const float* __restrict__ dh1, const uint8_t* __restrict__ arg, int64_t B, int k, int L1,
                   const float* __restrict__ w5, float* __restrict__ dpooled) {
     __shared__ float w5s[kC5 * kKW];
-    __shared__ float zv[8][kC5];
-    __shared__ int za[8][kC5];
+    constexpr int TP = 32;                              // pairs per CTA iteration (4 per warp)
+    __shared__ float zv[TP][kC5 + 1];
+    __shared__ unsigned char za[TP][kC5];
     for (int idx = threadIdx.x; idx < kC5 * kKW; idx += 256) w5s[idx] = w5[idx];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t pairs = B * L1;
-    for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += (int64_t)gridDim.x * 8) {
-        const int64_t b = pr / L1;
-        const int j = (int)(pr - b * L1);
-        if (lane < kC5) {
-            const int64_t o = (b * kC5 + lane) * L1 + j;
-            zv[warp][lane] = dh1[o];
-            za[warp][lane] = arg[o];
+    for (int64_t pr0 = (int64_t)blockIdx.x * TP; pr0 < pairs; pr0 += (int64_t)gridDim.x * TP) {
+        __syncthreads();
+        // tile [16 channels][32 consecutive pairs] of dh1 / arg: 32 consecutive j of one channel
+        // are contiguous (within a graph), so these loads are coalesced -- one pair at a time they
+        // were 16 scattered floats + 16 scattered bytes per pair
+        for (int idx = threadIdx.x; idx < kC5 * TP; idx += 256) {
+            const int c = idx / TP, q = idx - c * TP;
+            const int64_t pr = pr0 + q;
+            float v = 0.f;
+            unsigned char a = 2;
+            if (pr < pairs) {
+                const int64_t b = pr / L1;
+                const int j = (int)(pr - b * L1);
+                const int64_t o = (b * kC5 + c) * L1 + j;
+                v = dh1[o];
+                a = arg[o];
+            }
+            zv[q][c] = v;
+            za[q][c] = a;
         }
-        __syncwarp();
-        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < kC5; ++c) {
-            const int r = za[warp][c];
-            if (r > 1) continue;                       // ReLU dead
-            const float v = zv[warp][c];
-            const float* wr = w5s + c * kKW;
-            if (r == 0) {
+        __syncthreads();
+        for (int q = warp; q < TP; q += 8) {
+            const int64_t pr = pr0 + q;
+            if (pr >= pairs) break;
+            const int64_t b = pr / L1;
+            const int j = (int)(pr - b * L1);
+            float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < kC5; ++c) {
+                const int r = za[q][c];
+                if (r > 1) continue;                       // ReLU dead
+                const float v = zv[q][c];
+                const float* wr = w5s + c * kKW;
+                if (r == 0) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { int i = lane + 32 * q; if (i < kKW) a0[q] = fmaf(v, wr[i], a0[q]); }
-            } else {
+                    for (int u = 0; u < 4; ++u) { int i = lane + 32 * u; if (i < kKW) a0[u] = fmaf(v, wr[i], a0[u]); }
+                } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { int i = lane + 32 * q; if (i < kKW) a1[q] = fmaf(v, wr[i], a1[q]); }
+                    for (int u = 0; u < 4; ++u) { int i = lane + 32 * u; if (i < kKW) a1[u] = fmaf(v, wr[i], a1[u]); }
+                }
+            }
+            float* dst = dpooled + (b * k + 2 * j) * kKW;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = lane + 32 * u;
+                if (i < kKW) { dst[i] = a0[u]; dst[kKW + i] = a1[u]; }
             }
         }
-        float* dst = dpooled + (b * k + 2 * j) * kKW;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int i = lane + 32 * q;
-            if (i < kKW) { dst[i] = a0[q]; dst[kKW + i] = a1[q]; }
-        }
-        __syncwarp();
     }
     // an odd k leaves the last row outside every pooling window: zero gradient
     if ((k & 1) && blockIdx.x == 0)
@@ -699,8 +746,11 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     tail_c5_fwd<<<grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st>>>(pooled, B, k, d.L1, w5, b5, h1,
                                                                              arg);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const size_t smem6 = sizeof(float) * (kC5 * kK6 * kC6 + kC6 + kC5 * (d.L1 + 8));
-    if (smem6 > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    const size_t smem6 = sizeof(float) * (kC5 * kK6 * kC6 + kC6 + kC5 * (d.L1 + 8) + kC6 * d.L2);
+    if (smem6 > 96 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    if (smem6 > 48 * 1024 &&
+        cudaFuncSetAttribute(tail_c6_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
     tail_c6_fwd<<<grid_for(B, 1, 4), 256, smem6, st>>>(h1, B, d.L1, w6, b6, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // fc1: [B, D1] x Wf1^T [D1, 128], split-K slabs
@@ -810,9 +860,13 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
         tail_reduce_partials<<<(total + 31) / 32, 256, 0, sw>>>(slabw, splits, total, total, dwf1, dwf1);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
-    const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * (d.L2 + 2 * (kK6 - 1) + 8));
+    const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * (d.L2 + 2 * (kK6 - 1) + 8) + kC5 * d.L1);
     const size_t smem_w = sizeof(float) * (kC6 * d.L2 + kC5 * (d.L1 | 1));
-    if (smem_in > 48 * 1024 || smem_w > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    if (smem_in > 200 * 1024 || smem_w > 48 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    if (smem_in > 48 * 1024 &&
+        cudaFuncSetAttribute(tail_c6_bwd_input, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_in) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
     if (!fork(1)) return DGCNN_ERR_CUDA;             // dz2 is ready
     tail_c6_bwd_input<<<grid_for(B, 1, 4), 256, smem_in, st>>>(dz2, B, d.L1, w6, dh1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
@@ -823,7 +877,7 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
     tail_reduce_partials<<<(n6 + kC6 + 31) / 32, 256, 0, sw>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (!fork(2)) return DGCNN_ERR_CUDA;             // dh1 is ready
-    tail_c5_bwd_input<<<grid_for(B * d.L1, 8, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
+    tail_c5_bwd_input<<<grid_for(B * d.L1, 32, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const size_t smem5 = sizeof(float) * (kC5Pairs * kC5Row + 2 * kC5Pairs * kC5);
     if (cudaFuncSetAttribute(tail_c5_bwd_weight, cudaFuncAttributeMaxDynamicSharedMemorySize,

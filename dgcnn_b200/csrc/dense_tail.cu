@@ -195,29 +195,55 @@ tail_c6_fwd(const float* __restrict__ h1, int64_t B, int L1, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// fp32 GEMM  C[m][n] = sum_k A(m,k) * Bm(k,n)  on the FMA pipe, 64 x 128 tiles, 256 threads,
-// 4 x 8 outputs per thread with interleaved ownership (conflict-free scalar shared loads for
-// every operand layout).  A_KM: A is stored [k][m] (else [m][k]); B_KN: Bm is stored [k][n]
-// (else [n][k]).  blockIdx.z splits K; each split writes its own [M][N] slab of C (the
-// caller adds the slabs in order).  RELU_MASK: C *= (mask > 0), the ReLU backward.
+// fp32-accurate GEMM  C[m][n] = sum_k A(m,k) * Bm(k,n)  on the tensor cores: 3xTF32
+// (mma.sync.m16n8k8.tf32; every operand split x = big + small with big = tf32(x), small =
+// tf32(x - big); big*big + big*small + small*big accumulated in fp32 -- the dropped
+// small*small term is < 2^-22 relative).  64 x 128 tiles, 256 threads = 2 x 4 warps,
+// shared-memory tiles As[k][m] / Bs[k][n] with strides = 8 (mod 32): conflict-free fragment
+// loads.  The next k-tile's global loads are issued before the current tile's MMAs.
+// A_KM: A is stored [k][m] (else [m][k]); B_KN: Bm is stored [k][n] (else [n][k]).  blockIdx.z
+// splits K; each split writes its own [M][N] slab of C (the caller adds the slabs in order).
+// RELU_MASK: C *= (mask > 0), the ReLU backward.  The FMA version of this kernel spent
+// 7-8 M warp instructions per GEMM at 50-60 % issue utilisation on 128 CTAs (profiles/).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tf32_split(float x, uint32_t& big, uint32_t& small) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(big) : "f"(x));
+    const float rem = x - __uint_as_float(big);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(small) : "f"(rem));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// CTA tile of the GEMM: 64 x 64 (2 x 4 warps of 32 x 16).  Narrow tiles on purpose: these GEMMs
+// are small (M = batch, K or N = 128) and latency-bound, so several CTAs per SM matter more than
+// operand reuse.
+constexpr int kGemmBM = 64, kGemmBN = 64;
+
 template <bool A_KM, bool B_KN, bool RELU_MASK>
 __global__ void __launch_bounds__(256)
 gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm, int64_t ldb,
          float* __restrict__ C, int M, int N, int K, int kchunk, const float* __restrict__ mask) {
-    constexpr int BM = 64, BN = 128, BK = 16, BMP = BM + 1, BNP = BN + 1;
+    constexpr int BM = kGemmBM, BN = kGemmBN, BK = 16, BMP = BM + 8, BNP = BN + 8;
+    constexpr int NI = BN / 32;                            // 8-column MMA tiles per warp (4 warps along N)
     __shared__ float As[BK * BMP];
     __shared__ float Bs[BK * BNP];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * (BN / 4);   // warp tile origin inside the CTA tile
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
-    float acc[4][8];
+    float acc[2][NI][4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
-    // the next k-tile's global loads are issued before the current tile's FMAs (register
-    // double buffer): the loads come from L2 and would otherwise sit exposed between two barriers
+        for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.f;
     constexpr int RA = (BM * BK) / 256, RB = (BN * BK) / 256;
     float ra[RA], rb[RB];
     auto fetch = [&](int k0) {
@@ -259,33 +285,50 @@ gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
         __syncthreads();
         if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float a[4], bv[8];
+        for (int ks = 0; ks < BK / 8; ++ks) {
+            uint32_t abig[2][4], asml[2][4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) a[p] = As[kk * BMP + ty + 16 * p];
+            for (int mi = 0; mi < 2; ++mi) {
+                const float* ap = As + (ks * 8 + t) * BMP + wm + mi * 16 + g;
+                tf32_split(ap[0], abig[mi][0], asml[mi][0]);
+                tf32_split(ap[8], abig[mi][1], asml[mi][1]);
+                tf32_split(ap[4 * BMP], abig[mi][2], asml[mi][2]);
+                tf32_split(ap[4 * BMP + 8], abig[mi][3], asml[mi][3]);
+            }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) bv[q] = Bs[kk * BNP + tx + 16 * q];
+            for (int ni = 0; ni < NI; ++ni) {
+                const float* bp = Bs + (ks * 8 + t) * BNP + wn + ni * 8 + g;
+                uint32_t bb0, bs0, bb1, bs1;
+                tf32_split(bp[0], bb0, bs0);
+                tf32_split(bp[4 * BNP], bb1, bs1);
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(a[p], bv[q], acc[p][q]);
+                for (int mi = 0; mi < 2; ++mi) {
+                    mma_tf32(acc[mi][ni], asml[mi], bb0, bb1);
+                    mma_tf32(acc[mi][ni], abig[mi], bs0, bs1);
+                    mma_tf32(acc[mi][ni], abig[mi], bb0, bb1);
+                }
+            }
         }
         __syncthreads();
     }
     float* out = C + (int64_t)blockIdx.z * M * N;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int gm = m0 + ty + 16 * p;
-        if (gm >= M) continue;
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int gn = n0 + tx + 16 * q;
-            if (gn >= N) continue;
-            float v = acc[p][q];
-            if (RELU_MASK) v = mask[(int64_t)gm * N + gn] > 0.f ? v : 0.f;
-            out[(int64_t)gm * N + gn] = v;
+        for (int half = 0; half < 2; ++half) {
+            const int gm = m0 + wm + mi * 16 + g + 8 * half;
+            if (gm >= M) continue;
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int gn = n0 + wn + ni * 8 + 2 * t + q;
+                    if (gn >= N) continue;
+                    float v = acc[mi][ni][2 * half + q];
+                    if (RELU_MASK) v = mask[(int64_t)gm * N + gn] > 0.f ? v : 0.f;
+                    out[(int64_t)gm * N + gn] = v;
+                }
         }
-    }
 }
 
 // 32-bit mix (murmur3 finaliser) of (seed, offset, index): one dropout decision per element
@@ -756,7 +799,7 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     // fc1: [B, D1] x Wf1^T [D1, 128], split-K slabs
     const int kchunk = (int)ceil_div(ceil_div(d.D1, kFc1Splits), 16) * 16;
     const int splits = (int)ceil_div(d.D1, kchunk);
-    dim3 g1(1, (unsigned)ceil_div(B, 64), (unsigned)splits);
+    dim3 g1((unsigned)ceil_div(kFc, kGemmBN), (unsigned)ceil_div(B, kGemmBM), (unsigned)splits);
     gemm_f32<false, false, false><<<g1, 256, 0, st>>>(h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
                                                       nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
@@ -845,14 +888,14 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
         dlogit, h3, dz3, B, num_classes, dwf2, dbf2, dbf1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dz2 = (dz3 Wf1) * (h2 > 0):  [B,128] x [128,D1]
-    dim3 ga((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(B, 64), 1);
+    dim3 ga((unsigned)ceil_div(d.D1, kGemmBN), (unsigned)ceil_div(B, kGemmBM), 1);
     gemm_f32<false, true, true><<<ga, 256, 0, st>>>(dz3, kFc, wf1, d.D1, dz2, (int)B, d.D1, kFc, kFc, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dWf1 = dz3^T h2:  [128,B] x [B,D1]
     {   // split over the batch, slabs summed in order
         const int kchunk = (int)ceil_div(ceil_div(B, kDwSplits), 16) * 16;
         const int splits = (int)ceil_div(B, kchunk);
-        dim3 gb((unsigned)ceil_div(d.D1, 128), (unsigned)ceil_div(kFc, 64), (unsigned)splits);
+        dim3 gb((unsigned)ceil_div(d.D1, kGemmBN), (unsigned)ceil_div(kFc, kGemmBM), (unsigned)splits);
         gemm_f32<true, true, false><<<gb, 256, 0, sw>>>(dz3, kFc, h2, d.D1, slabw, kFc, d.D1, (int)B, kchunk,
                                                         nullptr);
         DGCNN_RETURN_IF_LAUNCH_FAILED();

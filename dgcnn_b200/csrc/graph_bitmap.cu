@@ -95,9 +95,7 @@ k0b_offsets(const int32_t* __restrict__ gptr, int num_graphs, int max_nodes,
 
 // One warp per node row; blockIdx.y = 1 builds the bitmap of A_hat^T from the CSR by source
 // (skipped on the device when K0 proved the batch symmetric: gate_word / gate_mask).
-// Lane l accumulates word l of the row (wpr <= 32 for n <= 1024).  The columns of a CSR row
-// ascend, so the lanes of a 32-edge chunk that hit the same word are handled together:
-// leader by leader, one ballot + one OR-reduction per distinct word.
+// (wpr <= 32 words per row for n <= 1024.)
 __global__ void __launch_bounds__(256)
 k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
          const int32_t* __restrict__ rowptr1, const int32_t* __restrict__ col1,
@@ -134,8 +132,12 @@ k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
         const int np = (n + 15) & ~15, wpr = (np + 31) >> 5;
         const int r = (int)(i - base);
         uint32_t* brow = bitmap + bmoff[g] + (int64_t)r * wpr;
+        // Lanes of a 32-edge chunk that hit the same word are grouped (match), their bits OR-ed
+        // (one reduction per group, all groups at once) and the group's first lane ORs the result
+        // into the row -- the bitmap was zeroed by the caller, the row belongs to this warp, so the
+        // atomic only merges this warp's own chunks.  Chunks carry no state: their loads overlap.
         bool dup = false;
-        uint32_t mine = 0;            // lane l holds word l of the row
+#pragma unroll 2
         for (int c0 = beg; c0 < end; c0 += 32) {
             const int e = c0 + lane;
             int j = -1;
@@ -145,21 +147,17 @@ k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
             }
             const int word = j >= 0 ? (j >> 5) : -1;
             const uint32_t bit = j >= 0 ? (1u << (j & 31)) : 0u;
-#pragma unroll 1
-            for (uint32_t todo = __ballot_sync(DGCNN_FULL_MASK, j >= 0); todo;) {
-                const int w = __shfl_sync(DGCNN_FULL_MASK, word, __ffs(todo) - 1);
-                const uint32_t peers = __ballot_sync(DGCNN_FULL_MASK, word == w);
-                const uint32_t val = __reduce_or_sync(DGCNN_FULL_MASK, word == w ? bit : 0u);
+            const uint32_t peers = __match_any_sync(DGCNN_FULL_MASK, word);
+            const uint32_t val = __reduce_or_sync(peers, bit);
+            if (j >= 0) {
                 if (__popc(val) != __popc(peers)) dup = true;          // same bit twice in this chunk
-                if (lane == w) {
-                    if (mine & val) dup = true;                        // bit already set by an earlier chunk
-                    mine |= val;
+                if (lane == __ffs(peers) - 1) {
+                    const uint32_t old = atomicOr(&brow[word], val);
+                    if (old & val) dup = true;                         // bit already set by an earlier chunk
                 }
-                todo &= ~peers;
             }
         }
-        if (lane == (r >> 5)) mine |= 1u << (r & 31);                  // the self loop
-        if (lane < wpr) brow[lane] = mine;
+        if (lane == 0) atomicOr(&brow[r >> 5], 1u << (r & 31));       // the self loop
         if (__any_sync(DGCNN_FULL_MASK, dup) && lane == 0) atomicOr(&gflags[g], 1);
     }
 }

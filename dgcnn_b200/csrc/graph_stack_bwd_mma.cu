@@ -337,15 +337,22 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     if (dup)
         for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr_t[base + j] - e0;
     float amax = 0.f;
-    {   // eight loads in flight per thread: the sweep is pure memory latency
+    {   // sixteen loads in flight per thread: the sweep is pure memory latency
         const int total = keep * kCat;
         int idx = tid;
-        for (; idx + 7 * nthreads < total; idx += 8 * nthreads) {
-            float v[8];
+        for (; idx + 15 * nthreads < total; idx += 16 * nthreads) {
+            float v[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = dp[idx + u * nthreads];
+            for (int u = 0; u < 16; ++u) v[u] = dp[idx + u * nthreads];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) amax = fmaxf(amax, fabsf(v[u]));
+            for (int u = 0; u < 16; ++u) amax = fmaxf(amax, fabsf(v[u]));
+        }
+        for (; idx + 3 * nthreads < total; idx += 4 * nthreads) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = dp[idx + u * nthreads];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) amax = fmaxf(amax, fabsf(v[u]));
         }
         for (; idx < total; idx += nthreads) amax = fmaxf(amax, fabsf(dp[idx]));
     }

@@ -136,7 +136,10 @@ k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
         // (one reduction per group, all groups at once) and the group's first lane ORs the result
         // into the row -- the bitmap was zeroed by the caller, the row belongs to this warp, so the
         // atomic only merges this warp's own chunks.  Chunks carry no state: their loads overlap.
+        // Duplicate edges (multigraphs) are adjacent in a K0 row (columns ascend): compare each
+        // column with its left neighbour instead of waiting for what the atomic returns.
         bool dup = false;
+        int prev_last = -1;                             // last column of the previous chunk
 #pragma unroll 2
         for (int c0 = beg; c0 < end; c0 += 32) {
             const int e = c0 + lane;
@@ -145,17 +148,14 @@ k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
                 const unsigned t = (unsigned)(col[e] - base);
                 if (t < (unsigned)n) j = (int)t;       // edges leaving the graph are ignored (K0 flags them)
             }
+            const int left = __shfl_up_sync(DGCNN_FULL_MASK, j, 1);
+            if (j >= 0 && j == (lane == 0 ? prev_last : left)) dup = true;
+            prev_last = __shfl_sync(DGCNN_FULL_MASK, j, 31);
             const int word = j >= 0 ? (j >> 5) : -1;
             const uint32_t bit = j >= 0 ? (1u << (j & 31)) : 0u;
             const uint32_t peers = __match_any_sync(DGCNN_FULL_MASK, word);
             const uint32_t val = __reduce_or_sync(peers, bit);
-            if (j >= 0) {
-                if (__popc(val) != __popc(peers)) dup = true;          // same bit twice in this chunk
-                if (lane == __ffs(peers) - 1) {
-                    const uint32_t old = atomicOr(&brow[word], val);
-                    if (old & val) dup = true;                         // bit already set by an earlier chunk
-                }
-            }
+            if (j >= 0 && lane == __ffs(peers) - 1) atomicOr(&brow[word], val);
         }
         if (lane == 0) atomicOr(&brow[r >> 5], 1u << (r & 31));       // the self loop
         if (__any_sync(DGCNN_FULL_MASK, dup) && lane == 0) atomicOr(&gflags[g], 1);
@@ -181,7 +181,9 @@ k0b_fragments(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ b
         const int np = (n + 15) & ~15, wpr = (np + 31) >> 5, T = np >> 4, G = (T + 3) >> 2;
         const uint32_t* bm = bitmap + bmoff[d.x];
         uint32_t* out = fragmap + d.w;
-        for (int u = threadIdx.x >> 5; u < T * G; u += blockDim.x >> 5) {
+        // gridDim.y CTAs share a graph's (mt, grp) units: the largest graph is the tail of the launch
+        for (int u = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); u < T * G;
+             u += gridDim.y * (blockDim.x >> 5)) {
             const int mt = u / G, grp = u - mt * G;
             const uint32_t* r0 = bm + (int64_t)(mt * 16 + gq) * wpr;
             const uint32_t* r1 = r0 + 8 * wpr;
@@ -272,7 +274,7 @@ extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
                                        gflags_t, gate_word, gate_mask);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         if (fragmap && gdesc) {
-            k0b_fragments<<<grid_for(num_graphs, 1, 8), 256, 0, st>>>(
+            k0b_fragments<<<dim3((unsigned)grid_for(num_graphs, 1, 8), 4), 256, 0, st>>>(
                 bitmap, bmoff, reinterpret_cast<const int4*>(gdesc), (int)num_graphs, (int)max_nodes,
                 fragmap);
             DGCNN_RETURN_IF_LAUNCH_FAILED();

@@ -388,6 +388,14 @@ def main():
         sys.stdout.flush()
         os._exit(0)
 
+    comm_kind = "none (1 GPU)"
+    if world > 1:
+        p2p = fused_step and getattr(trainer, "exchange", None) is not None
+        comm_kind = ("one-shot NVLink peer-memory all-reduce fused with Adam (csrc/allreduce_adam.cu)" if p2p
+                     else "NCCL all-reduce + flat Adam")
+        if p2p and int(trainer.comm_status.item()) != 0:
+            comm_kind += " -- COMM TIMEOUT RAISED, numbers invalid"
+
     # ---- roofline: forward hot path and its dominant kernel, each timed alone ----
     peak, peak_kind = measured_peaks()
     db0 = dev_batches[0]
@@ -505,6 +513,7 @@ def main():
                    "l2": f"flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every timed step; "
                          f"ring of {RING} distinct batches",
                    "cuda_graph": use_graph, "fused_trainer": fused_step, "parallelism": f"dp{world} (graph-sharded)",
+                   "gradient_exchange": comm_kind,
                    "wall_s_incl_flush": wall},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,

@@ -55,7 +55,7 @@ typedef enum dgcnn_act { DGCNN_ACT_NONE = 0, DGCNN_ACT_TANH = 1 } dgcnn_act;
 #define DGCNN_GRAPH_BAD_EDGE 1    /* an edge_index entry outside [0, N)      */
 #define DGCNN_GRAPH_BAD_BATCH 2   /* batch not non-decreasing / outside [0,B) */
 #define DGCNN_GRAPH_RANGE 4       /* a projected feature exceeded the fp16 split range */
-#define DGCNN_COMM_TIMEOUT 16     /* dgcnn_allreduce_adam: a peer did not arrive within ~2 s */
+#define DGCNN_COMM_TIMEOUT 16     /* dgcnn_allreduce_adam: a peer did not arrive within ~20 s */
 #define DGCNN_GRAPH_GENERIC 8     /* (informational) input was not a sorted symmetric edge list:
                                      K0 took the generic path, A_hat^T != A_hat may hold */
 

@@ -4,9 +4,10 @@ against NCCL all-reduce + flat Adam.  Launch with torchrun, one rank per GPU:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29512 scripts/check_p2p_allreduce.py
 
-With two ranks both paths add the same two numbers; the two Adam kernels may contract their
-FMAs differently, so parameters are compared to 1e-7.  Across RANKS the fused kernel must give
-bit-identical parameters (fixed summation order)."""
+Every step starts both trainers from the same state.  With two ranks both paths add the same two
+numbers, so the reduced gradients must match bit for bit; the two Adam kernels may contract
+their FMAs differently, so the updated parameters are compared to 1e-6.  Across RANKS the fused
+kernel must give bit-identical parameters (fixed summation order)."""
 import copy
 import os
 import sys
@@ -43,14 +44,35 @@ tr_b = dg.FusedTrainer(model_b, lr=1e-3)
 assert tr_a.exchange is not None, "peer mapping failed"
 assert tr_b.exchange is None
 gb = cfg.batch_size * world
-for step in range(6):
-    sa = tr_a.step(batches[step % 4], gb).clone()
-    sb = tr_b.step(batches[step % 4], gb).clone()
-    torch.cuda.synchronize()
+
+
+def sync_state():
+    """Trainer b continues from trainer a's exact state: the comparison is per step (Adam turns a
+    1e-9 difference in a near-zero gradient into an lr-sized difference in the parameter, so
+    trajectories of several steps are not comparable to a tight tolerance)."""
+    tr_b.flat.copy_(tr_a.flat)
+    tr_b.exp_avg.copy_(tr_a.exp_avg)
+    tr_b.exp_avg_sq.copy_(tr_a.exp_avg_sq)
+    tr_b.step_count.copy_(tr_a.step_count)
+    model_b._tail_rng_offset.copy_(model_a._tail_rng_offset)
+
+
+def compare(tag):
     assert int(tr_a.comm_status.item()) == 0, "peer all-reduce timed out"
-    assert torch.equal(sa, sb), (step, sa, sb)
-    diff = (tr_a.flat - tr_b.flat).abs().max().item()
-    assert diff < 1e-7, (step, diff)
+    # the two sums of W = 2 numbers are the same additions: bit-identical reduced gradients
+    gd = (tr_a.grad - tr_b.grad).abs().max().item()
+    assert (gd == 0.0) if world == 2 else gd <= 1e-5 * tr_b.grad.abs().max().item(), (tag, gd)
+    # one Adam step from identical state and (near-)identical gradients
+    pd = (tr_a.flat - tr_b.flat).abs().max().item()
+    assert pd <= 1e-6, (tag, pd)
+
+
+for step in range(6):
+    sync_state()
+    tr_a.step(batches[step % 4], gb)
+    tr_b.step(batches[step % 4], gb)
+    torch.cuda.synchronize()
+    compare(step)
 # ranks hold identical parameters
 mine = tr_a.flat.clone()
 ref = mine.clone()
@@ -67,13 +89,13 @@ torch.cuda.current_stream().wait_stream(side)
 torch.cuda.synchronize()
 with torch.cuda.graph(g):
     tr_a.step(batches[1], gb)
-for _ in range(3):
+for it in range(3):
+    sync_state()
     g.replay()
     tr_b.step(batches[1], gb)
-torch.cuda.synchronize()
-assert int(tr_a.comm_status.item()) == 0
+    torch.cuda.synchronize()
+    compare(f"graph replay {it}")
 diff = (tr_a.flat - tr_b.flat).abs().max().item()
-assert diff < 1e-6, diff
 if rank == 0:
     print(f"p2p all-reduce + Adam == NCCL all-reduce + Adam on {world} GPUs (max diff {diff})", flush=True)
 torch.cuda.synchronize()

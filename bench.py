@@ -355,13 +355,14 @@ def main():
             ev.record(copy_stream)
         return data, ev
 
-    def e2e_run(nsteps):
-        nxt = h2d(host_batches[0])
+    def e2e_run(nsteps, hbs=None):
+        hbs = host_batches if hbs is None else hbs
+        nxt = h2d(hbs[0])
         last = 0.0
         for i in range(nsteps):
             data, ev = nxt
             if i + 1 < nsteps:
-                nxt = h2d(host_batches[(i + 1) % RING])
+                nxt = h2d(hbs[(i + 1) % RING])
             torch.cuda.current_stream().wait_event(ev)
             loss = train_step(data)
             for t in (data.x, data.edge_index, data.batch, data.ptr, data.y):
@@ -380,6 +381,24 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = global_batch * e2e_steps / float(e2e_s.item())
     h2d_bytes = host_batches[0].nbytes()
+
+    # the same loop on COMPACT host batches (int32 indices, dgcnn_build_graph_i32): not the
+    # reference's tensor format, reported next to `e2e`, never instead of it
+    compact_batches = []
+    for hb in host_batches:
+        cb = hb.compact().pin_memory()
+        cb.max_nodes = hb.max_nodes
+        compact_batches.append(cb)
+    e2e_run(3, compact_batches)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(e2e_steps, compact_batches)
+    barrier()
+    e2e_c = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_c, op=dist.ReduceOp.MAX)
+    e2e_compact_value = global_batch * e2e_steps / float(e2e_c.item())
+    h2d_compact_bytes = compact_batches[0].nbytes()
 
     if rank != 0:
         # Nothing collective happens after this point.  Tearing down an NCCL communicator whose
@@ -519,6 +538,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
                 "note": "pinned host batch -> H2D (copy stream, overlapped with the previous step) -> Model(data) -> NLL -> backward -> Adam -> loss.item()"},
+        "e2e_int32_indices": {"value": e2e_compact_value, "unit": UNIT, "h2d_bytes_per_step": h2d_compact_bytes,
+                              "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                              "note": "same loop, host batch collated with int32 edge_index/batch "
+                                      "(dgcnn_build_graph_i32): NOT the reference's int64 format; `e2e` is"},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,

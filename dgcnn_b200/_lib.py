@@ -33,9 +33,13 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_void_p, c_size_t, c_void_p]),
+    "dgcnn_build_graph_i32": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                        c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                        c_void_p, c_size_t, c_void_p]),
     "dgcnn_graph_bitmap_words": (c_int64, [c_int64, c_int64, c_int64]),
     "dgcnn_graph_fragmap_words": (c_int64, [c_int64, c_int64, c_int64]),
-    "dgcnn_build_bitmaps": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "dgcnn_build_bitmaps": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64,
                                       c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p,

@@ -99,7 +99,8 @@ k0b_offsets(const int32_t* __restrict__ gptr, int num_graphs, int max_nodes,
 __global__ void __launch_bounds__(256)
 k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
          const int32_t* __restrict__ rowptr1, const int32_t* __restrict__ col1,
-         const int32_t* __restrict__ gptr, const int64_t* __restrict__ batch, int num_graphs,
+         const int32_t* __restrict__ gptr, const int64_t* __restrict__ batch,
+         const int32_t* __restrict__ batch32, int num_graphs,
          int64_t n_nodes, int max_nodes, const int32_t* __restrict__ bmoff,
          uint32_t* __restrict__ bitmap0, uint32_t* __restrict__ bitmap1,
          int32_t* __restrict__ gflags0, int32_t* __restrict__ gflags1,
@@ -118,6 +119,8 @@ k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
         int g;
         if (batch) {
             g = (int)batch[i];
+        } else if (batch32) {
+            g = batch32[i];
         } else {                                     // graph of node i: last g with gptr[g] <= i
             int lo = 0, hi = num_graphs;
             while (hi - lo > 1) {
@@ -229,7 +232,7 @@ extern "C" int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_grap
 
 extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
                                    const int32_t* rowptr_t, const int32_t* col_t,
-                                   const int32_t* gptr, const int64_t* batch,
+                                   const int32_t* gptr, const int64_t* batch, const int32_t* batch32,
                                    int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                                    uint32_t* bitmap, uint32_t* bitmap_t, int64_t bitmap_words,
                                    int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,
@@ -269,7 +272,7 @@ extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (num_nodes > 0) {
         dim3 grid((unsigned)grid_for(num_nodes, 8, 8), transposed ? 2 : 1);
-        k0b_fill<<<grid, 256, 0, st>>>(rowptr, col, rowptr_t, col_t, gptr, batch, (int)num_graphs,
+        k0b_fill<<<grid, 256, 0, st>>>(rowptr, col, rowptr_t, col_t, gptr, batch, batch32, (int)num_graphs,
                                        num_nodes, (int)max_nodes, bmoff, bitmap, bitmap_t, gflags,
                                        gflags_t, gate_word, gate_mask);
         DGCNN_RETURN_IF_LAUNCH_FAILED();

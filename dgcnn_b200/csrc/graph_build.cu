@@ -68,13 +68,19 @@ __host__ inline BuildWorkspace carve_build_workspace(void* base, int64_t n, int6
     return w;
 }
 
+// Index arrays arrive as int64 (what the reference / PyG hands over) or, for compact host
+// batches that halve the host-to-device traffic, as int32: one loader for both.
+__device__ __forceinline__ int64_t ld_idx(const void* __restrict__ p, int64_t i, bool i32) {
+    return i32 ? (int64_t)static_cast<const int32_t*>(p)[i] : static_cast<const int64_t*>(p)[i];
+}
+
 // gptr[g] = first node of graph g.  batch is non-decreasing, so node i opens
 // every graph in (batch[i-1], batch[i]]; the sentinel i == N closes the rest.
-__device__ __forceinline__ void graph_ptr_body(const int64_t* __restrict__ batch, int64_t n,
+__device__ __forceinline__ void graph_ptr_body(const void* __restrict__ batch, bool i32, int64_t n,
                                                int64_t num_graphs, int32_t* __restrict__ gptr,
                                                int32_t* status, int64_t i) {
-    int64_t cur = (i < n) ? batch[i] : num_graphs;
-    int64_t prev = (i > 0) ? batch[i - 1] : -1;
+    int64_t cur = (i < n) ? ld_idx(batch, i, i32) : num_graphs;
+    int64_t prev = (i > 0) ? ld_idx(batch, i - 1, i32) : -1;
     bool bad = (i < n) && (cur < 0 || cur >= num_graphs || cur < prev);
     if (bad) {
         if (status) atomicOr(status, DGCNN_GRAPH_BAD_BATCH);
@@ -86,11 +92,11 @@ __device__ __forceinline__ void graph_ptr_body(const int64_t* __restrict__ batch
 }
 
 __global__ void __launch_bounds__(256)
-k0_graph_ptr(const int64_t* __restrict__ batch, int64_t n, int64_t num_graphs,
+k0_graph_ptr(const void* __restrict__ batch, bool i32, int64_t n, int64_t num_graphs,
              int32_t* __restrict__ gptr, int32_t* status) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride)
-        graph_ptr_body(batch, n, num_graphs, gptr, status, i);
+        graph_ptr_body(batch, i32, n, num_graphs, gptr, status, i);
 }
 
 __device__ __forceinline__ int block_sum_256(int v, int* smem /*[8]*/) {
@@ -112,8 +118,8 @@ __device__ __forceinline__ int block_sum_256(int v, int* smem /*[8]*/) {
 // normal case -- the flag is clear and every thread leaves at once: one empty launch instead
 // of six.
 struct GenericArgs {
-    const int64_t* src; const int64_t* dst; int64_t e0;
-    const int64_t* batch; int64_t n; int64_t num_graphs;
+    const void* src; const void* dst; int64_t e0; bool i32;
+    const void* batch; int64_t n; int64_t num_graphs;
     int32_t* indeg; int32_t* outdeg; int32_t* bsum; int64_t nb;
     int32_t* rowptr; int32_t* rowptr_t; float* dis;
     int32_t* tmp_in; int32_t* tmp_out; int32_t* col; int32_t* col_t;
@@ -135,7 +141,7 @@ k0_generic(GenericArgs a) {
     // 1. degrees (self loops dropped: the +1 in dis re-adds exactly one loop per node)
     if (tid == 0 && a.status) atomicOr(a.status, DGCNN_GRAPH_GENERIC);      // not proven symmetric
     for (int64_t e = tid; e < a.e0; e += stride) {
-        const int64_t s = a.src[e], d = a.dst[e];
+        const int64_t s = ld_idx(a.src, e, a.i32), d = ld_idx(a.dst, e, a.i32);
         if ((uint64_t)s >= (uint64_t)a.n || (uint64_t)d >= (uint64_t)a.n) {
             if (a.status) atomicOr(a.status, DGCNN_GRAPH_BAD_EDGE);
             continue;
@@ -232,7 +238,7 @@ k0_generic(GenericArgs a) {
     // 5. scatter sources (targets) into their rows; the degree counters double as reverse
     //    cursors, so they end at zero
     for (int64_t e = tid; e < a.e0; e += stride) {
-        const int64_t s = a.src[e], d = a.dst[e];
+        const int64_t s = ld_idx(a.src, e, a.i32), d = ld_idx(a.dst, e, a.i32);
         if ((uint64_t)s >= (uint64_t)a.n || (uint64_t)d >= (uint64_t)a.n || s == d) continue;
         const int p = atomicSub(&a.indeg[d], 1) - 1;
         a.tmp_in[a.rowptr[d] + p] = (int32_t)s;
@@ -299,8 +305,8 @@ __device__ __forceinline__ uint32_t pair_mix(uint32_t a, uint32_t b, uint32_t k1
 // k0_finalize raises the flag when either sum is non-zero.  (The exact check, one binary
 // search per edge, is k0_fast_verify: `exact_verify` of dgcnn_build_graph.)
 __global__ void __launch_bounds__(256)
-k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0,
-              const int64_t* __restrict__ batch, int64_t n, int64_t num_graphs,
+k0_fast_build(const void* __restrict__ src, const void* __restrict__ dst, int64_t e0,
+              const void* __restrict__ batch, bool i32, int64_t n, int64_t num_graphs,
               int32_t* __restrict__ rowptr, int32_t* __restrict__ col,
               int32_t* __restrict__ rowptr_t, int32_t* __restrict__ col_t,
               int32_t* __restrict__ gptr, int32_t* flags, int32_t* status) {
@@ -311,8 +317,8 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
     for (int64_t e = tid; e <= e0; e += stride) {
         int64_t s = n, d = 0;
         if (e < e0) {
-            s = src[e];
-            d = dst[e];
+            s = ld_idx(src, e, i32);
+            d = ld_idx(dst, e, i32);
             if ((uint64_t)s >= (uint64_t)n || (uint64_t)d >= (uint64_t)n) {
                 if (status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE);
                 atomicOr(flags, 1);
@@ -331,8 +337,8 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
         }
         int64_t ps = -1, pd = -1;
         if (e > 0) {
-            ps = src[e - 1];
-            pd = dst[e - 1];
+            ps = ld_idx(src, e - 1, i32);
+            pd = ld_idx(dst, e - 1, i32);
             if ((uint64_t)ps >= (uint64_t)n) { atomicOr(flags, 1); continue; }
         }
         if (e < e0 && !(ps < s || (ps == s && pd < d))) atomicOr(flags, 1);   // not strictly sorted
@@ -363,7 +369,7 @@ k0_fast_build(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, 
     }
     if (gptr)
         for (int64_t i = tid; i <= n; i += stride)
-            graph_ptr_body(batch, n, num_graphs, gptr, status, i);
+            graph_ptr_body(batch, i32, n, num_graphs, gptr, status, i);
 }
 
 // After the streaming pass: dis from the row lengths (in-degree == out-degree once the
@@ -419,14 +425,14 @@ k0_finalize(int64_t n, const int32_t* __restrict__ rowptr, float* __restrict__ d
 // exact symmetry check (optional): every edge (s,d) must find s in row d (rows are sorted:
 // binary search)
 __global__ void __launch_bounds__(256)
-k0_fast_verify(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e0, int64_t n,
+k0_fast_verify(const void* __restrict__ src, const void* __restrict__ dst, bool i32, int64_t e0, int64_t n,
                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int32_t* flags) {
     if (*flags & 1) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t e = tid; e < e0; e += stride) {
-        const int32_t s = (int32_t)src[e];
-        const int64_t d = dst[e];
+        const int32_t s = (int32_t)ld_idx(src, e, i32);
+        const int64_t d = ld_idx(dst, e, i32);
         int lo = rowptr[d], hi = rowptr[d + 1];
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
@@ -451,18 +457,18 @@ extern "C" int dgcnn_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t 
         return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    k0_graph_ptr<<<grid_for(num_nodes + 1, 256, 8), 256, 0, st>>>(batch, num_nodes, num_graphs, gptr,
+    k0_graph_ptr<<<grid_for(num_nodes + 1, 256, 8), 256, 0, st>>>(batch, false, num_nodes, num_graphs, gptr,
                                                                  status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }
 
-extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, const int64_t* batch,
-                                 int64_t num_nodes, int64_t num_graphs, int32_t* rowptr,
-                                 int32_t* col, int32_t* rowptr_t, int32_t* col_t, float* dis,
-                                 int32_t* gptr, int32_t* gorder, int32_t* status,
-                                 int32_t exact_verify, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+static int build_graph_impl(const void* edge_index, bool i32, int64_t num_edges, const void* batch,
+                            int64_t num_nodes, int64_t num_graphs, int32_t* rowptr,
+                            int32_t* col, int32_t* rowptr_t, int32_t* col_t, float* dis,
+                            int32_t* gptr, int32_t* gorder, int32_t* status,
+                            int32_t exact_verify, void* workspace, size_t workspace_bytes,
+                            void* stream) {
     const int64_t n = num_nodes, e0 = num_edges;
     if (n < 0 || e0 < 0 || num_graphs < 0 || !rowptr || !dis) return DGCNN_ERR_INVALID_ARGUMENT;
     if (e0 > 0 && (!edge_index || !col)) return DGCNN_ERR_INVALID_ARGUMENT;
@@ -477,19 +483,20 @@ extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, c
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     BuildWorkspace w = carve_build_workspace(reinterpret_cast<void*>(aligned), n, e0);
-    const int64_t* src = edge_index;
-    const int64_t* dst = edge_index + e0;
+    const void* src = edge_index;
+    const void* dst = i32 ? static_cast<const void*>(static_cast<const int32_t*>(edge_index) + e0)
+                          : static_cast<const void*>(static_cast<const int64_t*>(edge_index) + e0);
 
     size_t clear_span = (size_t)((char*)w.outdeg - (char*)w.flags) + sizeof(int32_t) * (size_t)n;
     if (cudaMemsetAsync(w.flags, 0, clear_span, st) != cudaSuccess) return DGCNN_ERR_CUDA;
 
     // fast path (sorted + symmetric input), verified on the device
     int64_t work = e0 + 1 > n + 1 ? e0 + 1 : n + 1;
-    k0_fast_build<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, batch, n, num_graphs, rowptr,
+    k0_fast_build<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, batch, i32, n, num_graphs, rowptr,
                                                           col, rowptr_t, col_t, gptr, w.flags, status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (exact_verify) {
-        k0_fast_verify<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, n, rowptr, col, w.flags);
+        k0_fast_verify<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, i32, e0, n, rowptr, col, w.flags);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     int fin_grid = grid_for(n + 1, 1024, 1);
@@ -503,7 +510,7 @@ extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, c
 
     // generic path: one cooperative launch that returns at once unless the flag was raised
     GenericArgs ga;
-    ga.src = src; ga.dst = dst; ga.e0 = e0; ga.batch = batch; ga.n = n; ga.num_graphs = num_graphs;
+    ga.src = src; ga.dst = dst; ga.e0 = e0; ga.i32 = i32; ga.batch = batch; ga.n = n; ga.num_graphs = num_graphs;
     ga.indeg = w.indeg; ga.outdeg = transposed ? w.outdeg : nullptr; ga.bsum = w.bsum; ga.nb = w.nb;
     ga.rowptr = rowptr; ga.rowptr_t = rowptr_t; ga.dis = dis;
     ga.tmp_in = w.tmp_in; ga.tmp_out = w.tmp_out; ga.col = col; ga.col_t = col_t;
@@ -521,4 +528,26 @@ extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, c
                                     dim3(kScanThreads), args, 0, st) != cudaSuccess)
         return DGCNN_ERR_CUDA;
     return DGCNN_OK;
+}
+
+extern "C" int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges, const int64_t* batch,
+                                 int64_t num_nodes, int64_t num_graphs, int32_t* rowptr,
+                                 int32_t* col, int32_t* rowptr_t, int32_t* col_t, float* dis,
+                                 int32_t* gptr, int32_t* gorder, int32_t* status,
+                                 int32_t exact_verify, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    return build_graph_impl(edge_index, false, num_edges, batch, num_nodes, num_graphs, rowptr, col,
+                            rowptr_t, col_t, dis, gptr, gorder, status, exact_verify, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int dgcnn_build_graph_i32(const int32_t* edge_index, int64_t num_edges, const int32_t* batch,
+                                     int64_t num_nodes, int64_t num_graphs, int32_t* rowptr,
+                                     int32_t* col, int32_t* rowptr_t, int32_t* col_t, float* dis,
+                                     int32_t* gptr, int32_t* gorder, int32_t* status,
+                                     int32_t exact_verify, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    return build_graph_impl(edge_index, true, num_edges, batch, num_nodes, num_graphs, rowptr, col,
+                            rowptr_t, col_t, dis, gptr, gorder, status, exact_verify, workspace,
+                            workspace_bytes, stream);
 }

@@ -118,14 +118,17 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
                 transpose: bool = True, max_nodes: int = 0) -> Graph:
     """K0 (model.py:28 + gcn_norm prologue + to_dense_batch offsets), once per batch."""
     lib = _lib.load_library()
-    _require_cuda(edge_index, "edge_index", torch.int64)
+    # int64 indices are the reference's (PyG's) format; int32 is the compact host format
+    compact = isinstance(edge_index, Tensor) and edge_index.dtype == torch.int32
+    idt = torch.int32 if compact else torch.int64
+    _require_cuda(edge_index, "edge_index", idt)
     if edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise ValueError("dgcnn_b200: edge_index must be [2, E]")
     edge_index = edge_index.contiguous()
     dev = edge_index.device
     n, e, b = int(num_nodes), int(edge_index.size(1)), int(num_graphs)
     if batch is not None:
-        _require_cuda(batch, "batch", torch.int64)
+        _require_cuda(batch, "batch", idt)
         batch = batch.contiguous()
         if batch.numel() != n:
             raise ValueError("dgcnn_b200: batch must have one entry per node")
@@ -141,7 +144,8 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
     wbytes = lib.dgcnn_build_graph_workspace_bytes(n, e)
     ws = _workspace(wbytes, dev)
     with torch.cuda.device(dev):
-        rc = lib.dgcnn_build_graph(_ptr(edge_index), e, _ptr(batch), n, b,
+        entry = lib.dgcnn_build_graph_i32 if compact else lib.dgcnn_build_graph
+        rc = entry(_ptr(edge_index), e, _ptr(batch), n, b,
                                    _ptr(rowptr), _ptr(col), _ptr(rowptr_t), _ptr(col_t),
                                    _ptr(dis), _ptr(gptr), _ptr(gorder), _ptr(status),
                                    int(EXACT_SYMMETRY_CHECK), _ptr(ws), ws.numel(), _stream())
@@ -177,7 +181,10 @@ def _build_bitmaps(graph: Graph, transpose: bool, batch: Optional[Tensor] = None
         rc = lib.dgcnn_build_bitmaps(_ptr(graph.rowptr), _ptr(graph.col),
                                      _ptr(graph.rowptr_t) if transpose else None,
                                      _ptr(graph.col_t) if transpose else None,
-                                     _ptr(graph.gptr), _ptr(batch), n, b, mx,
+                                     _ptr(graph.gptr),
+                                     _ptr(batch) if batch is not None and batch.dtype == torch.int64 else None,
+                                     _ptr(batch) if batch is not None and batch.dtype == torch.int32 else None,
+                                     n, b, mx,
                                      _ptr(graph.bitmap), _ptr(graph.bitmap_t), words,
                                      _ptr(graph.bmoff), _ptr(graph.gflags), _ptr(graph.gflags_t),
                                      _ptr(graph.fragmap), fwords, _ptr(graph.fgoff),

@@ -100,6 +100,14 @@ int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges,
                       int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
                       float* dis, int32_t* gptr, int32_t* gorder, int32_t* status,
                       int32_t exact_verify, void* workspace, size_t workspace_bytes, void* stream);
+/* The same for COMPACT host batches: edge_index [2,E] and batch [N] as int32 (a loader that
+ * collates int32 indices halves the host-to-device copy of train.py:36, which is what bounds
+ * the end-to-end rate: 16 of the 16.2 bytes per edge are indices). */
+int dgcnn_build_graph_i32(const int32_t* edge_index, int64_t num_edges,
+                          const int32_t* batch, int64_t num_nodes, int64_t num_graphs,
+                          int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t,
+                          float* dis, int32_t* gptr, int32_t* gorder, int32_t* status,
+                          int32_t exact_verify, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * K0b  per-graph adjacency bitmaps (with GCNConv's self loop) for the fused per-graph
@@ -107,7 +115,8 @@ int dgcnn_build_graph(const int64_t* edge_index, int64_t num_edges,
  * when bitmap_t is given, `bitmap_t` (A_hat^T) from rowptr_t/col_t -- that half is skipped ON
  * THE DEVICE when K0 proved the batch symmetric (gate_word/gate_mask: pass K0's status word
  * and DGCNN_GRAPH_GENERIC; a skipped bitmap_t stays all-zero).  Both share bmoff.
- * batch (optional, the reference's int64 [N] vector) saves a search per node row.
+ * batch / batch32 (optional, at most one: the reference's int64 [N] vector or its int32 form)
+ * saves a search per node row.
  *   bitmap  uint32[dgcnn_graph_bitmap_words(N, B, max_nodes)]; graph g owns
  *           np_g * ceil(np_g/32) words at bmoff[g], np_g = n_g rounded up to 16
  *   bmoff   int32[B+1];  gflags int32[B]: bit 0 duplicate edges, bit 1 no bitmap (too large)
@@ -125,7 +134,7 @@ int64_t dgcnn_graph_bitmap_words(int64_t num_nodes, int64_t num_graphs, int64_t 
 int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_graphs, int64_t max_nodes);
 int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
                         const int32_t* rowptr_t, const int32_t* col_t,
-                        const int32_t* gptr, const int64_t* batch,
+                        const int32_t* gptr, const int64_t* batch, const int32_t* batch32,
                         int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                         uint32_t* bitmap, uint32_t* bitmap_t, int64_t bitmap_words,
                         int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,

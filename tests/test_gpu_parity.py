@@ -136,6 +136,34 @@ def test_build_graph_fast_path_equals_generic_path():
         np.testing.assert_allclose(g3.dis.cpu().numpy(), dis, rtol=2e-7)
 
 
+def test_build_graph_int32_indices_equal_int64():
+    """dgcnn_build_graph_i32 (compact host batches) gives the same graph as the int64 entry
+    point, on the fast path (sorted symmetric batch) and on the generic one (shuffled edges)."""
+    b = make_batch("collab", num_graphs=24)
+    mx = int((b.ptr[1:] - b.ptr[:-1]).max())
+    perm = torch.randperm(b.edge_index.size(1), generator=torch.Generator().manual_seed(1))
+    for ei in (b.edge_index, b.edge_index[:, perm].contiguous()):
+        g64 = ops.build_graph(ei.to(DEV), b.batch.to(DEV), b.num_nodes, b.num_graphs, max_nodes=mx)
+        g32 = ops.build_graph(ei.to(torch.int32).to(DEV), b.batch.to(torch.int32).to(DEV), b.num_nodes,
+                              b.num_graphs, max_nodes=mx)
+        assert int(g64.status.item()) == int(g32.status.item())
+        e = ei.size(1)
+        for name in ("rowptr", "rowptr_t", "dis", "gptr", "gorder", "bitmap", "bmoff", "gflags", "fgoff",
+                     "gdesc"):
+            assert torch.equal(getattr(g64, name), getattr(g32, name)), name
+        used = int(g64.fgoff[-1])                   # the buffer is sized by an upper bound
+        assert torch.equal(g64.fragmap[:used], g32.fragmap[:used])
+        assert torch.equal(g64.col[:e], g32.col[:e]) and torch.equal(g64.col_t[:e], g32.col_t[:e])
+    # and the whole model runs on a compact batch
+    cfg = CONFIGS["collab"]
+    torch.manual_seed(0)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    d64, d32 = b.to(DEV), b.compact().to(DEV)
+    d64.max_nodes = d32.max_nodes = mx
+    with torch.no_grad():
+        assert torch.equal(model(d64), model(d32))
+
+
 def test_fingerprint_symmetry_check_rejects_asymmetric_sorted_lists(monkeypatch):
     """K0's fast path proves symmetry with multiset fingerprints.  Sorted, duplicate-free lists
     that are NOT symmetric -- including ones that keep every in/out degree intact -- must take

@@ -1,0 +1,185 @@
+// One training step of the reference loop (train.py:35-45: model(data) -> NLL -> backward ->
+// Adam) as ONE host call: K0 -> K0b -> KS -> KT forward -> NLL -> KT backward -> KSB ->
+// [peer all-reduce +] Adam, every intermediate buffer carved from a caller-owned arena.
+// The Python trainer makes the same sequence of C-ABI calls one by one (~30 launches, ~45
+// allocations: ~0.5 ms of interpreter time per step, more than the GPU needs for the
+// reference's small batches); this entry point is the same sequence without the interpreter.
+// No allocation, no synchronisation: capturable in a CUDA graph.
+#include "common.cuh"
+
+namespace {
+
+struct Arena {
+    char* base;
+    size_t off;
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += sizeof(T) * (count ? count : 1);
+        return p;
+    }
+};
+
+struct StepBuffers {
+    int32_t *rowptr, *col, *rowptr_t, *col_t, *gptr, *gorder, *bmoff, *gflags, *gflags_t, *fgoff, *gdesc, *perm;
+    uint32_t *bitmap, *bitmap_t, *fragmap;
+    float *dis, *xcat, *pooled, *h1, *h2, *h3, *logp, *dlogp, *dpooled;
+    uint8_t *arg, *keep;
+    void *ws_build, *ws_fwd, *ws_tail_f, *ws_tail_b, *ws_bwd;
+    size_t n_build, n_fwd, n_tail, n_bwd;
+    int64_t bm_words, fm_words;
+};
+
+constexpr int kXcatLd = 100;
+
+StepBuffers carve(Arena& a, int64_t N, int64_t E, int64_t B, int32_t F, int32_t k, int32_t C,
+                  int64_t max_nodes) {
+    StepBuffers s{};
+    const int64_t l1 = k / 2, d1 = 32 * (l1 - 4);
+    s.bm_words = dgcnn_graph_bitmap_words(N, B, max_nodes);
+    s.fm_words = dgcnn_graph_fragmap_words(N, B, max_nodes);
+    s.rowptr = a.take<int32_t>(N + 1);
+    s.col = a.take<int32_t>(E);
+    s.rowptr_t = a.take<int32_t>(N + 1);
+    s.col_t = a.take<int32_t>(E);
+    s.dis = a.take<float>(N);
+    s.gptr = a.take<int32_t>(B + 1);
+    s.gorder = a.take<int32_t>(B);
+    s.bitmap = a.take<uint32_t>(2 * s.bm_words);          // A_hat | A_hat^T, adjacent: one memset
+    s.bitmap_t = s.bitmap ? s.bitmap + s.bm_words : nullptr;
+    s.bmoff = a.take<int32_t>(B + 1);
+    s.gflags = a.take<int32_t>(B);
+    s.gflags_t = a.take<int32_t>(B);
+    s.fragmap = a.take<uint32_t>(s.fm_words);
+    s.fgoff = a.take<int32_t>(B + 1);
+    s.gdesc = a.take<int32_t>(4 * B);
+    s.xcat = a.take<float>(N * kXcatLd);
+    s.pooled = a.take<float>(B * k * 97);
+    s.perm = a.take<int32_t>(B * k);
+    s.h1 = a.take<float>(B * 16 * l1);
+    s.arg = a.take<uint8_t>(B * 16 * l1);
+    s.h2 = a.take<float>(B * d1);
+    s.h3 = a.take<float>(B * 128);
+    s.keep = a.take<uint8_t>(B * 128);
+    s.logp = a.take<float>(B * C);
+    s.dlogp = a.take<float>(B * C);
+    s.dpooled = a.take<float>(B * k * 97);
+    s.n_build = dgcnn_build_graph_workspace_bytes(N, E);
+    s.n_fwd = dgcnn_stack_fwd_workspace_bytes();
+    s.n_tail = dgcnn_tail_workspace_bytes(B, k, C);
+    s.n_bwd = dgcnn_stack_bwd_workspace_bytes(F, B, N);
+    s.ws_build = a.take<char>(s.n_build);
+    s.ws_fwd = a.take<char>(s.n_fwd);
+    s.ws_tail_f = a.take<char>(s.n_tail);
+    s.ws_tail_b = a.take<char>(s.n_tail);
+    s.ws_bwd = a.take<char>(s.n_bwd);
+    return s;
+}
+
+}  // namespace
+
+extern "C" size_t dgcnn_train_step_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t num_graphs,
+                                                   int32_t num_features, int32_t k, int32_t num_classes,
+                                                   int64_t max_nodes) {
+    if (num_nodes < 0 || num_edges < 0 || num_graphs < 1 || num_features < 1 || k < 10 || num_classes < 1 ||
+        max_nodes < 1)
+        return 0;
+    Arena a{nullptr, 0};
+    carve(a, num_nodes, num_edges, num_graphs, num_features, k, num_classes, max_nodes);
+    return a.off + 512;
+}
+
+extern "C" int64_t dgcnn_train_step_num_params(int32_t num_features, int32_t k, int32_t num_classes) {
+    const int64_t d1 = 32 * ((int64_t)k / 2 - 4);
+    return dgcnn_stack_num_params(num_features) + 16 * 97 + 16 + 32 * 16 * 5 + 32 + 128 * d1 + 128 +
+           (int64_t)num_classes * 128 + num_classes;
+}
+
+extern "C" int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_index, int32_t index_is_i32,
+                                const void* batch, const int64_t* y, int64_t num_nodes, int64_t num_edges,
+                                int64_t num_graphs, int32_t num_features, int32_t k, int32_t num_classes,
+                                int64_t max_nodes, int32_t norm, float* params, float* grads,
+                                float* exp_avg, float* exp_avg_sq, int64_t* step, float lr, float beta1,
+                                float beta2, float eps, int64_t global_batch, int32_t training,
+                                uint64_t seed, int64_t* rng_offset, void* const* exchange, int32_t world,
+                                int32_t rank, int64_t* epoch, int32_t* comm_status, int32_t* graph_status,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    const int64_t N = num_nodes, E = num_edges, B = num_graphs;
+    const int32_t F = num_features, C = num_classes;
+    if (N < 1 || E < 0 || B < 1 || F < 1 || k < 10 || C < 1 || max_nodes < 1 || global_batch < 1)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!x || !edge_index || !batch || !y || !params || !grads || !exp_avg || !exp_avg_sq || !step ||
+        !graph_status || !workspace)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (training && !rng_offset) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (C > 32) return DGCNN_ERR_UNSUPPORTED;
+    const int bwd_kind = dgcnn_stack_bwd_supported(F, max_nodes);     // 0 no, 1 MMA, 2 FMA only
+    if (!dgcnn_stack_fwd_supported(F, max_nodes) || bwd_kind == 0) return DGCNN_ERR_UNSUPPORTED;
+    if (workspace_bytes < dgcnn_train_step_workspace_bytes(N, E, B, F, k, C, max_nodes))
+        return DGCNN_ERR_WORKSPACE;
+    Arena a{reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255), 0};
+    StepBuffers s = carve(a, N, E, B, F, k, C, max_nodes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    // parameters and gradients: the flat layout of FusedTrainer (PyG order for the graph
+    // convolutions, then conv5, conv6, classifier_1, classifier_2; weight before bias)
+    const int64_t d1 = 32 * ((int64_t)k / 2 - 4);
+    const int64_t sizes[16] = {32LL * F, 32, 32 * 32, 32, 32 * 32, 32, 32, 1,
+                               16 * 97, 16, 32 * 16 * 5, 32, 128 * d1, 128, (int64_t)C * 128, C};
+    float* p[16];
+    float* g[16];
+    int64_t off = 0;
+    for (int i = 0; i < 16; ++i) { p[i] = params + off; g[i] = grads + off; off += sizes[i]; }
+    const int64_t n_params = off;
+    float* stats = grads + n_params;                  // [sum of NLL, #correct] ride the all-reduce
+
+#define DGCNN_TRY(call) do { const int rc_ = (call); if (rc_ != DGCNN_OK) return rc_; } while (0)
+    if (cudaMemsetAsync(graph_status, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
+    if (index_is_i32)
+        DGCNN_TRY(dgcnn_build_graph_i32(static_cast<const int32_t*>(edge_index), E,
+                                        static_cast<const int32_t*>(batch), N, B, s.rowptr, s.col, s.rowptr_t,
+                                        s.col_t, s.dis, s.gptr, s.gorder, graph_status, 0, s.ws_build,
+                                        s.n_build, stream));
+    else
+        DGCNN_TRY(dgcnn_build_graph(static_cast<const int64_t*>(edge_index), E,
+                                    static_cast<const int64_t*>(batch), N, B, s.rowptr, s.col, s.rowptr_t,
+                                    s.col_t, s.dis, s.gptr, s.gorder, graph_status, 0, s.ws_build, s.n_build,
+                                    stream));
+    DGCNN_TRY(dgcnn_build_bitmaps(s.rowptr, s.col, s.rowptr_t, s.col_t, s.gptr,
+                                  index_is_i32 ? nullptr : static_cast<const int64_t*>(batch),
+                                  index_is_i32 ? static_cast<const int32_t*>(batch) : nullptr, N, B, max_nodes,
+                                  s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags, s.gflags_t, s.fragmap,
+                                  s.fm_words, s.fgoff, s.gorder, s.gdesc, graph_status, DGCNN_GRAPH_GENERIC,
+                                  stream));
+    DGCNN_TRY(dgcnn_stack_fwd(x, ldx, F, s.rowptr, s.col, s.dis, s.gptr, s.gorder, s.bitmap, s.bmoff,
+                              s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, max_nodes, p[0], p[1], p[2], p[3],
+                              p[4], p[5], p[6], p[7], s.xcat, kXcatLd, s.pooled, s.perm, k, norm,
+                              DGCNN_STACK_MMA, graph_status, s.ws_fwd, s.n_fwd, stream));
+    DGCNN_TRY(dgcnn_tail_fwd(s.pooled, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, training,
+                             seed, rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp, s.ws_tail_f, s.n_tail,
+                             stream));
+    DGCNN_TRY(dgcnn_nll_sum(s.logp, y, B, C, 1.0f, stats, s.dlogp, stream));
+    // the tail's parameter gradients run on the library's side stream underneath KSB
+    DGCNN_TRY(dgcnn_tail_bwd(s.dlogp, s.pooled, B, k, p[8], p[10], p[12], p[14], C, s.h1, s.arg, s.h2, s.h3,
+                             s.keep, s.logp, s.dpooled, g[8], g[9], g[10], g[11], g[12], g[13], g[14], g[15],
+                             2, s.ws_tail_b, s.n_tail, stream));
+    DGCNN_TRY(dgcnn_stack_bwd(s.dpooled, s.perm, k, s.xcat, kXcatLd, x, ldx, F, s.rowptr_t, s.col_t, s.dis,
+                              s.gptr, s.gorder, s.gdesc, s.fragmap, s.bitmap, s.bmoff, s.gflags, s.bitmap_t,
+                              s.bmoff, s.gflags_t, N, B, max_nodes, p[2], p[4], p[6], norm,
+                              bwd_kind == 1 ? DGCNN_STACK_MMA : DGCNN_STACK_FMA, grads, graph_status, s.ws_bwd,
+                              s.n_bwd, stream));
+    DGCNN_TRY(dgcnn_tail_bwd_join(stream));
+    const float scale = 1.0f / (float)global_batch;
+    if (world > 1 && exchange) {
+        if (!epoch) return DGCNN_ERR_INVALID_ARGUMENT;
+        DGCNN_TRY(dgcnn_allreduce_adam(params, grads, exp_avg, exp_avg_sq, n_params, n_params + 2, step, epoch,
+                                       lr, beta1, beta2, eps, scale, exchange, world, rank, comm_status,
+                                       stream));
+    } else {
+        DGCNN_TRY(dgcnn_adam_step(params, grads, exp_avg, exp_avg_sq, n_params, step, lr, beta1, beta2, eps,
+                                  scale, stream));
+    }
+#undef DGCNN_TRY
+    return DGCNN_OK;
+}

@@ -68,6 +68,11 @@ class FusedTrainer:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        # dgcnn_train_step: the whole step as ONE call into the library (DGCNN_NATIVE_STEP=0 keeps
+        # the one-by-one Python sequence below, which is also the fallback)
+        self.native = os.environ.get("DGCNN_NATIVE_STEP", "1") != "0"
+        self._arena = None
+        self._graph_status = torch.zeros(1, dtype=torch.int32, device=dev)
         # multi-GPU: gradients are summed by the fused peer-memory all-reduce + Adam kernel when
         # the ranks (one node) can map each other's memory, else by NCCL (DGCNN_ALLREDUCE=nccl)
         self.exchange = None
@@ -100,6 +105,8 @@ class FusedTrainer:
             raise RuntimeError("FusedTrainer.step: batch not supported by the fused kernels "
                                "(set data.max_nodes; graphs must fit shared memory)")
         world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        if self.native and self._native_step(data, global_batch, world):
+            return self.stats
         graph = m.build_graph(data)
         weights = self.stack_params[0::2]
         biases = self.stack_params[1::2]
@@ -128,3 +135,48 @@ class FusedTrainer:
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
                       self.betas[0], self.betas[1], self.eps, grad_scale=1.0 / float(global_batch))
         return self.stats
+
+    def _native_step(self, data, global_batch, world) -> bool:
+        """The same step through dgcnn_train_step (one ctypes call, buffers from a cached arena);
+        False when the configuration is outside what that entry point covers."""
+        import ctypes
+        from . import _lib
+        m = self.model
+        x, ei, bt, y = data.x, data.edge_index, data.batch, data.y
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and
+                ei.dtype in (torch.int32, torch.int64) and bt.dtype == ei.dtype and y.dtype == torch.int64 and
+                ei.is_contiguous() and bt.is_contiguous() and y.is_contiguous() and
+                ops.STACK_VARIANT == ops.STACK_MMA and ops.TAIL_OVERLAP and not ops.EXACT_SYMMETRY_CHECK):
+            return False
+        if world > 1 and self.exchange is None:
+            return False                                   # NCCL path: keep the Python sequence
+        lib = _lib.load_library()
+        n, f = x.shape
+        e, b = ei.size(1), int(data.num_graphs)
+        k, c = m.sort_pool.k, m.classifier_2.out_features
+        mx = int(data.max_nodes)
+        if self.num_params != int(lib.dgcnn_train_step_num_params(f, k, c)) or e < 1:
+            return False
+        need = int(lib.dgcnn_train_step_workspace_bytes(n, e, b, f, k, c, mx))
+        if self._arena is None or self._arena.numel() < need:
+            self._arena = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=x.device)
+        if global_batch is None:
+            global_batch = b * world
+        table, epoch, rank = None, None, 0
+        if world > 1:
+            table = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p_)) for p_ in self.exchange.ptrs])
+            epoch, rank = self.exchange.epoch.data_ptr(), self.exchange.rank
+        with torch.cuda.device(x.device):
+            rc = lib.dgcnn_train_step(
+                x.data_ptr(), int(x.stride(0)) if n > 1 else max(int(x.stride(0)), f), ei.data_ptr(),
+                int(ei.dtype == torch.int32), bt.data_ptr(), y.data_ptr(), n, e, b, f, k, c, mx, int(m.conv1.norm),
+                self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                self.step_count.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, int(global_batch),
+                int(bool(m.training)), int(m._tail_seed) & 0xFFFFFFFFFFFFFFFF, m._tail_rng_offset.data_ptr(),
+                table, world, rank, epoch, self.comm_status.data_ptr(), self._graph_status.data_ptr(),
+                self._arena.data_ptr(), self._arena.numel(), torch.cuda.current_stream().cuda_stream)
+        if rc == -2:                                       # DGCNN_ERR_UNSUPPORTED: graphs too large for KS / KSB
+            return False
+        _lib.check(rc, "train_step")
+        ops.LAUNCHES["train_step"] = ops.LAUNCHES.get("train_step", 0) + 29
+        return True

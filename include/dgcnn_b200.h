@@ -354,6 +354,39 @@ int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg, float* exp
                          void* const* exchange, int32_t world, int32_t rank, int32_t* status,
                          void* stream);
 
+/* ------------------------------------------------------------------------
+ * One training step of train.py:35-45 (model(data) -> NLL -> backward -> Adam) as ONE host
+ * call: K0 -> K0b -> KS -> KT forward -> NLL -> KT backward (parameter gradients on the side
+ * stream) -> KSB -> [dgcnn_allreduce_adam | dgcnn_adam_step], every intermediate buffer carved
+ * from `workspace`.  Same kernels, same order and same results as the one-by-one sequence.
+ *   edge_index/batch  int64 (index_is_i32 = 0, the reference's format) or int32
+ *   params, grads, exp_avg, exp_avg_sq   flat fp32, dgcnn_train_step_num_params() entries in
+ *       the order conv1.lin.weight [32,F], conv1.bias, conv2.*, conv3.*, conv4.lin.weight
+ *       [1,32], conv4.bias, conv5.weight [16,1,97], conv5.bias, conv6.weight [32,16,5],
+ *       conv6.bias, classifier_1.weight [128, 32(k/2-4)], .bias, classifier_2.weight [C,128],
+ *       .bias; grads has two more entries: [sum of NLL, #correct] of this call's batch (summed
+ *       over ranks when exchange != NULL)
+ *   global_batch      the gradient is divided by it (graphs of all ranks)
+ *   exchange/world/rank/epoch/comm_status   as for dgcnn_allreduce_adam; exchange NULL or
+ *       world <= 1: plain Adam
+ *   graph_status      device int32, reset and OR-ed with DGCNN_GRAPH_* by the call
+ * Needs graphs that fit the fused kernels (dgcnn_stack_fwd_supported / _bwd_supported), else
+ * DGCNN_ERR_UNSUPPORTED.  No allocation, no synchronisation: capturable in a CUDA graph.
+ * ------------------------------------------------------------------------ */
+size_t dgcnn_train_step_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t num_graphs,
+                                        int32_t num_features, int32_t k, int32_t num_classes,
+                                        int64_t max_nodes);
+int64_t dgcnn_train_step_num_params(int32_t num_features, int32_t k, int32_t num_classes);
+int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_index, int32_t index_is_i32,
+                     const void* batch, const int64_t* y, int64_t num_nodes, int64_t num_edges,
+                     int64_t num_graphs, int32_t num_features, int32_t k, int32_t num_classes,
+                     int64_t max_nodes, int32_t norm, float* params, float* grads,
+                     float* exp_avg, float* exp_avg_sq, int64_t* step, float lr, float beta1,
+                     float beta2, float eps, int64_t global_batch, int32_t training,
+                     uint64_t seed, int64_t* rng_offset, void* const* exchange, int32_t world,
+                     int32_t rank, int64_t* epoch, int32_t* comm_status, int32_t* graph_status,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

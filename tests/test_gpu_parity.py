@@ -939,6 +939,40 @@ def test_fused_trainer_matches_autograd_training():
     assert int(trainer.step_count.item()) == 3
 
 
+@pytest.mark.parametrize("name,count,compact", [("proteins", 64, False), ("collab", 48, False), ("mutag", 50, True)])
+def test_native_train_step_equals_the_python_sequence(name, count, compact, monkeypatch):
+    """dgcnn_train_step (one host call, arena-carved buffers) launches the same kernels in the
+    same order as FusedTrainer's one-by-one sequence: parameters, Adam state and the
+    loss / accuracy scalars must match bit for bit, step after step, also for int32 batches."""
+    import copy
+    cfg = CONFIGS[name]
+    batches = []
+    for i in range(3):
+        hb = make_batch(name, seed=11 + i, num_graphs=count)
+        mx = int((hb.ptr[1:] - hb.ptr[:-1]).max())
+        db = (hb.compact() if compact else hb).to(DEV)
+        db.max_nodes = mx
+        batches.append(db)
+    torch.manual_seed(5)
+    model_a = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    model_b = copy.deepcopy(model_a)
+    monkeypatch.setenv("DGCNN_NATIVE_STEP", "1")
+    tr_a = dg.FusedTrainer(model_a, lr=1e-3)
+    monkeypatch.setenv("DGCNN_NATIVE_STEP", "0")
+    tr_b = dg.FusedTrainer(model_b, lr=1e-3)
+    assert tr_a.native and not tr_b.native
+    for step in range(5):
+        before = ops.LAUNCHES.get("train_step", 0)
+        sa = tr_a.step(batches[step % 3]).clone()
+        assert ops.LAUNCHES.get("train_step", 0) > before, "the native entry point was not used"
+        sb = tr_b.step(batches[step % 3]).clone()
+        assert torch.equal(sa, sb), (step, sa, sb)
+        assert torch.equal(tr_a.flat, tr_b.flat), step
+        assert torch.equal(tr_a.exp_avg_sq, tr_b.exp_avg_sq), step
+        assert torch.equal(tr_a.grad, tr_b.grad), step
+    assert int(tr_a._graph_status.item()) & ~ops.GRAPH_GENERIC == 0
+
+
 def test_cuda_graph_capture_replays_bit_identically():
     cfg = CONFIGS["mutag"]
     batch = make_batch("mutag").to(DEV)

@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-resident", action="store_true", help="skip the resident-data-set leg")
     ap.add_argument("--autograd", action="store_true",
                     help="step through torch autograd (Model + GradBucket + FlatAdam) instead of FusedTrainer")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -529,6 +530,61 @@ def main():
                                "frac_of_peak": 24 * e / t_k0 / 1e9 / peak},
                "per_layer_kernel": per_layer}
 
+    # ---- resident data set: the ring's graphs live in HBM, a step's input is
+    # its list of graph ids; dgcnn_collate replaces the host collate, the H2D copy and K0 ----
+    resident = None
+    if fused_step and world == 1 and not args.no_resident:
+        try:
+            import numpy as np
+            from dgcnn_b200.synth import make_graphs
+            ds_graphs = []
+            for i in range(RING):                         # the same graphs as host_batches[i]
+                ds_graphs += make_graphs(cfg, cfg.batch_size, seed=324 + 1000 * rank + i)
+            ds = dg.DeviceDataset(ds_graphs, dev, num_classes=cfg.num_classes)
+            bs = cfg.batch_size
+            id_sets = [np.arange(i * bs, (i + 1) * bs, dtype=np.int32) for i in range(RING)]
+            id_pinned = [torch.from_numpy(a).pin_memory() for a in id_sets]
+            model.train()
+
+            def resident_run(nsteps):
+                last = 0.0
+                for i in range(nsteps):
+                    ids_dev = id_pinned[i % RING].to(dev, non_blocking=True)     # the step's H2D: 4 B / graph
+                    stats = trainer.step_resident(ds, id_sets[i % RING], ids_dev, global_batch)
+                    last = float(stats[0].item())          # D2H read of the step's result
+                return last
+
+            resident_run(3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            resident_run(e2e_steps)
+            torch.cuda.synchronize()
+            res_s = time.perf_counter() - t0
+            # device time of the gather (+ K0b, like graph_build_us) and of one whole resident step
+            ids0 = id_pinned[0].to(dev)
+            with torch.no_grad():
+                t_gather = timed(lambda: ds.batch(id_sets[0], ids0))
+                t_collate = timed(lambda: ds.batch(id_sets[0], ids0, bitmaps=False))
+            t_res_step = timed(lambda: trainer.step_resident(ds, id_sets[0], ids0, global_batch))
+            gather_bytes = 8 * e + 4 * (n + 1) * 2 + 8 * n + 8 * n * cfg.num_features   # read + write
+            resident = {"value": global_batch * e2e_steps / res_s, "unit": UNIT,
+                        "h2d_bytes_per_step": 4 * bs, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                        "device_step_us": t_res_step * 1e6,
+                        "device_value": global_batch / t_res_step,
+                        "collate_us": t_collate * 1e6, "collate_plus_bitmaps_us": t_gather * 1e6,
+                        "collate_algorithmic_bytes": gather_bytes,
+                        "collate_GBps": gather_bytes / t_collate / 1e9,
+                        "collate_frac_of_peak": gather_bytes / t_collate / 1e9 / peak,
+                        "dataset_bytes_in_hbm": ds.nbytes(), "dataset_graphs": len(ds),
+                        "note": "data set resident in HBM (DeviceDataset); per step: pinned int32 graph ids -> H2D "
+                                "-> FusedTrainer.step_resident (dgcnn_collate gather instead of host collate + "
+                                "H2D of the batch + K0, then K0b .. Adam) -> loss.item(); bit-identical to the "
+                                "host-fed step (tests/test_gpu_resident.py).  NOT `e2e`: the batch tensors never "
+                                "cross PCIe"}
+        except Exception as exc:                       # noqa: BLE001  (never lose the main line)
+            resident = {"error": repr(exc)}
+            print(f"[bench] resident-data-set leg failed: {exc!r}", file=sys.stderr)
+
     cpu = None
     if not args.no_cpu_baseline:
         cb = make_batch(args.workload, seed=324)
@@ -560,6 +616,7 @@ def main():
                               "d2h_bytes_per_step": 4, "steps": e2e_steps,
                               "note": "same loop, host batch collated with int32 edge_index/batch "
                                       "(dgcnn_build_graph_i32): NOT the reference's int64 format; `e2e` is"},
+        "e2e_resident_dataset": resident,
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,

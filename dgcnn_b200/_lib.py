@@ -24,8 +24,30 @@ NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC",
 ]
 
+class DgcnnDataset(ctypes.Structure):
+    """``dgcnn_dataset`` of include/dgcnn_b200.h: a HOST struct of device pointers."""
+    _fields_ = [("num_graphs", c_int64), ("num_nodes", c_int64), ("num_edges", c_int64),
+                ("num_features", c_int32), ("symmetric", c_int32),
+                ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p),
+                ("gptr", c_void_p), ("rowptr", c_void_p), ("col", c_void_p),
+                ("rowptr_t", c_void_p), ("col_t", c_void_p), ("dis", c_void_p)]
+
+
+_DATASET_P = ctypes.POINTER(DgcnnDataset)
+_STEP_TAIL = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int64,
+              c_int32, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+              c_void_p, c_void_p, c_size_t, c_void_p]
+
 # name -> (restype, argtypes); mirrors include/dgcnn_b200.h one to one
 SIGNATURES = {
+    "dgcnn_collate_workspace_bytes": (c_size_t, [c_int64]),
+    "dgcnn_collate": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dgcnn_train_step_resident_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32,
+                                                             c_int32, c_int64]),
+    "dgcnn_train_step_resident": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, c_int32,
+                                            c_int32, c_int64, c_int32] + _STEP_TAIL),
     "dgcnn_abi_version": (c_int32, []),
     "dgcnn_status_string": (c_char_p, [c_int32]),
     "dgcnn_build_graph_workspace_bytes": (c_size_t, [c_int64, c_int64]),

@@ -29,12 +29,16 @@ struct StepBuffers {
     void *ws_build, *ws_fwd, *ws_tail_f, *ws_tail_b, *ws_bwd;
     size_t n_build, n_fwd, n_tail, n_bwd;
     int64_t bm_words, fm_words;
+    // resident data set (dgcnn_train_step_resident): the collated batch lives in the arena too
+    float* x_batch;
+    int32_t* batch32;
+    int64_t* y_batch;
 };
 
 constexpr int kXcatLd = 100;
 
 StepBuffers carve(Arena& a, int64_t N, int64_t E, int64_t B, int32_t F, int32_t k, int32_t C,
-                  int64_t max_nodes) {
+                  int64_t max_nodes, bool resident) {
     StepBuffers s{};
     const int64_t l1 = k / 2, d1 = 32 * (l1 - 4);
     s.bm_words = dgcnn_graph_bitmap_words(N, B, max_nodes);
@@ -65,7 +69,7 @@ StepBuffers carve(Arena& a, int64_t N, int64_t E, int64_t B, int32_t F, int32_t 
     s.logp = a.take<float>(B * C);
     s.dlogp = a.take<float>(B * C);
     s.dpooled = a.take<float>(B * k * 97);
-    s.n_build = dgcnn_build_graph_workspace_bytes(N, E);
+    s.n_build = resident ? dgcnn_collate_workspace_bytes(B) : dgcnn_build_graph_workspace_bytes(N, E);
     s.n_fwd = dgcnn_stack_fwd_workspace_bytes();
     s.n_tail = dgcnn_tail_workspace_bytes(B, k, C);
     s.n_bwd = dgcnn_stack_bwd_workspace_bytes(F, B, N);
@@ -74,6 +78,11 @@ StepBuffers carve(Arena& a, int64_t N, int64_t E, int64_t B, int32_t F, int32_t 
     s.ws_tail_f = a.take<char>(s.n_tail);
     s.ws_tail_b = a.take<char>(s.n_tail);
     s.ws_bwd = a.take<char>(s.n_bwd);
+    if (resident) {
+        s.x_batch = a.take<float>(N * F);
+        s.batch32 = a.take<int32_t>(N);
+        s.y_batch = a.take<int64_t>(B);
+    }
     return s;
 }
 
@@ -86,7 +95,19 @@ extern "C" size_t dgcnn_train_step_workspace_bytes(int64_t num_nodes, int64_t nu
         max_nodes < 1)
         return 0;
     Arena a{nullptr, 0};
-    carve(a, num_nodes, num_edges, num_graphs, num_features, k, num_classes, max_nodes);
+    carve(a, num_nodes, num_edges, num_graphs, num_features, k, num_classes, max_nodes, false);
+    return a.off + 512;
+}
+
+extern "C" size_t dgcnn_train_step_resident_workspace_bytes(int64_t num_nodes, int64_t num_edges,
+                                                            int64_t num_graphs, int32_t num_features,
+                                                            int32_t k, int32_t num_classes,
+                                                            int64_t max_nodes) {
+    if (num_nodes < 0 || num_edges < 0 || num_graphs < 1 || num_features < 1 || k < 10 || num_classes < 1 ||
+        max_nodes < 1)
+        return 0;
+    Arena a{nullptr, 0};
+    carve(a, num_nodes, num_edges, num_graphs, num_features, k, num_classes, max_nodes, true);
     return a.off + 512;
 }
 
@@ -95,6 +116,105 @@ extern "C" int64_t dgcnn_train_step_num_params(int32_t num_features, int32_t k, 
     return dgcnn_stack_num_params(num_features) + 16 * 97 + 16 + 32 * 16 * 5 + 32 + 128 * d1 + 128 +
            (int64_t)num_classes * 128 + num_classes;
 }
+
+namespace {
+
+#define DGCNN_TRY(call) do { const int rc_ = (call); if (rc_ != DGCNN_OK) return rc_; } while (0)
+
+struct StepArgs {
+    int64_t N, E, B;
+    int32_t F, k, C;
+    int64_t max_nodes;
+    int32_t norm;
+    float *params, *grads, *exp_avg, *exp_avg_sq;
+    int64_t* step;
+    float lr, beta1, beta2, eps;
+    int64_t global_batch;
+    int32_t training;
+    uint64_t seed;
+    int64_t* rng_offset;
+    void* const* exchange;
+    int32_t world, rank;
+    int64_t* epoch;
+    int32_t *comm_status, *graph_status;
+    void* workspace;
+    size_t workspace_bytes;
+    void* stream;
+};
+
+int check_step_args(const StepArgs& t, bool resident) {
+    if (t.N < 1 || t.E < 0 || t.B < 1 || t.F < 1 || t.k < 10 || t.C < 1 || t.max_nodes < 1 || t.global_batch < 1)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!t.params || !t.grads || !t.exp_avg || !t.exp_avg_sq || !t.step || !t.graph_status || !t.workspace)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (t.training && !t.rng_offset) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (t.C > 32) return DGCNN_ERR_UNSUPPORTED;
+    if (!dgcnn_stack_fwd_supported(t.F, t.max_nodes) || dgcnn_stack_bwd_supported(t.F, t.max_nodes) == 0)
+        return DGCNN_ERR_UNSUPPORTED;
+    const size_t need = resident
+        ? dgcnn_train_step_resident_workspace_bytes(t.N, t.E, t.B, t.F, t.k, t.C, t.max_nodes)
+        : dgcnn_train_step_workspace_bytes(t.N, t.E, t.B, t.F, t.k, t.C, t.max_nodes);
+    if (t.workspace_bytes < need) return DGCNN_ERR_WORKSPACE;
+    return DGCNN_OK;
+}
+
+// Everything after the graph build: K0b -> KS -> KT forward -> NLL -> KT backward -> KSB ->
+// [peer all-reduce +] Adam.  batch64 / batch32: the node -> graph vector in whichever form
+// the batch has it (K0b saves a search per row with it).
+int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, int64_t ldx,
+                     const int64_t* batch64, const int32_t* batch32, const int64_t* y) {
+    const int64_t N = t.N, B = t.B;
+    const int32_t F = t.F, C = t.C, k = t.k;
+    void* stream = t.stream;
+    // parameters and gradients: the flat layout of FusedTrainer (PyG order for the graph
+    // convolutions, then conv5, conv6, classifier_1, classifier_2; weight before bias)
+    const int64_t d1 = 32 * ((int64_t)k / 2 - 4);
+    const int64_t sizes[16] = {32LL * F, 32, 32 * 32, 32, 32 * 32, 32, 32, 1,
+                               16 * 97, 16, 32 * 16 * 5, 32, 128 * d1, 128, (int64_t)C * 128, C};
+    float* p[16];
+    float* g[16];
+    int64_t off = 0;
+    for (int i = 0; i < 16; ++i) { p[i] = t.params + off; g[i] = t.grads + off; off += sizes[i]; }
+    const int64_t n_params = off;
+    float* stats = t.grads + n_params;                // [sum of NLL, #correct] ride the all-reduce
+    const int bwd_kind = dgcnn_stack_bwd_supported(F, t.max_nodes);   // 1 MMA, 2 FMA only
+
+    DGCNN_TRY(dgcnn_build_bitmaps(s.rowptr, s.col, s.rowptr_t, s.col_t, s.gptr, batch64, batch32, N, B,
+                                  t.max_nodes, s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags,
+                                  s.gflags_t, s.fragmap, s.fm_words, s.fgoff, s.gorder, s.gdesc,
+                                  t.graph_status, DGCNN_GRAPH_GENERIC, stream));
+    DGCNN_TRY(dgcnn_stack_fwd(x, ldx, F, s.rowptr, s.col, s.dis, s.gptr, s.gorder, s.bitmap, s.bmoff,
+                              s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, t.max_nodes, p[0], p[1], p[2], p[3],
+                              p[4], p[5], p[6], p[7], s.xcat, kXcatLd, s.pooled, s.perm, k, t.norm,
+                              DGCNN_STACK_MMA, t.graph_status, s.ws_fwd, s.n_fwd, stream));
+    DGCNN_TRY(dgcnn_tail_fwd(s.pooled, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, t.training,
+                             t.seed, t.rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp, s.ws_tail_f,
+                             s.n_tail, stream));
+    DGCNN_TRY(dgcnn_nll_sum(s.logp, y, B, C, 1.0f, stats, s.dlogp, stream));
+    // the tail's parameter gradients run on the library's side stream underneath KSB
+    DGCNN_TRY(dgcnn_tail_bwd(s.dlogp, s.pooled, B, k, p[8], p[10], p[12], p[14], C, s.h1, s.arg, s.h2, s.h3,
+                             s.keep, s.logp, s.dpooled, g[8], g[9], g[10], g[11], g[12], g[13], g[14], g[15],
+                             2, s.ws_tail_b, s.n_tail, stream));
+    DGCNN_TRY(dgcnn_stack_bwd(s.dpooled, s.perm, k, s.xcat, kXcatLd, x, ldx, F, s.rowptr_t, s.col_t, s.dis,
+                              s.gptr, s.gorder, s.gdesc, s.fragmap, s.bitmap, s.bmoff, s.gflags, s.bitmap_t,
+                              s.bmoff, s.gflags_t, N, B, t.max_nodes, p[2], p[4], p[6], t.norm,
+                              bwd_kind == 1 ? DGCNN_STACK_MMA : DGCNN_STACK_FMA, t.grads, t.graph_status,
+                              s.ws_bwd, s.n_bwd, stream));
+    DGCNN_TRY(dgcnn_tail_bwd_join(stream));
+    const float scale = 1.0f / (float)t.global_batch;
+    if (t.world > 1 && t.exchange) {
+        if (!t.epoch) return DGCNN_ERR_INVALID_ARGUMENT;
+        DGCNN_TRY(dgcnn_allreduce_adam(t.params, t.grads, t.exp_avg, t.exp_avg_sq, n_params, n_params + 2,
+                                       t.step, t.epoch, t.lr, t.beta1, t.beta2, t.eps, scale, t.exchange,
+                                       t.world, t.rank, t.comm_status, stream));
+    } else {
+        DGCNN_TRY(dgcnn_adam_step(t.params, t.grads, t.exp_avg, t.exp_avg_sq, n_params, t.step, t.lr, t.beta1,
+                                  t.beta2, t.eps, scale, stream));
+    }
+    return DGCNN_OK;
+}
+
+}  // namespace
 
 extern "C" int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_index, int32_t index_is_i32,
                                 const void* batch, const int64_t* y, int64_t num_nodes, int64_t num_edges,
@@ -105,36 +225,16 @@ extern "C" int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_in
                                 uint64_t seed, int64_t* rng_offset, void* const* exchange, int32_t world,
                                 int32_t rank, int64_t* epoch, int32_t* comm_status, int32_t* graph_status,
                                 void* workspace, size_t workspace_bytes, void* stream) {
+    const StepArgs t{num_nodes, num_edges, num_graphs, num_features, k, num_classes, max_nodes, norm,
+                     params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, global_batch, training,
+                     seed, rng_offset, exchange, world, rank, epoch, comm_status, graph_status, workspace,
+                     workspace_bytes, stream};
+    if (!x || !edge_index || !batch || !y) return DGCNN_ERR_INVALID_ARGUMENT;
+    DGCNN_TRY(check_step_args(t, false));
     const int64_t N = num_nodes, E = num_edges, B = num_graphs;
-    const int32_t F = num_features, C = num_classes;
-    if (N < 1 || E < 0 || B < 1 || F < 1 || k < 10 || C < 1 || max_nodes < 1 || global_batch < 1)
-        return DGCNN_ERR_INVALID_ARGUMENT;
-    if (!x || !edge_index || !batch || !y || !params || !grads || !exp_avg || !exp_avg_sq || !step ||
-        !graph_status || !workspace)
-        return DGCNN_ERR_INVALID_ARGUMENT;
-    if (training && !rng_offset) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (C > 32) return DGCNN_ERR_UNSUPPORTED;
-    const int bwd_kind = dgcnn_stack_bwd_supported(F, max_nodes);     // 0 no, 1 MMA, 2 FMA only
-    if (!dgcnn_stack_fwd_supported(F, max_nodes) || bwd_kind == 0) return DGCNN_ERR_UNSUPPORTED;
-    if (workspace_bytes < dgcnn_train_step_workspace_bytes(N, E, B, F, k, C, max_nodes))
-        return DGCNN_ERR_WORKSPACE;
     Arena a{reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255), 0};
-    StepBuffers s = carve(a, N, E, B, F, k, C, max_nodes);
+    const StepBuffers s = carve(a, N, E, B, num_features, k, num_classes, max_nodes, false);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-
-    // parameters and gradients: the flat layout of FusedTrainer (PyG order for the graph
-    // convolutions, then conv5, conv6, classifier_1, classifier_2; weight before bias)
-    const int64_t d1 = 32 * ((int64_t)k / 2 - 4);
-    const int64_t sizes[16] = {32LL * F, 32, 32 * 32, 32, 32 * 32, 32, 32, 1,
-                               16 * 97, 16, 32 * 16 * 5, 32, 128 * d1, 128, (int64_t)C * 128, C};
-    float* p[16];
-    float* g[16];
-    int64_t off = 0;
-    for (int i = 0; i < 16; ++i) { p[i] = params + off; g[i] = grads + off; off += sizes[i]; }
-    const int64_t n_params = off;
-    float* stats = grads + n_params;                  // [sum of NLL, #correct] ride the all-reduce
-
-#define DGCNN_TRY(call) do { const int rc_ = (call); if (rc_ != DGCNN_OK) return rc_; } while (0)
     if (cudaMemsetAsync(graph_status, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
     if (index_is_i32)
         DGCNN_TRY(dgcnn_build_graph_i32(static_cast<const int32_t*>(edge_index), E,
@@ -146,40 +246,41 @@ extern "C" int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_in
                                     static_cast<const int64_t*>(batch), N, B, s.rowptr, s.col, s.rowptr_t,
                                     s.col_t, s.dis, s.gptr, s.gorder, graph_status, 0, s.ws_build, s.n_build,
                                     stream));
-    DGCNN_TRY(dgcnn_build_bitmaps(s.rowptr, s.col, s.rowptr_t, s.col_t, s.gptr,
-                                  index_is_i32 ? nullptr : static_cast<const int64_t*>(batch),
-                                  index_is_i32 ? static_cast<const int32_t*>(batch) : nullptr, N, B, max_nodes,
-                                  s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags, s.gflags_t, s.fragmap,
-                                  s.fm_words, s.fgoff, s.gorder, s.gdesc, graph_status, DGCNN_GRAPH_GENERIC,
-                                  stream));
-    DGCNN_TRY(dgcnn_stack_fwd(x, ldx, F, s.rowptr, s.col, s.dis, s.gptr, s.gorder, s.bitmap, s.bmoff,
-                              s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, max_nodes, p[0], p[1], p[2], p[3],
-                              p[4], p[5], p[6], p[7], s.xcat, kXcatLd, s.pooled, s.perm, k, norm,
-                              DGCNN_STACK_MMA, graph_status, s.ws_fwd, s.n_fwd, stream));
-    DGCNN_TRY(dgcnn_tail_fwd(s.pooled, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, training,
-                             seed, rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp, s.ws_tail_f, s.n_tail,
-                             stream));
-    DGCNN_TRY(dgcnn_nll_sum(s.logp, y, B, C, 1.0f, stats, s.dlogp, stream));
-    // the tail's parameter gradients run on the library's side stream underneath KSB
-    DGCNN_TRY(dgcnn_tail_bwd(s.dlogp, s.pooled, B, k, p[8], p[10], p[12], p[14], C, s.h1, s.arg, s.h2, s.h3,
-                             s.keep, s.logp, s.dpooled, g[8], g[9], g[10], g[11], g[12], g[13], g[14], g[15],
-                             2, s.ws_tail_b, s.n_tail, stream));
-    DGCNN_TRY(dgcnn_stack_bwd(s.dpooled, s.perm, k, s.xcat, kXcatLd, x, ldx, F, s.rowptr_t, s.col_t, s.dis,
-                              s.gptr, s.gorder, s.gdesc, s.fragmap, s.bitmap, s.bmoff, s.gflags, s.bitmap_t,
-                              s.bmoff, s.gflags_t, N, B, max_nodes, p[2], p[4], p[6], norm,
-                              bwd_kind == 1 ? DGCNN_STACK_MMA : DGCNN_STACK_FMA, grads, graph_status, s.ws_bwd,
-                              s.n_bwd, stream));
-    DGCNN_TRY(dgcnn_tail_bwd_join(stream));
-    const float scale = 1.0f / (float)global_batch;
-    if (world > 1 && exchange) {
-        if (!epoch) return DGCNN_ERR_INVALID_ARGUMENT;
-        DGCNN_TRY(dgcnn_allreduce_adam(params, grads, exp_avg, exp_avg_sq, n_params, n_params + 2, step, epoch,
-                                       lr, beta1, beta2, eps, scale, exchange, world, rank, comm_status,
-                                       stream));
-    } else {
-        DGCNN_TRY(dgcnn_adam_step(params, grads, exp_avg, exp_avg_sq, n_params, step, lr, beta1, beta2, eps,
-                                  scale, stream));
-    }
-#undef DGCNN_TRY
-    return DGCNN_OK;
+    return step_after_build(t, s, x, ldx, index_is_i32 ? nullptr : static_cast<const int64_t*>(batch),
+                            index_is_i32 ? static_cast<const int32_t*>(batch) : nullptr, y);
 }
+
+// The same step fed from a data set that is resident in HBM: dgcnn_collate
+// gathers the batch's CSR, dis, x, batch and y from the data-set arrays -- no host-to-device
+// copy of the batch (train.py:36) and no K0.
+extern "C" int dgcnn_train_step_resident(const dgcnn_dataset* dataset, const int32_t* ids, int64_t num_nodes,
+                                         int64_t num_edges, int64_t num_graphs, int32_t k,
+                                         int32_t num_classes, int64_t max_nodes, int32_t norm, float* params,
+                                         float* grads, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                                         float lr, float beta1, float beta2, float eps, int64_t global_batch,
+                                         int32_t training, uint64_t seed, int64_t* rng_offset,
+                                         void* const* exchange, int32_t world, int32_t rank, int64_t* epoch,
+                                         int32_t* comm_status, int32_t* graph_status, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    if (!dataset || !ids || !dataset->x || !dataset->y) return DGCNN_ERR_INVALID_ARGUMENT;
+    const StepArgs t{num_nodes, num_edges, num_graphs, dataset->num_features, k, num_classes, max_nodes, norm,
+                     params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, global_batch, training,
+                     seed, rng_offset, exchange, world, rank, epoch, comm_status, graph_status, workspace,
+                     workspace_bytes, stream};
+    DGCNN_TRY(check_step_args(t, true));
+    const int64_t N = num_nodes, E = num_edges, B = num_graphs;
+    const int32_t F = dataset->num_features;
+    Arena a{reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255), 0};
+    StepBuffers s = carve(a, N, E, B, F, k, num_classes, max_nodes, true);
+    if (dataset->symmetric) {                          // one CSR serves both directions
+        s.rowptr_t = s.rowptr;
+        s.col_t = s.col;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(graph_status, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
+    DGCNN_TRY(dgcnn_collate(dataset, ids, B, N, E, s.x_batch, F, s.batch32, s.y_batch, s.rowptr, s.col,
+                            s.rowptr_t, s.col_t, s.dis, s.gptr, s.gorder, graph_status, s.ws_build, s.n_build,
+                            stream));
+    return step_after_build(t, s, s.x_batch, F, nullptr, s.batch32, s.y_batch);
+}
+#undef DGCNN_TRY

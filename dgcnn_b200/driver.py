@@ -1,0 +1,209 @@
+"""The reference's training driver on the B200-native path.
+
+    python -m dgcnn_b200.driver --data_type MUTAG --batch_size 50 --num_epochs 100 --seed 324
+
+Same command line, same 10-fold protocol, same output files as train.py:69-148:
+
+    epochs/{data_type}_{fold}.pth                   model.state_dict() (PyG parameter names)
+    statistics/{data_type}_results_{fold}.csv       index 'epoch'; train_loss, test_loss,
+                                                    train_accuracy, test_accuracy
+    statistics/{data_type}_results_overall.csv      index 'fold'; train_accuracy, test_accuracy
+
+What is different is where the work happens: the data set is parsed once (TU raw text files,
+``data.read_tu_dataset``), lives in HBM (``DeviceDataset``), every training step is ONE
+library call on a list of graph ids (``FusedTrainer.step_resident``: gather, forward, NLL,
+backward, Adam), evaluation gathers its batches on the device too, and loss / accuracy
+accumulate ON THE DEVICE and are read once per epoch instead of twice per batch
+(train.py:44-45).  visdom plots (train.py:72, 122-125) are replaced by one JSON line per epoch
+on stdout.
+
+The TU downloads need PyG + network, neither of which exists here: ``--synthetic`` writes a
+TU-format stand-in with the data set's shape (``synth.CONFIGS``) under ``--data_root`` first, and
+makes up the fold files when the reference's ``10fold_idx`` is not there.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import sys
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .data import DeviceDataset, epoch_batches, load_fold, read_tu_dataset, write_tu_dataset
+from .nn import Model
+from .trainer import FusedTrainer
+
+DATA_TYPES = ["DD", "PTC_MR", "NCI1", "PROTEINS", "IMDB-BINARY", "IMDB-MULTI", "MUTAG", "COLLAB"]
+SYNTH_SHAPES = {"MUTAG": "mutag", "PROTEINS": "proteins", "DD": "dd", "COLLAB": "collab"}
+
+
+def get_args(argv: Optional[Sequence[str]] = None):
+    """train.py:16-24, plus where to read / write and the knobs the reference hard-codes."""
+    p = argparse.ArgumentParser(description="Train Model")
+    p.add_argument("--data_type", default="DD", type=str, choices=DATA_TYPES, help="dataset type")
+    p.add_argument("--batch_size", default=50, type=int, help="train batch size")
+    p.add_argument("--num_epochs", default=100, type=int, help="train epochs number")
+    p.add_argument("--seed", default=324, type=int, help="random seed")
+    p.add_argument("--data_root", default="data", type=str, help="holds {data_type}/ (train.py:82)")
+    p.add_argument("--out_root", default=".", type=str, help="holds epochs/ and statistics/")
+    p.add_argument("--k", default=30, type=int, help="SortPooling k (model.py:17 hard-codes 30)")
+    p.add_argument("--folds", default=10, type=int, help="folds to run (train.py:94: 10)")
+    p.add_argument("--synthetic", action="store_true",
+                   help="write a TU-format synthetic stand-in when the raw files are absent")
+    p.add_argument("--synthetic_graphs", default=0, type=int, help="graphs in the stand-in (0: shape default)")
+    return p.parse_args(argv)
+
+
+def set_determ(seed: int) -> None:
+    """set_determ.py:1-31: seed python, numpy and torch (all devices)."""
+    random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    np.random.seed(seed)
+
+
+def fold_split(data_root: str, data_type: str, fold: int, num_graphs: int, folds: int = 10,
+               seed: int = 324) -> Tuple[np.ndarray, np.ndarray]:
+    """train.py:102-105 when the fold files exist; otherwise a seeded permutation cut into
+    ``folds`` nearly equal test sets (the stand-in data sets have no published folds)."""
+    try:
+        return load_fold(data_root, data_type, fold)
+    except (OSError, FileNotFoundError):
+        perm = np.random.RandomState(seed).permutation(num_graphs)
+        bounds = np.linspace(0, num_graphs, folds + 1).astype(np.int64)
+        test = np.sort(perm[bounds[fold - 1]:bounds[fold]])
+        train = np.sort(np.setdiff1d(perm, test))
+        return train.astype(np.int64), test.astype(np.int64)
+
+
+def ensure_dataset(args) -> Tuple[List[dict], int, int]:
+    root = os.path.join(args.data_root, args.data_type)
+    try:
+        return read_tu_dataset(root, args.data_type)
+    except FileNotFoundError:
+        if not args.synthetic:
+            raise
+    from .synth import CONFIGS, make_graphs
+    cfg = CONFIGS[SYNTH_SHAPES.get(args.data_type, "mutag")]
+    count = args.synthetic_graphs or cfg.num_graphs
+    graphs = make_graphs(cfg, count, seed=args.seed)
+    raw = os.path.join(root, "raw")
+    write_tu_dataset(raw, args.data_type, graphs)
+    return read_tu_dataset(root, args.data_type)
+
+
+class EpochStats:
+    """running_loss / correct of train.py:33, 44-45 as device accumulators: one read per epoch."""
+
+    def __init__(self, device):
+        self.acc = torch.zeros(2, dtype=torch.float32, device=device)
+        self.batches, self.samples = 0, 0
+
+    def add(self, stats: torch.Tensor, batch_graphs: int) -> None:
+        # stats = [sum of NLL over the batch, #correct]; the reference adds the batch MEAN
+        self.acc[0] += stats[0] / float(batch_graphs)
+        self.acc[1] += stats[1]
+        self.batches += 1
+        self.samples += batch_graphs
+
+    def result(self) -> Tuple[float, float]:
+        loss, correct = self.acc.tolist()                     # the epoch's only host sync
+        return loss / max(self.batches, 1), correct / max(self.samples, 1) * 100.0
+
+
+def train_epoch(trainer: FusedTrainer, ds: DeviceDataset, ids: np.ndarray, batch_size: int,
+                generator: torch.Generator) -> Tuple[float, float]:
+    """train.py:27-47."""
+    trainer.model.train()
+    st = EpochStats(ds.device)
+    for b in epoch_batches(ids, batch_size, shuffle=True, generator=generator):
+        st.add(trainer.step_resident(ds, b), len(b))
+    return st.result()
+
+
+def test_epoch(model: Model, ds: DeviceDataset, ids: np.ndarray, batch_size: int) -> Tuple[float, float]:
+    """train.py:49-66."""
+    model.eval()
+    st = EpochStats(ds.device)
+    with torch.no_grad():
+        for b in epoch_batches(ids, batch_size, shuffle=False):
+            data = ds.batch(b)
+            stats, _ = ops.nll_sum(model(data), data.y, 1.0, want_grad=False)
+            st.add(stats, len(b))
+    return st.result()
+
+
+test_epoch.__test__ = False          # not a pytest test
+
+
+def write_fold_csv(path: str, results: Dict[str, List[float]], index_label: str) -> None:
+    """pd.DataFrame(data=results, index=range(1, n+1)).to_csv(path, index_label=...)
+    (train.py:130-131, 143-144) without the pandas dependency: same header, same rows."""
+    cols = list(results)
+    n = len(results[cols[0]]) if cols else 0
+    with open(path, "w") as fh:
+        fh.write(",".join([index_label] + cols) + "\n")
+        for i in range(n):
+            fh.write(",".join([str(i + 1)] + [repr(float(results[c][i])) for c in cols]) + "\n")
+
+
+def main(argv: Optional[Sequence[str]] = None) -> Dict[str, List[float]]:
+    opt = get_args(argv)
+    set_determ(opt.seed)
+    if not torch.cuda.is_available():
+        raise SystemExit("dgcnn_b200.driver: no CUDA device; the hot path has no CPU fallback")
+    device = torch.device("cuda", torch.cuda.current_device())
+    graphs, num_features, num_classes = ensure_dataset(opt)
+    print(f"data_set.num_features={num_features}, data_set.num_classes={num_classes}", flush=True)
+    ds = DeviceDataset(graphs, device, num_classes=num_classes)
+    os.makedirs(os.path.join(opt.out_root, "epochs"), exist_ok=True)
+    os.makedirs(os.path.join(opt.out_root, "statistics"), exist_ok=True)
+    generator = torch.Generator().manual_seed(opt.seed)
+
+    over_results = {"train_accuracy": [], "test_accuracy": []}
+    for fold_number in range(1, opt.folds + 1):
+        model = Model(num_features, num_classes, k=opt.k).to(device)           # train.py:98
+        trainer = FusedTrainer(model)                                          # NLL + Adam defaults
+        train_idx, test_idx = fold_split(opt.data_root, opt.data_type, fold_number, len(ds),
+                                         max(opt.folds, 2), opt.seed)
+        fold_results = {"train_loss": [], "test_loss": [], "train_accuracy": [], "test_accuracy": []}
+        for epoch in range(1, opt.num_epochs + 1):
+            t0 = time.perf_counter()
+            train_loss, train_acc = train_epoch(trainer, ds, train_idx, opt.batch_size, generator)
+            test_loss, test_acc = test_epoch(model, ds, test_idx, opt.batch_size)
+            fold_results["train_loss"].append(train_loss)
+            fold_results["train_accuracy"].append(train_acc)
+            fold_results["test_loss"].append(test_loss)
+            fold_results["test_accuracy"].append(test_acc)
+            print(json.dumps({"fold": fold_number, "epoch": epoch, "train_loss": train_loss,
+                              "train_accuracy": train_acc, "test_loss": test_loss,
+                              "test_accuracy": test_acc, "epoch_s": time.perf_counter() - t0}), flush=True)
+        torch.save(model.state_dict(), os.path.join(opt.out_root, "epochs", f"{opt.data_type}_{fold_number}.pth"))
+        write_fold_csv(os.path.join(opt.out_root, "statistics", f"{opt.data_type}_results_{fold_number}.csv"),
+                       fold_results, "epoch")
+        over_results["train_accuracy"].append(fold_results["train_accuracy"][-1])
+        over_results["test_accuracy"].append(fold_results["test_accuracy"][-1])
+        print(f"[{fold_number}] Train Acc: {fold_results['train_accuracy'][-1]:.2f}% "
+              f"Test Acc: {fold_results['test_accuracy'][-1]:.2f}%", flush=True)
+    write_fold_csv(os.path.join(opt.out_root, "statistics", f"{opt.data_type}_results_overall.csv"),
+                   over_results, "fold")
+    tr, te = np.array(over_results["train_accuracy"]), np.array(over_results["test_accuracy"])
+    print("Overall Training Accuracy: %.2f%% (std: %.2f) Testing Accuracy: %.2f%% (std: %.2f)"
+          % (tr.mean(), tr.std(), te.mean(), te.std()), flush=True)
+    int_status = int(trainer._graph_status.item())
+    if int_status & ~ops.GRAPH_GENERIC:
+        raise RuntimeError(f"dgcnn_b200.driver: the kernels flagged bad input (status {int_status})")
+    return over_results
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

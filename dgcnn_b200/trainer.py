@@ -136,6 +136,57 @@ class FusedTrainer:
                       self.betas[0], self.betas[1], self.eps, grad_scale=1.0 / float(global_batch))
         return self.stats
 
+    def step_resident(self, dataset, ids, ids_device: Optional[torch.Tensor] = None,
+                      global_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimisation step on the graphs ``ids`` of a ``DeviceDataset``:
+        dgcnn_collate gathers the batch from the resident data set, so neither the host
+        collate (train.py:108-109) nor the host-to-device copy (train.py:36) nor K0 runs.
+        Bit-identical to ``step()`` on the host-collated batch of the same graphs.  Returns
+        the device tensor [sum of NLL, number of correct predictions]."""
+        import ctypes
+        from . import _lib
+        m = self.model
+        lib = _lib.load_library()
+        n, e, mx = dataset.plan(ids)
+        b, f = int(len(ids)), dataset.num_features
+        k, c = m.sort_pool.k, m.classifier_2.out_features
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        if dataset.device != self.flat.device:
+            raise RuntimeError("FusedTrainer.step_resident: data set and model live on different devices")
+        if self.num_params != int(lib.dgcnn_train_step_num_params(f, k, c)):
+            raise RuntimeError("FusedTrainer.step_resident: the model does not match the data set "
+                               "(num_features / k / num_classes)")
+        if world > 1 and self.exchange is None:
+            raise RuntimeError("FusedTrainer.step_resident: multi-GPU needs the peer-memory exchange "
+                               "(DGCNN_ALLREDUCE=p2p)")
+        if ids_device is None:
+            ids_device = dataset.ids_to_device(ids)
+        need = int(lib.dgcnn_train_step_resident_workspace_bytes(n, e, b, f, k, c, mx))
+        if need == 0:
+            raise ValueError("FusedTrainer.step_resident: bad sizes")
+        if self._arena is None or self._arena.numel() < need:
+            self._arena = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.flat.device)
+        if global_batch is None:
+            global_batch = b * world
+        table, epoch, rank = None, None, 0
+        if world > 1:
+            table = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p_)) for p_ in self.exchange.ptrs])
+            epoch, rank = self.exchange.epoch.data_ptr(), self.exchange.rank
+        with torch.cuda.device(self.flat.device):
+            rc = lib.dgcnn_train_step_resident(
+                dataset.c_struct, ids_device.data_ptr(), n, e, b, k, c, mx, int(m.conv1.norm),
+                self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                self.step_count.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, int(global_batch),
+                int(bool(m.training)), int(m._tail_seed) & 0xFFFFFFFFFFFFFFFF, m._tail_rng_offset.data_ptr(),
+                table, world, rank, epoch, self.comm_status.data_ptr(), self._graph_status.data_ptr(),
+                self._arena.data_ptr(), self._arena.numel(), torch.cuda.current_stream().cuda_stream)
+        if rc == -2:
+            raise RuntimeError("FusedTrainer.step_resident: the batch holds graphs too large for the fused "
+                               "kernels (dgcnn_stack_fwd_supported); feed it through step()")
+        _lib.check(rc, "train_step_resident")
+        ops.LAUNCHES["train_step_resident"] = ops.LAUNCHES.get("train_step_resident", 0) + 28
+        return self.stats
+
     def _native_step(self, data, global_batch, world) -> bool:
         """The same step through dgcnn_train_step (one ctypes call, buffers from a cached arena);
         False when the configuration is outside what that entry point covers."""

@@ -387,6 +387,72 @@ int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_index, int32_
                      int32_t rank, int64_t* epoch, int32_t* comm_status, int32_t* graph_status,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * N1  device-resident data set + collate on the GPU.  Replaces, per step,
+ *   train.py:108-109  DataLoader -> PyG Batch.from_data_list (concatenate, shift edge ids by the
+ *                     node offset, emit `batch`)        train.py:36  sample.to(device)
+ *   model.py:28 + gcn_norm prologue (K0) for that batch
+ * The data set is ONE batch of all its graphs that went through dgcnn_build_graph once (so
+ * loops are dropped, rows sorted, the symmetry verdict known) and stays in HBM:
+ *   gptr [G+1], rowptr [Nd+1], col [Ed], dis [Nd]   K0's outputs over the whole data set
+ *   rowptr_t, col_t   K0's CSR by source; may be NULL when `symmetric` (K0 did not raise
+ *                     DGCNN_GRAPH_GENERIC: both CSRs are equal)
+ *   x [Nd, F] (row stride ldx), y [G] int64        features and labels (either may be NULL
+ *                     when the matching output is not requested)
+ * Edges must not cross graphs (true of any PyG data set; the Python side checks it once).
+ * The struct itself lives in HOST memory (its members are device pointers) and is only read
+ * during the call.
+ * ------------------------------------------------------------------------ */
+typedef struct dgcnn_dataset {
+    int64_t num_graphs, num_nodes, num_edges;   /* G, Nd, Ed = rowptr[Nd] */
+    int32_t num_features;                       /* F */
+    int32_t symmetric;                          /* 1: rowptr_t/col_t unused */
+    const float* x;
+    int64_t ldx;
+    const int64_t* y;
+    const int32_t* gptr;
+    const int32_t* rowptr;
+    const int32_t* col;
+    const int32_t* rowptr_t;
+    const int32_t* col_t;
+    const float* dis;
+} dgcnn_dataset;
+
+/* A batch = ids[0..B) (device int32, graph ids of the data set in batch order, repeats
+ * allowed).  Writes exactly what dgcnn_build_graph(_i32) produces from the host-collated
+ * batch -- rowptr [N+1], col [E], dis [N], gptr [B+1], gorder [B] (optional) -- plus the
+ * collated x [N, F] (row stride ldx; optional), batch32 [N] (optional), y [B] (optional).
+ * rowptr_t / col_t: both NULL, or aliases of rowptr / col (fine for a symmetric data set: one
+ * copy is written), or separate buffers.  `status` is OR-ed with DGCNN_GRAPH_GENERIC when the
+ * data set is not symmetric (what K0 would report), DGCNN_GRAPH_BAD_BATCH when an id is
+ * outside [0, G) or num_nodes / num_edges (host arithmetic on the per-graph sizes, which size
+ * the outputs) disagree with the ids -- then nothing else is written --, DGCNN_GRAPH_BAD_EDGE
+ * when an edge leaves its graph.  Two launches, B, N, E < 2^31. */
+size_t dgcnn_collate_workspace_bytes(int64_t num_graphs);
+int dgcnn_collate(const dgcnn_dataset* dataset, const int32_t* ids, int64_t num_graphs,
+                  int64_t num_nodes, int64_t num_edges, float* x, int64_t ldx,
+                  int32_t* batch32, int64_t* y, int32_t* rowptr, int32_t* col,
+                  int32_t* rowptr_t, int32_t* col_t, float* dis, int32_t* gptr,
+                  int32_t* gorder, int32_t* status, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* dgcnn_train_step with the batch taken from a resident data set: dgcnn_collate replaces K0
+ * and the host-to-device copy; everything after it is the same call sequence, and the result
+ * is bit-identical to dgcnn_train_step on the host-collated batch of the same graphs.
+ * num_nodes, num_edges, max_nodes: sums / maximum of the per-graph sizes over ids (host
+ * arithmetic; the caller keeps the sizes).  Other arguments as for dgcnn_train_step. */
+size_t dgcnn_train_step_resident_workspace_bytes(int64_t num_nodes, int64_t num_edges,
+                                                 int64_t num_graphs, int32_t num_features, int32_t k,
+                                                 int32_t num_classes, int64_t max_nodes);
+int dgcnn_train_step_resident(const dgcnn_dataset* dataset, const int32_t* ids, int64_t num_nodes,
+                              int64_t num_edges, int64_t num_graphs, int32_t k, int32_t num_classes,
+                              int64_t max_nodes, int32_t norm, float* params, float* grads,
+                              float* exp_avg, float* exp_avg_sq, int64_t* step, float lr, float beta1,
+                              float beta2, float eps, int64_t global_batch, int32_t training,
+                              uint64_t seed, int64_t* rng_offset, void* const* exchange, int32_t world,
+                              int32_t rank, int64_t* epoch, int32_t* comm_status, int32_t* graph_status,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,181 @@
+"""CPU tests of the host side of the data path: TU raw-format reader,
+Indegree, fold files, DataLoader-order batching, CSV writers, the collate algebra that
+csrc/collate.cu implements.  No GPU, no compute call into the library."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dgcnn_b200 import data as dd
+from dgcnn_b200 import driver
+from dgcnn_b200.synth import CONFIGS, collate, make_graphs
+from oracle import dgcnn_oracle as orc
+
+
+def write(path, text):
+    with open(path, "w") as fh:
+        fh.write(text)
+
+
+def test_tu_reader_hand_fixture(tmp_path):
+    """Two graphs written by hand in the TU raw format; expected tensors follow PyG's
+    read_tu_data: 1-based ids, self loops removed, duplicates merged, edges sorted by
+    (row, col); x = [node_attributes | one-hot(node_labels - min)] then Indegree appended;
+    graph labels {-1, 1} -> {0, 1}."""
+    root = tmp_path / "TOY" / "raw"
+    root.mkdir(parents=True)
+    # graph 1: path 1-2-3 (both directions) + a self loop on 2 + a duplicate of (1,2)
+    # graph 2: single edge 4-5, node 6 isolated
+    write(root / "TOY_A.txt", "2, 1\n1, 2\n2, 3\n3, 2\n2, 2\n1, 2\n4, 5\n5, 4\n")
+    write(root / "TOY_graph_indicator.txt", "1\n1\n1\n2\n2\n2\n")
+    write(root / "TOY_graph_labels.txt", "1\n-1\n")
+    write(root / "TOY_node_labels.txt", "3\n5\n3\n4\n3\n5\n")          # min 3 -> classes 0..2
+    write(root / "TOY_node_attributes.txt", "0.5\n1.5\n2.5\n3.5\n4.5\n5.5\n")
+    graphs, f, c = dd.read_tu_dataset(str(tmp_path / "TOY"), "TOY")
+    assert (f, c, len(graphs)) == (5, 2, 2)
+    g0, g1 = graphs
+    assert g0["edge_index"].tolist() == [[0, 1, 1, 2], [1, 0, 2, 1]]
+    assert g1["edge_index"].tolist() == [[0, 1], [1, 0]]
+    assert (g0["y"], g1["y"]) == (1, 0)
+    want0 = np.array([[0.5, 1, 0, 0, 0.5], [1.5, 0, 0, 1, 1.0], [2.5, 1, 0, 0, 0.5]], np.float32)
+    want1 = np.array([[3.5, 0, 1, 0, 1.0], [4.5, 1, 0, 0, 1.0], [5.5, 0, 0, 1, 0.0]], np.float32)
+    assert np.array_equal(g0["x"], want0) and np.array_equal(g1["x"], want1)
+    # use_node_attr=False drops the attribute column (PyG TUDataset default)
+    graphs, f, _ = dd.read_tu_dataset(str(tmp_path / "TOY"), "TOY", use_node_attr=False)
+    assert f == 4 and np.array_equal(graphs[0]["x"], want0[:, 1:])
+
+
+def test_tu_reader_rejects_cross_graph_edges_and_missing_files(tmp_path):
+    root = tmp_path / "BAD"
+    root.mkdir()
+    with pytest.raises(FileNotFoundError):
+        dd.read_tu_dataset(str(root), "BAD")
+    write(root / "BAD_A.txt", "1, 3\n3, 1\n")
+    write(root / "BAD_graph_indicator.txt", "1\n1\n2\n")
+    write(root / "BAD_graph_labels.txt", "0\n1\n")
+    with pytest.raises(ValueError, match="different graphs"):
+        dd.read_tu_dataset(str(root), "BAD")
+
+
+@pytest.mark.parametrize("name", ["mutag", "proteins", "collab"])
+def test_tu_round_trip_of_synthetic_graphs(tmp_path, name):
+    """write_tu_dataset -> read_tu_dataset reproduces the synthetic graphs bit for bit:
+    edges, labels, one-hot features and the Indegree column (utils.py:18-33)."""
+    cfg = CONFIGS[name]
+    graphs = make_graphs(cfg, 40, seed=3)
+    dd.write_tu_dataset(str(tmp_path / "raw"), "SYN", graphs)
+    back, f, c = dd.read_tu_dataset(str(tmp_path), "SYN")
+    assert len(back) == len(graphs) and f == cfg.num_features
+    assert c == len({g["y"] for g in graphs})
+    for a, b in zip(graphs, back):
+        assert np.array_equal(a["edge_index"], b["edge_index"])
+        assert np.array_equal(a["x"], b["x"], equal_nan=True)
+    ys = sorted({g["y"] for g in graphs})
+    assert [ys.index(g["y"]) for g in graphs] == [g["y"] for g in back]
+
+
+def test_indegree_matches_the_oracle_restatement():
+    rng = np.random.RandomState(0)
+    for n, m in [(7, 12), (1, 0), (5, 0), (30, 200)]:
+        ei = np.stack([rng.randint(0, n, m), rng.randint(0, n, m)]).astype(np.int64)
+        x = rng.standard_normal((n, 3)).astype(np.float32)
+        want = orc.indegree_feature(torch.from_numpy(ei), n, torch.from_numpy(x)).numpy()
+        got = dd.indegree(x, ei, n)
+        assert np.array_equal(got, want, equal_nan=True)
+        want = orc.indegree_feature(torch.from_numpy(ei), n, None).numpy()
+        assert np.array_equal(dd.indegree(None, ei, n), want, equal_nan=True)
+    # max_value / norm=False / cat=False branches of utils.py:11-33
+    ei = np.array([[0, 1, 2], [1, 1, 0]])
+    assert dd.indegree(None, ei, 3, norm=False).ravel().tolist() == [1.0, 2.0, 0.0]
+    assert dd.indegree(None, ei, 3, max_value=4).ravel().tolist() == [0.25, 0.5, 0.0]
+    assert dd.indegree(np.ones(3, np.float32), ei, 3, cat=False).shape == (3, 1)
+    assert dd.indegree(np.ones(3, np.float32), ei, 3).shape == (3, 2)
+
+
+def test_fold_files_and_fallback_split(tmp_path):
+    base = tmp_path / "MUTAG" / "10fold_idx"
+    base.mkdir(parents=True)
+    write(base / "train_idx-3.txt", "5\n1\n9\n")
+    write(base / "test_idx-3.txt", "2\n")
+    tr, te = dd.load_fold(str(tmp_path), "MUTAG", 3)
+    assert tr.tolist() == [5, 1, 9] and te.tolist() == [2] and tr.dtype == np.int64
+    tr2, te2 = driver.fold_split(str(tmp_path), "MUTAG", 3, 10)
+    assert tr2.tolist() == [5, 1, 9] and te2.tolist() == [2]
+    # no files: ten disjoint test sets that cover the data set, train = the rest
+    seen = []
+    for fold in range(1, 11):
+        tr, te = driver.fold_split(str(tmp_path), "NCI1", fold, 103)
+        assert len(tr) + len(te) == 103 and not set(tr) & set(te)
+        seen += te.tolist()
+    assert sorted(seen) == list(range(103))
+
+
+def test_epoch_batches_follow_the_dataloader_contract():
+    ids = np.arange(100, 123)
+    got = list(dd.epoch_batches(ids, 10, shuffle=False))
+    assert [len(b) for b in got] == [10, 10, 3] and np.concatenate(got).tolist() == ids.tolist()
+    g1 = torch.Generator().manual_seed(7)
+    g2 = torch.Generator().manual_seed(7)
+    a = np.concatenate(list(dd.epoch_batches(ids, 10, True, g1)))
+    want = ids[torch.randperm(23, generator=g2).numpy()]           # RandomSampler's draw
+    assert a.tolist() == want.tolist() and sorted(a.tolist()) == ids.tolist()
+    b = np.concatenate(list(dd.epoch_batches(ids, 10, True, g1)))  # the next epoch reshuffles
+    assert a.tolist() != b.tolist()
+
+
+def test_driver_arguments_and_csv_layout(tmp_path):
+    opt = driver.get_args([])
+    assert (opt.data_type, opt.batch_size, opt.num_epochs, opt.seed) == ("DD", 50, 100, 324)   # train.py:18-23
+    with pytest.raises(SystemExit):
+        driver.get_args(["--data_type", "CORA"])
+    res = {"train_loss": [0.7, 0.5], "test_loss": [0.8, 0.6], "train_accuracy": [50.0, 75.0],
+           "test_accuracy": [40.0, 60.0]}
+    path = tmp_path / "MUTAG_results_1.csv"
+    driver.write_fold_csv(str(path), res, "epoch")
+    lines = path.read_text().strip().split("\n")
+    assert lines[0] == "epoch,train_loss,test_loss,train_accuracy,test_accuracy"      # train.py:130-131
+    assert lines[1].split(",")[0] == "1" and float(lines[2].split(",")[3]) == 75.0
+    pd = pytest.importorskip("pandas")
+    frame = pd.read_csv(path, index_col="epoch")
+    assert frame.index.tolist() == [1, 2] and frame["test_accuracy"].tolist() == [40.0, 60.0]
+
+
+def test_collate_algebra_of_the_device_gather():
+    """The formulas in csrc/collate.cu's header, in numpy: the CSR of a batch is the
+    concatenation of the per-graph CSR segments of the data set with the node and edge
+    offsets fixed up -- equal to the CSR built from the host-collated batch."""
+    cfg = CONFIGS["proteins"]
+    graphs = make_graphs(cfg, 30, seed=4)
+
+    def csr(batch):
+        src, dst = batch.edge_index.numpy()
+        n = batch.num_nodes
+        order = np.lexsort((src, dst))
+        rowptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=n))])
+        return rowptr, src[order], batch.ptr.numpy()
+
+    ds_rowptr, ds_col, ds_gptr = csr(collate(graphs))
+    ids = np.array([7, 3, 3, 29, 0, 11])
+    want_rowptr, want_col, want_gptr = csr(collate([graphs[i] for i in ids]))
+    nodes = ds_gptr[ids + 1] - ds_gptr[ids]
+    gptr = np.concatenate([[0], np.cumsum(nodes)])
+    sn0 = ds_gptr[ids]
+    se0 = ds_rowptr[sn0]
+    eoff = np.concatenate([[0], np.cumsum(ds_rowptr[ds_gptr[ids + 1]] - se0)])
+    rowptr = np.zeros(gptr[-1] + 1, dtype=np.int64)
+    col = np.zeros(eoff[-1], dtype=np.int64)
+    for b in range(len(ids)):
+        i = np.arange(nodes[b])
+        rowptr[gptr[b] + i] = ds_rowptr[sn0[b] + i] - se0[b] + eoff[b]
+        j = np.arange(eoff[b + 1] - eoff[b])
+        col[eoff[b] + j] = ds_col[se0[b] + j] - sn0[b] + gptr[b]
+    rowptr[-1] = eoff[-1]
+    assert np.array_equal(gptr, want_gptr)
+    assert np.array_equal(rowptr, want_rowptr) and np.array_equal(col, want_col)
+
+
+def test_device_dataset_refuses_cpu():
+    graphs = make_graphs(CONFIGS["mutag"], 3, seed=0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dd.DeviceDataset(graphs, "cpu")

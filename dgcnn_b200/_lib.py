@@ -30,10 +30,22 @@ class DgcnnDataset(ctypes.Structure):
                 ("num_features", c_int32), ("symmetric", c_int32),
                 ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p),
                 ("gptr", c_void_p), ("rowptr", c_void_p), ("col", c_void_p),
-                ("rowptr_t", c_void_p), ("col_t", c_void_p), ("dis", c_void_p)]
+                ("rowptr_t", c_void_p), ("col_t", c_void_p), ("dis", c_void_p),
+                ("bitmap", c_void_p), ("bitmap_t", c_void_p), ("bmoff", c_void_p), ("gflags", c_void_p),
+                ("gflags_t", c_void_p), ("fragmap", c_void_p), ("fgoff", c_void_p)]
+
+
+class DgcnnBatchGraph(ctypes.Structure):
+    """``dgcnn_batch_graph`` of include/dgcnn_b200.h: where dgcnn_collate writes a batch."""
+    _fields_ = [("x", c_void_p), ("ldx", c_int64), ("batch32", c_void_p), ("y", c_void_p),
+                ("rowptr", c_void_p), ("col", c_void_p), ("rowptr_t", c_void_p), ("col_t", c_void_p),
+                ("dis", c_void_p), ("gptr", c_void_p), ("gorder", c_void_p),
+                ("bitmap", c_void_p), ("bitmap_t", c_void_p), ("bmoff", c_void_p), ("gflags", c_void_p),
+                ("gflags_t", c_void_p), ("fragmap", c_void_p), ("fgoff", c_void_p), ("gdesc", c_void_p)]
 
 
 _DATASET_P = ctypes.POINTER(DgcnnDataset)
+_BATCH_P = ctypes.POINTER(DgcnnBatchGraph)
 _STEP_TAIL = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int64,
               c_int32, c_uint64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
               c_void_p, c_void_p, c_size_t, c_void_p]
@@ -41,9 +53,8 @@ _STEP_TAIL = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float
 # name -> (restype, argtypes); mirrors include/dgcnn_b200.h one to one
 SIGNATURES = {
     "dgcnn_collate_workspace_bytes": (c_size_t, [c_int64]),
-    "dgcnn_collate": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dgcnn_collate": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, _BATCH_P, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
     "dgcnn_train_step_resident_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32,
                                                              c_int32, c_int64]),
     "dgcnn_train_step_resident": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, c_int32,

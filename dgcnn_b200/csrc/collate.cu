@@ -5,161 +5,188 @@
 //                     fix-up of edge_index, `batch`, `ptr`)
 //   train.py:36       sample.to(device)  (16 bytes of int64 indices per edge over PCIe: what
 //                     bounds the end-to-end rate of the host-fed step)
-//   model.py:28 + gcn_norm prologue (K0) for that batch
+//   model.py:28 + gcn_norm prologue (K0) and the adjacency bitmaps (K0b) for that batch
 // by a gather: the whole data set lives in HBM as ONE canonical CSR (built once by K0 over all
-// graphs, so loops are dropped, duplicates kept, rows sorted and the symmetry verdict known);
-// a batch is a list of graph ids.  Graphs never share nodes or edges, therefore the CSR of a
-// batch is the concatenation of the per-graph CSR segments with two offsets fixed up:
+// graphs, so loops are dropped, duplicates kept, rows sorted and the symmetry verdict known)
+// plus K0b's per-graph bitmaps / fragment maps; a batch is a list of graph ids.  Graphs never
+// share nodes or edges and K0b's blocks are relative to the graph's first node, therefore the
+// graph structures of a batch are the concatenation of the per-graph segments with offsets
+// fixed up:
 //
 //   gptr[b]              = sum_{b' < b} n(ids[b'])
 //   rowptr[gptr[b] + i]  = ds.rowptr[sn0 + i] - se0 + eoff[b]       sn0 = ds.gptr[ids[b]]
 //   col[eoff[b] + j]     = ds.col[se0 + j]    - sn0 + gptr[b]       se0 = ds.rowptr[sn0]
 //   dis, x               = copies of the graph's rows               eoff = prefix sum of e(ids[.])
 //   batch[gptr[b] + i]   = b,   y[b] = ds.y[ids[b]]
+//   bitmap[bmoff[b] + w] = ds.bitmap[ds.bmoff[ids[b]] + w]          bmoff, fgoff = prefix sums of
+//   fragmap[fgoff[b] + w]= ds.fragmap[ds.fgoff[ids[b]] + w]         the per-graph word counts
+//   gorder = graphs by descending size (ties by index), gdesc[q] = {g, gptr[g], n_g, fgoff[g]}
 //
-// which is bit for bit what K0 produces from the host-collated batch (tests/test_gpu_parity.py).
-// Two launches: n1_plan (one CTA: offsets, graph order, labels, validation) and n1_gather
-// (grid-stride, HBM-bound: 4 B read + 4 B written per edge instead of 16 B over PCIe + K0).
+// which is bit for bit what K0 + K0b produce from the host-collated batch
+// (tests/test_gpu_resident.py).  ONE launch for batches of up to 1024 graphs: every CTA derives
+// the offset tables itself (ids -> sizes -> block scan, a few microseconds of redundant work
+// that saves a dependent launch), then all CTAs stride over one unified index space of edges,
+// nodes, feature elements and map words, so the phases overlap instead of queueing.  HBM-bound
+// copy: ~8 B per edge + the maps, instead of 16 B per edge over PCIe + K0 + K0b.  Larger
+// batches take a one-CTA plan kernel first and read the tables from global memory.
 #include "common.cuh"
 
 namespace dgcnn {
 
-constexpr int kPlanThreads = 1024;
-constexpr int kPlanOrderGraphs = 4096;     // rank sort in shared memory up to here (as K0)
 constexpr int kGatherThreads = 256;
-constexpr int kGatherSmemGraphs = 2048;    // offset tables in shared memory up to here
+constexpr int kFusedGraphs = 1024;         // tables derived per CTA in shared memory up to here
+constexpr int kPlanThreads = 1024;
+constexpr int kOrderGraphs = 4096;         // rank sort up to here, identity order beyond (as K0)
+constexpr int kMapMaxNodes = 1024;         // K0b's cap: larger graphs own no bitmap
+constexpr int kEdgesPerItem = 8;           // edges one work item of n1_gather copies
 
-struct CollateWorkspace {
-    int32_t* eoff;   // [B+1] first batch edge of batch graph b
-    int32_t* sn0;    // [B]   first data-set node of graph ids[b]
-    int32_t* se0;    // [B]   first data-set edge of graph ids[b]
-    int32_t* ok;     // [1]   1 when ids and the caller's totals are consistent (n1_gather runs)
-    size_t bytes;
+__device__ __forceinline__ int map_words_bitmap(int n) {
+    if (n <= 0 || n > kMapMaxNodes) return 0;
+    const int np = (n + 15) & ~15;
+    return np * ((np + 31) >> 5);
+}
+__device__ __forceinline__ int map_words_fragmap(int n) {
+    if (n <= 0 || n > kMapMaxNodes) return 0;
+    const int t = (n + 15) >> 4;
+    return t * ((t + 3) >> 2) * 32;
+}
+
+// The offset tables of one batch, in shared memory (fused launch) or in the workspace.
+struct Tables {
+    int32_t* gptr;    // [B+1] first batch node of batch graph b
+    int32_t* eoff;    // [B+1] first batch edge
+    int32_t* bmoff;   // [B+1] first bitmap word
+    int32_t* fgoff;   // [B+1] first fragment-map word
+    int32_t* sn0;     // [B]   first data-set node of graph ids[b]
+    int32_t* se0;     // [B]   first data-set edge of graph ids[b]
+};
+__host__ __device__ inline size_t table_ints(int64_t b) { return (size_t)(6 * b + 4); }
+__host__ __device__ inline Tables carve_tables(int32_t* base, int64_t b) {
+    Tables t;
+    t.gptr = base;
+    t.eoff = t.gptr + (b + 1);
+    t.bmoff = t.eoff + (b + 1);
+    t.fgoff = t.bmoff + (b + 1);
+    t.sn0 = t.fgoff + (b + 1);
+    t.se0 = t.sn0 + b;
+    return t;
+}
+
+struct CollateArgs {
+    dgcnn_dataset ds;
+    dgcnn_batch_graph out;
+    const int32_t* ids;
+    int32_t num_graphs, num_nodes, num_edges;
+    int32_t generic;                 // data set not symmetric: second CSR / bitmap in use
+    int32_t want_maps;               // gather K0b's outputs too
+    int32_t* status;
+    int32_t* ws_tables;              // global tables (plan kernel) or NULL (derive per CTA)
+    int32_t* ws_ok;                  // [1] verdict of the plan kernel
 };
 
-__host__ inline CollateWorkspace carve_collate_workspace(void* base, int64_t b) {
-    CollateWorkspace w;
-    char* p = static_cast<char*>(base);
-    size_t off = 0;
-    auto take = [&](size_t bytes) {
-        char* q = p ? p + off : nullptr;
-        off += align_up(bytes, 256);
-        return q;
-    };
-    w.eoff = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)(b + 1)));
-    w.sn0 = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)(b > 0 ? b : 1)));
-    w.se0 = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)(b > 0 ? b : 1)));
-    w.ok = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
-    w.bytes = off;
-    return w;
-}
-
-// exclusive scan of one int per thread over the CTA (kPlanThreads = 32 warps); returns the
-// exclusive prefix, *total = sum over the CTA.  warp_sums: int[33] in shared memory.
-__device__ __forceinline__ int plan_scan(int v, int* warp_sums, int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
+// exclusive block scan of two packed 64-bit sums (lo | hi << 32 each); red: u64[2][33] in
+// shared memory.  Returns the exclusive prefixes, totals through tot0/tot1.
+__device__ __forceinline__ void scan2(unsigned long long v0, unsigned long long v1,
+                                      unsigned long long (*red)[33], unsigned long long* x0,
+                                      unsigned long long* x1, unsigned long long* tot0,
+                                      unsigned long long* tot1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = (blockDim.x + 31) >> 5;
+    unsigned long long i0 = v0, i1 = v1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(DGCNN_FULL_MASK, inc, o);
-        if (lane >= o) inc += t;
+        const unsigned long long a = __shfl_up_sync(DGCNN_FULL_MASK, i0, o);
+        const unsigned long long b = __shfl_up_sync(DGCNN_FULL_MASK, i1, o);
+        if (lane >= o) { i0 += a; i1 += b; }
     }
-    if (lane == 31) warp_sums[warp] = inc;
+    if (lane == 31) { red[0][warp] = i0; red[1][warp] = i1; }
     __syncthreads();
     if (warp == 0) {
-        const int w = warp_sums[lane];
-        int winc = w;
+        const unsigned long long w0 = lane < warps ? red[0][lane] : 0ull;
+        const unsigned long long w1 = lane < warps ? red[1][lane] : 0ull;
+        unsigned long long c0 = w0, c1 = w1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(DGCNN_FULL_MASK, winc, o);
-            if (lane >= o) winc += t;
+            const unsigned long long a = __shfl_up_sync(DGCNN_FULL_MASK, c0, o);
+            const unsigned long long b = __shfl_up_sync(DGCNN_FULL_MASK, c1, o);
+            if (lane >= o) { c0 += a; c1 += b; }
         }
-        warp_sums[lane] = winc - w;                 // exclusive prefix of the warp sums
-        if (lane == 31) warp_sums[32] = winc;
+        red[0][lane] = c0 - w0;                     // exclusive prefix of the warp sums
+        red[1][lane] = c1 - w1;
+        if (lane == 31) { red[0][32] = c0; red[1][32] = c1; }
     }
     __syncthreads();
-    const int excl = warp_sums[warp] + inc - v;
-    *total = warp_sums[32];
-    __syncthreads();                                // the next scan reuses warp_sums
-    return excl;
+    *x0 = red[0][warp] + i0 - v0;
+    *x1 = red[1][warp] + i1 - v1;
+    *tot0 = red[0][32];
+    *tot1 = red[1][32];
+    __syncthreads();
 }
 
-// One CTA.  Offsets of every batch graph (chunked block scan with a running carry), the
-// processing order of the graphs (descending size, ties by index: the rule of k0_finalize),
-// labels, and validation of ids and of the caller's totals.
-__global__ void __launch_bounds__(kPlanThreads)
-n1_plan(const int32_t* __restrict__ ds_gptr, const int32_t* __restrict__ ds_rowptr,
-        const int32_t* __restrict__ ds_rowptr_t, const int64_t* __restrict__ ds_y, int64_t ds_graphs,
-        int generic, const int32_t* __restrict__ ids, int num_graphs, int64_t num_nodes, int64_t num_edges,
-        int32_t* __restrict__ gptr, int32_t* __restrict__ eoff, int32_t* __restrict__ sn0,
-        int32_t* __restrict__ se0, int32_t* __restrict__ ok, int32_t* __restrict__ gorder,
-        int64_t* __restrict__ y, int32_t* status) {
-    __shared__ int warp_sums[33];
-    __shared__ int sizes[kPlanOrderGraphs];
-    const int B = num_graphs;
-    long long carry_n = 0, carry_e = 0;
+// sizes of batch graph b from the data-set arrays; false when the id is outside the data set
+// or the two CSRs disagree about the graph's edge span (edges never leave their graph)
+__device__ __forceinline__ bool graph_extent(const CollateArgs& a, int b, int* n, int* e, int* first_node,
+                                             int* first_edge) {
+    const int64_t g = a.ids[b];
+    *n = 0; *e = 0; *first_node = 0; *first_edge = 0;
+    if (g < 0 || g >= a.ds.num_graphs) return false;
+    const int n0 = a.ds.gptr[g], n1 = a.ds.gptr[g + 1];
+    const int e0 = a.ds.rowptr[n0], e1 = a.ds.rowptr[n1];
+    if (n1 < n0 || e1 < e0) return false;
+    *first_node = n0; *first_edge = e0;
+    *n = n1 - n0; *e = e1 - e0;
+    if (a.generic && (a.ds.rowptr_t[n0] != e0 || a.ds.rowptr_t[n1] != e1)) return false;
+    return true;
+}
+
+// Block-wide: fill the tables for all B graphs (thread t owns a contiguous run of graphs:
+// sums, one packed scan, then the running prefixes).  Returns true when every id is valid and
+// the totals equal the caller's num_nodes / num_edges, which size every output buffer.
+__device__ bool build_tables(const CollateArgs& a, const Tables& t, unsigned long long (*red)[33]) {
+    const int B = a.num_graphs;
+    const int per = (B + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int b0 = min(B, (int)threadIdx.x * per), b1 = min(B, b0 + per);
+    unsigned long long ne = 0ull, wf = 0ull;         // (nodes | edges << 32), (bitmap | fragmap words << 32)
     bool bad = false;
-    for (int base = 0; base < B; base += kPlanThreads) {
-        const int b = base + threadIdx.x;
-        int n = 0, e = 0, first_node = 0, first_edge = 0;
-        if (b < B) {
-            const int64_t g = ids[b];
-            if (g < 0 || g >= ds_graphs) {
-                bad = true;
-            } else {
-                first_node = ds_gptr[g];
-                const int last_node = ds_gptr[g + 1];
-                first_edge = ds_rowptr[first_node];
-                const int last_edge = ds_rowptr[last_node];
-                n = last_node - first_node;
-                e = last_edge - first_edge;
-                // edges never leave their graph, so both CSRs put a graph's edges in the same span
-                if (ds_rowptr_t && (ds_rowptr_t[first_node] != first_edge || ds_rowptr_t[last_node] != last_edge))
-                    bad = true;
-                if (n < 0 || e < 0) { bad = true; n = 0; e = 0; }
-                if (y) y[b] = ds_y ? ds_y[g] : 0;
-            }
-            sn0[b] = first_node;
-            se0[b] = first_edge;
-            if (b < kPlanOrderGraphs) sizes[b] = n;
-        }
-        int tn, te;
-        const int xn = plan_scan(n, warp_sums, &tn);
-        const int xe = plan_scan(e, warp_sums, &te);
-        if (b < B) {
-            gptr[b] = (int32_t)(carry_n + xn);
-            eoff[b] = (int32_t)(carry_e + xe);
-        }
-        carry_n += tn;
-        carry_e += te;
+    for (int b = b0; b < b1; ++b) {
+        int n, e, fn, fe;
+        bad |= !graph_extent(a, b, &n, &e, &fn, &fe);
+        ne += (unsigned long long)(unsigned)n | ((unsigned long long)(unsigned)e << 32);
+        wf += (unsigned long long)(unsigned)map_words_bitmap(n) |
+              ((unsigned long long)(unsigned)map_words_fragmap(n) << 32);
     }
-    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    unsigned long long xne, xwf, tne, twf;
+    scan2(ne, wf, red, &xne, &xwf, &tne, &twf);
+    for (int b = b0; b < b1; ++b) {
+        int n, e, fn, fe;
+        graph_extent(a, b, &n, &e, &fn, &fe);
+        t.gptr[b] = (int32_t)(unsigned)(xne & 0xffffffffull);
+        t.eoff[b] = (int32_t)(unsigned)(xne >> 32);
+        t.bmoff[b] = (int32_t)(unsigned)(xwf & 0xffffffffull);
+        t.fgoff[b] = (int32_t)(unsigned)(xwf >> 32);
+        t.sn0[b] = fn;
+        t.se0[b] = fe;
+        xne += (unsigned long long)(unsigned)n | ((unsigned long long)(unsigned)e << 32);
+        xwf += (unsigned long long)(unsigned)map_words_bitmap(n) |
+               ((unsigned long long)(unsigned)map_words_fragmap(n) << 32);
+    }
     if (threadIdx.x == 0) {
-        // the caller's totals size every output buffer; n1_gather only runs when they are right
-        gptr[B] = (int32_t)num_nodes;
-        eoff[B] = (int32_t)num_edges;
-        const bool consistent = !any_bad && carry_n == num_nodes && carry_e == num_edges;
-        int s = 0;
-        if (!consistent) s |= DGCNN_GRAPH_BAD_BATCH;
-        if (generic) s |= DGCNN_GRAPH_GENERIC;
-        if (s && status) atomicOr(status, s);
-        *ok = consistent ? 1 : 0;
+        t.gptr[B] = a.num_nodes;                      // the caller's totals bound every loop below
+        t.eoff[B] = a.num_edges;
+        t.bmoff[B] = (int32_t)(unsigned)(twf & 0xffffffffull);
+        t.fgoff[B] = (int32_t)(unsigned)(twf >> 32);
     }
-    if (gorder) {
-        if (B > kPlanOrderGraphs) {
-            for (int g = threadIdx.x; g < B; g += kPlanThreads) gorder[g] = g;
-        } else {
-            for (int g = threadIdx.x; g < B; g += kPlanThreads) {
-                const int mine = sizes[g];
-                int rank = 0;
-                for (int h = 0; h < B; ++h) {
-                    const int other = sizes[h];
-                    rank += (other > mine) || (other == mine && h < g);
-                }
-                gorder[rank] = g;
-            }
-        }
-    }
+    const int any_bad = __syncthreads_or(bad ? 1 : 0);   // also publishes the tables to the CTA
+    return !any_bad && (unsigned)(tne & 0xffffffffull) == (unsigned)a.num_nodes &&
+           (unsigned)(tne >> 32) == (unsigned)a.num_edges;
+}
+
+// Plan kernel of the large-batch path: one CTA writes the tables and the verdict to the workspace.
+__global__ void __launch_bounds__(kPlanThreads)
+n1_plan(const CollateArgs a) {
+    __shared__ unsigned long long red[2][33];
+    const Tables t = carve_tables(a.ws_tables, a.num_graphs);
+    const bool ok = build_tables(a, t, red);
+    if (threadIdx.x == 0) *a.ws_ok = ok ? 1 : 0;
 }
 
 // largest b in [0, count) with table[b] <= v (table[0] == 0 <= v): with equal neighbours
@@ -173,108 +200,168 @@ __device__ __forceinline__ int owner_of(const int32_t* table, int count, int v) 
     return lo;
 }
 
-struct GatherArgs {
-    // data set
-    const float* ds_x; int64_t ds_ldx; int32_t num_features;
-    const int32_t* ds_rowptr; const int32_t* ds_col;
-    const int32_t* ds_rowptr_t; const int32_t* ds_col_t;     // NULL: symmetric, use rowptr/col
-    const float* ds_dis;
-    // plan
-    const int32_t* gptr; const int32_t* eoff; const int32_t* sn0; const int32_t* se0; const int32_t* ok;
-    int32_t num_graphs; int32_t num_nodes; int32_t num_edges;
-    // batch
-    float* x; int64_t ldx; int32_t* batch32;
-    int32_t* rowptr; int32_t* col; int32_t* rowptr_t; int32_t* col_t; float* dis;
-    int32_t* status;
-};
-
-__global__ void __launch_bounds__(kGatherThreads)
-n1_gather(const GatherArgs a) {
-    extern __shared__ int32_t tables[];
+__global__ void __launch_bounds__(kGatherThreads, 4)
+n1_gather(const CollateArgs a) {
+    extern __shared__ __align__(16) int32_t smem_tables[];
+    __shared__ unsigned long long red[2][33];
     const int B = a.num_graphs, N = a.num_nodes, E = a.num_edges;
-    if (*a.ok == 0) return;                          // inconsistent ids / totals: flagged by n1_plan
-    const int32_t *gptr = a.gptr, *eoff = a.eoff, *sn0 = a.sn0, *se0 = a.se0;
-    if (B <= kGatherSmemGraphs) {                    // offset tables into shared memory
-        int32_t* s_gptr = tables;
-        int32_t* s_eoff = s_gptr + (B + 1);
-        int32_t* s_sn0 = s_eoff + (B + 1);
-        int32_t* s_se0 = s_sn0 + B;
-        for (int i = threadIdx.x; i <= B; i += kGatherThreads) {
-            s_gptr[i] = gptr[i];
-            s_eoff[i] = eoff[i];
-            if (i < B) { s_sn0[i] = sn0[i]; s_se0[i] = se0[i]; }
-        }
-        __syncthreads();
-        gptr = s_gptr; eoff = s_eoff; sn0 = s_sn0; se0 = s_se0;
+    Tables t;
+    bool ok;
+    if (a.ws_tables) {                                // large batch: n1_plan ran first
+        t = carve_tables(a.ws_tables, B);
+        ok = *a.ws_ok != 0;
+    } else {
+        t = carve_tables(smem_tables, B);
+        ok = build_tables(a, t, red);
     }
+    const dgcnn_dataset& ds = a.ds;
+    const dgcnn_batch_graph& o = a.out;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.status) {
+        int s = ok ? 0 : DGCNN_GRAPH_BAD_BATCH;
+        if (a.generic) s |= DGCNN_GRAPH_GENERIC;
+        if (s) atomicOr(a.status, s);
+    }
+    if (!ok) return;                                  // nothing is written for an inconsistent batch
+    const bool maps = a.want_maps != 0;
     const int64_t stride = (int64_t)gridDim.x * kGatherThreads;
     const int64_t tid = (int64_t)blockIdx.x * kGatherThreads + threadIdx.x;
     bool bad = false;
 
-    // ---- edges: four consecutive batch edges per thread, one 16-byte store per array ----
-    const bool two = a.col_t != nullptr && a.col_t != a.col;
-    const int32_t* src_t = a.ds_col_t ? a.ds_col_t : a.ds_col;
-    const bool vec = ((reinterpret_cast<uintptr_t>(a.col) | (two ? reinterpret_cast<uintptr_t>(a.col_t) : 0)) & 15) == 0;
-    const int64_t quads = ((int64_t)E + 3) >> 2;
-    for (int64_t q = tid; q < quads; q += stride) {
-        const int j0 = (int)(q << 2);
-        int b = owner_of(eoff, B, j0);
-        int32_t v[4] = {0, 0, 0, 0}, vt[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int j = j0 + r;
-            if (j >= E) break;
-            while (b + 1 < B && j >= eoff[b + 1]) ++b;
-            const int first = gptr[b], nodes = gptr[b + 1] - first;
-            const int from = se0[b] + (j - eoff[b]);
-            const int base = sn0[b];
-            const int c = a.ds_col[from] - base;
-            bad |= (unsigned)c >= (unsigned)nodes;
-            v[r] = c + first;
-            if (two) {
-                const int ct = src_t[from] - base;
-                bad |= (unsigned)ct >= (unsigned)nodes;
-                vt[r] = ct + first;
-            }
+    // ---- per-graph outputs, spread over the first threads of the grid -------------------
+    for (int64_t b = tid; b <= B; b += stride) {
+        o.gptr[b] = t.gptr[b];
+        if (maps) { o.bmoff[b] = t.bmoff[b]; o.fgoff[b] = t.fgoff[b]; }
+        if (b == B) break;
+        const int64_t g = a.ids[b];
+        if (o.y) o.y[b] = ds.y[g];
+        if (maps) {
+            const int n = t.gptr[b + 1] - t.gptr[b];
+            o.gflags[b] = ds.gflags[g];
+            if (o.gflags_t) o.gflags_t[b] = a.generic ? ds.gflags_t[g] : (n > kMapMaxNodes ? 2 : 0);
         }
-        if (vec && j0 + 3 < E) {
-            *reinterpret_cast<int4*>(a.col + j0) = make_int4(v[0], v[1], v[2], v[3]);
-            if (two) *reinterpret_cast<int4*>(a.col_t + j0) = make_int4(vt[0], vt[1], vt[2], vt[3]);
+    }
+    // processing order: rank of every graph among all sizes (descending, ties by index), eight
+    // threads per graph; the owner of a rank also writes that slot's work descriptor
+    if (o.gorder) {
+        if (B > kOrderGraphs) {
+            for (int64_t b = tid; b < B; b += stride) {
+                o.gorder[b] = (int32_t)b;
+                if (maps && o.gdesc)
+                    reinterpret_cast<int4*>(o.gdesc)[b] =
+                        make_int4((int)b, t.gptr[b], t.gptr[b + 1] - t.gptr[b], t.fgoff[b]);
+            }
         } else {
-            for (int r = 0; r < 4 && j0 + r < E; ++r) {
-                a.col[j0 + r] = v[r];
-                if (two) a.col_t[j0 + r] = vt[r];
+            for (int64_t item = tid; item < ((int64_t)B + 3) / 4 * 32; item += stride) {   // whole warps
+                const int b = (int)(item >> 3), part = (int)(item & 7);
+                const bool live = b < B;
+                const int mine = live ? t.gptr[b + 1] - t.gptr[b] : 0;
+                int rank = 0;
+                if (live)
+                    for (int h = part; h < B; h += 8) {
+                        const int other = t.gptr[h + 1] - t.gptr[h];
+                        rank += (other > mine) || (other == mine && h < b);
+                    }
+                rank += __shfl_xor_sync(DGCNN_FULL_MASK, rank, 4);
+                rank += __shfl_xor_sync(DGCNN_FULL_MASK, rank, 2);
+                rank += __shfl_xor_sync(DGCNN_FULL_MASK, rank, 1);
+                if (live && part == 0) {
+                    o.gorder[rank] = b;
+                    if (maps && o.gdesc)
+                        reinterpret_cast<int4*>(o.gdesc)[rank] = make_int4(b, t.gptr[b], mine, t.fgoff[b]);
+                }
             }
         }
     }
 
-    // ---- nodes: row pointers, dis, graph id; i == N closes the last row ----
-    const bool two_rp = a.rowptr_t != nullptr && a.rowptr_t != a.rowptr;
-    const int32_t* rp_t = a.ds_rowptr_t ? a.ds_rowptr_t : a.ds_rowptr;
-    for (int64_t i = tid; i <= N; i += stride) {
-        if (i == N) {
-            a.rowptr[N] = E;
-            if (two_rp) a.rowptr_t[N] = E;
-            break;
-        }
-        const int b = owner_of(gptr, B, (int)i);
-        const int from = sn0[b] + ((int)i - gptr[b]);
-        const int shift = eoff[b] - se0[b];
-        a.rowptr[i] = a.ds_rowptr[from] + shift;
-        if (two_rp) a.rowptr_t[i] = rp_t[from] + shift;
-        a.dis[i] = a.ds_dis[from];
-        if (a.batch32) a.batch32[i] = b;
-    }
-
-    // ---- features: element-wise so that wide rows stay coalesced ----
-    if (a.x) {
-        const int F = a.num_features;
-        const int64_t total = (int64_t)N * F;
-        for (int64_t t = tid; t < total; t += stride) {
-            const int i = (int)(t / F), f = (int)(t - (int64_t)i * F);
-            const int b = owner_of(gptr, B, i);
-            const int64_t from = sn0[b] + (i - gptr[b]);
-            a.x[(int64_t)i * a.ldx + f] = a.ds_x[from * a.ds_ldx + f];
+    // ---- one index space for everything that is copied: [edge octets | nodes | feature elements
+    //      | bitmap quads | bitmap_t quads | fragment-map quads] -----------------------------
+    const bool two = o.col_t != nullptr && o.col_t != o.col;          // a second CSR to write
+    const bool two_rp = o.rowptr_t != nullptr && o.rowptr_t != o.rowptr;
+    const int32_t* col_t_src = a.generic ? ds.col_t : ds.col;
+    const int32_t* rowptr_t_src = a.generic ? ds.rowptr_t : ds.rowptr;
+    const bool vec = ((reinterpret_cast<uintptr_t>(o.col) | (two ? reinterpret_cast<uintptr_t>(o.col_t) : 0)) & 15) == 0;
+    const int F = ds.num_features;
+    const int64_t n_quads = ((int64_t)E + kEdgesPerItem - 1) / kEdgesPerItem;
+    const int64_t n_nodes = (int64_t)N + 1;
+    const int64_t n_feat = o.x ? (int64_t)N * F : 0;
+    const int64_t n_bm = maps ? (t.bmoff[B] >> 2) : 0;                 // word counts are multiples of 16
+    const int64_t n_bmt = (maps && a.generic && o.bitmap_t) ? n_bm : 0;
+    const int64_t n_fg = maps ? (t.fgoff[B] >> 2) : 0;
+    const int64_t c1 = n_quads, c2 = c1 + n_nodes, c3 = c2 + n_feat, c4 = c3 + n_bm, c5 = c4 + n_bmt,
+                  c6 = c5 + n_fg;
+    for (int64_t u = tid; u < c6; u += stride) {
+        if (u < c1) {                                 // eight consecutive batch edges: eight loads in flight,
+            const int j0 = (int)(u << 3);             // two 16-byte stores per array
+            int b = owner_of(t.eoff, B, j0);
+            int32_t v[kEdgesPerItem], vt[kEdgesPerItem];
+#pragma unroll
+            for (int r = 0; r < kEdgesPerItem; ++r) {
+                const int j = j0 + r;
+                v[r] = 0; vt[r] = 0;
+                if (j < E) {
+                    while (b + 1 < B && j >= t.eoff[b + 1]) ++b;
+                    const int first = t.gptr[b], nodes = t.gptr[b + 1] - first;
+                    const int from = t.se0[b] + (j - t.eoff[b]);
+                    const int base = t.sn0[b];
+                    const int c = ds.col[from] - base;
+                    bad |= (unsigned)c >= (unsigned)nodes;
+                    v[r] = c + first;
+                    if (two) {
+                        const int ct = col_t_src[from] - base;
+                        bad |= (unsigned)ct >= (unsigned)nodes;
+                        vt[r] = ct + first;
+                    }
+                }
+            }
+            if (vec && j0 + kEdgesPerItem <= E) {
+#pragma unroll
+                for (int r = 0; r < kEdgesPerItem; r += 4) {
+                    *reinterpret_cast<int4*>(o.col + j0 + r) = make_int4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+                    if (two)
+                        *reinterpret_cast<int4*>(o.col_t + j0 + r) = make_int4(vt[r], vt[r + 1], vt[r + 2], vt[r + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < kEdgesPerItem; ++r)
+                    if (j0 + r < E) {
+                        o.col[j0 + r] = v[r];
+                        if (two) o.col_t[j0 + r] = vt[r];
+                    }
+            }
+        } else if (u < c2) {                          // row pointers, dis, graph id; i == N closes the last row
+            const int i = (int)(u - c1);
+            if (i == N) {
+                o.rowptr[N] = E;
+                if (two_rp) o.rowptr_t[N] = E;
+            } else {
+                const int b = owner_of(t.gptr, B, i);
+                const int from = t.sn0[b] + (i - t.gptr[b]);
+                const int shift = t.eoff[b] - t.se0[b];
+                o.rowptr[i] = ds.rowptr[from] + shift;
+                if (two_rp) o.rowptr_t[i] = rowptr_t_src[from] + shift;
+                o.dis[i] = ds.dis[from];
+                if (o.batch32) o.batch32[i] = b;
+            }
+        } else if (u < c3) {                          // features, element-wise: wide rows stay coalesced
+            const int64_t e = u - c2;
+            const int i = e < 0x7fffffff ? (int)((unsigned)e / (unsigned)F) : (int)(e / F);
+            const int f = (int)(e - (int64_t)i * F);
+            const int b = owner_of(t.gptr, B, i);
+            const int64_t from = t.sn0[b] + (i - t.gptr[b]);
+            o.x[(int64_t)i * o.ldx + f] = ds.x[from * ds.ldx + f];
+        } else if (u < c5) {                          // adjacency bitmaps (A_hat, then A_hat^T), 16 bytes at a time
+            const bool second = u >= c4;
+            const int w = (int)((u - (second ? c4 : c3)) << 2);
+            const int b = owner_of(t.bmoff, B, w);
+            const int64_t from = (int64_t)ds.bmoff[a.ids[b]] + (w - t.bmoff[b]);
+            const uint32_t* src = second ? ds.bitmap_t : ds.bitmap;
+            uint32_t* dst = second ? o.bitmap_t : o.bitmap;
+            *reinterpret_cast<int4*>(dst + w) = *reinterpret_cast<const int4*>(src + from);
+        } else {                                      // fragment maps
+            const int w = (int)((u - c5) << 2);
+            const int b = owner_of(t.fgoff, B, w);
+            const int64_t from = (int64_t)ds.fgoff[a.ids[b]] + (w - t.fgoff[b]);
+            *reinterpret_cast<int4*>(o.fragmap + w) = *reinterpret_cast<const int4*>(ds.fragmap + from);
         }
     }
     if (bad && a.status) atomicOr(a.status, DGCNN_GRAPH_BAD_EDGE);
@@ -286,52 +373,67 @@ using namespace dgcnn;
 
 extern "C" size_t dgcnn_collate_workspace_bytes(int64_t num_graphs) {
     if (num_graphs < 0) return 0;
-    return carve_collate_workspace(nullptr, num_graphs).bytes + 256;
+    return sizeof(int32_t) * (table_ints(num_graphs) + 64) + 512;
 }
 
 extern "C" int dgcnn_collate(const dgcnn_dataset* ds, const int32_t* ids, int64_t num_graphs,
-                             int64_t num_nodes, int64_t num_edges, float* x, int64_t ldx,
-                             int32_t* batch32, int64_t* y, int32_t* rowptr, int32_t* col,
-                             int32_t* rowptr_t, int32_t* col_t, float* dis, int32_t* gptr,
-                             int32_t* gorder, int32_t* status, void* workspace, size_t workspace_bytes,
-                             void* stream) {
+                             int64_t num_nodes, int64_t num_edges, const dgcnn_batch_graph* out,
+                             int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     const int64_t B = num_graphs, N = num_nodes, E = num_edges;
-    if (!ds || !ids || B < 1 || N < 0 || E < 0) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!ds || !ids || !out || B < 1 || N < 0 || E < 0) return DGCNN_ERR_INVALID_ARGUMENT;
     if (!ds->gptr || !ds->rowptr || !ds->dis || ds->num_graphs < 1 || ds->num_features < 1)
         return DGCNN_ERR_INVALID_ARGUMENT;
     if (ds->num_edges > 0 && !ds->col) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (!ds->symmetric && (!ds->rowptr_t || (ds->num_edges > 0 && !ds->col_t))) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (!rowptr || !dis || !gptr || (E > 0 && !col)) return DGCNN_ERR_INVALID_ARGUMENT;
-    if ((rowptr_t == nullptr) != (col_t == nullptr) && E > 0) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (x && (!ds->x || ldx < ds->num_features || ds->ldx < ds->num_features)) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (y && !ds->y) return DGCNN_ERR_INVALID_ARGUMENT;
+    const bool generic = !ds->symmetric;
+    if (generic && (!ds->rowptr_t || (ds->num_edges > 0 && !ds->col_t))) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!out->rowptr || !out->dis || !out->gptr || (E > 0 && !out->col)) return DGCNN_ERR_INVALID_ARGUMENT;
+    if ((out->rowptr_t == nullptr) != (out->col_t == nullptr) && E > 0) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (out->x && (!ds->x || out->ldx < ds->num_features || ds->ldx < ds->num_features))
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (out->y && !ds->y) return DGCNN_ERR_INVALID_ARGUMENT;
+    const bool maps = out->bitmap != nullptr;
+    if (maps) {                                       // K0b's outputs come as a set
+        if (!out->bmoff || !out->gflags || !out->fragmap || !out->fgoff) return DGCNN_ERR_INVALID_ARGUMENT;
+        if (!ds->bitmap || !ds->bmoff || !ds->gflags || !ds->fragmap || !ds->fgoff)
+            return DGCNN_ERR_INVALID_ARGUMENT;
+        if (out->gdesc && (!out->gorder || ((uintptr_t)out->gdesc & 15))) return DGCNN_ERR_INVALID_ARGUMENT;
+        if (generic && out->bitmap_t && (!ds->bitmap_t || !ds->gflags_t || !out->gflags_t))
+            return DGCNN_ERR_INVALID_ARGUMENT;
+        if (((uintptr_t)out->bitmap | (uintptr_t)out->bitmap_t | (uintptr_t)out->fragmap |
+             (uintptr_t)ds->bitmap | (uintptr_t)ds->bitmap_t | (uintptr_t)ds->fragmap) & 15)
+            return DGCNN_ERR_INVALID_ARGUMENT;
+    }
     if (N >= INT32_MAX || E >= INT32_MAX || B >= INT32_MAX || ds->num_nodes >= INT32_MAX ||
         ds->num_edges >= INT32_MAX)
         return DGCNN_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < dgcnn_collate_workspace_bytes(B)) return DGCNN_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
-    CollateWorkspace w = carve_collate_workspace(reinterpret_cast<void*>(aligned), B);
-    const bool generic = !ds->symmetric;
 
-    n1_plan<<<1, kPlanThreads, 0, st>>>(ds->gptr, ds->rowptr, generic ? ds->rowptr_t : nullptr, ds->y,
-                                        ds->num_graphs, generic ? 1 : 0, ids, (int)B, N, E, gptr, w.eoff,
-                                        w.sn0, w.se0, w.ok, gorder, y, status);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-
-    GatherArgs a;
-    a.ds_x = x ? ds->x : nullptr; a.ds_ldx = ds->ldx; a.num_features = ds->num_features;
-    a.ds_rowptr = ds->rowptr; a.ds_col = ds->col;
-    a.ds_rowptr_t = generic ? ds->rowptr_t : nullptr; a.ds_col_t = generic ? ds->col_t : nullptr;
-    a.ds_dis = ds->dis;
-    a.gptr = gptr; a.eoff = w.eoff; a.sn0 = w.sn0; a.se0 = w.se0; a.ok = w.ok;
+    CollateArgs a;
+    a.ds = *ds;
+    a.out = *out;
+    a.ids = ids;
     a.num_graphs = (int32_t)B; a.num_nodes = (int32_t)N; a.num_edges = (int32_t)E;
-    a.x = x; a.ldx = ldx; a.batch32 = batch32;
-    a.rowptr = rowptr; a.col = col; a.rowptr_t = rowptr_t; a.col_t = col_t; a.dis = dis;
+    a.generic = generic ? 1 : 0;
+    a.want_maps = maps ? 1 : 0;
     a.status = status;
-    const int64_t work = ((E + 3) >> 2) > N + 1 ? ((E + 3) >> 2) : N + 1;
-    const size_t smem = B <= kGatherSmemGraphs ? sizeof(int32_t) * (size_t)(4 * B + 2) : 0;
-    n1_gather<<<grid_for(work, kGatherThreads, 8), kGatherThreads, smem, st>>>(a);
+    a.ws_tables = nullptr;
+    a.ws_ok = nullptr;
+    size_t smem = sizeof(int32_t) * table_ints(B);
+    if (B > kFusedGraphs) {
+        int32_t* base = reinterpret_cast<int32_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        a.ws_ok = base;
+        a.ws_tables = base + 64;
+        smem = 0;
+        n1_plan<<<1, kPlanThreads, 0, st>>>(a);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
+    // upper bound of the unified index space (map words: at most (N + 15 B) * 32 / 4 quads each);
+    // ONE wave of CTAs (4 per SM at <= 64 registers): every CTA of the fused launch derives the
+    // tables first, a second wave would pay for that again
+    const int64_t work = (E + kEdgesPerItem - 1) / kEdgesPerItem + N + 1 +
+                         (out->x ? N * ds->num_features : 0) + (maps ? (N + 16 * B) : 0);
+    n1_gather<<<grid_for(work, kGatherThreads, 4), kGatherThreads, smem, st>>>(a);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

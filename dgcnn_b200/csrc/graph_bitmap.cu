@@ -219,7 +219,8 @@ extern "C" int64_t dgcnn_graph_bitmap_words(int64_t num_nodes, int64_t num_graph
     if (max_nodes > 1024) max_nodes = 1024;
     const int64_t npmax = (max_nodes + 15) / 16 * 16;
     // sum_g np_g * wpr_g <= (N + 15 B) * wpr_max
-    return (num_nodes + 15 * num_graphs) * ((npmax + 31) / 32) + 32;
+    // (a multiple of 4 words, so that a second bitmap placed right behind stays 16-byte aligned)
+    return ((num_nodes + 15 * num_graphs) * ((npmax + 31) / 32) + 32 + 3) / 4 * 4;
 }
 
 extern "C" int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_graphs, int64_t max_nodes) {

@@ -162,7 +162,7 @@ int check_step_args(const StepArgs& t, bool resident) {
 // [peer all-reduce +] Adam.  batch64 / batch32: the node -> graph vector in whichever form
 // the batch has it (K0b saves a search per row with it).
 int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, int64_t ldx,
-                     const int64_t* batch64, const int32_t* batch32, const int64_t* y) {
+                     const int64_t* batch64, const int32_t* batch32, const int64_t* y, bool maps_ready) {
     const int64_t N = t.N, B = t.B;
     const int32_t F = t.F, C = t.C, k = t.k;
     void* stream = t.stream;
@@ -179,10 +179,11 @@ int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, in
     float* stats = t.grads + n_params;                // [sum of NLL, #correct] ride the all-reduce
     const int bwd_kind = dgcnn_stack_bwd_supported(F, t.max_nodes);   // 1 MMA, 2 FMA only
 
-    DGCNN_TRY(dgcnn_build_bitmaps(s.rowptr, s.col, s.rowptr_t, s.col_t, s.gptr, batch64, batch32, N, B,
-                                  t.max_nodes, s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags,
-                                  s.gflags_t, s.fragmap, s.fm_words, s.fgoff, s.gorder, s.gdesc,
-                                  t.graph_status, DGCNN_GRAPH_GENERIC, stream));
+    if (!maps_ready)                                  // (a resident data set hands K0b's outputs over)
+        DGCNN_TRY(dgcnn_build_bitmaps(s.rowptr, s.col, s.rowptr_t, s.col_t, s.gptr, batch64, batch32, N, B,
+                                      t.max_nodes, s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags,
+                                      s.gflags_t, s.fragmap, s.fm_words, s.fgoff, s.gorder, s.gdesc,
+                                      t.graph_status, DGCNN_GRAPH_GENERIC, stream));
     DGCNN_TRY(dgcnn_stack_fwd(x, ldx, F, s.rowptr, s.col, s.dis, s.gptr, s.gorder, s.bitmap, s.bmoff,
                               s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, t.max_nodes, p[0], p[1], p[2], p[3],
                               p[4], p[5], p[6], p[7], s.xcat, kXcatLd, s.pooled, s.perm, k, t.norm,
@@ -247,7 +248,7 @@ extern "C" int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_in
                                     s.col_t, s.dis, s.gptr, s.gorder, graph_status, 0, s.ws_build, s.n_build,
                                     stream));
     return step_after_build(t, s, x, ldx, index_is_i32 ? nullptr : static_cast<const int64_t*>(batch),
-                            index_is_i32 ? static_cast<const int32_t*>(batch) : nullptr, y);
+                            index_is_i32 ? static_cast<const int32_t*>(batch) : nullptr, y, false);
 }
 
 // The same step fed from a data set that is resident in HBM: dgcnn_collate
@@ -278,9 +279,18 @@ extern "C" int dgcnn_train_step_resident(const dgcnn_dataset* dataset, const int
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(graph_status, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
-    DGCNN_TRY(dgcnn_collate(dataset, ids, B, N, E, s.x_batch, F, s.batch32, s.y_batch, s.rowptr, s.col,
-                            s.rowptr_t, s.col_t, s.dis, s.gptr, s.gorder, graph_status, s.ws_build, s.n_build,
-                            stream));
-    return step_after_build(t, s, s.x_batch, F, nullptr, s.batch32, s.y_batch);
+    // K0b's outputs are gathered too when the data set carries them and every graph of the batch
+    // owns a bitmap (max_nodes <= 1024); otherwise K0b runs on the gathered CSR
+    const bool maps = dataset->bitmap && dataset->fragmap && max_nodes <= 1024;
+    dgcnn_batch_graph out{};
+    out.x = s.x_batch; out.ldx = F; out.batch32 = s.batch32; out.y = s.y_batch;
+    out.rowptr = s.rowptr; out.col = s.col; out.rowptr_t = s.rowptr_t; out.col_t = s.col_t;
+    out.dis = s.dis; out.gptr = s.gptr; out.gorder = s.gorder;
+    if (maps) {
+        out.bitmap = s.bitmap; out.bitmap_t = s.bitmap_t; out.bmoff = s.bmoff; out.gflags = s.gflags;
+        out.gflags_t = s.gflags_t; out.fragmap = s.fragmap; out.fgoff = s.fgoff; out.gdesc = s.gdesc;
+    }
+    DGCNN_TRY(dgcnn_collate(dataset, ids, B, N, E, &out, graph_status, s.ws_build, s.n_build, stream));
+    return step_after_build(t, s, s.x_batch, F, nullptr, s.batch32, s.y_batch, maps);
 }
 #undef DGCNN_TRY

@@ -212,7 +212,8 @@ class DeviceDataset:
     batch for ``Model(data)`` (evaluation, train.py:60); ``FusedTrainer.step_resident`` runs a
     whole training step on ``ids`` (train.py:35-45)."""
 
-    def __init__(self, graphs: Sequence[dict], device, num_classes: Optional[int] = None):
+    def __init__(self, graphs: Sequence[dict], device, num_classes: Optional[int] = None,
+                 maps: bool = True):
         if not graphs:
             raise ValueError("DeviceDataset needs at least one graph")
         dev = torch.device(device)
@@ -243,12 +244,26 @@ class DeviceDataset:
         self.col_t = None if self.symmetric else graph.col_t[:max(self.num_edges, 1)].contiguous()
         first = self.rowptr[self.gptr.long()]
         self.edges = (first[1:] - first[:-1]).cpu().numpy().astype(np.int64)   # per-graph edge counts
+        # K0b over the whole data set, once: per-graph bitmaps / fragment maps are relative to the
+        # graph's first node, so a batch's maps are copies of these blocks
+        self.maps = None
+        if maps and int(self.nodes.max()) > 0:
+            graph.max_nodes = int(min(int(self.nodes.max()), ops.BITMAP_MAX_NODES))
+            graph.gorder = None                                          # descriptors are per batch
+            ops._build_bitmaps(graph, not self.symmetric, host.batch.to(dev))
+            self.maps = graph
+        m = self.maps
         self._struct = _lib.DgcnnDataset(
             self.num_graphs, self.num_nodes, self.num_edges, self.num_features, int(self.symmetric),
             self.x.data_ptr(), int(self.x.stride(0)) if n > 1 else self.num_features, self.y.data_ptr(),
             self.gptr.data_ptr(), self.rowptr.data_ptr(), self.col.data_ptr(),
             None if self.symmetric else self.rowptr_t.data_ptr(),
-            None if self.symmetric else self.col_t.data_ptr(), self.dis.data_ptr())
+            None if self.symmetric else self.col_t.data_ptr(), self.dis.data_ptr(),
+            None if m is None else m.bitmap.data_ptr(),
+            None if m is None or self.symmetric else m.bitmap_t.data_ptr(),
+            None if m is None else m.bmoff.data_ptr(), None if m is None else m.gflags.data_ptr(),
+            None if m is None or self.symmetric else m.gflags_t.data_ptr(),
+            None if m is None else m.fragmap.data_ptr(), None if m is None else m.fgoff.data_ptr())
 
     def __len__(self) -> int:
         return self.num_graphs
@@ -259,6 +274,9 @@ class DeviceDataset:
 
     def nbytes(self) -> int:
         ts = [self.x, self.y, self.gptr, self.rowptr, self.col, self.dis, self.rowptr_t, self.col_t]
+        if self.maps is not None:
+            m = self.maps
+            ts += [m.bitmap, m.bitmap_t, m.bmoff, m.gflags, m.gflags_t, m.fragmap, m.fgoff]
         return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
     def plan(self, ids) -> Tuple[int, int, int]:
@@ -295,17 +313,32 @@ class DeviceDataset:
         gptr, gorder = torch.empty(b + 1, **i32), torch.empty(b, **i32)
         status = torch.zeros(1, **i32)
         ws = torch.empty(int(lib.dgcnn_collate_workspace_bytes(b)), dtype=torch.uint8, device=dev)
+        graph = ops.Graph(rowptr, col, rowptr_t, col_t, dis, gptr, gorder, status, n, b, mx)
+        want_maps = bitmaps and 0 < mx <= ops.BITMAP_MAX_NODES
+        gathered = want_maps and self.maps is not None
+        p = lambda t: None if t is None else t.data_ptr()
+        if gathered:                                   # K0b's outputs come from the data set's cache
+            words = int(lib.dgcnn_graph_bitmap_words(n, b, mx))
+            fwords = int(lib.dgcnn_graph_fragmap_words(n, b, mx))
+            both = torch.empty((1 if self.symmetric else 2) * words, **i32)
+            graph.bitmap = both[:words]
+            graph.bitmap_t = None if self.symmetric else both[words:]
+            graph.bmoff, graph.gflags = torch.empty(b + 1, **i32), torch.empty(b, **i32)
+            graph.bmoff_t = None if self.symmetric else graph.bmoff
+            graph.gflags_t = None if self.symmetric else torch.empty(b, **i32)
+            graph.fragmap, graph.fgoff = torch.empty(fwords, **i32), torch.empty(b + 1, **i32)
+            graph.gdesc = torch.empty(b, 4, **i32)
+        out = _lib.DgcnnBatchGraph(
+            p(x), self.num_features, p(batch32), p(y), p(rowptr), p(col), p(rowptr_t), p(col_t), p(dis),
+            p(gptr), p(gorder), p(graph.bitmap), p(graph.bitmap_t), p(graph.bmoff), p(graph.gflags),
+            p(graph.gflags_t), p(graph.fragmap), p(graph.fgoff), p(graph.gdesc))
         with torch.cuda.device(dev):
-            rc = lib.dgcnn_collate(self.c_struct, ids_device.data_ptr(), b, n, e,
-                                   None if x is None else x.data_ptr(), self.num_features,
-                                   batch32.data_ptr(), y.data_ptr(), rowptr.data_ptr(), col.data_ptr(),
-                                   rowptr_t.data_ptr(), col_t.data_ptr(), dis.data_ptr(), gptr.data_ptr(),
-                                   gorder.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(),
+            rc = lib.dgcnn_collate(self.c_struct, ids_device.data_ptr(), b, n, e, ctypes.byref(out),
+                                   status.data_ptr(), ws.data_ptr(), ws.numel(),
                                    torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "collate")
-        ops.LAUNCHES["collate"] = ops.LAUNCHES.get("collate", 0) + 2
-        graph = ops.Graph(rowptr, col, rowptr_t, col_t, dis, gptr, gorder, status, n, b, mx)
-        if bitmaps and 0 < mx <= ops.BITMAP_MAX_NODES:
+        ops.LAUNCHES["collate"] = ops.LAUNCHES.get("collate", 0) + (1 if b <= 1024 else 2)
+        if want_maps and not gathered:
             ops._build_bitmaps(graph, True, batch32)
         return ResidentBatch(x, batch32, y, gptr, graph, ids)
 

@@ -392,13 +392,19 @@ int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_index, int32_
  *   train.py:108-109  DataLoader -> PyG Batch.from_data_list (concatenate, shift edge ids by the
  *                     node offset, emit `batch`)        train.py:36  sample.to(device)
  *   model.py:28 + gcn_norm prologue (K0) for that batch
- * The data set is ONE batch of all its graphs that went through dgcnn_build_graph once (so
- * loops are dropped, rows sorted, the symmetry verdict known) and stays in HBM:
+ * The data set is ONE batch of all its graphs that went through dgcnn_build_graph (and,
+ * optionally, dgcnn_build_bitmaps with max_nodes = min(largest graph, 1024)) once -- so loops
+ * are dropped, rows sorted, the symmetry verdict known -- and stays in HBM:
  *   gptr [G+1], rowptr [Nd+1], col [Ed], dis [Nd]   K0's outputs over the whole data set
  *   rowptr_t, col_t   K0's CSR by source; may be NULL when `symmetric` (K0 did not raise
  *                     DGCNN_GRAPH_GENERIC: both CSRs are equal)
  *   x [Nd, F] (row stride ldx), y [G] int64        features and labels (either may be NULL
  *                     when the matching output is not requested)
+ *   bitmap, bmoff [G+1], gflags [G], fragmap, fgoff [G+1]   K0b's outputs over the whole data
+ *                     set (NULL: the batch's maps cannot be gathered, run dgcnn_build_bitmaps on
+ *                     the gathered CSR instead); bitmap_t, gflags_t [G] for a data set that is
+ *                     not symmetric.  K0b's per-graph blocks are relative to the graph's first
+ *                     node, so they can be copied as they are.
  * Edges must not cross graphs (true of any PyG data set; the Python side checks it once).
  * The struct itself lives in HOST memory (its members are device pointers) and is only read
  * during the call.
@@ -406,7 +412,7 @@ int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_index, int32_
 typedef struct dgcnn_dataset {
     int64_t num_graphs, num_nodes, num_edges;   /* G, Nd, Ed = rowptr[Nd] */
     int32_t num_features;                       /* F */
-    int32_t symmetric;                          /* 1: rowptr_t/col_t unused */
+    int32_t symmetric;                          /* 1: rowptr_t/col_t/bitmap_t/gflags_t unused */
     const float* x;
     int64_t ldx;
     const int64_t* y;
@@ -416,29 +422,64 @@ typedef struct dgcnn_dataset {
     const int32_t* rowptr_t;
     const int32_t* col_t;
     const float* dis;
+    const uint32_t* bitmap;
+    const uint32_t* bitmap_t;
+    const int32_t* bmoff;
+    const int32_t* gflags;
+    const int32_t* gflags_t;
+    const uint32_t* fragmap;
+    const int32_t* fgoff;
 } dgcnn_dataset;
 
+/* Where a gathered batch goes (HOST struct of device pointers, caller-owned buffers): exactly the
+ * outputs of dgcnn_build_graph(_i32) and dgcnn_build_bitmaps on the host-collated batch of the
+ * same graphs, plus the collated features / graph ids / labels.
+ *   x [N, F] (row stride ldx), batch32 [N], y [B]                 optional
+ *   rowptr [N+1], col [E], dis [N], gptr [B+1]                    required;  gorder [B] optional
+ *   rowptr_t / col_t   both NULL, or aliases of rowptr / col (fine for a symmetric data set:
+ *                      one copy is written), or separate buffers
+ *   bitmap .. gdesc    K0b's outputs, sized as for dgcnn_build_bitmaps with max_nodes =
+ *                      min(largest graph of the batch, 1024); bitmap NULL skips all of them;
+ *                      bitmap_t / gflags_t optional (only written -- bitmap_t -- for a data set
+ *                      that is not symmetric); gdesc (16-byte aligned, needs gorder) optional.
+ *                      Words past bmoff[B] / fgoff[B] are not touched. */
+typedef struct dgcnn_batch_graph {
+    float* x;
+    int64_t ldx;
+    int32_t* batch32;
+    int64_t* y;
+    int32_t* rowptr;
+    int32_t* col;
+    int32_t* rowptr_t;
+    int32_t* col_t;
+    float* dis;
+    int32_t* gptr;
+    int32_t* gorder;
+    uint32_t* bitmap;
+    uint32_t* bitmap_t;
+    int32_t* bmoff;
+    int32_t* gflags;
+    int32_t* gflags_t;
+    uint32_t* fragmap;
+    int32_t* fgoff;
+    int32_t* gdesc;
+} dgcnn_batch_graph;
+
 /* A batch = ids[0..B) (device int32, graph ids of the data set in batch order, repeats
- * allowed).  Writes exactly what dgcnn_build_graph(_i32) produces from the host-collated
- * batch -- rowptr [N+1], col [E], dis [N], gptr [B+1], gorder [B] (optional) -- plus the
- * collated x [N, F] (row stride ldx; optional), batch32 [N] (optional), y [B] (optional).
- * rowptr_t / col_t: both NULL, or aliases of rowptr / col (fine for a symmetric data set: one
- * copy is written), or separate buffers.  `status` is OR-ed with DGCNN_GRAPH_GENERIC when the
- * data set is not symmetric (what K0 would report), DGCNN_GRAPH_BAD_BATCH when an id is
- * outside [0, G) or num_nodes / num_edges (host arithmetic on the per-graph sizes, which size
- * the outputs) disagree with the ids -- then nothing else is written --, DGCNN_GRAPH_BAD_EDGE
- * when an edge leaves its graph.  Two launches, B, N, E < 2^31. */
+ * allowed).  `status` is OR-ed with DGCNN_GRAPH_GENERIC when the data set is not symmetric
+ * (what K0 would report), DGCNN_GRAPH_BAD_BATCH when an id is outside [0, G) or num_nodes /
+ * num_edges (host arithmetic on the per-graph sizes, which size the outputs) disagree with
+ * the ids -- then nothing is written --, DGCNN_GRAPH_BAD_EDGE when an edge leaves its graph.
+ * One launch for B <= 1024 (two beyond); B, N, E < 2^31. */
 size_t dgcnn_collate_workspace_bytes(int64_t num_graphs);
 int dgcnn_collate(const dgcnn_dataset* dataset, const int32_t* ids, int64_t num_graphs,
-                  int64_t num_nodes, int64_t num_edges, float* x, int64_t ldx,
-                  int32_t* batch32, int64_t* y, int32_t* rowptr, int32_t* col,
-                  int32_t* rowptr_t, int32_t* col_t, float* dis, int32_t* gptr,
-                  int32_t* gorder, int32_t* status, void* workspace, size_t workspace_bytes,
-                  void* stream);
+                  int64_t num_nodes, int64_t num_edges, const dgcnn_batch_graph* out,
+                  int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
-/* dgcnn_train_step with the batch taken from a resident data set: dgcnn_collate replaces K0
- * and the host-to-device copy; everything after it is the same call sequence, and the result
- * is bit-identical to dgcnn_train_step on the host-collated batch of the same graphs.
+/* dgcnn_train_step with the batch taken from a resident data set: dgcnn_collate replaces the
+ * host-to-device copy, K0 and (when the data set carries K0b's maps) K0b; everything after it
+ * is the same call sequence, and the result is bit-identical to dgcnn_train_step on the
+ * host-collated batch of the same graphs.
  * num_nodes, num_edges, max_nodes: sums / maximum of the per-graph sizes over ids (host
  * arithmetic; the caller keeps the sizes).  Other arguments as for dgcnn_train_step. */
 size_t dgcnn_train_step_resident_workspace_bytes(int64_t num_nodes, int64_t num_edges,

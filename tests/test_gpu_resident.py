@@ -103,11 +103,20 @@ def test_collate_of_a_generic_data_set(sizes):
         if ds.nodes[ids].sum() == 0:
             continue
         hb, db = host_graph(graphs, ids)
-        want = ops.build_graph(db.edge_index, db.batch, hb.num_nodes, len(ids), transpose=True, max_nodes=0)
+        want = ops.build_graph(db.edge_index, db.batch, hb.num_nodes, len(ids), transpose=True,
+                               max_nodes=db.max_nodes)
         rb = ds.batch(ids)
         e = ds.plan(ids)[1]
         assert e == int(want.rowptr[-1].item())                 # loops dropped
-        assert_same_graph(rb._dgcnn_graph, want, e)
+        got = rb._dgcnn_graph
+        assert_same_graph(got, want, e)
+        # K0b's outputs gathered from the data set's cache: both bitmaps, duplicate flags, fragment maps
+        for name_ in ("bmoff", "gflags", "gflags_t", "fgoff", "gdesc"):
+            assert torch.equal(getattr(got, name_), getattr(want, name_)), name_
+        bm_end, fg_end = int(want.bmoff[-1]), int(want.fgoff[-1])
+        assert torch.equal(got.bitmap[:bm_end], want.bitmap[:bm_end]), "bitmap"
+        assert torch.equal(got.bitmap_t[:bm_end], want.bitmap_t[:bm_end]), "bitmap_t"
+        assert torch.equal(got.fragmap[:fg_end], want.fragmap[:fg_end]), "fragmap"
         assert torch.equal(rb.x, db.x) and torch.equal(rb.batch.long(), db.batch)
         st = int(rb._dgcnn_graph.status.item())
         assert st & ops.GRAPH_GENERIC and not st & (ops.GRAPH_BAD_EDGE | ops.GRAPH_BAD_BATCH)
@@ -149,10 +158,10 @@ def test_collate_flags_bad_ids_and_totals():
         dis = torch.empty(n_, device=DEV)
         gptr, status = torch.empty(b + 1, **i32), torch.zeros(1, **i32)
         ws = torch.empty(int(lib.dgcnn_collate_workspace_bytes(b)), dtype=torch.uint8, device=DEV)
-        rc = lib.dgcnn_collate(ds.c_struct, ids_dev.data_ptr(), b, n_, e_, None, ds.num_features, None, None,
-                               rowptr.data_ptr(), col.data_ptr(), None, None, dis.data_ptr(), gptr.data_ptr(),
-                               None, status.data_ptr(), ws.data_ptr(), ws.numel(),
-                               torch.cuda.current_stream().cuda_stream)
+        out = _lib.DgcnnBatchGraph()                             # everything optional stays NULL
+        out.rowptr, out.col, out.dis, out.gptr = rowptr.data_ptr(), col.data_ptr(), dis.data_ptr(), gptr.data_ptr()
+        rc = lib.dgcnn_collate(ds.c_struct, ids_dev.data_ptr(), b, n_, e_, ctypes.byref(out), status.data_ptr(),
+                               ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         return int(status.item()), rowptr, col
 
@@ -165,8 +174,11 @@ def test_collate_flags_bad_ids_and_totals():
     st, _, col = run(bad, n, e)
     assert st & ops.GRAPH_BAD_BATCH and int(col[0]) == -7
     # argument errors come back as codes, never as exceptions or crashes
-    assert lib.dgcnn_collate(ds.c_struct, None, 1, 1, 0, None, 1, None, None, None, None, None, None, None,
-                             None, None, None, None, 0, None) == -1
+    empty = _lib.DgcnnBatchGraph()
+    assert lib.dgcnn_collate(ds.c_struct, None, 1, 1, 0, ctypes.byref(empty), None, None, 0, None) == -1
+    ids_dev = torch.zeros(1, **i32)
+    assert lib.dgcnn_collate(ds.c_struct, ids_dev.data_ptr(), 1, 1, 0, ctypes.byref(empty), None, None, 0,
+                             None) == -1                        # required outputs missing
 
 
 @pytest.mark.parametrize("name,count,bs", [("proteins", 150, 64), ("collab", 70, 32), ("mutag", 120, 50)])

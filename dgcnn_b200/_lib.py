@@ -32,7 +32,7 @@ class DgcnnDataset(ctypes.Structure):
                 ("gptr", c_void_p), ("rowptr", c_void_p), ("col", c_void_p),
                 ("rowptr_t", c_void_p), ("col_t", c_void_p), ("dis", c_void_p),
                 ("bitmap", c_void_p), ("bitmap_t", c_void_p), ("bmoff", c_void_p), ("gflags", c_void_p),
-                ("gflags_t", c_void_p), ("fragmap", c_void_p), ("fgoff", c_void_p)]
+                ("gflags_t", c_void_p), ("fragmap", c_void_p), ("fgoff", c_void_p), ("gext", c_void_p)]
 
 
 class DgcnnBatchGraph(ctypes.Structure):
@@ -53,6 +53,7 @@ _STEP_TAIL = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float
 # name -> (restype, argtypes); mirrors include/dgcnn_b200.h one to one
 SIGNATURES = {
     "dgcnn_collate_workspace_bytes": (c_size_t, [c_int64]),
+    "dgcnn_dataset_prepare": (c_int32, [_DATASET_P, c_void_p, c_void_p, c_void_p]),
     "dgcnn_collate": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, _BATCH_P, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
     "dgcnn_train_step_resident_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32,

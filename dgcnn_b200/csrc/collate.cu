@@ -122,19 +122,16 @@ __device__ __forceinline__ void scan2(unsigned long long v0, unsigned long long 
     __syncthreads();
 }
 
-// sizes of batch graph b from the data-set arrays; false when the id is outside the data set
-// or the two CSRs disagree about the graph's edge span (edges never leave their graph)
+// extent of batch graph b: ids[b] -> the data set's {first node, nodes, first edge, edges}
+// record (dgcnn_dataset_prepare wrote and validated it): two dependent loads per graph.
+// false when the id is outside the data set.
 __device__ __forceinline__ bool graph_extent(const CollateArgs& a, int b, int* n, int* e, int* first_node,
                                              int* first_edge) {
     const int64_t g = a.ids[b];
     *n = 0; *e = 0; *first_node = 0; *first_edge = 0;
     if (g < 0 || g >= a.ds.num_graphs) return false;
-    const int n0 = a.ds.gptr[g], n1 = a.ds.gptr[g + 1];
-    const int e0 = a.ds.rowptr[n0], e1 = a.ds.rowptr[n1];
-    if (n1 < n0 || e1 < e0) return false;
-    *first_node = n0; *first_edge = e0;
-    *n = n1 - n0; *e = e1 - e0;
-    if (a.generic && (a.ds.rowptr_t[n0] != e0 || a.ds.rowptr_t[n1] != e1)) return false;
+    const int4 x = reinterpret_cast<const int4*>(a.ds.gext)[g];
+    *first_node = x.x; *n = x.y; *first_edge = x.z; *e = x.w;
     return true;
 }
 
@@ -200,6 +197,9 @@ __device__ __forceinline__ int owner_of(const int32_t* table, int count, int v) 
     return lo;
 }
 
+// kFused: the CTA derives the tables itself, in shared memory (the compiler then knows the
+// address space of every table read); otherwise n1_plan left them in the workspace.
+template <bool kFused>
 __global__ void __launch_bounds__(kGatherThreads, 4)
 n1_gather(const CollateArgs a) {
     extern __shared__ __align__(16) int32_t smem_tables[];
@@ -207,12 +207,12 @@ n1_gather(const CollateArgs a) {
     const int B = a.num_graphs, N = a.num_nodes, E = a.num_edges;
     Tables t;
     bool ok;
-    if (a.ws_tables) {                                // large batch: n1_plan ran first
-        t = carve_tables(a.ws_tables, B);
-        ok = *a.ws_ok != 0;
-    } else {
+    if (kFused) {
         t = carve_tables(smem_tables, B);
         ok = build_tables(a, t, red);
+    } else {                                          // large batch: n1_plan ran first
+        t = carve_tables(a.ws_tables, B);
+        ok = *a.ws_ok != 0;
     }
     const dgcnn_dataset& ds = a.ds;
     const dgcnn_batch_graph& o = a.out;
@@ -225,7 +225,6 @@ n1_gather(const CollateArgs a) {
     const bool maps = a.want_maps != 0;
     const int64_t stride = (int64_t)gridDim.x * kGatherThreads;
     const int64_t tid = (int64_t)blockIdx.x * kGatherThreads + threadIdx.x;
-    bool bad = false;
 
     // ---- per-graph outputs, spread over the first threads of the grid -------------------
     for (int64_t b = tid; b <= B; b += stride) {
@@ -279,9 +278,8 @@ n1_gather(const CollateArgs a) {
     const bool two_rp = o.rowptr_t != nullptr && o.rowptr_t != o.rowptr;
     const int32_t* col_t_src = a.generic ? ds.col_t : ds.col;
     const int32_t* rowptr_t_src = a.generic ? ds.rowptr_t : ds.rowptr;
-    const bool vec = ((reinterpret_cast<uintptr_t>(o.col) | (two ? reinterpret_cast<uintptr_t>(o.col_t) : 0)) & 15) == 0;
     const int F = ds.num_features;
-    const int64_t n_quads = ((int64_t)E + kEdgesPerItem - 1) / kEdgesPerItem;
+    const int64_t n_quads = ((int64_t)E + 32 * kEdgesPerItem - 1) / (32 * kEdgesPerItem) * 32;   // whole warps
     const int64_t n_nodes = (int64_t)N + 1;
     const int64_t n_feat = o.x ? (int64_t)N * F : 0;
     const int64_t n_bm = maps ? (t.bmoff[B] >> 2) : 0;                 // word counts are multiples of 16
@@ -290,43 +288,39 @@ n1_gather(const CollateArgs a) {
     const int64_t c1 = n_quads, c2 = c1 + n_nodes, c3 = c2 + n_feat, c4 = c3 + n_bm, c5 = c4 + n_bmt,
                   c6 = c5 + n_fg;
     for (int64_t u = tid; u < c6; u += stride) {
-        if (u < c1) {                                 // eight consecutive batch edges: eight loads in flight,
-            const int j0 = (int)(u << 3);             // two 16-byte stores per array
-            int b = owner_of(t.eoff, B, j0);
-            int32_t v[kEdgesPerItem], vt[kEdgesPerItem];
+        if (u < c1) {
+            // The 32 lanes of a warp own 256 consecutive batch edges, lane l the edges jb + 32 r:
+            // every load / store instruction of the warp is one coalesced 128-byte access.  First
+            // the (branchy) source addresses, then eight independent loads in flight, then the
+            // stores.  A graph change inside a lane's run is rare (graphs own thousands of edges).
+            const int jb = (int)(u >> 5) * (32 * kEdgesPerItem) + (int)(u & 31);
+            int b = owner_of(t.eoff, B, min(jb, E - 1));
+            int next_e = t.eoff[b + 1], delta = t.se0[b] - t.eoff[b], add = t.gptr[b] - t.sn0[b];
+            int src[kEdgesPerItem], ad[kEdgesPerItem];
 #pragma unroll
             for (int r = 0; r < kEdgesPerItem; ++r) {
-                const int j = j0 + r;
-                v[r] = 0; vt[r] = 0;
+                const int j = jb + 32 * r;
+                src[r] = -1; ad[r] = 0;
                 if (j < E) {
-                    while (b + 1 < B && j >= t.eoff[b + 1]) ++b;
-                    const int first = t.gptr[b], nodes = t.gptr[b + 1] - first;
-                    const int from = t.se0[b] + (j - t.eoff[b]);
-                    const int base = t.sn0[b];
-                    const int c = ds.col[from] - base;
-                    bad |= (unsigned)c >= (unsigned)nodes;
-                    v[r] = c + first;
-                    if (two) {
-                        const int ct = col_t_src[from] - base;
-                        bad |= (unsigned)ct >= (unsigned)nodes;
-                        vt[r] = ct + first;
+                    while (j >= next_e && b + 1 < B) {
+                        ++b;
+                        next_e = t.eoff[b + 1]; delta = t.se0[b] - t.eoff[b]; add = t.gptr[b] - t.sn0[b];
                     }
+                    src[r] = j + delta; ad[r] = add;
                 }
             }
-            if (vec && j0 + kEdgesPerItem <= E) {
+            int c[kEdgesPerItem];
 #pragma unroll
-                for (int r = 0; r < kEdgesPerItem; r += 4) {
-                    *reinterpret_cast<int4*>(o.col + j0 + r) = make_int4(v[r], v[r + 1], v[r + 2], v[r + 3]);
-                    if (two)
-                        *reinterpret_cast<int4*>(o.col_t + j0 + r) = make_int4(vt[r], vt[r + 1], vt[r + 2], vt[r + 3]);
-                }
-            } else {
+            for (int r = 0; r < kEdgesPerItem; ++r) c[r] = src[r] >= 0 ? ds.col[src[r]] : 0;
+#pragma unroll
+            for (int r = 0; r < kEdgesPerItem; ++r)
+                if (src[r] >= 0) o.col[jb + 32 * r] = c[r] + ad[r];
+            if (two) {
+#pragma unroll
+                for (int r = 0; r < kEdgesPerItem; ++r) c[r] = src[r] >= 0 ? col_t_src[src[r]] : 0;
 #pragma unroll
                 for (int r = 0; r < kEdgesPerItem; ++r)
-                    if (j0 + r < E) {
-                        o.col[j0 + r] = v[r];
-                        if (two) o.col_t[j0 + r] = vt[r];
-                    }
+                    if (src[r] >= 0) o.col_t[jb + 32 * r] = c[r] + ad[r];
             }
         } else if (u < c2) {                          // row pointers, dis, graph id; i == N closes the last row
             const int i = (int)(u - c1);
@@ -364,7 +358,53 @@ n1_gather(const CollateArgs a) {
             *reinterpret_cast<int4*>(o.fragmap + w) = *reinterpret_cast<const int4*>(ds.fragmap + from);
         }
     }
-    if (bad && a.status) atomicOr(a.status, DGCNN_GRAPH_BAD_EDGE);
+}
+
+// Set-up pass over the whole data set (once): validates what dgcnn_collate then trusts --
+// graph offsets, both CSRs agreeing on every graph's edge span, no edge leaving its graph --
+// and writes the per-graph extent records {first node, nodes, first edge, edges}.
+__global__ void __launch_bounds__(256)
+n1_prepare(const dgcnn_dataset ds, int4* __restrict__ gext, int32_t* status) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t G = ds.num_graphs, Nd = ds.num_nodes;
+    const bool generic = !ds.symmetric;
+    int bad = 0;
+    if (tid == 0 && (ds.gptr[0] != 0 || ds.gptr[G] != Nd || ds.rowptr[0] != 0 || ds.rowptr[Nd] != ds.num_edges))
+        bad |= DGCNN_GRAPH_BAD_BATCH;
+    for (int64_t g = tid; g < G; g += stride) {
+        const int n0 = ds.gptr[g], n1 = ds.gptr[g + 1];
+        int4 x = make_int4(0, 0, 0, 0);
+        if (n0 < 0 || n1 < n0 || n1 > Nd) {
+            bad |= DGCNN_GRAPH_BAD_BATCH;
+        } else {
+            const int e0 = ds.rowptr[n0], e1 = ds.rowptr[n1];
+            if (e0 < 0 || e1 < e0 || e1 > ds.num_edges) bad |= DGCNN_GRAPH_BAD_EDGE;
+            else if (generic && (ds.rowptr_t[n0] != e0 || ds.rowptr_t[n1] != e1)) bad |= DGCNN_GRAPH_BAD_EDGE;
+            else x = make_int4(n0, n1 - n0, e0, e1 - e0);
+        }
+        gext[g] = x;
+    }
+    for (int64_t i = tid; i < Nd; i += stride) {        // one thread per row: set-up code, rows are short
+        int lo = 0, hi = (int)G;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (ds.gptr[mid] <= i) lo = mid; else hi = mid;
+        }
+        const int first = ds.gptr[lo], last = ds.gptr[lo + 1];
+        if (i < first || i >= last) { bad |= DGCNN_GRAPH_BAD_BATCH; continue; }
+        for (int pass = 0; pass < (generic ? 2 : 1); ++pass) {
+            const int32_t* rp = pass ? ds.rowptr_t : ds.rowptr;
+            const int32_t* cl = pass ? ds.col_t : ds.col;
+            const int beg = rp[i], end = rp[i + 1];
+            if (beg < 0 || end < beg || end > ds.num_edges) { bad |= DGCNN_GRAPH_BAD_EDGE; continue; }
+            for (int e = beg; e < end; ++e) {
+                const int c = cl[e];
+                if (c < first || c >= last) bad |= DGCNN_GRAPH_BAD_EDGE;
+            }
+        }
+    }
+    if (bad && status) atomicOr(status, bad);
 }
 
 }  // namespace dgcnn
@@ -381,7 +421,8 @@ extern "C" int dgcnn_collate(const dgcnn_dataset* ds, const int32_t* ids, int64_
                              int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     const int64_t B = num_graphs, N = num_nodes, E = num_edges;
     if (!ds || !ids || !out || B < 1 || N < 0 || E < 0) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (!ds->gptr || !ds->rowptr || !ds->dis || ds->num_graphs < 1 || ds->num_features < 1)
+    if (!ds->gptr || !ds->rowptr || !ds->dis || !ds->gext || ((uintptr_t)ds->gext & 15) || ds->num_graphs < 1 ||
+        ds->num_features < 1)
         return DGCNN_ERR_INVALID_ARGUMENT;
     if (ds->num_edges > 0 && !ds->col) return DGCNN_ERR_INVALID_ARGUMENT;
     const bool generic = !ds->symmetric;
@@ -431,9 +472,28 @@ extern "C" int dgcnn_collate(const dgcnn_dataset* ds, const int32_t* ids, int64_
     // upper bound of the unified index space (map words: at most (N + 15 B) * 32 / 4 quads each);
     // ONE wave of CTAs (4 per SM at <= 64 registers): every CTA of the fused launch derives the
     // tables first, a second wave would pay for that again
-    const int64_t work = (E + kEdgesPerItem - 1) / kEdgesPerItem + N + 1 +
+    const int64_t work = (E + kEdgesPerItem - 1) / kEdgesPerItem + 32 + N + 1 +
                          (out->x ? N * ds->num_features : 0) + (maps ? (N + 16 * B) : 0);
-    n1_gather<<<grid_for(work, kGatherThreads, 4), kGatherThreads, smem, st>>>(a);
+    const int grid = grid_for(work, kGatherThreads, 4);
+    if (B > kFusedGraphs)
+        n1_gather<false><<<grid, kGatherThreads, 0, st>>>(a);
+    else
+        n1_gather<true><<<grid, kGatherThreads, smem, st>>>(a);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
+extern "C" int dgcnn_dataset_prepare(const dgcnn_dataset* ds, int32_t* gext, int32_t* status, void* stream) {
+    if (!ds || !gext || ((uintptr_t)gext & 15)) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!ds->gptr || !ds->rowptr || ds->num_graphs < 1 || ds->num_nodes < 0 || ds->num_edges < 0)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (ds->num_edges > 0 && !ds->col) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!ds->symmetric && (!ds->rowptr_t || (ds->num_edges > 0 && !ds->col_t))) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (ds->num_nodes >= INT32_MAX || ds->num_edges >= INT32_MAX || ds->num_graphs >= INT32_MAX)
+        return DGCNN_ERR_UNSUPPORTED;
+    const int64_t work = ds->num_nodes > ds->num_graphs ? ds->num_nodes : ds->num_graphs;
+    n1_prepare<<<grid_for(work, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        *ds, reinterpret_cast<int4*>(gext), status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

@@ -263,7 +263,19 @@ class DeviceDataset:
             None if m is None or self.symmetric else m.bitmap_t.data_ptr(),
             None if m is None else m.bmoff.data_ptr(), None if m is None else m.gflags.data_ptr(),
             None if m is None or self.symmetric else m.gflags_t.data_ptr(),
-            None if m is None else m.fragmap.data_ptr(), None if m is None else m.fgoff.data_ptr())
+            None if m is None else m.fragmap.data_ptr(), None if m is None else m.fgoff.data_ptr(), None)
+        # one validating pass (offsets closed, CSRs consistent, no edge leaves its graph) that also
+        # writes the per-graph extent records the gather starts from
+        self.gext = torch.empty(self.num_graphs, 4, dtype=torch.int32, device=dev)
+        check = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load_library().dgcnn_dataset_prepare(self.c_struct, self.gext.data_ptr(), check.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "dataset_prepare")
+        if int(check.item()) != 0:
+            raise ValueError(f"DeviceDataset: inconsistent data set (status {int(check.item())}): an edge "
+                             "leaves its graph or the offsets are not monotone")
+        self._struct.gext = self.gext.data_ptr()
 
     def __len__(self) -> int:
         return self.num_graphs
@@ -273,7 +285,7 @@ class DeviceDataset:
         return ctypes.byref(self._struct)
 
     def nbytes(self) -> int:
-        ts = [self.x, self.y, self.gptr, self.rowptr, self.col, self.dis, self.rowptr_t, self.col_t]
+        ts = [self.x, self.y, self.gptr, self.rowptr, self.col, self.dis, self.rowptr_t, self.col_t, self.gext]
         if self.maps is not None:
             m = self.maps
             ts += [m.bitmap, m.bitmap_t, m.bmoff, m.gflags, m.gflags_t, m.fragmap, m.fgoff]

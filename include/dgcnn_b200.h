@@ -405,7 +405,7 @@ int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_index, int32_
  *                     the gathered CSR instead); bitmap_t, gflags_t [G] for a data set that is
  *                     not symmetric.  K0b's per-graph blocks are relative to the graph's first
  *                     node, so they can be copied as they are.
- * Edges must not cross graphs (true of any PyG data set; the Python side checks it once).
+ * Edges must not cross graphs (true of any PyG data set; dgcnn_dataset_prepare checks it once).
  * The struct itself lives in HOST memory (its members are device pointers) and is only read
  * during the call.
  * ------------------------------------------------------------------------ */
@@ -429,7 +429,15 @@ typedef struct dgcnn_dataset {
     const int32_t* gflags_t;
     const uint32_t* fragmap;
     const int32_t* fgoff;
+    const int32_t* gext;                        /* [G][4], 16-byte aligned: dgcnn_dataset_prepare */
 } dgcnn_dataset;
+
+/* Set-up, once per data set (one launch): validates everything dgcnn_collate then trusts --
+ * gptr / rowptr monotone and closed, both CSRs agreeing on every graph's edge span, no edge
+ * leaving its graph (status |= DGCNN_GRAPH_BAD_BATCH / DGCNN_GRAPH_BAD_EDGE otherwise) -- and
+ * writes gext [G][4] = {first node, nodes, first edge, edges} per graph, which the caller then
+ * stores in dataset->gext (the field is not read by this call). */
+int dgcnn_dataset_prepare(const dgcnn_dataset* dataset, int32_t* gext, int32_t* status, void* stream);
 
 /* Where a gathered batch goes (HOST struct of device pointers, caller-owned buffers): exactly the
  * outputs of dgcnn_build_graph(_i32) and dgcnn_build_bitmaps on the host-collated batch of the
@@ -469,8 +477,8 @@ typedef struct dgcnn_batch_graph {
  * allowed).  `status` is OR-ed with DGCNN_GRAPH_GENERIC when the data set is not symmetric
  * (what K0 would report), DGCNN_GRAPH_BAD_BATCH when an id is outside [0, G) or num_nodes /
  * num_edges (host arithmetic on the per-graph sizes, which size the outputs) disagree with
- * the ids -- then nothing is written --, DGCNN_GRAPH_BAD_EDGE when an edge leaves its graph.
- * One launch for B <= 1024 (two beyond); B, N, E < 2^31. */
+ * the ids -- then nothing is written.  The data set itself is trusted: check the status of
+ * dgcnn_dataset_prepare once.  One launch for B <= 1024 (two beyond); B, N, E < 2^31. */
 size_t dgcnn_collate_workspace_bytes(int64_t num_graphs);
 int dgcnn_collate(const dgcnn_dataset* dataset, const int32_t* ids, int64_t num_graphs,
                   int64_t num_nodes, int64_t num_edges, const dgcnn_batch_graph* out,

@@ -12,6 +12,8 @@ single gradient all-reduce when N > 1, Adam.  Prints ONE JSON line on rank 0.
 `value`      graphs/s with the batch (x, edge_index, batch) already resident in HBM
 `e2e`        the same step through the public API from pinned HOST buffers, the H2D
              copy and the D2H loss read inside the timed region
+`e2e_resident_dataset`   the same step fed from a data set resident in HBM: per
+             step only the graph ids cross PCIe; reported next to `e2e`, never instead of it
 `roofline`   the dominant kernel, timed alone with CUDA events, against MEASURED_PEAKS
 `cpu_baseline` / `--impl reference`   the CPU oracle restatement of the reference's
              path (PyG itself is not installable here), timed on this host's cores

@@ -299,6 +299,12 @@ class DeviceDataset:
         nn = self.nodes[ids]
         return int(nn.sum()), int(self.edges[ids].sum()), int(nn.max())
 
+    def shard(self, ids, world_size: int, rank: int) -> np.ndarray:
+        """This rank's slice of the batch ``ids`` (SURVEY.md 8e: graph-sharded data parallelism;
+        every rank holds the whole data set, the split is balanced by nodes + edges)."""
+        from .dp import shard_ids
+        return shard_ids(np.asarray(ids, dtype=np.int64), self.nodes, self.edges, world_size, rank)
+
     def ids_to_device(self, ids) -> torch.Tensor:
         t = ids if isinstance(ids, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32))
         return t.to(dtype=torch.int32).to(self.device, non_blocking=True)

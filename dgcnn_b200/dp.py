@@ -14,7 +14,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "GradBucket", "PeerExchange"]
+__all__ = ["shard_bounds", "shard_ids", "GradBucket", "PeerExchange"]
 
 
 def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
@@ -36,6 +36,17 @@ def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int
         bounds.append((lo, hi))
         lo = hi
     return bounds
+
+
+def shard_ids(ids: Sequence[int], nodes: Sequence[int], edges: Sequence[int], world_size: int,
+              rank: int):
+    """The slice of a batch's graph ids that ``rank`` trains on when the data set is resident in
+    HBM on every rank (``DeviceDataset``): contiguous in batch order, balanced by
+    nodes + edges of the graphs (``nodes`` / ``edges``: per-graph sizes of the DATA SET, indexed
+    by id).  Every rank computes the same split from the same ids: no communication."""
+    costs = [float(nodes[int(i)]) + float(edges[int(i)]) for i in ids]
+    lo, hi = shard_bounds(costs, world_size)[rank]
+    return ids[lo:hi]
 
 
 class GradBucket:

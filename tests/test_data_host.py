@@ -179,3 +179,19 @@ def test_device_dataset_refuses_cpu():
     graphs = make_graphs(CONFIGS["mutag"], 3, seed=0)
     with pytest.raises(RuntimeError, match="CUDA"):
         dd.DeviceDataset(graphs, "cpu")
+
+
+def test_shard_ids_splits_a_batch_of_graph_ids_across_ranks():
+    """SURVEY 8e on the resident path: contiguous slices in batch order, disjoint, covering,
+    balanced by nodes + edges; identical on every rank without communication."""
+    from dgcnn_b200 import shard_ids
+    rng = np.random.RandomState(0)
+    nodes = rng.randint(5, 500, size=300)
+    edges = nodes * rng.randint(2, 60, size=300)
+    ids = rng.permutation(300)[:128]
+    for world in (1, 2, 4, 8):
+        parts = [shard_ids(ids, nodes, edges, world, r) for r in range(world)]
+        assert np.concatenate(parts).tolist() == ids.tolist()
+        cost = [float((nodes[p] + edges[p]).sum()) for p in parts]
+        assert max(cost) <= sum(cost) / world + float((nodes[ids] + edges[ids]).max())
+    assert shard_ids(ids[:1], nodes, edges, 2, 1).tolist() == ids[:1].tolist()   # the last rank takes the rest

@@ -184,7 +184,8 @@ class FusedTrainer:
             raise RuntimeError("FusedTrainer.step_resident: the batch holds graphs too large for the fused "
                                "kernels (dgcnn_stack_fwd_supported); feed it through step()")
         _lib.check(rc, "train_step_resident")
-        ops.LAUNCHES["train_step_resident"] = ops.LAUNCHES.get("train_step_resident", 0) + 28
+        # n1_gather + KS + 5 tail fwd + NLL + 12 tail bwd + 2 KSB + 2 Adam (profiles/r01_launches_resident_step.md)
+        ops.LAUNCHES["train_step_resident"] = ops.LAUNCHES.get("train_step_resident", 0) + (23 if b <= 1024 else 24)
         return self.stats
 
     def _native_step(self, data, global_batch, world) -> bool:

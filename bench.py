@@ -562,6 +562,20 @@ def main():
             resident_run(e2e_steps)
             torch.cuda.synchronize()
             res_s = time.perf_counter() - t0
+            # the product's own loop (dgcnn_b200.driver.train_epoch = train.py:27-47): shuffled ids,
+            # one library call per step, loss / accuracy accumulated on the device and read ONCE
+            # per epoch (the reference syncs twice per batch, train.py:44-45)
+            from dgcnn_b200 import driver as drv
+            all_ids = np.arange(len(ds), dtype=np.int64)
+            gen = torch.Generator().manual_seed(324)
+            drv.train_epoch(trainer, ds, all_ids, bs, gen)
+            torch.cuda.synchronize()
+            epochs = max(3, e2e_steps // RING)
+            t0 = time.perf_counter()
+            for _ in range(epochs):
+                ep_loss, ep_acc = drv.train_epoch(trainer, ds, all_ids, bs, gen)
+            torch.cuda.synchronize()
+            epoch_s = time.perf_counter() - t0
             # device time of the gather (+ K0b, like graph_build_us) and of one whole resident step
             ids0 = id_pinned[0].to(dev)
             with torch.no_grad():
@@ -571,6 +585,10 @@ def main():
             gather_bytes = 8 * e + 4 * (n + 1) * 2 + 8 * n + 8 * n * cfg.num_features   # read + write
             resident = {"value": global_batch * e2e_steps / res_s, "unit": UNIT,
                         "h2d_bytes_per_step": 4 * bs, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                        "driver_epoch_value": len(ds) * epochs / epoch_s, "driver_epochs": epochs,
+                        "driver_epoch_note": "dgcnn_b200.driver.train_epoch over the resident data set "
+                                             f"({len(ds)} graphs, {len(ds) // bs} steps per epoch, shuffled): "
+                                             "one host sync per epoch",
                         "device_step_us": t_res_step * 1e6,
                         "device_value": global_batch / t_res_step,
                         "collate_us": t_collate * 1e6, "collate_plus_bitmaps_us": t_gather * 1e6,

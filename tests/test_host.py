@@ -171,3 +171,78 @@ def test_shard_bounds_balance_and_cover():
     assert max(loads) <= 0.6 * sum(costs)
     eq = dg.shard_bounds([1.0] * 512, 8)
     assert [hi - lo for lo, hi in eq] == [64] * 8
+
+
+def header_prototypes():
+    """name -> number of parameters, parsed from the header's declarations."""
+    text = open(os.path.join(ROOT, "include", "dgcnn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for name, args in re.findall(r"\b(dgcnn_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        args = args.strip()
+        protos[name] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_ctypes_table_has_the_headers_arity():
+    protos = header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == protos[name], f"{name}: header has {protos[name]} parameters, ctypes {len(argtypes)}"
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/dgcnn_b200.h compiles as C (gcc, no CUDA, no C++), and the two structs that cross
+    the boundary have the layout the ctypes mirrors assume."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc unavailable")
+    fields = {"dgcnn_dataset": [f for f, _ in _lib.DgcnnDataset._fields_],
+              "dgcnn_batch_graph": [f for f, _ in _lib.DgcnnBatchGraph._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dgcnn_b200.h"', "int main(void) {"]
+    for struct, names in fields.items():
+        lines.append(f'  printf("{struct} %zu\\n", sizeof({struct}));')
+        for f in names:
+            lines.append(f'  printf("{struct}.{f} %zu\\n", offsetof({struct}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True)
+               .stdout.strip().splitlines())
+    for struct, cls in (("dgcnn_dataset", _lib.DgcnnDataset), ("dgcnn_batch_graph", _lib.DgcnnBatchGraph)):
+        assert int(out[struct]) == ctypes.sizeof(cls)
+        for f, _ in cls._fields_:
+            assert int(out[f"{struct}.{f}"]) == getattr(cls, f).offset, f"{struct}.{f}"
+
+
+def test_resident_entry_points_validate_before_touching_cuda():
+    lib = _lib.load_library()
+    INVALID, WORKSPACE = -1, -3
+    ds, out = _lib.DgcnnDataset(), _lib.DgcnnBatchGraph()
+    assert lib.dgcnn_collate(None, None, 1, 1, 0, None, None, None, 0, None) == INVALID
+    assert lib.dgcnn_collate(ctypes.byref(ds), 8, 1, 1, 0, ctypes.byref(out), None, None, 0, None) == INVALID
+    assert lib.dgcnn_dataset_prepare(None, None, None, None) == INVALID
+    assert lib.dgcnn_dataset_prepare(ctypes.byref(ds), 16, None, None) == INVALID      # empty data set
+    assert lib.dgcnn_dataset_prepare(ctypes.byref(ds), 12, None, None) == INVALID      # gext not 16-byte aligned
+    # a structurally complete data set / batch with a missing workspace: the size check comes last
+    for f in ("x", "y", "gptr", "rowptr", "col", "dis", "gext"):
+        setattr(ds, f, 256)
+    ds.num_graphs, ds.num_nodes, ds.num_edges, ds.num_features, ds.symmetric, ds.ldx = 4, 40, 100, 3, 1, 3
+    for f in ("rowptr", "col", "dis", "gptr"):
+        setattr(out, f, 256)
+    assert lib.dgcnn_collate(ctypes.byref(ds), 256, 2, 20, 50, ctypes.byref(out), None, None, 0, None) == WORKSPACE
+    out.bitmap = 256                                                                   # maps come as a set
+    assert lib.dgcnn_collate(ctypes.byref(ds), 256, 2, 20, 50, ctypes.byref(out), None, 256, 1 << 20, None) == INVALID
+    # workspace queries: pure host arithmetic, monotone, resident >= the batch buffers it adds
+    assert lib.dgcnn_collate_workspace_bytes(512) >= 6 * 512 * 4
+    assert lib.dgcnn_collate_workspace_bytes(4096) > lib.dgcnn_collate_workspace_bytes(512)
+    a = lib.dgcnn_train_step_workspace_bytes(38898, 2359942, 512, 1, 130, 3, 492)
+    b = lib.dgcnn_train_step_resident_workspace_bytes(38898, 2359942, 512, 1, 130, 3, 492)
+    assert a > 0 and b > 0 and lib.dgcnn_train_step_resident_workspace_bytes(0, 0, 0, 1, 130, 3, 1) == 0
+    assert lib.dgcnn_train_step_resident(None, None, 1, 0, 1, 30, 2, 1, 0, None, None, None, None, None,
+                                         1e-3, 0.9, 0.999, 1e-8, 1, 0, 0, None, None, 1, 0, None, None, None,
+                                         None, 0, None) == INVALID

@@ -165,6 +165,44 @@ def sort_aggregation(x: Tensor, batch: Tensor, k: int, batch_size: Optional[int]
 
 
 # ----------------------------------------------------------------------------
+# train.py:108-109 -> DataLoader -> Batch.from_data_list (PyG data/batch.py + collate.py)
+# ----------------------------------------------------------------------------
+def from_data_list(graphs):
+    """What PyG's collate does for the attributes model.py:27 / train.py:36 read: ``x`` and
+    ``y`` concatenated along dim 0, ``edge_index`` concatenated along dim 1 with every graph's
+    ids incremented by the number of nodes before it (``__inc__`` = num_nodes), ``batch`` =
+    graph id repeated per node, ``ptr`` = cumulative node counts.  ``graphs``: sequence of
+    (x [n,F], edge_index [2,e] local ids, y) -> (x, edge_index, batch, ptr, y)."""
+    xs, eis, ys, batch, ptr = [], [], [], [], [0]
+    for g, (x, ei, y) in enumerate(graphs):
+        x, ei = torch.as_tensor(x), torch.as_tensor(ei, dtype=torch.long)
+        xs.append(x)
+        eis.append(ei + ptr[-1])
+        ys.append(int(y))
+        batch.append(torch.full((x.size(0),), g, dtype=torch.long))
+        ptr.append(ptr[-1] + x.size(0))
+    return (torch.cat(xs, 0), torch.cat(eis, 1), torch.cat(batch), torch.tensor(ptr, dtype=torch.long),
+            torch.tensor(ys, dtype=torch.long))
+
+
+def batch_csr(edge_index: Tensor, num_nodes: int):
+    """The graph structure every kernel consumes, from the reference's edge list: self loops
+    dropped (model.py:28), CSR by target with ascending sources, CSR by source with ascending
+    targets, dis = (1 + in-degree)^-1/2 (gcn_norm with the appended self loop), multi-edges kept."""
+    src, dst = edge_index[0], edge_index[1]
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    by_t = torch.argsort(dst * num_nodes + src, stable=True)
+    by_s = torch.argsort(src * num_nodes + dst, stable=True)
+    indeg = torch.bincount(dst, minlength=num_nodes)
+    outdeg = torch.bincount(src, minlength=num_nodes)
+    rowptr = torch.cat([indeg.new_zeros(1), indeg.cumsum(0)])
+    rowptr_t = torch.cat([outdeg.new_zeros(1), outdeg.cumsum(0)])
+    dis = (indeg + 1).to(torch.float32).pow(-0.5)
+    return rowptr, src[by_t], rowptr_t, dst[by_s], dis
+
+
+# ----------------------------------------------------------------------------
 # utils.py:18-33  Indegree (norm=True, max_value=None, cat=True)
 # ----------------------------------------------------------------------------
 def indegree_feature(edge_index: Tensor, num_nodes: int, x: Optional[Tensor]) -> Tensor:

@@ -90,7 +90,41 @@ def sortpool_cases():
     print("sortpool_cases", out.shape, perm.tolist())
 
 
+def collate_case():
+    """A data set of six hand-sized graphs (path, triangle with a duplicated edge and a self
+    loop, an EMPTY graph, a single node, a directed 3-cycle, a star) and a batch of ids with a
+    repeat: the batch a resident data set must gather (tests/test_gpu_resident.py), as the
+    oracle's Batch.from_data_list + CSR restatement build it."""
+    def und(pairs):
+        return np.array([[a for a, b in pairs] + [b for a, b in pairs],
+                         [b for a, b in pairs] + [a for a, b in pairs]], dtype=np.int64)
+    eis = [und([(0, 1), (1, 2)]),
+           np.concatenate([und([(0, 1), (1, 2), (0, 2)]), np.array([[0, 2], [1, 2]])], axis=1),
+           np.zeros((2, 0), np.int64),
+           np.zeros((2, 0), np.int64),
+           np.array([[0, 1, 2], [1, 2, 0]], dtype=np.int64),
+           und([(0, 1), (0, 2), (0, 3), (0, 4)])]
+    sizes = [3, 4, 0, 1, 3, 5]
+    rng = np.random.RandomState(3)
+    xs = [rng.standard_normal((n, 2)).astype(np.float32) for n in sizes]
+    ys = [0, 1, 1, 0, 1, 0]
+    ids = np.array([5, 1, 2, 4, 1, 3, 0], dtype=np.int64)
+    x, ei, batch, ptr, y = orc.from_data_list([(xs[i], eis[i], ys[i]) for i in ids])
+    rowptr, col, rowptr_t, col_t, dis = orc.batch_csr(ei, int(ptr[-1]))
+    n_b = [sizes[i] for i in ids]
+    gorder = sorted(range(len(ids)), key=lambda q: (-n_b[q], q))
+    out = {"ids": ids, "sizes": np.array(sizes), "ys": np.array(ys), "x": x.numpy(),
+           "edge_index": ei.numpy(), "batch": batch.numpy(), "ptr": ptr.numpy(), "y": y.numpy(),
+           "rowptr": rowptr.numpy(), "col": col.numpy(), "rowptr_t": rowptr_t.numpy(), "col_t": col_t.numpy(),
+           "dis": dis.numpy(), "gorder": np.array(gorder)}
+    for i in range(len(sizes)):
+        out[f"g{i}_x"], out[f"g{i}_edge_index"] = xs[i], eis[i]
+    np.savez_compressed(os.path.join(HERE, "collate_case.npz"), **out)
+    print("collate_case", {k_: v.shape for k_, v in out.items() if not k_.startswith("g")})
+
+
 if __name__ == "__main__":
+    collate_case()
     x, ei, b, nb = hand_fixture()
     stack_case("hand_sym", x, ei, b, nb, k=3, seed=11, norm=orc.NORM_SYM)
     stack_case("hand_rw", x, ei, b, nb, k=3, seed=11, norm=orc.NORM_RW)

@@ -195,3 +195,46 @@ def test_shard_ids_splits_a_batch_of_graph_ids_across_ranks():
         cost = [float((nodes[p] + edges[p]).sum()) for p in parts]
         assert max(cost) <= sum(cost) / world + float((nodes[ids] + edges[ids]).max())
     assert shard_ids(ids[:1], nodes, edges, 2, 1).tolist() == ids[:1].tolist()   # the last rank takes the rest
+
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def golden_collate_case():
+    z = np.load(os.path.join(GOLDEN, "collate_case.npz"))
+    graphs = [{"x": z[f"g{i}_x"], "edge_index": z[f"g{i}_edge_index"], "y": int(z["ys"][i])}
+              for i in range(len(z["sizes"]))]
+    return z, graphs
+
+
+def test_collate_golden_pins_the_oracle_and_the_host_loader():
+    """tests/golden/collate_case.npz: Batch.from_data_list (train.py:108-109) and the batch's
+    graph structure, restated in the oracle, against the committed vectors, against the
+    product's host loader (synth.collate) and against an independent numpy CSR; a few entries
+    by hand."""
+    z, graphs = golden_collate_case()
+    ids = z["ids"]
+    x, ei, batch, ptr, y = orc.from_data_list([(graphs[i]["x"], graphs[i]["edge_index"], graphs[i]["y"]) for i in ids])
+    for name, t in (("x", x), ("edge_index", ei), ("batch", batch), ("ptr", ptr), ("y", y)):
+        assert np.array_equal(t.numpy(), z[name]), name
+    assert ptr.tolist() == [0, 5, 9, 9, 12, 16, 17, 20] and y.tolist() == [0, 1, 1, 1, 1, 0, 0]
+    hb = collate([graphs[i] for i in ids])                       # the product's host loader
+    assert torch.equal(hb.x, x) and torch.equal(hb.edge_index, ei) and torch.equal(hb.batch, batch)
+    assert torch.equal(hb.ptr, ptr) and torch.equal(hb.y, y)
+    rowptr, col, rowptr_t, col_t, dis = orc.batch_csr(ei, 20)
+    for name, t in (("rowptr", rowptr), ("col", col), ("rowptr_t", rowptr_t), ("col_t", col_t), ("dis", dis)):
+        assert np.array_equal(t.numpy(), z[name]), name
+    # independent numpy restatement (lexsort), and hand-checked entries
+    src, dst = ei.numpy()
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    assert src.size == 29 == int(rowptr[-1])                     # 8 + 7 + 0 + 3 + 7 + 0 + 4, the self loops dropped
+    o = np.lexsort((src, dst))
+    assert np.array_equal(col.numpy(), src[o])
+    assert np.array_equal(rowptr.numpy(), np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=20))]))
+    ot = np.lexsort((dst, src))
+    assert np.array_equal(col_t.numpy(), dst[ot])
+    assert rowptr[:6].tolist() == [0, 4, 5, 6, 7, 8]             # the star: hub 0 has in-degree 4
+    assert np.allclose(dis[:5].numpy(), [5 ** -0.5] + [2 ** -0.5] * 4)
+    assert col[8:11].tolist() == [6, 7, 5]                       # triangle node 5: sources 6 (0->1), 7 (2->1); node 6: 5
+    assert z["gorder"].tolist() == [0, 1, 4, 3, 6, 5, 2]         # sizes 5,4,0,3,4,1,3: descending, ties by index

@@ -278,3 +278,30 @@ def test_reference_driver_two_folds_on_a_tu_format_stand_in(tmp_path):
     first = (tmp_path / "statistics" / "MUTAG_results_1.csv").read_text().strip().split("\n")[1].split(",")
     assert abs(float(first[1]) - loss_sum / batches) <= 1e-5 * max(1.0, abs(loss_sum / batches))
     assert abs(float(first[3]) - correct / len(train_idx) * 100.0) <= 1e-4
+
+
+def test_collate_against_the_committed_golden_vectors():
+    """tests/golden/collate_case.npz (generated from the oracle's Batch.from_data_list + CSR
+    restatement, pinned on the CPU by tests/test_data_host.py): six hand-sized graphs incl. an
+    empty one, a duplicated edge, a self loop and a directed cycle; a batch with a repeated id."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "collate_case.npz"))
+    graphs = [{"x": z[f"g{i}_x"], "edge_index": z[f"g{i}_edge_index"], "y": int(z["ys"][i])}
+              for i in range(len(z["sizes"]))]
+    ds = dg.DeviceDataset(graphs, DEV, num_classes=2)
+    assert not ds.symmetric and ds.num_edges == 4 + 7 + 3 + 8
+    rb = ds.batch(z["ids"])
+    g = rb._dgcnn_graph
+    e = int(z["rowptr"][-1])
+    np.testing.assert_array_equal(g.rowptr.cpu().numpy(), z["rowptr"])
+    np.testing.assert_array_equal(g.col.cpu().numpy()[:e], z["col"])
+    np.testing.assert_array_equal(g.rowptr_t.cpu().numpy(), z["rowptr_t"])
+    np.testing.assert_array_equal(g.col_t.cpu().numpy()[:e], z["col_t"])
+    np.testing.assert_allclose(g.dis.cpu().numpy(), z["dis"], rtol=5e-7, atol=0)   # 1/sqrtf vs torch pow(-0.5)
+    np.testing.assert_array_equal(g.gptr.cpu().numpy(), z["ptr"])
+    np.testing.assert_array_equal(g.gorder.cpu().numpy(), z["gorder"])
+    np.testing.assert_array_equal(rb.x.cpu().numpy(), z["x"])
+    np.testing.assert_array_equal(rb.batch.cpu().numpy(), z["batch"])
+    np.testing.assert_array_equal(rb.y.cpu().numpy(), z["y"])
+    st = int(g.status.item())
+    assert st & ops.GRAPH_GENERIC and not st & (ops.GRAPH_BAD_EDGE | ops.GRAPH_BAD_BATCH)

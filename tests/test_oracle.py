@@ -184,3 +184,117 @@ def test_oracle_model_forward_backward_runs():
     np.testing.assert_allclose(out.exp().sum(1).detach().numpy(), 1.0, atol=1e-5)
     torch.nn.functional.nll_loss(out, b.y).backward()
     assert all(p.grad is not None for p in m.parameters())
+
+
+# ----------------------------------------------------------------------------------------
+# property tests: hypothesis draws small block-diagonal multigraphs
+# ----------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@st.composite
+def graph_lists(draw, max_graphs=5, max_nodes=9, features=3):
+    """A list of small directed multigraphs (loops and duplicates allowed, empty graphs too),
+    tie-free float64 features."""
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    sizes = draw(st.lists(st.integers(0, max_nodes), min_size=1, max_size=max_graphs))
+    if sum(sizes) == 0:
+        sizes[0] = 1
+    rng = np.random.RandomState(seed)
+    graphs = []
+    for n in sizes:
+        m = int(rng.randint(0, 3 * n + 1)) if n else 0
+        ei = np.stack([rng.randint(0, max(n, 1), m), rng.randint(0, max(n, 1), m)]).astype(np.int64)
+        graphs.append((rng.standard_normal((n, features)), ei, int(rng.randint(0, 2))))
+    return graphs
+
+
+def oracle_weights(features, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    dims = [(features, 32), (32, 32), (32, 32), (32, 1)]
+    ws = [(torch.rand(co, ci, generator=g, dtype=torch.float64) * 2 - 1) * (6.0 / (ci + co)) ** 0.5 for ci, co in dims]
+    bs = [(torch.rand(co, generator=g, dtype=torch.float64) * 2 - 1) * 0.1 for _, co in dims]
+    return ws, bs
+
+
+@settings(max_examples=25, deadline=None)
+@given(graph_lists(), st.sampled_from([orc.NORM_SYM, orc.NORM_RW]))
+def test_property_stack_matches_dense_matmul_in_float64(graphs, norm):
+    """4 x tanh(N(A+I) X W^T + b) on the batched multigraph == the dense closed form."""
+    x, ei, batch, ptr, y = orc.from_data_list(graphs)
+    ws, bs = oracle_weights(x.size(1))
+    got = orc.graph_conv_stack(x, ei, ws, bs, norm).numpy()
+    h, outs = x.numpy(), []
+    for w, b in zip(ws, bs):
+        h = np.tanh(dense_gcn(h, ei.numpy(), w.numpy(), b.numpy(), norm))
+        outs.append(h)
+    np.testing.assert_allclose(got, np.concatenate(outs, 1), rtol=0, atol=1e-12)
+
+
+@settings(max_examples=25, deadline=None)
+@given(graph_lists(), st.integers(1, 12))
+def test_property_batch_of_one_equals_batched(graphs, k):
+    """Graphs never interact (model.py:30-35): the batched hot path == every graph on its own."""
+    x, ei, batch, ptr, y = orc.from_data_list(graphs)
+    ws, bs = oracle_weights(x.size(1))
+    xcat = orc.graph_conv_stack(x, ei, ws, bs)
+    pooled, perm = orc.sort_aggregation(xcat, batch, k, len(graphs), return_perm=True)
+    for g, (gx, gei, _) in enumerate(graphs):
+        lo, hi = int(ptr[g]), int(ptr[g + 1])
+        if hi == lo:
+            assert pooled[g].abs().sum() == 0 and (perm[g] == -1).all()      # empty graph: all padding
+            continue
+        own = orc.graph_conv_stack(torch.as_tensor(gx), torch.as_tensor(gei), ws, bs)
+        np.testing.assert_allclose(xcat[lo:hi].numpy(), own.numpy(), rtol=0, atol=1e-13)
+        own_pool, own_perm = orc.sort_aggregation(own, torch.zeros(hi - lo, dtype=torch.long), k, 1, return_perm=True)
+        np.testing.assert_allclose(pooled[g].numpy(), own_pool[0].numpy(), rtol=0, atol=1e-13)
+        assert torch.equal(torch.where(perm[g] >= 0, perm[g] - lo, perm[g]), own_perm[0])
+
+
+@settings(max_examples=25, deadline=None)
+@given(graph_lists(), st.integers(1, 12), st.integers(0, 2 ** 31 - 1))
+def test_property_relabelling_nodes_keeps_the_pooled_output(graphs, k, seed):
+    """Permutation equivariance: relabel the nodes of every graph => same pooled rows (keys are
+    tie-free with probability 1, so the tie rule does not enter), x_cat rows permuted."""
+    rng = np.random.RandomState(seed)
+    relabelled, perms = [], []
+    for gx, gei, gy in graphs:
+        p = rng.permutation(gx.shape[0])                     # new id of old node i is p[i]
+        inv = np.argsort(p)
+        relabelled.append((gx[inv], p[gei] if gei.size else gei, gy))
+        perms.append(p)
+    ws, bs = oracle_weights(graphs[0][0].shape[1])
+    x, ei, batch, ptr, _ = orc.from_data_list(graphs)
+    x2, ei2, batch2, _, _ = orc.from_data_list(relabelled)
+    xcat, xcat2 = orc.graph_conv_stack(x, ei, ws, bs), orc.graph_conv_stack(x2, ei2, ws, bs)
+    for g, p in enumerate(perms):
+        lo = int(ptr[g])
+        np.testing.assert_allclose(xcat2[lo + p].numpy(), xcat[lo:lo + len(p)].numpy(), rtol=0, atol=1e-13)
+    keys = xcat[:, -1].numpy()
+    for g in range(len(graphs)):                             # the property needs well-separated keys
+        seg = np.sort(keys[int(ptr[g]):int(ptr[g + 1])])
+        if seg.size > 1 and np.min(np.diff(seg)) < 1e-9:
+            return
+    pooled = orc.sort_aggregation(xcat, batch, k, len(graphs))
+    pooled2 = orc.sort_aggregation(xcat2, batch2, k, len(graphs))
+    np.testing.assert_allclose(pooled2.numpy(), pooled.numpy(), rtol=0, atol=1e-12)
+
+
+@settings(max_examples=40, deadline=None)
+@given(graph_lists(max_graphs=6, max_nodes=12))
+def test_property_batch_csr_is_the_edge_multiset(graphs):
+    """from_data_list + batch_csr: both CSRs hold exactly the non-loop edges (multi-edges kept),
+    rows ascending, and dis = (1 + in-degree)^-1/2."""
+    x, ei, batch, ptr, _ = orc.from_data_list(graphs)
+    n = int(ptr[-1])
+    rowptr, col, rowptr_t, col_t, dis = orc.batch_csr(ei, n)
+    want = sorted((int(s), int(d)) for s, d in ei.t().tolist() if s != d)
+    by_target = sorted((int(col[e]), i) for i in range(n) for e in range(int(rowptr[i]), int(rowptr[i + 1])))
+    by_source = sorted((i, int(col_t[e])) for i in range(n) for e in range(int(rowptr_t[i]), int(rowptr_t[i + 1])))
+    assert by_target == want and by_source == want
+    for i in range(n):
+        row = col[int(rowptr[i]):int(rowptr[i + 1])].tolist()
+        assert row == sorted(row)
+        assert all(int(batch[j]) == int(batch[i]) for j in row)       # edges never leave their graph
+    indeg = np.bincount([d for _, d in want], minlength=n)
+    np.testing.assert_allclose(dis.numpy(), (1.0 + indeg) ** -0.5, rtol=1e-6)

@@ -201,8 +201,11 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}-synth bs{batch.num_graphs} k{cfg.k}",
-                   "nodes": batch.num_nodes, "edges": batch.num_edges,
+        "config": {"workload": f"{args.workload}-synth bs{cfg.batch_size}/GPU k{cfg.k} "
+                               f"F{cfg.num_features} (BASELINE.json configs[3])",
+                   "sample_graphs": batch.num_graphs,
+                   "nodes_per_batch": batch.num_nodes, "edges_per_batch": batch.num_edges,
+                   "global_batch": batch.num_graphs,
                    "note": "CPU oracle restatement of model.py:26-45 + train.py:35-42 "
                            "(torch_geometric is not installable here); rank 0 only"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(),

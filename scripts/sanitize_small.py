@@ -23,4 +23,25 @@ for name, count in (("mutag", 12), ("proteins", 6), ("collab", 6)):
         torch.nn.functional.nll_loss(out, data.y).backward()
         torch.cuda.synchronize()
         print(name, "fused" if fused else "per-layer", float(out.sum()))
+# N1: resident data set -- dgcnn_dataset_prepare, n1_gather (fused tables), n1_plan + gather
+# (> 1024 graphs per batch), a symmetric and a generic (multigraph) data set, one resident step
+import numpy as np
+from dgcnn_b200.synth import make_graphs
+dg.set_fused(True)
+cfg = CONFIGS["mutag"]
+graphs = make_graphs(cfg, 24, seed=1)
+ds = dg.DeviceDataset(graphs, dev, num_classes=cfg.num_classes)
+rb = ds.batch(np.array([3, 3, 0, 23, 7]))
+big = ds.batch(np.random.RandomState(0).randint(0, 24, size=1100), bitmaps=False)
+rng = np.random.RandomState(2)
+multi = [{"x": rng.standard_normal((n, 3)).astype(np.float32),
+          "edge_index": np.stack([rng.randint(0, max(n, 1), 3 * n), rng.randint(0, max(n, 1), 3 * n)]).astype(np.int64),
+          "y": 0} for n in (5, 0, 7, 1, 9)]
+gds = dg.DeviceDataset(multi, dev, num_classes=2)
+gb = gds.batch(np.array([4, 1, 0, 2, 2]))
+model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(dev).train()
+trainer = dg.FusedTrainer(model)
+stats = trainer.step_resident(ds, np.arange(12))
+torch.cuda.synchronize()
+print("resident", rb.num_nodes, big.num_nodes, gb.num_nodes, float(stats[0]))
 print("sanitize workload done", dg.ops.LAUNCHES)

@@ -30,7 +30,7 @@ import torch
 from . import _lib, ops
 from .synth import GraphBatch, collate
 
-__all__ = ["read_tu_dataset", "write_tu_dataset", "indegree", "load_fold", "epoch_batches",
+__all__ = ["read_tu_dataset", "write_tu_dataset", "indegree", "Indegree", "load_fold", "epoch_batches",
            "DeviceDataset", "ResidentBatch"]
 
 
@@ -79,6 +79,31 @@ def indegree(x: Optional[np.ndarray], edge_index: np.ndarray, num_nodes: int, no
         x = x.reshape(-1, 1) if x.ndim == 1 else x
         return np.concatenate([x, deg.astype(x.dtype)], axis=1)                  # utils.py:29
     return deg
+
+
+class Indegree:
+    """The reference's ``utils.Indegree`` transform object (utils.py:5-36), same constructor and
+    call convention: ``Indegree(norm=True, max_value=None, cat=True)(data)`` appends (or, with
+    ``cat=False``, substitutes) the normalised in-degree column on any object with
+    ``edge_index`` / ``x`` / ``num_nodes`` and returns it.  A pre-transform: it runs on the host,
+    once per graph, before the data set goes to HBM; the arithmetic is ``indegree`` above."""
+
+    def __init__(self, norm: bool = True, max_value: Optional[float] = None, cat: bool = True):
+        self.norm, self.max, self.cat = norm, max_value, cat
+
+    def __call__(self, data):
+        ei = data.edge_index
+        ei_np = ei.detach().cpu().numpy() if isinstance(ei, torch.Tensor) else np.asarray(ei)
+        x = getattr(data, "x", None)
+        as_tensor = isinstance(x, torch.Tensor) or (x is None and isinstance(ei, torch.Tensor))
+        x_np = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
+        n = int(data.num_nodes) if getattr(data, "num_nodes", None) is not None else int(x_np.shape[0])
+        out = indegree(x_np, ei_np, n, self.norm, self.max, self.cat)
+        data.x = torch.from_numpy(np.ascontiguousarray(out)) if as_tensor else out
+        return data
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(norm={self.norm}, max_value={self.max})"
 
 
 def read_tu_dataset(root: str, name: str, use_node_attr: bool = True,

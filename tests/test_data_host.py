@@ -238,3 +238,24 @@ def test_collate_golden_pins_the_oracle_and_the_host_loader():
     assert np.allclose(dis[:5].numpy(), [5 ** -0.5] + [2 ** -0.5] * 4)
     assert col[8:11].tolist() == [6, 7, 5]                       # triangle node 5: sources 6 (0->1), 7 (2->1); node 6: 5
     assert z["gorder"].tolist() == [0, 1, 4, 3, 6, 5, 2]         # sizes 5,4,0,3,4,1,3: descending, ties by index
+
+
+def test_indegree_transform_object_has_the_reference_interface():
+    """utils.py:5-36: Indegree(norm, max_value, cat)(data) -> data, on tensors, against the oracle."""
+    from types import SimpleNamespace
+    rng = np.random.RandomState(1)
+    ei = torch.from_numpy(np.stack([rng.randint(0, 9, 30), rng.randint(0, 9, 30)]))
+    x = torch.from_numpy(rng.standard_normal((9, 4)).astype(np.float32))
+    data = SimpleNamespace(x=x.clone(), edge_index=ei, num_nodes=9)
+    out = dd.Indegree()(data)
+    assert out is data and isinstance(data.x, torch.Tensor) and data.x.dtype == torch.float32
+    assert torch.equal(data.x, orc.indegree_feature(ei, 9, x))
+    data = SimpleNamespace(x=None, edge_index=ei, num_nodes=9)                 # COLLAB / IMDB: no node features
+    assert torch.equal(dd.Indegree()(data).x, orc.indegree_feature(ei, 9, None))
+    data = SimpleNamespace(x=x[:, 0].clone(), edge_index=ei, num_nodes=9)      # 1-D x is viewed as a column
+    assert dd.Indegree()(data).x.shape == (9, 2)
+    data = SimpleNamespace(x=x.clone(), edge_index=ei, num_nodes=9)
+    assert dd.Indegree(cat=False)(data).x.shape == (9, 1)
+    raw = dd.Indegree(norm=False)(SimpleNamespace(x=None, edge_index=ei, num_nodes=9)).x
+    assert torch.equal(raw.ravel(), torch.bincount(ei[1], minlength=9).float())
+    assert repr(dd.Indegree(max_value=3)) == "Indegree(norm=True, max_value=3)"

@@ -10,7 +10,7 @@ from .synth import CONFIGS, GraphBatch, collate, make_batch, make_graphs
 from .dp import GradBucket, shard_bounds, shard_ids
 from .optim import FlatAdam
 from .trainer import FusedTrainer
-from .data import (DeviceDataset, Indegree, ResidentBatch, epoch_batches, indegree, load_fold, read_tu_dataset,
+from .data import (DeviceDataset, Indegree, ResidentBatch, ResidentLoader, epoch_batches, indegree, load_fold, read_tu_dataset,
                    write_tu_dataset)
 
 __version__ = "0.1.0"

@@ -31,7 +31,7 @@ from . import _lib, ops
 from .synth import GraphBatch, collate
 
 __all__ = ["read_tu_dataset", "write_tu_dataset", "indegree", "Indegree", "load_fold", "epoch_batches",
-           "DeviceDataset", "ResidentBatch"]
+           "DeviceDataset", "ResidentBatch", "ResidentLoader"]
 
 
 # ----------------------------------------------------------------------------------------
@@ -390,3 +390,27 @@ class DeviceDataset:
         b = collate([graphs[int(i)] for i in ids])
         b.max_nodes = int(self.nodes[np.asarray(ids, dtype=np.int64)].max())
         return b
+
+
+class ResidentLoader:
+    """``DataLoader(dataset=data_set[ids], batch_size=..., shuffle=...)`` of train.py:108-109 over a
+    resident data set: iterating yields gathered batches (``ResidentBatch``: ``.x .batch .y
+    .num_graphs``, ``.to(device)`` is a no-op) in the DataLoader's order, so the loops of
+    train.py:35-45 / 57-64 (``for sample in dataloader: data, y = sample.to(device),
+    sample.y.to(device); pred = model(data) ...``) run as they are.  ``len(loader)`` = number of
+    batches, ``len(loader.dataset)`` = number of graphs, as the reference's averages need."""
+
+    def __init__(self, dataset: "DeviceDataset", ids, batch_size: int = 1, shuffle: bool = False,
+                 generator: Optional[torch.Generator] = None):
+        self.source = dataset
+        self.dataset = np.asarray(ids, dtype=np.int64)          # what len(dataloader.dataset) counts
+        self.batch_size, self.shuffle, self.generator = int(batch_size), bool(shuffle), generator
+        if self.batch_size < 1:
+            raise ValueError("batch_size must be positive")
+
+    def __len__(self) -> int:
+        return -(-len(self.dataset) // self.batch_size)
+
+    def __iter__(self):
+        for ids in epoch_batches(self.dataset, self.batch_size, self.shuffle, self.generator):
+            yield self.source.batch(ids)

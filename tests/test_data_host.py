@@ -259,3 +259,27 @@ def test_indegree_transform_object_has_the_reference_interface():
     raw = dd.Indegree(norm=False)(SimpleNamespace(x=None, edge_index=ei, num_nodes=9)).x
     assert torch.equal(raw.ravel(), torch.bincount(ei[1], minlength=9).float())
     assert repr(dd.Indegree(max_value=3)) == "Indegree(norm=True, max_value=3)"
+
+
+def test_resident_loader_iterates_like_the_reference_dataloader():
+    """train.py:108-109 / 31-32: len(loader) batches, len(loader.dataset) graphs, DataLoader order;
+    the gather itself is the data set's business (a stand-in records the ids it is asked for)."""
+    class Recorder:
+        def __init__(self):
+            self.seen = []
+
+        def batch(self, ids):
+            self.seen.append(np.asarray(ids).tolist())
+            return len(ids)
+
+    rec = Recorder()
+    ids = np.arange(50, 73)
+    loader = dd.ResidentLoader(rec, ids, batch_size=10, shuffle=False)
+    assert len(loader) == 3 and len(loader.dataset) == 23
+    assert list(loader) == [10, 10, 3] and sum(rec.seen, []) == ids.tolist()
+    g1, g2 = torch.Generator().manual_seed(3), torch.Generator().manual_seed(3)
+    rec2 = Recorder()
+    list(dd.ResidentLoader(rec2, ids, batch_size=8, shuffle=True, generator=g1))
+    assert sum(rec2.seen, []) == ids[torch.randperm(23, generator=g2).numpy()].tolist()
+    with pytest.raises(ValueError):
+        dd.ResidentLoader(rec, ids, batch_size=0)

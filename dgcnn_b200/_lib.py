@@ -164,34 +164,74 @@ def sources():
     return sorted(CSRC_DIR.glob("*.cu"))
 
 
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive a copy of
+    the tree to another machine; contents do)."""
+    import hashlib
+    h = hashlib.sha1()
+    deps = sorted(CSRC_DIR.glob("*.cu")) + sorted(CSRC_DIR.glob("*.cuh")) + sorted(INCLUDE_DIR.glob("*.h"))
+    for p in deps:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("DGCNN_NVCC_EXTRA", "").split()).encode())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not LIB_PATH.exists():
+    stamp = LIB_PATH.with_suffix(".srchash")
+    if not LIB_PATH.exists() or not stamp.exists():
         return True
-    built = LIB_PATH.stat().st_mtime
-    deps = list(CSRC_DIR.glob("*.cu")) + list(CSRC_DIR.glob("*.cuh")) + list(INCLUDE_DIR.glob("*.h"))
-    return any(p.stat().st_mtime > built for p in deps)
+    return stamp.read_text().strip() != _source_hash()
+
+
+def _compile_one(nvcc: str, src: Path, obj: Path, flags) -> None:
+    cmd = [nvcc, *flags, "-I", str(INCLUDE_DIR), "-c", str(src), "-o", str(obj)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        obj.unlink(missing_ok=True)
+        raise RuntimeError(f"dgcnn_b200: nvcc failed\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+    if proc.stderr.strip() and "-Xptxas=-v" in flags:
+        print(proc.stderr)
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """nvcc-compile every kernel for sm_100a into one in-tree shared library."""
+    """nvcc-compile every kernel for sm_100a into one in-tree shared library: one object per
+    source (compiled in parallel, reused while neither the source, a header nor the flags
+    changed), then one link."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("dgcnn_b200: nvcc not found; cannot build libdgcnn_b200.so")
     LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
-    tmp = LIB_PATH.with_suffix(f".tmp{os.getpid()}.so")
+    obj_dir = PKG_DIR / "build"
+    obj_dir.mkdir(parents=True, exist_ok=True)
     extra = os.environ.get("DGCNN_NVCC_EXTRA", "").split()      # e.g. -DDGCNN_FWD_THREADS=768 (tuning runs)
-    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(INCLUDE_DIR), "-o", str(tmp), *map(str, sources())]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas=-v"] if verbose else [])
+    stamp = obj_dir / "flags.txt"
+    flags_changed = (not stamp.exists()) or stamp.read_text() != " ".join(cflags)
+    headers = list(CSRC_DIR.glob("*.cuh")) + list(INCLUDE_DIR.glob("*.h"))
+    hdr_time = max(p.stat().st_mtime for p in headers)
+    jobs = []
+    for src in sources():
+        obj = obj_dir / (src.stem + ".o")
+        if (force and verbose) or flags_changed or not obj.exists() or \
+                obj.stat().st_mtime < max(src.stat().st_mtime, hdr_time):
+            jobs.append((src, obj))
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], cflags), jobs))
+    stamp.write_text(" ".join(cflags))
+    tmp = LIB_PATH.with_suffix(f".tmp{os.getpid()}.so")
+    objs = [str(obj_dir / (src.stem + ".o")) for src in sources()]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp), *objs]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         tmp.unlink(missing_ok=True)
-        raise RuntimeError(f"dgcnn_b200: nvcc failed\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError(f"dgcnn_b200: link failed\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
     os.replace(tmp, LIB_PATH)
+    LIB_PATH.with_suffix(".srchash").write_text(_source_hash())
     return LIB_PATH
 
 

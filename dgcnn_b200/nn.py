@@ -24,7 +24,7 @@ from . import ops
 from .ops import ACT_NONE, ACT_TANH, NORM_RW, NORM_SYM, Graph
 
 __all__ = ["set_fused", "fused_enabled", "set_custom_tail", "custom_tail_enabled", "GCNConv", "GraphConvolution", "SortAggregation", "SortPool", "Model",
-           "remove_self_loops", "graph_conv_stack", "classifier_in_features"]
+           "remove_self_loops", "graph_conv_stack", "classifier_in_features", "batch_max_nodes"]
 
 
 def remove_self_loops(edge_index: Tensor, edge_attr: Optional[Tensor] = None):
@@ -75,7 +75,7 @@ class _GraphConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, graph: Graph, norm: int, act: int):
         x = x if x.stride(-1) == 1 else x.contiguous()
-        out = torch.empty(x.size(0), weight.size(0), dtype=torch.float32, device=x.device)
+        out = ops._empty(x.size(0), weight.size(0), dtype=torch.float32, device=x.device)
         ops.graph_conv_fwd(x, graph.rowptr, graph.col, graph.dis, weight, bias, norm, act, out)
         ctx.graph, ctx.norm, ctx.act = graph, norm, act
         ctx.has_bias = bias is not None
@@ -89,7 +89,7 @@ class _GraphConvFn(torch.autograd.Function):
         if g.rowptr_t is None:
             raise RuntimeError("dgcnn_b200: graph was built with transpose=False; no backward")
         dy = dy if dy.stride(-1) == 1 and dy.dim() == 2 else dy.contiguous()
-        dx = (torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        dx = (ops._empty(x.shape, dtype=x.dtype, device=x.device)
               if ctx.needs_input_grad[0] else None)
         dw, db = ops.graph_conv_bwd(dy, y, x, g.rowptr_t, g.col_t, g.dis, weight, ctx.norm, ctx.act,
                                     dx, False, need_db=ctx.has_bias)
@@ -149,7 +149,7 @@ class _StackFn(torch.autograd.Function):
         if fused:          # KS: one launch, one CTA per graph, everything in shared memory
             pooled, xcat, perm = ops.stack_fwd(x, graph, weights, biases, k, norm)
         else:              # K1 x L + K2: any widths, any graph size
-            xcat = torch.empty(n, offs[-1], dtype=torch.float32, device=x.device)
+            xcat = ops._empty(n, offs[-1], dtype=torch.float32, device=x.device)
             h = x
             for l, (w, b) in enumerate(zip(weights, biases)):
                 out = xcat[:, offs[l]:offs[l + 1]]
@@ -196,7 +196,7 @@ class _StackFn(torch.autograd.Function):
                 xin, dx, acc = xcat[:, xsl], dxcat[:, xsl], True
             else:
                 xin = x
-                dx = (torch.empty(x.shape, dtype=x.dtype, device=x.device)
+                dx = (ops._empty(x.shape, dtype=x.dtype, device=x.device)
                       if ctx.needs_input_grad[0] else None)
                 acc = False
             dw, db = ops.graph_conv_bwd(dxcat[:, ysl], xcat[:, ysl], xin, g.rowptr_t, g.col_t, g.dis,
@@ -262,8 +262,10 @@ class GCNConv(nn.Module):
             nn.init.zeros_(self.bias)
 
     def forward(self, x: Tensor, edge_index: Union[Tensor, Graph], act: int = ACT_NONE) -> Tensor:
-        graph = edge_index if isinstance(edge_index, Graph) else ops.build_graph(
-            edge_index, None, x.size(0), 0, transpose=torch.is_grad_enabled())
+        # model.py:30-33 hands the SAME edge_index tensor to all four layers: K0 runs once
+        # (PyG re-runs gcn_norm in every layer) and later calls hit the cache
+        graph = edge_index if isinstance(edge_index, Graph) else ops.cached_graph(
+            edge_index, x.size(0), transpose=torch.is_grad_enabled())
         return _GraphConvFn.apply(x, self.lin.weight, self.bias, graph, self.norm, act)
 
     def extra_repr(self):
@@ -299,6 +301,30 @@ class SortAggregation(nn.Module):
 
 GraphConvolution = GCNConv
 SortPool = SortAggregation
+
+
+def batch_max_nodes(data) -> int:
+    """Nodes of the largest graph of a batch: what selects the one-launch fused kernels (KS /
+    KSB) and sizes K0b's bitmaps.  Taken from ``data.max_nodes`` when the loader provides it
+    (no sync); otherwise computed from ``data.ptr`` (PyG batches carry it) or ``data.batch``
+    with ONE device-to-host read per batch object, cached on the object -- PyG's own
+    ``SortAggregation`` pays two such reads per forward (``to_dense_batch``: ``batch.max()``
+    and the largest graph)."""
+    mx = getattr(data, "max_nodes", None)
+    if mx:
+        return int(mx)
+    ptr = getattr(data, "ptr", None)
+    if isinstance(ptr, Tensor) and ptr.numel() > 1:
+        mx = int((ptr[1:] - ptr[:-1]).max())
+    elif data.batch.numel():
+        mx = int(torch.bincount(data.batch).max())
+    else:
+        mx = 0
+    try:
+        data.max_nodes = mx
+    except Exception:                                   # noqa: BLE001  (read-only containers)
+        pass
+    return mx
 
 
 def classifier_in_features(k: int) -> int:
@@ -339,8 +365,7 @@ class Model(nn.Module):
         if num_graphs is None:
             num_graphs = int(data.batch.max()) + 1                    # sync, like PyG
         return ops.build_graph(data.edge_index, data.batch, data.x.size(0), int(num_graphs),
-                               transpose=torch.is_grad_enabled(),
-                               max_nodes=int(getattr(data, "max_nodes", 0) or 0))
+                               transpose=torch.is_grad_enabled(), max_nodes=batch_max_nodes(data))
 
     def hot_path(self, x: Tensor, graph: Graph):
         convs = (self.conv1, self.conv2, self.conv3, self.conv4)

@@ -71,8 +71,32 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Debug aid (tests/test_gpu_parity.py::test_poisoned_buffers_*): every output / workspace the
+# operator layer allocates is pre-filled with a pattern ("nan": float NaN / int 0x7fc00000,
+# "ff": all-ones bytes), so that a kernel reading memory it did not write changes its result.
+_POISON: Optional[str] = os.environ.get("DGCNN_POISON") or None
+
+
+def set_poison(kind: Optional[str]) -> None:
+    global _POISON
+    if kind not in (None, "nan", "ff"):
+        raise ValueError("poison must be None, 'nan' or 'ff'")
+    _POISON = kind
+
+
+def _empty(*shape, dtype, device) -> Tensor:
+    t = torch.empty(*shape, dtype=dtype, device=device)
+    if _POISON is not None and t.numel():
+        raw = t.view(-1).view(torch.uint8)
+        if _POISON == "ff" or raw.numel() % 4:
+            raw.fill_(0xFF)
+        else:
+            raw.view(torch.int32).fill_(0x7FC00000)
+    return t
+
+
 def _workspace(nbytes: int, device) -> Tensor:
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    return _empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 @dataclass
@@ -133,13 +157,13 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
         if batch.numel() != n:
             raise ValueError("dgcnn_b200: batch must have one entry per node")
     i32 = dict(dtype=torch.int32, device=dev)
-    rowptr = torch.empty(n + 1, **i32)
-    col = torch.empty(max(e, 1), **i32)
-    rowptr_t = torch.empty(n + 1, **i32) if transpose else None
-    col_t = torch.empty(max(e, 1), **i32) if transpose else None
-    dis = torch.empty(n, dtype=torch.float32, device=dev)
-    gptr = torch.empty(b + 1, **i32) if batch is not None else None
-    gorder = torch.empty(max(b, 1), **i32) if batch is not None else None
+    rowptr = _empty(n + 1, **i32)
+    col = _empty(max(e, 1), **i32)
+    rowptr_t = _empty(n + 1, **i32) if transpose else None
+    col_t = _empty(max(e, 1), **i32) if transpose else None
+    dis = _empty(n, dtype=torch.float32, device=dev)
+    gptr = _empty(b + 1, **i32) if batch is not None else None
+    gorder = _empty(max(b, 1), **i32) if batch is not None else None
     status = torch.zeros(1, **i32)
     wbytes = lib.dgcnn_build_graph_workspace_bytes(n, e)
     ws = _workspace(wbytes, dev)
@@ -157,6 +181,29 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
     return graph
 
 
+# GCNConv.forward(x, edge_index) as the reference calls it (model.py:30-33): the four layers of
+# one forward pass the same tensor, so K0's result is kept for the last few edge_index tensors
+# (identity + in-place version counter; weak references, nothing is kept alive).
+_GRAPH_CACHE: list = []
+_GRAPH_CACHE_SIZE = 4
+GRAPH_CACHE_HITS = 0
+
+
+def cached_graph(edge_index: Tensor, num_nodes: int, transpose: bool = True) -> Graph:
+    global GRAPH_CACHE_HITS
+    import weakref
+    for ref, ver, n, graph in _GRAPH_CACHE:
+        if ref() is edge_index and ver == edge_index._version and n == int(num_nodes) and \
+                (graph.rowptr_t is not None or not transpose):
+            GRAPH_CACHE_HITS += 1
+            return graph
+    graph = build_graph(edge_index, None, num_nodes, 0, transpose=transpose)
+    _GRAPH_CACHE[:] = [c for c in _GRAPH_CACHE if c[0]() is not None and c[0]() is not edge_index]
+    _GRAPH_CACHE.append((weakref.ref(edge_index), edge_index._version, int(num_nodes), graph))
+    del _GRAPH_CACHE[:-_GRAPH_CACHE_SIZE]
+    return graph
+
+
 def _build_bitmaps(graph: Graph, transpose: bool, batch: Optional[Tensor] = None) -> None:
     """K0b: adjacency bitmaps of A_hat (and of A_hat^T unless K0 proved symmetry), the
     fragment-major copy for the tensor-core kernels and the work descriptors; one call."""
@@ -167,16 +214,16 @@ def _build_bitmaps(graph: Graph, transpose: bool, batch: Optional[Tensor] = None
     fwords = int(lib.dgcnn_graph_fragmap_words(n, b, mx))
     i32 = dict(dtype=torch.int32, device=dev)
     transpose = transpose and graph.rowptr_t is not None
-    both = torch.empty((2 if transpose else 1) * words, **i32)
+    both = _empty((2 if transpose else 1) * words, **i32)
     graph.bitmap = both[:words]
     graph.bitmap_t = both[words:] if transpose else None
-    graph.bmoff = torch.empty(b + 1, **i32)
+    graph.bmoff = _empty(b + 1, **i32)
     graph.bmoff_t = graph.bmoff if transpose else None          # same sizes, same offsets
-    graph.gflags = torch.empty(b, **i32)
-    graph.gflags_t = torch.empty(b, **i32) if transpose else None
-    graph.fragmap = torch.empty(fwords, **i32)
-    graph.fgoff = torch.empty(b + 1, **i32)
-    graph.gdesc = torch.empty(b, 4, **i32)
+    graph.gflags = _empty(b, **i32)
+    graph.gflags_t = _empty(b, **i32) if transpose else None
+    graph.fragmap = _empty(fwords, **i32)
+    graph.fgoff = _empty(b + 1, **i32)
+    graph.gdesc = _empty(b, 4, **i32)
     with torch.cuda.device(dev):
         rc = lib.dgcnn_build_bitmaps(_ptr(graph.rowptr), _ptr(graph.col),
                                      _ptr(graph.rowptr_t) if transpose else None,
@@ -198,7 +245,7 @@ def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
     lib = _lib.load_library()
     _require_cuda(batch, "batch", torch.int64)
     batch = batch.contiguous()
-    gptr = torch.empty(int(num_graphs) + 1, dtype=torch.int32, device=batch.device)
+    gptr = _empty(int(num_graphs) + 1, dtype=torch.int32, device=batch.device)
     with torch.cuda.device(batch.device):
         rc = lib.dgcnn_graph_ptr(_ptr(batch), batch.numel(), int(num_graphs), _ptr(gptr), None,
                                  _stream())
@@ -254,8 +301,8 @@ def graph_conv_bwd(dy: Tensor, y: Optional[Tensor], x: Tensor, rowptr_t: Tensor,
         if dx.shape != (n, cin):
             raise ValueError("dgcnn_b200: dx shape mismatch")
     weight = weight.contiguous()
-    dw = torch.empty_like(weight)
-    db = torch.empty(cout, dtype=torch.float32, device=x.device) if need_db else None
+    dw = _empty(weight.shape, dtype=weight.dtype, device=weight.device)
+    db = _empty(cout, dtype=torch.float32, device=x.device) if need_db else None
     ws = _workspace(lib.dgcnn_graph_conv_bwd_workspace_bytes(n, cin, cout), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_graph_conv_bwd(
@@ -275,8 +322,8 @@ def sort_pool_fwd(x: Tensor, gptr: Tensor, k: int, max_nodes: int = 0) -> Tuple[
     _require_cuda(gptr, "gptr", torch.int32)
     n, d = x.shape
     b = gptr.numel() - 1
-    out = torch.empty(b, int(k) * d, dtype=torch.float32, device=x.device)
-    perm = torch.empty(b, int(k), dtype=torch.int32, device=x.device)
+    out = _empty(b, int(k) * d, dtype=torch.float32, device=x.device)
+    perm = _empty(b, int(k), dtype=torch.int32, device=x.device)
     ws = _workspace(lib.dgcnn_sort_pool_workspace_bytes(n, b), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_sort_pool_fwd(_ptr(x), _rows(x, "x"), d, _ptr(gptr), n, b, int(k),
@@ -296,7 +343,7 @@ def sort_pool_bwd(dout: Tensor, perm: Tensor, num_nodes: int, out: Optional[Tens
     d = dout.numel() // max(b * k, 1) if b * k else (out.size(1) if out is not None else 1)
     dout = dout.contiguous()
     if out is None:
-        out = torch.empty(int(num_nodes), d, dtype=torch.float32, device=dout.device)
+        out = _empty(int(num_nodes), d, dtype=torch.float32, device=dout.device)
     with torch.cuda.device(dout.device):
         rc = lib.dgcnn_sort_pool_bwd(_ptr(dout), _ptr(perm), b, k, d, _ptr(out), _rows(out, "dx"),
                                      int(num_nodes), _stream())
@@ -328,9 +375,9 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
         _require_cuda(t, "parameter", torch.float32)
     b = graph.num_graphs
     # rows padded to 100 floats (16-byte aligned rows: vector stores in KS); callers see [N,97]
-    xcat = torch.empty(n, XCAT_LD, dtype=torch.float32, device=x.device)[:, :97]
-    pooled = torch.empty(b, int(k) * 97, dtype=torch.float32, device=x.device)
-    perm = torch.empty(b, int(k), dtype=torch.int32, device=x.device)
+    xcat = _empty(n, XCAT_LD, dtype=torch.float32, device=x.device)[:, :97]
+    pooled = _empty(b, int(k) * 97, dtype=torch.float32, device=x.device)
+    perm = _empty(b, int(k), dtype=torch.int32, device=x.device)
     wsp = _workspace(lib.dgcnn_stack_fwd_workspace_bytes(), x.device)
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_stack_fwd(_ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr), _ptr(graph.col),
@@ -379,7 +426,7 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     dpooled = dpooled.contiguous()
     ws = [w.contiguous() for w in weights]
     total = int(lib.dgcnn_stack_num_params(f))
-    grads = out if out is not None else torch.empty(total, dtype=torch.float32, device=x.device)
+    grads = out if out is not None else _empty(total, dtype=torch.float32, device=x.device)
     if grads.numel() != total or not grads.is_contiguous():
         raise ValueError("dgcnn_b200: stack_bwd out buffer mismatch")
     wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f, b, n), x.device)
@@ -424,12 +471,12 @@ def tail_fwd(pooled: Tensor, k: int, params, training: bool, seed: int, rng_offs
     dev = pooled.device
     f32 = dict(dtype=torch.float32, device=dev)
     u8 = dict(dtype=torch.uint8, device=dev)
-    h1 = torch.empty(b, 16, l1, **f32)
-    arg = torch.empty(b, 16, l1, **u8)
-    h2 = torch.empty(b, d1, **f32)
-    h3 = torch.empty(b, 128, **f32)
-    keep = torch.empty(b, 128, **u8)
-    logp = torch.empty(b, c, **f32)
+    h1 = _empty(b, 16, l1, **f32)
+    arg = _empty(b, 16, l1, **u8)
+    h2 = _empty(b, d1, **f32)
+    h3 = _empty(b, 128, **f32)
+    keep = _empty(b, 128, **u8)
+    logp = _empty(b, c, **f32)
     ws = _workspace(lib.dgcnn_tail_workspace_bytes(b, k, c), dev)
     if training and rng_offset is None:
         raise ValueError("dgcnn_b200: training-mode tail needs the device rng_offset counter")
@@ -472,9 +519,9 @@ def tail_bwd(dlogp: Tensor, logp: Tensor, saved, k: int, params, out_grads=None,
     dlogp = dlogp.contiguous()
     b, c = logp.shape
     dev = pooled.device
-    dpooled = torch.empty_like(pooled)
+    dpooled = _empty(pooled.shape, dtype=pooled.dtype, device=pooled.device)
     grads = list(out_grads) if out_grads is not None else \
-        [torch.empty_like(p) for p in (w5, b5, w6, b6, wf1, bf1, wf2, bf2)]
+        [_empty(p.shape, dtype=p.dtype, device=p.device) for p in (w5, b5, w6, b6, wf1, bf1, wf2, bf2)]
     for g_, p_ in zip(grads, (w5, b5, w6, b6, wf1, bf1, wf2, bf2)):
         if g_.numel() != p_.numel() or not g_.is_contiguous():
             raise ValueError("dgcnn_b200: tail_bwd out_grads mismatch")
@@ -502,8 +549,8 @@ def nll_sum(logp: Tensor, y: Tensor, grad_scale: float = 1.0, want_grad: bool = 
     logp, y = logp.contiguous(), y.contiguous()
     b, c = logp.shape
     if stats is None:
-        stats = torch.empty(2, dtype=torch.float32, device=logp.device)
-    dlogp = torch.empty_like(logp) if want_grad else None
+        stats = _empty(2, dtype=torch.float32, device=logp.device)
+    dlogp = _empty(logp.shape, dtype=logp.dtype, device=logp.device) if want_grad else None
     with torch.cuda.device(logp.device):
         rc = lib.dgcnn_nll_sum(_ptr(logp), _ptr(y), b, c, float(grad_scale), _ptr(stats), _ptr(dlogp),
                                _stream())
@@ -581,7 +628,7 @@ def register_torch_ops() -> None:
 
     def _build(edge_index, batch, num_graphs, transpose):
         g = build_graph(edge_index, batch, batch.numel(), num_graphs, transpose)
-        empty = torch.empty(0, dtype=torch.int32, device=edge_index.device)
+        empty = _empty(0, dtype=torch.int32, device=edge_index.device)
         return (g.rowptr, g.col, g.rowptr_t if transpose else empty,
                 g.col_t if transpose else empty, g.dis, g.gptr, g.gorder, g.status)
 

@@ -92,7 +92,8 @@ class FusedTrainer:
 
     def supported(self, data) -> bool:
         """The fused kernels need the largest graph of the batch (host knowledge)."""
-        mx = int(getattr(data, "max_nodes", 0) or 0)
+        from .nn import batch_max_nodes
+        mx = batch_max_nodes(data)                 # data.max_nodes, or one cached device read
         f = data.x.size(1)
         return (ops.stack_fwd_supported(f, mx) and ops.stack_bwd_supported(f, mx)
                 and self.model.classifier_2.out_features <= 32)
@@ -103,7 +104,7 @@ class FusedTrainer:
         m = self.model
         if not self.supported(data):
             raise RuntimeError("FusedTrainer.step: batch not supported by the fused kernels "
-                               "(set data.max_nodes; graphs must fit shared memory)")
+                               "(every graph must fit the shared memory of one SM; use Model(data) + autograd)")
         world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
         if self.native and self._native_step(data, global_batch, world):
             return self.stats
@@ -165,7 +166,7 @@ class FusedTrainer:
         if need == 0:
             raise ValueError("FusedTrainer.step_resident: bad sizes")
         if self._arena is None or self._arena.numel() < need:
-            self._arena = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.flat.device)
+            self._arena = ops._empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.flat.device)
         if global_batch is None:
             global_batch = b * world
         table, epoch, rank = None, None, 0
@@ -211,7 +212,7 @@ class FusedTrainer:
             return False
         need = int(lib.dgcnn_train_step_workspace_bytes(n, e, b, f, k, c, mx))
         if self._arena is None or self._arena.numel() < need:
-            self._arena = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=x.device)
+            self._arena = ops._empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=x.device)
         if global_batch is None:
             global_batch = b * world
         table, epoch, rank = None, None, 0

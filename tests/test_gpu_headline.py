@@ -1,0 +1,313 @@
+"""GPU parity tests of the HEADLINE path at BASELINE.json's full sizes ("parity
+first"): the fused kernels KS / KSB and FusedTrainer.step on COLLAB-synth bs512 against the
+float64 oracle, configs[2] D&D and configs[4] power-law at full size, determinism with
+poisoned buffers, and the drop-in `Model(data)` / `GCNConv(x, edge_index)` calls of the
+reference (model.py:27-35, train.py:36-37) reaching the fused kernels without any hint.
+
+Tolerances: x_cat / pooled within 1e-5 absolute of the float64 oracle; permutation equal to
+the oracle's wherever its sorted float64 keys are further apart than 1e-5; gradients within
+2e-3 of the largest gradient entry of the tensor (sums of ~1e5 fp32 terms); CSR bit-exact.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import dgcnn_b200 as dg
+from dgcnn_b200 import ops
+from dgcnn_b200.synth import CONFIGS, make_batch
+from oracle import dgcnn_oracle as orc
+from test_gpu_parity import assert_perm_matches
+
+ATOL = 1e-5
+DEV = "cuda:0"
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def oracle_and_model(cfg, seed=324, train=False):
+    """float64 oracle with non-zero GCN biases and our model loaded with the same values."""
+    torch.manual_seed(seed)
+    ref = orc.OracleModel(cfg.num_features, cfg.num_classes, cfg.k).double().eval()
+    with torch.no_grad():
+        for c in (ref.conv1, ref.conv2, ref.conv3, ref.conv4):
+            c.bias.uniform_(-0.1, 0.1)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k)
+    model.load_state_dict({k_: v.float() for k_, v in ref.state_dict().items()})
+    model = model.to(DEV)
+    return ref, (model.train() if train else model.eval())
+
+
+def oracle_pooled_from_perm(rx, perm, count, k):
+    """The oracle's pooled output continued from OUR (validated) permutation: near-tied keys
+    may legitimately swap ranks, the gather itself is exact."""
+    pcpu = perm.cpu().long()
+    rpool = torch.where((pcpu >= 0).unsqueeze(-1), rx[pcpu.clamp(min=0)], rx.new_zeros(()))
+    return rpool.reshape(count, k * 97)
+
+
+def check_forward(cfg, batch, model, ref, expect_fused):
+    data = batch.to(DEV)
+    before = ops.LAUNCHES["stack_fwd"]
+    g = model.build_graph(data)
+    pooled, xcat, perm = model.hot_path(data.x, g)
+    g.check()
+    assert (ops.LAUNCHES["stack_fwd"] > before) == expect_fused, "unexpected kernel path"
+    count = batch.num_graphs
+    rx, _ = ref.hot_path(batch.x.double(), batch.edge_index, batch.batch, count)
+    err = (xcat.detach().cpu().double() - rx.detach()).abs().max().item()
+    assert err <= ATOL, f"x_cat differs from the float64 oracle by {err:.3e}"
+    _, rperm = orc.sort_aggregation(rx.detach(), batch.batch, cfg.k, count, return_perm=True)
+    assert_perm_matches(perm.cpu().numpy(), rperm.numpy(), rx.detach().numpy()[:, -1], batch.ptr.numpy(), cfg.k)
+    rpool = oracle_pooled_from_perm(rx, perm, count, cfg.k)
+    assert (pooled.detach().cpu().double() - rpool.detach()).abs().max().item() <= ATOL
+    # size-independent properties: sorted keys, zero padding, rows are x_cat rows of the own graph
+    keys = pooled.view(count, cfg.k, 97)[:, :, -1]
+    valid = perm >= 0
+    both = valid[:, 1:] & valid[:, :-1]
+    assert (keys[:, :-1][both] >= keys[:, 1:][both]).all()
+    assert (pooled.view(count, cfg.k, 97)[~valid] == 0).all()
+    gp = g.gptr.long()
+    lo, hi = gp[:-1].view(-1, 1), gp[1:].view(-1, 1)
+    assert ((perm >= lo) & (perm < hi))[valid].all()
+    assert torch.equal(pooled.view(-1, 97)[valid.view(-1)], xcat[perm[valid].long()])
+    return data, rx, rpool, pooled, xcat, perm
+
+
+def check_gradients(model, ref, data, batch, rpool, rtol=2e-3):
+    out = model(data)
+    rout = ref.tail(rpool)
+    assert (out.detach().cpu().double() - rout.detach()).abs().max().item() <= 1e-4
+    model.zero_grad()
+    F.nll_loss(out, data.y).backward()
+    F.nll_loss(rout, batch.y).backward()
+    rp = dict(ref.named_parameters())
+    for pname, p in model.named_parameters():
+        want = rp[pname].grad
+        scale = max(1e-3, float(want.abs().max()))
+        err = (p.grad.cpu().double() - want).abs().max().item()
+        assert err <= rtol * scale, f"{pname}: {err:.3e} vs scale {scale:.3e}"
+
+
+# ---------------------------------------------------------------- BASELINE configs at full size
+def test_collab_full_size_fused_forward_backward_vs_float64_oracle():
+    """configs[3] COLLAB-synth bs512 (the workload bench.py times) on KS / KSB, no hint on the batch."""
+    cfg = CONFIGS["collab"]
+    batch = make_batch("collab")                       # the bench's own batch (degree-only features: exact ties)
+    ref, model = oracle_and_model(cfg)
+    before_b = ops.LAUNCHES["stack_bwd"]
+    data, rx, rpool, *_ = check_forward(cfg, batch, model, ref, expect_fused=True)
+    check_gradients(model, ref, data, batch, rpool)
+    assert ops.LAUNCHES["stack_bwd"] > before_b, "KSB was not used"
+
+
+def test_dd_full_size_vs_float64_oracle():
+    """configs[2] D&D-synth bs64 F90 k291, with its 5748-node graph: forward and backward of the
+    path that serves graphs beyond one SM's shared memory."""
+    cfg = CONFIGS["dd"]
+    batch = make_batch("dd", tie_free=True)
+    assert int((batch.ptr[1:] - batch.ptr[:-1]).max()) == 5748
+    ref, model = oracle_and_model(cfg)
+    data, rx, rpool, *_ = check_forward(cfg, batch, model, ref,
+                                        expect_fused=ops.stack_fwd_supported(cfg.num_features, 5748))
+    check_gradients(model, ref, data, batch, rpool)
+
+
+def test_powerlaw_full_size_vs_float64_oracle():
+    """configs[4] power-law 1000 nodes x ~10k edges, F64, bs256, k512 (256k nodes, 5.07M edges)."""
+    cfg = CONFIGS["powerlaw"]
+    batch = make_batch("powerlaw", tie_free=True)
+    assert batch.num_nodes == 256000 and batch.num_graphs == 256
+    ref, model = oracle_and_model(cfg)
+    data, rx, rpool, *_ = check_forward(cfg, batch, model, ref,
+                                        expect_fused=ops.stack_fwd_supported(cfg.num_features, 1000))
+    check_gradients(model, ref, data, batch, rpool)
+
+
+# ---------------------------------------------------------------- FusedTrainer.step == what bench.py times
+def test_fused_trainer_step_collab_bs512_vs_float64_oracle():
+    """One optimisation step of FusedTrainer on COLLAB-synth bs512 (exactly bench.py's step):
+    loss, #correct, all 16 parameter gradients and the parameters after Adam against the
+    float64 oracle + torch.optim.Adam.  The dropout mask and the (validated) permutation are
+    taken from our own forward: the oracle cannot reproduce a counter-hash RNG, and near-tied
+    keys may swap ranks."""
+    cfg = CONFIGS["collab"]
+    batch = make_batch("collab", seed=1324)
+    ref, model = oracle_and_model(cfg, train=True)
+    ref.train()
+    data = batch.to(DEV)
+    b, k = batch.num_graphs, cfg.k
+
+    # (a) the step's kernels one by one through the operator layer, on a copy of the model
+    m_seq = copy.deepcopy(model)
+    convs = (m_seq.conv1, m_seq.conv2, m_seq.conv3, m_seq.conv4)
+    weights, biases = [c.lin.weight for c in convs], [c.bias for c in convs]
+    tail = [m_seq.conv5.weight, m_seq.conv5.bias, m_seq.conv6.weight, m_seq.conv6.bias,
+            m_seq.classifier_1.weight, m_seq.classifier_1.bias, m_seq.classifier_2.weight, m_seq.classifier_2.bias]
+    with torch.no_grad():
+        g = m_seq.build_graph(data)
+        pooled, xcat, perm = ops.stack_fwd(data.x, g, weights, biases, k, 0)
+        logp, saved = ops.tail_fwd(pooled, k, tail, True, m_seq._tail_seed, m_seq._tail_rng_offset.clone())
+        stats, dlogp = ops.nll_sum(logp, data.y, 1.0, True)
+        dpooled, tgrads = ops.tail_bwd(dlogp, logp, saved, k, tail)
+        sgrads = ops.stack_bwd(dpooled, perm, xcat, data.x, g, weights, k, 0)
+    keep = saved[5].cpu().double()
+
+    # (b) the oracle in float64 from our permutation and our dropout mask
+    rx, _ = ref.hot_path(batch.x.double(), batch.edge_index, batch.batch, b)
+    assert (xcat.cpu().double() - rx.detach()).abs().max().item() <= ATOL
+    _, rperm = orc.sort_aggregation(rx.detach(), batch.batch, k, b, return_perm=True)
+    assert_perm_matches(perm.cpu().numpy(), rperm.numpy(), rx.detach().numpy()[:, -1], batch.ptr.numpy(), k)
+    rpool = oracle_pooled_from_perm(rx, perm, b, k)
+    h = rpool.view(b, 1, -1)
+    h = ref.pool(F.relu(ref.conv5(h)))
+    h = F.relu(ref.conv6(h)).flatten(1)
+    h = F.relu(ref.classifier_1(h)) * keep                             # Dropout(0.5): `keep` holds OUR multiplier (0 or 2)
+    rlogp = F.log_softmax(ref.classifier_2(h), dim=-1)
+    rloss = F.nll_loss(rlogp, batch.y, reduction="sum")
+    rloss.backward()
+    assert abs(float(stats[0]) - float(rloss)) <= 1e-4 * max(1.0, abs(float(rloss)))
+    assert float(stats[1]) == float((rlogp.argmax(1) == batch.y).sum())
+    names = ["conv1.lin.weight", "conv1.bias", "conv2.lin.weight", "conv2.bias", "conv3.lin.weight", "conv3.bias",
+             "conv4.lin.weight", "conv4.bias", "conv5.weight", "conv5.bias", "conv6.weight", "conv6.bias",
+             "classifier_1.weight", "classifier_1.bias", "classifier_2.weight", "classifier_2.bias"]
+    got = [t for pair in sgrads for t in pair] + list(tgrads)
+    rp = dict(ref.named_parameters())
+    for name, gt in zip(names, got):
+        want = rp[name].grad
+        scale = max(1e-3, float(want.abs().max()))
+        err = (gt.cpu().double().view_as(want) - want).abs().max().item()
+        assert err <= 2e-3 * scale, f"{name}: {err:.3e} vs scale {scale:.3e}"
+
+    # (c) FusedTrainer.step (one native call): same gradients bit for bit, and the parameters
+    # after its Adam equal torch.optim.Adam on the oracle's mean-loss gradients
+    trainer = dg.FusedTrainer(model, lr=1e-3)
+    before = ops.LAUNCHES.get("train_step", 0)
+    st = trainer.step(data).clone()
+    assert ops.LAUNCHES.get("train_step", 0) > before, "the native one-call step was not used"
+    assert torch.equal(st, stats)
+    flat_seq = torch.cat([t.reshape(-1) for t in got])
+    assert torch.equal(trainer.grad[:trainer.num_params], flat_seq), "native step != operator sequence"
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    for p in ref.parameters():
+        p.grad.div_(b)                                                  # train.py:39: mean NLL
+    opt.step()
+    mp = dict(model.named_parameters())
+    for name in names:
+        err = (mp[name].detach().cpu().double() - rp[name].detach()).abs().max().item()
+        assert err <= 2e-5, f"{name} after Adam: {err:.3e}"              # |update| = lr = 1e-3 on step 1
+
+
+# ---------------------------------------------------------------- determinism with poisoned buffers
+@pytest.mark.parametrize("path", ["per-layer", "fused"])
+def test_poisoned_buffers_give_bit_identical_results(path):
+    """Every output / workspace of the operator layer pre-filled with NaN or 0xFF bytes
+    (ops.set_poison): K0 -> K1 x 4 -> K2 (+ K3 / K4) and K0 + K0b -> KS -> KT -> KSB must return
+    the same bits as with fresh memory, five times over (a kernel that
+    reads memory it did not write shows up here)."""
+    cfg = CONFIGS["proteins"]
+    batch = make_batch("proteins", num_graphs=40, tie_free=True)
+    torch.manual_seed(3)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    data = batch.to(DEV)
+    dg.set_fused(path == "fused")
+    try:
+        ref = None
+        for kind in (None, "nan", "ff", "nan", None):
+            ops.set_poison(kind)
+            junk = [ops._empty(s, dtype=torch.float32, device=DEV) for s in (1 << 22, 1 << 20, 1 << 16, 1 << 12)]
+            del junk                                     # poisoned blocks go back to the allocator
+            model.zero_grad()
+            g = model.build_graph(data)
+            pooled, xcat, perm = model.hot_path(data.x, g)
+            out = model.tail(pooled)
+            F.nll_loss(out, data.y).backward()
+            torch.cuda.synchronize()
+            got = [xcat.detach().clone(), perm.clone(), pooled.detach().clone(), out.detach().clone(),
+                   g.rowptr.clone(), g.col[:batch.num_edges].clone(), g.dis.clone(), g.gptr.clone()]
+            got += [p.grad.clone() for p in model.parameters()]
+            assert not any(torch.isnan(t).any() for t in got if t.is_floating_point())
+            if ref is None:
+                ref = got
+            else:
+                for i, (a, b_) in enumerate(zip(ref, got)):
+                    assert torch.equal(a, b_), f"poison={kind}: result {i} changed"
+    finally:
+        ops.set_poison(None)
+        dg.set_fused(True)
+
+
+def test_poisoned_native_train_step_is_bit_identical():
+    """The one-call training step (arena-carved buffers) with a NaN-poisoned arena."""
+    cfg = CONFIGS["collab"]
+    batch = make_batch("collab", num_graphs=64)
+    data = batch.to(DEV)
+    torch.manual_seed(3)
+    base = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    flats = []
+    try:
+        for kind in (None, "nan", "ff"):
+            ops.set_poison(kind)
+            tr = dg.FusedTrainer(copy.deepcopy(base))
+            for _ in range(2):
+                st = tr.step(data).clone()
+            flats.append((tr.flat.clone(), st))
+    finally:
+        ops.set_poison(None)
+    for flat, st in flats[1:]:
+        assert torch.equal(flat, flats[0][0]) and torch.equal(st, flats[0][1])
+        assert not torch.isnan(flat).any()
+
+
+# ---------------------------------------------------------------- the reference's own calls
+class PlainBatch:
+    """What PyG's DataLoader yields, reduced to the attributes model.py:27 and train.py:36 touch;
+    no num_graphs, no max_nodes, no ptr."""
+
+    def __init__(self, x, edge_index, batch, y):
+        self.x, self.edge_index, self.batch, self.y = x, edge_index, batch, y
+
+
+def test_drop_in_model_call_reaches_the_fused_kernels_without_hints():
+    cfg = CONFIGS["collab"]
+    hb = make_batch("collab", num_graphs=128)
+    data = PlainBatch(hb.x.to(DEV), hb.edge_index.to(DEV), hb.batch.to(DEV), hb.y.to(DEV))
+    ref, model = oracle_and_model(cfg)
+    f0, b0 = ops.LAUNCHES["stack_fwd"], ops.LAUNCHES["stack_bwd"]
+    out = model(data)                                   # train.py:37
+    F.nll_loss(out, data.y).backward()                  # train.py:39-40
+    assert ops.LAUNCHES["stack_fwd"] == f0 + 1 and ops.LAUNCHES["stack_bwd"] > b0
+    assert data.max_nodes == int((hb.ptr[1:] - hb.ptr[:-1]).max())     # cached: one read per batch
+    rx, _ = ref.hot_path(hb.x.double(), hb.edge_index, hb.batch, hb.num_graphs)
+    with torch.no_grad():
+        _, xcat, _ = model.hot_path(data.x, model.build_graph(data))
+    assert (xcat.cpu().double() - rx.detach()).abs().max().item() <= ATOL
+
+
+def test_reference_forward_body_with_our_modules_builds_the_graph_once():
+    """model.py:27-35 verbatim with dgcnn_b200's GCNConv / SortAggregation / remove_self_loops
+    (INTEGRATION.md section 1): K0 runs once for the four layers, results match the oracle."""
+    cfg = CONFIGS["proteins"]
+    hb = make_batch("proteins", num_graphs=32, tie_free=True)
+    ref, model = oracle_and_model(cfg)
+    x, edge_index, batch = hb.x.to(DEV), hb.edge_index.to(DEV), hb.batch.to(DEV)
+    k0, hits = ops.LAUNCHES["build_graph"], ops.GRAPH_CACHE_HITS
+    edge_index, _ = dg.remove_self_loops(edge_index)
+    x_1 = torch.tanh(model.conv1(x, edge_index))
+    x_2 = torch.tanh(model.conv2(x_1, edge_index))
+    x_3 = torch.tanh(model.conv3(x_2, edge_index))
+    x_4 = torch.tanh(model.conv4(x_3, edge_index))
+    xc = torch.cat([x_1, x_2, x_3, x_4], dim=-1)
+    pooled = model.sort_pool(xc, batch)
+    assert ops.LAUNCHES["build_graph"] - k0 == 3, "K0 must run once per forward, not once per layer"
+    assert ops.GRAPH_CACHE_HITS - hits == 3
+    rx, _ = ref.hot_path(hb.x.double(), hb.edge_index, hb.batch, hb.num_graphs)
+    assert (xc.detach().cpu().double() - rx.detach()).abs().max().item() <= ATOL
+    opool = orc.sort_aggregation(xc.detach().cpu(), hb.batch, cfg.k, hb.num_graphs)
+    assert torch.equal(pooled.detach().cpu(), opool)
+    pooled.sum().backward()
+    assert model.conv1.lin.weight.grad is not None and torch.isfinite(model.conv1.lin.weight.grad).all()

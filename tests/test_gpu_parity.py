@@ -353,8 +353,8 @@ def test_graph_conv_forward_without_bias_and_via_torch_ops():
     out = torch.empty(n, 32, device=DEV)
     torch.ops.dgcnn_b200.graph_conv_fwd(torch.from_numpy(x).to(DEV), g.rowptr, g.col, g.dis,
                                         torch.from_numpy(w).to(DEV), None, 0, 0, out)
-    ref = orc.gcn_conv(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(w), None)
-    assert (out.cpu() - ref).abs().max().item() <= ATOL
+    ref = orc.gcn_conv(torch.from_numpy(x).double(), torch.from_numpy(ei), torch.from_numpy(w).double(), None)
+    assert (out.cpu().double() - ref).abs().max().item() <= ATOL
 
 
 @pytest.mark.parametrize("cin,cout", DIMS)
@@ -401,14 +401,14 @@ def test_gcnconv_module_autograd_matches_oracle():
     xd = torch.from_numpy(x).to(DEV).requires_grad_(True)
     out = conv(xd, torch.from_numpy(ei).to(DEV))
     out.square().sum().backward()
-    xr = torch.from_numpy(x).requires_grad_(True)
-    wr = conv.lin.weight.detach().cpu().requires_grad_(True)
-    br = conv.bias.detach().cpu().requires_grad_(True)
+    xr = torch.from_numpy(x).double().requires_grad_(True)           # float64 oracle: host-independent
+    wr = conv.lin.weight.detach().cpu().double().requires_grad_(True)
+    br = conv.bias.detach().cpu().double().requires_grad_(True)
     ref = orc.gcn_conv(xr, torch.from_numpy(ei), wr, br)
     ref.square().sum().backward()
-    assert (out.detach().cpu() - ref.detach()).abs().max().item() <= ATOL * max(1, ref.abs().max().item())
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= ATOL * max(1, ref.abs().max().item())
     for got, want in ((xd.grad, xr.grad), (conv.lin.weight.grad, wr.grad), (conv.bias.grad, br.grad)):
-        assert (got.cpu() - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+        assert (got.cpu().double() - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
 
 
 # ------------------------------------------------------------------ K2 / K4
@@ -746,18 +746,26 @@ def batch_to_double(b):
     return dg.GraphBatch(b.x.double(), b.edge_index, b.batch, b.ptr, b.y, b.num_graphs)
 
 
-def test_full_size_collab_properties():
-    """BASELINE config 4 at full size (512 graphs, ~2.4M edges): determinism,
-    sortedness of the pooled keys, batch-of-1 == batched, and direct oracle parity."""
+@pytest.mark.parametrize("path", ["fused", "per-layer"])
+def test_full_size_collab_properties(path):
+    """BASELINE config 4 at full size (512 graphs, ~2.4M edges) on BOTH CUDA paths (KS, and
+    K1 x 4 + K2): determinism, sortedness of the pooled keys, batch-of-1 == batched, and
+    direct oracle parity.  The batch carries no max_nodes hint (train.py:36-37)."""
     cfg = CONFIGS["collab"]
     batch = make_batch("collab")
     torch.manual_seed(324)
     model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
     data = batch.to(DEV)
-    g = model.build_graph(data)
-    with torch.no_grad():
-        pooled, xcat, perm = model.hot_path(data.x, g)
-        pooled2, xcat2, perm2 = model.hot_path(data.x, model.build_graph(data))
+    dg.set_fused(path == "fused")
+    try:
+        before = ops.LAUNCHES["stack_fwd"]
+        g = model.build_graph(data)
+        with torch.no_grad():
+            pooled, xcat, perm = model.hot_path(data.x, g)
+            pooled2, xcat2, perm2 = model.hot_path(data.x, model.build_graph(data))
+        assert ops.LAUNCHES["stack_fwd"] - before == (2 if path == "fused" else 0), "wrong kernel path"
+    finally:
+        dg.set_fused(True)
     assert torch.equal(xcat, xcat2) and torch.equal(perm, perm2) and torch.equal(pooled, pooled2)
     keys = pooled.view(cfg.batch_size, cfg.k, 97)[:, :, -1]
     valid = perm >= 0
@@ -774,8 +782,9 @@ def test_full_size_collab_properties():
     # oracle parity on x_cat
     ws = [c.lin.weight.detach().cpu() for c in (model.conv1, model.conv2, model.conv3, model.conv4)]
     bs = [c.bias.detach().cpu() for c in (model.conv1, model.conv2, model.conv3, model.conv4)]
-    ref = orc.graph_conv_stack(batch.x, batch.edge_index, ws, bs)
-    assert (xcat.cpu() - ref).abs().max().item() <= ATOL
+    ref = orc.graph_conv_stack(batch.x.double(), batch.edge_index, [w.double() for w in ws],
+                               [b.double() for b in bs])            # float64: host-independent
+    assert (xcat.cpu().double() - ref).abs().max().item() <= ATOL
     # batch-of-1 == batched for a few graphs
     graphs = make_graphs(cfg, cfg.batch_size, 324)
     for gi in (0, 17, 511):

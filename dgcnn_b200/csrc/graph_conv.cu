@@ -221,7 +221,7 @@ static int launch_aggregate(const AggParams& p, cudaStream_t st) {
 // block = (CX, 256/CX): x indexes the channel, y a row inside the block's slab
 __global__ void __launch_bounds__(256)
 gc_bwd_dpre(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy,
-            int cout, int64_t n, int act, float* __restrict__ dpre, float* __restrict__ db) {
+            int cout, int64_t n, int act, float* __restrict__ dpre, float* __restrict__ db_part) {
     __shared__ float red[256];
     const int c = threadIdx.x;
     const int rows_per_block = blockDim.y;
@@ -238,13 +238,39 @@ gc_bwd_dpre(const float* __restrict__ dy, int64_t lddy, const float* __restrict_
             part += g;
         }
     }
-    if (!db) return;
+    if (!db_part) return;
     red[threadIdx.y * blockDim.x + c] = part;
     __syncthreads();
     if (threadIdx.y == 0 && c < cout) {
         float s = 0.0f;
         for (int r = 0; r < rows_per_block; ++r) s += red[r * blockDim.x + c];
-        atomicAdd(&db[c], s);
+        db_part[(int64_t)blockIdx.x * cout + c] = s;     // summed in CTA order by gc_reduce_parts
+    }
+}
+
+// out[o] = sum over `parts` partial vectors, in a fixed order (no float atomics: the
+// gradients are bit-reproducible).  Block = 32 outputs x 8 part lanes.
+__global__ void __launch_bounds__(256)
+gc_reduce_parts(const float* __restrict__ part, int parts, int total, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int ox = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + ox;
+    float s0 = 0.f, s1 = 0.f;
+    if (o < total) {
+        int b = py;
+        for (; b + 8 < parts; b += 16) {
+            s0 += part[(int64_t)b * total + o];
+            s1 += part[(int64_t)(b + 8) * total + o];
+        }
+        if (b < parts) s0 += part[(int64_t)b * total + o];
+    }
+    red[py][ox] = s0 + s1;
+    __syncthreads();
+    if (py == 0 && o < total) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][ox];
+        out[o] = s;
     }
 }
 
@@ -254,7 +280,7 @@ gc_bwd_dpre(const float* __restrict__ dy, int64_t lddy, const float* __restrict_
 constexpr int kDwRows = 32;
 __global__ void __launch_bounds__(256)
 gc_bwd_dw(const float* __restrict__ dh, const float* __restrict__ x, int64_t ldx, int cin, int cout,
-          int64_t n, float* __restrict__ dw) {
+          int64_t n, float* __restrict__ dw_part) {
     extern __shared__ float smem[];
     float* sdh = smem;                   // [kDwRows][cout]
     float* sx = smem + kDwRows * cout;   // [kDwRows][cin]
@@ -290,22 +316,32 @@ gc_bwd_dw(const float* __restrict__ dh, const float* __restrict__ x, int64_t ldx
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m)
-        if (oc[m] >= 0) atomicAdd(&dw[oc[m] * cin + ok[m]], acc[m]);
+        if (oc[m] >= 0) dw_part[(int64_t)blockIdx.x * total + oc[m] * cin + ok[m]] = acc[m];
 }
 
 struct BwdWorkspace {
     float* dpre;
     float* dh;
+    float* db_part;   // [grid of gc_bwd_dpre][cout]
+    float* dw_part;   // [grid.x of gc_bwd_dw][cin * cout]
+    int grid_a, grid_c;
     size_t bytes;
 };
 
-__host__ inline BwdWorkspace carve_bwd_workspace(void* base, int64_t n, int cout) {
+__host__ inline BwdWorkspace carve_bwd_workspace(void* base, int64_t n, int cin, int cout) {
     BwdWorkspace w;
+    const int cx = (int)next_pow2((uint32_t)cout);
+    w.grid_a = grid_for(n, 256 / cx, 8);
+    w.grid_c = grid_for(ceil_div(n, kDwRows), 1, 2);
     size_t each = align_up(sizeof(float) * (size_t)n * (size_t)cout, 256);
+    size_t dbp = align_up(sizeof(float) * (size_t)w.grid_a * (size_t)cout, 256);
+    size_t dwp = align_up(sizeof(float) * (size_t)w.grid_c * (size_t)cin * (size_t)cout, 256);
     char* p = static_cast<char*>(base);
     w.dpre = reinterpret_cast<float*>(p);
     w.dh = reinterpret_cast<float*>(p ? p + each : nullptr);
-    w.bytes = 2 * each;
+    w.db_part = reinterpret_cast<float*>(p ? p + 2 * each : nullptr);
+    w.dw_part = reinterpret_cast<float*>(p ? p + 2 * each + dbp : nullptr);
+    w.bytes = 2 * each + dbp + dwp;
     return w;
 }
 
@@ -334,9 +370,8 @@ extern "C" int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin, co
 }
 
 extern "C" size_t dgcnn_graph_conv_bwd_workspace_bytes(int64_t num_nodes, int32_t cin, int32_t cout) {
-    (void)cin;
-    if (num_nodes < 0 || cout < 1) return 0;
-    return carve_bwd_workspace(nullptr, num_nodes, cout).bytes + 256;
+    if (num_nodes < 0 || cout < 1 || cin < 1) return 0;
+    return carve_bwd_workspace(nullptr, num_nodes, cin, cout).bytes + 256;
 }
 
 extern "C" int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy,
@@ -354,23 +389,28 @@ extern "C" int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* 
     if (cin > kMaxChannels || cout > kMaxChannels) return DGCNN_ERR_UNSUPPORTED;
     if (!dw || (dx && lddx < cin)) return DGCNN_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cin * cout, st) != cudaSuccess)
-        return DGCNN_ERR_CUDA;
-    if (db && cudaMemsetAsync(db, 0, sizeof(float) * (size_t)cout, st) != cudaSuccess)
-        return DGCNN_ERR_CUDA;
-    if (n == 0) return DGCNN_OK;
+    if (n == 0) {
+        if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cin * cout, st) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+        if (db && cudaMemsetAsync(db, 0, sizeof(float) * (size_t)cout, st) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+        return DGCNN_OK;
+    }
     if (!dy || !x || !rowptr_t || !dis || !weight) return DGCNN_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < dgcnn_graph_conv_bwd_workspace_bytes(n, cin, cout))
         return DGCNN_ERR_WORKSPACE;
     uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
-    BwdWorkspace w = carve_bwd_workspace(reinterpret_cast<void*>(aligned), n, cout);
+    BwdWorkspace w = carve_bwd_workspace(reinterpret_cast<void*>(aligned), n, cin, cout);
 
-    // A: dpre, db
+    // A: dpre, db (per-CTA partial sums, added in CTA order)
     int cx = (int)next_pow2((uint32_t)cout);
     dim3 block_a(cx, 256 / cx);
-    gc_bwd_dpre<<<grid_for(n, block_a.y, 8), block_a, 0, st>>>(dy, lddy, y, ldy, cout, n, act, w.dpre,
-                                                               db);
+    gc_bwd_dpre<<<w.grid_a, block_a, 0, st>>>(dy, lddy, y, ldy, cout, n, act, w.dpre, db ? w.db_part : nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (db) {
+        gc_reduce_parts<<<(cout + 31) / 32, 256, 0, st>>>(w.db_part, w.grid_a, cout, db);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
 
     // B: dh = A_hat^T dpre (kept dense for step C), dx (+)= dh W
     AggParams p{};
@@ -382,10 +422,12 @@ extern "C" int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* 
     int rc = launch_aggregate(p, st);
     if (rc != DGCNN_OK) return rc;
 
-    // C: dw = dh^T x
-    dim3 grid_c((unsigned)grid_for(ceil_div(n, kDwRows), 1, 2), (unsigned)ceil_div(cin * cout, 1024));
+    // C: dw = dh^T x (per-CTA partial products, added in CTA order)
+    dim3 grid_c((unsigned)w.grid_c, (unsigned)ceil_div(cin * cout, 1024));
     size_t smem_c = sizeof(float) * kDwRows * (size_t)(cin + cout);
-    gc_bwd_dw<<<grid_c, 256, smem_c, st>>>(w.dh, x, ldx, cin, cout, n, dw);
+    gc_bwd_dw<<<grid_c, 256, smem_c, st>>>(w.dh, x, ldx, cin, cout, n, w.dw_part);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    gc_reduce_parts<<<(cin * cout + 31) / 32, 256, 0, st>>>(w.dw_part, w.grid_c, cin * cout, dw);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

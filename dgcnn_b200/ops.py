@@ -311,7 +311,7 @@ def graph_conv_bwd(dy: Tensor, y: Optional[Tensor], x: Tensor, rowptr_t: Tensor,
             _ptr(dx), _rows(dx, "dx") if dx is not None else 0, int(bool(accumulate)),
             _ptr(dw), _ptr(db), cout, n, int(norm), int(act), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "graph_conv_bwd")
-    LAUNCHES["graph_conv_bwd"] += 3 if n > 0 else 0
+    LAUNCHES["graph_conv_bwd"] += (5 if need_db else 4) if n > 0 else 0
     return dw, db
 
 

@@ -148,8 +148,8 @@ def test_fused_trainer_step_collab_bs512_vs_float64_oracle():
     weights, biases = [c.lin.weight for c in convs], [c.bias for c in convs]
     tail = [m_seq.conv5.weight, m_seq.conv5.bias, m_seq.conv6.weight, m_seq.conv6.bias,
             m_seq.classifier_1.weight, m_seq.classifier_1.bias, m_seq.classifier_2.weight, m_seq.classifier_2.bias]
+    g = m_seq.build_graph(data)                        # grad mode on: the transposed CSR / maps are built too
     with torch.no_grad():
-        g = m_seq.build_graph(data)
         pooled, xcat, perm = ops.stack_fwd(data.x, g, weights, biases, k, 0)
         logp, saved = ops.tail_fwd(pooled, k, tail, True, m_seq._tail_seed, m_seq._tail_rng_offset.clone())
         stats, dlogp = ops.nll_sum(logp, data.y, 1.0, True)

@@ -101,6 +101,7 @@ SIGNATURES = {
     "dgcnn_stack_fwd_supported": (c_int32, [c_int32, c_int64]),
     "dgcnn_stack_fwd_workspace_bytes": (c_size_t, []),
     "dgcnn_stack_fwd_set_trace": (None, [c_void_p]),
+    "dgcnn_stack_fwd_configure": (None, [c_int32, c_int32]),
     "dgcnn_stack_fwd": (c_int32, [c_void_p, c_int64, c_int32,
                                   c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -25,8 +25,22 @@ struct Team {
     int tid, nthreads, warp, nwarps, lane;
     int bar;                 // named barrier id (1 + first quad of the group)
     unsigned char* smem;     // the group's slice of dynamic shared memory
-    __device__ __forceinline__ void sync() const {
+    // A graph that alone would outlast the rest of the launch is SPLIT over the two CTAs of a
+    // thread-block cluster (forward kernel): each CTA owns half of the 16-row tiles, keeps a full
+    // copy of the feature planes and writes its rows into both copies (distributed shared
+    // memory); the team is then all warps of BOTH CTAs and sync() is the cluster barrier.
+    int split = 0;           // 1: this graph is shared with the peer CTA of the cluster
+    int rank = 0;            // this CTA's rank in the pair
+    __device__ __forceinline__ void sync_local() const {
         asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
+    }
+    __device__ __forceinline__ void sync() const {
+        if (split) {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                         "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        } else {
+            sync_local();
+        }
     }
 };
 
@@ -105,32 +119,59 @@ __device__ __forceinline__ int graph_cost(int n) {
 template <class NeedFn>
 __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B, int nsm, int sm, int next,
                                           int& excl, bool first_pass, int budget, int total_warps,
-                                          NeedFn need_of, PlanEntry* s_plan, int* s_count) {
+                                          NeedFn need_of, PlanEntry* s_plan, int* s_count,
+                                          int& nsplit, bool pairs = false, int split_pct = 80) {
     const int lane = threadIdx.x & 31;
     int4 cand = make_int4(0, 0, 0, 0);                      // the eight largest graphs
-    if (first_pass && B > nsm) {
-        // fair share of one SM ~ (B / S) x mean cost; the median stands in for the mean
-        const int nmed = gdesc[B >> 1].z;
+    if (first_pass) {
+        excl = 0;
+        nsplit = 0;
+        // every CTA reads the same few KB of descriptors: pull them into L2 / L1 now, so that the
+        // dependent lookup below (position known only after the split decision) is not a second
+        // DRAM round trip
+        for (int i = lane * 8; i < B; i += 256)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gdesc + i));
         if (lane < 8 && lane < B) cand = gdesc[lane];
-        const int share = (int)fminf(1.25f * (float)graph_cost(nmed) * (float)B / (float)nsm, 2.0e9f);
-        const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && graph_cost(cand.z) > share);
-        excl = min(__ffs(~big) - 1, nsm / 2);               // leading run (sizes descend)
+        if (B > nsm) {
+            // fair share of one SM ~ (B / S) x mean cost; the median stands in for the mean
+            const int nmed = gdesc[B >> 1].z;
+            const int share = (int)fminf(1.25f * (float)graph_cost(nmed) * (float)B / (float)nsm, 2.0e9f);
+            const bool mine = lane < 8 && lane < B;
+            if (pairs) {                                    // leading run worth two SMs each
+                const int thr = (int)fminf((float)share * (float)split_pct * 0.01f, 2.0e9f);
+                const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, mine && graph_cost(cand.z) > thr);
+                nsplit = min(__ffs(~big) - 1, min(8, nsm / 4));
+            }
+            const uint32_t big1 = __ballot_sync(DGCNN_FULL_MASK, mine && lane >= nsplit &&
+                                                                    graph_cost(cand.z) > share) >> nsplit;
+            excl = min(__ffs(~big1) - 1, (nsm - 2 * nsplit) / 2);   // then: an SM of their own
+        } else if (pairs) {
+            // fewer graphs than SMs: the spare CTAs double up on the largest graphs (>= 8 row tiles)
+            const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && lane < B && cand.z > 112);
+            nsplit = min(__ffs(~big) - 1, min(8, nsm - B));
+            if (nsplit < 0) nsplit = 0;
+        }
     }
     excl = __shfl_sync(DGCNN_FULL_MASK, excl, 0);
+    nsplit = __shfl_sync(DGCNN_FULL_MASK, nsplit, 0);
     // lane j proposes the CTA's item next + j
     const int item = next + lane;
     int pos;
-    if (sm < excl) {
-        pos = item == 0 ? sm : B;
+    const bool is_split = sm < 2 * nsplit;
+    const int s1 = sm - 2 * nsplit, n1 = nsm - 2 * nsplit;
+    if (is_split) {
+        pos = item == 0 ? (sm >> 1) : B;
+    } else if (s1 < excl) {
+        pos = item == 0 ? nsplit + s1 : B;
     } else {
-        const int s2 = sm - excl, n2 = nsm - excl;
-        pos = excl + item * n2 + ((item & 1) ? n2 - 1 - s2 : s2);
+        const int s2 = s1 - excl, n2 = n1 - excl;
+        pos = nsplit + excl + item * n2 + ((item & 1) ? n2 - 1 - s2 : s2);
     }
     const bool valid = lane < kMaxTeams && pos < B;
     int4 d = make_int4(0, 0, 0, 0);
-    if (first_pass && sm < excl) {
-        // a graph with an SM of its own is one of the candidates just loaded: no second round trip
-        const int src = sm & 31;
+    if (first_pass && (is_split || s1 < excl)) {
+        // a graph with SMs of its own is one of the candidates just loaded: no second round trip
+        const int src = (is_split ? (sm >> 1) : nsplit + s1) & 31;
         d.x = __shfl_sync(DGCNN_FULL_MASK, cand.x, src); d.y = __shfl_sync(DGCNN_FULL_MASK, cand.y, src);
         d.z = __shfl_sync(DGCNN_FULL_MASK, cand.z, src); d.w = __shfl_sync(DGCNN_FULL_MASK, cand.w, src);
         if (!valid) d = make_int4(0, 0, 0, 0);
@@ -158,6 +199,7 @@ __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B,
         if (member)
             w = min(T, 1 + (int)((float)(total_warps - count) * (float)cost / (float)max(total, 1) - 1e-3f));
     }
+    if (is_split && member) w = total_warps;               // the cluster barrier wants every warp
     const int used = (int)__reduce_add_sync(DGCNN_FULL_MASK, (unsigned)w);
     for (int spare = total_warps - used; spare > 0 && count > 0; --spare) {
         const uint32_t lat = (member && w < T) ? (uint32_t)layer_latency(T, w) : 0u;
@@ -174,7 +216,7 @@ __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B,
     if (member) {
         PlanEntry e;
         e.gi = d.x; e.base = d.y; e.n = n; e.fgoff = d.w;
-        e.warp0 = winc - w; e.nwarps = w; e.smem_off = incl - need; e.pad = 0;
+        e.warp0 = winc - w; e.nwarps = w; e.smem_off = incl - need; e.pad = is_split ? 1 : 0;
         s_plan[lane] = e;
     }
     if (lane == 0) *s_count = count;

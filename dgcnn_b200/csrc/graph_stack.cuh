@@ -30,6 +30,8 @@ struct StackFwdParams {
     int32_t* counter;   // work queue head, zeroed by the host wrapper
     int32_t* status;    // optional
     int64_t* trace;     // optional debug timeline, [num_graphs][16] (dgcnn_stack_fwd_set_trace)
+    int pairs;          // tensor-core variant: launched as clusters of two CTAs (largest graphs are split)
+    int split_pct;      // split a graph whose cost exceeds this percentage of an SM's fair share
 };
 
 

@@ -653,12 +653,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
     const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
     constexpr int kWarps = kBwdThreads / 32;
     const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
-    int next = 0, excl = 0;
+    int next = 0, excl = 0, nsplit = 0;              // (no cluster split in the backward kernel)
 
     for (int pass = 0;; ++pass) {
         if (warp_id == 0) {
             plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
-                      [f](int np) { return bwd_team_layout(f, np).total; }, s_plan, &s_count);
+                      [f](int np) { return bwd_team_layout(f, np).total; }, s_plan, &s_count, nsplit);
         } else if (pass == 0) {
             const int tid = threadIdx.x - 32, nthreads = kBwdThreads - 32;
             __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);

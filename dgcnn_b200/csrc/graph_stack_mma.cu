@@ -30,8 +30,13 @@
 // tiles of M >= 64/128 rows in descriptor layouts plus a TMEM round trip per tile, which
 // would waste most of each tile on 75-node graphs.  The kernel is bound by issue slots and
 // latency, not by the tensor pipe (profiles/).
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "graph_mma.cuh"
 #include "sort_key.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dgcnn {
 
@@ -117,7 +122,6 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
 }
 
 // Optional per-graph timeline (debug hook dgcnn_stack_fwd_set_trace): clock64 at phase ends.
-#define KS_TRACE(slot) do { if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ int64_t global_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -223,7 +227,8 @@ __device__ __forceinline__ void project32(const float (&acc)[4][4], const __half
 __device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][4], int mt, int lane,
                                                float* __restrict__ xo, int64_t ldc, bool vec2,
                                                __half* __restrict__ out_pl, __half* __restrict__ vpl,
-                                               const float* __restrict__ w4s) {
+                                               const float* __restrict__ w4s,
+                                               __half* out_pl_peer = nullptr, __half* vpl_peer = nullptr) {
     const int g = lane >> 2, t = lane & 3;
     const int row0 = mt * 16 + g, row1 = row0 + 8;
 #pragma unroll
@@ -250,13 +255,18 @@ __device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][
     if (out_pl) {
         uint32_t* o0 = reinterpret_cast<uint32_t*>(out_pl + row0 * kRowH) + t;
         uint32_t* o1 = reinterpret_cast<uint32_t*>(out_pl + row1 * kRowH) + t;
+        // split graph: the same rows go into the peer CTA's copy (distributed shared memory)
+        uint32_t* q0 = out_pl_peer ? reinterpret_cast<uint32_t*>(out_pl_peer + row0 * kRowH) + t : nullptr;
+        uint32_t* q1 = out_pl_peer ? reinterpret_cast<uint32_t*>(out_pl_peer + row1 * kRowH) + t : nullptr;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             uint32_t hi, lo;
             split_pair(c0 * y[nt][0], c0 * y[nt][1], hi, lo);
             o0[nt * 4] = hi; o0[16 + nt * 4] = lo;
+            if (q0) { q0[nt * 4] = hi; q0[16 + nt * 4] = lo; }
             split_pair(c1 * y[nt][2], c1 * y[nt][3], hi, lo);
             o1[nt * 4] = hi; o1[16 + nt * 4] = lo;
+            if (q1) { q1[nt * 4] = hi; q1[16 + nt * 4] = lo; }
         }
     }
     if (vpl) {
@@ -274,8 +284,26 @@ __device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][
         if (t == 0) {
             store_split(vpl, vpl + c.S, row0, c0 * p0);
             store_split(vpl, vpl + c.S, row1, c1 * p1);
+            if (vpl_peer) {
+                store_split(vpl_peer, vpl_peer + c.S, row0, c0 * p0);
+                store_split(vpl_peer, vpl_peer + c.S, row1, c1 * p1);
+            }
         }
     }
+}
+
+// zeros over [beg, end) of a float array, 16-byte stores where the alignment allows (the array
+// itself is only 4-byte aligned: rows of 97 floats); strided over `nthreads` threads
+__device__ __forceinline__ void zero_fill(float* __restrict__ base, int beg, int end, int tid, int nthreads) {
+    if (beg >= end) return;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(base + beg);
+    const int head = min(end - beg, (int)(((16u - (unsigned)(a0 & 15u)) & 15u) >> 2));
+    const int body4 = (end - beg - head) >> 2;
+    if (tid < head) base[beg + tid] = 0.f;
+    float4* b4 = reinterpret_cast<float4*>(base + beg + head);
+    for (int i = tid; i < body4; i += nthreads) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tail0 = beg + head + 4 * body4;
+    if (tid < end - tail0) base[tail0 + tid] = 0.f;
 }
 
 __device__ __forceinline__ void load_bias(const float* __restrict__ bias, int t, float (&y)[4][4]) {
@@ -286,7 +314,10 @@ __device__ __forceinline__ void load_bias(const float* __restrict__ bias, int t,
     }
 }
 
-// model.py:28-35 for ONE graph, executed by one team
+// model.py:28-35 for ONE graph, executed by one team.  A SPLIT graph (tm.split) is executed by
+// the two CTAs of a cluster together: CTA `tm.rank` owns the row tiles [t0, t1), every plane /
+// key / order store of its rows also goes into the peer's shared memory, and the team barrier
+// is the cluster barrier.
 __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Team& tm, const PlanEntry& e,
                                               const unsigned char* shraw) {
     const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
@@ -305,8 +336,20 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     const int keep = min(n, p.k);
     float* __restrict__ pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
     int32_t* __restrict__ perm_g = p.perm + (int64_t)gi * p.k;
+    // the two CTAs of a split graph act as one team of 2 x nthreads threads wherever the work is
+    // per element (sort, copy-out, padding): gtid / gthreads / gwarp / gwarps
+    const bool split = tm.split != 0;
+    const int rank = split ? tm.rank : 0, ways = split ? 2 : 1;
+    const int gtid = tid + rank * nthreads, gthreads = ways * nthreads;
+    const int gwarp = warp + rank * nwarps, gwarps = ways * nwarps;
+    const bool tracer = p.trace && tm.tid == 0 && rank == 0;
+#define KS_TRACE(slot) do { if (tracer) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
+    // rows of `pooled` past the graph's last node: zeros (PyG's fill trick), perm -1.  Plain
+    // stores, issued first: they drain while the team waits for its inputs.
+    zero_fill(pooled_g, keep * kCat, p.k * kCat, gtid, gthreads);
+    for (int r = keep + gtid; r < p.k; r += gthreads) perm_g[r] = -1;
     if (n == 0) return;
-    if (p.trace && tm.tid == 0) {
+    if (tracer) {
         uint32_t smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         p.trace[(int64_t)gi * 16 + 15] = ((int64_t)smid << 32) | (uint32_t)(tm.nthreads | (n << 12));
@@ -317,6 +360,8 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     GraphCtx c;
     c.n = n; c.np = (n + 15) & ~15; c.T = c.np >> 4; c.G = (c.T + 3) >> 2; c.base = base;
     const int np = c.np;
+    const int t0 = split ? (rank ? (c.T + 1) >> 1 : 0) : 0;          // this CTA's row tiles
+    const int t1 = split ? (rank ? c.T : (c.T + 1) >> 1) : c.T;
     const TeamLayout L = team_layout(f, np);
     c.S = L.S;
     const int S = L.S;
@@ -334,6 +379,19 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     float* stage = reinterpret_cast<float*>(PB);        // layer-1 inputs c_j x_j, fp32 [n][f] (F <= 8)
     float* wmax = reinterpret_cast<float*>(vpl);        // per-warp max |c_j x_j|
     c.fbm = fbm; c.cs = cs; c.rs = rs; c.rp = rp;
+    // the peer CTA's copies (same offsets in its shared memory)
+    __half *PA_peer = nullptr, *PB_peer = nullptr, *vpl_peer = nullptr;
+    float* key_peer = nullptr;
+    int* order_peer = nullptr;
+    if (split) {
+        cg::cluster_group cluster = cg::this_cluster();
+        const unsigned peer = (unsigned)(rank ^ 1);
+        PA_peer = cluster.map_shared_rank(PA, peer);
+        PB_peer = cluster.map_shared_rank(PB, peer);
+        vpl_peer = cluster.map_shared_rank(vpl, peer);
+        key_peer = cluster.map_shared_rank(key, peer);
+        order_peer = cluster.map_shared_rank(order, peer);
+    }
 
     float* xc = p.xcat + (int64_t)base * p.ldc;
     const bool vec2 = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.xcat) & 7) == 0);
@@ -342,7 +400,8 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
 
     // ---- phase 0, one DRAM round trip: adjacency fragments (K0b), coefficients, inputs ----
     c.dup = (p.gflags[gi] & 1) != 0;                 // multigraph: walk the CSR instead
-    load_bitmap<8>(p.fragmap + e.fgoff, fbm, frag_words(np), tid, nthreads);
+    load_bitmap<8>(p.fragmap + e.fgoff + t0 * c.G * 32, fbm + t0 * c.G * 32, (t1 - t0) * c.G * 32, tid,
+                   nthreads);                            // (only the CTA's own row tiles)
     for (int j = tid; j < np; j += nthreads) {
         const float d = j < n ? p.dis[base + j] : 0.f;
         cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
@@ -366,7 +425,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
         for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
     }
     c.col_g = p.col + e0;
-    tm.sync();
+    tm.sync();            // (split: also tells that the peer CTA runs -- its shared memory may be written)
     KS_TRACE(1);
 
     float pow2 = 1.f;
@@ -387,7 +446,8 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
             store_split(xs, xs + f * S, idx, j < n ? stage[j * f + k] * inv : 0.f);
         }
     } else {
-        // F > 8: project first (FMA), c_j (x_j W1^T) as planes in PB
+        // F > 8: project first (FMA), c_j (x_j W1^T) as planes in PB (a split graph: both CTAs
+        // compute all rows -- cheaper than an exchange)
         for (int j = warp; j < np; j += nwarps) {
             float acc = 0.f;
             if (j < n) {
@@ -399,7 +459,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
             store_split(PB + j * kRowH, PB + j * kRowH + kHid, lane, acc);
         }
     }
-    tm.sync();
+    tm.sync_local();
     KS_TRACE(2);
 
     // ---- layers 1..3: aggregate on the tensor cores, project, tanh ------------------------
@@ -407,11 +467,12 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     for (int layer = 0; layer < 3; ++layer) {
         const __half* in_pl = layer == 1 ? PA : PB;
         __half* out_pl = layer == 0 ? PA : (layer == 1 ? PB : nullptr);
+        __half* out_peer = layer == 0 ? PA_peer : (layer == 1 ? PB_peer : nullptr);
         const __half* wp = layer == 1 ? w2p : w3p;
         const float* bias = b1s + layer * kHid;
         float* xo = xc + layer * kHid;
 #pragma unroll 1
-        for (int mt = warp; mt < c.T; mt += nwarps) {
+        for (int mt = t0 + warp; mt < t1; mt += nwarps) {
             float y[4][4];
             load_bias(bias, t, y);
             if (layer == 0 && small_f) {
@@ -448,14 +509,15 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
                     project32(acc, wp, lane, y);
                 }
             }
-            layer_epilogue(c, y, mt, lane, xo, p.ldc, vec2, out_pl, layer == 2 ? vpl : nullptr, w4s);
+            layer_epilogue(c, y, mt, lane, xo, p.ldc, vec2, out_pl, layer == 2 ? vpl : nullptr, w4s, out_peer,
+                           layer == 2 ? vpl_peer : nullptr);
         }
         tm.sync();
         KS_TRACE(3 + layer);
     }
 
     // ---- layer 4: 32 -> 1, already projected into v: one MMA column -------------------
-    for (int mt = warp; mt < c.T; mt += nwarps) {
+    for (int mt = t0 + warp; mt < t1; mt += nwarps) {
         float a4[4];
         aggregate8(c, vpl, S, 1, mt, lane, a4);
         if (t == 0) {                                  // column 0 of the tile lives in t == 0
@@ -465,6 +527,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
                 if (row < n) {
                     const float x4 = tanhf(fmaf(rs[row], a4[2 * half], b4));
                     key[row] = x4;
+                    if (key_peer) key_peer[row] = x4;
                     float* o = xc + (int64_t)row * p.ldc + 3 * kHid;
                     // padded rows (ldc >= 100, 16-byte aligned): write the pad too, so that no
                     // 32-byte sector of x_cat is left partially written (a later read of such a
@@ -483,42 +546,49 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     if (n <= kRankSortMax) {
         for (int j = tid; j < n; j += nthreads)
             comp[j] = ((uint64_t)descending_key_bits(key[j]) << 32) | (uint32_t)j;
-        tm.sync();
+        tm.sync_local();
         // rank = number of smaller composites; `parts` lanes share one element (interleaved j)
         int parts = 1;
-        while (parts < 32 && n * parts * 2 <= nthreads) parts <<= 1;
+        while (parts < 32 && n * parts * 2 <= gthreads) parts <<= 1;
         const int lp = 31 - __clz(parts);
-        for (int it0 = 0; it0 < n * parts; it0 += nthreads) {
-            const int item = it0 + tid;
+        for (int it0 = 0; it0 < n * parts; it0 += gthreads) {
+            const int item = it0 + gtid;
             const int i = item >> lp, part = item & (parts - 1);
             const bool live = i < n;
             const uint64_t mine = live ? comp[i] : 0ull;
-            int rank = 0;
+            int rnk = 0;
             if (live) {
                 int j = part, r1 = 0, r2 = 0, r3 = 0;                // four independent count chains
                 for (; j + 7 * parts < n; j += 8 * parts) {          // eight independent loads in flight
                     uint64_t o[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] = comp[j + u * parts];
-                    rank += (o[0] < mine) + (o[4] < mine);
+                    rnk += (o[0] < mine) + (o[4] < mine);
                     r1 += (o[1] < mine) + (o[5] < mine);
                     r2 += (o[2] < mine) + (o[6] < mine);
                     r3 += (o[3] < mine) + (o[7] < mine);
                 }
-                for (; j < n; j += parts) rank += comp[j] < mine;
-                rank += r1 + r2 + r3;
+                for (; j < n; j += parts) rnk += comp[j] < mine;
+                rnk += r1 + r2 + r3;
             }
-            for (int o = parts >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(DGCNN_FULL_MASK, rank, o);
-            if (live && part == 0 && rank < keep) order[rank] = i;
+            for (int o = parts >> 1; o > 0; o >>= 1) rnk += __shfl_xor_sync(DGCNN_FULL_MASK, rnk, o);
+            if (live && part == 0 && rnk < keep) {
+                order[rnk] = i;
+                if (order_peer) order_peer[rnk] = i;
+            }
         }
+        tm.sync();
     } else {
+        // (a split graph sorts redundantly in both CTAs: no exchange)
         const uint32_t pw = next_pow2((uint32_t)n);
         for (uint32_t j = tid; j < pw; j += nthreads)
             comp[j] = (j < (uint32_t)n) ? (((uint64_t)descending_key_bits(key[j]) << 32) | j) : ~0ull;
-        bitonic_sort_team(comp, pw, tm);
+        Team local = tm;
+        local.split = 0;
+        bitonic_sort_team(comp, pw, local);
         for (int r = tid; r < keep; r += nthreads) order[r] = (int)(uint32_t)(comp[r] & 0xffffffffu);
+        tm.sync_local();
     }
-    tm.sync();
     KS_TRACE(7);
 
     // ---- the k winners, one warp per row (rows of x_cat this team just wrote: L2 hits);
@@ -527,7 +597,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     {
         const float* __restrict__ xsrc = xc;
         constexpr int R = 16;
-        for (int r0 = warp * R; r0 < keep; r0 += nwarps * R) {
+        for (int r0 = gwarp * R; r0 < keep; r0 += gwarps * R) {
             float v[R][3], v96;
 #pragma unroll
             for (int u = 0; u < R; ++u) {
@@ -545,9 +615,10 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
             if (lane < R && r0 + lane < keep) pooled_g[(r0 + lane) * kCat + 96] = v96;
         }
     }
-    for (int r = tid; r < keep; r += nthreads) perm_g[r] = base + order[r];
+    for (int r = gtid; r < keep; r += gthreads) perm_g[r] = base + order[r];
     KS_TRACE(8);
-    if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + 10] = global_ns();
+    if (tracer) p.trace[(int64_t)gi * 16 + 10] = global_ns();
+#undef KS_TRACE
 }
 
 // The CTA's graphs and their teams: plan_pass() in graph_mma.cuh.
@@ -568,11 +639,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
     const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);      // {graph, base, n, fgoff}
     int next = 0;                                    // items of this CTA consumed so far
     int excl = 0;                                    // graphs with an SM of their own (warp 0 only)
+    int nsplit = 0;                                  // graphs split over a CTA pair (warp 0 only)
+    uint32_t crank = 0;                              // rank of this CTA in its cluster
+    if (p.pairs) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
 
     for (int pass = 0;; ++pass) {
         if (warp_id == 0) {
             plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
-                      [f](int np) { return team_layout(f, np).total; }, s_plan, &s_count);
+                      [f](int np) { return team_layout(f, np).total; }, s_plan, &s_count, nsplit,
+                      p.pairs != 0, p.split_pct);
         } else if (pass == 0) {
             // meanwhile the other warps stage the weights: W1 transposed fp32 (F -> 32 stays on
             // the FMA pipe), W2/W3 as hi/lo fp16 planes [cout][cin] = the MMA "col" operand
@@ -621,15 +696,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
         const int count = s_count;
         if (count == 0) break;
         if (p.trace) cta_c1 = clock64();
-        // rows of `pooled` past each graph's last node: zeros (PyG's fill trick), perm -1.
-        // Done by the whole CTA: a one-warp team would spend longer on this than on its graph.
-        for (int j = 0; j < count; ++j) {
-            const int gi = s_plan[j].gi, keep = min(s_plan[j].n, p.k);
-            float* pooled_g = p.pooled + (int64_t)gi * p.k * kCat;
-            int32_t* perm_g = p.perm + (int64_t)gi * p.k;
-            for (int idx = keep * kCat + threadIdx.x; idx < p.k * kCat; idx += kFwdThreads) pooled_g[idx] = 0.f;
-            for (int r = keep + threadIdx.x; r < p.k; r += kFwdThreads) perm_g[r] = -1;
-        }
         int mine = -1;
         for (int j = 0; j < count; ++j)
             if (warp_id >= s_plan[j].warp0 && warp_id < s_plan[j].warp0 + s_plan[j].nwarps) mine = j;
@@ -646,7 +712,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
                 tm.lane = lane;
                 tm.bar = 1 + mine;
                 tm.smem = team_base + e.smem_off;
-                if (p.trace && tm.tid == 0) {
+                tm.split = e.pad;                    // shared with the peer CTA of the cluster
+                tm.rank = (int)crank;
+                if (p.trace && tm.tid == 0 && (!tm.split || crank == 0)) {
                     cta_c2 = clock64();
                     p.trace[(int64_t)e.gi * 16 + 11] = cta_t0;
                     p.trace[(int64_t)e.gi * 16 + 12] = cta_c0;       // CTA entry
@@ -679,6 +747,12 @@ int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes);
 
 static int64_t* g_trace = nullptr;
 extern "C" void dgcnn_stack_fwd_set_trace(int64_t* device_buffer) { g_trace = device_buffer; }
+
+static int g_pairs_ok = -1, g_split_pct = 80;
+extern "C" void dgcnn_stack_fwd_configure(int32_t pairs, int32_t split_pct) {
+    g_pairs_ok = pairs < 0 ? -1 : (pairs ? 2 : 0);      // 2: requested, still to be probed
+    if (split_pct > 0) g_split_pct = split_pct;
+}
 
 static int mma_supported(int32_t f, int64_t max_nodes) {
     if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
@@ -746,9 +820,52 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
+    // Clusters of two CTAs (one TPC): the plan splits the largest graphs of the batch over a pair
+    // (planes exchanged through distributed shared memory), everything else runs as before.
+    // DGCNN_KS_PAIRS=0 launches without clusters; DGCNN_KS_SPLIT_PCT tunes the split threshold.
+    if (g_pairs_ok < 0 || g_pairs_ok == 2) {
+        int ok = 1;
+        if (g_pairs_ok < 0) {
+            const char* env = getenv("DGCNN_KS_PAIRS");
+            const char* pct = getenv("DGCNN_KS_SPLIT_PCT");
+            if (pct && atoi(pct) > 0) g_split_pct = atoi(pct);
+            ok = !(env && env[0] == '0');
+        }
+        if (ok) {
+            cudaLaunchConfig_t probe{};
+            cudaLaunchAttribute pattr[1];
+            pattr[0].id = cudaLaunchAttributeClusterDimension;
+            pattr[0].val.clusterDim.x = 2; pattr[0].val.clusterDim.y = 1; pattr[0].val.clusterDim.z = 1;
+            probe.gridDim = dim3(DGCNN_NUM_SMS); probe.blockDim = dim3(kFwdThreads);
+            probe.dynamicSmemBytes = smem; probe.attrs = pattr; probe.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, stack_fwd_mma_kernel, &probe) != cudaSuccess ||
+                2 * nclusters < DGCNN_NUM_SMS) {
+                cudaGetLastError();
+                ok = 0;                              // every pair must be co-resident in ONE wave
+            }
+        }
+        g_pairs_ok = ok;
+    }
+    p.pairs = g_pairs_ok;
+    p.split_pct = g_split_pct;
     int64_t grid = DGCNN_NUM_SMS;
-    if (grid > num_graphs) grid = num_graphs;
-    stack_fwd_mma_kernel<<<(unsigned)grid, kFwdThreads, smem, st>>>(p);
+    if (p.pairs) {
+        // fewer graphs than SMs: up to 8 spare CTAs double up on the largest graphs
+        if (grid > num_graphs + 8) grid = num_graphs + 8;
+        grid += grid & 1;
+        if (grid > DGCNN_NUM_SMS) grid = DGCNN_NUM_SMS;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFwdThreads);
+        cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, stack_fwd_mma_kernel, p) != cudaSuccess) return DGCNN_ERR_CUDA;
+    } else {
+        if (grid > num_graphs) grid = num_graphs;
+        stack_fwd_mma_kernel<<<(unsigned)grid, kFwdThreads, smem, st>>>(p);
+    }
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

@@ -228,6 +228,14 @@ int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes);
  * its phases per graph (slots 0-8) and (smid << 32 | team threads | n << 12) in slot 15.
  * Pass NULL to switch it off.  Used by scripts/trace_stack_fwd.py. */
 void dgcnn_stack_fwd_set_trace(int64_t* device_buffer);
+/* Tuning / test hook of the tensor-core KS kernel.  It is launched as thread-block clusters of
+ * two CTAs and splits the largest graphs of a batch over a CTA pair (each CTA owns half of the
+ * 16-row tiles; planes, keys and ranks are exchanged through distributed shared memory).
+ * pairs: 1 clusters (default when the device can co-schedule all pairs), 0 plain launch,
+ * -1 probe again (also re-reads DGCNN_KS_PAIRS / DGCNN_KS_SPLIT_PCT); split_pct > 0: split a
+ * graph whose cost exceeds this percentage of one SM's fair share of the batch (default 80).
+ * Results are bit-identical either way (tests/test_gpu_headline.py). */
+void dgcnn_stack_fwd_configure(int32_t pairs, int32_t split_pct);
 size_t dgcnn_stack_fwd_workspace_bytes(void);
 int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                     const int32_t* rowptr, const int32_t* col, const float* dis,

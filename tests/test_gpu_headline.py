@@ -311,3 +311,33 @@ def test_reference_forward_body_with_our_modules_builds_the_graph_once():
     assert torch.equal(pooled.detach().cpu(), opool)
     pooled.sum().backward()
     assert model.conv1.lin.weight.grad is not None and torch.isfinite(model.conv1.lin.weight.grad).all()
+
+
+# ---------------------------------------------------------------- cluster-pair split of the largest graphs
+@pytest.mark.parametrize("name,count", [("collab", 512), ("proteins", 128), ("proteins", 20), ("collab", 3)])
+def test_cluster_split_is_bit_identical_to_the_plain_launch(name, count):
+    """KS launched as clusters of two CTAs (largest graphs split over a pair, planes exchanged
+    through distributed shared memory) against the same kernel launched without clusters:
+    x_cat, perm and pooled bit for bit; also with an aggressive split threshold."""
+    from dgcnn_b200 import _lib
+    lib = _lib.load_library()
+    cfg = CONFIGS[name]
+    batch = make_batch(name, num_graphs=count, seed=77)
+    torch.manual_seed(1)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    data = batch.to(DEV)
+    outs = []
+    try:
+        for pairs, pct in ((0, 80), (1, 80), (1, 20)):
+            lib.dgcnn_stack_fwd_configure(pairs, pct)
+            with torch.no_grad():
+                g = model.build_graph(data)
+                pooled, xcat, perm = model.hot_path(data.x, g)
+            g.check()
+            torch.cuda.synchronize()
+            outs.append((pooled.clone(), xcat.clone(), perm.clone()))
+    finally:
+        lib.dgcnn_stack_fwd_configure(-1, 80)
+    for got in outs[1:]:
+        for a, b_ in zip(outs[0], got):
+            assert torch.equal(a, b_)

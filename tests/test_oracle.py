@@ -248,7 +248,11 @@ def test_property_batch_of_one_equals_batched(graphs, k):
         np.testing.assert_allclose(xcat[lo:hi].numpy(), own.numpy(), rtol=0, atol=1e-13)
         own_pool, own_perm = orc.sort_aggregation(own, torch.zeros(hi - lo, dtype=torch.long), k, 1, return_perm=True)
         np.testing.assert_allclose(pooled[g].numpy(), own_pool[0].numpy(), rtol=0, atol=1e-13)
-        assert torch.equal(torch.where(perm[g] >= 0, perm[g] - lo, perm[g]), own_perm[0])
+        # ranks are only defined up to rounding when two keys agree to ~1e-13 (the two runs sum in
+        # different orders); the pooled rows were compared above
+        ks = torch.sort(own[:, -1], descending=True).values
+        if hi - lo < 2 or float((ks[:-1] - ks[1:]).min()) > 1e-9:
+            assert torch.equal(torch.where(perm[g] >= 0, perm[g] - lo, perm[g]), own_perm[0])
 
 
 @settings(max_examples=25, deadline=None)

@@ -112,6 +112,34 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int32,
                                   c_int32, c_int32, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
+    "dgcnn_stack_fwd_conv5_supported": (c_int32, [c_int32, c_int64]),
+    "dgcnn_stack_fwd_conv5": (c_int32, [c_void_p, c_int64, c_int32,
+                                        c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p,
+                                        c_int64, c_int64, c_int64,
+                                        c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p,
+                                        c_void_p, c_int64, c_void_p, c_void_p, c_int32,
+                                        c_void_p, c_void_p, c_int32, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    "dgcnn_stack_bwd_conv5_supported": (c_int32, [c_int32, c_int64]),
+    "dgcnn_stack_conv5_num_params": (c_int64, [c_int32]),
+    "dgcnn_stack_bwd_conv5": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32,
+                                        c_void_p, c_int64, c_void_p, c_int64,
+                                        c_int32, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p,
+                                        c_int64, c_int64, c_int64,
+                                        c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int32, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    "dgcnn_tail_bwd_h1": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_void_p] * 7 +
+                          [c_int32, c_void_p, c_size_t, c_void_p]),
     "dgcnn_stack_bwd_supported": (c_int32, [c_int32, c_int64]),
     "dgcnn_stack_bwd_set_trace": (None, [c_void_p]),
     "dgcnn_stack_num_params": (c_int64, [c_int32]),

@@ -773,7 +773,8 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     if (B < 0 || k < 10 || num_classes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_classes > 32) return DGCNN_ERR_UNSUPPORTED;
     if (B == 0) return DGCNN_OK;
-    if (!pooled || !w5 || !b5 || !w6 || !b6 || !wf1 || !bf1 || !wf2 || !bf2 || !h1 || !arg || !h2 ||
+    // pooled == NULL: h1 / arg were already produced by dgcnn_stack_fwd_conv5
+    if ((pooled && (!w5 || !b5)) || !w6 || !b6 || !wf1 || !bf1 || !wf2 || !bf2 || !h1 || !arg || !h2 ||
         !h3 || !keep || !logp)
         return DGCNN_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < dgcnn_tail_workspace_bytes(B, k, num_classes))
@@ -783,12 +784,14 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* slabs = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 
-    if (cudaFuncSetAttribute(tail_c5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)kC5StageBytes) != cudaSuccess)
-        return DGCNN_ERR_CUDA;
-    tail_c5_fwd<<<grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st>>>(pooled, B, k, d.L1, w5, b5, h1,
-                                                                             arg);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (pooled) {
+        if (cudaFuncSetAttribute(tail_c5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kC5StageBytes) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+        tail_c5_fwd<<<grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st>>>(pooled, B, k, d.L1, w5, b5, h1,
+                                                                                 arg);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
     const size_t smem6 = sizeof(float) * (kC5 * kK6 * kC6 + kC6 + kC5 * (d.L1 + 8) + kC6 * d.L2);
     if (smem6 > 96 * 1024) return DGCNN_ERR_UNSUPPORTED;
     if (smem6 > 48 * 1024 &&
@@ -833,37 +836,40 @@ static SideStream* side_stream() {
     return &s;
 }
 
-extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, int32_t k,
-                              const float* w5, const float* w6, const float* wf1, const float* wf2,
-                              int32_t num_classes, const float* h1, const uint8_t* arg, const float* h2,
-                              const float* h3, const uint8_t* keep, const float* logp, float* dpooled,
-                              float* dw5, float* db5, float* dw6, float* db6, float* dwf1, float* dbf1,
-                              float* dwf2, float* dbf2, int32_t overlap, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+// dh1_ext != NULL: stop at d(h1) (written there); conv5's backward -- dpooled, dw5, db5 -- is then
+// done by the caller (dgcnn_stack_bwd_conv5) and pooled / dpooled / dw5 / db5 are unused.
+static int tail_bwd_impl(const float* dlogp, const float* pooled, int64_t num_graphs, int32_t k,
+                         const float* w5, const float* w6, const float* wf1, const float* wf2,
+                         int32_t num_classes, const float* h1, const uint8_t* arg, const float* h2,
+                         const float* h3, const uint8_t* keep, const float* logp, float* dpooled,
+                         float* dw5, float* db5, float* dw6, float* db6, float* dwf1, float* dbf1,
+                         float* dwf2, float* dbf2, int32_t overlap, void* workspace,
+                         size_t workspace_bytes, void* stream, bool to_h1, float* dh1_ext) {
     const int64_t B = num_graphs;
     if (B < 0 || k < 10 || num_classes < 1 || overlap < 0 || overlap > 2) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_classes > 32) return DGCNN_ERR_UNSUPPORTED;
-    if (!dw5 || !db5 || !dw6 || !db6 || !dwf1 || !dbf1 || !dwf2 || !dbf2) return DGCNN_ERR_INVALID_ARGUMENT;
+    if ((!to_h1 && (!dw5 || !db5)) || !dw6 || !db6 || !dwf1 || !dbf1 || !dwf2 || !dbf2)
+        return DGCNN_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < dgcnn_tail_workspace_bytes(B, k, num_classes))
         return DGCNN_ERR_WORKSPACE;
     const TailDims d = tail_dims(k);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B == 0) {
-        cudaMemsetAsync(dw5, 0, sizeof(float) * kC5 * kKW, st);  cudaMemsetAsync(db5, 0, sizeof(float) * kC5, st);
+        if (!to_h1) { cudaMemsetAsync(dw5, 0, sizeof(float) * kC5 * kKW, st);  cudaMemsetAsync(db5, 0, sizeof(float) * kC5, st); }
         cudaMemsetAsync(dw6, 0, sizeof(float) * kC6 * kC5 * kK6, st);  cudaMemsetAsync(db6, 0, sizeof(float) * kC6, st);
         cudaMemsetAsync(dwf1, 0, sizeof(float) * kFc * d.D1, st);  cudaMemsetAsync(dbf1, 0, sizeof(float) * kFc, st);
         cudaMemsetAsync(dwf2, 0, sizeof(float) * num_classes * kFc, st);
         cudaMemsetAsync(dbf2, 0, sizeof(float) * num_classes, st);
         return DGCNN_OK;
     }
-    if (!dlogp || !pooled || !w5 || !w6 || !wf1 || !wf2 || !h1 || !arg || !h2 || !h3 || !keep || !logp ||
-        !dpooled)
+    if (!dlogp || (!to_h1 && (!pooled || !w5 || !dpooled || !arg)) || !w6 || !wf1 || !wf2 || !h1 || !h2 || !h3 ||
+        !keep || !logp)
         return DGCNN_ERR_INVALID_ARGUMENT;
     float* ws = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* dlogit = ws;                         ws += B * num_classes;
     float* dz3 = ws;                            ws += B * kFc;
     float* dz2 = ws;                            ws += B * (int64_t)d.D1;
-    float* dh1 = ws;                            ws += B * (int64_t)kC5 * d.L1;
+    float* dh1 = to_h1 ? dh1_ext : ws;          ws += B * (int64_t)kC5 * d.L1;
     float* part6 = ws;                          ws += B * (kC6 * kC5 * kK6 + kC6);
     float* part5 = ws;                          ws += 4 * DGCNN_NUM_SMS * (kC5 * kKW + kC5);
     float* slabw = ws;
@@ -919,24 +925,52 @@ extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t n
     const int n6 = kC6 * kC5 * kK6;
     tail_reduce_partials<<<(n6 + kC6 + 31) / 32, 256, 0, sw>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    if (!fork(2)) return DGCNN_ERR_CUDA;             // dh1 is ready
-    tail_c5_bwd_input<<<grid_for(B * d.L1, 32, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const size_t smem5 = sizeof(float) * (kC5Pairs * kC5Row + 2 * kC5Pairs * kC5);
-    if (cudaFuncSetAttribute(tail_c5_bwd_weight, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem5) != cudaSuccess)
-        return DGCNN_ERR_CUDA;
-    const int parts5 = grid_for(B * d.L1, kC5Pairs, 2);
-    tail_c5_bwd_weight<<<parts5, 256, smem5, sw>>>(dh1, arg, pooled, B, k, d.L1, part5);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const int n5 = kC5 * kKW;
-    tail_reduce_partials<<<(n5 + kC5 + 31) / 32, 256, 0, sw>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (!to_h1) {
+        if (!fork(2)) return DGCNN_ERR_CUDA;             // dh1 is ready
+        tail_c5_bwd_input<<<grid_for(B * d.L1, 32, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+        const size_t smem5 = sizeof(float) * (kC5Pairs * kC5Row + 2 * kC5Pairs * kC5);
+        if (cudaFuncSetAttribute(tail_c5_bwd_weight, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem5) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+        const int parts5 = grid_for(B * d.L1, kC5Pairs, 2);
+        tail_c5_bwd_weight<<<parts5, 256, smem5, sw>>>(dh1, arg, pooled, B, k, d.L1, part5);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+        const int n5 = kC5 * kKW;
+        tail_reduce_partials<<<(n5 + kC5 + 31) / 32, 256, 0, sw>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
     if (side) {
         if (cudaEventRecord(side->done, sw) != cudaSuccess) return DGCNN_ERR_CUDA;
         if (overlap == 1 && cudaStreamWaitEvent(st, side->done, 0) != cudaSuccess) return DGCNN_ERR_CUDA;
     }
     return DGCNN_OK;
+}
+
+extern "C" int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, int32_t k,
+                              const float* w5, const float* w6, const float* wf1, const float* wf2,
+                              int32_t num_classes, const float* h1, const uint8_t* arg, const float* h2,
+                              const float* h3, const uint8_t* keep, const float* logp, float* dpooled,
+                              float* dw5, float* db5, float* dw6, float* db6, float* dwf1, float* dbf1,
+                              float* dwf2, float* dbf2, int32_t overlap, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    return tail_bwd_impl(dlogp, pooled, num_graphs, k, w5, w6, wf1, wf2, num_classes, h1, arg, h2, h3, keep, logp,
+                         dpooled, dw5, db5, dw6, db6, dwf1, dbf1, dwf2, dbf2, overlap, workspace, workspace_bytes,
+                         stream, false, nullptr);
+}
+
+// The tail's backward down to d(h1) [B,16,k/2] only: conv5's own backward runs
+// inside dgcnn_stack_bwd_conv5.  dw6 .. dbf2 as in dgcnn_tail_bwd.
+extern "C" int dgcnn_tail_bwd_h1(const float* dlogp, int64_t num_graphs, int32_t k, const float* w6,
+                                 const float* wf1, const float* wf2, int32_t num_classes, const float* h1,
+                                 const float* h2, const float* h3, const uint8_t* keep, const float* logp,
+                                 float* dh1, float* dw6, float* db6, float* dwf1, float* dbf1, float* dwf2,
+                                 float* dbf2, int32_t overlap, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (!dh1 && num_graphs > 0) return DGCNN_ERR_INVALID_ARGUMENT;
+    return tail_bwd_impl(dlogp, nullptr, num_graphs, k, nullptr, w6, wf1, wf2, num_classes, h1, nullptr, h2, h3,
+                         keep, logp, nullptr, nullptr, nullptr, dw6, db6, dwf1, dbf1, dwf2, dbf2, overlap,
+                         workspace, workspace_bytes, stream, true, dh1);
 }
 
 extern "C" int dgcnn_tail_bwd_join(void* stream) {

@@ -31,6 +31,7 @@ struct Team {
     // memory); the team is then all warps of BOTH CTAs and sync() is the cluster barrier.
     int split = 0;           // 1: this graph is shared with the peer CTA of the cluster
     int rank = 0;            // this CTA's rank in the pair
+    uint32_t mbar = 0;       // split: shared::cta address of this CTA's exchange mbarrier
     __device__ __forceinline__ void sync_local() const {
         asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
     }
@@ -43,6 +44,45 @@ struct Team {
         }
     }
 };
+
+// ---- distributed shared memory exchange of a graph split over a CTA pair -------------------
+// Each CTA of the pair finishes its rows of a plane in its OWN shared memory, then one thread
+// pushes them into the peer's copy with a bulk async copy (cp.async.bulk shared::cta ->
+// shared::cluster, the TMA engine moves the bytes) that signals the PEER's mbarrier with the
+// byte count; the peer's threads wait on their mbarrier.  No remote scalar stores, no cluster
+// barrier per layer.  One mbarrier per CTA, one phase per exchange.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t cta_addr, uint32_t peer_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(peer_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    }
+}
+// push `bytes` at cta_addr into the same place of the peer's shared memory; completion is
+// signalled on the peer's mbarrier (peer_mbar = shared::cluster address)
+__device__ __forceinline__ void push_to_peer(uint32_t cta_addr, uint32_t bytes, uint32_t peer_rank,
+                                             uint32_t peer_mbar) {
+    const uint32_t dst = map_to_peer(cta_addr, peer_rank);
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "r"(cta_addr), "r"(bytes), "r"(peer_mbar) : "memory");
+}
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(

@@ -30,6 +30,13 @@ struct StackFwdParams {
     int32_t* counter;   // work queue head, zeroed by the host wrapper
     int32_t* status;    // optional
     int64_t* trace;     // optional debug timeline, [num_graphs][16] (dgcnn_stack_fwd_set_trace)
+    // SURVEY 8f N2 (tensor-core variant): the head of the dense tail fused into SortPooling.
+    // conv5 = Conv1d(1,16,97,97) is a per-row 97 -> 16 linear map (model.py:19,37), so it commutes
+    // with the row gather: z = W5 x_cat[node] + b5 is accumulated per NODE in the layer epilogues,
+    // and after the sort ReLU + MaxPool1d(2,2) (model.py:37-38) run on the k winners.  h1 != null
+    // switches it on; `pooled` may then be null (no [B, k*97] round trip at all).
+    const float* w5; const float* b5;      // [16,97], [16]
+    float* h1; uint8_t* arg;               // [B,16,k/2] pooled activations and the winning row (0/1, 2 = dead)
     int pairs;          // tensor-core variant: launched as clusters of two CTAs (largest graphs are split)
     int split_pct;      // split a graph whose cost exceeds this percentage of an SM's fair share
 };

@@ -336,7 +336,7 @@ static int stack_bwd_grid(int f, int nmax, int threads, size_t smem, int64_t num
 using namespace dgcnn;
 
 // tensor-core variant, graph_stack_bwd_mma.cu
-int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes);
+int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes, bool conv5 = false);
 size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_t num_nodes);
 int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
                         int64_t ldc, const float* x, int64_t ldx, int32_t f, const int32_t* rowptr_t,
@@ -346,7 +346,8 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
                         const int32_t* gflags, const uint32_t* bitmap_t, const int32_t* bmoff_t,
                         const int32_t* gflags_t, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                         const float* w2, const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
-                        void* workspace, cudaStream_t st);
+                        void* workspace, cudaStream_t st, const float* dh1 = nullptr,
+                        const uint8_t* arg = nullptr, const float* w5 = nullptr);
 
 static int fma_bwd_supported(int32_t num_features, int64_t max_nodes) {
     if (num_features < 1 || num_features > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
@@ -436,4 +437,49 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
     stack_bwd_reduce<<<(G.total + 255) / 256, 256, 0, st>>>(p.partials, grid, G.total, grads);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
+}
+
+// ---- the fused backward fed with d(h1) instead of d(pooled) -------------------------
+extern "C" int dgcnn_stack_bwd_conv5_supported(int32_t num_features, int64_t max_nodes) {
+    return dgcnn_stack_bwd_mma_supported(num_features, max_nodes, true);
+}
+
+extern "C" int64_t dgcnn_stack_conv5_num_params(int32_t num_features) {
+    return num_features < 1 ? 0 : grad_offsets(num_features).total + 16 * kCat + 16;
+}
+
+extern "C" int dgcnn_stack_bwd_conv5(const float* dh1, const uint8_t* arg, const int32_t* perm, int32_t k,
+                                     const float* xcat, int64_t ldc, const float* x, int64_t ldx,
+                                     int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
+                                     const float* dis, const int32_t* gptr, const int32_t* gorder,
+                                     const int32_t* gdesc, const uint32_t* fragmap,
+                                     const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                                     const uint32_t* bitmap_t, const int32_t* bmoff_t,
+                                     const int32_t* gflags_t,
+                                     int64_t num_nodes, int64_t num_graphs, int64_t max_nodes, const float* w2,
+                                     const float* w3, const float* w4, const float* w5, int32_t norm,
+                                     float* grads, int32_t* status, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    if (num_nodes < 0 || num_graphs < 0 || k < 2 || num_features < 1 || ldx < num_features ||
+        ldc < kCat || !grads)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (norm != DGCNN_NORM_SYM && norm != DGCNN_NORM_RW) return DGCNN_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t total = dgcnn_stack_conv5_num_params(num_features);
+    if (num_graphs == 0) {
+        if (cudaMemsetAsync(grads, 0, sizeof(float) * total, st) != cudaSuccess) return DGCNN_ERR_CUDA;
+        return DGCNN_OK;
+    }
+    if (!dgcnn_stack_bwd_mma_supported(num_features, max_nodes, true)) return DGCNN_ERR_UNSUPPORTED;
+    if (num_graphs >= INT32_MAX || num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
+    if (!bitmap || !bmoff || !gflags || !status || !gdesc) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!dh1 || !arg || !perm || !xcat || (num_nodes > 0 && !x) || !rowptr_t || !dis || !gptr || !w2 || !w3 ||
+        !w4 || !w5)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < dgcnn_stack_bwd_workspace_bytes(num_features, num_graphs, num_nodes))
+        return DGCNN_ERR_WORKSPACE;
+    return dgcnn_stack_bwd_mma(nullptr, perm, k, xcat, ldc, x, ldx, num_features, rowptr_t, col_t, dis, gptr,
+                               gorder, gdesc, fragmap, bitmap, bmoff, gflags, bitmap_t, bmoff_t, gflags_t,
+                               num_nodes, num_graphs, max_nodes, w2, w3, w4, norm, grads, status, workspace, st,
+                               dh1, arg, w5);
 }

@@ -42,12 +42,18 @@ struct StackBwdMmaParams {
     int32_t* counter;
     int32_t* status;
     int64_t* trace;      // optional debug timeline [num_graphs][16] (dgcnn_stack_bwd_set_trace)
+    // conv5 + ReLU + max-pool's backward fused in (dh1 != null; dpooled is then unused):
+    // the pooled gradient is dz W5 with dz[r][c] = dh1[c][r/2] routed through `arg`, never materialised
+    const float* dh1; const uint8_t* arg; const float* w5;
 };
 #define KSB_TRACE(slot) do { if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
 
-struct GradOffsetsM { int w1, b1, w2, b2, w3, b3, w4, b4, total; };
+constexpr int kC5b = 16;                   // conv5 output channels
+constexpr int kW5TPad = 24;                // row stride (halfs) of the transposed W5 planes [97][16]
 
-__host__ __device__ inline GradOffsetsM grad_offsets_m(int f) {
+struct GradOffsetsM { int w1, b1, w2, b2, w3, b3, w4, b4, w5, b5, total; };
+
+__host__ __device__ inline GradOffsetsM grad_offsets_m(int f, bool conv5 = false) {
     GradOffsetsM g;
     int o = 0;
     g.w1 = o; o += kHid * f;
@@ -58,32 +64,37 @@ __host__ __device__ inline GradOffsetsM grad_offsets_m(int f) {
     g.b3 = o; o += kHid;
     g.w4 = o; o += kHid;
     g.b4 = o; o += 1;
+    g.w5 = o; o += conv5 ? kC5b * kCat : 0;              // conv5.weight [16,97], conv5.bias [16]: the
+    g.b5 = o; o += conv5 ? kC5b : 0;                     // next two tensors of the flat parameter order
     g.total = o;
     return g;
 }
 
 // CTA-wide: W2^T, W3^T hi/lo planes [k][c] (B operand of dx = dh W), w4
-struct BwdShared { int w2p, w3p, w4, acc, total; };
-__host__ __device__ inline BwdShared bwd_shared_layout(int f) {
+struct BwdShared { int w2p, w3p, w4, w5t, w5x, acc, total; };
+__host__ __device__ inline BwdShared bwd_shared_layout(int f, bool conv5 = false) {
     BwdShared L;
     int o = 0;
     L.w2p = o; o += 2 * kHid * kWPad * 2;
     L.w3p = o; o += 2 * kHid * kWPad * 2;
     L.w4 = o; o += kHid * 4;
-    L.acc = o; o += al16(grad_offsets_m(f).total * 4);   // the CTA's running parameter-gradient sum
+    L.w5t = o; o += conv5 ? 2 * 104 * kW5TPad * 2 : 0;   // W5^T hi/lo planes [plane][column i][channel]
+    L.w5x = o; o += conv5 ? (kC5b + 4) * 4 : 0;          // W5[:, 96] fp32, then max_i sum_c |W5[c][i]|
+    L.acc = o; o += al16(grad_offsets_m(f, conv5).total * 4);   // the CTA's running parameter-gradient sum
     L.total = o;
     return L;
 }
 
 // per graph (bytes)
-struct BwdTeamLayout { int P, DH, vpl, bm, cs, rs, hv, rank, rp, red, sacc, total; int S; };
-__host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np) {
+struct BwdTeamLayout { int P, DH, DZ, vpl, bm, cs, rs, hv, rank, rp, red, sacc, total; int S; };
+__host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np, bool conv5 = false) {
     BwdTeamLayout L;
     L.S = np + 8;
     const int wpr = (np + 31) >> 5;
     int o = 0;
     L.P = o; o += 2 * kHid * L.S * 2;                    // hi/lo planes of r * dpre * scale
     L.DH = o; o += 2 * kHid * L.S * 2;                   // hi/lo planes of dh * scale
+    L.DZ = o; o += conv5 ? 2 * kC5b * L.S * 2 : 0;       // hi/lo planes [16][S] of dz * scale (conv5 pre-activation grads)
     L.vpl = o; o += al16(2 * L.S * 2);
     {
         const int plain = np * wpr * 4, frag = frag_words(np) * 4;
@@ -95,21 +106,13 @@ __host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np) {
     L.rank = o; o += al16(np * 4);
     L.rp = o; o += al16((np + 1) * 4);
     L.red = o; o += (kBwdThreads / 32) * kHid * 4;
-    L.sacc = o; o += al16(grad_offsets_m(f).total * 4);
+    L.sacc = o; o += al16(grad_offsets_m(f, conv5).total * 4);
     L.total = o;
     return L;
 }
 
-__host__ __device__ inline int bwd_quad_bytes(int f) {
-    return ((kSmemBudget - 1024 - bwd_shared_layout(f).total) / kQuads) & ~15;
-}
-
-__host__ __device__ inline int bwd_quads_needed(int f, int n) {
-    const int np = (n + 15) & ~15, tiles = np >> 4;
-    int q = tiles <= 4 ? 1 : (tiles <= 8 ? 2 : 4);
-    const int need = bwd_team_layout(f, np < 16 ? 16 : np).total, qb = bwd_quad_bytes(f);
-    while (q < kQuads && need > q * qb) q <<= 1;
-    return q;
+__host__ __device__ inline int bwd_quad_bytes(int f, bool conv5 = false) {
+    return ((kSmemBudget - 1024 - bwd_shared_layout(f, conv5).total) / kQuads) & ~15;
 }
 
 // sum red[w][c] over the team's warps (c < 32)
@@ -117,6 +120,38 @@ __device__ __forceinline__ float reduce_rows_t(const float* red, int nwarps, int
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) s += red[w * kHid + c];
     return s;
+}
+
+// SURVEY 8f N2.  Pooled gradient of one x_cat slice for the 16-row tile mt, never materialised in
+// HBM:  gz[node][k] = sum_c dz[node][c] W5[c][off + k]  (scaled like dz).  A = dz planes
+// [channel][node] read transposed (ldmatrix.trans), B = W5^T planes [column][channel];
+// hi*hi + lo*hi + hi*lo.  C layout: gz[nt][0..1] row g, gz[nt][2..3] row g+8, columns nt*8+2t, +1.
+struct Conv5Bwd {
+    const __half* DZ;       // [plane][16][S]
+    const __half* w5t;      // [plane][104][kW5TPad]
+    bool on;
+};
+
+__device__ __forceinline__ void dz_w5_tile(const Conv5Bwd& c5, int S, int mt, int off, int lane,
+                                           float (&gz)[4][4]) {
+    const int g = lane >> 2, t = lane & 3, j = lane >> 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) gz[nt][0] = gz[nt][1] = gz[nt][2] = gz[nt][3] = 0.f;
+    // matrix j of the x4 load: channels (j>>1)*8 .. +7 (rows), nodes mt*16 + (j&1)*8 .. +7
+    const uint32_t a0 = smem_u32(c5.DZ) + (uint32_t)((((j >> 1) * 8 + (lane & 7)) * S + mt * 16 + (j & 1) * 8) * 2);
+    uint32_t ah[4], al[4];
+    ldsm_x4_t(a0, ah[0], ah[1], ah[2], ah[3]);
+    ldsm_x4_t(a0 + (uint32_t)(kC5b * S * 2), al[0], al[1], al[2], al[3]);
+    const uint32_t* wh = reinterpret_cast<const uint32_t*>(c5.w5t);
+    const uint32_t* wl = reinterpret_cast<const uint32_t*>(c5.w5t + 104 * kW5TPad);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int widx = ((off + nt * 8 + g) * kW5TPad + 2 * t) >> 1;
+        const uint32_t h0 = wh[widx], h1 = wh[widx + 4], l0 = wl[widx], l1 = wl[widx + 4];
+        mma_fp16(gz[nt], ah, h0, h1);
+        mma_fp16(gz[nt], al, h0, h1);
+        mma_fp16(gz[nt], ah, l0, l1);
+    }
 }
 
 // dh tile(s) = c_i * (A_hat^T . P) for every 16-row tile owned by this warp; then
@@ -129,7 +164,7 @@ __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, cons
                                               const int32_t* __restrict__ col_g, int base,
                                               const float* __restrict__ cs, const int* __restrict__ rank,
                                               const float* __restrict__ dp, int offx, float inv_scale,
-                                              const Team& tm) {
+                                              const Team& tm, const Conv5Bwd& c5) {
     const int lane = tm.lane, warp = tm.warp, nwarps = tm.nwarps;
     const int g = lane >> 2, t = lane & 3;
     const int tiles = (n + 15) >> 4;
@@ -254,12 +289,20 @@ __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, cons
                     mma_f16(y[nt], ah, l0, l1);
                 }
             }
+            if (c5.on) {                                 // + dz W5[:, slice] (still scaled)
+                float gz[4][4];
+                dz_w5_tile(c5, S, mt, offx, lane, gz);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    y[nt][0] += gz[nt][0]; y[nt][1] += gz[nt][1]; y[nt][2] += gz[nt][2]; y[nt][3] += gz[nt][3];
+                }
+            }
             // unscale, add the pooled gradient of x_in's slice, store as the next layer's G
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int row = half ? row1 : row0;
                 if (row >= n) continue;
-                const int r = rank[row];
+                const int r = c5.on ? -1 : rank[row];
                 const float* gp = r >= 0 ? dp + r * kCat + offx + 2 * t : nullptr;
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
@@ -280,25 +323,47 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
     const int nthreads = tm.nthreads, nwarps = tm.nwarps;
     const int f = p.f;
-    const GradOffsetsM GO = grad_offsets_m(f);
-    const BwdShared SL = bwd_shared_layout(f);
+    const bool conv5 = p.dh1 != nullptr;
+    const GradOffsetsM GO = grad_offsets_m(f, conv5);
+    const BwdShared SL = bwd_shared_layout(f, conv5);
     const __half* w2p = reinterpret_cast<const __half*>(shraw + SL.w2p);
     const __half* w3p = reinterpret_cast<const __half*>(shraw + SL.w3p);
     const float* w4s = reinterpret_cast<const float*>(shraw + SL.w4);
+    const float* w5x = reinterpret_cast<const float*>(shraw + SL.w5x);    // W5[:, 96], then the column-sum bound
+    const int L1 = p.k >> 1;
+    const float* dh1g = conv5 ? p.dh1 + (int64_t)gi * kC5b * L1 : nullptr;
+    const uint8_t* argg = conv5 ? p.arg + (int64_t)gi * kC5b * L1 : nullptr;
+    // db5[c] = sum_j dh1[c][j] over the live pairs: every (c, j) feeds exactly one pooled row, real
+    // or padding (a padding row's pre-activation is b5 itself)
+    auto conv5_bias_grad = [&](float* sacc_) {
+        for (int c = warp; c < kC5b; c += nwarps) {
+            float sb = 0.f;
+            for (int j = lane; j < L1; j += 32) sb += argg[c * L1 + j] != 2 ? dh1g[c * L1 + j] : 0.f;
+            sb = warp_sum(sb);
+            if (lane == 0) sacc_[GO.b5 + c] = sb;
+        }
+    };
     // The team leaves this graph's parameter-gradient vector in `sacc` (every entry is
     // written exactly once below); the CTA adds the vectors of a pass in team order.
     if (n == 0) {
-        float* sacc0 = reinterpret_cast<float*>(tm.smem + bwd_team_layout(f, 16).sacc);
+        float* sacc0 = reinterpret_cast<float*>(tm.smem + bwd_team_layout(f, 16, conv5).sacc);
         for (int idx = tid; idx < GO.total; idx += nthreads) sacc0[idx] = 0.f;
+        if (conv5) {
+            tm.sync();
+            conv5_bias_grad(sacc0);
+        }
         return;
     }
     const int keep = min(n, p.k);
     const int np = (n + 15) & ~15;
     const int wpr = (np + 31) >> 5;
     const int tiles = np >> 4;
-    const BwdTeamLayout L = bwd_team_layout(f, np);
+    const BwdTeamLayout L = bwd_team_layout(f, np, conv5);
     const int S = L.S;
     unsigned char* sm = tm.smem;
+    __half* DZ = reinterpret_cast<__half*>(sm + L.DZ);
+    Conv5Bwd c5;
+    c5.DZ = DZ; c5.w5t = reinterpret_cast<const __half*>(shraw + SL.w5t); c5.on = conv5;
     float* G = p.gws + (int64_t)base * kHid;             // this graph's rows
     __half* P = reinterpret_cast<__half*>(sm + L.P);
     __half* DH = reinterpret_cast<__half*>(sm + L.DH);
@@ -337,7 +402,12 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     if (dup)
         for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr_t[base + j] - e0;
     float amax = 0.f;
-    {   // sixteen loads in flight per thread: the sweep is pure memory latency
+    if (conv5) {
+        // |pooled gradient| <= max |dz| * max_i sum_c |W5[c][i]|
+        for (int idx = tid; idx < kC5b * L1; idx += nthreads)
+            if (argg[idx] != 2) amax = fmaxf(amax, fabsf(dh1g[idx]));
+        amax *= w5x[kC5b];
+    } else {   // sixteen loads in flight per thread: the sweep is pure memory latency
         const int total = keep * kCat;
         int idx = tid;
         for (; idx + 15 * nthreads < total; idx += 16 * nthreads) {
@@ -372,13 +442,26 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         // would hide it, so write NaN-free zeros only for the exact-zero case)
         const float fillv = amax > 0.f ? amax * 0.f + (amax - amax) : 0.f;   // NaN if inf/nan
         for (int idx = tid; idx < GO.total; idx += nthreads) sacc[idx] = fillv;
-        return;
+        return;                                          // (conv5: every live dh1 entry is zero, so is db5)
     }
     // power-of-two scale: max |pooled gradient| -> about 2^6, leaving 2^9 of head room
     int ex;
     frexpf(amax, &ex);
     const float scale = ldexpf(1.f, 6 - ex), inv_scale = ldexpf(1.f, ex - 6);
 
+    if (conv5) {
+        // dz[node][c] = dh1[c][r/2] when pooled row r = rank[node] won its pair (arg), else 0; as
+        // scaled hi/lo planes [c][node]
+        for (int idx = tid; idx < kC5b * S; idx += nthreads) {
+            const int ch = idx / S, i = idx - ch * S;
+            float v = 0.f;
+            const int r = i < n ? rank[i] : -1;
+            if (r >= 0 && (r >> 1) < L1 && argg[ch * L1 + (r >> 1)] == (r & 1)) v = dh1g[ch * L1 + (r >> 1)];
+            store_split(DZ, DZ + kC5b * S, idx, v * scale);
+        }
+        conv5_bias_grad(sacc);
+        tm.sync();
+    }
     KSB_TRACE(1);
     // ---- layer 4 (32 -> 1) --------------------------------------------------------------------
     {
@@ -387,7 +470,16 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             float v = 0.f;
             if (i < n) {
                 const float y = xc[(int64_t)i * p.ldc + 3 * kHid];
-                const float gy = rank[i] >= 0 ? dp[rank[i] * kCat + 3 * kHid] : 0.f;
+                float gy;
+                if (conv5) {                             // dz . W5[:, 96]
+                    float sg = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < kC5b; ++ch)
+                        sg = fmaf(__half2float(DZ[ch * S + i]) + __half2float(DZ[(kC5b + ch) * S + i]), w5x[ch], sg);
+                    gy = sg * inv_scale;
+                } else {
+                    gy = rank[i] >= 0 ? dp[rank[i] * kCat + 3 * kHid] : 0.f;
+                }
                 const float d = gy * (1.f - y * y);
                 dbp += d;
                 v = rs[i] * d * scale;
@@ -457,10 +549,40 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         }
     }
     tm.sync();
+    float* xin3 = reinterpret_cast<float*>(P);           // conv5: x3 as fp32 [feature][S] (P is still free)
+    const uint32_t* dz32[2] = {reinterpret_cast<const uint32_t*>(DZ),
+                               reinterpret_cast<const uint32_t*>(DZ + kC5b * S)};
+    if (conv5) {
+        // pooled gradient of the x3 slice, dz W5[:, 64..95], straight into G (unscaled)
+        const int g = lane >> 2, t = lane & 3;
+        for (int mt = warp; mt < tiles; mt += nwarps) {
+            float gz[4][4];
+            dz_w5_tile(c5, S, mt, 2 * kHid, lane, gz);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = mt * 16 + g + 8 * half;
+                if (row >= n) continue;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    *reinterpret_cast<float2*>(G + row * kHid + nt * 8 + 2 * t) =
+                        make_float2(gz[nt][2 * half] * inv_scale, gz[nt][2 * half + 1] * inv_scale);
+            }
+        }
+        // dW5[c][96] = sum_i dz[i][c] x4[i]
+        for (int ch = warp; ch < kC5b; ch += nwarps) {
+            float sw = 0.f;
+            for (int i = lane; i < n; i += 32)
+                sw = fmaf(__half2float(DZ[ch * S + i]) + __half2float(DZ[(kC5b + ch) * S + i]),
+                          xc[(int64_t)i * p.ldc + 3 * kHid], sw);
+            sw = warp_sum(sw);
+            if (lane == 0) sacc[GO.w5 + ch * kCat + 3 * kHid] = sw * inv_scale;
+        }
+        tm.sync();
+    }
     {   // dW4[k] += sum_i dh4[i] x3[i][k];  G3[i][k] = dh4[i] w4[k] + pooled gradient of x3
         float dwp = 0.f;
         const float w4k = w4s[lane];
-        for (int i0 = warp; i0 < n; i0 += 8 * nwarps) {          // eight rows in flight per warp
+        for (int i0 = warp; i0 < np; i0 += 8 * nwarps) {         // eight rows in flight per warp
             float xv[8], gp[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -468,8 +590,12 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 xv[u] = 0.f; gp[u] = 0.f;
                 if (i < n) {
                     xv[u] = xc[(int64_t)i * p.ldc + 2 * kHid + lane];
-                    const int r = rank[i];
-                    if (r >= 0) gp[u] = dp[r * kCat + 2 * kHid + lane];
+                    if (conv5) {
+                        gp[u] = G[i * kHid + lane];
+                    } else {
+                        const int r = rank[i];
+                        if (r >= 0) gp[u] = dp[r * kCat + 2 * kHid + lane];
+                    }
                 }
             }
 #pragma unroll
@@ -480,12 +606,38 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                     dwp = fmaf(h, xv[u], dwp);
                     G[i * kHid + lane] = fmaf(h, w4k, gp[u]);
                 }
+                if (conv5 && i < np) xin3[lane * S + i] = xv[u];     // (zero beyond n: NaN-free MMA padding)
             }
         }
         red0[warp * kHid + lane] = dwp;
     }
     tm.sync();
     if (tid < kHid) sacc[GO.w4 + tid] = reduce_rows_t(red0, nwarps, tid);
+    if (conv5) {
+        // dW5[c][64 + k] = sum_i dz[i][c] x3[i][k]: four 16 x 8 output tiles on the tensor cores
+        const int g = lane >> 2, t = lane & 3;
+        for (int nk = warp; nk < 4; nk += nwarps) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* xcol = xin3 + (8 * nk + g) * S + 2 * t;
+            for (int kt = 0; kt < tiles; ++kt) {
+                const float2 x01 = *reinterpret_cast<const float2*>(xcol + kt * 16);
+                const float2 x89 = *reinterpret_cast<const float2*>(xcol + kt * 16 + 8);
+                const int ia = (g * S + kt * 16 + 2 * t) >> 1;
+                uint32_t ah[4], al[4];
+                ah[0] = dz32[0][ia]; ah[1] = dz32[0][ia + 4 * S]; ah[2] = dz32[0][ia + 4]; ah[3] = dz32[0][ia + 4 * S + 4];
+                al[0] = dz32[1][ia]; al[1] = dz32[1][ia + 4 * S]; al[2] = dz32[1][ia + 4]; al[3] = dz32[1][ia + 4 * S + 4];
+                uint32_t bh0, bl0, bh1, bl1;
+                split2(x01.x, x01.y, bh0, bl0);
+                split2(x89.x, x89.y, bh1, bl1);
+                mma_fp16(acc, ah, bh0, bh1);
+                mma_fp16(acc, al, bh0, bh1);
+                mma_fp16(acc, ah, bl0, bl1);
+            }
+            float* o = sacc + GO.w5 + g * kCat + 2 * kHid + 8 * nk + 2 * t;
+            o[0] = acc[0] * inv_scale; o[1] = acc[1] * inv_scale;
+            o[8 * kCat] = acc[2] * inv_scale; o[8 * kCat + 1] = acc[3] * inv_scale;
+        }
+    }
     tm.sync();
 
     KSB_TRACE(2);
@@ -533,7 +685,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         KSB_TRACE(3 + 3 * (3 - layer));
         // B: dh planes, and G <- dx (layers 3, 2)
         bwd_mma_layer(P, layer == 3 ? w3p : (layer == 2 ? w2p : nullptr), DH, G, bm, frag, wpr, n, S, dup, rp,
-                      col_g, base, cs, rank, dp, offx, inv_scale, tm);
+                      col_g, base, cs, rank, dp, offx, inv_scale, tm, c5);
         tm.sync();
         KSB_TRACE(4 + 3 * (3 - layer));
         // C: parameter gradient of the layer
@@ -563,19 +715,23 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             const int g = lane >> 2, t = lane & 3;
             const uint32_t* dh32[2] = {reinterpret_cast<const uint32_t*>(DH),
                                        reinterpret_cast<const uint32_t*>(DH + kHid * S)};
-            for (int tile = warp; tile < 8; tile += nwarps) {
+            // (conv5: four more tiles, dW5[c][offx + k] = sum_i dz[i][c] x_in[i][k], A = the dz planes)
+            for (int tile = warp; tile < (conv5 ? 12 : 8); tile += nwarps) {
                 const int mc = tile >> 2, nk = tile & 3;
+                const bool zt = mc == 2;
+                const uint32_t* a_hi = zt ? dz32[0] : dh32[0];
+                const uint32_t* a_lo = zt ? dz32[1] : dh32[1];
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 const float* xcol = xin + (8 * nk + g) * S + 2 * t;      // feature column of this lane
                 for (int kt = 0; kt < tiles; ++kt) {
                     const float2 x01 = *reinterpret_cast<const float2*>(xcol + kt * 16);
                     const float2 x89 = *reinterpret_cast<const float2*>(xcol + kt * 16 + 8);
-                    const int ia = ((16 * mc + g) * S + kt * 16 + 2 * t) >> 1;
+                    const int ia = (((zt ? 0 : 16 * mc) + g) * S + kt * 16 + 2 * t) >> 1;
                     uint32_t ah[4], al[4];
-                    ah[0] = dh32[0][ia]; ah[1] = dh32[0][ia + 4 * S]; ah[2] = dh32[0][ia + 4];
-                    ah[3] = dh32[0][ia + 4 * S + 4];
-                    al[0] = dh32[1][ia]; al[1] = dh32[1][ia + 4 * S]; al[2] = dh32[1][ia + 4];
-                    al[3] = dh32[1][ia + 4 * S + 4];
+                    ah[0] = a_hi[ia]; ah[1] = a_hi[ia + 4 * S]; ah[2] = a_hi[ia + 4];
+                    ah[3] = a_hi[ia + 4 * S + 4];
+                    al[0] = a_lo[ia]; al[1] = a_lo[ia + 4 * S]; al[2] = a_lo[ia + 4];
+                    al[3] = a_lo[ia + 4 * S + 4];
                     uint32_t bh0, bl0, bh1, bl1;
                     split2(x01.x, x01.y, bh0, bl0);
                     split2(x89.x, x89.y, bh1, bl1);
@@ -583,9 +739,11 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                     mma_fp16(acc, al, bh0, bh1);
                     mma_fp16(acc, ah, bl0, bl1);
                 }
-                float* o = sacc + ow + (16 * mc + g) * kHid + 8 * nk + 2 * t;
+                const int ld = zt ? kCat : kHid;
+                float* o = zt ? sacc + GO.w5 + g * kCat + offx + 8 * nk + 2 * t
+                              : sacc + ow + (16 * mc + g) * kHid + 8 * nk + 2 * t;
                 o[0] = acc[0] * inv_scale; o[1] = acc[1] * inv_scale;
-                o[8 * kHid] = acc[2] * inv_scale; o[8 * kHid + 1] = acc[3] * inv_scale;
+                o[8 * ld] = acc[2] * inv_scale; o[8 * ld + 1] = acc[3] * inv_scale;
             }
         } else {
             // dW1[c][k] = sum_i dh[i][c] x0[i][k], k < F (any F): FMA, dh rebuilt from its planes.
@@ -636,8 +794,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
     __shared__ PlanEntry s_plan[kMaxTeams];
     __shared__ int s_count;
     const int f = p.f;
-    const BwdShared SL = bwd_shared_layout(f);
-    const int gtotal = grad_offsets_m(f).total;
+    const bool conv5 = p.dh1 != nullptr;
+    const BwdShared SL = bwd_shared_layout(f, conv5);
+    const int gtotal = grad_offsets_m(f, conv5).total;
     float* cta_acc = reinterpret_cast<float*>(smraw + SL.acc);
     for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) cta_acc[idx] = 0.f;
     // A_hat^T: the forward bitmap when K0 proved the batch symmetric, else the transposed one
@@ -648,7 +807,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
     const bool frag = !use_t && p.fragmap != nullptr;   // symmetric batch: A_hat^T == A_hat
 
     unsigned char* team_base = smraw + al16(SL.total);
-    const int budget = kQuads * bwd_quad_bytes(f);
+    const int budget = kQuads * bwd_quad_bytes(f, conv5);
     const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
     constexpr int kWarps = kBwdThreads / 32;
@@ -658,7 +817,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
     for (int pass = 0;; ++pass) {
         if (warp_id == 0) {
             plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
-                      [f](int np) { return bwd_team_layout(f, np).total; }, s_plan, &s_count, nsplit);
+                      [f, conv5](int np) { return bwd_team_layout(f, np, conv5).total; }, s_plan, &s_count, nsplit);
         } else if (pass == 0) {
             const int tid = threadIdx.x - 32, nthreads = kBwdThreads - 32;
             __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
@@ -671,6 +830,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
                 store_split(w3p, w3p + kHid * kWPad, k * kWPad + c, p.w3[idx]);
             }
             if (tid < kHid) w4s[tid] = p.w4[tid];
+            if (conv5) {
+                // W5^T as hi/lo planes [column i][channel c] (the "col" operand of dz W5), W5[:, 96],
+                // and the bound max_i sum_c |W5[c][i]| that sizes the per-graph gradient scale
+                __half* w5t = reinterpret_cast<__half*>(smraw + SL.w5t);
+                float* w5x = reinterpret_cast<float*>(smraw + SL.w5x);
+                for (int idx = tid; idx < kC5b * kCat; idx += nthreads) {
+                    const int c = idx / kCat, i = idx - c * kCat;
+                    const float v = p.w5[idx];
+                    store_split(w5t, w5t + 104 * kW5TPad, i * kW5TPad + c, v);
+                    if (i == 3 * kHid) w5x[c] = v;
+                }
+                if (tid < 32) {
+                    float m = 0.f;
+                    for (int i = tid; i < kCat; i += 32) {
+                        float sum = 0.f;
+                        for (int c = 0; c < kC5b; ++c) sum += fabsf(p.w5[c * kCat + i]);
+                        m = fmaxf(m, sum);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(DGCNN_FULL_MASK, m, o));
+                    if (tid == 0) w5x[kC5b] = m;
+                }
+            }
         }
         __syncthreads();                             // the plan (and, first time, the weights)
         const int count = s_count;
@@ -701,7 +883,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
             if (e.n > p.nmax) continue;
             const int np = max(16, (e.n + 15) & ~15);
             const float* sacc = reinterpret_cast<const float*>(team_base + e.smem_off +
-                                                               bwd_team_layout(f, np).sacc);
+                                                               bwd_team_layout(f, np, conv5).sacc);
             for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) cta_acc[idx] += sacc[idx];
         }
         next += count;                               // (the next pass syncs before it re-carves)
@@ -745,14 +927,15 @@ using namespace dgcnn;
 static int64_t* g_bwd_trace = nullptr;
 extern "C" void dgcnn_stack_bwd_set_trace(int64_t* device_buffer) { g_bwd_trace = device_buffer; }
 
-int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes) {
+int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes, bool conv5) {
     if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
     const int np = (int)((max_nodes + 15) / 16 * 16);
-    return bwd_team_layout(f, np).total <= kQuads * bwd_quad_bytes(f) ? 1 : 0;
+    return bwd_team_layout(f, np, conv5).total <= kQuads * bwd_quad_bytes(f, conv5) ? 1 : 0;
 }
 
 size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_t num_nodes) {
-    return sizeof(float) * ((size_t)grad_offsets_m(f).total * (size_t)(num_graphs > 0 ? num_graphs : 1) +
+    // (sized for the conv5 variant: one partial vector per CTA, at most one CTA per graph)
+    return sizeof(float) * ((size_t)grad_offsets_m(f, true).total * (size_t)(num_graphs > 0 ? num_graphs : 1) +
                             (size_t)(num_nodes > 0 ? num_nodes : 0) * kHid) + 1024;
 }
 
@@ -765,8 +948,11 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
                         const int32_t* gflags_t, int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
                         const float* w2,
                         const float* w3, const float* w4, int32_t norm, float* grads, int32_t* status,
-                        void* workspace, cudaStream_t st) {
+                        void* workspace, cudaStream_t st, const float* dh1, const uint8_t* arg,
+                        const float* w5) {
+    const bool conv5 = dh1 != nullptr;
     StackBwdMmaParams p{};
+    p.dh1 = dh1; p.arg = arg; p.w5 = w5;
     p.dpooled = dpooled; p.perm = perm; p.k = k; p.xcat = xcat; p.ldc = ldc;
     p.x = x; p.ldx = ldx; p.f = f;
     p.rowptr_t = rowptr_t; p.col_t = col_t; p.dis = dis; p.gptr = gptr; p.gorder = gorder;
@@ -779,12 +965,12 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     p.counter = reinterpret_cast<int32_t*>(aligned);
     p.partials = reinterpret_cast<float*>(aligned + 256);
     p.gws = reinterpret_cast<float*>(
-        ((uintptr_t)(p.partials + (size_t)grad_offsets_m(f).total * (size_t)num_graphs) + 255) &
+        ((uintptr_t)(p.partials + (size_t)grad_offsets_m(f, conv5).total * (size_t)num_graphs) + 255) &
         ~(uintptr_t)255);
     p.status = status;
     p.trace = g_bwd_trace;
     if (!gdesc) return DGCNN_ERR_INVALID_ARGUMENT;
-    const size_t smem = (size_t)al16(bwd_shared_layout(f).total) + (size_t)kQuads * bwd_quad_bytes(f);
+    const size_t smem = (size_t)al16(bwd_shared_layout(f, conv5).total) + (size_t)kQuads * bwd_quad_bytes(f, conv5);
     if (cudaFuncSetAttribute(stack_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
@@ -792,7 +978,7 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     if (grid > num_graphs) grid = num_graphs;
     stack_bwd_mma_kernel<<<(unsigned)grid, kBwdThreads, smem, st>>>(p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    const int total = grad_offsets_m(f).total;
+    const int total = grad_offsets_m(f, conv5).total;
     stack_bwd_reduce_graphs<<<(total + 31) / 32, 256, 0, st>>>(p.partials, (int)grid, total, grads);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;

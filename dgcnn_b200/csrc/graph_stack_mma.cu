@@ -52,26 +52,34 @@ constexpr int kRowB = kRowH * 2;           // 144 bytes
 constexpr int kRankSortMax = 640;          // rank sort (one pass, no barriers) up to this many nodes
 
 // CTA-wide region: weights, shared by all teams.  Byte offsets, 16-byte aligned.
-struct SharedLayout { int w2p, w3p, w1t, misc, total; };
+constexpr int kC5 = 16;                    // conv5 output channels (model.py:19)
+constexpr int kW5Pad = 104;                // row stride (halfs) of the W5 planes: 208 B, conflict-free ldmatrix
 
-__host__ __device__ inline SharedLayout shared_layout(int f) {
+constexpr int kZeroBytes = 4096;          // zeroed staging buffer: source of the bulk stores that pad `pooled`
+
+struct SharedLayout { int w2p, w3p, w1t, misc, w5p, w5x, zero, total; };
+
+__host__ __device__ inline SharedLayout shared_layout(int f, bool conv5 = false) {
     SharedLayout L;
     int o = 0;
     L.w2p = o; o += 2 * kHid * kWPad * 2;                // [plane][cout][kWPad] fp16
     L.w3p = o; o += 2 * kHid * kWPad * 2;
     L.w1t = o; o += al16(f * kHid * 4);                  // [F][32] fp32
     L.misc = o; o += 4 * kHid * 4;                       // w4, b1, b2, b3
+    L.w5p = o; o += conv5 ? 2 * kC5 * kW5Pad * 2 : 0;    // [plane][16][kW5Pad] fp16: W5[:, 0..95]
+    L.w5x = o; o += conv5 ? 2 * kC5 * 4 : 0;             // W5[:, 96] and b5, fp32
+    L.zero = o; o += kZeroBytes;
     L.total = o;
     return L;
 }
 
 // Per-graph region, sized by the graph's own padded node count np (multiple of 16).
 struct TeamLayout {
-    int PA, PB, vpl, fbm, xs, cs, rs, rp, total;
+    int PA, PB, vpl, fbm, xs, cs, rs, rp, zs, total;
     int S;      // row stride (halfs) of the single-column planes (vpl, xs): np + 8
 };
 
-__host__ __device__ inline TeamLayout team_layout(int f, int np) {
+__host__ __device__ inline TeamLayout team_layout(int f, int np, bool conv5 = false) {
     TeamLayout L;
     L.S = np + 8;
     int o = 0;
@@ -83,22 +91,14 @@ __host__ __device__ inline TeamLayout team_layout(int f, int np) {
     L.cs = o; o += al16(np * 4);
     L.rs = o; o += al16(np * 4);
     L.rp = o; o += al16((np + 1) * 4);
+    L.zs = o; o += conv5 ? np * kC5 * 4 : 0;             // conv5 pre-activations per node, fp32 [np][16]
     L.total = o;
     return L;
 }
 
 // bytes of one quad's slice when the CTA takes (almost) all of the SM's shared memory
-__host__ __device__ inline int quad_bytes(int f) {
-    return ((kSmemBudget - 1024 - shared_layout(f).total) / kQuads) & ~15;
-}
-
-// quads a graph of n nodes is given: enough warps for its 16-row tiles, enough memory
-__host__ __device__ inline int quads_needed(int f, int n) {
-    const int np = (n + 15) & ~15, tiles = np >> 4;
-    int q = tiles <= 4 ? 1 : (tiles <= 8 ? 2 : 4);
-    const int need = team_layout(f, np < 16 ? 16 : np).total, qb = quad_bytes(f);
-    while (q < kQuads && need > q * qb) q <<= 1;
-    return q;
+__host__ __device__ inline int quad_bytes(int f, bool conv5 = false) {
+    return ((kSmemBudget - 1024 - shared_layout(f, conv5).total) / kQuads) & ~15;
 }
 
 // tanh for the hidden layers: (1 - t) / (1 + t), t = 2^(-2 log2(e) |v|); two MUFU ops, no
@@ -222,13 +222,38 @@ __device__ __forceinline__ void project32(const float (&acc)[4][4], const __half
     }
 }
 
+// z += x_l @ W5[:, slice]^T on the tensor cores: x_l = the layer's tanh outputs in
+// the accumulator fragments (C layout of two n-tiles == A layout of one k-tile), split hi/lo;
+// W5 as hi/lo planes [plane][16][kW5Pad] (columns 0..95 of conv5's [16,97] weight).
+__device__ __forceinline__ void project16(const float (&y)[4][4], const __half* __restrict__ w5p, int slice,
+                                          int lane, float (&z)[2][4]) {
+    const int j = lane >> 3;
+    const uint32_t wbase = smem_u32(w5p) +
+        (uint32_t)(((j >> 1) * kC5 * kW5Pad + (lane & 7) * kW5Pad + (j & 1) * 8 + slice * kHid) * 2);
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        uint32_t ah[4], al[4];
+        split_pair(y[2 * kk][0], y[2 * kk][1], ah[0], al[0]);
+        split_pair(y[2 * kk][2], y[2 * kk][3], ah[1], al[1]);
+        split_pair(y[2 * kk + 1][0], y[2 * kk + 1][1], ah[2], al[2]);
+        split_pair(y[2 * kk + 1][2], y[2 * kk + 1][3], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            uint32_t h0, h1, l0, l1;
+            ldsm_x4(wbase + (uint32_t)((nt * 8 * kW5Pad + kk * 16) * 2), h0, h1, l0, l1);
+            mma_fp16(z[nt], ah, h0, h1);
+            mma_fp16(z[nt], al, h0, h1);
+            mma_fp16(z[nt], ah, l0, l1);
+        }
+    }
+}
+
 // tanh, x_l slice of x_cat to HBM, c_i * x_l as hi/lo planes for the next layer (out_pl),
 // and v = c_i (x_l . w4) for layer 4 (vpl).  y holds the pre-activations (C layout).
 __device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][4], int mt, int lane,
                                                float* __restrict__ xo, int64_t ldc, bool vec2,
                                                __half* __restrict__ out_pl, __half* __restrict__ vpl,
-                                               const float* __restrict__ w4s,
-                                               __half* out_pl_peer = nullptr, __half* vpl_peer = nullptr) {
+                                               const float* __restrict__ w4s) {
     const int g = lane >> 2, t = lane & 3;
     const int row0 = mt * 16 + g, row1 = row0 + 8;
 #pragma unroll
@@ -255,18 +280,13 @@ __device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][
     if (out_pl) {
         uint32_t* o0 = reinterpret_cast<uint32_t*>(out_pl + row0 * kRowH) + t;
         uint32_t* o1 = reinterpret_cast<uint32_t*>(out_pl + row1 * kRowH) + t;
-        // split graph: the same rows go into the peer CTA's copy (distributed shared memory)
-        uint32_t* q0 = out_pl_peer ? reinterpret_cast<uint32_t*>(out_pl_peer + row0 * kRowH) + t : nullptr;
-        uint32_t* q1 = out_pl_peer ? reinterpret_cast<uint32_t*>(out_pl_peer + row1 * kRowH) + t : nullptr;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             uint32_t hi, lo;
             split_pair(c0 * y[nt][0], c0 * y[nt][1], hi, lo);
             o0[nt * 4] = hi; o0[16 + nt * 4] = lo;
-            if (q0) { q0[nt * 4] = hi; q0[16 + nt * 4] = lo; }
             split_pair(c1 * y[nt][2], c1 * y[nt][3], hi, lo);
             o1[nt * 4] = hi; o1[16 + nt * 4] = lo;
-            if (q1) { q1[nt * 4] = hi; q1[16 + nt * 4] = lo; }
         }
     }
     if (vpl) {
@@ -284,26 +304,41 @@ __device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][
         if (t == 0) {
             store_split(vpl, vpl + c.S, row0, c0 * p0);
             store_split(vpl, vpl + c.S, row1, c1 * p1);
-            if (vpl_peer) {
-                store_split(vpl_peer, vpl_peer + c.S, row0, c0 * p0);
-                store_split(vpl_peer, vpl_peer + c.S, row1, c1 * p1);
-            }
         }
     }
 }
 
-// zeros over [beg, end) of a float array, 16-byte stores where the alignment allows (the array
-// itself is only 4-byte aligned: rows of 97 floats); strided over `nthreads` threads
-__device__ __forceinline__ void zero_fill(float* __restrict__ base, int beg, int end, int tid, int nthreads) {
-    if (beg >= end) return;
+// zeros over [beg, end) of a float array that is only 4-byte aligned (rows of 97 floats): the
+// 16-byte aligned body goes out as bulk async stores (TMA engine, cp.async.bulk shared -> global)
+// from a zeroed staging buffer, issued by the lanes of the team's first warp -- no store traffic
+// through the LSU, nothing for the team to wait for; head and tail (< 4 floats each) are plain
+// stores.  Returns true on the lanes that issued bulk stores (they call bulk_store_wait() before
+// the kernel ends).
+__device__ __forceinline__ bool zero_fill_bulk(float* __restrict__ base, int beg, int end, int tid,
+                                               uint32_t zero_smem) {
+    if (beg >= end) return false;
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(base + beg);
     const int head = min(end - beg, (int)(((16u - (unsigned)(a0 & 15u)) & 15u) >> 2));
-    const int body4 = (end - beg - head) >> 2;
+    const int body = ((end - beg - head) >> 2) << 4;                  // bytes, multiple of 16
+    const int tail0 = beg + head + (body >> 2);
     if (tid < head) base[beg + tid] = 0.f;
-    float4* b4 = reinterpret_cast<float4*>(base + beg + head);
-    for (int i = tid; i < body4; i += nthreads) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int tail0 = beg + head + 4 * body4;
     if (tid < end - tail0) base[tail0 + tid] = 0.f;
+    bool issued = false;
+    if (tid < 32 && tid * kZeroBytes < body) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        char* g = reinterpret_cast<char*>(base + beg + head);
+        for (int off = tid * kZeroBytes; off < body; off += 32 * kZeroBytes) {
+            const int bytes = min(kZeroBytes, body - off);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(g + off), "r"(zero_smem), "r"(bytes) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        issued = true;
+    }
+    return issued;
+}
+__device__ __forceinline__ void bulk_store_wait() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void load_bias(const float* __restrict__ bias, int t, float (&y)[4][4]) {
@@ -324,12 +359,15 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     const int nthreads = tm.nthreads, nwarps = tm.nwarps;
     const int f = p.f;
     const bool small_f = f <= kSmallF;
-    const SharedLayout SL = shared_layout(f);
+    const bool conv5 = p.h1 != nullptr;                  // conv5 + ReLU + max-pool fused in
+    const SharedLayout SL = shared_layout(f, conv5);
     const __half* w2p = reinterpret_cast<const __half*>(shraw + SL.w2p);
     const __half* w3p = reinterpret_cast<const __half*>(shraw + SL.w3p);
     const float* w1t = reinterpret_cast<const float*>(shraw + SL.w1t);
     const float* w4s = reinterpret_cast<const float*>(shraw + SL.misc);
     const float* b1s = w4s + kHid;                       // b1, b2, b3 contiguous
+    const __half* w5p = reinterpret_cast<const __half*>(shraw + SL.w5p);
+    const float* w5x = reinterpret_cast<const float*>(shraw + SL.w5x);      // W5[:, 96] | b5
     const float b4 = p.b4 ? p.b4[0] : 0.f;
 
     const int gi = e.gi, base = e.base, n = e.n;
@@ -346,9 +384,25 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
 #define KS_TRACE(slot) do { if (tracer) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
     // rows of `pooled` past the graph's last node: zeros (PyG's fill trick), perm -1.  Plain
     // stores, issued first: they drain while the team waits for its inputs.
-    zero_fill(pooled_g, keep * kCat, p.k * kCat, gtid, gthreads);
+    bool bulk_pending = false;
+    if (p.pooled) {
+        const int z0 = keep * kCat, z1 = p.k * kCat, zm = split ? z0 + (((z1 - z0) >> 1) & ~3) : z1;
+        bulk_pending = zero_fill_bulk(pooled_g, rank ? zm : z0, rank ? z1 : zm, tid,
+                                      smem_u32(shraw + SL.zero));
+    }
     for (int r = keep + gtid; r < p.k; r += gthreads) perm_g[r] = -1;
-    if (n == 0) return;
+    if (n == 0) {
+        if (bulk_pending) bulk_store_wait();
+        if (conv5) {                                   // every row is padding: z = b5
+            const int L1 = p.k >> 1;
+            for (int item = tid; item < kC5 * L1; item += nthreads) {
+                const float z = fmaxf(w5x[kC5 + item / L1], 0.f);
+                p.h1[(int64_t)gi * kC5 * L1 + item] = z;
+                p.arg[(int64_t)gi * kC5 * L1 + item] = (uint8_t)(z <= 0.f ? 2 : 0);
+            }
+        }
+        return;
+    }
     if (tracer) {
         uint32_t smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -362,10 +416,11 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     const int np = c.np;
     const int t0 = split ? (rank ? (c.T + 1) >> 1 : 0) : 0;          // this CTA's row tiles
     const int t1 = split ? (rank ? c.T : (c.T + 1) >> 1) : c.T;
-    const TeamLayout L = team_layout(f, np);
+    const TeamLayout L = team_layout(f, np, conv5);
     c.S = L.S;
     const int S = L.S;
     unsigned char* smraw = tm.smem;
+    float* zs = reinterpret_cast<float*>(smraw + L.zs);  // conv5 pre-activations per node [np][16]
     __half* PA = reinterpret_cast<__half*>(smraw + L.PA);
     __half* PB = reinterpret_cast<__half*>(smraw + L.PB);
     __half* vpl = reinterpret_cast<__half*>(smraw + L.vpl);
@@ -379,19 +434,31 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     float* stage = reinterpret_cast<float*>(PB);        // layer-1 inputs c_j x_j, fp32 [n][f] (F <= 8)
     float* wmax = reinterpret_cast<float*>(vpl);        // per-warp max |c_j x_j|
     c.fbm = fbm; c.cs = cs; c.rs = rs; c.rp = rp;
-    // the peer CTA's copies (same offsets in its shared memory)
-    __half *PA_peer = nullptr, *PB_peer = nullptr, *vpl_peer = nullptr;
-    float* key_peer = nullptr;
+    // split graph: rows are exchanged with bulk copies (pair_exchange below); only the sort ranks
+    // are scattered remote stores
     int* order_peer = nullptr;
+    uint32_t peer_mbar = 0, xparity = 0;
+    const uint32_t peer = (uint32_t)(rank ^ 1);
     if (split) {
         cg::cluster_group cluster = cg::this_cluster();
-        const unsigned peer = (unsigned)(rank ^ 1);
-        PA_peer = cluster.map_shared_rank(PA, peer);
-        PB_peer = cluster.map_shared_rank(PB, peer);
-        vpl_peer = cluster.map_shared_rank(vpl, peer);
-        key_peer = cluster.map_shared_rank(key, peer);
         order_peer = cluster.map_shared_rank(order, peer);
+        peer_mbar = map_to_peer(tm.mbar, peer);
     }
+    const int my_rows = (t1 - t0) * 16, peer_rows = np - my_rows, row0 = t0 * 16;
+    // push my rows of up to three row-major regions (row_bytes each) into the peer's copies and
+    // wait for the peer's rows; replaces the team barrier at the end of a phase
+    auto pair_exchange = [&](const void* b0, int rb0, const void* b1, int rb1, const void* b2, int rb2) {
+        tm.sync_local();                                 // my rows are complete in MY shared memory
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(tm.mbar, (uint32_t)(peer_rows * (rb0 + rb1 + rb2)));
+            push_to_peer(smem_addr_u32(b0) + (uint32_t)(row0 * rb0), (uint32_t)(my_rows * rb0), peer, peer_mbar);
+            if (rb1) push_to_peer(smem_addr_u32(b1) + (uint32_t)(row0 * rb1), (uint32_t)(my_rows * rb1), peer, peer_mbar);
+            if (rb2) push_to_peer(smem_addr_u32(b2) + (uint32_t)(row0 * rb2), (uint32_t)(my_rows * rb2), peer, peer_mbar);
+        }
+        mbar_wait(tm.mbar, xparity);
+        xparity ^= 1u;
+    };
 
     float* xc = p.xcat + (int64_t)base * p.ldc;
     const bool vec2 = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.xcat) & 7) == 0);
@@ -467,7 +534,6 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     for (int layer = 0; layer < 3; ++layer) {
         const __half* in_pl = layer == 1 ? PA : PB;
         __half* out_pl = layer == 0 ? PA : (layer == 1 ? PB : nullptr);
-        __half* out_peer = layer == 0 ? PA_peer : (layer == 1 ? PB_peer : nullptr);
         const __half* wp = layer == 1 ? w2p : w3p;
         const float* bias = b1s + layer * kHid;
         float* xo = xc + layer * kHid;
@@ -509,10 +575,34 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
                     project32(acc, wp, lane, y);
                 }
             }
-            layer_epilogue(c, y, mt, lane, xo, p.ldc, vec2, out_pl, layer == 2 ? vpl : nullptr, w4s, out_peer,
-                           layer == 2 ? vpl_peer : nullptr);
+            layer_epilogue(c, y, mt, lane, xo, p.ldc, vec2, out_pl, layer == 2 ? vpl : nullptr, w4s);
+            if (conv5) {
+                // y now holds x_l of this tile: z += x_l W5[:, 32 l .. 32 l + 31]^T (+ b5 first time).
+                // The same thread owns the same (row, channel) entries in every layer: no barrier.
+                float z[2][4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) z[nt][0] = z[nt][1] = z[nt][2] = z[nt][3] = 0.f;
+                project16(y, w5p, layer, lane, z);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int col = nt * 8 + 2 * t;
+                    float2* a0 = reinterpret_cast<float2*>(zs + (mt * 16 + g) * kC5 + col);
+                    float2* a1 = reinterpret_cast<float2*>(zs + (mt * 16 + g + 8) * kC5 + col);
+                    float2 v0, v1;
+                    if (layer == 0) {
+                        const float2 b = *reinterpret_cast<const float2*>(w5x + kC5 + col);
+                        v0 = b; v1 = b;
+                    } else {
+                        v0 = *a0; v1 = *a1;
+                    }
+                    v0.x += z[nt][0]; v0.y += z[nt][1]; v1.x += z[nt][2]; v1.y += z[nt][3];
+                    *a0 = v0; *a1 = v1;
+                }
+            }
         }
-        tm.sync();
+        if (!split) tm.sync();
+        else if (layer < 2) pair_exchange(out_pl, kRowB, nullptr, 0, nullptr, 0);
+        else pair_exchange(vpl, 2, vpl + S, 2, conv5 ? zs : nullptr, conv5 ? kC5 * 4 : 0);
         KS_TRACE(3 + layer);
     }
 
@@ -527,7 +617,6 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
                 if (row < n) {
                     const float x4 = tanhf(fmaf(rs[row], a4[2 * half], b4));
                     key[row] = x4;
-                    if (key_peer) key_peer[row] = x4;
                     float* o = xc + (int64_t)row * p.ldc + 3 * kHid;
                     // padded rows (ldc >= 100, 16-byte aligned): write the pad too, so that no
                     // 32-byte sector of x_cat is left partially written (a later read of such a
@@ -538,7 +627,8 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
             }
         }
     }
-    tm.sync();
+    if (!split) tm.sync();
+    else pair_exchange(key, 4, nullptr, 0, nullptr, 0);
     KS_TRACE(6);
 
     // ---- SortPool: order by x_4 descending, ties by node index -----------------------
@@ -594,7 +684,32 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     // ---- the k winners, one warp per row (rows of x_cat this team just wrote: L2 hits);
     //      sixteen rows in flight per warp, loads unconditional (clamped) so they all overlap:
     //      the copy is pure L2 latency ------------------------------------------------------
-    {
+    if (conv5) {
+        // conv5 pre-activation of pooled row r: z[order[r]] + W5[:, 96] x_4 (padding rows: b5), then
+        // ReLU and the max over the row pair (2j, 2j+1): h1[g][c][j]; arg = winning row, 2 = dead
+        const int L1 = p.k >> 1;
+        float* h1g = p.h1 + (int64_t)gi * kC5 * L1;
+        uint8_t* argg = p.arg + (int64_t)gi * kC5 * L1;
+        for (int item = gtid; item < kC5 * L1; item += gthreads) {
+            const int ch = item / L1, j = item - ch * L1;
+            float zr[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = 2 * j + u;
+                if (r < keep) {
+                    const int node = order[r];
+                    zr[u] = fmaf(w5x[ch], key[node], zs[node * kC5 + ch]);
+                } else {
+                    zr[u] = w5x[kC5 + ch];
+                }
+                zr[u] = fmaxf(zr[u], 0.f);
+            }
+            const float m = fmaxf(zr[0], zr[1]);
+            h1g[item] = m;
+            argg[item] = (uint8_t)(m <= 0.f ? 2 : (zr[0] >= zr[1] ? 0 : 1));
+        }
+    }
+    if (p.pooled) {
         const float* __restrict__ xsrc = xc;
         constexpr int R = 16;
         for (int r0 = gwarp * R; r0 < keep; r0 += gwarps * R) {
@@ -616,6 +731,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
         }
     }
     for (int r = gtid; r < keep; r += gthreads) perm_g[r] = base + order[r];
+    if (bulk_pending) bulk_store_wait();
     KS_TRACE(8);
     if (tracer) p.trace[(int64_t)gi * 16 + 10] = global_ns();
 #undef KS_TRACE
@@ -630,9 +746,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
     const int64_t cta_c0 = p.trace ? clock64() : 0;
     int64_t cta_c1 = 0, cta_c2 = 0;
     const int f = p.f;
-    const SharedLayout SL = shared_layout(f);
+    const bool conv5 = p.h1 != nullptr;
+    const SharedLayout SL = shared_layout(f, conv5);
     unsigned char* team_base = smraw + al16(SL.total);
-    const int budget = kQuads * quad_bytes(f);
+    const int budget = kQuads * quad_bytes(f, conv5);
     const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
     constexpr int kWarps = kFwdThreads / 32;
@@ -641,12 +758,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
     int excl = 0;                                    // graphs with an SM of their own (warp 0 only)
     int nsplit = 0;                                  // graphs split over a CTA pair (warp 0 only)
     uint32_t crank = 0;                              // rank of this CTA in its cluster
-    if (p.pairs) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    __shared__ __align__(8) uint64_t s_pair_mbar;    // exchange barrier of a graph split over the pair
+    if (p.pairs) {
+        asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        if (threadIdx.x == 0) mbar_init(smem_addr_u32(&s_pair_mbar), 1);   // (visible to the peer after the
+    }                                                                      //  split graph's first cluster barrier)
 
     for (int pass = 0;; ++pass) {
         if (warp_id == 0) {
             plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
-                      [f](int np) { return team_layout(f, np).total; }, s_plan, &s_count, nsplit,
+                      [f, conv5](int np) { return team_layout(f, np, conv5).total; }, s_plan, &s_count, nsplit,
                       p.pairs != 0, p.split_pct);
         } else if (pass == 0) {
             // meanwhile the other warps stage the weights: W1 transposed fp32 (F -> 32 stays on
@@ -690,6 +811,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
                     const int c = idx / f, k = idx - c * f;
                     w1t[k * kHid + c] = p.w1[idx];
                 }
+                {
+                    uint32_t* zb = reinterpret_cast<uint32_t*>(smraw + SL.zero);
+                    for (int idx = tid; idx < kZeroBytes / 4; idx += nthreads) zb[idx] = 0u;
+                }
+                if (conv5) {   // W5[:, 0..95] as hi/lo planes [16][kW5Pad]; W5[:, 96] and b5 in fp32
+                    __half* w5p = reinterpret_cast<__half*>(smraw + SL.w5p);
+                    float* w5x = reinterpret_cast<float*>(smraw + SL.w5x);
+                    for (int idx = tid; idx < kC5 * kCat; idx += nthreads) {
+                        const int c = idx / kCat, k = idx - c * kCat;
+                        const float v = p.w5[idx];
+                        if (k < 3 * kHid) store_split(w5p, w5p + kC5 * kW5Pad, c * kW5Pad + k, v);
+                        else w5x[c] = v;
+                    }
+                    if (tid < kC5) w5x[kC5 + tid] = p.b5 ? p.b5[tid] : 0.f;
+                }
             }
         }
         __syncthreads();                             // the plan (and, first time, the weights)
@@ -714,6 +850,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
                 tm.smem = team_base + e.smem_off;
                 tm.split = e.pad;                    // shared with the peer CTA of the cluster
                 tm.rank = (int)crank;
+                tm.mbar = smem_addr_u32(&s_pair_mbar);
                 if (p.trace && tm.tid == 0 && (!tm.split || crank == 0)) {
                     cta_c2 = clock64();
                     p.trace[(int64_t)e.gi * 16 + 11] = cta_t0;
@@ -754,43 +891,50 @@ extern "C" void dgcnn_stack_fwd_configure(int32_t pairs, int32_t split_pct) {
     if (split_pct > 0) g_split_pct = split_pct;
 }
 
-static int mma_supported(int32_t f, int64_t max_nodes) {
+static int mma_supported(int32_t f, int64_t max_nodes, bool conv5 = false) {
     if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
     const int np = (int)((max_nodes + 15) / 16 * 16);
-    return team_layout(f, np).total <= kQuads * quad_bytes(f) ? 1 : 0;
+    return team_layout(f, np, conv5).total <= kQuads * quad_bytes(f, conv5) ? 1 : 0;
 }
 
 extern "C" int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes) {
     return mma_supported(num_features, max_nodes);
 }
 
+extern "C" int dgcnn_stack_fwd_conv5_supported(int32_t num_features, int64_t max_nodes) {
+    return mma_supported(num_features, max_nodes, true);
+}
+
 extern "C" size_t dgcnn_stack_fwd_workspace_bytes(void) { return 256; }
 
-extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
-                               const int32_t* rowptr, const int32_t* col, const float* dis,
-                               const int32_t* gptr, const int32_t* gorder,
-                               const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
-                               const uint32_t* fragmap, const int32_t* fgoff, const int32_t* gdesc,
-                               int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
-                               const float* w1, const float* b1, const float* w2, const float* b2,
-                               const float* w3, const float* b3, const float* w4, const float* b4,
-                               float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
-                               int32_t norm, int32_t variant, int32_t* status, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+static int stack_fwd_impl(const float* x, int64_t ldx, int32_t num_features,
+                          const int32_t* rowptr, const int32_t* col, const float* dis,
+                          const int32_t* gptr, const int32_t* gorder,
+                          const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                          const uint32_t* fragmap, const int32_t* fgoff, const int32_t* gdesc,
+                          int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                          const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* w3, const float* b3, const float* w4, const float* b4,
+                          float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
+                          int32_t norm, int32_t variant, int32_t* status, void* workspace,
+                          size_t workspace_bytes, void* stream,
+                          const float* w5, const float* b5, float* h1, uint8_t* arg) {
+    const bool conv5 = h1 != nullptr;
     if (num_nodes < 0 || num_graphs < 0 || k < 1 || num_features < 1 || ldx < num_features ||
         ldc < kCat)
         return DGCNN_ERR_INVALID_ARGUMENT;
+    if (conv5 && (!w5 || !b5 || !arg || k < 2 || variant != DGCNN_STACK_MMA)) return DGCNN_ERR_INVALID_ARGUMENT;
     if (norm != DGCNN_NORM_SYM && norm != DGCNN_NORM_RW) return DGCNN_ERR_INVALID_ARGUMENT;
     if (variant != DGCNN_STACK_MMA && variant != DGCNN_STACK_FMA) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_graphs == 0) return DGCNN_OK;
     if (num_graphs >= INT32_MAX || num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
-    if (variant == DGCNN_STACK_MMA ? !mma_supported(num_features, max_nodes)
+    if (variant == DGCNN_STACK_MMA ? !mma_supported(num_features, max_nodes, conv5)
                                    : !dgcnn_stack_fwd_fma_supported(num_features, max_nodes))
         return DGCNN_ERR_UNSUPPORTED;
     if (!bitmap || !bmoff || !gflags) return DGCNN_ERR_INVALID_ARGUMENT;
     if (variant == DGCNN_STACK_MMA && (!fragmap || !fgoff || !gdesc)) return DGCNN_ERR_INVALID_ARGUMENT;
     if (max_nodes > 1024) return DGCNN_ERR_UNSUPPORTED;
-    if (!rowptr || !dis || !gptr || !w1 || !w2 || !w3 || !w4 || !xcat || !pooled || !perm ||
+    if (!rowptr || !dis || !gptr || !w1 || !w2 || !w3 || !w4 || !xcat || (!pooled && !conv5) || !perm ||
         (num_nodes > 0 && !x))
         return DGCNN_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < dgcnn_stack_fwd_workspace_bytes()) return DGCNN_ERR_WORKSPACE;
@@ -815,8 +959,9 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     p.norm = norm; p.nmax = (int)max_nodes;
     p.gdesc = gdesc; p.counter = counter; p.status = status;
     p.trace = g_trace;
+    p.w5 = w5; p.b5 = b5; p.h1 = h1; p.arg = arg;
     // one CTA per SM with (almost) all of its shared memory: 4 quad slices + the weights
-    const size_t smem = (size_t)al16(shared_layout(p.f).total) + (size_t)kQuads * quad_bytes(p.f);
+    const size_t smem = (size_t)al16(shared_layout(p.f, conv5).total) + (size_t)kQuads * quad_bytes(p.f, conv5);
     if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
@@ -868,4 +1013,43 @@ extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features
     }
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
+}
+
+extern "C" int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
+                               const int32_t* rowptr, const int32_t* col, const float* dis,
+                               const int32_t* gptr, const int32_t* gorder,
+                               const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                               const uint32_t* fragmap, const int32_t* fgoff, const int32_t* gdesc,
+                               int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                               const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* w3, const float* b3, const float* w4, const float* b4,
+                               float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
+                               int32_t norm, int32_t variant, int32_t* status, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    return stack_fwd_impl(x, ldx, num_features, rowptr, col, dis, gptr, gorder, bitmap, bmoff, gflags, fragmap,
+                          fgoff, gdesc, num_nodes, num_graphs, max_nodes, w1, b1, w2, b2, w3, b3, w4, b4, xcat,
+                          ldc, pooled, perm, k, norm, variant, status, workspace, workspace_bytes, stream,
+                          nullptr, nullptr, nullptr, nullptr);
+}
+
+// KS + the head of the dense tail (model.py:36-38): as dgcnn_stack_fwd, and
+// h1[g][c][j] = max(relu(conv5(pooled)[g][c][2j]), relu(...[2j+1])), arg = the winning row (2: dead).
+// `pooled` may be NULL: the [B, k*97] SortPooling output is then never materialised.
+extern "C" int dgcnn_stack_fwd_conv5(const float* x, int64_t ldx, int32_t num_features,
+                                     const int32_t* rowptr, const int32_t* col, const float* dis,
+                                     const int32_t* gptr, const int32_t* gorder,
+                                     const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                                     const uint32_t* fragmap, const int32_t* fgoff, const int32_t* gdesc,
+                                     int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                                     const float* w1, const float* b1, const float* w2, const float* b2,
+                                     const float* w3, const float* b3, const float* w4, const float* b4,
+                                     const float* w5, const float* b5,
+                                     float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
+                                     float* h1, uint8_t* arg, int32_t norm, int32_t* status, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    if (!h1 || !arg || !w5 || !b5) return DGCNN_ERR_INVALID_ARGUMENT;
+    return stack_fwd_impl(x, ldx, num_features, rowptr, col, dis, gptr, gorder, bitmap, bmoff, gflags, fragmap,
+                          fgoff, gdesc, num_nodes, num_graphs, max_nodes, w1, b1, w2, b2, w3, b3, w4, b4, xcat,
+                          ldc, pooled, perm, k, norm, DGCNN_STACK_MMA, status, workspace, workspace_bytes, stream,
+                          w5, b5, h1, arg);
 }

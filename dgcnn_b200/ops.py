@@ -393,6 +393,54 @@ def stack_fwd(x: Tensor, graph: Graph, weights, biases, k: int, norm: int
     return pooled, xcat, perm
 
 
+def stack_fwd_conv5_supported(num_features: int, max_nodes: int) -> bool:
+    """Can KS with the fused conv5 + ReLU + max-pool head hold the largest graph?"""
+    if max_nodes <= 0 or max_nodes > BITMAP_MAX_NODES or STACK_VARIANT != STACK_MMA:
+        return False
+    return bool(_lib.load_library().dgcnn_stack_fwd_conv5_supported(int(num_features), int(max_nodes)))
+
+
+def stack_fwd_conv5(x: Tensor, graph: Graph, weights, biases, w5: Tensor, b5: Tensor, k: int, norm: int,
+                    want_pooled: bool = False):
+    """KS + model.py:36-38 in one launch -> (h1 [B,16,k/2], arg u8 [B,16,k/2], xcat [N,97],
+    perm [B,k], pooled [B,k*97] or None).  Without `want_pooled` SortPooling's output is never
+    materialised."""
+    lib = _lib.load_library()
+    _require_cuda(x, "x", torch.float32)
+    n, f = x.shape
+    if len(weights) != 4 or [tuple(w.shape) for w in weights] != [(32, f), (32, 32), (32, 32), (1, 32)]:
+        raise ValueError("dgcnn_b200: stack_fwd_conv5 needs the model's F->32->32->32->1 weights")
+    if graph.gptr is None or graph.bitmap is None:
+        raise ValueError("dgcnn_b200: stack_fwd_conv5 needs a graph built with `batch` and `max_nodes`")
+    if w5.numel() != 16 * 97 or b5.numel() != 16:
+        raise ValueError("dgcnn_b200: conv5 must be Conv1d(1, 16, 97, 97)")
+    ws = [w.contiguous() for w in weights]
+    bs = [None if b is None else b.contiguous() for b in biases]
+    w5, b5 = w5.contiguous(), b5.contiguous()
+    for t in ws + [b for b in bs if b is not None] + [w5, b5]:
+        _require_cuda(t, "parameter", torch.float32)
+    b, k = graph.num_graphs, int(k)
+    dev = x.device
+    xcat = _empty(n, XCAT_LD, dtype=torch.float32, device=dev)[:, :97]
+    pooled = _empty(b, k * 97, dtype=torch.float32, device=dev) if want_pooled else None
+    perm = _empty(b, k, dtype=torch.int32, device=dev)
+    h1 = _empty(b, 16, k // 2, dtype=torch.float32, device=dev)
+    arg = _empty(b, 16, k // 2, dtype=torch.uint8, device=dev)
+    wsp = _workspace(lib.dgcnn_stack_fwd_workspace_bytes(), dev)
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_stack_fwd_conv5(_ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr), _ptr(graph.col),
+                                       _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder),
+                                       _ptr(graph.bitmap), _ptr(graph.bmoff), _ptr(graph.gflags),
+                                       _ptr(graph.fragmap), _ptr(graph.fgoff), _ptr(graph.gdesc), n, b,
+                                       int(graph.max_nodes), _ptr(ws[0]), _ptr(bs[0]), _ptr(ws[1]), _ptr(bs[1]),
+                                       _ptr(ws[2]), _ptr(bs[2]), _ptr(ws[3]), _ptr(bs[3]), _ptr(w5), _ptr(b5),
+                                       _ptr(xcat), XCAT_LD, _ptr(pooled), _ptr(perm), k, _ptr(h1), _ptr(arg),
+                                       int(norm), _ptr(graph.status), _ptr(wsp), wsp.numel(), _stream())
+    _lib.check(rc, "stack_fwd_conv5")
+    LAUNCHES["stack_fwd"] += 1 if b > 0 else 0
+    return h1, arg, xcat, perm, pooled
+
+
 def stack_bwd_supported(num_features: int, max_nodes: int) -> bool:
     return _stack_bwd_variant(num_features, max_nodes) is not None
 
@@ -452,27 +500,43 @@ def stack_bwd(dpooled: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Gra
     return out
 
 
-def tail_fwd(pooled: Tensor, k: int, params, training: bool, seed: int, rng_offset: Optional[Tensor]):
-    """KT forward (model.py:36-43) -> (logp [B,C], saved tensors for tail_bwd)."""
+def tail_fwd(pooled: Optional[Tensor], k: int, params, training: bool, seed: int, rng_offset: Optional[Tensor],
+             h1: Optional[Tensor] = None, arg: Optional[Tensor] = None):
+    """KT forward (model.py:36-43) -> (logp [B,C], saved tensors for tail_bwd).  With
+    ``pooled=None`` the conv5 + ReLU + max-pool head was already done by ``stack_fwd_conv5``
+     and ``h1`` / ``arg`` are inputs."""
     lib = _lib.load_library()
-    _require_cuda(pooled, "pooled", torch.float32)
     w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
     for t in (w5, b5, w6, b6, wf1, bf1, wf2, bf2):
         _require_cuda(t, "parameter", torch.float32)
-    pooled = pooled.contiguous()
-    b = pooled.size(0)
     k = int(k)
     l1 = k // 2
     d1 = 32 * (l1 - 4)
     c = wf2.size(0)
-    if pooled.numel() != b * k * 97 or tuple(wf1.shape) != (128, d1) or w5.numel() != 16 * 97 \
+    if pooled is not None:
+        _require_cuda(pooled, "pooled", torch.float32)
+        pooled = pooled.contiguous()
+        b = pooled.size(0)
+        if pooled.numel() != b * k * 97:
+            raise ValueError("dgcnn_b200: tail_fwd shape mismatch")
+    else:
+        if h1 is None or arg is None:
+            raise ValueError("dgcnn_b200: tail_fwd needs either pooled or (h1, arg)")
+        _require_cuda(h1, "h1", torch.float32)
+        _require_cuda(arg, "arg", torch.uint8)
+        b = h1.size(0)
+        if tuple(h1.shape) != (b, 16, l1) or tuple(arg.shape) != (b, 16, l1) or not h1.is_contiguous() \
+                or not arg.is_contiguous():
+            raise ValueError("dgcnn_b200: tail_fwd h1 / arg shape mismatch")
+    if tuple(wf1.shape) != (128, d1) or w5.numel() != 16 * 97 \
             or w6.numel() != 32 * 16 * 5 or wf2.size(1) != 128:
         raise ValueError("dgcnn_b200: tail_fwd shape mismatch")
-    dev = pooled.device
+    dev = w5.device
     f32 = dict(dtype=torch.float32, device=dev)
     u8 = dict(dtype=torch.uint8, device=dev)
-    h1 = _empty(b, 16, l1, **f32)
-    arg = _empty(b, 16, l1, **u8)
+    if pooled is not None:
+        h1 = _empty(b, 16, l1, **f32)
+        arg = _empty(b, 16, l1, **u8)
     h2 = _empty(b, d1, **f32)
     h3 = _empty(b, 128, **f32)
     keep = _empty(b, 128, **u8)
@@ -488,6 +552,84 @@ def tail_fwd(pooled: Tensor, k: int, params, training: bool, seed: int, rng_offs
     _lib.check(rc, "tail_fwd")
     LAUNCHES["tail_fwd"] += 5 if b > 0 else 0
     return logp, (pooled, h1, arg, h2, h3, keep)
+
+
+def tail_bwd_h1(dlogp: Tensor, logp: Tensor, saved, k: int, params, out_grads=None, defer_join: bool = False):
+    """KT backward stopped at d(h1) -> (dh1 [B,16,k/2], [dw6, db6, dwf1, dbf1, dwf2,
+    dbf2][, PendingTailGrads]); conv5's backward belongs to ``stack_bwd_conv5``."""
+    lib = _lib.load_library()
+    _, h1, _, h2, h3, keep = saved
+    w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
+    _require_cuda(dlogp, "dlogp", torch.float32)
+    dlogp = dlogp.contiguous()
+    b, c = logp.shape
+    dev = h1.device
+    dh1 = _empty(h1.shape, dtype=torch.float32, device=dev)
+    grads = list(out_grads) if out_grads is not None else \
+        [_empty(p.shape, dtype=p.dtype, device=p.device) for p in (w6, b6, wf1, bf1, wf2, bf2)]
+    for g_, p_ in zip(grads, (w6, b6, wf1, bf1, wf2, bf2)):
+        if g_.numel() != p_.numel() or not g_.is_contiguous():
+            raise ValueError("dgcnn_b200: tail_bwd_h1 out_grads mismatch")
+    ws = _workspace(lib.dgcnn_tail_workspace_bytes(b, int(k), c), dev)
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_tail_bwd_h1(_ptr(dlogp), b, int(k), _ptr(w6), _ptr(wf1), _ptr(wf2), c, _ptr(h1), _ptr(h2),
+                                   _ptr(h3), _ptr(keep), _ptr(logp), _ptr(dh1), *[_ptr(g) for g in grads],
+                                   (2 if defer_join else 1) if TAIL_OVERLAP else 0, _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "tail_bwd_h1")
+    LAUNCHES["tail_bwd"] += 9 if b > 0 else 0
+    if defer_join:
+        keepalive = (dlogp, logp, saved, grads, ws, dh1, w6, wf1, wf2) if TAIL_OVERLAP and b > 0 else None
+        return dh1, grads, PendingTailGrads(dev, keepalive)
+    return dh1, grads
+
+
+def stack_bwd_conv5_supported(num_features: int, max_nodes: int) -> bool:
+    if max_nodes <= 0 or max_nodes > BITMAP_MAX_NODES or STACK_VARIANT != STACK_MMA:
+        return False
+    return bool(_lib.load_library().dgcnn_stack_bwd_conv5_supported(int(num_features), int(max_nodes)))
+
+
+def stack_bwd_conv5(dh1: Tensor, arg: Tensor, perm: Tensor, xcat: Tensor, x: Tensor, graph: Graph, weights,
+                    w5: Tensor, k: int, norm: int, out: Optional[Tensor] = None):
+    """KSB fed with d(h1): gradients of the eight GraphConv parameters AND of conv5
+    (weight [16,1,97], bias [16]) as views of one flat buffer, in the model's parameter order."""
+    lib = _lib.load_library()
+    for t, name in ((dh1, "dh1"), (xcat, "xcat"), (x, "x"), (w5, "w5")):
+        _require_cuda(t, name, torch.float32)
+    _require_cuda(perm, "perm", torch.int32)
+    _require_cuda(arg, "arg", torch.uint8)
+    if graph.rowptr_t is None or graph.gptr is None or graph.bitmap is None:
+        raise ValueError("dgcnn_b200: stack_bwd_conv5 needs a graph built with batch, max_nodes and "
+                         "transpose=True")
+    n, f = x.shape
+    b = graph.num_graphs
+    dh1, arg, w5 = dh1.contiguous(), arg.contiguous(), w5.contiguous()
+    ws = [w.contiguous() for w in weights]
+    total = int(lib.dgcnn_stack_conv5_num_params(f))
+    grads = out if out is not None else _empty(total, dtype=torch.float32, device=x.device)
+    if grads.numel() != total or not grads.is_contiguous():
+        raise ValueError("dgcnn_b200: stack_bwd_conv5 out buffer mismatch")
+    wsp = _workspace(lib.dgcnn_stack_bwd_workspace_bytes(f, b, n), x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.dgcnn_stack_bwd_conv5(_ptr(dh1), _ptr(arg), _ptr(perm), int(k), _ptr(xcat), _rows(xcat, "xcat"),
+                                       _ptr(x), _rows(x, "x"), f, _ptr(graph.rowptr_t), _ptr(graph.col_t),
+                                       _ptr(graph.dis), _ptr(graph.gptr), _ptr(graph.gorder), _ptr(graph.gdesc),
+                                       _ptr(graph.fragmap), _ptr(graph.bitmap), _ptr(graph.bmoff),
+                                       _ptr(graph.gflags), _ptr(graph.bitmap_t), _ptr(graph.bmoff_t),
+                                       _ptr(graph.gflags_t), n, b, int(graph.max_nodes), _ptr(ws[1]), _ptr(ws[2]),
+                                       _ptr(ws[3]), _ptr(w5), int(norm), _ptr(grads), _ptr(graph.status),
+                                       _ptr(wsp), wsp.numel(), _stream())
+    _lib.check(rc, "stack_bwd_conv5")
+    LAUNCHES["stack_bwd"] += 2 if b > 0 else 0
+    outl, o = [], 0
+    for cout, cin in ((32, f), (32, 32), (32, 32), (1, 32)):
+        dw = grads[o:o + cout * cin].view(cout, cin)
+        o += cout * cin
+        db = grads[o:o + cout]
+        o += cout
+        outl.append((dw, db))
+    outl.append((grads[o:o + 16 * 97].view(16, 1, 97), grads[o + 16 * 97:o + 16 * 97 + 16]))
+    return outl
 
 
 class PendingTailGrads:

@@ -249,6 +249,32 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
                     int32_t norm, int32_t variant, int32_t* status,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* KS + the head of the dense tail (model.py:36-38 view -> conv5 -> ReLU ->
+ * MaxPool1d(2,2)) in the same launch.  conv5 = Conv1d(1,16,97,97) has kernel == stride == 97: it
+ * is a per-row 97 -> 16 linear map, so it commutes with SortPooling's row gather.  The kernel
+ * accumulates z = W5 x_cat[node] + b5 per NODE in the layer epilogues (tensor cores, hi/lo
+ * split) and, once the order is known, emits for the k winners
+ *     h1[g][c][j]  = max(relu(z[row 2j][c]), relu(z[row 2j+1][c]))     float [B,16,k/2]
+ *     arg[g][c][j] = 0 / 1 the winning row, 2 when the maximum is not positive   uint8 [B,16,k/2]
+ * (padding rows have z = b5) -- exactly what dgcnn_tail_fwd's first kernel computes from
+ * `pooled`.  `pooled` may be NULL: the [B, k*97] SortPooling output is then never written
+ * (-26 MB per COLLAB batch) and dgcnn_tail_fwd is called with pooled == NULL.
+ * Tensor-core variant only; dgcnn_stack_fwd_conv5_supported: the graphs need 64 bytes more
+ * shared memory per node than for dgcnn_stack_fwd. */
+int dgcnn_stack_fwd_conv5_supported(int32_t num_features, int64_t max_nodes);
+int dgcnn_stack_fwd_conv5(const float* x, int64_t ldx, int32_t num_features,
+                          const int32_t* rowptr, const int32_t* col, const float* dis,
+                          const int32_t* gptr, const int32_t* gorder,
+                          const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                          const uint32_t* fragmap, const int32_t* fgoff, const int32_t* gdesc,
+                          int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                          const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* w3, const float* b3, const float* w4, const float* b4,
+                          const float* w5, const float* b5,
+                          float* xcat, int64_t ldc, float* pooled, int32_t* perm, int32_t k,
+                          float* h1, uint8_t* arg, int32_t norm, int32_t* status,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * KSB  fused backward of the hot path (autograd of model.py:28-35, train.py:40),
  * companion of dgcnn_stack_fwd: from the gradient of `pooled` to the gradients of
@@ -293,6 +319,7 @@ int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_t k,
  * Limits: num_classes <= 32, k <= ~700 (shared-memory tiles).
  * ------------------------------------------------------------------------ */
 size_t dgcnn_tail_workspace_bytes(int64_t num_graphs, int32_t k, int32_t num_classes);
+/* pooled == NULL: h1 and arg are INPUTS (written by dgcnn_stack_fwd_conv5); conv5 is skipped. */
 int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k,
                    const float* w5, const float* b5, const float* w6, const float* b6,
                    const float* wf1, const float* bf1, const float* wf2, const float* bf2,
@@ -309,6 +336,38 @@ int dgcnn_tail_bwd(const float* dlogp, const float* pooled, int64_t num_graphs, 
                    float* dpooled, float* dw5, float* db5, float* dw6, float* db6,
                    float* dwf1, float* dbf1, float* dwf2, float* dbf2, int32_t overlap,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* KSB fed with d(h1) instead of d(pooled): the backward of conv5 + ReLU +
+ * MaxPool1d(2,2) (model.py:37-38) runs inside the fused graph backward.  Per graph:
+ *   dz[node][c] = dh1[c][r/2] if pooled row r = rank(node) won its pair (arg), else 0
+ *   d x_cat[node] = dz[node] W5     (per 32-column slice, on the tensor cores, where the layer's
+ *                                    gradient tile is assembled: no [B, k*97] dpooled in HBM)
+ *   dW5 = dz^T x_cat, db5 = column sums of dz over ALL k rows (padding rows included)
+ * `grads` receives dgcnn_stack_conv5_num_params(F) floats: the eight GraphConv gradients in
+ * dgcnn_stack_bwd's order followed by dW5 [16,97] and db5 [16] -- the next two tensors of the
+ * model's flat parameter order, so the buffer is one contiguous slice of it.  Bit-reproducible
+ * (static plan, ordered reductions).  Workspace: dgcnn_stack_bwd_workspace_bytes. */
+int dgcnn_stack_bwd_conv5_supported(int32_t num_features, int64_t max_nodes);
+int64_t dgcnn_stack_conv5_num_params(int32_t num_features);
+int dgcnn_stack_bwd_conv5(const float* dh1, const uint8_t* arg, const int32_t* perm, int32_t k,
+                          const float* xcat, int64_t ldc, const float* x, int64_t ldx,
+                          int32_t num_features, const int32_t* rowptr_t, const int32_t* col_t,
+                          const float* dis, const int32_t* gptr, const int32_t* gorder,
+                          const int32_t* gdesc, const uint32_t* fragmap,
+                          const uint32_t* bitmap, const int32_t* bmoff, const int32_t* gflags,
+                          const uint32_t* bitmap_t, const int32_t* bmoff_t, const int32_t* gflags_t,
+                          int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                          const float* w2, const float* w3, const float* w4, const float* w5,
+                          int32_t norm, float* grads, int32_t* status,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same backward stopped at d(h1) [B,16,k/2]: conv5's own backward
+ * (d x_cat, dw5, db5) runs inside dgcnn_stack_bwd_conv5.  Six parameter gradients. */
+int dgcnn_tail_bwd_h1(const float* dlogp, int64_t num_graphs, int32_t k, const float* w6,
+                      const float* wf1, const float* wf2, int32_t num_classes,
+                      const float* h1, const float* h2, const float* h3, const uint8_t* keep,
+                      const float* logp, float* dh1, float* dw6, float* db6, float* dwf1,
+                      float* dbf1, float* dwf2, float* dbf2, int32_t overlap,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* `overlap`: 0 = everything on `stream`.  1 = the parameter-gradient chain (dW/db of fc2, fc1,
  * conv6, conv5) runs on a side stream owned by the library, concurrently with the
  * input-gradient chain that produces dpooled, and is joined into `stream` before the call

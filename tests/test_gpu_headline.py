@@ -341,3 +341,129 @@ def test_cluster_split_is_bit_identical_to_the_plain_launch(name, count):
     for got in outs[1:]:
         for a, b_ in zip(outs[0], got):
             assert torch.equal(a, b_)
+
+
+# ---------------------------------------------------------------- conv5 + ReLU + max-pool inside KS
+@pytest.mark.parametrize("name,count,seed", [("collab", 512, 324), ("proteins", 128, 5), ("mutag", 50, 7),
+                                             ("collab", 5, 9)])
+def test_fused_conv5_head_matches_oracle_and_the_unfused_kernels(name, count, seed):
+    """dgcnn_stack_fwd_conv5: h1 / arg from the fused kernel against (a) conv5 -> ReLU -> MaxPool1d
+    of the float64 oracle on OUR pooled rows and (b) dgcnn_tail_fwd's own conv5 kernel; x_cat,
+    perm and pooled bit-identical to plain KS."""
+    cfg = CONFIGS[name]
+    batch = make_batch(name, num_graphs=count, seed=seed)
+    ref, model = oracle_and_model(cfg, seed=seed)
+    data = batch.to(DEV)
+    convs = (model.conv1, model.conv2, model.conv3, model.conv4)
+    weights, biases = [c.lin.weight for c in convs], [c.bias for c in convs]
+    with torch.no_grad():
+        g = model.build_graph(data)
+        pooled0, xcat0, perm0 = ops.stack_fwd(data.x, g, weights, biases, cfg.k, 0)
+        h1, arg, xcat, perm, pooled = ops.stack_fwd_conv5(data.x, g, weights, biases, model.conv5.weight,
+                                                          model.conv5.bias, cfg.k, 0, want_pooled=True)
+        h1n, argn, xcatn, permn, none = ops.stack_fwd_conv5(data.x, g, weights, biases, model.conv5.weight,
+                                                            model.conv5.bias, cfg.k, 0)
+    g.check()
+    assert none is None
+    assert torch.equal(xcat, xcat0) and torch.equal(perm, perm0) and torch.equal(pooled, pooled0)
+    assert torch.equal(h1, h1n) and torch.equal(arg, argn) and torch.equal(xcatn, xcat0) and torch.equal(permn, perm0)
+    # (a) float64 conv5 + ReLU + max-pool on our pooled rows
+    z = F.conv1d(pooled0.cpu().double().view(count, 1, -1), ref.conv5.weight, ref.conv5.bias, stride=97)
+    want = F.max_pool1d(F.relu(z), 2, 2)
+    assert h1.shape == want.shape
+    assert (h1.cpu().double() - want).abs().max().item() <= 2e-5 * max(1.0, float(want.abs().max()))
+    zr = F.relu(z)[:, :, : 2 * (cfg.k // 2)].reshape(count, 16, cfg.k // 2, 2)
+    clear = (zr[..., 0] - zr[..., 1]).abs() > 1e-4                      # winner not a rounding matter
+    warg = torch.where(zr.max(-1).values <= 0, torch.full_like(zr[..., 0], 2.0), (zr[..., 1] > zr[..., 0]).double())
+    dead_clear = (z[:, :, : 2 * (cfg.k // 2)].reshape(count, 16, cfg.k // 2, 2).abs() > 1e-4).all(-1)
+    sel = clear & dead_clear
+    assert torch.equal(arg.cpu().double()[sel], warg[sel])
+    # (b) the unfused conv5 kernel of the dense tail
+    tail = [model.conv5.weight, model.conv5.bias, model.conv6.weight, model.conv6.bias,
+            model.classifier_1.weight, model.classifier_1.bias, model.classifier_2.weight, model.classifier_2.bias]
+    with torch.no_grad():
+        _, saved = ops.tail_fwd(pooled0, cfg.k, tail, False, 0, None)
+    assert (h1 - saved[1]).abs().max().item() <= 2e-5 * max(1.0, float(want.abs().max()))
+
+
+def step_kernels(model, data, k, fused_conv5, training=True):
+    """The training step's kernels one by one through the operator layer: forward, NLL, backward.
+    fused_conv5: SURVEY 8f N2 path (stack_fwd_conv5 -> tail from h1 -> tail_bwd_h1 -> stack_bwd_conv5)
+    instead of (stack_fwd -> tail -> tail_bwd -> stack_bwd).  Returns (stats, 16 gradients, perm, keep)."""
+    convs = (model.conv1, model.conv2, model.conv3, model.conv4)
+    weights, biases = [c.lin.weight for c in convs], [c.bias for c in convs]
+    tail = [model.conv5.weight, model.conv5.bias, model.conv6.weight, model.conv6.bias,
+            model.classifier_1.weight, model.classifier_1.bias, model.classifier_2.weight, model.classifier_2.bias]
+    g = model.build_graph(data)
+    off = model._tail_rng_offset.clone()
+    with torch.no_grad():
+        if fused_conv5:
+            h1, arg, xcat, perm, _ = ops.stack_fwd_conv5(data.x, g, weights, biases, tail[0], tail[1], k, 0)
+            logp, saved = ops.tail_fwd(None, k, tail, training, model._tail_seed, off, h1=h1, arg=arg)
+            stats, dlogp = ops.nll_sum(logp, data.y, 1.0, True)
+            dh1, tg = ops.tail_bwd_h1(dlogp, logp, saved, k, tail)
+            sg = ops.stack_bwd_conv5(dh1, arg, perm, xcat, data.x, g, weights, tail[0], k, 0)
+            grads = [t for pair in sg for t in pair] + list(tg)
+        else:
+            pooled, xcat, perm = ops.stack_fwd(data.x, g, weights, biases, k, 0)
+            logp, saved = ops.tail_fwd(pooled, k, tail, training, model._tail_seed, off)
+            stats, dlogp = ops.nll_sum(logp, data.y, 1.0, True)
+            dpooled, tg = ops.tail_bwd(dlogp, logp, saved, k, tail)
+            sg = ops.stack_bwd(dpooled, perm, xcat, data.x, g, weights, k, 0)
+            grads = [t for pair in sg for t in pair] + list(tg)
+    g.check()
+    torch.cuda.synchronize()
+    return stats.clone(), [t.clone() for t in grads], perm.clone(), saved[5].clone(), xcat.clone()
+
+
+PARAM_NAMES = ["conv1.lin.weight", "conv1.bias", "conv2.lin.weight", "conv2.bias", "conv3.lin.weight", "conv3.bias",
+               "conv4.lin.weight", "conv4.bias", "conv5.weight", "conv5.bias", "conv6.weight", "conv6.bias",
+               "classifier_1.weight", "classifier_1.bias", "classifier_2.weight", "classifier_2.bias"]
+
+
+@pytest.mark.parametrize("name,count,seed", [("collab", 512, 324), ("proteins", 128, 5), ("mutag", 50, 7),
+                                             ("dd", 40, 3), ("collab", 2, 11)])
+def test_fused_conv5_backward_matches_the_unfused_kernels_and_the_oracle(name, count, seed):
+    """SURVEY 8f N2 end to end: loss, #correct and all 16 parameter gradients of the path that
+    never materialises pooled / dpooled against (a) the unfused kernel sequence and (b) the
+    float64 oracle continued from our permutation and dropout mask; bit-reproducible."""
+    cfg = CONFIGS[name]
+    batch = make_batch(name, num_graphs=count, seed=seed, tie_free=(name != "collab"))
+    mx = int((batch.ptr[1:] - batch.ptr[:-1]).max())
+    if not (ops.stack_fwd_conv5_supported(cfg.num_features, mx) and ops.stack_bwd_conv5_supported(cfg.num_features, mx)):
+        keep_ids = [i for i in range(count) if int(batch.ptr[i + 1] - batch.ptr[i]) <= 400]
+        from dgcnn_b200.synth import collate, make_graphs
+        graphs = make_graphs(cfg, count, seed, tie_free=True)
+        batch = collate([graphs[i] for i in keep_ids])
+        count = batch.num_graphs
+    ref, model = oracle_and_model(cfg, seed=seed, train=True)
+    data = batch.to(DEV)
+    k = cfg.k
+    st_f, gr_f, perm_f, keep_f, xcat_f = step_kernels(model, data, k, True)
+    st_u, gr_u, perm_u, keep_u, xcat_u = step_kernels(model, data, k, False)
+    assert torch.equal(perm_f, perm_u) and torch.equal(xcat_f, xcat_u)
+    assert abs(float(st_f[0]) - float(st_u[0])) <= 1e-4 * max(1.0, abs(float(st_u[0])))
+    for pname, a, b_ in zip(PARAM_NAMES, gr_f, gr_u):
+        scale = max(1e-3, float(b_.abs().max()))
+        if torch.equal(keep_f, keep_u):                  # same dropout decisions: same function
+            err = (a.reshape(-1) - b_.reshape(-1)).abs().max().item()
+            assert err <= 2e-3 * scale, f"{pname}: fused vs unfused {err:.3e} (scale {scale:.3e})"
+    st_f2, gr_f2, *_ = step_kernels(model, data, k, True)
+    assert torch.equal(st_f, st_f2) and all(torch.equal(a, b_) for a, b_ in zip(gr_f, gr_f2)), "not reproducible"
+    # (b) the float64 oracle from our permutation and our mask
+    ref.train()
+    rx, _ = ref.hot_path(batch.x.double(), batch.edge_index, batch.batch, count)
+    rpool = oracle_pooled_from_perm(rx, perm_f, count, k)
+    h = ref.pool(F.relu(ref.conv5(rpool.view(count, 1, -1))))
+    h = F.relu(ref.conv6(h)).flatten(1)
+    h = F.relu(ref.classifier_1(h)) * keep_f.cpu().double()
+    rlogp = F.log_softmax(ref.classifier_2(h), dim=-1)
+    rloss = F.nll_loss(rlogp, batch.y, reduction="sum")
+    rloss.backward()
+    assert abs(float(st_f[0]) - float(rloss.detach())) <= 1e-4 * max(1.0, abs(float(rloss.detach())))
+    rp = dict(ref.named_parameters())
+    for pname, gt in zip(PARAM_NAMES, gr_f):
+        want = rp[pname].grad
+        scale = max(1e-3, float(want.abs().max()))
+        err = (gt.cpu().double().view_as(want) - want).abs().max().item()
+        assert err <= 2e-3 * scale, f"{pname}: vs float64 oracle {err:.3e} (scale {scale:.3e})"

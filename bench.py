@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resident", action="store_true", help="skip the resident-data-set leg")
+    ap.add_argument("--no-fuse-conv5", action="store_true",
+                    help="keep conv5 + ReLU + max-pool out of KS / KSB (SURVEY 8f N2 off; A/B timing)")
     ap.add_argument("--autograd", action="store_true",
                     help="step through torch autograd (Model + GradBucket + FlatAdam) instead of FusedTrainer")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -240,6 +242,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.no_fuse_conv5:
+        ops.set_fuse_conv5(False)
     cfg = CONFIGS[args.workload]
     # weak scaling: every rank owns RING distinct batches of cfg.batch_size graphs
     host_batches = [make_batch(args.workload, seed=324 + 1000 * rank + i).pin_memory()
@@ -628,7 +632,9 @@ def main():
                            "+ grad all-reduce (N>1) + Adam (all hand-written kernels except NLL)",
                    "l2": f"flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every timed step; "
                          f"ring of {RING} distinct batches",
-                   "cuda_graph": use_graph, "fused_trainer": fused_step, "parallelism": f"dp{world} (graph-sharded)",
+                   "cuda_graph": use_graph, "fused_trainer": fused_step,
+                   "conv5_fused_into_graph_kernels": bool(fused_step and ops.conv5_fusable(cfg.num_features, db0.max_nodes)),
+                   "parallelism": f"dp{world} (graph-sharded)",
                    "gradient_exchange": comm_kind,
                    "wall_s_incl_flush": wall},
         "clocks": clocks.summary(),

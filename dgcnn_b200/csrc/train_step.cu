@@ -5,7 +5,22 @@
 // allocations: ~0.5 ms of interpreter time per step, more than the GPU needs for the
 // reference's small batches); this entry point is the same sequence without the interpreter.
 // No allocation, no synchronisation: capturable in a CUDA graph.
+#include <cstdlib>
+
 #include "common.cuh"
+
+// conv5 + ReLU + max-pool run inside KS / KSB whenever the batch fits (no pooled /
+// dpooled round trip).  dgcnn_train_step_configure(0) or DGCNN_FUSE_CONV5=0 keeps the unfused
+// sequence (A/B timing, tests).
+static int g_fuse_conv5 = -1;
+extern "C" void dgcnn_train_step_configure(int32_t fuse_conv5) { g_fuse_conv5 = fuse_conv5 < 0 ? -1 : (fuse_conv5 != 0); }
+static bool fuse_conv5_enabled() {
+    if (g_fuse_conv5 < 0) {
+        const char* env = getenv("DGCNN_FUSE_CONV5");
+        g_fuse_conv5 = !(env && env[0] == '0');
+    }
+    return g_fuse_conv5 != 0;
+}
 
 namespace {
 
@@ -24,7 +39,7 @@ struct Arena {
 struct StepBuffers {
     int32_t *rowptr, *col, *rowptr_t, *col_t, *gptr, *gorder, *bmoff, *gflags, *gflags_t, *fgoff, *gdesc, *perm;
     uint32_t *bitmap, *bitmap_t, *fragmap;
-    float *dis, *xcat, *pooled, *h1, *h2, *h3, *logp, *dlogp, *dpooled;
+    float *dis, *xcat, *pooled, *h1, *h2, *h3, *logp, *dlogp, *dpooled, *dh1;
     uint8_t *arg, *keep;
     void *ws_build, *ws_fwd, *ws_tail_f, *ws_tail_b, *ws_bwd;
     size_t n_build, n_fwd, n_tail, n_bwd;
@@ -37,9 +52,16 @@ struct StepBuffers {
 
 constexpr int kXcatLd = 100;
 
+// does this step run conv5 + ReLU + max-pool inside KS / KSB (no pooled / dpooled at all)?
+bool step_fuses_conv5(int32_t F, int64_t max_nodes) {
+    return fuse_conv5_enabled() && dgcnn_stack_bwd_supported(F, max_nodes) == 1 &&
+           dgcnn_stack_fwd_conv5_supported(F, max_nodes) && dgcnn_stack_bwd_conv5_supported(F, max_nodes);
+}
+
 StepBuffers carve(Arena& a, int64_t N, int64_t E, int64_t B, int32_t F, int32_t k, int32_t C,
                   int64_t max_nodes, bool resident) {
     StepBuffers s{};
+    const bool fused5 = step_fuses_conv5(F, max_nodes);
     const int64_t l1 = k / 2, d1 = 32 * (l1 - 4);
     s.bm_words = dgcnn_graph_bitmap_words(N, B, max_nodes);
     s.fm_words = dgcnn_graph_fragmap_words(N, B, max_nodes);
@@ -59,7 +81,7 @@ StepBuffers carve(Arena& a, int64_t N, int64_t E, int64_t B, int32_t F, int32_t 
     s.fgoff = a.take<int32_t>(B + 1);
     s.gdesc = a.take<int32_t>(4 * B);
     s.xcat = a.take<float>(N * kXcatLd);
-    s.pooled = a.take<float>(B * k * 97);
+    s.pooled = fused5 ? nullptr : a.take<float>(B * k * 97);   // N2: SortPooling's output is never materialised
     s.perm = a.take<int32_t>(B * k);
     s.h1 = a.take<float>(B * 16 * l1);
     s.arg = a.take<uint8_t>(B * 16 * l1);
@@ -68,7 +90,8 @@ StepBuffers carve(Arena& a, int64_t N, int64_t E, int64_t B, int32_t F, int32_t 
     s.keep = a.take<uint8_t>(B * 128);
     s.logp = a.take<float>(B * C);
     s.dlogp = a.take<float>(B * C);
-    s.dpooled = a.take<float>(B * k * 97);
+    s.dpooled = fused5 ? nullptr : a.take<float>(B * k * 97);
+    s.dh1 = a.take<float>(B * 16 * l1);
     s.n_build = resident ? dgcnn_collate_workspace_bytes(B) : dgcnn_build_graph_workspace_bytes(N, E);
     s.n_fwd = dgcnn_stack_fwd_workspace_bytes();
     s.n_tail = dgcnn_tail_workspace_bytes(B, k, C);
@@ -184,6 +207,24 @@ int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, in
                                       t.max_nodes, s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags,
                                       s.gflags_t, s.fragmap, s.fm_words, s.fgoff, s.gorder, s.gdesc,
                                       t.graph_status, DGCNN_GRAPH_GENERIC, stream));
+    if (step_fuses_conv5(F, t.max_nodes)) {
+        // N2: KS emits h1 / arg, the tail starts at conv6, its backward stops at d(h1), KSB does the
+        // rest and writes the ten gradients g[0..9] (GraphConv + conv5: one contiguous slice)
+        DGCNN_TRY(dgcnn_stack_fwd_conv5(x, ldx, F, s.rowptr, s.col, s.dis, s.gptr, s.gorder, s.bitmap, s.bmoff,
+                                        s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, t.max_nodes, p[0], p[1], p[2],
+                                        p[3], p[4], p[5], p[6], p[7], p[8], p[9], s.xcat, kXcatLd, nullptr, s.perm,
+                                        k, s.h1, s.arg, t.norm, t.graph_status, s.ws_fwd, s.n_fwd, stream));
+        DGCNN_TRY(dgcnn_tail_fwd(nullptr, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, t.training,
+                                 t.seed, t.rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp, s.ws_tail_f,
+                                 s.n_tail, stream));
+        DGCNN_TRY(dgcnn_nll_sum(s.logp, y, B, C, 1.0f, stats, s.dlogp, stream));
+        DGCNN_TRY(dgcnn_tail_bwd_h1(s.dlogp, B, k, p[10], p[12], p[14], C, s.h1, s.h2, s.h3, s.keep, s.logp, s.dh1,
+                                    g[10], g[11], g[12], g[13], g[14], g[15], 2, s.ws_tail_b, s.n_tail, stream));
+        DGCNN_TRY(dgcnn_stack_bwd_conv5(s.dh1, s.arg, s.perm, k, s.xcat, kXcatLd, x, ldx, F, s.rowptr_t, s.col_t,
+                                        s.dis, s.gptr, s.gorder, s.gdesc, s.fragmap, s.bitmap, s.bmoff, s.gflags,
+                                        s.bitmap_t, s.bmoff, s.gflags_t, N, B, t.max_nodes, p[2], p[4], p[6], p[8],
+                                        t.norm, t.grads, t.graph_status, s.ws_bwd, s.n_bwd, stream));
+    } else {
     DGCNN_TRY(dgcnn_stack_fwd(x, ldx, F, s.rowptr, s.col, s.dis, s.gptr, s.gorder, s.bitmap, s.bmoff,
                               s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, t.max_nodes, p[0], p[1], p[2], p[3],
                               p[4], p[5], p[6], p[7], s.xcat, kXcatLd, s.pooled, s.perm, k, t.norm,
@@ -201,6 +242,7 @@ int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, in
                               s.bmoff, s.gflags_t, N, B, t.max_nodes, p[2], p[4], p[6], t.norm,
                               bwd_kind == 1 ? DGCNN_STACK_MMA : DGCNN_STACK_FMA, t.grads, t.graph_status,
                               s.ws_bwd, s.n_bwd, stream));
+    }
     DGCNN_TRY(dgcnn_tail_bwd_join(stream));
     const float scale = 1.0f / (float)t.global_batch;
     if (t.world > 1 && t.exchange) {

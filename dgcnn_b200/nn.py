@@ -129,6 +129,52 @@ class _TailFn(torch.autograd.Function):
         return (dpooled if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
 
 
+class _StackConv5Fn(torch.autograd.Function):
+    """model.py:28-38 as ONE autograd node: KS with conv5 + ReLU + MaxPool1d fused
+    in, so SortPooling's [B, k*97] output and its gradient never exist.  Returns h1 [B,16,k/2]."""
+
+    @staticmethod
+    def forward(ctx, x, graph: Graph, k: int, norm: int, *params):
+        weights, biases, (w5, b5) = params[0:8:2], params[1:8:2], params[8:10]
+        x = x if x.stride(-1) == 1 else x.contiguous()
+        h1, arg, xcat, perm, _ = ops.stack_fwd_conv5(x, graph, weights, biases, w5, b5, k, norm)
+        ctx.graph, ctx.norm, ctx.k = graph, norm, k
+        ctx.save_for_backward(x, xcat, perm, arg, w5, *weights)
+        ctx.mark_non_differentiable(arg)
+        return h1, arg
+
+    @staticmethod
+    def backward(ctx, dh1, _darg):
+        x, xcat, perm, arg, w5, *weights = ctx.saved_tensors
+        if ctx.graph.rowptr_t is None:
+            raise RuntimeError("dgcnn_b200: graph was built with transpose=False; no backward")
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("dgcnn_b200: the fused conv5 path has no gradient w.r.t. the node features; "
+                               "call ops.set_fuse_conv5(False)")
+        pairs = ops.stack_bwd_conv5(dh1.contiguous(), arg, perm, xcat, x, ctx.graph, weights, w5, ctx.k, ctx.norm)
+        flat = []
+        for dw, db in pairs:
+            flat += [dw, db]
+        return (None, None, None, None, *flat)
+
+
+class _TailH1Fn(torch.autograd.Function):
+    """model.py:39-43 (conv6 ... log_softmax) from h1; conv5's gradients come from _StackConv5Fn."""
+
+    @staticmethod
+    def forward(ctx, h1, arg, k, training, seed, rng_offset, *params):
+        logp, saved = ops.tail_fwd(None, k, params, training, seed, rng_offset, h1=h1.contiguous(), arg=arg)
+        ctx.k = k
+        ctx.save_for_backward(logp, *saved[1:], *params)
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        logp, h1, arg, h2, h3, keep, *params = ctx.saved_tensors
+        dh1, grads = ops.tail_bwd_h1(dlogp, logp, (None, h1, arg, h2, h3, keep), ctx.k, params)
+        return (dh1, None, None, None, None, None, None, None, *grads)
+
+
 class _StackFn(torch.autograd.Function):
     """model.py:28-35 as ONE autograd node: L x tanh(GCNConv) written in place into
     the concatenated [N, sum(Cout)] buffer, then SortPooling.  Backward scatters the
@@ -388,5 +434,25 @@ class Model(nn.Module):
         return F.log_softmax(self.classifier_2(h), dim=-1)
 
     def forward(self, data) -> Tensor:
-        pooled, _, _ = self.hot_path(data.x, self.build_graph(data))
+        graph = self.build_graph(data)
+        x = data.x
+        if (fused_enabled() and custom_tail_enabled() and x.is_cuda and not x.requires_grad
+                and graph.bitmap is not None and self.classifier_2.out_features <= 32
+                and ops.conv5_fusable(x.size(1), graph.max_nodes)):
+            # conv5 + ReLU + max-pool inside the fused graph kernels
+            convs = (self.conv1, self.conv2, self.conv3, self.conv4)
+            params = []
+            for c in convs:
+                if c.bias is None:
+                    break
+                params += [c.lin.weight, c.bias]
+            if len(params) == 8:
+                h1, arg = _StackConv5Fn.apply(x, graph, self.sort_pool.k, self.conv1.norm, *params,
+                                              self.conv5.weight, self.conv5.bias)
+                tail = (self.conv5.weight, self.conv5.bias, self.conv6.weight, self.conv6.bias,
+                        self.classifier_1.weight, self.classifier_1.bias,
+                        self.classifier_2.weight, self.classifier_2.bias)
+                return _TailH1Fn.apply(h1, arg, self.sort_pool.k, self.training, self._tail_seed,
+                                       self._tail_rng_offset, *tail)
+        pooled, _, _ = self.hot_path(x, graph)
         return self.tail(pooled)

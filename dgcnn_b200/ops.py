@@ -28,6 +28,8 @@ STACK_MMA, STACK_FMA = 0, 1
 EXACT_SYMMETRY_CHECK = os.environ.get("DGCNN_EXACT_SYMMETRY", "0") == "1"
 # parameter gradients of the dense tail on a side stream (set DGCNN_TAIL_OVERLAP=0 to serialise)
 TAIL_OVERLAP = os.environ.get("DGCNN_TAIL_OVERLAP", "1") != "0"
+# conv5 + ReLU + max-pool (model.py:36-38) and their backward inside KS / KSB
+FUSE_CONV5 = os.environ.get("DGCNN_FUSE_CONV5", "1") != "0"
 XCAT_LD = 100     # row stride (floats) of the x_cat buffer the fused forward allocates
 # implementation of the fused forward; tests flip it to cross-check the two kernels
 STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower() == "fma" else STACK_MMA
@@ -37,6 +39,18 @@ STACK_VARIANT = STACK_FMA if os.environ.get("DGCNN_STACK_VARIANT", "mma").lower(
 LAUNCHES = {"build_graph": 0, "graph_ptr": 0, "graph_conv_fwd": 0, "graph_conv_bwd": 0,
             "sort_pool_fwd": 0, "sort_pool_bwd": 0, "stack_fwd": 0, "stack_bwd": 0,
             "build_bitmaps": 0, "tail_fwd": 0, "tail_bwd": 0, "adam_step": 0, "nll_sum": 0}
+
+
+def set_fuse_conv5(enabled: bool) -> None:
+    """Switch the N2 fusion on / off everywhere (Python paths and dgcnn_train_step)."""
+    global FUSE_CONV5
+    FUSE_CONV5 = bool(enabled)
+    _lib.load_library().dgcnn_train_step_configure(int(FUSE_CONV5))
+
+
+def conv5_fusable(num_features: int, max_nodes: int) -> bool:
+    return (FUSE_CONV5 and STACK_VARIANT == STACK_MMA and stack_fwd_conv5_supported(num_features, max_nodes)
+            and stack_bwd_conv5_supported(num_features, max_nodes))
 
 
 def launches_total() -> int:

@@ -112,16 +112,28 @@ class FusedTrainer:
         weights = self.stack_params[0::2]
         biases = self.stack_params[1::2]
         k, norm = m.sort_pool.k, m.conv1.norm
-        pooled, xcat, perm = ops.stack_fwd(data.x, graph, weights, biases, k, norm)
-        logp, saved = ops.tail_fwd(pooled, k, self.tail_params, m.training, m._tail_seed,
-                                   m._tail_rng_offset)
-        _, dlogp = ops.nll_sum(logp, data.y, 1.0, True, stats=self.stats)
-        # the tail's parameter gradients run on a side stream underneath KSB; joined before
-        # the all-reduce / Adam read them
-        dpooled, _, pending = ops.tail_bwd(dlogp, logp, saved, k, self.tail_params,
-                                           out_grads=self.tail_grad_views, defer_join=True)
-        ops.stack_bwd(dpooled, perm, xcat, data.x, graph, weights, k, norm,
-                      out=self.grad[:self.num_stack])
+        if ops.conv5_fusable(data.x.size(1), graph.max_nodes):
+            # no pooled / dpooled; KSB writes the GraphConv + conv5 gradients
+            h1, arg, xcat, perm, _ = ops.stack_fwd_conv5(data.x, graph, weights, biases, self.tail_params[0],
+                                                         self.tail_params[1], k, norm)
+            logp, saved = ops.tail_fwd(None, k, self.tail_params, m.training, m._tail_seed,
+                                       m._tail_rng_offset, h1=h1, arg=arg)
+            _, dlogp = ops.nll_sum(logp, data.y, 1.0, True, stats=self.stats)
+            dh1, _, pending = ops.tail_bwd_h1(dlogp, logp, saved, k, self.tail_params,
+                                              out_grads=self.tail_grad_views[2:], defer_join=True)
+            ops.stack_bwd_conv5(dh1, arg, perm, xcat, data.x, graph, weights, self.tail_params[0], k, norm,
+                                out=self.grad[:self.num_stack + 16 * 97 + 16])
+        else:
+            pooled, xcat, perm = ops.stack_fwd(data.x, graph, weights, biases, k, norm)
+            logp, saved = ops.tail_fwd(pooled, k, self.tail_params, m.training, m._tail_seed,
+                                       m._tail_rng_offset)
+            _, dlogp = ops.nll_sum(logp, data.y, 1.0, True, stats=self.stats)
+            # the tail's parameter gradients run on a side stream underneath KSB; joined before
+            # the all-reduce / Adam read them
+            dpooled, _, pending = ops.tail_bwd(dlogp, logp, saved, k, self.tail_params,
+                                               out_grads=self.tail_grad_views, defer_join=True)
+            ops.stack_bwd(dpooled, perm, xcat, data.x, graph, weights, k, norm,
+                          out=self.grad[:self.num_stack])
         pending.join()
         if global_batch is None:
             global_batch = graph.num_graphs * world
@@ -185,8 +197,10 @@ class FusedTrainer:
             raise RuntimeError("FusedTrainer.step_resident: the batch holds graphs too large for the fused "
                                "kernels (dgcnn_stack_fwd_supported); feed it through step()")
         _lib.check(rc, "train_step_resident")
-        # n1_gather + KS + 5 tail fwd + NLL + 12 tail bwd + 2 KSB + 2 Adam (profiles/r01_launches_resident_step.md)
-        ops.LAUNCHES["train_step_resident"] = ops.LAUNCHES.get("train_step_resident", 0) + (23 if b <= 1024 else 24)
+        # n1_gather + KS + 5 tail fwd + NLL + 12 tail bwd + 2 KSB + 2 Adam; with conv5 fused into KS / KSB
+        #  the tail loses its conv5 forward kernel and three backward ones
+        launches = (19 if ops.conv5_fusable(f, mx) else 23) + (0 if b <= 1024 else 1)
+        ops.LAUNCHES["train_step_resident"] = ops.LAUNCHES.get("train_step_resident", 0) + launches
         return self.stats
 
     def _native_step(self, data, global_batch, world) -> bool:
@@ -231,5 +245,5 @@ class FusedTrainer:
         if rc == -2:                                       # DGCNN_ERR_UNSUPPORTED: graphs too large for KS / KSB
             return False
         _lib.check(rc, "train_step")
-        ops.LAUNCHES["train_step"] = ops.LAUNCHES.get("train_step", 0) + 29
+        ops.LAUNCHES["train_step"] = ops.LAUNCHES.get("train_step", 0) + (25 if ops.conv5_fusable(f, mx) else 29)
         return True

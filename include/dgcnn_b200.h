@@ -440,6 +440,11 @@ int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg, float* exp
  * Needs graphs that fit the fused kernels (dgcnn_stack_fwd_supported / _bwd_supported), else
  * DGCNN_ERR_UNSUPPORTED.  No allocation, no synchronisation: capturable in a CUDA graph.
  * ------------------------------------------------------------------------ */
+/* SURVEY.md 8f N2 switch of dgcnn_train_step / dgcnn_train_step_resident: 1 (default, also
+ * DGCNN_FUSE_CONV5 unset) runs conv5 + ReLU + max-pool and their backward inside KS / KSB whenever
+ * the batch fits (dgcnn_stack_fwd_conv5_supported / dgcnn_stack_bwd_conv5_supported); 0 keeps the
+ * unfused sequence; -1 re-reads the environment. */
+void dgcnn_train_step_configure(int32_t fuse_conv5);
 size_t dgcnn_train_step_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t num_graphs,
                                         int32_t num_features, int32_t k, int32_t num_classes,
                                         int64_t max_nodes);

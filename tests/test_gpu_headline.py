@@ -142,20 +142,12 @@ def test_fused_trainer_step_collab_bs512_vs_float64_oracle():
     data = batch.to(DEV)
     b, k = batch.num_graphs, cfg.k
 
-    # (a) the step's kernels one by one through the operator layer, on a copy of the model
+    # (a) the step's kernels one by one through the operator layer, on a copy of the model (the
+    #     SURVEY 8f N2 sequence when the batch fits it: exactly what the native step launches)
     m_seq = copy.deepcopy(model)
-    convs = (m_seq.conv1, m_seq.conv2, m_seq.conv3, m_seq.conv4)
-    weights, biases = [c.lin.weight for c in convs], [c.bias for c in convs]
-    tail = [m_seq.conv5.weight, m_seq.conv5.bias, m_seq.conv6.weight, m_seq.conv6.bias,
-            m_seq.classifier_1.weight, m_seq.classifier_1.bias, m_seq.classifier_2.weight, m_seq.classifier_2.bias]
-    g = m_seq.build_graph(data)                        # grad mode on: the transposed CSR / maps are built too
-    with torch.no_grad():
-        pooled, xcat, perm = ops.stack_fwd(data.x, g, weights, biases, k, 0)
-        logp, saved = ops.tail_fwd(pooled, k, tail, True, m_seq._tail_seed, m_seq._tail_rng_offset.clone())
-        stats, dlogp = ops.nll_sum(logp, data.y, 1.0, True)
-        dpooled, tgrads = ops.tail_bwd(dlogp, logp, saved, k, tail)
-        sgrads = ops.stack_bwd(dpooled, perm, xcat, data.x, g, weights, k, 0)
-    keep = saved[5].cpu().double()
+    fused5 = ops.conv5_fusable(cfg.num_features, int((batch.ptr[1:] - batch.ptr[:-1]).max()))
+    stats, got, perm, keep_u8, xcat = step_kernels(m_seq, data, k, fused5)
+    keep = keep_u8.cpu().double()
 
     # (b) the oracle in float64 from our permutation and our dropout mask
     rx, _ = ref.hot_path(batch.x.double(), batch.edge_index, batch.batch, b)
@@ -175,7 +167,6 @@ def test_fused_trainer_step_collab_bs512_vs_float64_oracle():
     names = ["conv1.lin.weight", "conv1.bias", "conv2.lin.weight", "conv2.bias", "conv3.lin.weight", "conv3.bias",
              "conv4.lin.weight", "conv4.bias", "conv5.weight", "conv5.bias", "conv6.weight", "conv6.bias",
              "classifier_1.weight", "classifier_1.bias", "classifier_2.weight", "classifier_2.bias"]
-    got = [t for pair in sgrads for t in pair] + list(tgrads)
     rp = dict(ref.named_parameters())
     for name, gt in zip(names, got):
         want = rp[name].grad
@@ -467,3 +458,52 @@ def test_fused_conv5_backward_matches_the_unfused_kernels_and_the_oracle(name, c
         scale = max(1e-3, float(want.abs().max()))
         err = (gt.cpu().double().view_as(want) - want).abs().max().item()
         assert err <= 2e-3 * scale, f"{pname}: vs float64 oracle {err:.3e} (scale {scale:.3e})"
+
+
+def test_training_with_and_without_the_conv5_fusion_agree():
+    """Three optimisation steps of FusedTrainer (native one-call step and the Python sequence) with
+    SURVEY 8f N2 on and off: same losses and parameters up to fp32 rounding; the fused step
+    launches four kernels fewer."""
+    cfg = CONFIGS["collab"]
+    batches = [make_batch("collab", seed=40 + i, num_graphs=96).to(DEV) for i in range(3)]
+    torch.manual_seed(9)
+    base = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    results = {}
+    try:
+        for fuse in (True, False):
+            ops.set_fuse_conv5(fuse)
+            tr = dg.FusedTrainer(copy.deepcopy(base))
+            before = ops.LAUNCHES.get("train_step", 0)
+            losses = [float(tr.step(d)[0]) for d in batches]
+            results[fuse] = (losses, tr.flat.clone(), ops.LAUNCHES.get("train_step", 0) - before)
+    finally:
+        ops.set_fuse_conv5(True)
+    (la, pa, na), (lb, pb, nb) = results[True], results[False]
+    assert na == 3 * 25 and nb == 3 * 29
+    for x_, y_ in zip(la, lb):
+        assert abs(x_ - y_) <= 1e-4 * max(1.0, abs(y_))
+    assert (pa - pb).abs().max().item() <= 2e-5
+
+
+def test_model_autograd_uses_the_conv5_fusion_and_matches_the_unfused_model():
+    """Model(data) + loss.backward() (the reference's train.py:37-40) goes through the N2 autograd
+    nodes; gradients equal the unfused autograd path up to fp32 rounding."""
+    cfg = CONFIGS["proteins"]
+    data = make_batch("proteins", num_graphs=64, seed=3, tie_free=True).to(DEV)
+    torch.manual_seed(2)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).eval()
+    grads = {}
+    try:
+        for fuse in (True, False):
+            ops.set_fuse_conv5(fuse)
+            model.zero_grad()
+            before = ops.LAUNCHES["tail_fwd"]
+            out = model(data)
+            F.nll_loss(out, data.y).backward()
+            grads[fuse] = (out.detach().clone(), [p.grad.clone() for p in model.parameters()])
+    finally:
+        ops.set_fuse_conv5(True)
+    assert (grads[True][0] - grads[False][0]).abs().max().item() <= 1e-5
+    for (n_, _), a, b_ in zip(model.named_parameters(), grads[True][1], grads[False][1]):
+        scale = max(1e-3, float(b_.abs().max()))
+        assert (a - b_).abs().max().item() <= 2e-3 * scale, n_

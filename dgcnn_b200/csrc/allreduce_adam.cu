@@ -29,7 +29,7 @@
 namespace dgcnn {
 
 constexpr int kArMaxWorld = 16;
-constexpr int kArCtas = 32;
+constexpr int kArCtas = 64;                // all co-resident (the kernel is its own barrier); 16-byte pushes
 constexpr int kArThreads = 256;
 constexpr int kArHeaderBytes = 256;
 
@@ -59,8 +59,17 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
     const int64_t slot = (a.n_total + 31) / 32 * 32;             // floats per slot
     const int64_t region = (int64_t)parity * a.world * slot;     // floats before this parity's slots
 
-    // 1. push the local sums into slot [rank] of every rank's buffer
-    for (int64_t i = tid; i < a.n_total; i += stride) {
+    // 1. push the local sums into slot [rank] of every rank's buffer: 16-byte remote stores (the
+    //    slots are 128-byte aligned; `g` is when n_total is a multiple of 4 and the buffer aligned)
+    const bool vec = ((reinterpret_cast<uintptr_t>(a.g) & 15) == 0);
+    const int64_t n4 = vec ? a.n_total / 4 : 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+        const float4 gi = reinterpret_cast<const float4*>(a.g)[i];
+        for (int r = 0; r < a.world; ++r)
+            reinterpret_cast<float4*>(reinterpret_cast<float*>(a.exch[r] + kArHeaderBytes) + region +
+                                      (int64_t)a.rank * slot)[i] = gi;
+    }
+    for (int64_t i = 4 * n4 + tid; i < a.n_total; i += stride) {
         const float gi = a.g[i];
         for (int r = 0; r < a.world; ++r)
             reinterpret_cast<float*>(a.exch[r] + kArHeaderBytes)[region + (int64_t)a.rank * slot + i] = gi;
@@ -71,18 +80,25 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
         for (int r = 0; r < a.world; ++r)
             atomicAdd_system(reinterpret_cast<uint32_t*>(a.exch[r] + parity * 128), 1u);
 
-    // 2. wait until every CTA of every rank has arrived at the LOCAL counter
+    // 2. wait until every CTA of every rank has arrived at the LOCAL counter.  A peer that never
+    //    shows up (~20 s) raises DGCNN_COMM_TIMEOUT and the step is ABANDONED: no sum, no Adam, no
+    //    counter bump -- stale or missing slots must never reach the parameters.
+    __shared__ int timed_out;
     if (threadIdx.x == 0) {
+        timed_out = 0;
         const uint32_t* cnt = reinterpret_cast<const uint32_t*>(a.exch[a.rank] + parity * 128);
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(cnt) - target) < 0) {
-            if (clock64() - t0 > 40000000000ll) {                 // ~20 s: a peer is gone
+            if ((a.status && (*reinterpret_cast<volatile int32_t*>(a.status) & DGCNN_COMM_TIMEOUT)) ||
+                clock64() - t0 > 40000000000ll) {                 // ~20 s: a peer is gone
                 if (a.status) atomicOr(a.status, DGCNN_COMM_TIMEOUT);
+                timed_out = 1;
                 break;
             }
         }
     }
     __syncthreads();
+    if (timed_out) return;
 
     // 3. sum the local slots in rank order, Adam on the parameters
     const int64_t t = *a.step + 1;
@@ -104,7 +120,11 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
     }
 }
 
-__global__ void allreduce_adam_bump(int64_t* step, int64_t* epoch) { *step += 1; *epoch += 1; }
+__global__ void allreduce_adam_bump(int64_t* step, int64_t* epoch, const int32_t* status) {
+    if (status && (*status & DGCNN_COMM_TIMEOUT)) return;         // the step was abandoned
+    *step += 1;
+    *epoch += 1;
+}
 
 }  // namespace dgcnn
 
@@ -185,7 +205,7 @@ extern "C" int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     allreduce_adam_kernel<<<kArCtas, kArThreads, 0, st>>>(a);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    allreduce_adam_bump<<<1, 1, 0, st>>>(step, epoch);
+    allreduce_adam_bump<<<1, 1, 0, st>>>(step, epoch, status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

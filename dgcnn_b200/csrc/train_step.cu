@@ -22,6 +22,15 @@ static bool fuse_conv5_enabled() {
     return g_fuse_conv5 != 0;
 }
 
+// graph_status is int32[2]: [0] the flags of the CURRENT step (DGCNN_GRAPH_GENERIC is per-batch
+// state the kernels read back), [1] the OR of the error flags of every earlier step since the
+// caller last cleared it -- a bad batch in the middle of an epoch is not lost (one tiny launch
+// in place of the memset that used to clear the word).
+__global__ void step_status_begin(int32_t* status) {
+    status[1] |= status[0] & ~DGCNN_GRAPH_GENERIC;
+    status[0] = 0;
+}
+
 namespace {
 
 struct Arena {
@@ -278,7 +287,8 @@ extern "C" int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_in
     Arena a{reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255), 0};
     const StepBuffers s = carve(a, N, E, B, num_features, k, num_classes, max_nodes, false);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (cudaMemsetAsync(graph_status, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
+    step_status_begin<<<1, 1, 0, st>>>(graph_status);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (index_is_i32)
         DGCNN_TRY(dgcnn_build_graph_i32(static_cast<const int32_t*>(edge_index), E,
                                         static_cast<const int32_t*>(batch), N, B, s.rowptr, s.col, s.rowptr_t,
@@ -320,7 +330,8 @@ extern "C" int dgcnn_train_step_resident(const dgcnn_dataset* dataset, const int
         s.col_t = s.col;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (cudaMemsetAsync(graph_status, 0, sizeof(int32_t), st) != cudaSuccess) return DGCNN_ERR_CUDA;
+    step_status_begin<<<1, 1, 0, st>>>(graph_status);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
     // K0b's outputs are gathered too when the data set carries them and every graph of the batch
     // owns a bitmap (max_nodes <= 1024); otherwise K0b runs on the gathered CSR
     const bool maps = dataset->bitmap && dataset->fragmap && max_nodes <= 1024;

@@ -18,21 +18,28 @@ __all__ = ["shard_bounds", "shard_ids", "GradBucket", "PeerExchange"]
 
 
 def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
-    """Split graphs ``0..len(costs)`` into ``world_size`` CONTIGUOUS slices of nearly
-    equal total cost (cost ~ nodes + edges of a graph; counts alone skew badly on
-    D&D-like size tails).  Returns [(lo, hi)] per rank; slices may be empty."""
+    """Split graphs ``0..len(costs)`` into ``world_size`` CONTIGUOUS slices of nearly equal
+    total cost (cost ~ nodes + edges of a graph; counts alone skew badly on D&D-like size
+    tails).  Every rank gets at least one graph whenever there are at least ``world_size``
+    graphs; with fewer, the LAST ranks take them and the first slices are empty (such a rank
+    still joins the gradient exchange: ``FusedTrainer.step_autograd(None, global_batch)``).
+    Returns [(lo, hi)] per rank."""
     n = len(costs)
     total = float(sum(costs))
     bounds, lo, acc = [], 0, 0.0
     for r in range(world_size):
-        target = total * (r + 1) / world_size
-        hi = lo
-        while hi < n and (acc + costs[hi] <= target or hi == lo and n - hi > world_size - r - 1
-                          and acc + 0.5 * costs[hi] <= target):
-            acc += costs[hi]
-            hi += 1
+        later = world_size - r - 1                        # ranks still to be served after this one
         if r == world_size - 1:
             hi = n
+        elif n < world_size:
+            hi = lo + (1 if n - lo > later else 0)        # the last `n` ranks take one graph each
+        else:
+            target = total * (r + 1) / world_size
+            cap = n - later                               # leave one graph for every later rank
+            hi = lo
+            while hi < cap and (hi == lo or acc + 0.5 * costs[hi] <= target):
+                acc += costs[hi]
+                hi += 1
         bounds.append((lo, hi))
         lo = hi
     return bounds

@@ -126,7 +126,14 @@ def train_epoch(trainer: FusedTrainer, ds: DeviceDataset, ids: np.ndarray, batch
     trainer.model.train()
     st = EpochStats(ds.device)
     for b in epoch_batches(ids, batch_size, shuffle=True, generator=generator):
-        st.add(trainer.step_resident(ds, b), len(b))
+        if trainer.resident_supported(ds, b):
+            stats = trainer.step_resident(ds, b)          # one library call: gather .. Adam
+        else:
+            # a graph of this batch exceeds the fused kernels (D&D's 5748 nodes, PROTEINS' 620):
+            # same step through Model(data) + autograd on the per-layer kernels, same flat Adam
+            stats = trainer.step_autograd(ds.batch(b))
+        st.add(stats, len(b))
+    trainer.check_status()                                # comm timeout / bad input: once per epoch
     return st.result()
 
 
@@ -199,9 +206,6 @@ def main(argv: Optional[Sequence[str]] = None) -> Dict[str, List[float]]:
     tr, te = np.array(over_results["train_accuracy"]), np.array(over_results["test_accuracy"])
     print("Overall Training Accuracy: %.2f%% (std: %.2f) Testing Accuracy: %.2f%% (std: %.2f)"
           % (tr.mean(), tr.std(), te.mean(), te.std()), flush=True)
-    int_status = int(trainer._graph_status.item())
-    if int_status & ~ops.GRAPH_GENERIC:
-        raise RuntimeError(f"dgcnn_b200.driver: the kernels flagged bad input (status {int_status})")
     return over_results
 
 

@@ -72,7 +72,8 @@ class FusedTrainer:
         # the one-by-one Python sequence below, which is also the fallback)
         self.native = os.environ.get("DGCNN_NATIVE_STEP", "1") != "0"
         self._arena = None
-        self._graph_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # [0] flags of the last step, [1] sticky OR of the error flags of the earlier ones
+        self._graph_status = torch.zeros(2, dtype=torch.int32, device=dev)
         # multi-GPU: gradients are summed by the fused peer-memory all-reduce + Adam kernel when
         # the ranks (one node) can map each other's memory, else by NCCL (DGCNN_ALLREDUCE=nccl)
         self.exchange = None
@@ -90,6 +91,36 @@ class FusedTrainer:
             if float(flag.item()) < 1.0:
                 self.exchange = None
 
+    def _world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def _global_batch(self, local_graphs: int, global_batch: Optional[int], world: int) -> int:
+        """Number of graphs the mean NLL of train.py:39 runs over.  With several ranks it MUST be
+        given: cost-balanced shards (dp.shard_ids) hold different numbers of graphs, and every
+        rank has to scale the summed gradient by the same 1 / global_batch."""
+        if global_batch is not None:
+            if int(global_batch) < 1:
+                raise ValueError("FusedTrainer: global_batch must be positive")
+            return int(global_batch)
+        if world > 1:
+            raise ValueError("FusedTrainer: pass global_batch (graphs over ALL ranks) when training on "
+                             "several GPUs; the ranks' shards need not hold the same number of graphs")
+        return int(local_graphs)
+
+    def check_status(self) -> None:
+        """Host-syncing check of the device status words (call once per epoch): a gradient
+        exchange that timed out leaves the parameters untouched and raises here; bad input flags
+        (BAD_EDGE / BAD_BATCH / fp16 RANGE) accumulate across steps until cleared."""
+        gs = self._graph_status.tolist()
+        comm, graph = int(self.comm_status.item()), int(gs[0]) | int(gs[1])
+        if comm:
+            raise RuntimeError("FusedTrainer: the peer-memory gradient exchange timed out (a rank is gone or "
+                               "stuck); parameters were NOT updated by the affected steps")
+        if graph & ~ops.GRAPH_GENERIC:
+            self._graph_status.zero_()
+            raise RuntimeError(f"FusedTrainer: the kernels flagged bad input (status {graph}): "
+                               "1 = edge outside the batch, 2 = batch vector, 4 = fp16 split range")
+
     def supported(self, data) -> bool:
         """The fused kernels need the largest graph of the batch (host knowledge)."""
         from .nn import batch_max_nodes
@@ -105,7 +136,8 @@ class FusedTrainer:
         if not self.supported(data):
             raise RuntimeError("FusedTrainer.step: batch not supported by the fused kernels "
                                "(every graph must fit the shared memory of one SM; use Model(data) + autograd)")
-        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        world = self._world()
+        global_batch = self._global_batch(int(data.num_graphs), global_batch, world)
         if self.native and self._native_step(data, global_batch, world):
             return self.stats
         graph = m.build_graph(data)
@@ -135,8 +167,10 @@ class FusedTrainer:
             ops.stack_bwd(dpooled, perm, xcat, data.x, graph, weights, k, norm,
                           out=self.grad[:self.num_stack])
         pending.join()
-        if global_batch is None:
-            global_batch = graph.num_graphs * world
+        return self._finish(global_batch, world)
+
+    def _finish(self, global_batch: int, world: int) -> torch.Tensor:
+        """Gradient sum over the ranks (one exchange of the flat buffer) + flat Adam."""
         if world > 1 and self.exchange is not None:
             ops.allreduce_adam(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count,
                                self.exchange.epoch, self.lr, self.betas[0], self.betas[1], self.eps,
@@ -148,6 +182,33 @@ class FusedTrainer:
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
                       self.betas[0], self.betas[1], self.eps, grad_scale=1.0 / float(global_batch))
         return self.stats
+
+    def step_autograd(self, data, global_batch: Optional[int] = None) -> torch.Tensor:
+        """The same optimisation step for ANY batch (graphs of any size: D&D's 5748-node graph,
+        PROTEINS' 620): ``Model(data)`` through torch autograd -- the per-layer kernels K1 / K3
+        where a graph exceeds one SM's shared memory -- with the gradients accumulated in place in
+        the flat bucket, then the same exchange + flat Adam.  An empty shard (``data`` None or
+        without graphs) still joins the exchange with zero gradients."""
+        world = self._world()
+        local = 0 if data is None else int(data.num_graphs)
+        global_batch = self._global_batch(local, global_batch, world)
+        self.grad.zero_()
+        if local > 0:
+            logp = self.model(data)
+            loss = torch.nn.functional.nll_loss(logp, data.y, reduction="sum")
+            loss.backward()
+            with torch.no_grad():
+                self.stats[0] = loss.detach()
+                self.stats[1] = (logp.argmax(1) == data.y).sum()
+        return self._finish(global_batch, world)
+
+    def resident_supported(self, dataset, ids) -> bool:
+        """Can the one-call fused step run this batch of a DeviceDataset (every graph must fit the
+        fused kernels)?  Otherwise use ``step_autograd(dataset.batch(ids))``."""
+        mx = dataset.plan(ids)[2]
+        f = dataset.num_features
+        return (ops.stack_fwd_supported(f, mx) and ops.stack_bwd_supported(f, mx)
+                and self.model.classifier_2.out_features <= 32)
 
     def step_resident(self, dataset, ids, ids_device: Optional[torch.Tensor] = None,
                       global_batch: Optional[int] = None) -> torch.Tensor:
@@ -163,7 +224,8 @@ class FusedTrainer:
         n, e, mx = dataset.plan(ids)
         b, f = int(len(ids)), dataset.num_features
         k, c = m.sort_pool.k, m.classifier_2.out_features
-        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        world = self._world()
+        global_batch = self._global_batch(b, global_batch, world)
         if dataset.device != self.flat.device:
             raise RuntimeError("FusedTrainer.step_resident: data set and model live on different devices")
         if self.num_params != int(lib.dgcnn_train_step_num_params(f, k, c)):
@@ -179,8 +241,6 @@ class FusedTrainer:
             raise ValueError("FusedTrainer.step_resident: bad sizes")
         if self._arena is None or self._arena.numel() < need:
             self._arena = ops._empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.flat.device)
-        if global_batch is None:
-            global_batch = b * world
         table, epoch, rank = None, None, 0
         if world > 1:
             table = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p_)) for p_ in self.exchange.ptrs])
@@ -227,8 +287,6 @@ class FusedTrainer:
         need = int(lib.dgcnn_train_step_workspace_bytes(n, e, b, f, k, c, mx))
         if self._arena is None or self._arena.numel() < need:
             self._arena = ops._empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=x.device)
-        if global_batch is None:
-            global_batch = b * world
         table, epoch, rank = None, None, 0
         if world > 1:
             table = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p_)) for p_ in self.exchange.ptrs])

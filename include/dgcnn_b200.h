@@ -436,7 +436,9 @@ int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg, float* exp
  *   global_batch      the gradient is divided by it (graphs of all ranks)
  *   exchange/world/rank/epoch/comm_status   as for dgcnn_allreduce_adam; exchange NULL or
  *       world <= 1: plain Adam
- *   graph_status      device int32, reset and OR-ed with DGCNN_GRAPH_* by the call
+ *   graph_status      device int32[2]: [0] = DGCNN_GRAPH_* flags of THIS step (reset at its start),
+ *                     [1] = OR of the error flags (everything but DGCNN_GRAPH_GENERIC) of all
+ *                     earlier steps since the caller last zeroed it: check [0] | [1] once per epoch
  * Needs graphs that fit the fused kernels (dgcnn_stack_fwd_supported / _bwd_supported), else
  * DGCNN_ERR_UNSUPPORTED.  No allocation, no synchronisation: capturable in a CUDA graph.
  * ------------------------------------------------------------------------ */

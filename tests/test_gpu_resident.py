@@ -207,7 +207,7 @@ def test_resident_train_step_is_bit_identical_to_the_host_fed_step(name, count, 
         assert torch.equal(tr_a.exp_avg_sq, tr_b.exp_avg_sq), steps
         steps += 1
     assert steps == -(-count // bs) and int(tr_a.step_count.item()) == steps
-    assert int(tr_a._graph_status.item()) == 0
+    assert tr_a._graph_status.tolist() == [0, 0]
     assert torch.isfinite(tr_a.flat).all()
 
 
@@ -305,3 +305,54 @@ def test_collate_against_the_committed_golden_vectors():
     np.testing.assert_array_equal(rb.y.cpu().numpy(), z["y"])
     st = int(g.status.item())
     assert st & ops.GRAPH_GENERIC and not st & (ops.GRAPH_BAD_EDGE | ops.GRAPH_BAD_BATCH)
+
+
+def test_driver_epoch_falls_back_for_graphs_beyond_the_fused_kernels():
+    """ADVICE r01 (driver.py:129): a data set with graphs of 1100 and 650 nodes (D&D / PROTEINS
+    tails) through driver.train_epoch -- batches that hold them take FusedTrainer.step_autograd
+    (per-layer kernels), the others the one-call resident step; the epoch finishes, the loss is
+    finite and equals a by-hand replay that uses Model(data) + torch Adam for every batch."""
+    from dgcnn_b200 import driver
+    cfg = CONFIGS["proteins"]
+    graphs = make_graphs(cfg, 30, seed=8, tie_free=True)
+    rng = np.random.RandomState(4)
+    for n in (1100, 650):
+        m = 3 * n
+        a, b_ = rng.randint(0, n, m), rng.randint(0, n, m)
+        keep = a != b_
+        lo, hi = np.minimum(a, b_)[keep], np.maximum(a, b_)[keep]
+        pairs = np.unique(np.stack([lo, hi], 1), axis=0)
+        src = np.concatenate([pairs[:, 0], pairs[:, 1]])
+        dst = np.concatenate([pairs[:, 1], pairs[:, 0]])
+        order = np.argsort(src * n + dst, kind="stable")
+        graphs.append({"x": rng.standard_normal((n, cfg.num_features)).astype(np.float32),
+                       "edge_index": np.stack([src[order], dst[order]]), "y": int(rng.randint(0, 2))})
+    ds = dg.DeviceDataset(graphs, DEV, num_classes=2)
+    ids = np.arange(len(graphs), dtype=np.int64)
+    torch.manual_seed(1)
+    model = dg.Model(cfg.num_features, 2, k=cfg.k).to(DEV)
+    ref_model = copy.deepcopy(model)
+    trainer = dg.FusedTrainer(model)
+    assert not trainer.resident_supported(ds, ids) and trainer.resident_supported(ds, ids[:8])
+    gen = torch.Generator().manual_seed(5)
+    loss, acc = driver.train_epoch(trainer, ds, ids, 8, gen)
+    assert np.isfinite(loss) and 0.0 <= acc <= 100.0
+    assert int(trainer.step_count.item()) == 4
+    # replay: same shuffles, every batch through Model(data) + autograd + torch Adam (dropout uses
+    # the model's own counter-hash stream: same seed, same offsets)
+    ref_model._tail_seed = model._tail_seed
+    ref_model.train()
+    opt = torch.optim.Adam(ref_model.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(5)
+    total = 0.0
+    for b in dg.epoch_batches(ids, 8, True, gen):
+        data = ds.batch(b)
+        opt.zero_grad()
+        out = ref_model(data)
+        l = torch.nn.functional.nll_loss(out, data.y)
+        l.backward()
+        opt.step()
+        total += float(l)
+    assert abs(loss - total / 4) <= 1e-4 * max(1.0, abs(total / 4))
+    for (n_, p_), (_, q_) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert (p_ - q_).abs().max().item() <= 5e-5, n_

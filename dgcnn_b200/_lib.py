@@ -84,6 +84,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p,
                                        c_void_p, c_int64, c_int32,
                                        c_int64, c_int32, c_int32, c_void_p]),
+    "dgcnn_project_rows": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "dgcnn_graph_conv_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "dgcnn_graph_conv_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64,
                                        c_void_p, c_int64, c_int32,

@@ -193,7 +193,149 @@ __global__ void __launch_bounds__(kConvThreads) gc_aggregate_edge(AggParams p) {
     }
 }
 
+
+// ---- 32-channel rows, vectorised: the kernel for graphs of ANY size ------------------------------
+// Eight lanes own one target row (lane q holds channels 4q..4q+3 as a float4), so a warp works on
+// FOUR rows at once and a neighbour row is ONE 16-byte load per lane.  Per step a group takes 8
+// neighbours: lane q fetches column index q of the step, the indices are shuffled to the group and
+// eight independent LDG.128 are in flight per lane (32 rows of 128 B per warp) -- the per-layer path
+// is bound by how many neighbour rows are in flight, not by arithmetic (the one-row-per-warp kernel
+// above keeps 4).  Needs fin == 32, 16-byte aligned rows (ldf % 4 == 0) and fout <= 32; anything
+// else takes the kernels above.  The summation order is the CSR order: deterministic.
+constexpr int kVecRows = 4;      // rows per warp
+
+__global__ void __launch_bounds__(kConvThreads) gc_aggregate_vec32(AggParams p) {
+    extern __shared__ float smem[];
+    float* smat = smem;                    // [32][32]: smat[k*32 + c], zero for c >= fout
+    float* sbias = smem + 32 * 32;
+    if (p.out) {
+        for (int idx = threadIdx.x; idx < 32 * 32; idx += blockDim.x) {
+            const int k = idx >> 5, c = idx & 31;
+            float v = 0.f;
+            if (!p.mat) v = k == c ? 1.f : 0.f;        // rows were projected first: identity
+            else if (c < p.fout) v = p.mat_transposed ? p.mat[c * 32 + k] : p.mat[k * p.fout + c];
+            smat[idx] = v;
+        }
+        for (int c = threadIdx.x; c < 32; c += blockDim.x) sbias[c] = (p.bias && c < p.fout) ? p.bias[c] : 0.0f;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, q = lane & 7, grp = lane >> 3;
+    const unsigned gmask = 0xffu << (grp * 8);
+    const int64_t warps = (int64_t)gridDim.x * (kConvThreads / 32);
+    const int64_t ntask = (p.n + kVecRows - 1) / kVecRows;
+    for (int64_t task = (int64_t)blockIdx.x * (kConvThreads / 32) + (threadIdx.x >> 5); task < ntask;
+         task += warps) {
+        const int64_t row = task * kVecRows + grp;
+        const bool live = row < p.n;
+        const int64_t rr = live ? row : p.n - 1;
+        const float di = p.dis[rr];
+        const float self_c = p.swap_coef ? row_coef(di, p.norm) : col_coef(di, p.norm);
+        const float scale = p.swap_coef ? col_coef(di, p.norm) : row_coef(di, p.norm);
+        const float4 fs = *reinterpret_cast<const float4*>(p.feat + rr * p.ldf + 4 * q);
+        float4 agg = make_float4(self_c * fs.x, self_c * fs.y, self_c * fs.z, self_c * fs.w);
+        const int beg = live ? p.rowptr[rr] : 0, end = live ? p.rowptr[rr + 1] : 0;
+        // all four groups of the warp step together (the shuffles are group-local, the loop is not)
+        int steps = (end - beg + 7) >> 3;
+        steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 8));
+        steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 16));
+        for (int it = 0; it < steps; ++it) {
+            const int e = beg + it * 8 + q;
+            int j = 0;
+            float cj = 0.0f;
+            if (e < end) {
+                j = p.col[e];
+                const float dj = p.dis[j];
+                cj = p.swap_coef ? row_coef(dj, p.norm) : col_coef(dj, p.norm);
+            }
+            float4 v[8];
+            float cc[8];
+            const int left = end - beg - it * 8;       // neighbours of this group's row in this step
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int jj = __shfl_sync(DGCNN_FULL_MASK, j, grp * 8 + u);
+                cc[u] = __shfl_sync(DGCNN_FULL_MASK, cj, grp * 8 + u);
+                v[u] = u < left ? *reinterpret_cast<const float4*>(p.feat + (int64_t)jj * p.ldf + 4 * q)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);     // (never 0 * NaN)
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                agg.x = fmaf(cc[u], v[u].x, agg.x); agg.y = fmaf(cc[u], v[u].y, agg.y);
+                agg.z = fmaf(cc[u], v[u].z, agg.z); agg.w = fmaf(cc[u], v[u].w, agg.w);
+            }
+        }
+        agg.x *= scale; agg.y *= scale; agg.z *= scale; agg.w *= scale;
+        if (p.agg_out && live) *reinterpret_cast<float4*>(p.agg_out + row * 32 + 4 * q) = agg;
+        if (!p.out) continue;
+        // y[4q..4q+3] = b + sum_k a_k M[k][4q..4q+3]; a_k sits in lane k>>2 of the group, component k&3
+        float4 y = *reinterpret_cast<const float4*>(sbias + 4 * q);
+        const float4* m4 = reinterpret_cast<const float4*>(smat);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float comp = (k & 3) == 0 ? agg.x : ((k & 3) == 1 ? agg.y : ((k & 3) == 2 ? agg.z : agg.w));
+            const float a = __shfl_sync(DGCNN_FULL_MASK, comp, grp * 8 + (k >> 2));
+            const float4 w = m4[k * 8 + q];
+            y.x = fmaf(a, w.x, y.x); y.y = fmaf(a, w.y, y.y); y.z = fmaf(a, w.z, y.z); y.w = fmaf(a, w.w, y.w);
+        }
+        if (p.act == DGCNN_ACT_TANH) { y.x = tanhf(y.x); y.y = tanhf(y.y); y.z = tanhf(y.z); y.w = tanhf(y.w); }
+        if (!live) continue;
+        float* orow = p.out + row * p.ldo + 4 * q;
+        const bool vec_ok = p.fout == 32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        if (vec_ok && !p.accumulate) {
+            *reinterpret_cast<float4*>(orow) = y;
+        } else {
+            const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (4 * q + u < p.fout) orow[u] = p.accumulate ? orow[u] + yy[u] : yy[u];
+        }
+    }
+    (void)gmask;
+}
+
+// identity "projection" variant: out = act(agg + bias) for fout == fin == 32 (the aggregation of
+// rows that were projected first, model.py:30 when F > 32)
+__global__ void __launch_bounds__(kConvThreads) gc_project_rows(const float* __restrict__ x, int64_t ldx, int fin,
+                                                                const float* __restrict__ w /*[32][fin]*/,
+                                                                float* __restrict__ h /*[n][32]*/, int64_t n) {
+    extern __shared__ float smem[];        // wt[k][32]
+    for (int idx = threadIdx.x; idx < fin * 32; idx += blockDim.x) {
+        const int c = idx / fin, k = idx - c * fin;
+        smem[k * 32 + c] = w[idx];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (kConvThreads / 32);
+    for (int64_t r0 = ((int64_t)blockIdx.x * (kConvThreads / 32) + (threadIdx.x >> 5)) * 4; r0 < n; r0 += warps * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* xr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xr[u] = x + min(r0 + u, n - 1) * ldx;
+        for (int k = 0; k < fin; ++k) {
+            const float wk = smem[k * 32 + lane];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(xr[u][k], wk, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (r0 + u < n) h[(r0 + u) * 32 + lane] = acc[u];
+    }
+}
+
+static bool vec32_ok(const AggParams& p) {
+    return p.fin == 32 && (p.ldf & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0 &&
+           (!p.out || p.fout <= 32) && p.n > 0;
+}
+
 static int launch_aggregate(const AggParams& p, cudaStream_t st) {
+    if (vec32_ok(p)) {
+        const size_t smem_v = p.out ? sizeof(float) * (32 * 32 + 32) : 0;
+        // one task (four rows) per warp whenever the device can hold them: the rows of a batch are
+        // independent latency chains
+        const int grid_v = grid_for((p.n + kVecRows - 1) / kVecRows, kConvThreads / 32, 16);
+        gc_aggregate_vec32<<<grid_v, kConvThreads, smem_v, st>>>(p);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+        return DGCNN_OK;
+    }
     size_t smem = p.out ? sizeof(float) * ((size_t)p.fin * p.fout + p.fout) : 0;
     int grid = grid_for(p.n, kConvThreads / 32, 8);
 #define DGCNN_LAUNCH_AGG(KERNEL)                                                              \
@@ -359,7 +501,11 @@ extern "C" int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin, co
     if (act != DGCNN_ACT_NONE && act != DGCNN_ACT_TANH) return DGCNN_ERR_INVALID_ARGUMENT;
     if (cin > kMaxChannels || cout > kMaxChannels) return DGCNN_ERR_UNSUPPORTED;
     if (num_nodes == 0) return DGCNN_OK;
-    if (!x || !rowptr || !dis || !weight || !y) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!x || !rowptr || !dis || !y) return DGCNN_ERR_INVALID_ARGUMENT;
+    // weight == NULL: the rows were projected first (dgcnn_project_rows); only for 32 -> 32 rows
+    // that the vectorised kernel can take
+    if (!weight && !(cin == 32 && cout == 32 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0))
+        return DGCNN_ERR_INVALID_ARGUMENT;
     AggParams p{};
     p.feat = x; p.ldf = ldx; p.fin = cin;
     p.rowptr = rowptr; p.col = col; p.dis = dis;
@@ -367,6 +513,25 @@ extern "C" int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin, co
     p.agg_out = nullptr; p.out = y; p.ldo = ldy; p.fout = cout;
     p.accumulate = 0; p.act = act; p.norm = norm; p.swap_coef = 0; p.n = num_nodes;
     return launch_aggregate(p, static_cast<cudaStream_t>(stream));
+}
+
+// h[n][32] = x[n][cin] W^T (W [32][cin], PyG's `lin` of GCNConv.forward): project FIRST when the
+// input is wider than the 32 output channels (D&D F = 90, power-law F = 64), then aggregate the
+// 32-wide rows with dgcnn_graph_conv_fwd(weight = NULL) -- the order PyG itself uses.
+extern "C" int dgcnn_project_rows(const float* x, int64_t ldx, int32_t cin, const float* weight, float* h,
+                                  int64_t num_nodes, void* stream) {
+    if (num_nodes < 0 || cin < 1 || ldx < cin) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (cin > 512) return DGCNN_ERR_UNSUPPORTED;
+    if (num_nodes == 0) return DGCNN_OK;
+    if (!x || !weight || !h) return DGCNN_ERR_INVALID_ARGUMENT;
+    const size_t smem = sizeof(float) * 32 * (size_t)cin;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(gc_project_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    gc_project_rows<<<grid_for((num_nodes + 3) / 4, kConvThreads / 32, 8), kConvThreads, smem,
+                      static_cast<cudaStream_t>(stream)>>>(x, ldx, cin, weight, h, num_nodes);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
 }
 
 extern "C" size_t dgcnn_graph_conv_bwd_workspace_bytes(int64_t num_nodes, int32_t cin, int32_t cout) {

@@ -195,7 +195,10 @@ class _StackFn(torch.autograd.Function):
         if fused:          # KS: one launch, one CTA per graph, everything in shared memory
             pooled, xcat, perm = ops.stack_fwd(x, graph, weights, biases, k, norm)
         else:              # K1 x L + K2: any widths, any graph size
-            xcat = ops._empty(n, offs[-1], dtype=torch.float32, device=x.device)
+            # rows padded to a multiple of 4 floats: 16-byte aligned slices for the vectorised K1
+            ld = (offs[-1] + 3) // 4 * 4 + (0 if offs[-1] % 4 else 0)
+            ld = ops.XCAT_LD if offs[-1] == 97 else ld
+            xcat = ops._empty(n, ld, dtype=torch.float32, device=x.device)[:, :offs[-1]]
             h = x
             for l, (w, b) in enumerate(zip(weights, biases)):
                 out = xcat[:, offs[l]:offs[l + 1]]

@@ -268,10 +268,15 @@ def graph_ptr(batch: Tensor, num_graphs: int) -> Tensor:
     return gptr
 
 
+PROJECT_FIRST_MIN = 33   # layers wider than this on the input side project before they aggregate
+
+
 def graph_conv_fwd(x: Tensor, rowptr: Tensor, col: Tensor, dis: Tensor, weight: Tensor,
                    bias: Optional[Tensor], norm: int, act: int, out: Tensor) -> None:
     """K1: ``out[:] = act(A_hat x W^T + b)`` in one launch; ``out`` may be a column
-    slice of the concatenated buffer (model.py:30-34)."""
+    slice of the concatenated buffer (model.py:30-34).  A layer with more than 32 input
+    channels and 32 outputs (D&D: 90, power-law: 64) projects first -- ``h = x W^T`` in one
+    dense kernel, then the aggregation runs on 32-wide rows (PyG's own order)."""
     lib = _lib.load_library()
     _require_cuda(x, "x", torch.float32)
     _require_cuda(out, "out", torch.float32)
@@ -284,12 +289,19 @@ def graph_conv_fwd(x: Tensor, rowptr: Tensor, col: Tensor, dis: Tensor, weight: 
     if weight.shape != (cout, cin) or out.shape != (n, cout) or rowptr.numel() != n + 1:
         raise ValueError("dgcnn_b200: graph_conv_fwd shape mismatch")
     weight = weight.contiguous()
+    if cin >= PROJECT_FIRST_MIN and cout == 32 and n > 0:
+        h = _empty(n, 32, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.dgcnn_project_rows(_ptr(x), _rows(x, "x"), cin, _ptr(weight), _ptr(h), n, _stream())
+        _lib.check(rc, "project_rows")
+        LAUNCHES["graph_conv_fwd"] += 1
+        x, cin, weight = h, 32, None
     if bias is not None:
         _require_cuda(bias, "bias", torch.float32)
         bias = bias.contiguous()
     with torch.cuda.device(x.device):
         rc = lib.dgcnn_graph_conv_fwd(_ptr(x), _rows(x, "x"), cin, _ptr(rowptr), _ptr(col),
-                                      _ptr(dis), _ptr(weight), _ptr(bias), _ptr(out),
+                                      _ptr(dis), _ptr(weight) if weight is not None else None, _ptr(bias), _ptr(out),
                                       _rows(out, "out"), cout, n, int(norm), int(act), _stream())
     _lib.check(rc, "graph_conv_fwd")
     LAUNCHES["graph_conv_fwd"] += 1 if n > 0 else 0

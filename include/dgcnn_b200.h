@@ -174,6 +174,11 @@ int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin,
  * gradient already sitting in that slice of the [N,97] gradient buffer).
  * dw [cout,cin] and db [cout] (db may be NULL) are overwritten.
  * ------------------------------------------------------------------------ */
+/* lin of GCNConv.forward on its own: h[n][32] = x W^T for inputs wider than 32 channels
+ * (project first, then aggregate 32-wide rows: dgcnn_graph_conv_fwd with weight == NULL, which
+ * is accepted for cin == cout == 32 and 16-byte aligned rows). */
+int dgcnn_project_rows(const float* x, int64_t ldx, int32_t cin, const float* weight, float* h,
+                       int64_t num_nodes, void* stream);
 size_t dgcnn_graph_conv_bwd_workspace_bytes(int64_t num_nodes, int32_t cin, int32_t cout);
 int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy,
                          const float* x, int64_t ldx, int32_t cin,

@@ -1011,3 +1011,73 @@ def test_cpu_tensors_are_rejected():
     m = dg.Model(8, 2)
     with pytest.raises((RuntimeError, TypeError)):
         m(make_batch("mutag", num_graphs=3))
+
+
+# ------------------------------------------------------------------ K1 vectorised / project-first
+@pytest.mark.parametrize("cout", [32, 1, 7])
+@pytest.mark.parametrize("norm", [0, 1])
+@pytest.mark.parametrize("sizes", [(17, 1, 0, 40, 9), (300, 3), (2, 2, 2, 2, 2, 2, 2), (1200,)])
+def test_graph_conv_vectorised_rows(cout, norm, sizes):
+    """gc_aggregate_vec32 (four 32-channel rows per warp, 16-byte neighbour loads): aligned
+    32-wide inputs in a padded buffer, outputs into a column slice, multigraph input with
+    loops, duplicates and edge-free rows; forward against the float64 oracle, backward against
+    float64 autograd (K3 takes the same kernel for A_hat^T dpre)."""
+    rng = np.random.RandomState(len(sizes) * 100 + cout)
+    ei, batch, n = random_multigraph(rng, list(sizes), avg_deg=5.0, loops=True)
+    b = len(sizes)
+    x = rng.standard_normal((n, 32)).astype(np.float32)
+    w = (rng.standard_normal((cout, 32)) * 0.3).astype(np.float32)
+    bias = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
+    g = gpu_graph(ei, batch, n, b)
+    xbuf = torch.zeros(n, 100, device=DEV)
+    xbuf[:, 32:64] = torch.from_numpy(x).to(DEV)                       # 16-byte aligned slice
+    obuf = torch.full((n, 100), 7.0, device=DEV)
+    osl = obuf[:, 64:64 + cout]
+    ops.graph_conv_fwd(xbuf[:, 32:64], g.rowptr, g.col, g.dis, torch.from_numpy(w).to(DEV),
+                       torch.from_numpy(bias).to(DEV), norm, 1, osl)
+    ref64 = torch.tanh(orc.gcn_conv(torch.from_numpy(x).double(), torch.from_numpy(ei), torch.from_numpy(w).double(),
+                                    torch.from_numpy(bias).double(), norm))
+    assert (osl.cpu().double() - ref64).abs().max().item() <= ATOL
+    assert (obuf[:, :64] == 7.0).all() and (obuf[:, 64 + cout:] == 7.0).all()
+    # backward through the module-level autograd function
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    bt = torch.from_numpy(bias).double().requires_grad_(True)
+    y64 = torch.tanh(orc.gcn_conv(xt, torch.from_numpy(ei), wt, bt, norm))
+    dy = rng.standard_normal((n, cout)).astype(np.float32)
+    y64.backward(torch.from_numpy(dy).double())
+    xd = xbuf[:, 32:64].detach().clone().requires_grad_(True)
+    wd = torch.from_numpy(w).to(DEV).requires_grad_(True)
+    bd = torch.from_numpy(bias).to(DEV).requires_grad_(True)
+    from dgcnn_b200.nn import _GraphConvFn
+    yd = _GraphConvFn.apply(xd, wd, bd, g, norm, 1)
+    yd.backward(torch.from_numpy(dy).to(DEV))
+    for got, want in ((xd.grad, xt.grad), (wd.grad, wt.grad), (bd.grad, bt.grad)):
+        assert (got.cpu().double() - want).abs().max().item() <= 3e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("cin", [33, 64, 90, 128])
+def test_graph_conv_projects_first_for_wide_inputs(cin):
+    """cin > 32 -> 32 (D&D F = 90, power-law F = 64): dgcnn_project_rows + the vectorised
+    aggregation with the identity matrix, against the float64 oracle; NaN rows stay local."""
+    rng = np.random.RandomState(cin)
+    ei, batch, n = random_multigraph(rng, [50, 0, 333, 7], avg_deg=4.0, loops=True)
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((32, cin)) * 0.2).astype(np.float32)
+    bias = rng.uniform(-0.1, 0.1, 32).astype(np.float32)
+    g = gpu_graph(ei, batch, n, 4)
+    out = torch.empty(n, 100, device=DEV)[:, :32]
+    before = ops.LAUNCHES["graph_conv_fwd"]
+    ops.graph_conv_fwd(torch.from_numpy(x).to(DEV), g.rowptr, g.col, g.dis, torch.from_numpy(w).to(DEV),
+                       torch.from_numpy(bias).to(DEV), 0, 1, out)
+    assert ops.LAUNCHES["graph_conv_fwd"] - before == 2            # project + aggregate
+    ref64 = torch.tanh(orc.gcn_conv(torch.from_numpy(x).double(), torch.from_numpy(ei), torch.from_numpy(w).double(),
+                                    torch.from_numpy(bias).double(), 0))
+    assert (out.cpu().double() - ref64).abs().max().item() <= ATOL
+    # a NaN feature poisons exactly the rows the oracle says it does
+    x[5, 3] = np.nan
+    ops.graph_conv_fwd(torch.from_numpy(x).to(DEV), g.rowptr, g.col, g.dis, torch.from_numpy(w).to(DEV),
+                       torch.from_numpy(bias).to(DEV), 0, 1, out)
+    refn = torch.tanh(orc.gcn_conv(torch.from_numpy(x).double(), torch.from_numpy(ei), torch.from_numpy(w).double(),
+                                   torch.from_numpy(bias).double(), 0))
+    assert torch.equal(torch.isnan(out.cpu()).any(1), torch.isnan(refn).any(1))

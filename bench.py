@@ -59,6 +59,12 @@ def parse_args():
     ap.add_argument("--autograd", action="store_true",
                     help="step through torch autograd (Model + GradBucket + FlatAdam) instead of FusedTrainer")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--shards", default="balanced", choices=["balanced", "independent"],
+                    help="N > 1: how the global batch of bs*N graphs is split (balanced: dp.balanced_shards, "
+                         "every rank gets the same count and the same size profile; independent: every rank "
+                         "draws its own bs graphs)")
+    ap.add_argument("--trace-exchange", default="",
+                    help="N > 1: write the gradient-exchange kernel's per-step timeline of every rank to this JSON")
     return ap.parse_args()
 
 
@@ -219,6 +225,52 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------
+# device time of a launch sequence
+# --------------------------------------------------------------------------------------
+def timed(fn, flush, reps=20):
+    """Mean device time of fn(): captured once in a CUDA graph and replayed, so that
+    Python/ctypes launch overhead never sits between the two events; L2 is flushed
+    (untimed) before every replay."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    # the two timing events are nodes of the captured graph (external events), right
+    # before and after the kernels of fn(): the graph-launch latency stays outside
+    try:
+        a = torch.cuda.Event(enable_timing=True, external=True)
+        b_ = torch.cuda.Event(enable_timing=True, external=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            a.record()
+            fn()
+            b_.record()
+        inside = True
+    except Exception:                          # noqa: BLE001  (older torch: events around the replay)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        inside = False
+    times = []
+    for _ in range(reps):
+        flush.zero_()
+        if inside:
+            g.replay()
+        else:
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b_.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b_))
+    return statistics.mean(times) * 1e-3
+
+
+# --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
 def main():
@@ -245,9 +297,22 @@ def main():
     if args.no_fuse_conv5:
         ops.set_fuse_conv5(False)
     cfg = CONFIGS[args.workload]
-    # weak scaling: every rank owns RING distinct batches of cfg.batch_size graphs
-    host_batches = [make_batch(args.workload, seed=324 + 1000 * rank + i).pin_memory()
-                    for i in range(RING)]
+    # weak scaling: every rank owns RING distinct batches of cfg.batch_size graphs.  With N > 1 the
+    # step's GLOBAL batch (bs * N graphs, the same on every rank) is split with dp.balanced_shards:
+    # equal counts, matching size profiles -- the per-step barrier of the gradient exchange then
+    # waits for ranks that finish together (power-law graphs all have 1000 nodes: nothing to balance)
+    from dgcnn_b200.synth import collate, make_graphs
+    balanced = world > 1 and args.shards == "balanced" and cfg.kind != "powerlaw"
+    ring_graphs = []                                   # this rank's graphs per ring slot
+    for i in range(RING):
+        if balanced:
+            pool = make_graphs(cfg, cfg.batch_size * world, seed=324 + i)
+            costs = [g["x"].shape[0] + g["edge_index"].shape[1] for g in pool]
+            mine = dg.balanced_shards(costs, world)[rank]
+            ring_graphs.append([pool[j] for j in mine])
+        else:
+            ring_graphs.append(make_graphs(cfg, cfg.batch_size, seed=324 + 1000 * rank + i))
+    host_batches = [collate(gs).pin_memory() for gs in ring_graphs]
     for hb in host_batches:
         hb.max_nodes = int((hb.ptr[1:] - hb.ptr[:-1]).max())
     dev_batches = []
@@ -284,6 +349,12 @@ def main():
             bucket.all_reduce(global_batch)
             opt.step()
             return loss
+
+    trace_buf = None
+    if world > 1 and args.trace_exchange and fused_step and getattr(trainer, "exchange", None) is not None:
+        from dgcnn_b200 import _lib as _dl
+        trace_buf = torch.zeros(1024, 4, dtype=torch.int64, device=dev)
+        _dl.load_library().dgcnn_allreduce_set_trace(trace_buf.data_ptr())
 
     # ---- launch census on one eager step ------------------------------------------
     before = ops.launches_total()
@@ -350,6 +421,44 @@ def main():
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
     value = global_batch * args.steps / (total_ms / 1e3)
+
+    # ---- every rank must hold the same parameters after the same updates ------------
+    params_equal, comm_status_all = None, None
+    if world > 1 and fused_step:
+        flat = trainer.flat.double()
+        digest = torch.stack([flat.sum(), flat.abs().sum(), (flat * torch.arange(1, flat.numel() + 1, device=dev,
+                                                                                dtype=torch.float64)).sum(),
+                              trainer.comm_status.double().sum()])
+        gathered = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        params_equal = all(torch.equal(g_[:3], gathered[0][:3]) for g_ in gathered)
+        comm_status_all = [int(g_[3].item()) for g_ in gathered]
+    if trace_buf is not None:
+        t_all = [torch.zeros_like(trace_buf) for _ in range(world)]
+        dist.all_gather(t_all, trace_buf)
+        if rank == 0:
+            steps_done = int(trainer.exchange.epoch.item())
+            rows = []
+            for e in range(max(0, steps_done - args.steps), steps_done):
+                per_rank = [t_all[r][e % 1024].tolist() for r in range(world)]
+                rows.append({"step": e,
+                             "wait_us": [round((p_[2] - p_[1]) / 1e3, 2) for p_ in per_rank],
+                             "push_us": [round((p_[1] - p_[0]) / 1e3, 2) for p_ in per_rank],
+                             "sum_adam_us": [round((p_[3] - p_[2]) / 1e3, 2) for p_ in per_rank],
+                             "enter_skew_us": round((max(p_[0] for p_ in per_rank) - min(p_[0] for p_ in per_rank)) / 1e3, 2)})
+            import statistics as _st
+            summary = {"world": world, "steps": len(rows),
+                       "mean_wait_us_per_rank": [round(_st.mean(r_["wait_us"][k] for r_ in rows), 2) for k in range(world)],
+                       "mean_push_us": round(_st.mean(_st.mean(r_["push_us"]) for r_ in rows), 2),
+                       "mean_sum_adam_us": round(_st.mean(_st.mean(r_["sum_adam_us"]) for r_ in rows), 2),
+                       "mean_enter_skew_us": round(_st.mean(r_["enter_skew_us"] for r_ in rows), 2),
+                       "note": "per step and rank, %globaltimer inside allreduce_adam_kernel: push = entered -> sums "
+                               "pushed; wait = pushed -> every rank arrived (the straggler cost); sum_adam = the rest. "
+                               "enter_skew = latest minus earliest kernel entry over the ranks (GPU timers are only "
+                               "loosely synchronised across devices)", "rows": rows}
+            os.makedirs(os.path.dirname(os.path.abspath(args.trace_exchange)), exist_ok=True)
+            with open(args.trace_exchange, "w") as fh:
+                json.dump(summary, fh, indent=1)
 
     # ---- end to end from pinned host buffers (public API, eager) ------------------
     # Every step's batch starts in pinned HOST memory.  Like a DataLoader with pin_memory +
@@ -428,6 +537,48 @@ def main():
     e2e_compact_value = global_batch * e2e_steps / float(e2e_c.item())
     h2d_compact_bytes = compact_batches[0].nbytes()
 
+    # ---- N > 1: the same training step fed from data sets resident in HBM (every rank holds the
+    # graphs of ITS shards; per step only the graph ids cross PCIe, the exchange is unchanged) ----
+    resident_multi = None
+    if world > 1 and fused_step and not args.no_resident and getattr(trainer, "exchange", None) is not None:
+        try:
+            import numpy as np
+            ds_m = dg.DeviceDataset([g_ for gs in ring_graphs for g_ in gs], dev, num_classes=cfg.num_classes)
+            bs_m = cfg.batch_size
+            id_sets_m = [np.arange(i * bs_m, (i + 1) * bs_m, dtype=np.int32) for i in range(RING)]
+            id_pinned_m = [torch.from_numpy(a_).pin_memory() for a_ in id_sets_m]
+            model.train()
+
+            def resident_run_m(nsteps):
+                last = 0.0
+                for i in range(nsteps):
+                    ids_dev = id_pinned_m[i % RING].to(dev, non_blocking=True)
+                    stats = trainer.step_resident(ds_m, id_sets_m[i % RING], ids_dev, global_batch)
+                    last = float(stats[0].item())
+                return last
+
+            resident_run_m(3)
+            barrier()
+            t0 = time.perf_counter()
+            resident_run_m(e2e_steps)
+            barrier()
+            res_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(res_s, op=dist.ReduceOp.MAX)
+            ids0_m = id_pinned_m[0].to(dev)
+            t_dev = torch.tensor([timed(lambda: trainer.step_resident(ds_m, id_sets_m[0], ids0_m, global_batch), flush)],
+                                 dtype=torch.float64, device=dev)
+            dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+            resident_multi = {"value": global_batch * e2e_steps / float(res_s.item()), "unit": UNIT,
+                              "h2d_bytes_per_step": 4 * bs_m, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                              "device_step_us": float(t_dev.item()) * 1e6,
+                              "device_value": global_batch / float(t_dev.item()),
+                              "note": "dgcnn_train_step_resident on every rank (its shard's graphs resident in HBM), "
+                                      "fused peer-memory exchange + Adam; wall clock and device time = max over ranks"}
+        except Exception as exc:                       # noqa: BLE001
+            resident_multi = {"error": repr(exc)}
+            if rank == 0:
+                print(f"[bench] multi-GPU resident leg failed: {exc!r}", file=sys.stderr)
+
     if rank != 0:
         # Nothing collective happens after this point.  Tearing down an NCCL communicator whose
         # kernels live inside captured CUDA graphs can block forever: leave without ceremony.
@@ -452,63 +603,21 @@ def main():
         g0 = model.build_graph(db0)
         convs = (model.conv1, model.conv2, model.conv3, model.conv4)
 
-        def timed(fn, reps=20):
-            """Mean device time of fn(): captured once in a CUDA graph and replayed, so that
-            Python/ctypes launch overhead never sits between the two events; L2 is flushed
-            (untimed) before every replay."""
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    fn()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            # the two timing events are nodes of the captured graph (external events), right
-            # before and after the kernels of fn(): the graph-launch latency stays outside
-            try:
-                a = torch.cuda.Event(enable_timing=True, external=True)
-                b_ = torch.cuda.Event(enable_timing=True, external=True)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    a.record()
-                    fn()
-                    b_.record()
-                inside = True
-            except Exception:                          # noqa: BLE001  (older torch: events around the replay)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    fn()
-                inside = False
-            times = []
-            for _ in range(reps):
-                flush.zero_()
-                if inside:
-                    g.replay()
-                else:
-                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    g.replay()
-                    b_.record()
-                torch.cuda.synchronize()
-                times.append(a.elapsed_time(b_))
-            return statistics.mean(times) * 1e-3
-
-        t_fwd = timed(lambda: model.hot_path(db0.x, g0))
-        xcat = torch.empty(n, 97, device=dev)
+        t_fwd = timed(lambda: model.hot_path(db0.x, g0), flush)
+        xcat = torch.empty(n, ops.XCAT_LD, device=dev)[:, :97]       # 16-byte aligned rows, like the model's
         ops.graph_conv_fwd(db0.x, g0.rowptr, g0.col, g0.dis, convs[0].lin.weight, convs[0].bias,
                            0, 1, xcat[:, 0:32])
         t_l2 = timed(lambda: ops.graph_conv_fwd(xcat[:, 0:32], g0.rowptr, g0.col, g0.dis,
                                                 convs[1].lin.weight, convs[1].bias, 0, 1,
-                                                xcat[:, 32:64]))
-        t_k0 = timed(lambda: model.build_graph(db0))
+                                                xcat[:, 32:64]), flush)
+        t_k0 = timed(lambda: model.build_graph(db0), flush)
     a_fwd = forward_bytes(n, e, cfg.batch_size, cfg.num_features, cfg.k)
     a_l2 = layer_bytes(n, e, 32, 32)
     # stricter figure when the layers are fused (x_1..x_3 never re-read from HBM)
     a_stack = (4 * (n + 1) + 4 * e + 4 * n + 4 * n * cfg.num_features + 4 * n * 97
                + 4 * (cfg.batch_size + 1) + 4 * cfg.batch_size * cfg.k * 98)
     fused = ops.stack_fwd_supported(cfg.num_features, db0.max_nodes) and dg.fused_enabled()
-    per_layer = {"kernel": "gc_aggregate_chan<1> (GraphConv 32->32 forward, per-layer path)",
+    per_layer = {"kernel": "gc_aggregate_vec32 (GraphConv 32->32 forward, per-layer path)",
                  "algorithmic_bytes": a_l2, "launch_us": t_l2 * 1e6,
                  "achieved_GBps": a_l2 / t_l2 / 1e9, "frac_of_peak": a_l2 / t_l2 / 1e9 / peak}
     if fused:
@@ -586,9 +695,9 @@ def main():
             # device time of the gather (+ K0b, like graph_build_us) and of one whole resident step
             ids0 = id_pinned[0].to(dev)
             with torch.no_grad():
-                t_gather = timed(lambda: ds.batch(id_sets[0], ids0))
-                t_collate = timed(lambda: ds.batch(id_sets[0], ids0, bitmaps=False))
-            t_res_step = timed(lambda: trainer.step_resident(ds, id_sets[0], ids0, global_batch))
+                t_gather = timed(lambda: ds.batch(id_sets[0], ids0), flush)
+                t_collate = timed(lambda: ds.batch(id_sets[0], ids0, bitmaps=False), flush)
+            t_res_step = timed(lambda: trainer.step_resident(ds, id_sets[0], ids0, global_batch), flush)
             gather_bytes = 8 * e + 4 * (n + 1) * 2 + 8 * n + 8 * n * cfg.num_features   # read + write
             resident = {"value": global_batch * e2e_steps / res_s, "unit": UNIT,
                         "h2d_bytes_per_step": 4 * bs, "d2h_bytes_per_step": 4, "steps": e2e_steps,
@@ -645,7 +754,10 @@ def main():
                               "d2h_bytes_per_step": 4, "steps": e2e_steps,
                               "note": "same loop, host batch collated with int32 edge_index/batch "
                                       "(dgcnn_build_graph_i32): NOT the reference's int64 format; `e2e` is"},
-        "e2e_resident_dataset": resident,
+        "e2e_resident_dataset": resident if world == 1 else resident_multi,
+        "params_equal_across_ranks": params_equal, "comm_status_per_rank": comm_status_all,
+        "shards": ("balanced (dp.balanced_shards of a global batch of bs*N graphs)" if balanced else
+                   "independent draws per rank") if world > 1 else "n/a",
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,

@@ -7,7 +7,7 @@ from .nn import (GCNConv, GraphConvolution, Model, SortAggregation, SortPool,
                  classifier_in_features, fused_enabled, graph_conv_stack, remove_self_loops,
                  set_fused, set_custom_tail, custom_tail_enabled)
 from .synth import CONFIGS, GraphBatch, collate, make_batch, make_graphs
-from .dp import GradBucket, shard_bounds, shard_ids
+from .dp import GradBucket, balanced_shards, shard_bounds, shard_ids
 from .optim import FlatAdam
 from .trainer import FusedTrainer
 from .data import (DeviceDataset, Indegree, ResidentBatch, ResidentLoader, epoch_batches, indegree, load_fold, read_tu_dataset,

@@ -84,6 +84,10 @@ SIGNATURES = {
                                        c_void_p, c_void_p,
                                        c_void_p, c_int64, c_int32,
                                        c_int64, c_int32, c_int32, c_void_p]),
+    "dgcnn_graph_conv_fwd_graphs": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_int64, c_int64,
+                                              c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                              c_int64, c_int32, c_int32, c_void_p]),
     "dgcnn_project_rows": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "dgcnn_graph_conv_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "dgcnn_graph_conv_bwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64,
@@ -168,6 +172,7 @@ SIGNATURES = {
     "dgcnn_exchange_open": (c_int32, [c_void_p, c_void_p]),
     "dgcnn_exchange_close": (c_int32, [c_void_p]),
     "dgcnn_exchange_destroy": (c_int32, [c_void_p]),
+    "dgcnn_allreduce_set_trace": (None, [c_void_p]),
     "dgcnn_allreduce_adam": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                        c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,
                                        c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

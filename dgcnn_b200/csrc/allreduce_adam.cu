@@ -41,7 +41,14 @@ struct AllreduceAdamParams {
     unsigned char* exch[kArMaxWorld];
     int world, rank;
     int32_t* status;
+    int64_t* trace;      // optional debug timeline (dgcnn_allreduce_set_trace): [steps][4] globaltimer ns
 };
+
+__device__ __forceinline__ int64_t ar_global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (int64_t)t;
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -53,6 +60,9 @@ __global__ void __launch_bounds__(kArThreads)
 allreduce_adam_kernel(AllreduceAdamParams a) {
     const int64_t e = *a.epoch;
     const int parity = (int)(e & 1);
+    const bool tracer = a.trace && blockIdx.x == 0 && threadIdx.x == 0;
+    int64_t* tr = tracer ? a.trace + (e & 1023) * 4 : nullptr;
+    if (tracer) tr[0] = ar_global_ns();                   // kernel entered: this rank's step is over
     const uint32_t target = (uint32_t)(gridDim.x * (uint64_t)a.world * (uint64_t)(e / 2 + 1));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,6 +89,7 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
     if (threadIdx.x == 0)
         for (int r = 0; r < a.world; ++r)
             atomicAdd_system(reinterpret_cast<uint32_t*>(a.exch[r] + parity * 128), 1u);
+    if (tracer) tr[1] = ar_global_ns();                   // sums pushed, arrival signalled
 
     // 2. wait until every CTA of every rank has arrived at the LOCAL counter.  A peer that never
     //    shows up (~20 s) raises DGCNN_COMM_TIMEOUT and the step is ABANDONED: no sum, no Adam, no
@@ -99,6 +110,7 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
     }
     __syncthreads();
     if (timed_out) return;
+    if (tracer) tr[2] = ar_global_ns();                   // every rank has arrived (wait = [2] - [1])
 
     // 3. sum the local slots in rank order, Adam on the parameters
     const int64_t t = *a.step + 1;
@@ -118,6 +130,7 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
             a.p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + a.eps);
         }
     }
+    if (tracer) tr[3] = ar_global_ns();                   // CTA 0 done with its share of sum + Adam
 }
 
 __global__ void allreduce_adam_bump(int64_t* step, int64_t* epoch, const int32_t* status) {
@@ -179,6 +192,9 @@ extern "C" int dgcnn_exchange_destroy(void* local_ptr) {
     return (!local_ptr || cudaFree(local_ptr) == cudaSuccess) ? DGCNN_OK : DGCNN_ERR_CUDA;
 }
 
+static int64_t* g_ar_trace = nullptr;
+extern "C" void dgcnn_allreduce_set_trace(int64_t* device_buffer) { g_ar_trace = device_buffer; }
+
 extern "C" size_t dgcnn_allreduce_adam_exchange_bytes(int64_t n_total, int32_t world) {
     if (n_total < 0 || world < 1) return 0;
     return exchange_bytes(n_total, world);
@@ -202,6 +218,7 @@ extern "C" int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg,
         a.exch[r] = static_cast<unsigned char*>(exchange[r]);
     }
     a.world = world; a.rank = rank; a.status = status;
+    a.trace = g_ar_trace;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     allreduce_adam_kernel<<<kArCtas, kArThreads, 0, st>>>(a);
     DGCNN_RETURN_IF_LAUNCH_FAILED();

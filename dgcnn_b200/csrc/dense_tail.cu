@@ -982,6 +982,24 @@ extern "C" int dgcnn_tail_bwd_join(void* stream) {
 }
 
 
+// h[n][32] = x[n][cin] W^T (W [32][cin], PyG's `lin` of GCNConv.forward) on the tensor cores
+// (3xTF32, fp32-accurate): project FIRST when the input is wider than the 32 output channels
+// (D&D F = 90, power-law F = 64), then aggregate 32-wide rows with dgcnn_graph_conv_fwd(weight =
+// NULL) -- the order PyG itself uses.
+extern "C" int dgcnn_project_rows(const float* x, int64_t ldx, int32_t cin, const float* weight, float* h,
+                                  int64_t num_nodes, void* stream) {
+    if (num_nodes < 0 || cin < 1 || ldx < cin) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_nodes >= (int64_t)kGemmBM * 65535 || num_nodes >= INT32_MAX / 64) return DGCNN_ERR_UNSUPPORTED;
+    if (num_nodes == 0) return DGCNN_OK;
+    if (!x || !weight || !h) return DGCNN_ERR_INVALID_ARGUMENT;
+    dim3 grid(1, (unsigned)ceil_div(num_nodes, kGemmBM), 1);
+    const int kchunk = (int)ceil_div(cin, 16) * 16;
+    gemm_f32<false, false, false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, weight, cin, h, (int)num_nodes, 32, cin, kchunk, nullptr);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
 extern "C" int dgcnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps,
                                float grad_scale, void* stream) {

@@ -42,6 +42,11 @@ struct AggParams {
     int norm;
     int swap_coef;       // 0: forward (A_hat), 1: backward (A_hat^T)
     int64_t n;
+    // gc_aggregate_vec32 only: when gptr != null, process ONLY the rows of graphs with more than
+    // `big_rows` nodes (what gc_aggregate_staged leaves behind)
+    const int32_t* gptr;
+    int num_graphs;
+    int big_rows;
 };
 
 __device__ __forceinline__ void load_matrix(const AggParams& p, float* smat, float* sbias) {
@@ -222,12 +227,20 @@ __global__ void __launch_bounds__(kConvThreads) gc_aggregate_vec32(AggParams p) 
     const int lane = threadIdx.x & 31, q = lane & 7, grp = lane >> 3;
     const unsigned gmask = 0xffu << (grp * 8);
     const int64_t warps = (int64_t)gridDim.x * (kConvThreads / 32);
-    const int64_t ntask = (p.n + kVecRows - 1) / kVecRows;
-    for (int64_t task = (int64_t)blockIdx.x * (kConvThreads / 32) + (threadIdx.x >> 5); task < ntask;
-         task += warps) {
-        const int64_t row = task * kVecRows + grp;
-        const bool live = row < p.n;
-        const int64_t rr = live ? row : p.n - 1;
+    const int64_t wid = (int64_t)blockIdx.x * (kConvThreads / 32) + (threadIdx.x >> 5);
+    // row ranges: the whole batch, or (big_only) one graph above the cap after the other
+    const int nrange = p.gptr ? p.num_graphs : 1;
+    for (int rg = 0; rg < nrange; ++rg) {
+    int64_t r_lo = 0, r_hi = p.n;
+    if (p.gptr) {
+        r_lo = p.gptr[rg]; r_hi = p.gptr[rg + 1];
+        if (r_hi - r_lo <= p.big_rows) continue;
+    }
+    const int64_t ntask = (r_hi - r_lo + kVecRows - 1) / kVecRows;
+    for (int64_t task = wid; task < ntask; task += warps) {
+        const int64_t row = r_lo + task * kVecRows + grp;
+        const bool live = row < r_hi;
+        const int64_t rr = live ? row : r_hi - 1;
         const float di = p.dis[rr];
         const float self_c = p.swap_coef ? row_coef(di, p.norm) : col_coef(di, p.norm);
         const float scale = p.swap_coef ? col_coef(di, p.norm) : row_coef(di, p.norm);
@@ -289,35 +302,121 @@ __global__ void __launch_bounds__(kConvThreads) gc_aggregate_vec32(AggParams p) 
                 if (4 * q + u < p.fout) orow[u] = p.accumulate ? orow[u] + yy[u] : yy[u];
         }
     }
+    }
     (void)gmask;
 }
 
-// identity "projection" variant: out = act(agg + bias) for fout == fin == 32 (the aggregation of
-// rows that were projected first, model.py:30 when F > 32)
-__global__ void __launch_bounds__(kConvThreads) gc_project_rows(const float* __restrict__ x, int64_t ldx, int fin,
-                                                                const float* __restrict__ w /*[32][fin]*/,
-                                                                float* __restrict__ h /*[n][32]*/, int64_t n) {
-    extern __shared__ float smem[];        // wt[k][32]
-    for (int idx = threadIdx.x; idx < fin * 32; idx += blockDim.x) {
-        const int c = idx / fin, k = idx - c * fin;
-        smem[k * 32 + c] = w[idx];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (kConvThreads / 32);
-    for (int64_t r0 = ((int64_t)blockIdx.x * (kConvThreads / 32) + (threadIdx.x >> 5)) * 4; r0 < n; r0 += warps * 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* xr[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) xr[u] = x + min(r0 + u, n - 1) * ldx;
-        for (int k = 0; k < fin; ++k) {
-            const float wk = smem[k * 32 + lane];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] = fmaf(xr[u][k], wk, acc[u]);
+
+// ---- per-graph, neighbour rows staged in shared memory ------------------------------------------
+// The vectorised kernel above fetches every neighbour row from L2: 128 B per edge and layer, 650 MB
+// per layer on the power-law configuration -- the L2 gather bandwidth is its bound.  Graphs never
+// share nodes, so a CTA that owns one graph can read the graph's input rows ONCE (coalesced,
+// pre-scaled by c_j), keep them in shared memory (128 B per node: 1728 nodes fit one SM) and serve
+// the gather from there: HBM / L2 traffic drops to one read + one write of the rows and the CSR
+// columns, the gather runs at shared-memory bandwidth.  Persistent CTAs walk the graphs largest
+// first (gorder); a graph that does not fit is left to gc_aggregate_vec32 in `big_only` mode.
+constexpr int kStagedThreads = 512;
+constexpr int kStagedMaxRows = 1728;     // 216 KB of rows + 4.2 KB of weights
+
+struct StagedParams {
+    AggParams a;
+    const int32_t* gptr;
+    const int32_t* gorder;     // optional: graph ids by descending size
+    int num_graphs;
+    int cap_rows;              // rows the dynamic shared buffer holds
+};
+
+__global__ void __launch_bounds__(kStagedThreads) gc_aggregate_staged(StagedParams sp) {
+    extern __shared__ __align__(16) float smem[];
+    const AggParams& p = sp.a;
+    float* smat = smem;                    // [32][32]
+    float* sbias = smem + 32 * 32;         // [32]
+    float4* rows = reinterpret_cast<float4*>(smem + 32 * 32 + 32);     // [cap_rows][8]
+    if (p.out) {
+        for (int idx = threadIdx.x; idx < 32 * 32; idx += blockDim.x) {
+            const int k = idx >> 5, c = idx & 31;
+            float v = 0.f;
+            if (!p.mat) v = k == c ? 1.f : 0.f;
+            else if (c < p.fout) v = p.mat_transposed ? p.mat[c * 32 + k] : p.mat[k * p.fout + c];
+            smat[idx] = v;
         }
+        for (int c = threadIdx.x; c < 32; c += blockDim.x) sbias[c] = (p.bias && c < p.fout) ? p.bias[c] : 0.0f;
+    }
+    const int lane = threadIdx.x & 31, q = lane & 7, grp = lane >> 3;
+    const int warp = threadIdx.x >> 5, nwarps = kStagedThreads / 32;
+    const bool vec_ok = p.out && p.fout == 32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    for (int gi = blockIdx.x; gi < sp.num_graphs; gi += gridDim.x) {
+        const int g = sp.gorder ? sp.gorder[gi] : gi;
+        const int base = sp.gptr[g], n = sp.gptr[g + 1] - base;
+        if (n <= 0 || n > sp.cap_rows) continue;                  // (too large: the big_only pass takes it)
+        __syncthreads();                                          // the previous graph's readers are done
+        // stage c_j * x_j, eight 16-byte loads in flight per thread
+        for (int i0 = threadIdx.x; i0 < n * 8; i0 += kStagedThreads * 8) {
+            float4 v[8];
+            float c[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (r0 + u < n) h[(r0 + u) * 32 + lane] = acc[u];
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0 + u * kStagedThreads;
+                const int r = min(idx, n * 8 - 1) >> 3;
+                v[u] = *reinterpret_cast<const float4*>(p.feat + (int64_t)(base + r) * p.ldf + 4 * (idx & 7));
+                const float d = p.dis[base + r];
+                c[u] = p.swap_coef ? row_coef(d, p.norm) : col_coef(d, p.norm);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0 + u * kStagedThreads;
+                if (idx < n * 8) rows[idx] = make_float4(c[u] * v[u].x, c[u] * v[u].y, c[u] * v[u].z, c[u] * v[u].w);
+            }
+        }
+        __syncthreads();
+        for (int r0 = warp * kVecRows; r0 < n; r0 += nwarps * kVecRows) {
+            const int row = r0 + grp;
+            const bool live = row < n;
+            const int rr = live ? row : n - 1;
+            const float di = p.dis[base + rr];
+            const float scale = p.swap_coef ? col_coef(di, p.norm) : row_coef(di, p.norm);
+            float4 agg = rows[rr * 8 + q];                        // the self loop, already c_i * x_i
+            const int beg = live ? p.rowptr[base + rr] : 0, end = live ? p.rowptr[base + rr + 1] : 0;
+            int steps = (end - beg + 7) >> 3;
+            steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 8));
+            steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 16));
+            for (int it = 0; it < steps; ++it) {
+                const int e = beg + it * 8 + q;
+                const int j = e < end ? p.col[e] - base : 0;
+                const int left = end - beg - it * 8;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int jj = __shfl_sync(DGCNN_FULL_MASK, j, grp * 8 + u);
+                    if (u < left) {
+                        const float4 v = rows[jj * 8 + q];
+                        agg.x += v.x; agg.y += v.y; agg.z += v.z; agg.w += v.w;
+                    }
+                }
+            }
+            agg.x *= scale; agg.y *= scale; agg.z *= scale; agg.w *= scale;
+            if (p.agg_out && live) *reinterpret_cast<float4*>(p.agg_out + (int64_t)(base + row) * 32 + 4 * q) = agg;
+            if (!p.out) continue;
+            float4 y = *reinterpret_cast<const float4*>(sbias + 4 * q);
+            const float4* m4 = reinterpret_cast<const float4*>(smat);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float comp = (k & 3) == 0 ? agg.x : ((k & 3) == 1 ? agg.y : ((k & 3) == 2 ? agg.z : agg.w));
+                const float a = __shfl_sync(DGCNN_FULL_MASK, comp, grp * 8 + (k >> 2));
+                const float4 w = m4[k * 8 + q];
+                y.x = fmaf(a, w.x, y.x); y.y = fmaf(a, w.y, y.y); y.z = fmaf(a, w.z, y.z); y.w = fmaf(a, w.w, y.w);
+            }
+            if (p.act == DGCNN_ACT_TANH) { y.x = tanhf(y.x); y.y = tanhf(y.y); y.z = tanhf(y.z); y.w = tanhf(y.w); }
+            if (!live) continue;
+            float* orow = p.out + (int64_t)(base + row) * p.ldo + 4 * q;
+            if (vec_ok && !p.accumulate) {
+                *reinterpret_cast<float4*>(orow) = y;
+            } else {
+                const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (4 * q + u < p.fout) orow[u] = p.accumulate ? orow[u] + yy[u] : yy[u];
+            }
+        }
     }
 }
 
@@ -356,6 +455,37 @@ static int launch_aggregate(const AggParams& p, cudaStream_t st) {
     else DGCNN_LAUNCH_AGG(gc_aggregate_chan<4>);
 #undef DGCNN_LAUNCH_AGG
     DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
+// Aggregation with the batch's graph structure known (gptr): graphs that fit one SM's shared
+// memory go through gc_aggregate_staged, larger ones (max_nodes unknown or above the cap) through
+// gc_aggregate_vec32 restricted to their rows.  Falls back to launch_aggregate when the rows are
+// not 32 aligned channels.
+static int launch_aggregate_graphs(const AggParams& p0, const int32_t* gptr, const int32_t* gorder,
+                                   int64_t num_graphs, int64_t max_nodes, cudaStream_t st) {
+    if (!gptr || num_graphs < 1 || !vec32_ok(p0)) return launch_aggregate(p0, st);
+    const int cap = (max_nodes > 0 && max_nodes < kStagedMaxRows) ? (int)((max_nodes + 15) / 16 * 16) : kStagedMaxRows;
+    StagedParams sp{};
+    sp.a = p0; sp.gptr = gptr; sp.gorder = gorder; sp.num_graphs = (int)num_graphs; sp.cap_rows = cap;
+    const size_t smem = sizeof(float) * (32 * 32 + 32) + (size_t)cap * 128;
+    if (cudaFuncSetAttribute(gc_aggregate_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;                                  // 512 threads each
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)DGCNN_NUM_SMS * per_sm;
+    if (grid > num_graphs) grid = num_graphs;
+    gc_aggregate_staged<<<(unsigned)grid, kStagedThreads, smem, st>>>(sp);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (max_nodes <= 0 || max_nodes > cap) {                     // someone may not have fitted
+        AggParams pb = p0;
+        pb.gptr = gptr; pb.num_graphs = (int)num_graphs; pb.big_rows = cap;
+        const size_t smem_v = pb.out ? sizeof(float) * (32 * 32 + 32) : 0;
+        gc_aggregate_vec32<<<DGCNN_NUM_SMS * 4, kConvThreads, smem_v, st>>>(pb);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
     return DGCNN_OK;
 }
 
@@ -515,23 +645,30 @@ extern "C" int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin, co
     return launch_aggregate(p, static_cast<cudaStream_t>(stream));
 }
 
-// h[n][32] = x[n][cin] W^T (W [32][cin], PyG's `lin` of GCNConv.forward): project FIRST when the
-// input is wider than the 32 output channels (D&D F = 90, power-law F = 64), then aggregate the
-// 32-wide rows with dgcnn_graph_conv_fwd(weight = NULL) -- the order PyG itself uses.
-extern "C" int dgcnn_project_rows(const float* x, int64_t ldx, int32_t cin, const float* weight, float* h,
-                                  int64_t num_nodes, void* stream) {
-    if (num_nodes < 0 || cin < 1 || ldx < cin) return DGCNN_ERR_INVALID_ARGUMENT;
-    if (cin > 512) return DGCNN_ERR_UNSUPPORTED;
+// dgcnn_graph_conv_fwd with the batch's graph offsets: same result, but every graph that fits one
+// SM's shared memory (<= 1728 nodes at 32 channels) is aggregated from rows staged there.
+extern "C" int dgcnn_graph_conv_fwd_graphs(const float* x, int64_t ldx, int32_t cin, const int32_t* rowptr,
+                                           const int32_t* col, const float* dis, const int32_t* gptr,
+                                           const int32_t* gorder, int64_t num_graphs, int64_t max_nodes,
+                                           const float* weight, const float* bias, float* y, int64_t ldy,
+                                           int32_t cout, int64_t num_nodes, int32_t norm, int32_t act,
+                                           void* stream) {
+    if (num_nodes < 0 || cin < 1 || cout < 1 || ldx < cin || ldy < cout || num_graphs < 0)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (norm != DGCNN_NORM_SYM && norm != DGCNN_NORM_RW) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (act != DGCNN_ACT_NONE && act != DGCNN_ACT_TANH) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (cin > kMaxChannels || cout > kMaxChannels) return DGCNN_ERR_UNSUPPORTED;
     if (num_nodes == 0) return DGCNN_OK;
-    if (!x || !weight || !h) return DGCNN_ERR_INVALID_ARGUMENT;
-    const size_t smem = sizeof(float) * 32 * (size_t)cin;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(gc_project_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return DGCNN_ERR_CUDA;
-    gc_project_rows<<<grid_for((num_nodes + 3) / 4, kConvThreads / 32, 8), kConvThreads, smem,
-                      static_cast<cudaStream_t>(stream)>>>(x, ldx, cin, weight, h, num_nodes);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
-    return DGCNN_OK;
+    if (!x || !rowptr || !dis || !y) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (!weight && !(cin == 32 && cout == 32 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0))
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    AggParams p{};
+    p.feat = x; p.ldf = ldx; p.fin = cin;
+    p.rowptr = rowptr; p.col = col; p.dis = dis;
+    p.mat = weight; p.mat_transposed = 1; p.bias = bias;
+    p.agg_out = nullptr; p.out = y; p.ldo = ldy; p.fout = cout;
+    p.accumulate = 0; p.act = act; p.norm = norm; p.swap_coef = 0; p.n = num_nodes;
+    return launch_aggregate_graphs(p, gptr, gorder, num_graphs, max_nodes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t dgcnn_graph_conv_bwd_workspace_bytes(int64_t num_nodes, int32_t cin, int32_t cout) {

@@ -17,6 +17,71 @@
 
 namespace dgcnn {
 
+// Top-k SELECTION for graphs much larger than k (D&D: 5748 nodes, k = 291): sorting all n keys is
+// wasted work -- only the k winners are needed, in order.  Radix select on the 32-bit order keys
+// (four 8-bit passes, shared-memory histograms) finds the k-th key T; an ORDERED count settles
+// the ties at T by ascending node index (the contract); the k winners are compacted and only THEY
+// are sorted (bitonic on <= next_pow2(k) composites).  Returns with the winners' composites sorted
+// in buf[0..keep).  Keys are re-read from x (L2 hits) instead of kept: any n fits.
+__device__ void select_top_k(const float* __restrict__ x, int64_t ldx, int d, int base, int n, int keep,
+                             uint64_t* buf /* >= next_pow2(keep) */, uint32_t* hist /* [256 + 8] */) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    auto key_of = [&](int t) { return descending_key_bits(x[(int64_t)(base + t) * ldx + (d - 1)]); };
+    uint32_t prefix = 0, want = (uint32_t)keep;            // the `want`-th smallest among keys matching prefix
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < 256; i += nt) hist[i] = 0;
+        __syncthreads();
+        for (int t = tid; t < n; t += nt) {
+            const uint32_t kb = key_of(t);
+            if ((kb & himask) == prefix) atomicAdd(&hist[(kb >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {                                    // 256 buckets: a serial scan is ~256 cycles
+            uint32_t cum = 0, b = 0;
+            for (; b < 256; ++b) {
+                if (cum + hist[b] >= want) break;
+                cum += hist[b];
+            }
+            hist[256] = b;
+            hist[257] = want - cum;
+        }
+        __syncthreads();
+        prefix |= hist[256] << shift;
+        want = hist[257];
+        __syncthreads();
+    }
+    const uint32_t T = prefix, r_eq = want;                // take every key < T and the first r_eq keys == T
+    // ordered count of the keys == T: contiguous chunks per thread, block scan of the chunk counts
+    const int chunk = (n + nt - 1) / nt;
+    const int t0 = min(n, tid * chunk), t1 = min(n, t0 + chunk);
+    uint32_t mine = 0;
+    for (int t = t0; t < t1; ++t) mine += key_of(t) == T;
+    uint32_t* scan = reinterpret_cast<uint32_t*>(buf);      // [nt] (buf is free until the compaction)
+    __syncthreads();
+    scan[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < nt; ++i) { const uint32_t v = scan[i]; scan[i] = run; run += v; }
+        hist[258] = 0;                                      // compaction cursor
+    }
+    __syncthreads();
+    uint32_t eq_before = scan[tid];
+    __syncthreads();                                        // scan[] (= buf) is rewritten below
+    const uint32_t p2 = next_pow2((uint32_t)keep);
+    for (uint32_t i = tid + keep; i < p2; i += nt) buf[i] = kPadComposite;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t kb = key_of(t);
+        bool take = kb < T;
+        if (kb == T) { take = eq_before < r_eq; ++eq_before; }
+        if (take) buf[atomicAdd(&hist[258], 1u)] = ((uint64_t)kb << 32) | (uint32_t)t;
+    }
+    bitonic_sort_block(buf, p2);                            // composites are unique: the order is fixed
+}
+
 // one CTA per graph (grid-stride). smem_cap = composites that fit the dynamic
 // shared buffer; larger graphs sort in the global workspace slice [2*base, 2*base+P)
 __global__ void __launch_bounds__(1024)
@@ -25,6 +90,7 @@ sp_fwd_kernel(const float* __restrict__ x, int64_t ldx, int d,
                               float* __restrict__ out, int32_t* __restrict__ perm,
                               uint64_t* __restrict__ workspace, uint32_t smem_cap) {
     extern __shared__ uint64_t sbuf[];
+    __shared__ uint32_t hist[264];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int64_t g = blockIdx.x; g < num_graphs; g += gridDim.x) {
         const int base = gptr[g];
@@ -32,24 +98,40 @@ sp_fwd_kernel(const float* __restrict__ x, int64_t ldx, int d,
         const int keep = min(n, k);
         if (n > 1) {
             const uint32_t p = next_pow2((uint32_t)n);
-            uint64_t* buf = (p <= smem_cap) ? sbuf : workspace + 2 * (int64_t)base;
+            // many more nodes than winners: select, then sort the winners only
+            const bool select = n >= 4 * keep && n > 1024 && next_pow2((uint32_t)keep) <= smem_cap &&
+                                (uint32_t)blockDim.x * 4u <= smem_cap * 8u;
+            uint64_t* buf = (select || p <= smem_cap) ? sbuf : workspace + 2 * (int64_t)base;
             __syncthreads();  // previous graph's readers are done with sbuf
-            for (uint32_t t = threadIdx.x; t < p; t += blockDim.x) {
-                uint64_t c = kPadComposite;
-                if (t < (uint32_t)n) {
-                    float key = x[(int64_t)(base + t) * ldx + (d - 1)];
-                    c = ((uint64_t)descending_key_bits(key) << 32) | t;
+            if (select) {
+                select_top_k(x, ldx, d, base, n, keep, buf, hist);
+            } else {
+                for (uint32_t t = threadIdx.x; t < p; t += blockDim.x) {
+                    uint64_t c = kPadComposite;
+                    if (t < (uint32_t)n) {
+                        float key = x[(int64_t)(base + t) * ldx + (d - 1)];
+                        c = ((uint64_t)descending_key_bits(key) << 32) | t;
+                    }
+                    buf[t] = c;
                 }
-                buf[t] = c;
+                bitonic_sort_block(buf, p);
             }
-            bitonic_sort_block(buf, p);
-            // warp per output row: gather the winners
-            for (int r = warp; r < keep; r += nwarps) {
-                int srcrow = base + (int)(uint32_t)(buf[r] & 0xffffffffu);
-                const float* xr = x + (int64_t)srcrow * ldx;
-                float* orow = out + ((int64_t)g * k + r) * d;
-                for (int c = lane; c < d; c += 32) orow[c] = xr[c];
-                if (lane == 0) perm[g * k + r] = srcrow;
+            // the winners, one warp per row, eight rows in flight per warp (the copy is L2 / HBM latency)
+            constexpr int R = 8;
+            for (int r0 = warp * R; r0 < keep; r0 += nwarps * R) {
+                int src[R];
+#pragma unroll
+                for (int u = 0; u < R; ++u) src[u] = base + (int)(uint32_t)(buf[min(r0 + u, keep - 1)] & 0xffffffffu);
+                for (int c0 = 0; c0 < d; c0 += 32) {
+                    const int c = c0 + lane;
+                    float v[R];
+#pragma unroll
+                    for (int u = 0; u < R; ++u) v[u] = c < d ? x[(int64_t)src[u] * ldx + c] : 0.f;
+#pragma unroll
+                    for (int u = 0; u < R; ++u)
+                        if (c < d && r0 + u < keep) out[((int64_t)g * k + r0 + u) * d + c] = v[u];
+                }
+                if (lane < R && r0 + lane < keep) perm[g * k + r0 + lane] = src[lane];
             }
         } else if (n == 1) {
             const float* xr = x + (int64_t)base * ldx;

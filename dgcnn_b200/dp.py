@@ -14,7 +14,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_ids", "GradBucket", "PeerExchange"]
+__all__ = ["shard_bounds", "shard_ids", "balanced_shards", "GradBucket", "PeerExchange"]
 
 
 def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
@@ -43,6 +43,23 @@ def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int
         bounds.append((lo, hi))
         lo = hi
     return bounds
+
+
+def balanced_shards(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Partition graphs ``0..len(costs)`` into ``world_size`` shards of (nearly) equal COUNT whose
+    cost PROFILES match: the graphs are ranked by cost and dealt boustrophedon-wise (rank 0, 1, ..,
+    W-1, W-1, .., 1, 0, ...), so every rank gets one graph of each size class -- including its share
+    of the largest ones, which bound the fused kernels' run time.  The per-step barrier of the
+    gradient exchange then waits for ranks that finish together, not for whoever drew the biggest
+    graph.  Deterministic: every rank computes the same partition without communication.  Each
+    shard lists its graphs in ascending id (the batch order of the loader is kept)."""
+    n = len(costs)
+    order = sorted(range(n), key=lambda i: (-float(costs[i]), i))
+    shards: List[List[int]] = [[] for _ in range(world_size)]
+    for pos, i in enumerate(order):
+        rnd, k = divmod(pos, world_size)
+        shards[k if rnd % 2 == 0 else world_size - 1 - k].append(i)
+    return [sorted(s) for s in shards]
 
 
 def shard_ids(ids: Sequence[int], nodes: Sequence[int], edges: Sequence[int], world_size: int,

@@ -202,7 +202,7 @@ class _StackFn(torch.autograd.Function):
             h = x
             for l, (w, b) in enumerate(zip(weights, biases)):
                 out = xcat[:, offs[l]:offs[l + 1]]
-                ops.graph_conv_fwd(h, graph.rowptr, graph.col, graph.dis, w, b, norm, ACT_TANH, out)
+                ops.graph_conv_fwd(h, graph.rowptr, graph.col, graph.dis, w, b, norm, ACT_TANH, out, graph=graph)
                 h = out
             pooled, perm = ops.sort_pool_fwd(xcat, graph.gptr, k, graph.max_nodes)
         ctx.graph, ctx.norm, ctx.offs, ctx.k, ctx.fused = graph, norm, offs, k, fused

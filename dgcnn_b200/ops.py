@@ -190,7 +190,9 @@ def build_graph(edge_index: Tensor, batch: Optional[Tensor], num_nodes: int, num
     _lib.check(rc, "build_graph")
     LAUNCHES["build_graph"] += 3 + (1 if EXACT_SYMMETRY_CHECK else 0)
     graph = Graph(rowptr, col, rowptr_t, col_t, dis, gptr, gorder, status, n, b, int(max_nodes))
-    if batch is not None and b > 0 and 0 < int(max_nodes) <= BITMAP_MAX_NODES:
+    # K0b's bitmaps only serve the fused kernels: skip them when the largest graph cannot run there
+    if (batch is not None and b > 0 and 0 < int(max_nodes) <= BITMAP_MAX_NODES
+            and int(lib.dgcnn_stack_fwd_supported(1, int(max_nodes)))):
         _build_bitmaps(graph, transpose, batch)
     return graph
 
@@ -272,7 +274,8 @@ PROJECT_FIRST_MIN = 33   # layers wider than this on the input side project befo
 
 
 def graph_conv_fwd(x: Tensor, rowptr: Tensor, col: Tensor, dis: Tensor, weight: Tensor,
-                   bias: Optional[Tensor], norm: int, act: int, out: Tensor) -> None:
+                   bias: Optional[Tensor], norm: int, act: int, out: Tensor,
+                   graph: Optional["Graph"] = None) -> None:
     """K1: ``out[:] = act(A_hat x W^T + b)`` in one launch; ``out`` may be a column
     slice of the concatenated buffer (model.py:30-34).  A layer with more than 32 input
     channels and 32 outputs (D&D: 90, power-law: 64) projects first -- ``h = x W^T`` in one
@@ -300,9 +303,17 @@ def graph_conv_fwd(x: Tensor, rowptr: Tensor, col: Tensor, dis: Tensor, weight: 
         _require_cuda(bias, "bias", torch.float32)
         bias = bias.contiguous()
     with torch.cuda.device(x.device):
-        rc = lib.dgcnn_graph_conv_fwd(_ptr(x), _rows(x, "x"), cin, _ptr(rowptr), _ptr(col),
-                                      _ptr(dis), _ptr(weight) if weight is not None else None, _ptr(bias), _ptr(out),
-                                      _rows(out, "out"), cout, n, int(norm), int(act), _stream())
+        if graph is not None and graph.gptr is not None and graph.num_graphs > 0 and cin == 32:
+            # the batch's graph offsets are known: rows staged in shared memory per graph
+            rc = lib.dgcnn_graph_conv_fwd_graphs(_ptr(x), _rows(x, "x"), cin, _ptr(rowptr), _ptr(col), _ptr(dis),
+                                                 _ptr(graph.gptr), _ptr(graph.gorder), graph.num_graphs,
+                                                 int(graph.max_nodes), _ptr(weight) if weight is not None else None,
+                                                 _ptr(bias), _ptr(out), _rows(out, "out"), cout, n, int(norm),
+                                                 int(act), _stream())
+        else:
+            rc = lib.dgcnn_graph_conv_fwd(_ptr(x), _rows(x, "x"), cin, _ptr(rowptr), _ptr(col),
+                                          _ptr(dis), _ptr(weight) if weight is not None else None, _ptr(bias),
+                                          _ptr(out), _rows(out, "out"), cout, n, int(norm), int(act), _stream())
     _lib.check(rc, "graph_conv_fwd")
     LAUNCHES["graph_conv_fwd"] += 1 if n > 0 else 0
 

@@ -174,6 +174,17 @@ int dgcnn_graph_conv_fwd(const float* x, int64_t ldx, int32_t cin,
  * gradient already sitting in that slice of the [N,97] gradient buffer).
  * dw [cout,cin] and db [cout] (db may be NULL) are overwritten.
  * ------------------------------------------------------------------------ */
+/* K1 with the batch's graph offsets (gptr [B+1], optionally gorder = graph ids by descending
+ * size, max_nodes = largest graph or 0 when unknown): the same result as dgcnn_graph_conv_fwd.
+ * For 32-channel, 16-byte aligned input rows every graph of up to 1728 nodes is aggregated by
+ * ONE CTA from rows staged in shared memory (one coalesced read of the graph's rows instead of
+ * 128 B per edge from L2); larger graphs are spread over the device by the row-parallel kernel. */
+int dgcnn_graph_conv_fwd_graphs(const float* x, int64_t ldx, int32_t cin, const int32_t* rowptr,
+                                const int32_t* col, const float* dis, const int32_t* gptr,
+                                const int32_t* gorder, int64_t num_graphs, int64_t max_nodes,
+                                const float* weight, const float* bias, float* y, int64_t ldy,
+                                int32_t cout, int64_t num_nodes, int32_t norm, int32_t act,
+                                void* stream);
 /* lin of GCNConv.forward on its own: h[n][32] = x W^T for inputs wider than 32 channels
  * (project first, then aggregate 32-wide rows: dgcnn_graph_conv_fwd with weight == NULL, which
  * is accepted for cin == cout == 32 and 16-byte aligned rows). */
@@ -420,6 +431,11 @@ int dgcnn_exchange_create(int64_t n_total, int32_t world, void** local_ptr, unsi
 int dgcnn_exchange_open(const unsigned char* handle64, void** peer_ptr);
 int dgcnn_exchange_close(void* peer_ptr);
 int dgcnn_exchange_destroy(void* local_ptr);
+/* Debug hook: device buffer int64[1024][4]; the exchange kernel of step e records
+ * %globaltimer (ns) at [e % 1024]: [0] entered, [1] sums pushed and arrival signalled, [2] all
+ * ranks arrived ([2] - [1] = time spent waiting for the slowest rank), [3] sum + Adam done.
+ * NULL switches it off.  Used by bench.py --trace-exchange (profiles/r02_exchange_trace_*.json). */
+void dgcnn_allreduce_set_trace(int64_t* device_buffer);
 int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                          int64_t n_params, int64_t n_total, int64_t* step, int64_t* epoch,
                          float lr, float beta1, float beta2, float eps, float grad_scale,

@@ -1014,11 +1014,14 @@ def test_cpu_tensors_are_rejected():
 
 
 # ------------------------------------------------------------------ K1 vectorised / project-first
+@pytest.mark.parametrize("staged", [False, True])
 @pytest.mark.parametrize("cout", [32, 1, 7])
 @pytest.mark.parametrize("norm", [0, 1])
-@pytest.mark.parametrize("sizes", [(17, 1, 0, 40, 9), (300, 3), (2, 2, 2, 2, 2, 2, 2), (1200,)])
-def test_graph_conv_vectorised_rows(cout, norm, sizes):
-    """gc_aggregate_vec32 (four 32-channel rows per warp, 16-byte neighbour loads): aligned
+@pytest.mark.parametrize("sizes", [(17, 1, 0, 40, 9), (300, 3), (2, 2, 2, 2, 2, 2, 2), (1200,), (1800, 5, 1729, 1728)])
+def test_graph_conv_vectorised_rows(cout, norm, sizes, staged):
+    """gc_aggregate_vec32 (four 32-channel rows per warp, 16-byte neighbour loads) and, with the
+    batch's graph offsets (`staged`), gc_aggregate_staged (one CTA per graph, rows in shared
+    memory; graphs above 1728 nodes fall to the row-parallel kernel in the same call): aligned
     32-wide inputs in a padded buffer, outputs into a column slice, multigraph input with
     loops, duplicates and edge-free rows; forward against the float64 oracle, backward against
     float64 autograd (K3 takes the same kernel for A_hat^T dpre)."""
@@ -1034,11 +1037,13 @@ def test_graph_conv_vectorised_rows(cout, norm, sizes):
     obuf = torch.full((n, 100), 7.0, device=DEV)
     osl = obuf[:, 64:64 + cout]
     ops.graph_conv_fwd(xbuf[:, 32:64], g.rowptr, g.col, g.dis, torch.from_numpy(w).to(DEV),
-                       torch.from_numpy(bias).to(DEV), norm, 1, osl)
+                       torch.from_numpy(bias).to(DEV), norm, 1, osl, graph=g if staged else None)
     ref64 = torch.tanh(orc.gcn_conv(torch.from_numpy(x).double(), torch.from_numpy(ei), torch.from_numpy(w).double(),
                                     torch.from_numpy(bias).double(), norm))
     assert (osl.cpu().double() - ref64).abs().max().item() <= ATOL
     assert (obuf[:, :64] == 7.0).all() and (obuf[:, 64 + cout:] == 7.0).all()
+    if staged:
+        return
     # backward through the module-level autograd function
     xt = torch.from_numpy(x).double().requires_grad_(True)
     wt = torch.from_numpy(w).double().requires_grad_(True)
@@ -1081,3 +1086,23 @@ def test_graph_conv_projects_first_for_wide_inputs(cin):
     refn = torch.tanh(orc.gcn_conv(torch.from_numpy(x).double(), torch.from_numpy(ei), torch.from_numpy(w).double(),
                                    torch.from_numpy(bias).double(), 0))
     assert torch.equal(torch.isnan(out.cpu()).any(1), torch.isnan(refn).any(1))
+
+
+@pytest.mark.parametrize("n,k", [(1500, 30), (5748, 291), (20000, 130), (4096, 1), (1025, 256)])
+@pytest.mark.parametrize("levels", [3, 50, 0])
+def test_sort_pool_selection_with_heavy_ties(n, k, levels):
+    """K2's radix SELECT path (graphs with at least 4k nodes and more than 1024): keys drawn from
+    a handful of distinct values (ties at the k-th key are settled by ascending node index),
+    -0.0 / +0.0, a NaN; permutation and pooled rows bit-exact against the oracle."""
+    rng = np.random.RandomState(n + k + levels)
+    x = rng.randn(n + 7, 5).astype(np.float32)
+    if levels:
+        x[:, -1] = rng.randint(0, levels, size=n + 7).astype(np.float32) * 0.25 - 0.5
+        x[rng.randint(0, n, 20), -1] = -0.0
+        x[rng.randint(0, n, 20), -1] = 0.0
+    batch = np.concatenate([np.zeros(n, np.int64), np.ones(7, np.int64)])
+    gptr = ops.graph_ptr(torch.from_numpy(batch).to(DEV), 2)
+    out, perm = ops.sort_pool_fwd(torch.from_numpy(x).to(DEV), gptr, k, n)
+    ro, rp = orc.sort_aggregation(torch.from_numpy(x), torch.from_numpy(batch), k, 2, return_perm=True)
+    np.testing.assert_array_equal(perm.cpu().numpy(), rp.numpy())
+    np.testing.assert_array_equal(out.cpu().numpy(), ro.numpy())

@@ -39,9 +39,27 @@ UNIT = "graphs/s"
 WORKLOAD = "collab"          # BASELINE.json configs[3]: the config the metric is quoted on
 RING = 4                     # distinct pre-built batches cycled through the timed steps
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
-# DRAM bytes (read + write) of one stack_fwd_mma_kernel launch on COLLAB-synth bs512, from the
-# ncu --set full capture summarised in profiles/r01_stack_fwd_mma_v3.md (not measurable live)
-KS_NCU_DRAM_BYTES = 1112064 + 109312
+# DRAM bytes (read + write) of one stack_fwd_mma_kernel launch on COLLAB-synth bs512 cannot be
+# measured live; they are parsed from the committed ncu --set full summary of the CURRENT kernel
+KS_PROFILE = os.path.join(ROOT, "profiles", "r02_stack_fwd_mma.md")
+
+
+def ks_traffic_from_profile():
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the first launch listed in
+    profiles/r02_stack_fwd_mma.md (written by scripts/summarize_ncu.py), or None."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        total, seen = 0.0, 0
+        for line in open(KS_PROFILE):
+            cells = [c.strip() for c in line.split("|")]
+            if len(cells) >= 4 and cells[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(cells[2].replace(",", "")) * unit.get(cells[3], 1.0)
+                seen += 1
+                if seen == 2:
+                    return int(total)
+    except (OSError, ValueError):
+        pass
+    return None
 
 
 def parse_args():
@@ -611,6 +629,30 @@ def main():
                                                 convs[1].lin.weight, convs[1].bias, 0, 1,
                                                 xcat[:, 32:64]), flush)
         t_k0 = timed(lambda: model.build_graph(db0), flush)
+        t_k0_only = timed(lambda: ops.build_graph(db0.edge_index, db0.batch, n, db0.num_graphs,
+                                                  transpose=False, max_nodes=0), flush)
+    # SURVEY 8f N2 variants of the two fused kernels (what the training step runs): KS that emits
+    # h1 / arg instead of `pooled`, KSB fed with d(h1)
+    n2 = None
+    if fused_step and ops.conv5_fusable(cfg.num_features, db0.max_nodes):
+        with torch.enable_grad():
+            g_t = model.build_graph(db0)               # with A_hat^T / transposed maps for the backward
+        with torch.no_grad():
+            ws_ = [c.lin.weight for c in convs]
+            bs_ = [c.bias for c in convs]
+            w5_, b5_ = model.conv5.weight, model.conv5.bias
+            t_ks5 = timed(lambda: ops.stack_fwd_conv5(db0.x, g_t, ws_, bs_, w5_, b5_, cfg.k, 0), flush)
+            h1_, arg_, xcat_, perm_, _ = ops.stack_fwd_conv5(db0.x, g_t, ws_, bs_, w5_, b5_, cfg.k, 0)
+            dh1_ = torch.randn_like(h1_)
+            t_ksb5 = timed(lambda: ops.stack_bwd_conv5(dh1_, arg_, perm_, xcat_, db0.x, g_t, ws_, w5_, cfg.k, 0), flush)
+        bsz, kk = cfg.batch_size, cfg.k
+        a_ks5 = (forward_bytes(n, e, bsz, cfg.num_features, kk) - 4 * bsz * kk * 97       # no pooled
+                 + bsz * 16 * (kk // 2) * 5 + 4 * 16 * 98)                                # + h1, arg, W5, b5
+        n2 = {"what": "SURVEY 8f N2: conv5 + ReLU + MaxPool1d(2,2) inside KS, their backward inside KSB; "
+                      "SortPooling's [B, k*97] output and its gradient are never materialised",
+              "stack_fwd_conv5_us": t_ks5 * 1e6, "algorithmic_bytes": a_ks5,
+              "achieved_GBps": a_ks5 / t_ks5 / 1e9, "frac_of_peak": a_ks5 / t_ks5 / 1e9 / peak,
+              "stack_bwd_conv5_us": t_ksb5 * 1e6}
     a_fwd = forward_bytes(n, e, cfg.batch_size, cfg.num_features, cfg.k)
     a_l2 = layer_bytes(n, e, 32, 32)
     # stricter figure when the layers are fused (x_1..x_3 never re-read from HBM)
@@ -624,10 +666,14 @@ def main():
         roofline = {"bound": "hbm",
                     "kernel": "stack_fwd_kernel (GraphConv x4 + SortPool forward, one launch)",
                     "achieved": a_fwd / t_fwd / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": a_fwd / t_fwd / 1e9 / peak, "traffic": KS_NCU_DRAM_BYTES, "peak_source": peak_kind,
+                    "frac": a_fwd / t_fwd / 1e9 / peak, "traffic": ks_traffic_from_profile(), "peak_source": peak_kind,
+                    # K0b (bitmaps / fragment maps, once per batch) does the adjacency read that A_fwd
+                    # charges to every layer: the same fraction with its time added to the launch
+                    "frac_with_k0b": a_fwd / (t_fwd + max(t_k0 - t_k0_only, 0.0)) / 1e9 / peak,
+                    "k0b_us": max(t_k0 - t_k0_only, 0.0) * 1e6,
                     "algorithmic_bytes": a_fwd, "launch_us": t_fwd * 1e6,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                                      "capture of this kernel on this workload (profiles/r01_stack_fwd_mma_v3.md): "
+                                      "capture of this kernel on this workload, parsed from profiles/r02_stack_fwd_mma.md: "
                                       "adjacency arrives as K0b bitmaps and the 41 MB of outputs stay in the "
                                       "126 MB L2, so DRAM traffic is far BELOW the algorithmic bytes",
                     "note": "effective figure on A_fwd = sum of per-layer algorithmic bytes + SortPool "
@@ -646,7 +692,7 @@ def main():
                                "algorithmic_bytes": 24 * e, "us": t_k0 * 1e6,
                                "achieved_GBps": 24 * e / t_k0 / 1e9,
                                "frac_of_peak": 24 * e / t_k0 / 1e9 / peak},
-               "per_layer_kernel": per_layer}
+               "per_layer_kernel": per_layer, "conv5_fused_variant": n2}
 
     # ---- resident data set: the ring's graphs live in HBM, a step's input is
     # its list of graph ids; dgcnn_collate replaces the host collate, the H2D copy and K0 ----

@@ -251,12 +251,14 @@ __global__ void __launch_bounds__(kConvThreads) gc_aggregate_vec32(AggParams p) 
         int steps = (end - beg + 7) >> 3;
         steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 8));
         steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 16));
+        int jn = beg + q < end ? p.col[beg + q] : 0;             // columns of step 0
         for (int it = 0; it < steps; ++it) {
             const int e = beg + it * 8 + q;
-            int j = 0;
+            const int j = jn;
+            const int en = e + 8;
+            jn = en < end ? p.col[en] : 0;                        // next step's columns are in flight
             float cj = 0.0f;
             if (e < end) {
-                j = p.col[e];
                 const float dj = p.dis[j];
                 cj = p.swap_coef ? row_coef(dj, p.norm) : col_coef(dj, p.norm);
             }
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kConvThreads) gc_aggregate_vec32(AggParams p) 
 // the gather from there: HBM / L2 traffic drops to one read + one write of the rows and the CSR
 // columns, the gather runs at shared-memory bandwidth.  Persistent CTAs walk the graphs largest
 // first (gorder); a graph that does not fit is left to gc_aggregate_vec32 in `big_only` mode.
-constexpr int kStagedThreads = 512;
+constexpr int kStagedThreads = 1024;      // 32 warps: the gather is a chain of dependent loads per warp
 constexpr int kStagedMaxRows = 1728;     // 216 KB of rows + 4.2 KB of weights
 
 struct StagedParams {
@@ -380,9 +382,11 @@ __global__ void __launch_bounds__(kStagedThreads) gc_aggregate_staged(StagedPara
             int steps = (end - beg + 7) >> 3;
             steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 8));
             steps = max(steps, __shfl_xor_sync(DGCNN_FULL_MASK, steps, 16));
+            int jn = beg + q < end ? p.col[beg + q] - base : 0;       // columns of step 0
             for (int it = 0; it < steps; ++it) {
-                const int e = beg + it * 8 + q;
-                const int j = e < end ? p.col[e] - base : 0;
+                const int j = jn;
+                const int en = beg + (it + 1) * 8 + q;                // next step's columns: in flight
+                jn = en < end ? p.col[en] - base : 0;                 // while this step's rows are added
                 const int left = end - beg - it * 8;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -464,7 +468,9 @@ static int launch_aggregate(const AggParams& p, cudaStream_t st) {
 // not 32 aligned channels.
 static int launch_aggregate_graphs(const AggParams& p0, const int32_t* gptr, const int32_t* gorder,
                                    int64_t num_graphs, int64_t max_nodes, cudaStream_t st) {
-    if (!gptr || num_graphs < 1 || !vec32_ok(p0)) return launch_aggregate(p0, st);
+    // one CTA per graph: worth it only with enough graphs to fill the device (D&D's 64 graphs of a
+    // few hundred nodes are better spread row by row)
+    if (!gptr || num_graphs < 96 || !vec32_ok(p0)) return launch_aggregate(p0, st);
     const int cap = (max_nodes > 0 && max_nodes < kStagedMaxRows) ? (int)((max_nodes + 15) / 16 * 16) : kStagedMaxRows;
     StagedParams sp{};
     sp.a = p0; sp.gptr = gptr; sp.gorder = gorder; sp.num_graphs = (int)num_graphs; sp.cap_rows = cap;
@@ -473,7 +479,7 @@ static int launch_aggregate_graphs(const AggParams& p0, const int32_t* gptr, con
         cudaSuccess)
         return DGCNN_ERR_CUDA;
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;                                  // 512 threads each
+    if (per_sm > 2) per_sm = 2;                                  // 1024 threads each
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)DGCNN_NUM_SMS * per_sm;
     if (grid > num_graphs) grid = num_graphs;

@@ -29,10 +29,11 @@ __all__ = ["FusedTrainer"]
 
 class FusedTrainer:
     def __init__(self, model: Model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 group=None):
+                 group=None, distributed: bool = True):
         convs = (model.conv1, model.conv2, model.conv3, model.conv4)
         self.model = model
         self.group = group
+        self.distributed = bool(distributed)       # False: never exchange gradients (single-process reference)
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         # flat order = KSB's gradient layout for the graph convolutions, then the dense tail
         self.stack_params = []
@@ -78,7 +79,7 @@ class FusedTrainer:
         # the ranks (one node) can map each other's memory, else by NCCL (DGCNN_ALLREDUCE=nccl)
         self.exchange = None
         self.comm_status = torch.zeros(1, dtype=torch.int32, device=dev)
-        if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if (self.distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
                 and os.environ.get("DGCNN_ALLREDUCE", "p2p").lower() == "p2p"):
             try:
                 from .dp import PeerExchange
@@ -92,6 +93,8 @@ class FusedTrainer:
                 self.exchange = None
 
     def _world(self) -> int:
+        if not self.distributed:
+            return 1
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def _global_batch(self, local_graphs: int, global_batch: Optional[int], world: int) -> int:

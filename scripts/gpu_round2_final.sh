@@ -1,0 +1,57 @@
+#!/bin/bash
+# Round 2 final single-GPU call: tests, smoke (plain + the driver's ncu command), bench lines of every
+# BASELINE workload, ncu --set full of the dominant kernels, launch lists, sanitizers.
+set -u
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-.}"
+D=gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $D/gpu.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=20 --tb=short -p no:cacheprovider > $D/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> $D/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $D/smoke.log 2>&1
+echo "smoke exit $?" >> $D/smoke.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file $D/smoke_ncu.csv \
+    python -c "import __graft_entry__ as g; g.smoke()" > $D/smoke_ncu.log 2>&1
+echo "smoke under ncu exit $?" >> $D/smoke_ncu.log
+timeout 900 python bench.py --steps 40 --warmup 5 > $D/bench_collab.json 2> $D/bench_collab.err
+for w in dd powerlaw proteins mutag; do
+  timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --cpu-seconds 3 > $D/bench_$w.json 2> $D/bench_$w.err
+done
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $D/bench_reference.json 2> $D/bench_reference.err
+if [ "${PROFILE:-1}" = "1" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:stack_fwd -s 1 -c 2 \
+    -f -o $D/prof_ks_r2 python scripts/profile_hot_path.py collab 3 fwd > $D/prof_ks_r2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:stack_fwd_mma -s 1 -c 1 \
+    -f -o $D/prof_ks_conv5_r2 python scripts/profile_resident_step.py > $D/prof_ks_conv5_r2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:stack_bwd_mma -s 1 -c 1 \
+    -f -o $D/prof_ksb_conv5_r2 python scripts/profile_resident_step.py > $D/prof_ksb_conv5_r2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gc_aggregate_staged -s 1 -c 1 \
+    -f -o $D/prof_k1_staged_r2 python scripts/profile_hot_path.py powerlaw 2 fwd > $D/prof_k1_staged_r2.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $D/resident_launches.csv \
+    python scripts/profile_resident_step.py > $D/profile_resident_step.log 2>&1
+for w in dd powerlaw; do
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $D/launches_fwd_$w.csv \
+    python scripts/profile_hot_path.py $w 2 fwd > $D/profile_fwd_$w.log 2>&1
+done
+fi
+if [ "${SANITIZE:-1}" = "1" ]; then
+  for tool in memcheck racecheck synccheck initcheck; do
+    timeout 900 compute-sanitizer --tool $tool python scripts/sanitize_small.py > $D/sanitize_$tool.log 2>&1
+    echo "$tool exit $?" >> $D/sanitize_$tool.log
+  done
+fi
+tail -6 $D/pytest_gpu.log; tail -2 $D/smoke.log; tail -2 $D/smoke_ncu.log
+python - <<'PY'
+import json
+for w in ("collab","dd","powerlaw","proteins","mutag"):
+    try:
+        d=json.loads(open(f"gpurun_out/bench_{w}.json").read().strip().splitlines()[-1])
+    except Exception as e:
+        print(w, "no bench line", e); continue
+    h=d["hot_path_fwd"]; r=d["roofline"]; res=d.get("e2e_resident_dataset") or {}
+    print(w, "ms/step", round(d["ms_per_step"],3), "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "fwd us", round(h["us"],1), "frac", round(h["frac_of_peak"],3),
+          "per-layer us", round(h["per_layer_kernel"]["launch_us"],1), round(h["per_layer_kernel"]["frac_of_peak"],3), "k0", round(h["graph_build_us"],1),
+          "resident", res.get("device_step_us"), res.get("value"), res.get("driver_epoch_value"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
+    if h.get("conv5_fused_variant"): print("   n2:", h["conv5_fused_variant"])
+PY
+for tool in memcheck racecheck synccheck initcheck; do echo "== $tool"; grep -E "SUMMARY|exit" $D/sanitize_$tool.log | tail -3; done

@@ -29,8 +29,8 @@
 namespace dgcnn {
 
 constexpr int kArMaxWorld = 16;
-constexpr int kArCtas = 64;                // all co-resident (the kernel is its own barrier); 16-byte pushes
-constexpr int kArThreads = 256;
+constexpr int kArCtas = DGCNN_NUM_SMS;     // one CTA per SM, all co-resident (the kernel is its own barrier)
+constexpr int kArThreads = 512;            // ~1 MB per rank: about one 16-byte element per thread
 constexpr int kArHeaderBytes = 256;
 
 struct AllreduceAdamParams {
@@ -112,22 +112,44 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
     if (timed_out) return;
     if (tracer) tr[2] = ar_global_ns();                   // every rank has arrived (wait = [2] - [1])
 
-    // 3. sum the local slots in rank order, Adam on the parameters
+    // 3. sum the local slots in rank order, Adam on the parameters (16 bytes per thread and step
+    //    where the layout allows: slots are 128-byte aligned, the state arrays are torch allocations)
     const int64_t t = *a.step + 1;
     const float bc1 = 1.f - powf(a.beta1, (float)t), bc2 = 1.f - powf(a.beta2, (float)t);
     const float step_size = a.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
     const float* mine = reinterpret_cast<const float*>(a.exch[a.rank] + kArHeaderBytes) + region;
-    for (int64_t i = tid; i < a.n_total; i += stride) {
+    auto adam1 = [&](float s, float& pi, float& mi, float& vi) {
+        const float gi = s * a.grad_scale;
+        mi = a.beta1 * mi + (1.f - a.beta1) * gi;
+        vi = a.beta2 * vi + (1.f - a.beta2) * gi * gi;
+        pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + a.eps);
+    };
+    const bool vec3 = vec && (((reinterpret_cast<uintptr_t>(a.p) | reinterpret_cast<uintptr_t>(a.m) |
+                                reinterpret_cast<uintptr_t>(a.v)) & 15) == 0);
+    const int64_t p4 = vec3 ? a.n_params / 4 : 0;              // float4 groups that are all parameters
+    for (int64_t i = tid; i < p4; i += stride) {
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < a.world; ++r) {
+            const float4 x4 = __ldcv(reinterpret_cast<const float4*>(mine + (int64_t)r * slot) + i);
+            s4.x += x4.x; s4.y += x4.y; s4.z += x4.z; s4.w += x4.w;
+        }
+        reinterpret_cast<float4*>(a.g)[i] = s4;
+        float4 pv = reinterpret_cast<float4*>(a.p)[i], mv = reinterpret_cast<float4*>(a.m)[i],
+               vv = reinterpret_cast<float4*>(a.v)[i];
+        adam1(s4.x, pv.x, mv.x, vv.x); adam1(s4.y, pv.y, mv.y, vv.y);
+        adam1(s4.z, pv.z, mv.z, vv.z); adam1(s4.w, pv.w, mv.w, vv.w);
+        reinterpret_cast<float4*>(a.p)[i] = pv;
+        reinterpret_cast<float4*>(a.m)[i] = mv;
+        reinterpret_cast<float4*>(a.v)[i] = vv;
+    }
+    for (int64_t i = 4 * p4 + tid; i < a.n_total; i += stride) {
         float s = 0.f;
         for (int r = 0; r < a.world; ++r) s += __ldcv(mine + (int64_t)r * slot + i);
         a.g[i] = s;
         if (i < a.n_params) {
-            const float gi = s * a.grad_scale;
-            const float mi = a.beta1 * a.m[i] + (1.f - a.beta1) * gi;
-            const float vi = a.beta2 * a.v[i] + (1.f - a.beta2) * gi * gi;
-            a.m[i] = mi;
-            a.v[i] = vi;
-            a.p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + a.eps);
+            float pi = a.p[i], mi = a.m[i], vi = a.v[i];
+            adam1(s, pi, mi, vi);
+            a.p[i] = pi; a.m[i] = mi; a.v[i] = vi;
         }
     }
     if (tracer) tr[3] = ar_global_ns();                   // CTA 0 done with its share of sum + Adam

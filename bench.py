@@ -77,10 +77,12 @@ def parse_args():
     ap.add_argument("--autograd", action="store_true",
                     help="step through torch autograd (Model + GradBucket + FlatAdam) instead of FusedTrainer")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--shards", default="balanced", choices=["balanced", "independent"],
+    ap.add_argument("--shards", default="independent", choices=["balanced", "independent"],
                     help="N > 1: how the global batch of bs*N graphs is split (balanced: dp.balanced_shards, "
                          "every rank gets the same count and the same size profile; independent: every rank "
-                         "draws its own bs graphs)")
+                         "draws its own bs graphs -- the default: measured faster at N = 8, 0.451 against 0.472 ms, "
+                         "because the rank that is dealt the LARGEST graph of the 4096 loses the conv5 fusion and "
+                         "sets the pace; profiles/r02_scaling.md)")
     ap.add_argument("--trace-exchange", default="",
                     help="N > 1: write the gradient-exchange kernel's per-step timeline of every rank to this JSON")
     return ap.parse_args()
@@ -457,9 +459,12 @@ def main():
         if rank == 0:
             steps_done = int(trainer.exchange.epoch.item())
             rows = []
-            for e in range(max(0, steps_done - args.steps), steps_done):
+            for e in range(max(1, steps_done - args.steps), steps_done):
                 per_rank = [t_all[r][e % 1024].tolist() for r in range(world)]
+                prev = [t_all[r][(e - 1) % 1024].tolist() for r in range(world)]
                 rows.append({"step": e,
+                             # the rank's own work between two exchanges: L2 flush + graph launch + K0 .. KSB
+                             "compute_us": [round((p_[0] - q_[3]) / 1e3, 2) for p_, q_ in zip(per_rank, prev)],
                              "wait_us": [round((p_[2] - p_[1]) / 1e3, 2) for p_ in per_rank],
                              "push_us": [round((p_[1] - p_[0]) / 1e3, 2) for p_ in per_rank],
                              "sum_adam_us": [round((p_[3] - p_[2]) / 1e3, 2) for p_ in per_rank],
@@ -467,6 +472,9 @@ def main():
             import statistics as _st
             summary = {"world": world, "steps": len(rows),
                        "mean_wait_us_per_rank": [round(_st.mean(r_["wait_us"][k] for r_ in rows), 2) for k in range(world)],
+                       "mean_compute_us_per_rank": [round(_st.median(r_["compute_us"][k] for r_ in rows), 2) for k in range(world)],
+                       "mean_of_max_compute_us": round(_st.mean(max(r_["compute_us"]) for r_ in rows), 2),
+                       "mean_of_mean_compute_us": round(_st.mean(_st.mean(r_["compute_us"]) for r_ in rows), 2),
                        "mean_push_us": round(_st.mean(_st.mean(r_["push_us"]) for r_ in rows), 2),
                        "mean_sum_adam_us": round(_st.mean(_st.mean(r_["sum_adam_us"]) for r_ in rows), 2),
                        "mean_enter_skew_us": round(_st.mean(r_["enter_skew_us"] for r_ in rows), 2),

@@ -164,6 +164,12 @@ SIGNATURES = {
                        [c_void_p, c_size_t, c_void_p]),
     "dgcnn_tail_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32] + [c_void_p] * 4 + [c_int32] +
                        [c_void_p] * 6 + [c_void_p] * 9 + [c_int32, c_void_p, c_size_t, c_void_p]),
+    "dgcnn_tail_fwd_loss": (c_int32, [c_void_p, c_int64, c_int32] + [c_void_p] * 8 +
+                            [c_int32, c_void_p, c_int32, c_uint64, c_void_p] + [c_void_p] * 6 +
+                            [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "dgcnn_tail_bwd_after_loss": (c_int32, [c_void_p, c_int64, c_int32] + [c_void_p] * 4 + [c_int32] +
+                                  [c_void_p] * 6 + [c_void_p] * 10 + [c_void_p, c_void_p, c_int32,
+                                                                      c_void_p, c_size_t, c_void_p]),
     "dgcnn_tail_bwd_join": (c_int32, [c_void_p]),
     "dgcnn_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_float, c_float, c_float, c_float, c_float, c_void_p]),

@@ -385,6 +385,88 @@ tail_fc2_lsm_fwd(const float* __restrict__ h3, int64_t B, int C, const float* __
     if (rng_offset && blockIdx.x == 0 && threadIdx.x == 0) *rng_offset += 1;
 }
 
+
+// ---- fc1 epilogue + fc2 + log_softmax + NLL + d(logits) + fc2's row backward in ONE launch ---------
+// Everything between the fc1 GEMM of the forward and the fc1 GEMMs of the backward is row-local on
+// [B,128] / [B,C]: four launches of 4-8 us each (tail_fc1_epilogue, tail_fc2_lsm_fwd, nll_sum_kernel,
+// tail_fc2_bwd_rows) for work that fits one warp per graph.  The arithmetic of every value is the
+// same as in those kernels (bit-identical h3, keep, logp, dlogit, dz3); the per-graph loss / hit
+// scalars are summed in a fixed order by one extra block of tail_fc2_bwd_params (the next kernel of
+// the parameter-gradient chain), which also bumps the dropout offset.  grad of the SUM of the NLL.
+__global__ void __launch_bounds__(256)
+tail_head_kernel(const float* __restrict__ slabs, int splits, int64_t B, int C, const float* __restrict__ bf1,
+                 const float* __restrict__ w2, const float* __restrict__ b2, const int64_t* __restrict__ y,
+                 int training, uint64_t seed, int64_t* rng_offset, float* __restrict__ h3,
+                 uint8_t* __restrict__ keep, float* __restrict__ logp, float* __restrict__ dlogit,
+                 float* __restrict__ dz3, float* __restrict__ per_graph /* [B][2] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t off = (training && rng_offset) ? (uint64_t)*rng_offset : 0ull;
+    const int64_t total = B * kFc;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+        // fc1 epilogue: slabs in order + bias, ReLU, Dropout(0.5)
+        float hv[kFc / 32];
+        uint8_t kp[kFc / 32];
+#pragma unroll
+        for (int q = 0; q < kFc / 32; ++q) {
+            const int64_t i = b * kFc + lane + 32 * q;
+            float sv = bf1[lane + 32 * q];
+            for (int sp = 0; sp < splits; ++sp) sv += slabs[(int64_t)sp * total + i];
+            sv = fmaxf(sv, 0.f);
+            uint8_t k8 = sv > 0.f ? 1 : 0;
+            if (training) {
+                if (mix32(seed, off, (uint32_t)i) & 0x80000000u) { sv *= 2.f; k8 = k8 ? 2 : 0; }
+                else { sv = 0.f; k8 = 0; }
+            }
+            hv[q] = sv; kp[q] = k8;
+            h3[i] = sv; keep[i] = k8;
+        }
+        // fc2 + log_softmax (lane c holds class c)
+        float mylogit = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            float sv = 0.f;
+#pragma unroll
+            for (int q = 0; q < kFc / 32; ++q) sv = fmaf(hv[q], w2[c * kFc + lane + 32 * q], sv);
+            sv = warp_sum(sv) + b2[c];
+            if (lane == c) mylogit = sv;
+        }
+        float mx = mylogit;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(DGCNN_FULL_MASK, mx, o));
+        const float e = lane < C ? expf(mylogit - mx) : 0.f;
+        const float lse = mx + logf(warp_sum(e));
+        const float lp = mylogit - lse;
+        if (lane < C) logp[b * C + lane] = lp;
+        // NLL of this graph, prediction, d(sum of NLL)/d(logp) = -[c == y]
+        const int yb = (int)y[b];
+        float bv = __shfl_sync(DGCNN_FULL_MASK, lp, 0);
+        int best = 0;
+        for (int c = 1; c < C; ++c) {
+            const float v = __shfl_sync(DGCNN_FULL_MASK, lp, c);
+            if (v > bv) { bv = v; best = c; }
+        }
+        const float ly = (yb >= 0 && yb < C) ? __shfl_sync(DGCNN_FULL_MASK, lp, yb & 31) : 0.f;
+        if (lane == 0) {
+            per_graph[2 * b] = (yb >= 0 && yb < C) ? -ly : 0.f;
+            per_graph[2 * b + 1] = best == yb ? 1.f : 0.f;
+        }
+        // log_softmax / fc2 backward rows: dlogit = dlogp - softmax * sum(dlogp); dz3 = (dlogit W2) * keep
+        const float gd = (lane < C && lane == yb) ? -1.f : 0.f;
+        const float sum = warp_sum(gd);
+        const float dl = lane < C ? gd - expf(lp) * sum : 0.f;
+        if (lane < C) dlogit[b * C + lane] = dl;
+        float acc[kFc / 32];
+#pragma unroll
+        for (int q = 0; q < kFc / 32; ++q) acc[q] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float dc = __shfl_sync(DGCNN_FULL_MASK, dl, c);
+#pragma unroll
+            for (int q = 0; q < kFc / 32; ++q) acc[q] = fmaf(dc, w2[c * kFc + lane + 32 * q], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kFc / 32; ++q) dz3[b * kFc + lane + 32 * q] = acc[q] * (float)kp[q];
+    }
+}
+
 // ---- backward -----------------------------------------------------------------------------
 // fc2 / log_softmax backward, part A (one warp per graph):
 //   dlogit = dlogp - softmax * sum(dlogp);   dz3 = (dlogit W2) * keep
@@ -419,9 +501,28 @@ tail_fc2_bwd_rows(const float* __restrict__ dlogp, const float* __restrict__ log
 __global__ void __launch_bounds__(256)
 tail_fc2_bwd_params(const float* __restrict__ dlogit, const float* __restrict__ h3,
                     const float* __restrict__ dz3, int64_t B, int C, float* __restrict__ dw2,
-                    float* __restrict__ db2, float* __restrict__ dbf1) {
+                    float* __restrict__ db2, float* __restrict__ dbf1,
+                    const float* __restrict__ per_graph = nullptr, float* __restrict__ stats = nullptr,
+                    int64_t* rng_offset = nullptr) {
     __shared__ float red[8][33];
     const int ox = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    if (per_graph && blockIdx.x == gridDim.x - 1) {
+        // (launched with one block more than the gradients need) loss sum / #correct of the step from
+        // tail_head_kernel's per-graph scalars, in a fixed order; the dropout stream moves on
+        float l = 0.f, cnt = 0.f;
+        for (int64_t b = threadIdx.x; b < B; b += 256) { l += per_graph[2 * b]; cnt += per_graph[2 * b + 1]; }
+        l = warp_sum(l); cnt = warp_sum(cnt);
+        if (ox == 0) { red[0][gy] = l; red[1][gy] = cnt; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, c2 = 0.f;
+            for (int w = 0; w < 8; ++w) { a += red[0][w]; c2 += red[1][w]; }
+            stats[0] = a;
+            stats[1] = c2;
+            if (rng_offset) *rng_offset += 1;
+        }
+        return;
+    }
     const int o = blockIdx.x * 32 + ox;
     const int total = C * kFc + C + kFc;
     float s = 0.f;
@@ -753,7 +854,8 @@ extern "C" size_t dgcnn_tail_workspace_bytes(int64_t num_graphs, int32_t k, int3
     if (num_graphs < 0 || k < 10 || num_classes < 1) return 0;
     const TailDims d = tail_dims(k);
     size_t fwd = sizeof(float) * (size_t)kFc1Splits * num_graphs * kFc;
-    size_t bwd = sizeof(float) * ((size_t)num_graphs * num_classes            // dlogit
+    size_t bwd = sizeof(float) * ((size_t)64 + 2 * (size_t)num_graphs          // ticket (256 B) + per-graph loss / hit
+                                  + (size_t)num_graphs * num_classes            // dlogit
                                   + (size_t)num_graphs * kFc                   // dz3
                                   + (size_t)num_graphs * d.D1                  // dz2
                                   + (size_t)num_graphs * kC5 * d.L1            // dh1
@@ -815,6 +917,64 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     return DGCNN_OK;
 }
 
+// dgcnn_tail_fwd + dgcnn_nll_sum + the first kernel of the backward in one call for a TRAINING step:
+// conv5 (unless pooled == NULL: h1 / arg are inputs) -> conv6 -> fc1 GEMM -> tail_head_kernel.
+// Leaves logp, h3, keep as dgcnn_tail_fwd does, and dlogit / dz3 / the per-graph loss and hit scalars in
+// `workspace_bwd` where dgcnn_tail_bwd_after_loss picks them up (it also writes stats = [sum of NLL,
+// #correct] and advances the dropout stream).  The gradient is that of the SUM of the NLL.
+extern "C" int dgcnn_tail_fwd_loss(const float* pooled, int64_t num_graphs, int32_t k, const float* w5,
+                                   const float* b5, const float* w6, const float* b6, const float* wf1,
+                                   const float* bf1, const float* wf2, const float* bf2, int32_t num_classes,
+                                   const int64_t* y, int32_t training, uint64_t seed, int64_t* rng_offset,
+                                   float* h1, uint8_t* arg, float* h2, float* h3, uint8_t* keep, float* logp,
+                                   void* workspace_fwd, size_t workspace_fwd_bytes, void* workspace_bwd,
+                                   size_t workspace_bwd_bytes, void* stream) {
+    const int64_t B = num_graphs;
+    if (B < 0 || k < 10 || num_classes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
+    if (num_classes > 32) return DGCNN_ERR_UNSUPPORTED;
+    if (B == 0) return DGCNN_OK;
+    if ((pooled && (!w5 || !b5)) || !w6 || !b6 || !wf1 || !bf1 || !wf2 || !bf2 || !h1 || !arg || !h2 ||
+        !h3 || !keep || !logp || !y)
+        return DGCNN_ERR_INVALID_ARGUMENT;
+    if (training && !rng_offset) return DGCNN_ERR_INVALID_ARGUMENT;
+    const size_t need = dgcnn_tail_workspace_bytes(B, k, num_classes);
+    if (!workspace_fwd || workspace_fwd_bytes < need || !workspace_bwd || workspace_bwd_bytes < need)
+        return DGCNN_ERR_WORKSPACE;
+    const TailDims d = tail_dims(k);
+    if (B * (int64_t)d.D1 >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* slabs = reinterpret_cast<float*>(((uintptr_t)workspace_fwd + 255) & ~(uintptr_t)255);
+    float* wb = reinterpret_cast<float*>(((uintptr_t)workspace_bwd + 255) & ~(uintptr_t)255);
+    float* per_graph = wb + 64;
+    float* dlogit = wb + 64 + 2 * B;
+    float* dz3 = dlogit + B * num_classes;
+    if (pooled) {
+        if (cudaFuncSetAttribute(tail_c5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kC5StageBytes) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+        tail_c5_fwd<<<grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st>>>(pooled, B, k, d.L1, w5, b5, h1,
+                                                                                 arg);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
+    const size_t smem6 = sizeof(float) * (kC5 * kK6 * kC6 + kC6 + kC5 * (d.L1 + 8) + kC6 * d.L2);
+    if (smem6 > 96 * 1024) return DGCNN_ERR_UNSUPPORTED;
+    if (smem6 > 48 * 1024 &&
+        cudaFuncSetAttribute(tail_c6_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess)
+        return DGCNN_ERR_CUDA;
+    tail_c6_fwd<<<grid_for(B, 1, 4), 256, smem6, st>>>(h1, B, d.L1, w6, b6, h2);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    const int kchunk = (int)ceil_div(ceil_div(d.D1, kFc1Splits), 16) * 16;
+    const int splits = (int)ceil_div(d.D1, kchunk);
+    dim3 g1((unsigned)ceil_div(kFc, kGemmBN), (unsigned)ceil_div(B, kGemmBM), (unsigned)splits);
+    gemm_f32<false, false, false><<<g1, 256, 0, st>>>(h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
+                                                      nullptr);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    tail_head_kernel<<<grid_for(B, 8, 2), 256, 0, st>>>(slabs, splits, B, num_classes, bf1, wf2, bf2, y, training,
+                                                        seed, rng_offset, h3, keep, logp, dlogit, dz3, per_graph);
+    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    return DGCNN_OK;
+}
+
 // Side stream of the parameter-gradient chain of dgcnn_tail_bwd (overlap != 0): one per
 // device, created on first use and kept for the life of the process.
 struct SideStream { cudaStream_t stream; cudaEvent_t ev[3]; cudaEvent_t done; bool ready; };
@@ -844,7 +1004,10 @@ static int tail_bwd_impl(const float* dlogp, const float* pooled, int64_t num_gr
                          const float* h3, const uint8_t* keep, const float* logp, float* dpooled,
                          float* dw5, float* db5, float* dw6, float* db6, float* dwf1, float* dbf1,
                          float* dwf2, float* dbf2, int32_t overlap, void* workspace,
-                         size_t workspace_bytes, void* stream, bool to_h1, float* dh1_ext) {
+                         size_t workspace_bytes, void* stream, bool to_h1, float* dh1_ext,
+                         float* stats_after_loss = nullptr, int64_t* rng_offset = nullptr) {
+    // stats_after_loss != NULL: dgcnn_tail_fwd_loss already left dlogit / dz3 / the per-graph scalars in
+    // THIS workspace; fc2's row backward is skipped and the scalars are summed into stats here
     const int64_t B = num_graphs;
     if (B < 0 || k < 10 || num_classes < 1 || overlap < 0 || overlap > 2) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_classes > 32) return DGCNN_ERR_UNSUPPORTED;
@@ -855,6 +1018,7 @@ static int tail_bwd_impl(const float* dlogp, const float* pooled, int64_t num_gr
     const TailDims d = tail_dims(k);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B == 0) {
+        if (stats_after_loss) cudaMemsetAsync(stats_after_loss, 0, 2 * sizeof(float), st);
         if (!to_h1) { cudaMemsetAsync(dw5, 0, sizeof(float) * kC5 * kKW, st);  cudaMemsetAsync(db5, 0, sizeof(float) * kC5, st); }
         cudaMemsetAsync(dw6, 0, sizeof(float) * kC6 * kC5 * kK6, st);  cudaMemsetAsync(db6, 0, sizeof(float) * kC6, st);
         cudaMemsetAsync(dwf1, 0, sizeof(float) * kFc * d.D1, st);  cudaMemsetAsync(dbf1, 0, sizeof(float) * kFc, st);
@@ -862,10 +1026,13 @@ static int tail_bwd_impl(const float* dlogp, const float* pooled, int64_t num_gr
         cudaMemsetAsync(dbf2, 0, sizeof(float) * num_classes, st);
         return DGCNN_OK;
     }
-    if (!dlogp || (!to_h1 && (!pooled || !w5 || !dpooled || !arg)) || !w6 || !wf1 || !wf2 || !h1 || !h2 || !h3 ||
-        !keep || !logp)
+    const bool after_loss = stats_after_loss != nullptr;
+    if ((!dlogp && !after_loss) || (!to_h1 && (!pooled || !w5 || !dpooled || !arg)) || !w6 || !wf1 || !wf2 || !h1 ||
+        !h2 || !h3 || !keep || !logp)
         return DGCNN_ERR_INVALID_ARGUMENT;
     float* ws = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* per_graph = ws + 64;
+    ws += 64 + 2 * B;                           // (per-graph loss / hit scalars of dgcnn_tail_fwd_loss)
     float* dlogit = ws;                         ws += B * num_classes;
     float* dz3 = ws;                            ws += B * kFc;
     float* dz2 = ws;                            ws += B * (int64_t)d.D1;
@@ -887,11 +1054,14 @@ static int tail_bwd_impl(const float* dlogp, const float* pooled, int64_t num_gr
                cudaStreamWaitEvent(sw, side->ev[i], 0) == cudaSuccess;
     };
 
-    tail_fc2_bwd_rows<<<grid_for(B, 8, 4), 256, 0, st>>>(dlogp, logp, keep, B, num_classes, wf2, dlogit, dz3);
-    DGCNN_RETURN_IF_LAUNCH_FAILED();
+    if (!after_loss) {
+        tail_fc2_bwd_rows<<<grid_for(B, 8, 4), 256, 0, st>>>(dlogp, logp, keep, B, num_classes, wf2, dlogit, dz3);
+        DGCNN_RETURN_IF_LAUNCH_FAILED();
+    }
     if (!fork(0)) return DGCNN_ERR_CUDA;
-    tail_fc2_bwd_params<<<(num_classes * kFc + num_classes + kFc + 31) / 32, 256, 0, sw>>>(
-        dlogit, h3, dz3, B, num_classes, dwf2, dbf2, dbf1);
+    tail_fc2_bwd_params<<<(num_classes * kFc + num_classes + kFc + 31) / 32 + (after_loss ? 1 : 0), 256, 0, sw>>>(
+        dlogit, h3, dz3, B, num_classes, dwf2, dbf2, dbf1, after_loss ? per_graph : nullptr, stats_after_loss,
+        rng_offset);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dz2 = (dz3 Wf1) * (h2 > 0):  [B,128] x [128,D1]
     dim3 ga((unsigned)ceil_div(d.D1, kGemmBN), (unsigned)ceil_div(B, kGemmBM), 1);
@@ -971,6 +1141,24 @@ extern "C" int dgcnn_tail_bwd_h1(const float* dlogp, int64_t num_graphs, int32_t
     return tail_bwd_impl(dlogp, nullptr, num_graphs, k, nullptr, w6, wf1, wf2, num_classes, h1, nullptr, h2, h3,
                          keep, logp, nullptr, nullptr, nullptr, dw6, db6, dwf1, dbf1, dwf2, dbf2, overlap,
                          workspace, workspace_bytes, stream, true, dh1);
+}
+
+// The backward after dgcnn_tail_fwd_loss: `workspace` is the workspace_bwd of that call (dlogit, dz3 and
+// the per-graph scalars are in it), `stats` receives [sum of NLL, #correct], `rng_offset` advances.
+// dh1 != NULL: stop at d(h1) (conv5's backward runs in dgcnn_stack_bwd_conv5; pooled, arg,
+// w5, dpooled, dw5, db5 unused); dh1 == NULL: the whole tail down to dpooled.
+extern "C" int dgcnn_tail_bwd_after_loss(const float* pooled, int64_t num_graphs, int32_t k, const float* w5,
+                                         const float* w6, const float* wf1, const float* wf2,
+                                         int32_t num_classes, const float* h1, const uint8_t* arg,
+                                         const float* h2, const float* h3, const uint8_t* keep,
+                                         const float* logp, float* dpooled, float* dh1, float* dw5, float* db5,
+                                         float* dw6, float* db6, float* dwf1, float* dbf1, float* dwf2,
+                                         float* dbf2, float* stats, int64_t* rng_offset, int32_t overlap,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+    if (!stats) return DGCNN_ERR_INVALID_ARGUMENT;
+    return tail_bwd_impl(nullptr, pooled, num_graphs, k, w5, w6, wf1, wf2, num_classes, h1, arg, h2, h3, keep, logp,
+                         dpooled, dw5, db5, dw6, db6, dwf1, dbf1, dwf2, dbf2, overlap, workspace, workspace_bytes,
+                         stream, dh1 != nullptr, dh1, stats, rng_offset);
 }
 
 extern "C" int dgcnn_tail_bwd_join(void* stream) {

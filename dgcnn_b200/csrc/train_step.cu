@@ -223,12 +223,14 @@ int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, in
                                         s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, t.max_nodes, p[0], p[1], p[2],
                                         p[3], p[4], p[5], p[6], p[7], p[8], p[9], s.xcat, kXcatLd, nullptr, s.perm,
                                         k, s.h1, s.arg, t.norm, t.graph_status, s.ws_fwd, s.n_fwd, stream));
-        DGCNN_TRY(dgcnn_tail_fwd(nullptr, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, t.training,
-                                 t.seed, t.rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp, s.ws_tail_f,
-                                 s.n_tail, stream));
-        DGCNN_TRY(dgcnn_nll_sum(s.logp, y, B, C, 1.0f, stats, s.dlogp, stream));
-        DGCNN_TRY(dgcnn_tail_bwd_h1(s.dlogp, B, k, p[10], p[12], p[14], C, s.h1, s.h2, s.h3, s.keep, s.logp, s.dh1,
-                                    g[10], g[11], g[12], g[13], g[14], g[15], 2, s.ws_tail_b, s.n_tail, stream));
+        // conv6 -> fc1 -> [fc1 epilogue + fc2 + log_softmax + NLL + d(logits) + fc2 rows: one kernel]
+        DGCNN_TRY(dgcnn_tail_fwd_loss(nullptr, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, y,
+                                      t.training, t.seed, t.rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp,
+                                      s.ws_tail_f, s.n_tail, s.ws_tail_b, s.n_tail, stream));
+        DGCNN_TRY(dgcnn_tail_bwd_after_loss(nullptr, B, k, nullptr, p[10], p[12], p[14], C, s.h1, nullptr, s.h2,
+                                            s.h3, s.keep, s.logp, nullptr, s.dh1, nullptr, nullptr, g[10], g[11],
+                                            g[12], g[13], g[14], g[15], stats, t.training ? t.rng_offset : nullptr,
+                                            2, s.ws_tail_b, s.n_tail, stream));
         DGCNN_TRY(dgcnn_stack_bwd_conv5(s.dh1, s.arg, s.perm, k, s.xcat, kXcatLd, x, ldx, F, s.rowptr_t, s.col_t,
                                         s.dis, s.gptr, s.gorder, s.gdesc, s.fragmap, s.bitmap, s.bmoff, s.gflags,
                                         s.bitmap_t, s.bmoff, s.gflags_t, N, B, t.max_nodes, p[2], p[4], p[6], p[8],
@@ -238,14 +240,14 @@ int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, in
                               s.gflags, s.fragmap, s.fgoff, s.gdesc, N, B, t.max_nodes, p[0], p[1], p[2], p[3],
                               p[4], p[5], p[6], p[7], s.xcat, kXcatLd, s.pooled, s.perm, k, t.norm,
                               DGCNN_STACK_MMA, t.graph_status, s.ws_fwd, s.n_fwd, stream));
-    DGCNN_TRY(dgcnn_tail_fwd(s.pooled, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, t.training,
-                             t.seed, t.rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp, s.ws_tail_f,
-                             s.n_tail, stream));
-    DGCNN_TRY(dgcnn_nll_sum(s.logp, y, B, C, 1.0f, stats, s.dlogp, stream));
+    DGCNN_TRY(dgcnn_tail_fwd_loss(s.pooled, B, k, p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15], C, y,
+                                  t.training, t.seed, t.rng_offset, s.h1, s.arg, s.h2, s.h3, s.keep, s.logp,
+                                  s.ws_tail_f, s.n_tail, s.ws_tail_b, s.n_tail, stream));
     // the tail's parameter gradients run on the library's side stream underneath KSB
-    DGCNN_TRY(dgcnn_tail_bwd(s.dlogp, s.pooled, B, k, p[8], p[10], p[12], p[14], C, s.h1, s.arg, s.h2, s.h3,
-                             s.keep, s.logp, s.dpooled, g[8], g[9], g[10], g[11], g[12], g[13], g[14], g[15],
-                             2, s.ws_tail_b, s.n_tail, stream));
+    DGCNN_TRY(dgcnn_tail_bwd_after_loss(s.pooled, B, k, p[8], p[10], p[12], p[14], C, s.h1, s.arg, s.h2, s.h3,
+                                        s.keep, s.logp, s.dpooled, nullptr, g[8], g[9], g[10], g[11], g[12], g[13],
+                                        g[14], g[15], stats, t.training ? t.rng_offset : nullptr, 2, s.ws_tail_b,
+                                        s.n_tail, stream));
     DGCNN_TRY(dgcnn_stack_bwd(s.dpooled, s.perm, k, s.xcat, kXcatLd, x, ldx, F, s.rowptr_t, s.col_t, s.dis,
                               s.gptr, s.gorder, s.gdesc, s.fragmap, s.bitmap, s.bmoff, s.gflags, s.bitmap_t,
                               s.bmoff, s.gflags_t, N, B, t.max_nodes, p[2], p[4], p[6], t.norm,

@@ -620,6 +620,82 @@ def tail_bwd_h1(dlogp: Tensor, logp: Tensor, saved, k: int, params, out_grads=No
     return dh1, grads
 
 
+def tail_fwd_loss(pooled: Optional[Tensor], k: int, params, y: Tensor, training: bool, seed: int,
+                  rng_offset: Optional[Tensor], h1: Optional[Tensor] = None, arg: Optional[Tensor] = None):
+    """The training step's tail forward (model.py:36-43 + NLL, train.py:39) with fc1's epilogue, fc2,
+    log_softmax, the NLL, d(logits) and fc2's row backward as ONE kernel.  Returns (logp, saved, ctx);
+    ``tail_bwd_after_loss(ctx, ...)`` finishes the backward and fills the loss / accuracy scalars."""
+    lib = _lib.load_library()
+    w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
+    _require_cuda(y, "y", torch.int64)
+    k = int(k)
+    l1, c = k // 2, wf2.size(0)
+    d1 = 32 * (l1 - 4)
+    if pooled is not None:
+        _require_cuda(pooled, "pooled", torch.float32)
+        pooled = pooled.contiguous()
+        b = pooled.size(0)
+    else:
+        if h1 is None or arg is None:
+            raise ValueError("dgcnn_b200: tail_fwd_loss needs either pooled or (h1, arg)")
+        b = h1.size(0)
+    if tuple(wf1.shape) != (128, d1) or y.numel() != b:
+        raise ValueError("dgcnn_b200: tail_fwd_loss shape mismatch")
+    dev = w5.device
+    f32, u8 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.uint8, device=dev)
+    if pooled is not None:
+        h1, arg = _empty(b, 16, l1, **f32), _empty(b, 16, l1, **u8)
+    h2, h3, keep, logp = _empty(b, d1, **f32), _empty(b, 128, **f32), _empty(b, 128, **u8), _empty(b, c, **f32)
+    nbytes = lib.dgcnn_tail_workspace_bytes(b, k, c)
+    ws_f, ws_b = _workspace(nbytes, dev), _workspace(nbytes, dev)
+    if training and rng_offset is None:
+        raise ValueError("dgcnn_b200: training-mode tail needs the device rng_offset counter")
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_tail_fwd_loss(_ptr(pooled), b, k, _ptr(w5), _ptr(b5), _ptr(w6), _ptr(b6), _ptr(wf1), _ptr(bf1),
+                                     _ptr(wf2), _ptr(bf2), c, _ptr(y.contiguous()), int(bool(training)),
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(rng_offset), _ptr(h1), _ptr(arg), _ptr(h2),
+                                     _ptr(h3), _ptr(keep), _ptr(logp), _ptr(ws_f), ws_f.numel(), _ptr(ws_b),
+                                     ws_b.numel(), _stream())
+    _lib.check(rc, "tail_fwd_loss")
+    LAUNCHES["tail_fwd"] += (4 if pooled is not None else 3) if b > 0 else 0
+    return logp, (pooled, h1, arg, h2, h3, keep), (ws_b, rng_offset if training else None)
+
+
+def tail_bwd_after_loss(ctx, logp: Tensor, saved, k: int, params, stats: Tensor, to_h1: bool, out_grads=None,
+                        defer_join: bool = False):
+    """Backward after ``tail_fwd_loss``: returns (dpooled or dh1, gradients[, PendingTailGrads]); eight
+    gradients (conv5 first) when ``to_h1`` is False, six (conv6 ..) when it stops at d(h1)."""
+    lib = _lib.load_library()
+    ws_b, rng_offset = ctx
+    pooled, h1, arg, h2, h3, keep = saved
+    w5, b5, w6, b6, wf1, bf1, wf2, bf2 = [p.contiguous() for p in params]
+    b, c = logp.shape
+    dev = h1.device
+    names = (w6, b6, wf1, bf1, wf2, bf2) if to_h1 else (w5, b5, w6, b6, wf1, bf1, wf2, bf2)
+    grads = list(out_grads) if out_grads is not None else [_empty(p.shape, dtype=p.dtype, device=p.device) for p in names]
+    if len(grads) != len(names):
+        raise ValueError("dgcnn_b200: tail_bwd_after_loss out_grads mismatch")
+    dpooled = None if to_h1 else _empty(pooled.shape, dtype=torch.float32, device=dev)
+    dh1 = _empty(h1.shape, dtype=torch.float32, device=dev) if to_h1 else None
+    g5 = [None, None] if to_h1 else grads[:2]
+    rest = grads if to_h1 else grads[2:]
+    with torch.cuda.device(dev):
+        rc = lib.dgcnn_tail_bwd_after_loss(_ptr(pooled) if not to_h1 else None, b, int(k),
+                                           _ptr(w5) if not to_h1 else None, _ptr(w6), _ptr(wf1), _ptr(wf2), c,
+                                           _ptr(h1), _ptr(arg) if not to_h1 else None, _ptr(h2), _ptr(h3), _ptr(keep),
+                                           _ptr(logp), _ptr(dpooled), _ptr(dh1), _ptr(g5[0]), _ptr(g5[1]),
+                                           *[_ptr(g) for g in rest], _ptr(stats), _ptr(rng_offset),
+                                           (2 if defer_join else 1) if TAIL_OVERLAP else 0, _ptr(ws_b), ws_b.numel(),
+                                           _stream())
+    _lib.check(rc, "tail_bwd_after_loss")
+    LAUNCHES["tail_bwd"] += (8 if to_h1 else 11) if b > 0 else 0
+    out = dh1 if to_h1 else dpooled
+    if defer_join:
+        keepalive = (logp, saved, grads, ws_b, out, w5, w6, wf1, wf2, stats) if TAIL_OVERLAP and b > 0 else None
+        return out, grads, PendingTailGrads(dev, keepalive)
+    return out, grads
+
+
 def stack_bwd_conv5_supported(num_features: int, max_nodes: int) -> bool:
     if max_nodes <= 0 or max_nodes > BITMAP_MAX_NODES or STACK_VARIANT != STACK_MMA:
         return False

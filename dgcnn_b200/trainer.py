@@ -137,8 +137,10 @@ class FusedTrainer:
         [sum of NLL over the (global) batch, number of correct predictions]."""
         m = self.model
         if not self.supported(data):
-            raise RuntimeError("FusedTrainer.step: batch not supported by the fused kernels "
-                               "(every graph must fit the shared memory of one SM; use Model(data) + autograd)")
+            # a graph beyond the fused kernels (more than ~600 nodes): same step on the per-layer
+            # kernels through autograd; the exchange and the optimiser are the same, so ranks may
+            # take different branches for their shards of one global batch
+            return self.step_autograd(data, global_batch)
         world = self._world()
         global_batch = self._global_batch(int(data.num_graphs), global_batch, world)
         if self.native and self._native_step(data, global_batch, world):
@@ -151,22 +153,20 @@ class FusedTrainer:
             # no pooled / dpooled; KSB writes the GraphConv + conv5 gradients
             h1, arg, xcat, perm, _ = ops.stack_fwd_conv5(data.x, graph, weights, biases, self.tail_params[0],
                                                          self.tail_params[1], k, norm)
-            logp, saved = ops.tail_fwd(None, k, self.tail_params, m.training, m._tail_seed,
-                                       m._tail_rng_offset, h1=h1, arg=arg)
-            _, dlogp = ops.nll_sum(logp, data.y, 1.0, True, stats=self.stats)
-            dh1, _, pending = ops.tail_bwd_h1(dlogp, logp, saved, k, self.tail_params,
-                                              out_grads=self.tail_grad_views[2:], defer_join=True)
+            logp, saved, tctx = ops.tail_fwd_loss(None, k, self.tail_params, data.y, m.training, m._tail_seed,
+                                                  m._tail_rng_offset, h1=h1, arg=arg)
+            dh1, _, pending = ops.tail_bwd_after_loss(tctx, logp, saved, k, self.tail_params, self.stats, True,
+                                                      out_grads=self.tail_grad_views[2:], defer_join=True)
             ops.stack_bwd_conv5(dh1, arg, perm, xcat, data.x, graph, weights, self.tail_params[0], k, norm,
                                 out=self.grad[:self.num_stack + 16 * 97 + 16])
         else:
             pooled, xcat, perm = ops.stack_fwd(data.x, graph, weights, biases, k, norm)
-            logp, saved = ops.tail_fwd(pooled, k, self.tail_params, m.training, m._tail_seed,
-                                       m._tail_rng_offset)
-            _, dlogp = ops.nll_sum(logp, data.y, 1.0, True, stats=self.stats)
+            logp, saved, tctx = ops.tail_fwd_loss(pooled, k, self.tail_params, data.y, m.training, m._tail_seed,
+                                                  m._tail_rng_offset)
             # the tail's parameter gradients run on a side stream underneath KSB; joined before
             # the all-reduce / Adam read them
-            dpooled, _, pending = ops.tail_bwd(dlogp, logp, saved, k, self.tail_params,
-                                               out_grads=self.tail_grad_views, defer_join=True)
+            dpooled, _, pending = ops.tail_bwd_after_loss(tctx, logp, saved, k, self.tail_params, self.stats, False,
+                                                          out_grads=self.tail_grad_views, defer_join=True)
             ops.stack_bwd(dpooled, perm, xcat, data.x, graph, weights, k, norm,
                           out=self.grad[:self.num_stack])
         pending.join()
@@ -262,7 +262,7 @@ class FusedTrainer:
         _lib.check(rc, "train_step_resident")
         # n1_gather + KS + 5 tail fwd + NLL + 12 tail bwd + 2 KSB + 2 Adam; with conv5 fused into KS / KSB
         #  the tail loses its conv5 forward kernel and three backward ones
-        launches = (19 if ops.conv5_fusable(f, mx) else 23) + (0 if b <= 1024 else 1)
+        launches = (16 if ops.conv5_fusable(f, mx) else 20) + (0 if b <= 1024 else 1)
         ops.LAUNCHES["train_step_resident"] = ops.LAUNCHES.get("train_step_resident", 0) + launches
         return self.stats
 
@@ -306,5 +306,5 @@ class FusedTrainer:
         if rc == -2:                                       # DGCNN_ERR_UNSUPPORTED: graphs too large for KS / KSB
             return False
         _lib.check(rc, "train_step")
-        ops.LAUNCHES["train_step"] = ops.LAUNCHES.get("train_step", 0) + (25 if ops.conv5_fusable(f, mx) else 29)
+        ops.LAUNCHES["train_step"] = ops.LAUNCHES.get("train_step", 0) + (22 if ops.conv5_fusable(f, mx) else 26)
         return True

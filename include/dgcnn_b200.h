@@ -384,6 +384,29 @@ int dgcnn_tail_bwd_h1(const float* dlogp, int64_t num_graphs, int32_t k, const f
                       const float* logp, float* dh1, float* dw6, float* db6, float* dwf1,
                       float* dbf1, float* dwf2, float* dbf2, int32_t overlap,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* The training step's variant of the tail: dgcnn_tail_fwd + dgcnn_nll_sum + the first kernel of
+ * the backward in ONE call (model.py:36-43 + train.py:39).  fc1's epilogue, fc2, log_softmax, the
+ * NLL of the labels `y`, d(sum of NLL)/d(logits) and fc2's row backward are row-local and run as
+ * one kernel (one warp per graph) instead of four launches.  Outputs as dgcnn_tail_fwd; dlogit,
+ * dz3 and the per-graph loss / hit scalars are left in `workspace_bwd`, which must then be handed
+ * to dgcnn_tail_bwd_after_loss: that call skips fc2's row backward, sums the scalars in a fixed
+ * order into stats = [sum of NLL, #correct] and advances *rng_offset (pass NULL when not training).
+ * dh1 != NULL stops at d(h1) (pooled, arg, w5, dpooled, dw5, db5 may be NULL). */
+int dgcnn_tail_fwd_loss(const float* pooled, int64_t num_graphs, int32_t k,
+                        const float* w5, const float* b5, const float* w6, const float* b6,
+                        const float* wf1, const float* bf1, const float* wf2, const float* bf2,
+                        int32_t num_classes, const int64_t* y, int32_t training, uint64_t seed,
+                        int64_t* rng_offset, float* h1, uint8_t* arg, float* h2, float* h3,
+                        uint8_t* keep, float* logp, void* workspace_fwd, size_t workspace_fwd_bytes,
+                        void* workspace_bwd, size_t workspace_bwd_bytes, void* stream);
+int dgcnn_tail_bwd_after_loss(const float* pooled, int64_t num_graphs, int32_t k, const float* w5,
+                              const float* w6, const float* wf1, const float* wf2,
+                              int32_t num_classes, const float* h1, const uint8_t* arg,
+                              const float* h2, const float* h3, const uint8_t* keep,
+                              const float* logp, float* dpooled, float* dh1, float* dw5, float* db5,
+                              float* dw6, float* db6, float* dwf1, float* dbf1, float* dwf2,
+                              float* dbf2, float* stats, int64_t* rng_offset, int32_t overlap,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* `overlap`: 0 = everything on `stream`.  1 = the parameter-gradient chain (dW/db of fc2, fc1,
  * conv6, conv5) runs on a side stream owned by the library, concurrently with the
  * input-gradient chain that produces dpooled, and is joined into `stream` before the call

@@ -33,7 +33,7 @@ PY
 done
 for f in $D/exchange_trace_*_n$N.json; do python - <<PY
 import json
-d=json.load(open("$f")); print("$f", "wait/rank", d["mean_wait_us_per_rank"], "push", d["mean_push_us"], "sum+adam", d["mean_sum_adam_us"], "skew", d["mean_enter_skew_us"])
+d=json.load(open("$f")); print("$f", "compute/rank", d.get("mean_compute_us_per_rank"), "max", d.get("mean_of_max_compute_us"), "mean", d.get("mean_of_mean_compute_us"), "wait/rank", d["mean_wait_us_per_rank"], "push", d["mean_push_us"], "sum+adam", d["mean_sum_adam_us"], "skew", d["mean_enter_skew_us"])
 PY
 done
 tail -3 $D/bench_collab_n$N.err

@@ -479,7 +479,7 @@ def test_training_with_and_without_the_conv5_fusion_agree():
     finally:
         ops.set_fuse_conv5(True)
     (la, pa, na), (lb, pb, nb) = results[True], results[False]
-    assert na == 3 * 25 and nb == 3 * 29
+    assert na == 3 * 22 and nb == 3 * 26
     for x_, y_ in zip(la, lb):
         assert abs(x_ - y_) <= 1e-4 * max(1.0, abs(y_))
     assert (pa - pb).abs().max().item() <= 2e-5
@@ -507,3 +507,35 @@ def test_model_autograd_uses_the_conv5_fusion_and_matches_the_unfused_model():
     for (n_, _), a, b_ in zip(model.named_parameters(), grads[True][1], grads[False][1]):
         scale = max(1e-3, float(b_.abs().max()))
         assert (a - b_).abs().max().item() <= 2e-3 * scale, n_
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("b,k,c", [(512, 130, 3), (37, 30, 2), (5, 61, 2)])
+def test_fused_tail_head_equals_the_separate_kernels(b, k, c, training):
+    """dgcnn_tail_fwd_loss / dgcnn_tail_bwd_after_loss (fc1 epilogue + fc2 + log_softmax + NLL +
+    d(logits) + fc2's row backward in one kernel) against dgcnn_tail_fwd + dgcnn_nll_sum +
+    dgcnn_tail_bwd: logp, the saved tensors, dpooled and all eight gradients bit for bit; the loss
+    sum to fp32 summation order; the dropout stream advances by one."""
+    torch.manual_seed(b + k)
+    model = dg.Model(7, c, k).to(DEV)
+    tail = [model.conv5.weight, model.conv5.bias, model.conv6.weight, model.conv6.bias,
+            model.classifier_1.weight, model.classifier_1.bias, model.classifier_2.weight, model.classifier_2.bias]
+    pooled = torch.randn(b, k * 97, device=DEV)
+    y = torch.randint(0, c, (b,), device=DEV)
+    off_a, off_b = torch.full((1,), 5, dtype=torch.int64, device=DEV), torch.full((1,), 5, dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        logp, saved = ops.tail_fwd(pooled, k, tail, training, 1234, off_a)
+        stats, dlogp = ops.nll_sum(logp, y, 1.0, True)
+        dpooled, grads = ops.tail_bwd(dlogp, logp, saved, k, tail)
+        stats2 = torch.zeros(2, device=DEV)
+        logp2, saved2, ctx = ops.tail_fwd_loss(pooled, k, tail, y, training, 1234, off_b)
+        dpooled2, grads2 = ops.tail_bwd_after_loss(ctx, logp2, saved2, k, tail, stats2, False)
+    torch.cuda.synchronize()
+    assert torch.equal(logp, logp2) and torch.equal(dpooled, dpooled2)
+    for a, b_ in zip(saved[1:], saved2[1:]):
+        assert torch.equal(a, b_)
+    for a, b_ in zip(grads, grads2):
+        assert torch.equal(a, b_)
+    assert abs(float(stats[0]) - float(stats2[0])) <= 1e-5 * max(1.0, abs(float(stats[0])))
+    assert float(stats[1]) == float(stats2[1])
+    assert int(off_a) == int(off_b) == (6 if training else 5)

@@ -20,6 +20,8 @@
 namespace dgcnn {
 
 constexpr int kC5 = 16, kKW = 97, kC6 = 32, kK6 = 5, kFc = 128;
+constexpr int kFc1Splits = 16;     // split-K slabs of the fc1 forward GEMM
+constexpr int kDwSplits = 4;       // batch splits of the fc1 weight-gradient GEMM
 
 // ------------------------------------------------------------------------------------------
 // conv5 + ReLU + MaxPool(2,2).  A pooled row pair (2j, 2j+1) is 194 contiguous floats; a CTA
@@ -393,7 +395,7 @@ tail_fc2_lsm_fwd(const float* __restrict__ h3, int64_t B, int C, const float* __
 // same as in those kernels (bit-identical h3, keep, logp, dlogit, dz3); the per-graph loss / hit
 // scalars are summed in a fixed order by one extra block of tail_fc2_bwd_params (the next kernel of
 // the parameter-gradient chain), which also bumps the dropout offset.  grad of the SUM of the NLL.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 tail_head_kernel(const float* __restrict__ slabs, int splits, int64_t B, int C, const float* __restrict__ bf1,
                  const float* __restrict__ w2, const float* __restrict__ b2, const int64_t* __restrict__ y,
                  int training, uint64_t seed, int64_t* rng_offset, float* __restrict__ h3,
@@ -402,15 +404,25 @@ tail_head_kernel(const float* __restrict__ slabs, int splits, int64_t B, int C, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t off = (training && rng_offset) ? (uint64_t)*rng_offset : 0ull;
     const int64_t total = B * kFc;
-    for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+    for (int64_t b = (int64_t)blockIdx.x * 4 + warp; b < B; b += (int64_t)gridDim.x * 4) {
         // fc1 epilogue: slabs in order + bias, ReLU, Dropout(0.5)
         float hv[kFc / 32];
         uint8_t kp[kFc / 32];
 #pragma unroll
+        // all slab loads of the row are issued before the first add (same sums, in slab order)
+        float part[kFc / 32][kFc1Splits];
+#pragma unroll
+        for (int q = 0; q < kFc / 32; ++q)
+#pragma unroll
+            for (int sp = 0; sp < kFc1Splits; ++sp)
+                part[q][sp] = sp < splits ? slabs[(int64_t)sp * total + b * kFc + lane + 32 * q] : 0.f;
+#pragma unroll
         for (int q = 0; q < kFc / 32; ++q) {
             const int64_t i = b * kFc + lane + 32 * q;
             float sv = bf1[lane + 32 * q];
-            for (int sp = 0; sp < splits; ++sp) sv += slabs[(int64_t)sp * total + i];
+#pragma unroll
+            for (int sp = 0; sp < kFc1Splits; ++sp)
+                if (sp < splits) sv += part[q][sp];
             sv = fmaxf(sv, 0.f);
             uint8_t k8 = sv > 0.f ? 1 : 0;
             if (training) {
@@ -528,7 +540,15 @@ tail_fc2_bwd_params(const float* __restrict__ dlogit, const float* __restrict__ 
     float s = 0.f;
     if (o < C * kFc) {
         const int c = o / kFc, j = o - c * kFc;
-        for (int64_t b = gy; b < B; b += 8) s = fmaf(dlogit[b * C + c], h3[b * kFc + j], s);
+        int64_t b = gy;
+        for (; b + 56 < B; b += 64) {                       // eight loads in flight, added in batch order
+            float dv[8], hv8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { dv[u] = dlogit[(b + 8 * u) * C + c]; hv8[u] = h3[(b + 8 * u) * kFc + j]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s = fmaf(dv[u], hv8[u], s);
+        }
+        for (; b < B; b += 8) s = fmaf(dlogit[b * C + c], h3[b * kFc + j], s);
     } else if (o < C * kFc + C) {
         const int c = o - C * kFc;
         for (int64_t b = gy; b < B; b += 8) s += dlogit[b * C + c];
@@ -843,8 +863,6 @@ __host__ inline TailDims tail_dims(int k) {
     d.D1 = kC6 * d.L2;
     return d;
 }
-constexpr int kFc1Splits = 16;
-constexpr int kDwSplits = 4;
 
 }  // namespace dgcnn
 
@@ -969,7 +987,7 @@ extern "C" int dgcnn_tail_fwd_loss(const float* pooled, int64_t num_graphs, int3
     gemm_f32<false, false, false><<<g1, 256, 0, st>>>(h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
                                                       nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    tail_head_kernel<<<grid_for(B, 8, 2), 256, 0, st>>>(slabs, splits, B, num_classes, bf1, wf2, bf2, y, training,
+    tail_head_kernel<<<grid_for(B, 4, 4), 128, 0, st>>>(slabs, splits, B, num_classes, bf1, wf2, bf2, y, training,
                                                         seed, rng_offset, h3, keep, logp, dlogit, dz3, per_graph);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;

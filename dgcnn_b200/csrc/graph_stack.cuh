@@ -39,6 +39,8 @@ struct StackFwdParams {
     float* h1; uint8_t* arg;               // [B,16,k/2] pooled activations and the winning row (0/1, 2 = dead)
     int pairs;          // tensor-core variant: launched as clusters of two CTAs (largest graphs are split)
     int split_pct;      // split a graph whose cost exceeds this percentage of an SM's fair share
+    int plain_zero;     // 1: pad `pooled` with ordinary stores instead of TMA bulk stores (sanitizer runs:
+                        // compute-sanitizer initcheck does not see memory written by the async proxy)
 };
 
 

@@ -315,8 +315,12 @@ __device__ __forceinline__ void layer_epilogue(const GraphCtx& c, float (&y)[4][
 // stores.  Returns true on the lanes that issued bulk stores (they call bulk_store_wait() before
 // the kernel ends).
 __device__ __forceinline__ bool zero_fill_bulk(float* __restrict__ base, int beg, int end, int tid,
-                                               uint32_t zero_smem) {
+                                               uint32_t zero_smem, int nthreads, bool plain) {
     if (beg >= end) return false;
+    if (plain) {                                         // (debug: ordinary stores, see StackFwdParams)
+        for (int i = beg + tid; i < end; i += nthreads) base[i] = 0.f;
+        return false;
+    }
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(base + beg);
     const int head = min(end - beg, (int)(((16u - (unsigned)(a0 & 15u)) & 15u) >> 2));
     const int body = ((end - beg - head) >> 2) << 4;                  // bytes, multiple of 16
@@ -388,7 +392,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     if (p.pooled) {
         const int z0 = keep * kCat, z1 = p.k * kCat, zm = split ? z0 + (((z1 - z0) >> 1) & ~3) : z1;
         bulk_pending = zero_fill_bulk(pooled_g, rank ? zm : z0, rank ? z1 : zm, tid,
-                                      smem_u32(shraw + SL.zero));
+                                      smem_u32(shraw + SL.zero), nthreads, p.plain_zero != 0);
     }
     for (int r = keep + gtid; r < p.k; r += gthreads) perm_g[r] = -1;
     if (n == 0) {
@@ -994,6 +998,11 @@ static int stack_fwd_impl(const float* x, int64_t ldx, int32_t num_features,
     }
     p.pairs = g_pairs_ok;
     p.split_pct = g_split_pct;
+    {
+        static int plain = -1;
+        if (plain < 0) { const char* env = getenv("DGCNN_KS_PLAIN_ZERO"); plain = (env && env[0] == '1') ? 1 : 0; }
+        p.plain_zero = plain;
+    }
     int64_t grid = DGCNN_NUM_SMS;
     if (p.pairs) {
         // fewer graphs than SMs: up to 8 spare CTAs double up on the largest graphs

@@ -77,12 +77,14 @@ def parse_args():
     ap.add_argument("--autograd", action="store_true",
                     help="step through torch autograd (Model + GradBucket + FlatAdam) instead of FusedTrainer")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--shards", default="independent", choices=["balanced", "independent"],
+    ap.add_argument("--shards", default="independent", choices=["balanced", "independent", "same"],
                     help="N > 1: how the global batch of bs*N graphs is split (balanced: dp.balanced_shards, "
                          "every rank gets the same count and the same size profile; independent: every rank "
                          "draws its own bs graphs -- the default: measured faster at N = 8, 0.451 against 0.472 ms, "
                          "because the rank that is dealt the LARGEST graph of the 4096 loses the conv5 fusion and "
                          "sets the pace; profiles/r02_scaling.md)")
+    ap.add_argument("--seed-rank", type=int, default=-1,
+                    help="diagnostic, N = 1: draw the batches rank R of a multi-GPU run would draw")
     ap.add_argument("--trace-exchange", default="",
                     help="N > 1: write the gradient-exchange kernel's per-step timeline of every rank to this JSON")
     return ap.parse_args()
@@ -331,7 +333,7 @@ def main():
             mine = dg.balanced_shards(costs, world)[rank]
             ring_graphs.append([pool[j] for j in mine])
         else:
-            ring_graphs.append(make_graphs(cfg, cfg.batch_size, seed=324 + 1000 * rank + i))
+            ring_graphs.append(make_graphs(cfg, cfg.batch_size, seed=324 + (0 if args.shards == "same" else 1000 * (args.seed_rank if args.seed_rank >= 0 else rank)) + i))
     host_batches = [collate(gs).pin_memory() for gs in ring_graphs]
     for hb in host_batches:
         hb.max_nodes = int((hb.ptr[1:] - hb.ptr[:-1]).max())
@@ -440,6 +442,16 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
+    ranks_report = None
+    if world > 1:
+        # each rank's own view: its device time per step (the wait for the slowest rank inside the
+        # exchange kernel included), its SM clock under load, the largest graph of each ring batch
+        rank_report = {"rank": rank, "ms_per_step": round(sum(step_ms) / args.steps, 4),
+                "sm_mhz": clocks.summary().get("sm_mhz"), "reasons": clocks.summary().get("reasons"),
+                "largest_graph_per_ring_batch": [hb.max_nodes for hb in host_batches],
+                "launches_per_step": launches_per_step}
+        ranks_report = [None] * world
+        dist.all_gather_object(ranks_report, rank_report)
     value = global_batch * args.steps / (total_ms / 1e3)
 
     # ---- every rank must hold the same parameters after the same updates ------------
@@ -809,9 +821,11 @@ def main():
                               "note": "same loop, host batch collated with int32 edge_index/batch "
                                       "(dgcnn_build_graph_i32): NOT the reference's int64 format; `e2e` is"},
         "e2e_resident_dataset": resident if world == 1 else resident_multi,
+        "per_rank": ranks_report,
         "params_equal_across_ranks": params_equal, "comm_status_per_rank": comm_status_all,
         "shards": ("balanced (dp.balanced_shards of a global batch of bs*N graphs)" if balanced else
-                   "independent draws per rank") if world > 1 else "n/a",
+                   ("every rank the same batches (diagnostic: separates batch variance from system effects)"
+                    if args.shards == "same" else "independent draws per rank")) if world > 1 else "n/a",
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,

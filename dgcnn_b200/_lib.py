@@ -286,11 +286,18 @@ def load_library() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         if _stale():
-            try:
-                build_library()
-            except RuntimeError:
-                if not LIB_PATH.exists():
-                    raise
+            # one builder at a time across PROCESSES too (torchrun starts N ranks at once)
+            import fcntl
+            LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
+            with open(LIB_PATH.with_suffix(".lock"), "w") as lock_fh:
+                fcntl.flock(lock_fh, fcntl.LOCK_EX)
+                try:
+                    build_library()               # (a no-op when another rank just built it)
+                except RuntimeError:
+                    if not LIB_PATH.exists():
+                        raise
+                finally:
+                    fcntl.flock(lock_fh, fcntl.LOCK_UN)
         lib = ctypes.CDLL(str(LIB_PATH))
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(lib, name)      # AttributeError = header/library mismatch: loud

@@ -32,6 +32,7 @@ struct Team {
     int split = 0;           // 1: this graph is shared with the peer CTA of the cluster
     int rank = 0;            // this CTA's rank in the pair
     uint32_t mbar = 0;       // split: shared::cta address of this CTA's exchange mbarrier
+    uint32_t xparity = 0;    // split: the mbarrier's current phase (carried from graph to graph)
     __device__ __forceinline__ void sync_local() const {
         asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
     }
@@ -126,6 +127,28 @@ __device__ __forceinline__ bool adj_fragment(const uint32_t* __restrict__ bm, in
     return __any_sync(DGCNN_FULL_MASK, (a[0] | a[1] | a[2] | a[3]) != 0u);
 }
 
+// host: can `kernel` be launched as clusters of two CTAs with one CTA per SM, every pair
+// co-resident in ONE wave?  (The plan's split graphs need both CTAs of their pair running.)
+template <class Kernel>
+static inline int cluster_pairs_fit(Kernel kernel, int threads, size_t smem) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t probe{};
+    cudaLaunchAttribute pattr[1];
+    pattr[0].id = cudaLaunchAttributeClusterDimension;
+    pattr[0].val.clusterDim.x = 2; pattr[0].val.clusterDim.y = 1; pattr[0].val.clusterDim.z = 1;
+    probe.gridDim = dim3(DGCNN_NUM_SMS & ~1); probe.blockDim = dim3(threads);
+    probe.dynamicSmemBytes = smem; probe.attrs = pattr; probe.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &probe) != cudaSuccess || 2 * nclusters < (DGCNN_NUM_SMS & ~1)) {
+        cudaGetLastError();
+        return 0;
+    }
+    return 1;
+}
+
 // ---- per-CTA plan of the fused per-graph kernels (KS forward, KSB backward) ----------------
 // The batch arrives in descending size (gdesc, written by K0b: {graph, first node, nodes,
 // fgoff}).  Graphs that alone cost more than an SM's fair share of the batch get an SM to
@@ -155,63 +178,94 @@ __device__ __forceinline__ int graph_cost(int n) {
 // One pass of the plan, executed by ONE WARP: fills s_plan[0..count) and *s_count with the
 // next graphs of this CTA that fit the shared-memory budget together.  `next` = items of this
 // CTA consumed so far; `excl` (in/out, lane-uniform) = number of graphs with an SM of their
-// own, computed on the first pass.  need_of(np) = shared-memory bytes of a graph of np rows.
+// own, computed on the first pass.  need_of(np, split) = shared-memory bytes of a graph of np
+// rows (split: its share when the graph is spread over a CTA pair).
+//
+// The SPLIT SET (cluster launches only, `pairs`): the leading `msplit` graphs are each processed
+// by the two CTAs of a cluster -- those whose own layout does not fit one CTA (mandatory), and
+// those that alone would outlast an SM's fair share of the batch (split_pct).  `nsplit` pairs
+// (CTAs 0 .. 2 nsplit - 1) take them round-robin, one graph per pass.
 template <class NeedFn>
 __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B, int nsm, int sm, int next,
                                           int& excl, bool first_pass, int budget, int total_warps,
                                           NeedFn need_of, PlanEntry* s_plan, int* s_count,
-                                          int& nsplit, bool pairs = false, int split_pct = 80) {
+                                          int& nsplit, int& msplit, bool pairs = false, int split_pct = 80) {
     const int lane = threadIdx.x & 31;
     int4 cand = make_int4(0, 0, 0, 0);                      // the eight largest graphs
     if (first_pass) {
         excl = 0;
         nsplit = 0;
+        msplit = 0;
         // every CTA reads the same few KB of descriptors: pull them into L2 / L1 now, so that the
         // dependent lookup below (position known only after the split decision) is not a second
         // DRAM round trip
         for (int i = lane * 8; i < B; i += 256)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gdesc + i));
         if (lane < 8 && lane < B) cand = gdesc[lane];
-        if (B > nsm) {
-            // fair share of one SM ~ (B / S) x mean cost; the median stands in for the mean
-            const int nmed = gdesc[B >> 1].z;
-            const int share = (int)fminf(1.25f * (float)graph_cost(nmed) * (float)B / (float)nsm, 2.0e9f);
-            const bool mine = lane < 8 && lane < B;
-            if (pairs) {                                    // leading run worth two SMs each
-                const int thr = (int)fminf((float)share * (float)split_pct * 0.01f, 2.0e9f);
-                const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, mine && graph_cost(cand.z) > thr);
-                nsplit = min(__ffs(~big) - 1, min(8, nsm / 4));
+        // (both loads issued before the first use: one round trip)
+        // fair share of one SM ~ (B / S) x mean cost; the median stands in for the mean
+        const int nmed = B > nsm ? gdesc[B >> 1].z : 0;
+        const int share = (int)fminf(1.25f * (float)graph_cost(nmed) * (float)B / (float)nsm, 2.0e9f);
+        int forced = 0;                                     // graphs that only fit a CTA pair
+        if (pairs) {
+            const int cap = max(1, min(8, nsm / 4));
+            uint32_t m = __ballot_sync(DGCNN_FULL_MASK,
+                                       lane < 8 && lane < B && need_of(max(16, (cand.z + 15) & ~15), false) > budget);
+            forced = __ffs(~m) - 1;
+            if (forced == 8) {                              // (rare: count on through the sorted list)
+                for (int i0 = 8; i0 < B; i0 += 32) {
+                    const int nz = i0 + lane < B ? gdesc[i0 + lane].z : 0;
+                    m = __ballot_sync(DGCNN_FULL_MASK, nz > 0 && need_of(max(16, (nz + 15) & ~15), false) > budget);
+                    forced += __ffs(~m) - 1;
+                    if (m != 0xffffffffu) break;
+                }
             }
-            const uint32_t big1 = __ballot_sync(DGCNN_FULL_MASK, mine && lane >= nsplit &&
-                                                                    graph_cost(cand.z) > share) >> nsplit;
-            excl = min(__ffs(~big1) - 1, (nsm - 2 * nsplit) / 2);   // then: an SM of their own
-        } else if (pairs) {
-            // fewer graphs than SMs: the spare CTAs double up on the largest graphs (>= 8 row tiles)
-            const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && lane < B && cand.z > 112);
-            nsplit = min(__ffs(~big) - 1, min(8, nsm - B));
-            if (nsplit < 0) nsplit = 0;
+            forced = min(forced, B);
+            int by_cost = 0;
+            if (B > nsm) {                                  // leading run worth two SMs each
+                const int thr = (int)fminf((float)share * (float)split_pct * 0.01f, 2.0e9f);
+                const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && lane < B && graph_cost(cand.z) > thr);
+                by_cost = min(__ffs(~big) - 1, cap);
+            } else {
+                // fewer graphs than SMs: the spare CTAs double up on the largest graphs (>= 8 row tiles)
+                const uint32_t big = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && lane < B && cand.z > 112);
+                by_cost = max(0, min(__ffs(~big) - 1, min(cap, nsm - B)));
+            }
+            msplit = max(by_cost, forced);
+            nsplit = min(msplit, max(by_cost, cap));
+            if (2 * nsplit >= nsm) {                       // (toy grids) no CTA left for the rest: the
+                nsplit = max(1, nsm / 2);                   // pairs take every graph, pass by pass
+                msplit = B;
+            }
+        }
+        if (B > nsm && msplit < 8) {
+            const uint32_t big1 = __ballot_sync(DGCNN_FULL_MASK, lane < 8 && lane < B && lane >= msplit &&
+                                                                    graph_cost(cand.z) > share) >> msplit;
+            excl = max(0, min(__ffs(~big1) - 1, (nsm - 2 * nsplit) / 2));   // then: an SM of their own
         }
     }
     excl = __shfl_sync(DGCNN_FULL_MASK, excl, 0);
     nsplit = __shfl_sync(DGCNN_FULL_MASK, nsplit, 0);
+    msplit = __shfl_sync(DGCNN_FULL_MASK, msplit, 0);
     // lane j proposes the CTA's item next + j
     const int item = next + lane;
     int pos;
     const bool is_split = sm < 2 * nsplit;
     const int s1 = sm - 2 * nsplit, n1 = nsm - 2 * nsplit;
     if (is_split) {
-        pos = item == 0 ? (sm >> 1) : B;
+        pos = lane == 0 ? (sm >> 1) + next * nsplit : B;    // one graph per pass: the pair works as one team
+        if (pos >= msplit) pos = B;
     } else if (s1 < excl) {
-        pos = item == 0 ? nsplit + s1 : B;
+        pos = item == 0 ? msplit + s1 : B;
     } else {
         const int s2 = s1 - excl, n2 = n1 - excl;
-        pos = nsplit + excl + item * n2 + ((item & 1) ? n2 - 1 - s2 : s2);
+        pos = msplit + excl + item * n2 + ((item & 1) ? n2 - 1 - s2 : s2);
     }
     const bool valid = lane < kMaxTeams && pos < B;
     int4 d = make_int4(0, 0, 0, 0);
     if (first_pass && (is_split || s1 < excl)) {
         // a graph with SMs of its own is one of the candidates just loaded: no second round trip
-        const int src = (is_split ? (sm >> 1) : nsplit + s1) & 31;
+        const int src = (is_split ? (sm >> 1) : msplit + s1) & 7;
         d.x = __shfl_sync(DGCNN_FULL_MASK, cand.x, src); d.y = __shfl_sync(DGCNN_FULL_MASK, cand.y, src);
         d.z = __shfl_sync(DGCNN_FULL_MASK, cand.z, src); d.w = __shfl_sync(DGCNN_FULL_MASK, cand.w, src);
         if (!valid) d = make_int4(0, 0, 0, 0);
@@ -219,7 +273,7 @@ __device__ __forceinline__ void plan_pass(const int4* __restrict__ gdesc, int B,
         d = gdesc[pos];
     }
     const int n = d.z, np = max(16, (n + 15) & ~15), T = np >> 4;
-    const int need = valid ? need_of(np) : 0;
+    const int need = valid ? need_of(np, is_split) : 0;
     int incl = need;
 #pragma unroll
     for (int o = 1; o < kMaxTeams; o <<= 1) {

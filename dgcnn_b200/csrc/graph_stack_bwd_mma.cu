@@ -45,8 +45,11 @@ struct StackBwdMmaParams {
     // conv5 + ReLU + max-pool's backward fused in (dh1 != null; dpooled is then unused):
     // the pooled gradient is dz W5 with dz[r][c] = dh1[c][r/2] routed through `arg`, never materialised
     const float* dh1; const uint8_t* arg; const float* w5;
+    int64_t num_nodes;   // gws holds two [num_nodes][32] buffers (split graphs alternate between them)
+    int pairs;           // launched as clusters of two CTAs: the plan may split graphs over a pair
+    int split_pct;
 };
-#define KSB_TRACE(slot) do { if (p.trace && tm.tid == 0) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
+#define KSB_TRACE(slot) do { if (p.trace && tm.tid == 0 && !(tm.split && tm.rank)) p.trace[(int64_t)gi * 16 + (slot)] = clock64(); } while (0)
 
 constexpr int kC5b = 16;                   // conv5 output channels
 constexpr int kW5TPad = 24;                // row stride (halfs) of the transposed W5 planes [97][16]
@@ -85,19 +88,23 @@ __host__ __device__ inline BwdShared bwd_shared_layout(int f, bool conv5 = false
     return L;
 }
 
-// per graph (bytes)
-struct BwdTeamLayout { int P, DH, DZ, vpl, bm, cs, rs, hv, rank, rp, red, sacc, total; int S; };
-__host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np, bool conv5 = false) {
+// per graph (bytes).  split: the graph is spread over the two CTAs of a cluster; each CTA owns the
+// first / last ceil(T / 2) row tiles and keeps the dh planes and the adjacency of THOSE rows only
+// (everything indexed by column -- P, dz, coefficients, ranks -- stays whole)
+struct BwdTeamLayout { int P, DH, DZ, vpl, bm, cs, rs, hv, rank, rp, red, sacc, total; int S, Sd; };
+__host__ __device__ inline BwdTeamLayout bwd_team_layout(int f, int np, bool conv5 = false, bool split = false) {
     BwdTeamLayout L;
     L.S = np + 8;
     const int wpr = (np + 31) >> 5;
+    const int T = np >> 4, own_t = split ? (T + 1) >> 1 : T, own_np = own_t * 16;
+    L.Sd = own_np + 8;
     int o = 0;
     L.P = o; o += 2 * kHid * L.S * 2;                    // hi/lo planes of r * dpre * scale
-    L.DH = o; o += 2 * kHid * L.S * 2;                   // hi/lo planes of dh * scale
+    L.DH = o; o += 2 * kHid * L.Sd * 2;                  // hi/lo planes of dh * scale (own rows)
     L.DZ = o; o += conv5 ? 2 * kC5b * L.S * 2 : 0;       // hi/lo planes [16][S] of dz * scale (conv5 pre-activation grads)
     L.vpl = o; o += al16(2 * L.S * 2);
     {
-        const int plain = np * wpr * 4, frag = frag_words(np) * 4;
+        const int plain = own_np * wpr * 4, frag = own_t * ((T + 3) >> 2) * 32 * 4;
         L.bm = o; o += al16(plain > frag ? plain : frag);
     }
     L.cs = o; o += al16(np * 4);
@@ -158,9 +165,9 @@ __device__ __forceinline__ void dz_w5_tile(const Conv5Bwd& c5, int S, int mt, in
 //   - dh planes (still scaled) for the dW product,
 //   - if wp: dx = dh W via the fragments, unscaled, + pooled gradient of the slice -> Gout
 __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, const __half* __restrict__ wp,
-                                              __half* __restrict__ DH, float* __restrict__ Gout,
+                                              __half* __restrict__ DH, int Sd, float* __restrict__ Gout,
                                               const uint32_t* __restrict__ bm, bool frag, int wpr, int n, int S,
-                                              bool dup, const int* __restrict__ rp,
+                                              int t_lo, int t_hi, bool dup, const int* __restrict__ rp,
                                               const int32_t* __restrict__ col_g, int base,
                                               const float* __restrict__ cs, const int* __restrict__ rank,
                                               const float* __restrict__ dp, int offx, float inv_scale,
@@ -170,7 +177,7 @@ __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, cons
     const int tiles = (n + 15) >> 4;
     const uint32_t* in32[2] = {reinterpret_cast<const uint32_t*>(P),
                                reinterpret_cast<const uint32_t*>(P + kHid * S)};
-    for (int mt = warp; mt < tiles; mt += nwarps) {
+    for (int mt = t_lo + warp; mt < t_hi; mt += nwarps) {      // (bm, DH: offset to the own rows by the caller)
         const int row0 = mt * 16 + g, row1 = row0 + 8;
         float acc[4][4];
 #pragma unroll
@@ -256,14 +263,14 @@ __device__ __forceinline__ void bwd_mma_layer(const __half* __restrict__ P, cons
         }
         {   // dh planes [channel][node] (scaled), the A operand of dW = dh^T x_in
             __half* oh = DH;
-            __half* ol = DH + kHid * S;
+            __half* ol = DH + kHid * Sd;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int ch = nt * 8 + 2 * t + q;
-                    store_split(oh, ol, ch * S + row0, acc[nt][q]);
-                    store_split(oh, ol, ch * S + row1, acc[nt][2 + q]);
+                    store_split(oh, ol, ch * Sd + row0, acc[nt][q]);
+                    store_split(oh, ol, ch * Sd + row1, acc[nt][2 + q]);
                 }
         }
         if (wp) {
@@ -335,10 +342,14 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     const uint8_t* argg = conv5 ? p.arg + (int64_t)gi * kC5b * L1 : nullptr;
     // db5[c] = sum_j dh1[c][j] over the live pairs: every (c, j) feeds exactly one pooled row, real
     // or padding (a padding row's pre-activation is b5 itself)
+    // (a graph split over a CTA pair: each CTA leaves the sums over ITS rows; db5 is rank 0's)
+    const bool split = tm.split != 0;
+    const int crank = split ? tm.rank : 0;
     auto conv5_bias_grad = [&](float* sacc_) {
         for (int c = warp; c < kC5b; c += nwarps) {
             float sb = 0.f;
-            for (int j = lane; j < L1; j += 32) sb += argg[c * L1 + j] != 2 ? dh1g[c * L1 + j] : 0.f;
+            if (crank == 0)
+                for (int j = lane; j < L1; j += 32) sb += argg[c * L1 + j] != 2 ? dh1g[c * L1 + j] : 0.f;
             sb = warp_sum(sb);
             if (lane == 0) sacc_[GO.b5 + c] = sb;
         }
@@ -346,10 +357,10 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     // The team leaves this graph's parameter-gradient vector in `sacc` (every entry is
     // written exactly once below); the CTA adds the vectors of a pass in team order.
     if (n == 0) {
-        float* sacc0 = reinterpret_cast<float*>(tm.smem + bwd_team_layout(f, 16, conv5).sacc);
+        float* sacc0 = reinterpret_cast<float*>(tm.smem + bwd_team_layout(f, 16, conv5, split).sacc);
         for (int idx = tid; idx < GO.total; idx += nthreads) sacc0[idx] = 0.f;
         if (conv5) {
-            tm.sync();
+            tm.sync_local();
             conv5_bias_grad(sacc0);
         }
         return;
@@ -358,17 +369,26 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     const int np = (n + 15) & ~15;
     const int wpr = (np + 31) >> 5;
     const int tiles = np >> 4;
-    const BwdTeamLayout L = bwd_team_layout(f, np, conv5);
-    const int S = L.S;
+    const BwdTeamLayout L = bwd_team_layout(f, np, conv5, split);
+    const int S = L.S, Sd = L.Sd;
+    // this CTA's row tiles [t_lo, t_hi), rows [r_lo, r_hi) of which [r_lo, n_hi) are nodes
+    const int t_lo = split ? (crank ? (tiles + 1) >> 1 : 0) : 0;
+    const int t_hi = split ? (crank ? tiles : (tiles + 1) >> 1) : tiles;
+    const int r_lo = t_lo * 16, r_hi = t_hi * 16, n_hi = min(r_hi, n);
     unsigned char* sm = tm.smem;
     __half* DZ = reinterpret_cast<__half*>(sm + L.DZ);
     Conv5Bwd c5;
     c5.DZ = DZ; c5.w5t = reinterpret_cast<const __half*>(shraw + SL.w5t); c5.on = conv5;
-    float* G = p.gws + (int64_t)base * kHid;             // this graph's rows
+    // gradient w.r.t. the current layer's output, this graph's rows.  A split graph alternates
+    // between two buffers: a CTA writes its rows of the next layer's G while the peer may still
+    // read the current one; one cluster barrier per layer orders the rest.
+    float* G = p.gws + (int64_t)base * kHid;             // read by phase A (all rows)
+    float* Gw = split ? p.gws + ((int64_t)p.num_nodes + base) * kHid : G;   // written by phase B (own rows)
     __half* P = reinterpret_cast<__half*>(sm + L.P);
-    __half* DH = reinterpret_cast<__half*>(sm + L.DH);
+    __half* DH = reinterpret_cast<__half*>(sm + L.DH) - r_lo;        // [channel][Sd], indexed by node
     __half* vpl = reinterpret_cast<__half*>(sm + L.vpl);
-    uint32_t* bm = reinterpret_cast<uint32_t*>(sm + L.bm);
+    // adjacency of the own rows, indexed like the whole map
+    uint32_t* bm = reinterpret_cast<uint32_t*>(sm + L.bm) - (frag ? t_lo * ((tiles + 3) >> 2) * 32 : r_lo * wpr);
     float* cs = reinterpret_cast<float*>(sm + L.cs);
     float* rs = reinterpret_cast<float*>(sm + L.rs);
     float* hv = reinterpret_cast<float*>(sm + L.hv);
@@ -391,8 +411,12 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     }
     KSB_TRACE(0);
     // ---- phase 0: bitmap, coefficients, inverse permutation, gradient scale -----------------
-    if (frag) load_bitmap<8>(p.fragmap + fgoff, bm, frag_words(np), tid, nthreads);
-    else load_bitmap(gbm + gbo[gi], bm, np * wpr, tid, nthreads);
+    if (frag) {
+        const int gw = ((tiles + 3) >> 2) * 32;
+        load_bitmap<8>(p.fragmap + fgoff + t_lo * gw, bm + t_lo * gw, (t_hi - t_lo) * gw, tid, nthreads);
+    } else {
+        load_bitmap(gbm + gbo[gi] + r_lo * wpr, bm + r_lo * wpr, (r_hi - r_lo) * wpr, tid, nthreads);
+    }
     for (int j = tid; j < np; j += nthreads) {
         const float d = j < n ? p.dis[base + j] : 0.f;
         cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
@@ -429,14 +453,14 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(DGCNN_FULL_MASK, amax, o));
     if (lane == 0) red0[warp] = amax;
-    tm.sync();
+    tm.sync_local();
     for (int r = tid; r < keep; r += nthreads) {
         const int node = perm_g[r] - base;
         if ((unsigned)node < (unsigned)n) rank[node] = r;
     }
     amax = 0.f;
     for (int w = 0; w < nwarps; ++w) amax = fmaxf(amax, red0[w]);
-    tm.sync();
+    tm.sync_local();
     if (!(amax > 0.f) || !(amax < 3.0e38f)) {
         // nothing flows into this graph (or the gradient is not finite: propagate as zeros
         // would hide it, so write NaN-free zeros only for the exact-zero case)
@@ -460,7 +484,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             store_split(DZ, DZ + kC5b * S, idx, v * scale);
         }
         conv5_bias_grad(sacc);
-        tm.sync();
+        tm.sync_local();
     }
     KSB_TRACE(1);
     // ---- layer 4 (32 -> 1) --------------------------------------------------------------------
@@ -481,7 +505,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                     gy = rank[i] >= 0 ? dp[rank[i] * kCat + 3 * kHid] : 0.f;
                 }
                 const float d = gy * (1.f - y * y);
-                dbp += d;
+                if (i >= r_lo && i < r_hi) dbp += d;
                 v = rs[i] * d * scale;
             }
             store_split(vpl, vpl + S, i, v);
@@ -489,7 +513,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         dbp = warp_sum(dbp);
         if (lane == 0) red0[warp] = dbp;
     }
-    tm.sync();
+    tm.sync_local();
     if (tid == 0) {
         float s = 0.f;
         for (int w = 0; w < nwarps; ++w) s += red0[w];
@@ -500,7 +524,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         c.n = n; c.np = np; c.T = tiles; c.G = (tiles + 3) >> 2; c.S = S; c.base = base; c.dup = dup;
         c.fbm = bm; c.rp = rp; c.col_g = col_g; c.cs = cs; c.rs = rs;
         const int g = lane >> 2, t = lane & 3;
-        for (int mt = warp; mt < tiles; mt += nwarps) {
+        for (int mt = t_lo + warp; mt < t_hi; mt += nwarps) {
             float a4[4];
             aggregate8(c, vpl, S, 1, mt, lane, a4);          // 2 x sum (A fragments are {0, 2})
             if (t == 0) {
@@ -514,7 +538,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         const int g = lane >> 2, t = lane & 3;
         const uint32_t* v32[2] = {reinterpret_cast<const uint32_t*>(vpl),
                                   reinterpret_cast<const uint32_t*>(vpl + S)};
-        for (int mt = warp; mt < tiles; mt += nwarps) {
+        for (int mt = t_lo + warp; mt < t_hi; mt += nwarps) {
             const int row0 = mt * 16 + g, row1 = row0 + 8;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             if (!dup) {
@@ -548,14 +572,14 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             }
         }
     }
-    tm.sync();
+    tm.sync_local();
     float* xin3 = reinterpret_cast<float*>(P);           // conv5: x3 as fp32 [feature][S] (P is still free)
     const uint32_t* dz32[2] = {reinterpret_cast<const uint32_t*>(DZ),
                                reinterpret_cast<const uint32_t*>(DZ + kC5b * S)};
     if (conv5) {
         // pooled gradient of the x3 slice, dz W5[:, 64..95], straight into G (unscaled)
         const int g = lane >> 2, t = lane & 3;
-        for (int mt = warp; mt < tiles; mt += nwarps) {
+        for (int mt = t_lo + warp; mt < t_hi; mt += nwarps) {
             float gz[4][4];
             dz_w5_tile(c5, S, mt, 2 * kHid, lane, gz);
 #pragma unroll
@@ -564,34 +588,34 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 if (row >= n) continue;
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
-                    *reinterpret_cast<float2*>(G + row * kHid + nt * 8 + 2 * t) =
+                    *reinterpret_cast<float2*>(Gw + row * kHid + nt * 8 + 2 * t) =
                         make_float2(gz[nt][2 * half] * inv_scale, gz[nt][2 * half + 1] * inv_scale);
             }
         }
         // dW5[c][96] = sum_i dz[i][c] x4[i]
         for (int ch = warp; ch < kC5b; ch += nwarps) {
             float sw = 0.f;
-            for (int i = lane; i < n; i += 32)
+            for (int i = r_lo + lane; i < n_hi; i += 32)
                 sw = fmaf(__half2float(DZ[ch * S + i]) + __half2float(DZ[(kC5b + ch) * S + i]),
                           xc[(int64_t)i * p.ldc + 3 * kHid], sw);
             sw = warp_sum(sw);
             if (lane == 0) sacc[GO.w5 + ch * kCat + 3 * kHid] = sw * inv_scale;
         }
-        tm.sync();
+        tm.sync_local();
     }
     {   // dW4[k] += sum_i dh4[i] x3[i][k];  G3[i][k] = dh4[i] w4[k] + pooled gradient of x3
         float dwp = 0.f;
         const float w4k = w4s[lane];
-        for (int i0 = warp; i0 < np; i0 += 8 * nwarps) {         // eight rows in flight per warp
+        for (int i0 = r_lo + warp; i0 < r_hi; i0 += 8 * nwarps) {     // eight rows in flight per warp
             float xv[8], gp[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u * nwarps;
                 xv[u] = 0.f; gp[u] = 0.f;
-                if (i < n) {
+                if (i < n_hi) {
                     xv[u] = xc[(int64_t)i * p.ldc + 2 * kHid + lane];
                     if (conv5) {
-                        gp[u] = G[i * kHid + lane];
+                        gp[u] = Gw[i * kHid + lane];
                     } else {
                         const int r = rank[i];
                         if (r >= 0) gp[u] = dp[r * kCat + 2 * kHid + lane];
@@ -601,17 +625,17 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u * nwarps;
-                if (i < n) {
+                if (i < n_hi) {
                     const float h = hv[i];
                     dwp = fmaf(h, xv[u], dwp);
-                    G[i * kHid + lane] = fmaf(h, w4k, gp[u]);
+                    Gw[i * kHid + lane] = fmaf(h, w4k, gp[u]);
                 }
-                if (conv5 && i < np) xin3[lane * S + i] = xv[u];     // (zero beyond n: NaN-free MMA padding)
+                if (conv5 && i < r_hi) xin3[lane * S + i] = xv[u];   // (zero beyond n: NaN-free MMA padding)
             }
         }
         red0[warp * kHid + lane] = dwp;
     }
-    tm.sync();
+    tm.sync_local();
     if (tid < kHid) sacc[GO.w4 + tid] = reduce_rows_t(red0, nwarps, tid);
     if (conv5) {
         // dW5[c][64 + k] = sum_i dz[i][c] x3[i][k]: four 16 x 8 output tiles on the tensor cores
@@ -619,7 +643,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         for (int nk = warp; nk < 4; nk += nwarps) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             const float* xcol = xin3 + (8 * nk + g) * S + 2 * t;
-            for (int kt = 0; kt < tiles; ++kt) {
+            for (int kt = t_lo; kt < t_hi; ++kt) {
                 const float2 x01 = *reinterpret_cast<const float2*>(xcol + kt * 16);
                 const float2 x89 = *reinterpret_cast<const float2*>(xcol + kt * 16 + 8);
                 const int ia = (g * S + kt * 16 + 2 * t) >> 1;
@@ -638,7 +662,8 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             o[8 * kCat] = acc[2] * inv_scale; o[8 * kCat + 1] = acc[3] * inv_scale;
         }
     }
-    tm.sync();
+    tm.sync();                                           // (split: the peer's rows of G are in L2 too)
+    if (split) { float* tmp = G; G = Gw; Gw = tmp; }
 
     KSB_TRACE(2);
     // ---- layers 3, 2, 1 -------------------------------------------------------------------------
@@ -658,7 +683,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                     yv[u] = 0.f; gv[u] = 0.f;
                     if (i < n) {
                         yv[u] = xc[(int64_t)i * p.ldc + offy + lane];
-                        gv[u] = G[i * kHid + lane];
+                        gv[u] = __ldcg(G + i * kHid + lane);     // (the peer's rows: written this launch)
                     }
                 }
 #pragma unroll
@@ -668,7 +693,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                         float sc = 0.f;
                         if (i < n) {
                             const float d = gv[u] * (1.f - yv[u] * yv[u]);
-                            dbp += d;
+                            if (i >= r_lo && i < r_hi) dbp += d;
                             sc = rs[i] * d * scale;
                         }
                         store_split(ph, pl, lane * S + i, sc);
@@ -677,16 +702,16 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             }
             red0[warp * kHid + lane] = dbp;
         }
-        tm.sync();
+        tm.sync_local();
         if (tid < kHid) {
             const int ob = layer == 3 ? GO.b3 : (layer == 2 ? GO.b2 : GO.b1);
             sacc[ob + tid] = reduce_rows_t(red0, nwarps, tid);
         }
         KSB_TRACE(3 + 3 * (3 - layer));
         // B: dh planes, and G <- dx (layers 3, 2)
-        bwd_mma_layer(P, layer == 3 ? w3p : (layer == 2 ? w2p : nullptr), DH, G, bm, frag, wpr, n, S, dup, rp,
-                      col_g, base, cs, rank, dp, offx, inv_scale, tm, c5);
-        tm.sync();
+        bwd_mma_layer(P, layer == 3 ? w3p : (layer == 2 ? w2p : nullptr), DH, Sd, Gw, bm, frag, wpr, n, S, t_lo, t_hi,
+                      dup, rp, col_g, base, cs, rank, dp, offx, inv_scale, tm, c5);
+        tm.sync_local();
         KSB_TRACE(4 + 3 * (3 - layer));
         // C: parameter gradient of the layer
         if (layer >= 2) {
@@ -697,24 +722,24 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             // k-tile -- and the MMA loop splits it hi/lo in registers.  S = np + 8 makes the
             // 8-byte fragment loads conflict-free per half-warp.
             float* xin = reinterpret_cast<float*>(P);
-            for (int i0 = warp; i0 < np; i0 += 8 * nwarps) {
+            for (int i0 = r_lo + warp; i0 < r_hi; i0 += 8 * nwarps) {
                 float v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = i0 + u * nwarps;
-                    v[u] = i < n ? xc[(int64_t)i * p.ldc + offx + lane] : 0.f;
+                    v[u] = i < n_hi ? xc[(int64_t)i * p.ldc + offx + lane] : 0.f;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = i0 + u * nwarps;
-                    if (i < np) xin[lane * S + i] = v[u];
+                    if (i < r_hi) xin[lane * S + i] = v[u];
                 }
             }
-            tm.sync();
+            tm.sync_local();
             const int ow = layer == 3 ? GO.w3 : GO.w2;
             const int g = lane >> 2, t = lane & 3;
             const uint32_t* dh32[2] = {reinterpret_cast<const uint32_t*>(DH),
-                                       reinterpret_cast<const uint32_t*>(DH + kHid * S)};
+                                       reinterpret_cast<const uint32_t*>(DH + kHid * Sd)};
             // (conv5: four more tiles, dW5[c][offx + k] = sum_i dz[i][c] x_in[i][k], A = the dz planes)
             for (int tile = warp; tile < (conv5 ? 12 : 8); tile += nwarps) {
                 const int mc = tile >> 2, nk = tile & 3;
@@ -723,15 +748,16 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 const uint32_t* a_lo = zt ? dz32[1] : dh32[1];
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 const float* xcol = xin + (8 * nk + g) * S + 2 * t;      // feature column of this lane
-                for (int kt = 0; kt < tiles; ++kt) {
+                const int Sa = zt ? S : Sd;                  // row stride of the A planes
+                for (int kt = t_lo; kt < t_hi; ++kt) {
                     const float2 x01 = *reinterpret_cast<const float2*>(xcol + kt * 16);
                     const float2 x89 = *reinterpret_cast<const float2*>(xcol + kt * 16 + 8);
-                    const int ia = (((zt ? 0 : 16 * mc) + g) * S + kt * 16 + 2 * t) >> 1;
+                    const int ia = (((zt ? 0 : 16 * mc) + g) * Sa + kt * 16 + 2 * t) >> 1;
                     uint32_t ah[4], al[4];
-                    ah[0] = a_hi[ia]; ah[1] = a_hi[ia + 4 * S]; ah[2] = a_hi[ia + 4];
-                    ah[3] = a_hi[ia + 4 * S + 4];
-                    al[0] = a_lo[ia]; al[1] = a_lo[ia + 4 * S]; al[2] = a_lo[ia + 4];
-                    al[3] = a_lo[ia + 4 * S + 4];
+                    ah[0] = a_hi[ia]; ah[1] = a_hi[ia + 4 * Sa]; ah[2] = a_hi[ia + 4];
+                    ah[3] = a_hi[ia + 4 * Sa + 4];
+                    al[0] = a_lo[ia]; al[1] = a_lo[ia + 4 * Sa]; al[2] = a_lo[ia + 4];
+                    al[3] = a_lo[ia + 4 * Sa + 4];
                     uint32_t bh0, bl0, bh1, bl1;
                     split2(x01.x, x01.y, bh0, bl0);
                     split2(x89.x, x89.y, bh1, bl1);
@@ -749,7 +775,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             // dW1[c][k] = sum_i dh[i][c] x0[i][k], k < F (any F): FMA, dh rebuilt from its planes.
             // With few outputs (small F) `parts` lanes share one output and split the rows.
             const __half* dhh = DH;
-            const __half* dhl = DH + kHid * S;
+            const __half* dhl = DH + kHid * Sd;
             const int outs = kHid * f;
             int parts = 1;
             while (parts < 32 && outs * parts * 2 <= nthreads) parts <<= 1;
@@ -762,19 +788,19 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 float a0 = 0.f;
                 if (live) {
                     const float* xr = p.x + (int64_t)base * p.ldx + k;
-                    int i = part;
-                    for (; i + 7 * parts < n; i += 8 * parts) {          // eight loads in flight
+                    int i = r_lo + part;
+                    for (; i + 7 * parts < n_hi; i += 8 * parts) {       // eight loads in flight
                         float xv[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) xv[u] = xr[(int64_t)(i + u * parts) * p.ldx];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int ii = c * S + i + u * parts;
+                            const int ii = c * Sd + i + u * parts;
                             a0 = fmaf(__half2float(dhh[ii]) + __half2float(dhl[ii]), xv[u], a0);
                         }
                     }
-                    for (; i < n; i += parts) {
-                        const int ii = c * S + i;
+                    for (; i < n_hi; i += parts) {
+                        const int ii = c * Sd + i;
                         a0 = fmaf(__half2float(dhh[ii]) + __half2float(dhl[ii]), xr[(int64_t)i * p.ldx], a0);
                     }
                 }
@@ -782,7 +808,12 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 if (live && part == 0) sacc[GO.w1 + c * f + k] = a0 * inv_scale;
             }
         }
-        tm.sync();
+        if (layer > 1) {
+            tm.sync();                                   // (split: cluster barrier -- G's new rows are visible)
+            if (split) { float* tmp = G; G = Gw; Gw = tmp; }
+        } else {
+            tm.sync_local();
+        }
         KSB_TRACE(5 + 3 * (3 - layer));
     }
 
@@ -812,12 +843,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
     const int nsm = gridDim.x, sm = blockIdx.x, B = p.num_graphs;
     constexpr int kWarps = kBwdThreads / 32;
     const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
-    int next = 0, excl = 0, nsplit = 0;              // (no cluster split in the backward kernel)
+    int next = 0, excl = 0, nsplit = 0, msplit = 0;
+    uint32_t crank = 0;                              // rank of this CTA in its cluster
+    if (p.pairs) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
 
     for (int pass = 0;; ++pass) {
         if (warp_id == 0) {
             plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
-                      [f, conv5](int np) { return bwd_team_layout(f, np, conv5).total; }, s_plan, &s_count, nsplit);
+                      [f, conv5](int np, bool split) { return bwd_team_layout(f, np, conv5, split).total; }, s_plan,
+                      &s_count, nsplit, msplit, p.pairs != 0, p.split_pct);
         } else if (pass == 0) {
             const int tid = threadIdx.x - 32, nthreads = kBwdThreads - 32;
             __half* w2p = reinterpret_cast<__half*>(smraw + SL.w2p);
@@ -873,6 +907,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
                 tm.lane = lane;
                 tm.bar = 1 + mine;
                 tm.smem = team_base + e.smem_off;
+                tm.split = e.pad;                    // shared with the peer CTA of the cluster
+                tm.rank = (int)crank;
                 bwd_process_graph(p, tm, e.gi, e.base, e.n, e.fgoff, smraw, gbm, gbo, gfl, frag);
             }
         }
@@ -883,7 +919,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
             if (e.n > p.nmax) continue;
             const int np = max(16, (e.n + 15) & ~15);
             const float* sacc = reinterpret_cast<const float*>(team_base + e.smem_off +
-                                                               bwd_team_layout(f, np, conv5).sacc);
+                                                               bwd_team_layout(f, np, conv5, e.pad != 0).sacc);
             for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) cta_acc[idx] += sacc[idx];
         }
         next += count;                               // (the next pass syncs before it re-carves)
@@ -927,16 +963,51 @@ using namespace dgcnn;
 static int64_t* g_bwd_trace = nullptr;
 extern "C" void dgcnn_stack_bwd_set_trace(int64_t* device_buffer) { g_bwd_trace = device_buffer; }
 
+// Clusters of two CTAs, like the forward kernel (graph_stack_mma.cu): the plan splits the largest
+// graphs of the batch over a pair.  -1: not probed yet, 0: off, 1: on.  DGCNN_KS_PAIRS=0 and
+// dgcnn_stack_fwd_configure(0, ..) switch both kernels to plain launches.
+static int g_bwd_pairs = -1, g_bwd_split_pct = 80;
+void dgcnn_stack_bwd_mma_configure(int pairs, int split_pct) {
+    g_bwd_pairs = pairs < 0 ? -1 : (pairs ? -2 : 0);     // -2: requested, still to be probed
+    if (split_pct > 0) g_bwd_split_pct = split_pct;
+}
+static int bwd_pairs_enabled() {
+    if (g_bwd_pairs >= 0) return g_bwd_pairs;
+    int ok = 1;
+    if (g_bwd_pairs == -1) {
+        const char* env = getenv("DGCNN_KS_PAIRS");
+        ok = !(env && env[0] == '0');
+    }
+    if (ok) ok = cluster_pairs_fit(stack_bwd_mma_kernel, kBwdThreads, (size_t)(kSmemBudget - 1024));
+    g_bwd_pairs = ok;
+    return ok;
+}
+
 int dgcnn_stack_bwd_mma_supported(int32_t f, int64_t max_nodes, bool conv5) {
     if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
     const int np = (int)((max_nodes + 15) / 16 * 16);
-    return bwd_team_layout(f, np, conv5).total <= kQuads * bwd_quad_bytes(f, conv5) ? 1 : 0;
+    const int budget = kQuads * bwd_quad_bytes(f, conv5);
+    if (bwd_team_layout(f, np, conv5, false).total <= budget) return 1;
+    // larger graphs only as a CTA pair (mandatory split: plan_pass)
+    return bwd_team_layout(f, np, conv5, true).total <= budget && bwd_pairs_enabled() ? 1 : 0;
+}
+
+static int64_t bwd_grid(int64_t num_graphs, bool pairs) {
+    int64_t grid = DGCNN_NUM_SMS;
+    if (pairs) {
+        if (grid > num_graphs + 8) grid = num_graphs + 8;   // spare CTAs double up on the largest graphs
+        grid += grid & 1;
+        if (grid > DGCNN_NUM_SMS) grid = DGCNN_NUM_SMS & ~1;
+    } else if (grid > num_graphs) {
+        grid = num_graphs;
+    }
+    return grid < 1 ? 1 : grid;
 }
 
 size_t dgcnn_stack_bwd_mma_workspace_bytes(int32_t f, int64_t num_graphs, int64_t num_nodes) {
-    // (sized for the conv5 variant: one partial vector per CTA, at most one CTA per graph)
-    return sizeof(float) * ((size_t)grad_offsets_m(f, true).total * (size_t)(num_graphs > 0 ? num_graphs : 1) +
-                            (size_t)(num_nodes > 0 ? num_nodes : 0) * kHid) + 1024;
+    // (sized for the conv5 variant: one partial vector per CTA; two G buffers)
+    return sizeof(float) * ((size_t)grad_offsets_m(f, true).total * (size_t)bwd_grid(num_graphs, true) +
+                            2 * (size_t)(num_nodes > 0 ? num_nodes : 0) * kHid) + 1024;
 }
 
 int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, const float* xcat,
@@ -964,8 +1035,12 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     uintptr_t aligned = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     p.counter = reinterpret_cast<int32_t*>(aligned);
     p.partials = reinterpret_cast<float*>(aligned + 256);
+    p.pairs = bwd_pairs_enabled();
+    p.split_pct = g_bwd_split_pct;
+    p.num_nodes = num_nodes;
+    const int64_t grid = bwd_grid(num_graphs, p.pairs != 0);
     p.gws = reinterpret_cast<float*>(
-        ((uintptr_t)(p.partials + (size_t)grad_offsets_m(f, conv5).total * (size_t)num_graphs) + 255) &
+        ((uintptr_t)(p.partials + (size_t)grad_offsets_m(f, conv5).total * (size_t)grid) + 255) &
         ~(uintptr_t)255);
     p.status = status;
     p.trace = g_bwd_trace;
@@ -974,9 +1049,17 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
     if (cudaFuncSetAttribute(stack_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
-    int64_t grid = DGCNN_NUM_SMS;
-    if (grid > num_graphs) grid = num_graphs;
-    stack_bwd_mma_kernel<<<(unsigned)grid, kBwdThreads, smem, st>>>(p);
+    if (p.pairs) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kBwdThreads);
+        cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, stack_bwd_mma_kernel, p) != cudaSuccess) return DGCNN_ERR_CUDA;
+    } else {
+        stack_bwd_mma_kernel<<<(unsigned)grid, kBwdThreads, smem, st>>>(p);
+    }
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int total = grad_offsets_m(f, conv5).total;
     stack_bwd_reduce_graphs<<<(total + 31) / 32, 256, 0, st>>>(p.partials, (int)grid, total, grads);

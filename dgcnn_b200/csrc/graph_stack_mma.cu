@@ -79,14 +79,19 @@ struct TeamLayout {
     int S;      // row stride (halfs) of the single-column planes (vpl, xs): np + 8
 };
 
-__host__ __device__ inline TeamLayout team_layout(int f, int np, bool conv5 = false) {
+// (split: the graph is spread over a CTA pair; each CTA keeps full copies of the planes but only
+// the adjacency fragments of its own row tiles -- the first or last ceil(T / 2) of them)
+__host__ __device__ inline TeamLayout team_layout(int f, int np, bool conv5 = false, bool split = false) {
     TeamLayout L;
     L.S = np + 8;
     int o = 0;
     L.PA = o; o += np * kRowB;
     L.PB = o; o += np * kRowB;
     L.vpl = o; o += al16(2 * L.S * 2);                   // layer-4 input: hi and lo [S]
-    L.fbm = o; o += frag_words(np) * 4;
+    {
+        const int T = np >> 4, own = split ? (T + 1) >> 1 : T;
+        L.fbm = o; o += own * ((T + 3) >> 2) * 32 * 4;
+    }
     L.xs = o; o += (f <= kSmallF) ? al16(2 * f * L.S * 2) : 0;   // layer-1 input planes [2][F][S]
     L.cs = o; o += al16(np * 4);
     L.rs = o; o += al16(np * 4);
@@ -357,7 +362,7 @@ __device__ __forceinline__ void load_bias(const float* __restrict__ bias, int t,
 // the two CTAs of a cluster together: CTA `tm.rank` owns the row tiles [t0, t1), every plane /
 // key / order store of its rows also goes into the peer's shared memory, and the team barrier
 // is the cluster barrier.
-__device__ __forceinline__ void process_graph(const StackFwdParams& p, const Team& tm, const PlanEntry& e,
+__device__ __forceinline__ void process_graph(const StackFwdParams& p, Team& tm, const PlanEntry& e,
                                               const unsigned char* shraw) {
     const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
     const int nthreads = tm.nthreads, nwarps = tm.nwarps;
@@ -420,7 +425,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     const int np = c.np;
     const int t0 = split ? (rank ? (c.T + 1) >> 1 : 0) : 0;          // this CTA's row tiles
     const int t1 = split ? (rank ? c.T : (c.T + 1) >> 1) : c.T;
-    const TeamLayout L = team_layout(f, np, conv5);
+    const TeamLayout L = team_layout(f, np, conv5, split);
     c.S = L.S;
     const int S = L.S;
     unsigned char* smraw = tm.smem;
@@ -428,7 +433,8 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     __half* PA = reinterpret_cast<__half*>(smraw + L.PA);
     __half* PB = reinterpret_cast<__half*>(smraw + L.PB);
     __half* vpl = reinterpret_cast<__half*>(smraw + L.vpl);
-    uint32_t* fbm = reinterpret_cast<uint32_t*>(smraw + L.fbm);
+    // (a split graph holds only its own row tiles' fragments: indexed by tile like the full map)
+    uint32_t* fbm = reinterpret_cast<uint32_t*>(smraw + L.fbm) - (split ? t0 * c.G * 32 : 0);
     __half* xs = reinterpret_cast<__half*>(smraw + L.xs);
     float* cs = reinterpret_cast<float*>(smraw + L.cs);
     float* rs = reinterpret_cast<float*>(smraw + L.rs);
@@ -441,7 +447,8 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     // split graph: rows are exchanged with bulk copies (pair_exchange below); only the sort ranks
     // are scattered remote stores
     int* order_peer = nullptr;
-    uint32_t peer_mbar = 0, xparity = 0;
+    uint32_t peer_mbar = 0;
+    uint32_t xparity = tm.xparity;                       // (the mbarrier's phase outlives the graph)
     const uint32_t peer = (uint32_t)(rank ^ 1);
     if (split) {
         cg::cluster_group cluster = cg::this_cluster();
@@ -736,6 +743,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, const Tea
     }
     for (int r = gtid; r < keep; r += gthreads) perm_g[r] = base + order[r];
     if (bulk_pending) bulk_store_wait();
+    tm.xparity = xparity;
     KS_TRACE(8);
     if (tracer) p.trace[(int64_t)gi * 16 + 10] = global_ns();
 #undef KS_TRACE
@@ -760,7 +768,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
     const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);      // {graph, base, n, fgoff}
     int next = 0;                                    // items of this CTA consumed so far
     int excl = 0;                                    // graphs with an SM of their own (warp 0 only)
-    int nsplit = 0;                                  // graphs split over a CTA pair (warp 0 only)
+    int nsplit = 0, msplit = 0;                      // CTA pairs / graphs split over a pair (warp 0 only)
+    uint32_t xparity = 0;                            // phase of the pair's exchange mbarrier
     uint32_t crank = 0;                              // rank of this CTA in its cluster
     __shared__ __align__(8) uint64_t s_pair_mbar;    // exchange barrier of a graph split over the pair
     if (p.pairs) {
@@ -771,8 +780,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
     for (int pass = 0;; ++pass) {
         if (warp_id == 0) {
             plan_pass(gdesc, B, nsm, sm, next, excl, pass == 0, budget, kWarps,
-                      [f, conv5](int np) { return team_layout(f, np, conv5).total; }, s_plan, &s_count, nsplit,
-                      p.pairs != 0, p.split_pct);
+                      [f, conv5](int np, bool split) { return team_layout(f, np, conv5, split).total; }, s_plan,
+                      &s_count, nsplit, msplit, p.pairs != 0, p.split_pct);
         } else if (pass == 0) {
             // meanwhile the other warps stage the weights: W1 transposed fp32 (F -> 32 stays on
             // the FMA pipe), W2/W3 as hi/lo fp16 planes [cout][cin] = the MMA "col" operand
@@ -855,6 +864,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
                 tm.split = e.pad;                    // shared with the peer CTA of the cluster
                 tm.rank = (int)crank;
                 tm.mbar = smem_addr_u32(&s_pair_mbar);
+                tm.xparity = xparity;
                 if (p.trace && tm.tid == 0 && (!tm.split || crank == 0)) {
                     cta_c2 = clock64();
                     p.trace[(int64_t)e.gi * 16 + 11] = cta_t0;
@@ -863,6 +873,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
                     p.trace[(int64_t)e.gi * 16 + 14] = cta_c2;       // padding rows zeroed, team starts
                 }
                 process_graph(p, tm, e, smraw);
+                xparity = tm.xparity;
             }
         }
         __syncthreads();                             // shared memory is re-carved by the next pass
@@ -889,16 +900,38 @@ int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes);
 static int64_t* g_trace = nullptr;
 extern "C" void dgcnn_stack_fwd_set_trace(int64_t* device_buffer) { g_trace = device_buffer; }
 
-static int g_pairs_ok = -1, g_split_pct = 80;
+void dgcnn_stack_bwd_mma_configure(int pairs, int split_pct);     // graph_stack_bwd_mma.cu
+
+// Clusters of two CTAs (one TPC): the plan splits the largest graphs of the batch over a pair
+// (planes exchanged through distributed shared memory), everything else runs as before.
+// DGCNN_KS_PAIRS=0 launches without clusters; DGCNN_KS_SPLIT_PCT tunes the split threshold.
+static int g_pairs_ok = -1, g_split_pct = 80;           // -1: not probed, -2: requested, 0 / 1: decided
 extern "C" void dgcnn_stack_fwd_configure(int32_t pairs, int32_t split_pct) {
-    g_pairs_ok = pairs < 0 ? -1 : (pairs ? 2 : 0);      // 2: requested, still to be probed
+    g_pairs_ok = pairs < 0 ? -1 : (pairs ? -2 : 0);
     if (split_pct > 0) g_split_pct = split_pct;
+    dgcnn_stack_bwd_mma_configure(pairs, split_pct);
+}
+static int pairs_enabled() {
+    if (g_pairs_ok >= 0) return g_pairs_ok;
+    int ok = 1;
+    if (g_pairs_ok == -1) {
+        const char* env = getenv("DGCNN_KS_PAIRS");
+        const char* pct = getenv("DGCNN_KS_SPLIT_PCT");
+        if (pct && atoi(pct) > 0) g_split_pct = atoi(pct);
+        ok = !(env && env[0] == '0');
+    }
+    if (ok) ok = cluster_pairs_fit(stack_fwd_mma_kernel, kFwdThreads, (size_t)(kSmemBudget - 1024));
+    g_pairs_ok = ok;
+    return ok;
 }
 
 static int mma_supported(int32_t f, int64_t max_nodes, bool conv5 = false) {
     if (f < 1 || f > kMaxF || max_nodes < 1 || max_nodes > 1024) return 0;
     const int np = (int)((max_nodes + 15) / 16 * 16);
-    return team_layout(f, np, conv5).total <= kQuads * quad_bytes(f, conv5) ? 1 : 0;
+    const int budget = kQuads * quad_bytes(f, conv5);
+    if (team_layout(f, np, conv5, false).total <= budget) return 1;
+    // larger graphs only as a CTA pair (mandatory split: plan_pass)
+    return team_layout(f, np, conv5, true).total <= budget && pairs_enabled() ? 1 : 0;
 }
 
 extern "C" int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes) {
@@ -969,34 +1002,7 @@ static int stack_fwd_impl(const float* x, int64_t ldx, int32_t num_features,
     if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
-    // Clusters of two CTAs (one TPC): the plan splits the largest graphs of the batch over a pair
-    // (planes exchanged through distributed shared memory), everything else runs as before.
-    // DGCNN_KS_PAIRS=0 launches without clusters; DGCNN_KS_SPLIT_PCT tunes the split threshold.
-    if (g_pairs_ok < 0 || g_pairs_ok == 2) {
-        int ok = 1;
-        if (g_pairs_ok < 0) {
-            const char* env = getenv("DGCNN_KS_PAIRS");
-            const char* pct = getenv("DGCNN_KS_SPLIT_PCT");
-            if (pct && atoi(pct) > 0) g_split_pct = atoi(pct);
-            ok = !(env && env[0] == '0');
-        }
-        if (ok) {
-            cudaLaunchConfig_t probe{};
-            cudaLaunchAttribute pattr[1];
-            pattr[0].id = cudaLaunchAttributeClusterDimension;
-            pattr[0].val.clusterDim.x = 2; pattr[0].val.clusterDim.y = 1; pattr[0].val.clusterDim.z = 1;
-            probe.gridDim = dim3(DGCNN_NUM_SMS); probe.blockDim = dim3(kFwdThreads);
-            probe.dynamicSmemBytes = smem; probe.attrs = pattr; probe.numAttrs = 1;
-            int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, stack_fwd_mma_kernel, &probe) != cudaSuccess ||
-                2 * nclusters < DGCNN_NUM_SMS) {
-                cudaGetLastError();
-                ok = 0;                              // every pair must be co-resident in ONE wave
-            }
-        }
-        g_pairs_ok = ok;
-    }
-    p.pairs = g_pairs_ok;
+    p.pairs = pairs_enabled();
     p.split_pct = g_split_pct;
     {
         static int plain = -1;

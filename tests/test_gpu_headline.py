@@ -460,6 +460,106 @@ def test_fused_conv5_backward_matches_the_unfused_kernels_and_the_oracle(name, c
         assert err <= 2e-3 * scale, f"{pname}: vs float64 oracle {err:.3e} (scale {scale:.3e})"
 
 
+def oracle_gradients_from_our_perm(ref, batch, count, k, perm, keep):
+    """loss and the 16 parameter gradients of the float64 oracle continued from OUR permutation
+    and OUR dropout mask"""
+    ref.train()
+    ref.zero_grad()
+    rx, _ = ref.hot_path(batch.x.double(), batch.edge_index, batch.batch, count)
+    rpool = oracle_pooled_from_perm(rx, perm, count, k)
+    h = ref.pool(F.relu(ref.conv5(rpool.view(count, 1, -1))))
+    h = F.relu(ref.conv6(h)).flatten(1)
+    h = F.relu(ref.classifier_1(h)) * keep.cpu().double()
+    rlogp = F.log_softmax(ref.classifier_2(h), dim=-1)
+    rloss = F.nll_loss(rlogp, batch.y, reduction="sum")
+    rloss.backward()
+    return rloss.detach(), dict(ref.named_parameters()), rx.detach()
+
+
+def collab_batch_with_big_graphs(big_sizes, small, seed):
+    """`small` ordinary COLLAB-synth graphs plus one dense ego-net-like graph per entry of big_sizes"""
+    from dgcnn_b200.synth import collate, make_graphs, _gnm_pairs, _symmetrise_sorted
+    cfg = CONFIGS["collab"]
+    graphs = make_graphs(cfg, small, seed=seed)
+    rng = np.random.RandomState(seed + 1)
+    for j, m in enumerate(big_sizes):
+        ei = _symmetrise_sorted(_gnm_pairs(rng, m, 33 * m), m)
+        deg = np.bincount(ei[1], minlength=m).astype(np.float32)
+        graphs.insert((7 * j) % (len(graphs) + 1), {"x": (deg / deg.max())[:, None].astype(np.float32),
+                                                    "edge_index": ei, "y": int(rng.randint(0, 3))})
+    return collate(graphs)
+
+
+@pytest.mark.parametrize("big_sizes,small", [((492,), 511), ((505, 470, 455), 60), ((512,) * 3 + (500,) * 4 + (450,) * 5, 200),
+                                             ((497,), 2), ((492, 300), 147)])
+def test_graphs_beyond_one_cta_are_split_over_a_cta_pair(big_sizes, small):
+    """COLLAB's largest graphs (up to 492 nodes) do not fit one CTA's shared memory in the conv5-fused
+    kernels: the plan gives them a CTA PAIR (mandatory split; more such graphs than pairs go round
+    by round).  Forward, loss and all 16 gradients of the fused path against the float64 oracle and
+    the unfused kernel sequence; bit-reproducible; the training step stays at 22 launches."""
+    cfg = CONFIGS["collab"]
+    batch = collab_batch_with_big_graphs(big_sizes, small, seed=sum(big_sizes))
+    count = batch.num_graphs
+    mx = int((batch.ptr[1:] - batch.ptr[:-1]).max())
+    assert mx == max(big_sizes)
+    assert ops.stack_fwd_conv5_supported(cfg.num_features, mx) and ops.stack_bwd_conv5_supported(cfg.num_features, mx)
+    ref, model = oracle_and_model(cfg, seed=3, train=True)
+    data = batch.to(DEV)
+    k = cfg.k
+    st_f, gr_f, perm_f, keep_f, xcat_f = step_kernels(model, data, k, True)
+    st_u, gr_u, perm_u, keep_u, xcat_u = step_kernels(model, data, k, False)
+    assert torch.equal(perm_f, perm_u) and torch.equal(xcat_f, xcat_u)
+    st_f2, gr_f2, *_ = step_kernels(model, data, k, True)
+    assert torch.equal(st_f, st_f2) and all(torch.equal(a, b_) for a, b_ in zip(gr_f, gr_f2)), "not reproducible"
+    rloss, rp, rx = oracle_gradients_from_our_perm(ref, batch, count, k, perm_f, keep_f)
+    assert (xcat_f.cpu().double() - rx).abs().max().item() <= ATOL
+    _, rperm = orc.sort_aggregation(rx, batch.batch, k, count, return_perm=True)
+    assert_perm_matches(perm_f.cpu().numpy(), rperm.numpy(), rx.numpy()[:, -1], batch.ptr.numpy(), k)
+    assert abs(float(st_f[0]) - float(rloss)) <= 1e-4 * max(1.0, abs(float(rloss)))
+    for pname, gt, gu in zip(PARAM_NAMES, gr_f, gr_u):
+        want = rp[pname].grad
+        scale = max(1e-3, float(want.abs().max()))
+        err = (gt.cpu().double().view_as(want) - want).abs().max().item()
+        assert err <= 2e-3 * scale, f"{pname}: vs float64 oracle {err:.3e} (scale {scale:.3e})"
+        if torch.equal(keep_f, keep_u):
+            erru = (gt.reshape(-1) - gu.reshape(-1)).abs().max().item()
+            assert erru <= 2e-3 * scale, f"{pname}: fused vs unfused {erru:.3e}"
+    tr = dg.FusedTrainer(model)
+    assert tr.supported(data)
+    before = ops.LAUNCHES.get("train_step", 0)
+    tr.step(data)
+    assert ops.LAUNCHES.get("train_step", 0) - before == 22
+
+
+@pytest.mark.parametrize("name,count", [("collab", 512), ("proteins", 128), ("collab", 3)])
+def test_backward_cluster_split_matches_the_plain_launch(name, count):
+    """KSB launched as clusters of two CTAs (largest graphs split over a pair: each CTA takes half of
+    the row tiles, the gradient rows cross through L2) against the plain launch: the same 16
+    gradients up to fp32 summation order (each CTA of a pair leaves its own partial sums)."""
+    from dgcnn_b200 import _lib
+    lib = _lib.load_library()
+    cfg = CONFIGS[name]
+    batch = make_batch(name, num_graphs=count, seed=78)
+    torch.manual_seed(1)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    data = batch.to(DEV)
+    outs = {}
+    try:
+        for pairs in (0, 1):
+            lib.dgcnn_stack_fwd_configure(pairs, 20)     # (aggressive threshold: several split graphs)
+            for fused in (True, False):
+                outs[(pairs, fused)] = step_kernels(model, data, cfg.k, fused, training=False)
+    finally:
+        lib.dgcnn_stack_fwd_configure(-1, 80)
+    for fused in (True, False):
+        st0, gr0, perm0, _, xcat0 = outs[(0, fused)]
+        st1, gr1, perm1, _, xcat1 = outs[(1, fused)]
+        assert torch.equal(perm0, perm1) and torch.equal(xcat0, xcat1) and torch.equal(st0, st1)
+        for pname, a, b_ in zip(PARAM_NAMES, gr0, gr1):
+            scale = max(1e-3, float(a.abs().max()))
+            assert (a - b_).abs().max().item() <= 2e-5 * scale, f"{pname} (fused={fused})"
+
+
 def test_training_with_and_without_the_conv5_fusion_agree():
     """Three optimisation steps of FusedTrainer (native one-call step and the Python sequence) with
     SURVEY 8f N2 on and off: same losses and parameters up to fp32 rounding; the fused step

@@ -77,12 +77,12 @@ def parse_args():
     ap.add_argument("--autograd", action="store_true",
                     help="step through torch autograd (Model + GradBucket + FlatAdam) instead of FusedTrainer")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--shards", default="independent", choices=["balanced", "independent", "same"],
-                    help="N > 1: how the global batch of bs*N graphs is split (balanced: dp.balanced_shards, "
-                         "every rank gets the same count and the same size profile; independent: every rank "
-                         "draws its own bs graphs -- the default: measured faster at N = 8, 0.451 against 0.472 ms, "
-                         "because the rank that is dealt the LARGEST graph of the 4096 loses the conv5 fusion and "
-                         "sets the pace; profiles/r02_scaling.md)")
+    ap.add_argument("--shards", default="balanced", choices=["balanced", "independent", "same"],
+                    help="N > 1: how the global batch of bs*N graphs is split (balanced, the default: "
+                         "dp.balanced_shards, every rank gets the same count and the same size profile; "
+                         "independent: every rank draws its own bs graphs; same: every rank the same batches, "
+                         "a diagnostic).  Measured at N = 8 after the cluster-pair split of large graphs: "
+                         "0.317 ms balanced, 0.318 ms independent (profiles/r02_scaling.md)")
     ap.add_argument("--seed-rank", type=int, default=-1,
                     help="diagnostic, N = 1: draw the batches rank R of a multi-GPU run would draw")
     ap.add_argument("--trace-exchange", default="",
@@ -426,8 +426,19 @@ def main():
         run_slot(i)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
+    # The sampler (NVML initialisation: milliseconds, different on every rank) is set up and started
+    # BEFORE the barrier: whatever a rank's host does between the barrier and its first launch is
+    # skew that the other ranks wait out inside the first timed step's gradient exchange (measured
+    # at N = 8: 1.5-3 ms in step 1, i.e. 75-150 us per step of a 20-40 step run;
+    # profiles/r02_scaling.md).
+    sync_token = torch.zeros(1, device=dev)
     with ClockSampler(local_rank) as clocks:
+        barrier()
+        if world > 1:
+            # device-side rendezvous on top of the host barrier: the collective completes on every
+            # GPU at the same moment, and each rank's timed steps are queued behind it -- the hosts
+            # leave dist.barrier() up to milliseconds apart, the GPUs now start together
+            dist.all_reduce(sync_token)
         wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()                              # evict the batch / weights from L2
@@ -442,11 +453,18 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
+    # where the time of a multi-rank run sits: the first timed step absorbs the ranks' skew after the
+    # barrier (every rank waits for the last one inside the exchange kernel); the rest is steady state
+    first_rest = torch.tensor([step_ms[0], sum(step_ms[1:]) / max(1, args.steps - 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(first_rest, op=dist.ReduceOp.MAX)
+    first_step_ms, steady_ms = (float(v) for v in first_rest.tolist())
     ranks_report = None
     if world > 1:
         # each rank's own view: its device time per step (the wait for the slowest rank inside the
         # exchange kernel included), its SM clock under load, the largest graph of each ring batch
         rank_report = {"rank": rank, "ms_per_step": round(sum(step_ms) / args.steps, 4),
+                "first_step_ms": round(step_ms[0], 4),
                 "sm_mhz": clocks.summary().get("sm_mhz"), "reasons": clocks.summary().get("reasons"),
                 "largest_graph_per_ring_batch": [hb.max_nodes for hb in host_batches],
                 "launches_per_step": launches_per_step}
@@ -821,6 +839,7 @@ def main():
                               "note": "same loop, host batch collated with int32 edge_index/batch "
                                       "(dgcnn_build_graph_i32): NOT the reference's int64 format; `e2e` is"},
         "e2e_resident_dataset": resident if world == 1 else resident_multi,
+        "first_timed_step_ms": first_step_ms, "ms_per_step_after_first": steady_ms,
         "per_rank": ranks_report,
         "params_equal_across_ranks": params_equal, "comm_status_per_rank": comm_status_all,
         "shards": ("balanced (dp.balanced_shards of a global batch of bs*N graphs)" if balanced else

@@ -24,7 +24,7 @@ for w in collab dd powerlaw proteins mutag; do
 done
 [ -s $G/bench_reference.json ] && tail -1 $G/bench_reference.json > $P/r02_bench_reference.json
 for n in 2 4 8; do
-  for w in collab powerlaw collab_indep collab_balanced; do
+  for w in collab powerlaw collab_indep collab_balanced collab_independent collab_same; do
     [ -s $G/bench_${w}_n$n.json ] && tail -1 $G/bench_${w}_n$n.json > $P/r02_bench_${w}_n$n.json
     [ -s $G/exchange_trace_${w}_n$n.json ] && python - <<PY
 import json
@@ -37,6 +37,9 @@ PY
     [ -s $G/${c}_n$n.log ] && grep -v "CUDAEvent\|Warning\|OMP_NUM\|\*\*\*\*" $G/${c}_n$n.log | tail -4 > $P/r02_${c}_n$n.log
   done
 done
+[ -s $G/ks_vs_largest.txt ] && cp $G/ks_vs_largest.txt $P/r02_ks_vs_largest.txt
+[ -s $G/resident_launches_warm.md ] && cp $G/resident_launches_warm.md $P/r02_launches_resident_step_warm.md
+[ -s $G/sanitize_initcheck_plain_zero.log ] && grep -E "SUMMARY|exit|sanitize workload|round-2 paths|Error" $G/sanitize_initcheck_plain_zero.log | head -20 > $P/r02_sanitize_initcheck_plain_zero.log
 for t in memcheck racecheck synccheck initcheck; do
   [ -s $G/sanitize_$t.log ] && grep -E "SUMMARY|exit|sanitize workload|round-2 paths|Error|Hazard" $G/sanitize_$t.log | head -20 > $P/r02_sanitize_$t.log
 done

@@ -345,11 +345,12 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     // (a graph split over a CTA pair: each CTA leaves the sums over ITS rows; db5 is rank 0's)
     const bool split = tm.split != 0;
     const int crank = split ? tm.rank : 0;
-    auto conv5_bias_grad = [&](float* sacc_) {
+    // (dh1v / argv: the graph's slab, staged in shared memory when it fits -- see phase 0)
+    auto conv5_bias_grad = [&](float* sacc_, const float* dh1v, const uint8_t* argv) {
         for (int c = warp; c < kC5b; c += nwarps) {
             float sb = 0.f;
             if (crank == 0)
-                for (int j = lane; j < L1; j += 32) sb += argg[c * L1 + j] != 2 ? dh1g[c * L1 + j] : 0.f;
+                for (int j = lane; j < L1; j += 32) sb += argv[c * L1 + j] != 2 ? dh1v[c * L1 + j] : 0.f;
             sb = warp_sum(sb);
             if (lane == 0) sacc_[GO.b5 + c] = sb;
         }
@@ -361,7 +362,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
         for (int idx = tid; idx < GO.total; idx += nthreads) sacc0[idx] = 0.f;
         if (conv5) {
             tm.sync_local();
-            conv5_bias_grad(sacc0);
+            conv5_bias_grad(sacc0, dh1g, argg);
         }
         return;
     }
@@ -426,10 +427,55 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     if (dup)
         for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr_t[base + j] - e0;
     float amax = 0.f;
+    // conv5: the graph's d(h1) / arg slab ([16][k/2] floats + bytes) is read three times below (the
+    // scale, the dz planes, db5) through dependent indices -- with 2-3 warps per small graph that
+    // was half of the graph's whole chain.  One coalesced copy into the P / dh planes' space (free
+    // until layer 4), everything else from shared memory.
+    const int slab = kC5b * L1;
+    const bool staged = conv5 && slab * 5 <= L.DZ - L.P;
+    const float* dh1v = dh1g;
+    const uint8_t* argv = argg;
+    if (staged) {
+        uint32_t* stg = reinterpret_cast<uint32_t*>(sm + L.P);
+        // (both slabs are multiples of 16 bytes per graph and 16-byte aligned: one round of 16-byte loads)
+        const uint4* s4 = reinterpret_cast<const uint4*>(dh1g);
+        const uint4* a4 = reinterpret_cast<const uint4*>(argg);
+        uint4* d4 = reinterpret_cast<uint4*>(stg);
+        const int nd = slab >> 2, na = slab >> 4, nq = nd + na;
+        const bool al = ((reinterpret_cast<uintptr_t>(dh1g) | reinterpret_cast<uintptr_t>(argg)) & 15) == 0;
+        if (al) {
+            for (int i0 = tid; i0 < nq; i0 += nthreads * 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = i0 + u * nthreads;
+                    v[u] = idx < nd ? s4[idx] : (idx < nq ? a4[idx - nd] : make_uint4(0u, 0u, 0u, 0u));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = i0 + u * nthreads;
+                    if (idx < nq) d4[idx] = v[u];
+                }
+            }
+        } else {
+            load_bitmap<8>(reinterpret_cast<const uint32_t*>(dh1g), stg, slab, tid, nthreads);
+            load_bitmap<8>(reinterpret_cast<const uint32_t*>(argg), stg + slab, slab >> 2, tid, nthreads);
+        }
+        dh1v = reinterpret_cast<const float*>(stg);
+        argv = reinterpret_cast<const uint8_t*>(stg + slab);
+        tm.sync_local();
+    }
+    auto scatter_ranks = [&]() {                         // inverse permutation of the kept rows
+        for (int r = tid; r < keep; r += nthreads) {
+            const int node = perm_g[r] - base;
+            if ((unsigned)node < (unsigned)n) rank[node] = r;
+        }
+    };
+    if (staged) scatter_ranks();                         // (rank[] was initialised before the barrier above)
     if (conv5) {
         // |pooled gradient| <= max |dz| * max_i sum_c |W5[c][i]|
-        for (int idx = tid; idx < kC5b * L1; idx += nthreads)
-            if (argg[idx] != 2) amax = fmaxf(amax, fabsf(dh1g[idx]));
+        for (int idx = tid; idx < slab; idx += nthreads)
+            if (argv[idx] != 2) amax = fmaxf(amax, fabsf(dh1v[idx]));
         amax *= w5x[kC5b];
     } else {   // sixteen loads in flight per thread: the sweep is pure memory latency
         const int total = keep * kCat;
@@ -454,10 +500,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(DGCNN_FULL_MASK, amax, o));
     if (lane == 0) red0[warp] = amax;
     tm.sync_local();
-    for (int r = tid; r < keep; r += nthreads) {
-        const int node = perm_g[r] - base;
-        if ((unsigned)node < (unsigned)n) rank[node] = r;
-    }
+    if (!staged) scatter_ranks();
     amax = 0.f;
     for (int w = 0; w < nwarps; ++w) amax = fmaxf(amax, red0[w]);
     tm.sync_local();
@@ -480,20 +523,22 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             const int ch = idx / S, i = idx - ch * S;
             float v = 0.f;
             const int r = i < n ? rank[i] : -1;
-            if (r >= 0 && (r >> 1) < L1 && argg[ch * L1 + (r >> 1)] == (r & 1)) v = dh1g[ch * L1 + (r >> 1)];
+            if (r >= 0 && (r >> 1) < L1 && argv[ch * L1 + (r >> 1)] == (r & 1)) v = dh1v[ch * L1 + (r >> 1)];
             store_split(DZ, DZ + kC5b * S, idx, v * scale);
         }
-        conv5_bias_grad(sacc);
+        conv5_bias_grad(sacc, dh1v, argv);
         tm.sync_local();
     }
     KSB_TRACE(1);
     // ---- layer 4 (32 -> 1) --------------------------------------------------------------------
+    float* x4s = reinterpret_cast<float*>(sm + L.DH);    // conv5: x_4 of every node (the dh planes are free until layer 3)
     {
         float dbp = 0.f;
         for (int i = tid; i < np; i += nthreads) {
             float v = 0.f;
             if (i < n) {
                 const float y = xc[(int64_t)i * p.ldc + 3 * kHid];
+                if (conv5) x4s[i] = y;                   // (for dW5[:, 96] below)
                 float gy;
                 if (conv5) {                             // dz . W5[:, 96]
                     float sg = 0.f;
@@ -577,7 +622,8 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
     const uint32_t* dz32[2] = {reinterpret_cast<const uint32_t*>(DZ),
                                reinterpret_cast<const uint32_t*>(DZ + kC5b * S)};
     if (conv5) {
-        // pooled gradient of the x3 slice, dz W5[:, 64..95], straight into G (unscaled)
+        // G3[i][k] = dh4[i] w4[k] + pooled gradient of the x3 slice (dz W5[:, 64..95], unscaled),
+        // from the tile's registers straight into G
         const int g = lane >> 2, t = lane & 3;
         for (int mt = t_lo + warp; mt < t_hi; mt += nwarps) {
             float gz[4][4];
@@ -586,24 +632,26 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
             for (int half = 0; half < 2; ++half) {
                 const int row = mt * 16 + g + 8 * half;
                 if (row >= n) continue;
+                const float h = hv[row];
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float2 w4v = *reinterpret_cast<const float2*>(w4s + nt * 8 + 2 * t);
                     *reinterpret_cast<float2*>(Gw + row * kHid + nt * 8 + 2 * t) =
-                        make_float2(gz[nt][2 * half] * inv_scale, gz[nt][2 * half + 1] * inv_scale);
+                        make_float2(fmaf(h, w4v.x, gz[nt][2 * half] * inv_scale),
+                                    fmaf(h, w4v.y, gz[nt][2 * half + 1] * inv_scale));
+                }
             }
         }
         // dW5[c][96] = sum_i dz[i][c] x4[i]
         for (int ch = warp; ch < kC5b; ch += nwarps) {
             float sw = 0.f;
             for (int i = r_lo + lane; i < n_hi; i += 32)
-                sw = fmaf(__half2float(DZ[ch * S + i]) + __half2float(DZ[(kC5b + ch) * S + i]),
-                          xc[(int64_t)i * p.ldc + 3 * kHid], sw);
+                sw = fmaf(__half2float(DZ[ch * S + i]) + __half2float(DZ[(kC5b + ch) * S + i]), x4s[i], sw);
             sw = warp_sum(sw);
             if (lane == 0) sacc[GO.w5 + ch * kCat + 3 * kHid] = sw * inv_scale;
         }
-        tm.sync_local();
     }
-    {   // dW4[k] += sum_i dh4[i] x3[i][k];  G3[i][k] = dh4[i] w4[k] + pooled gradient of x3
+    {   // dW4[k] += sum_i dh4[i] x3[i][k];  G3[i][k] = dh4[i] w4[k] + pooled gradient of x3 (conv5: above)
         float dwp = 0.f;
         const float w4k = w4s[lane];
         for (int i0 = r_lo + warp; i0 < r_hi; i0 += 8 * nwarps) {     // eight rows in flight per warp
@@ -614,9 +662,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 xv[u] = 0.f; gp[u] = 0.f;
                 if (i < n_hi) {
                     xv[u] = xc[(int64_t)i * p.ldc + 2 * kHid + lane];
-                    if (conv5) {
-                        gp[u] = Gw[i * kHid + lane];
-                    } else {
+                    if (!conv5) {
                         const int r = rank[i];
                         if (r >= 0) gp[u] = dp[r * kCat + 2 * kHid + lane];
                     }
@@ -628,7 +674,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
                 if (i < n_hi) {
                     const float h = hv[i];
                     dwp = fmaf(h, xv[u], dwp);
-                    Gw[i * kHid + lane] = fmaf(h, w4k, gp[u]);
+                    if (!conv5) Gw[i * kHid + lane] = fmaf(h, w4k, gp[u]);
                 }
                 if (conv5 && i < r_hi) xin3[lane * S + i] = xv[u];   // (zero beyond n: NaN-free MMA padding)
             }

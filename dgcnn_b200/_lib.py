@@ -183,6 +183,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,
                                        c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "dgcnn_train_step_configure": (None, [c_int32]),
+    "dgcnn_train_step_configure_maps": (None, [c_int32]),
     "dgcnn_train_step_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32, c_int32,
                                                     c_int64]),
     "dgcnn_train_step_num_params": (c_int64, [c_int32, c_int32, c_int32]),

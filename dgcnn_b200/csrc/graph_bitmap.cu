@@ -104,8 +104,8 @@ k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
          int64_t n_nodes, int max_nodes, const int32_t* __restrict__ bmoff,
          uint32_t* __restrict__ bitmap0, uint32_t* __restrict__ bitmap1,
          int32_t* __restrict__ gflags0, int32_t* __restrict__ gflags1,
-         const int32_t* gate_word, int gate_mask) {
-    const bool second = blockIdx.y != 0;
+         const int32_t* gate_word, int gate_mask, int only_second) {
+    const bool second = only_second || blockIdx.y != 0;
     if (second && gate_word && !(*gate_word & gate_mask)) return;
     const int32_t* __restrict__ rowptr = second ? rowptr1 : rowptr0;
     const int32_t* __restrict__ col = second ? col1 : col0;
@@ -231,15 +231,19 @@ extern "C" int64_t dgcnn_graph_fragmap_words(int64_t num_nodes, int64_t num_grap
     return (num_nodes / 16 + num_graphs) * ((tmax + 3) / 4) * 32 + 32;
 }
 
-extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
-                                   const int32_t* rowptr_t, const int32_t* col_t,
-                                   const int32_t* gptr, const int64_t* batch, const int32_t* batch32,
-                                   int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
-                                   uint32_t* bitmap, uint32_t* bitmap_t, int64_t bitmap_words,
-                                   int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,
-                                   uint32_t* fragmap, int64_t fragmap_words, int32_t* fgoff,
-                                   const int32_t* gorder, int32_t* gdesc,
-                                   const int32_t* gate_word, int32_t gate_mask, void* stream) {
+// lazy = 1 (internal, the one-call training step): only what the fused forward kernel cannot do for
+// itself -- the offsets / work descriptors and, for a batch K0 found asymmetric, the bitmap of
+// A_hat^T; the forward maps (fragmap, gflags bit 0) are then written by dgcnn_stack_fwd* itself
+// (StackFwdParams::lazy) and `bitmap` stays untouched.
+int dgcnn_build_bitmaps_impl(const int32_t* rowptr, const int32_t* col,
+                             const int32_t* rowptr_t, const int32_t* col_t,
+                             const int32_t* gptr, const int64_t* batch, const int32_t* batch32,
+                             int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                             uint32_t* bitmap, uint32_t* bitmap_t, int64_t bitmap_words,
+                             int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,
+                             uint32_t* fragmap, int64_t fragmap_words, int32_t* fgoff,
+                             const int32_t* gorder, int32_t* gdesc,
+                             const int32_t* gate_word, int32_t gate_mask, void* stream, int lazy) {
     if (num_nodes < 0 || num_graphs < 0 || max_nodes < 1) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_graphs == 0) return DGCNN_OK;
     if (!rowptr || !gptr || !bitmap || !bmoff || !gflags) return DGCNN_ERR_INVALID_ARGUMENT;
@@ -256,8 +260,13 @@ extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
     }
     if (gdesc && (!fragmap || ((uintptr_t)gdesc & 15))) return DGCNN_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (lazy && (!fragmap || !gdesc)) return DGCNN_ERR_INVALID_ARGUMENT;
     // padding rows / bits must be zero; one memset when the two bitmaps are adjacent
-    if (transposed && bitmap_t == bitmap + need) {
+    if (lazy) {
+        if (transposed &&
+            cudaMemsetAsync(bitmap_t, 0, sizeof(uint32_t) * (size_t)need, st) != cudaSuccess)
+            return DGCNN_ERR_CUDA;
+    } else if (transposed && bitmap_t == bitmap + need) {
         if (cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * 2 * (size_t)need, st) != cudaSuccess)
             return DGCNN_ERR_CUDA;
     } else {
@@ -271,11 +280,18 @@ extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
                                     fragmap ? fgoff : nullptr, gflags, gflags_t, gorder,
                                     reinterpret_cast<int4*>(gdesc));
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    if (num_nodes > 0) {
+    if (num_nodes > 0 && lazy) {
+        if (transposed) {                            // (returns at once unless K0 raised the gate)
+            k0b_fill<<<dim3((unsigned)grid_for(num_nodes, 8, 8), 1), 256, 0, st>>>(
+                rowptr, col, rowptr_t, col_t, gptr, batch, batch32, (int)num_graphs, num_nodes, (int)max_nodes,
+                bmoff, bitmap, bitmap_t, gflags, gflags_t, gate_word, gate_mask, 1);
+            DGCNN_RETURN_IF_LAUNCH_FAILED();
+        }
+    } else if (num_nodes > 0) {
         dim3 grid((unsigned)grid_for(num_nodes, 8, 8), transposed ? 2 : 1);
         k0b_fill<<<grid, 256, 0, st>>>(rowptr, col, rowptr_t, col_t, gptr, batch, batch32, (int)num_graphs,
                                        num_nodes, (int)max_nodes, bmoff, bitmap, bitmap_t, gflags,
-                                       gflags_t, gate_word, gate_mask);
+                                       gflags_t, gate_word, gate_mask, 0);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         if (fragmap && gdesc) {
             k0b_fragments<<<dim3((unsigned)grid_for(num_graphs, 1, 8), 4), 256, 0, st>>>(
@@ -285,4 +301,18 @@ extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
         }
     }
     return DGCNN_OK;
+}
+
+extern "C" int dgcnn_build_bitmaps(const int32_t* rowptr, const int32_t* col,
+                                   const int32_t* rowptr_t, const int32_t* col_t,
+                                   const int32_t* gptr, const int64_t* batch, const int32_t* batch32,
+                                   int64_t num_nodes, int64_t num_graphs, int64_t max_nodes,
+                                   uint32_t* bitmap, uint32_t* bitmap_t, int64_t bitmap_words,
+                                   int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,
+                                   uint32_t* fragmap, int64_t fragmap_words, int32_t* fgoff,
+                                   const int32_t* gorder, int32_t* gdesc,
+                                   const int32_t* gate_word, int32_t gate_mask, void* stream) {
+    return dgcnn_build_bitmaps_impl(rowptr, col, rowptr_t, col_t, gptr, batch, batch32, num_nodes, num_graphs,
+                                    max_nodes, bitmap, bitmap_t, bitmap_words, bmoff, gflags, gflags_t, fragmap,
+                                    fragmap_words, fgoff, gorder, gdesc, gate_word, gate_mask, stream, 0);
 }

@@ -41,6 +41,11 @@ struct StackFwdParams {
     int split_pct;      // split a graph whose cost exceeds this percentage of an SM's fair share
     int plain_zero;     // 1: pad `pooled` with ordinary stores instead of TMA bulk stores (sanitizer runs:
                         // compute-sanitizer initcheck does not see memory written by the async proxy)
+    // Lazy adjacency maps (the one-call training step): K0b only wrote the descriptors; every team
+    // expands its graph's CSR rows into the fragment-major map in shared memory itself and EXPORTS
+    // it (fragmap_w + fgoff, gflags_w bit 0 = duplicate edges) for the backward kernel.
+    int lazy;
+    uint32_t* fragmap_w; int32_t* gflags_w;
 };
 
 

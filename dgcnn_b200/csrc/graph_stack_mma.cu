@@ -477,9 +477,22 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, Team& tm,
     const int g = lane >> 2, t = lane & 3;
 
     // ---- phase 0, one DRAM round trip: adjacency fragments (K0b), coefficients, inputs ----
-    c.dup = (p.gflags[gi] & 1) != 0;                 // multigraph: walk the CSR instead
-    load_bitmap<8>(p.fragmap + e.fgoff + t0 * c.G * 32, fbm + t0 * c.G * 32, (t1 - t0) * c.G * 32, tid,
-                   nthreads);                            // (only the CTA's own row tiles)
+    const bool lazy = p.lazy != 0;
+    int* dupflag = reinterpret_cast<int*>(vpl) + 23;     // lazy: "this graph has duplicate edges" (wmax uses [0, 20))
+    int e0 = 0;
+    if (!lazy) {
+        c.dup = (p.gflags[gi] & 1) != 0;             // multigraph: walk the CSR instead
+        load_bitmap<8>(p.fragmap + e.fgoff + t0 * c.G * 32, fbm + t0 * c.G * 32, (t1 - t0) * c.G * 32, tid,
+                       nthreads);                        // (only the CTA's own row tiles)
+    } else {
+        // no K0b maps: clear the own tiles' words and fetch the graph's row pointers; the rows are
+        // expanded below, once these are in shared memory
+        uint32_t* own = fbm + t0 * c.G * 32;
+        for (int idx = tid; idx < (t1 - t0) * c.G * 32; idx += nthreads) own[idx] = 0u;
+        e0 = p.rowptr[base];
+        for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
+        if (tid == 0) *dupflag = 0;
+    }
     for (int j = tid; j < np; j += nthreads) {
         const float d = j < n ? p.dis[base + j] : 0.f;
         cs[j] = j < n ? col_coef(d, p.norm) : 0.f;
@@ -497,13 +510,77 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, Team& tm,
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(DGCNN_FULL_MASK, m, o));
         if (lane == 0) wmax[warp] = m;
     }
-    int e0 = 0;
-    if (c.dup) {
+    if (!lazy && c.dup) {
         e0 = p.rowptr[base];
         for (int j = tid; j <= n; j += nthreads) rp[j] = p.rowptr[base + j] - e0;
     }
     c.col_g = p.col + e0;
+    if (lazy) {
+        // CSR rows -> fragment-major bits (the layout k0b_fragments writes: graph_bitmap.cu): one warp
+        // per own row, 32 edges per step, shared-memory atomics; word (mt, grp, lane = 4 (r & 7) + t),
+        // bit m + 16 (column odd), m = 4 q + (row >= 8) + 2 (column >= 8) inside the 16 x 16 block.
+        // Duplicate edges are adjacent in a K0 row: such a graph walks its CSR instead (c.dup).
+        tm.sync_local();
+        const int* col_g = c.col_g;
+        bool dup = false;
+        const int r_hi = min(t1 * 16, n);
+        auto set_bit = [&](int r, int j) {
+            const int kt = j >> 4, cc = j & 15;
+            atomicOr(fbm + ((r >> 4) * c.G + (kt >> 2)) * 32 + 4 * (r & 7) + ((cc & 7) >> 1),
+                     1u << (4 * (kt & 3) + ((r >> 3) & 1) + 2 * (cc >> 3) + 16 * (cc & 1)));
+        };
+        // A warp takes eight consecutive rows at a time: their edges are one contiguous run of col[],
+        // read 8 x 32 at a time with every load in flight (a row at a time was one L2 round trip per
+        // row); the row of an edge = how many of the group's row boundaries lie at or below it.
+        constexpr int R = 8, U = 8;
+        for (int r0 = t0 * 16 + warp * R; r0 < r_hi; r0 += nwarps * R) {
+            const int rows = min(R, r_hi - r0);
+            const int beg = rp[r0], end = rp[r0 + rows];
+            int bnd[R - 1];
+#pragma unroll
+            for (int i = 1; i < R; ++i) bnd[i - 1] = i < rows ? rp[r0 + i] : 0x7fffffff;
+            int prev_j = -1, prev_r = -1;                         // last edge of the previous chunk
+            for (int c0 = beg; c0 < end; c0 += 32 * U) {
+                int cv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int ee = c0 + 32 * u + lane;
+                    cv[u] = ee < end ? col_g[ee] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (c0 + 32 * u >= end) break;                // (warp-uniform)
+                    const int ee = c0 + 32 * u + lane;
+                    int j = -1, r = r0;
+                    if (ee < end) {
+                        const unsigned tcol = (unsigned)(cv[u] - base);
+                        if (tcol < (unsigned)n) j = (int)tcol;   // edges leaving the graph are ignored (K0 flags them)
+#pragma unroll
+                        for (int i = 0; i < R - 1; ++i) r += ee >= bnd[i];
+                    }
+                    int lj = __shfl_up_sync(DGCNN_FULL_MASK, j, 1), lr = __shfl_up_sync(DGCNN_FULL_MASK, r, 1);
+                    if (lane == 0) { lj = prev_j; lr = prev_r; }
+                    if (j >= 0 && j == lj && r == lr) dup = true; // duplicates are adjacent in a K0 row
+                    prev_j = __shfl_sync(DGCNN_FULL_MASK, j, 31);
+                    prev_r = __shfl_sync(DGCNN_FULL_MASK, r, 31);
+                    if (j >= 0) set_bit(r, j);
+                }
+            }
+            if (lane < rows) set_bit(r0 + lane, r0 + lane);       // the self loops
+        }
+        if (__any_sync(DGCNN_FULL_MASK, dup) && lane == 0) *dupflag = 1;
+    }
     tm.sync();            // (split: also tells that the peer CTA runs -- its shared memory may be written)
+    if (lazy) {
+        // (split: either half may hold the duplicates; the peer's flag is final after the barrier and
+        // its slot is not reused before the next exchange, which needs this CTA)
+        c.dup = *dupflag != 0 || (split && *cg::this_cluster().map_shared_rank(dupflag, peer) != 0);
+        // export for the backward kernel (fire and forget)
+        uint32_t* out = p.fragmap_w + e.fgoff + t0 * c.G * 32;
+        const uint32_t* own = fbm + t0 * c.G * 32;
+        for (int idx = tid; idx < (t1 - t0) * c.G * 32; idx += nthreads) out[idx] = own[idx];
+        if (c.dup && tid == 0 && rank == 0) atomicOr(p.gflags_w + gi, 1);
+    }
     KS_TRACE(1);
 
     float pow2 = 1.f;
@@ -897,6 +974,12 @@ int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const
                         cudaStream_t st);
 int dgcnn_stack_fwd_fma_supported(int32_t num_features, int64_t max_nodes);
 
+// The next dgcnn_stack_fwd / dgcnn_stack_fwd_conv5 call of this thread's library state fills the
+// adjacency maps itself (StackFwdParams::lazy).  Internal: train_step.cu pairs it with
+// dgcnn_build_bitmaps_impl(.., lazy = 1); `fragmap` / `gflags` are then OUTPUTS of the forward call.
+static int g_next_lazy = 0;
+void dgcnn_stack_fwd_next_lazy(int on) { g_next_lazy = on; }
+
 static int64_t* g_trace = nullptr;
 extern "C" void dgcnn_stack_fwd_set_trace(int64_t* device_buffer) { g_trace = device_buffer; }
 
@@ -997,6 +1080,9 @@ static int stack_fwd_impl(const float* x, int64_t ldx, int32_t num_features,
     p.gdesc = gdesc; p.counter = counter; p.status = status;
     p.trace = g_trace;
     p.w5 = w5; p.b5 = b5; p.h1 = h1; p.arg = arg;
+    p.lazy = g_next_lazy;                             // (one-call training step: dgcnn_stack_fwd_next_lazy)
+    g_next_lazy = 0;
+    p.fragmap_w = const_cast<uint32_t*>(fragmap); p.gflags_w = const_cast<int32_t*>(gflags);
     // one CTA per SM with (almost) all of its shared memory: 4 quad slices + the weights
     const size_t smem = (size_t)al16(shared_layout(p.f, conv5).total) + (size_t)kQuads * quad_bytes(p.f, conv5);
     if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -14,6 +14,27 @@
 // sequence (A/B timing, tests).
 static int g_fuse_conv5 = -1;
 extern "C" void dgcnn_train_step_configure(int32_t fuse_conv5) { g_fuse_conv5 = fuse_conv5 < 0 ? -1 : (fuse_conv5 != 0); }
+// Lazy adjacency maps: K0b shrinks to the offsets / descriptors (and the gated A_hat^T bitmap of an
+// asymmetric batch); the forward kernel expands each graph's CSR rows into its fragment map itself
+// and exports it for the backward kernel -- two launches and one pass over col[] less per step.
+// dgcnn_train_step_configure_maps(0) or DGCNN_LAZY_MAPS=0 keeps the full K0b.
+static int g_lazy_maps = -1;
+extern "C" void dgcnn_train_step_configure_maps(int32_t lazy) { g_lazy_maps = lazy < 0 ? -1 : (lazy != 0); }
+static bool lazy_maps_enabled() {
+    if (g_lazy_maps < 0) {
+        const char* env = getenv("DGCNN_LAZY_MAPS");
+        g_lazy_maps = !(env && env[0] == '0');
+    }
+    return g_lazy_maps != 0;
+}
+void dgcnn_stack_fwd_next_lazy(int on);                  // graph_stack_mma.cu
+int dgcnn_build_bitmaps_impl(const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t,
+                             const int32_t* gptr, const int64_t* batch, const int32_t* batch32, int64_t num_nodes,
+                             int64_t num_graphs, int64_t max_nodes, uint32_t* bitmap, uint32_t* bitmap_t,
+                             int64_t bitmap_words, int32_t* bmoff, int32_t* gflags, int32_t* gflags_t,
+                             uint32_t* fragmap, int64_t fragmap_words, int32_t* fgoff, const int32_t* gorder,
+                             int32_t* gdesc, const int32_t* gate_word, int32_t gate_mask, void* stream, int lazy);
+
 static bool fuse_conv5_enabled() {
     if (g_fuse_conv5 < 0) {
         const char* env = getenv("DGCNN_FUSE_CONV5");
@@ -211,11 +232,14 @@ int step_after_build(const StepArgs& t, const StepBuffers& s, const float* x, in
     float* stats = t.grads + n_params;                // [sum of NLL, #correct] ride the all-reduce
     const int bwd_kind = dgcnn_stack_bwd_supported(F, t.max_nodes);   // 1 MMA, 2 FMA only
 
+    // (the FMA backward fallback reads the row bitmaps: full K0b then)
+    const bool lazy = !maps_ready && bwd_kind == 1 && lazy_maps_enabled();
     if (!maps_ready)                                  // (a resident data set hands K0b's outputs over)
-        DGCNN_TRY(dgcnn_build_bitmaps(s.rowptr, s.col, s.rowptr_t, s.col_t, s.gptr, batch64, batch32, N, B,
-                                      t.max_nodes, s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags,
-                                      s.gflags_t, s.fragmap, s.fm_words, s.fgoff, s.gorder, s.gdesc,
-                                      t.graph_status, DGCNN_GRAPH_GENERIC, stream));
+        DGCNN_TRY(dgcnn_build_bitmaps_impl(s.rowptr, s.col, s.rowptr_t, s.col_t, s.gptr, batch64, batch32, N, B,
+                                           t.max_nodes, s.bitmap, s.bitmap_t, s.bm_words, s.bmoff, s.gflags,
+                                           s.gflags_t, s.fragmap, s.fm_words, s.fgoff, s.gorder, s.gdesc,
+                                           t.graph_status, DGCNN_GRAPH_GENERIC, stream, lazy ? 1 : 0));
+    dgcnn_stack_fwd_next_lazy(lazy ? 1 : 0);          // the forward call below fills fragmap / gflags itself
     if (step_fuses_conv5(F, t.max_nodes)) {
         // N2: KS emits h1 / arg, the tail starts at conv6, its backward stops at d(h1), KSB does the
         // rest and writes the ten gradients g[0..9] (GraphConv + conv5: one contiguous slice)

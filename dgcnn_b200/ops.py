@@ -48,6 +48,17 @@ def set_fuse_conv5(enabled: bool) -> None:
     _lib.load_library().dgcnn_train_step_configure(int(FUSE_CONV5))
 
 
+LAZY_MAPS = os.environ.get("DGCNN_LAZY_MAPS", "1") != "0"
+
+
+def set_lazy_maps(enabled: bool) -> None:
+    """dgcnn_train_step: let the fused forward kernel build its adjacency maps itself (default on;
+    K0b then only writes the offsets / descriptors: one launch less, bit-identical results)."""
+    global LAZY_MAPS
+    LAZY_MAPS = bool(enabled)
+    _lib.load_library().dgcnn_train_step_configure_maps(int(LAZY_MAPS))
+
+
 def conv5_fusable(num_features: int, max_nodes: int) -> bool:
     return (FUSE_CONV5 and STACK_VARIANT == STACK_MMA and stack_fwd_conv5_supported(num_features, max_nodes)
             and stack_bwd_conv5_supported(num_features, max_nodes))

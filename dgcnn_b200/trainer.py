@@ -306,5 +306,9 @@ class FusedTrainer:
         if rc == -2:                                       # DGCNN_ERR_UNSUPPORTED: graphs too large for KS / KSB
             return False
         _lib.check(rc, "train_step")
-        ops.LAUNCHES["train_step"] = ops.LAUNCHES.get("train_step", 0) + (22 if ops.conv5_fusable(f, mx) else 26)
+        # status, K0 (3), K0b (3; lazy maps: 2), KS, tail forward (3) and backward (7), KSB (2), Adam (2);
+        # without the conv5 fusion four more (conv5 forward / backward, SortPool gradient)
+        lazy = ops.LAZY_MAPS and int(lib.dgcnn_stack_bwd_supported(int(f), int(mx))) == 1
+        ops.LAUNCHES["train_step"] = ops.LAUNCHES.get("train_step", 0) + \
+            (22 if ops.conv5_fusable(f, mx) else 26) - (1 if lazy else 0)
         return True

@@ -491,6 +491,11 @@ int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg, float* exp
  * the batch fits (dgcnn_stack_fwd_conv5_supported / dgcnn_stack_bwd_conv5_supported); 0 keeps the
  * unfused sequence; -1 re-reads the environment. */
 void dgcnn_train_step_configure(int32_t fuse_conv5);
+/* Lazy adjacency maps of dgcnn_train_step (host-fed batches): 1 (default, also DGCNN_LAZY_MAPS unset)
+ * lets the fused forward kernel expand every graph's CSR rows into its fragment map in shared memory
+ * and export it for the backward kernel, so that K0b shrinks to the offsets / descriptors; 0 runs the
+ * full K0b (dgcnn_build_bitmaps) first; -1 re-reads the environment.  Results are bit-identical. */
+void dgcnn_train_step_configure_maps(int32_t lazy);
 size_t dgcnn_train_step_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t num_graphs,
                                         int32_t num_features, int32_t k, int32_t num_classes,
                                         int64_t max_nodes);

@@ -362,6 +362,7 @@ __device__ __forceinline__ void load_bias(const float* __restrict__ bias, int t,
 // the two CTAs of a cluster together: CTA `tm.rank` owns the row tiles [t0, t1), every plane /
 // key / order store of its rows also goes into the peer's shared memory, and the team barrier
 // is the cluster barrier.
+template <bool LAZY>
 __device__ __forceinline__ void process_graph(const StackFwdParams& p, Team& tm, const PlanEntry& e,
                                               const unsigned char* shraw) {
     const int tid = tm.tid, lane = tm.lane, warp = tm.warp;
@@ -477,7 +478,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, Team& tm,
     const int g = lane >> 2, t = lane & 3;
 
     // ---- phase 0, one DRAM round trip: adjacency fragments (K0b), coefficients, inputs ----
-    const bool lazy = p.lazy != 0;
+    constexpr bool lazy = LAZY;                          // (a kernel of its own: StackFwdParams::lazy)
     int* dupflag = reinterpret_cast<int*>(vpl) + 23;     // lazy: "this graph has duplicate edges" (wmax uses [0, 20))
     int e0 = 0;
     if (!lazy) {
@@ -827,6 +828,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, Team& tm,
 }
 
 // The CTA's graphs and their teams: plan_pass() in graph_mma.cuh.
+template <bool LAZY>
 __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ PlanEntry s_plan[kMaxTeams];
@@ -949,7 +951,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdP
                     p.trace[(int64_t)e.gi * 16 + 13] = cta_c1;       // plan + weights done
                     p.trace[(int64_t)e.gi * 16 + 14] = cta_c2;       // padding rows zeroed, team starts
                 }
-                process_graph(p, tm, e, smraw);
+                process_graph<LAZY>(p, tm, e, smraw);
                 xparity = tm.xparity;
             }
         }
@@ -1003,7 +1005,8 @@ static int pairs_enabled() {
         if (pct && atoi(pct) > 0) g_split_pct = atoi(pct);
         ok = !(env && env[0] == '0');
     }
-    if (ok) ok = cluster_pairs_fit(stack_fwd_mma_kernel, kFwdThreads, (size_t)(kSmemBudget - 1024));
+    if (ok) ok = cluster_pairs_fit(stack_fwd_mma_kernel<false>, kFwdThreads, (size_t)(kSmemBudget - 1024)) &&
+                 cluster_pairs_fit(stack_fwd_mma_kernel<true>, kFwdThreads, (size_t)(kSmemBudget - 1024));
     g_pairs_ok = ok;
     return ok;
 }
@@ -1085,7 +1088,8 @@ static int stack_fwd_impl(const float* x, int64_t ldx, int32_t num_features,
     p.fragmap_w = const_cast<uint32_t*>(fragmap); p.gflags_w = const_cast<int32_t*>(gflags);
     // one CTA per SM with (almost) all of its shared memory: 4 quad slices + the weights
     const size_t smem = (size_t)al16(shared_layout(p.f, conv5).total) + (size_t)kQuads * quad_bytes(p.f, conv5);
-    if (cudaFuncSetAttribute(stack_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    auto kernel = p.lazy ? stack_fwd_mma_kernel<true> : stack_fwd_mma_kernel<false>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
     p.pairs = pairs_enabled();
@@ -1107,10 +1111,10 @@ static int stack_fwd_impl(const float* x, int64_t ldx, int32_t num_features,
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFwdThreads);
         cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, stack_fwd_mma_kernel, p) != cudaSuccess) return DGCNN_ERR_CUDA;
+        if (cudaLaunchKernelEx(&cfg, kernel, p) != cudaSuccess) return DGCNN_ERR_CUDA;
     } else {
         if (grid > num_graphs) grid = num_graphs;
-        stack_fwd_mma_kernel<<<(unsigned)grid, kFwdThreads, smem, st>>>(p);
+        kernel<<<(unsigned)grid, kFwdThreads, smem, st>>>(p);
     }
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;

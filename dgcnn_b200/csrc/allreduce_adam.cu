@@ -58,6 +58,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 __global__ void __launch_bounds__(kArThreads)
 allreduce_adam_kernel(AllreduceAdamParams a) {
+    DGCNN_PDL_WAIT();
     const int64_t e = *a.epoch;
     const int parity = (int)(e & 1);
     const bool tracer = a.trace && blockIdx.x == 0 && threadIdx.x == 0;
@@ -156,6 +157,7 @@ allreduce_adam_kernel(AllreduceAdamParams a) {
 }
 
 __global__ void allreduce_adam_bump(int64_t* step, int64_t* epoch, const int32_t* status) {
+    DGCNN_PDL_WAIT();
     if (status && (*status & DGCNN_COMM_TIMEOUT)) return;         // the step was abandoned
     *step += 1;
     *epoch += 1;
@@ -242,9 +244,9 @@ extern "C" int dgcnn_allreduce_adam(float* params, float* grads, float* exp_avg,
     a.world = world; a.rank = rank; a.status = status;
     a.trace = g_ar_trace;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    allreduce_adam_kernel<<<kArCtas, kArThreads, 0, st>>>(a);
+    DGCNN_LAUNCH(allreduce_adam_kernel, kArCtas, kArThreads, 0, st, a);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    allreduce_adam_bump<<<1, 1, 0, st>>>(step, epoch, status);
+    DGCNN_LAUNCH(allreduce_adam_bump, 1, 1, 0, st, step, epoch, status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

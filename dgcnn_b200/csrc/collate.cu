@@ -180,6 +180,7 @@ __device__ bool build_tables(const CollateArgs& a, const Tables& t, unsigned lon
 // Plan kernel of the large-batch path: one CTA writes the tables and the verdict to the workspace.
 __global__ void __launch_bounds__(kPlanThreads)
 n1_plan(const CollateArgs a) {
+    DGCNN_PDL_WAIT();
     __shared__ unsigned long long red[2][33];
     const Tables t = carve_tables(a.ws_tables, a.num_graphs);
     const bool ok = build_tables(a, t, red);
@@ -202,6 +203,7 @@ __device__ __forceinline__ int owner_of(const int32_t* table, int count, int v) 
 template <bool kFused>
 __global__ void __launch_bounds__(kGatherThreads, 4)
 n1_gather(const CollateArgs a) {
+    DGCNN_PDL_WAIT();
     extern __shared__ __align__(16) int32_t smem_tables[];
     __shared__ unsigned long long red[2][33];
     const int B = a.num_graphs, N = a.num_nodes, E = a.num_edges;
@@ -365,6 +367,7 @@ n1_gather(const CollateArgs a) {
 // and writes the per-graph extent records {first node, nodes, first edge, edges}.
 __global__ void __launch_bounds__(256)
 n1_prepare(const dgcnn_dataset ds, int4* __restrict__ gext, int32_t* status) {
+    DGCNN_PDL_WAIT();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t G = ds.num_graphs, Nd = ds.num_nodes;
@@ -466,7 +469,7 @@ extern "C" int dgcnn_collate(const dgcnn_dataset* ds, const int32_t* ids, int64_
         a.ws_ok = base;
         a.ws_tables = base + 64;
         smem = 0;
-        n1_plan<<<1, kPlanThreads, 0, st>>>(a);
+        DGCNN_LAUNCH(n1_plan, 1, kPlanThreads, 0, st, a);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     // upper bound of the unified index space (map words: at most (N + 15 B) * 32 / 4 quads each);
@@ -476,9 +479,9 @@ extern "C" int dgcnn_collate(const dgcnn_dataset* ds, const int32_t* ids, int64_
                          (out->x ? N * ds->num_features : 0) + (maps ? (N + 16 * B) : 0);
     const int grid = grid_for(work, kGatherThreads, 4);
     if (B > kFusedGraphs)
-        n1_gather<false><<<grid, kGatherThreads, 0, st>>>(a);
+        DGCNN_LAUNCH((n1_gather<false>), grid, kGatherThreads, 0, st, a);
     else
-        n1_gather<true><<<grid, kGatherThreads, smem, st>>>(a);
+        DGCNN_LAUNCH((n1_gather<true>), grid, kGatherThreads, smem, st, a);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }
@@ -492,7 +495,7 @@ extern "C" int dgcnn_dataset_prepare(const dgcnn_dataset* ds, int32_t* gext, int
     if (ds->num_nodes >= INT32_MAX || ds->num_edges >= INT32_MAX || ds->num_graphs >= INT32_MAX)
         return DGCNN_ERR_UNSUPPORTED;
     const int64_t work = ds->num_nodes > ds->num_graphs ? ds->num_nodes : ds->num_graphs;
-    n1_prepare<<<grid_for(work, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    DGCNN_LAUNCH(n1_prepare, grid_for(work, 256, 8), 256, 0, static_cast<cudaStream_t>(stream), 
         *ds, reinterpret_cast<int4*>(gext), status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;

@@ -77,6 +77,7 @@ __device__ __forceinline__ void c5_stage_pairs(const float* __restrict__ pooled,
 __global__ void __launch_bounds__(256)
 tail_c5_fwd(const float* __restrict__ pooled, int64_t B, int k, int L1, const float* __restrict__ w5,
             const float* __restrict__ b5, float* __restrict__ h1, uint8_t* __restrict__ arg) {
+    DGCNN_PDL_WAIT();
     extern __shared__ __align__(16) float c5sm[];
     float* xs = c5sm;                                   // [64][194]
     float* w5t = xs + kC5Pairs * kC5Row;                // [97][16]
@@ -145,6 +146,7 @@ tail_c5_fwd(const float* __restrict__ pooled, int64_t B, int k, int L1, const fl
 __global__ void __launch_bounds__(256)
 tail_c6_fwd(const float* __restrict__ h1, int64_t B, int L1, const float* __restrict__ w6,
             const float* __restrict__ b6, float* __restrict__ h2) {
+    DGCNN_PDL_WAIT();
     extern __shared__ float sm[];
     float* w6t = sm;                         // [(c*5+d)][o]
     float* sb = sm + kC5 * kK6 * kC6;        // [32]
@@ -230,6 +232,7 @@ template <bool A_KM, bool B_KN, bool RELU_MASK>
 __global__ void __launch_bounds__(256)
 gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm, int64_t ldb,
          float* __restrict__ C, int M, int N, int K, int kchunk, const float* __restrict__ mask) {
+    DGCNN_PDL_WAIT();
     constexpr int BM = kGemmBM, BN = kGemmBN, BK = 16, BMP = BM + 8, BNP = BN + 8;
     constexpr int NI = BN / 32;                            // 8-column MMA tiles per warp (4 warps along N)
     __shared__ float As[BK * BMP];
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(256)
 tail_fc1_epilogue(const float* __restrict__ slabs, int splits, int64_t total, const float* __restrict__ bias,
                   int training, uint64_t seed, const int64_t* __restrict__ rng_offset,
                   float* __restrict__ h3, uint8_t* __restrict__ keep) {
+    DGCNN_PDL_WAIT();
     const uint64_t off = (training && rng_offset) ? (uint64_t)*rng_offset : 0ull;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         float s = bias[i % kFc];
@@ -367,6 +371,7 @@ tail_fc1_epilogue(const float* __restrict__ slabs, int splits, int64_t total, co
 __global__ void __launch_bounds__(256)
 tail_fc2_lsm_fwd(const float* __restrict__ h3, int64_t B, int C, const float* __restrict__ w2,
                  const float* __restrict__ b2, float* __restrict__ logp, int64_t* rng_offset) {
+    DGCNN_PDL_WAIT();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
         const float* hr = h3 + b * kFc;
@@ -401,6 +406,7 @@ tail_head_kernel(const float* __restrict__ slabs, int splits, int64_t B, int C, 
                  int training, uint64_t seed, int64_t* rng_offset, float* __restrict__ h3,
                  uint8_t* __restrict__ keep, float* __restrict__ logp, float* __restrict__ dlogit,
                  float* __restrict__ dz3, float* __restrict__ per_graph /* [B][2] */) {
+    DGCNN_PDL_WAIT();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t off = (training && rng_offset) ? (uint64_t)*rng_offset : 0ull;
     const int64_t total = B * kFc;
@@ -486,6 +492,7 @@ __global__ void __launch_bounds__(256)
 tail_fc2_bwd_rows(const float* __restrict__ dlogp, const float* __restrict__ logp,
                   const uint8_t* __restrict__ keep, int64_t B, int C, const float* __restrict__ w2,
                   float* __restrict__ dlogit, float* __restrict__ dz3) {
+    DGCNN_PDL_WAIT();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
         const float g = lane < C ? dlogp[b * C + lane] : 0.f;
@@ -516,6 +523,7 @@ tail_fc2_bwd_params(const float* __restrict__ dlogit, const float* __restrict__ 
                     float* __restrict__ db2, float* __restrict__ dbf1,
                     const float* __restrict__ per_graph = nullptr, float* __restrict__ stats = nullptr,
                     int64_t* rng_offset = nullptr) {
+    DGCNN_PDL_WAIT();
     __shared__ float red[8][33];
     const int ox = threadIdx.x & 31, gy = threadIdx.x >> 5;
     if (per_graph && blockIdx.x == gridDim.x - 1) {
@@ -573,6 +581,7 @@ tail_fc2_bwd_params(const float* __restrict__ dlogit, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 tail_c6_bwd_input(const float* __restrict__ dz2, int64_t B, int L1, const float* __restrict__ w6,
                   float* __restrict__ dh1) {
+    DGCNN_PDL_WAIT_ONLY();
     extern __shared__ float sm[];
     float* w6c = sm;                         // [(o*5+d)][c]
     const int L2 = L1 - (kK6 - 1);
@@ -624,6 +633,7 @@ tail_c6_bwd_input(const float* __restrict__ dz2, int64_t B, int L1, const float*
 __global__ void __launch_bounds__(256)
 tail_c6_bwd_weight(const float* __restrict__ dz2, const float* __restrict__ h1, int64_t B, int L1,
                    float* __restrict__ partials) {
+    DGCNN_PDL_WAIT();
     extern __shared__ float sm[];
     const int L2 = L1 - (kK6 - 1);
     const int L1P = L1 | 1;          // odd row stride: the 16 channel rows hit distinct banks
@@ -669,6 +679,7 @@ tail_c6_bwd_weight(const float* __restrict__ dz2, const float* __restrict__ h1, 
 __global__ void __launch_bounds__(256)
 tail_c5_bwd_input(const float* __restrict__ dh1, const uint8_t* __restrict__ arg, int64_t B, int k, int L1,
                   const float* __restrict__ w5, float* __restrict__ dpooled) {
+    DGCNN_PDL_WAIT_ONLY();
     __shared__ float w5s[kC5 * kKW];
     constexpr int TP = 32;                              // pairs per CTA iteration (4 per warp)
     __shared__ float zv[TP][kC5 + 1];
@@ -740,6 +751,7 @@ __global__ void __launch_bounds__(256)
 tail_c5_bwd_weight(const float* __restrict__ dh1, const uint8_t* __restrict__ arg,
                    const float* __restrict__ pooled, int64_t B, int k, int L1,
                    float* __restrict__ partials) {
+    DGCNN_PDL_WAIT();
     constexpr int NW = kC5 * kKW;                           // 1552
     extern __shared__ __align__(16) float c5sm[];
     float* xs = c5sm;                                       // [64][194]
@@ -789,6 +801,7 @@ tail_c5_bwd_weight(const float* __restrict__ dh1, const uint8_t* __restrict__ ar
 __global__ void __launch_bounds__(256)
 tail_reduce_partials(const float* __restrict__ partials, int parts, int total, int split_at,
                      float* __restrict__ out_a, float* __restrict__ out_b) {
+    DGCNN_PDL_WAIT();
     __shared__ float red[8][33];
     const int ox = threadIdx.x & 31, gy = threadIdx.x >> 5;
     const int o = blockIdx.x * 32 + ox;
@@ -810,6 +823,7 @@ tail_reduce_partials(const float* __restrict__ partials, int parts, int total, i
 __global__ void __launch_bounds__(256)
 adam_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
           int64_t n, int64_t* step, float lr, float beta1, float beta2, float eps, float grad_scale) {
+    DGCNN_PDL_WAIT();
     const int64_t t = *step + 1;
     const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -822,13 +836,15 @@ adam_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict_
         p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
     }
 }
-__global__ void adam_bump(int64_t* step) { *step += 1; }
+__global__ void adam_bump(int64_t* step) {
+    DGCNN_PDL_WAIT(); *step += 1; }
 
 // NLL (train.py:39,44-45) on log-probabilities, single CTA: stats[0] = -sum_b logp[b][y_b],
 // stats[1] = #{argmax == y};  dlogp[b][c] = -grad_scale at c == y_b, else 0.
 __global__ void __launch_bounds__(1024)
 nll_sum_kernel(const float* __restrict__ logp, const int64_t* __restrict__ y, int64_t B, int C,
                float grad_scale, float* __restrict__ stats, float* __restrict__ dlogp) {
+    DGCNN_PDL_WAIT();
     __shared__ float sl[32], sc[32];
     float loss = 0.f, correct = 0.f;
     for (int64_t b = threadIdx.x; b < B; b += 1024) {
@@ -908,7 +924,7 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
         if (cudaFuncSetAttribute(tail_c5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kC5StageBytes) != cudaSuccess)
             return DGCNN_ERR_CUDA;
-        tail_c5_fwd<<<grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st>>>(pooled, B, k, d.L1, w5, b5, h1,
+        DGCNN_LAUNCH(tail_c5_fwd, grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st, pooled, B, k, d.L1, w5, b5, h1,
                                                                                  arg);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
@@ -917,19 +933,19 @@ extern "C" int dgcnn_tail_fwd(const float* pooled, int64_t num_graphs, int32_t k
     if (smem6 > 48 * 1024 &&
         cudaFuncSetAttribute(tail_c6_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess)
         return DGCNN_ERR_CUDA;
-    tail_c6_fwd<<<grid_for(B, 1, 4), 256, smem6, st>>>(h1, B, d.L1, w6, b6, h2);
+    DGCNN_LAUNCH(tail_c6_fwd, grid_for(B, 1, 4), 256, smem6, st, h1, B, d.L1, w6, b6, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // fc1: [B, D1] x Wf1^T [D1, 128], split-K slabs
     const int kchunk = (int)ceil_div(ceil_div(d.D1, kFc1Splits), 16) * 16;
     const int splits = (int)ceil_div(d.D1, kchunk);
     dim3 g1((unsigned)ceil_div(kFc, kGemmBN), (unsigned)ceil_div(B, kGemmBM), (unsigned)splits);
-    gemm_f32<false, false, false><<<g1, 256, 0, st>>>(h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
+    DGCNN_LAUNCH((gemm_f32<false, false, false>), g1, 256, 0, st, h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
                                                       nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    tail_fc1_epilogue<<<grid_for(B * kFc, 256, 4), 256, 0, st>>>(slabs, splits, B * kFc, bf1, training, seed,
+    DGCNN_LAUNCH(tail_fc1_epilogue, grid_for(B * kFc, 256, 4), 256, 0, st, slabs, splits, B * kFc, bf1, training, seed,
                                                                  rng_offset, h3, keep);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    tail_fc2_lsm_fwd<<<grid_for(B, 8, 2), 256, 0, st>>>(h3, B, num_classes, wf2, bf2, logp,
+    DGCNN_LAUNCH(tail_fc2_lsm_fwd, grid_for(B, 8, 2), 256, 0, st, h3, B, num_classes, wf2, bf2, logp,
                                                         training ? rng_offset : nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
@@ -970,7 +986,7 @@ extern "C" int dgcnn_tail_fwd_loss(const float* pooled, int64_t num_graphs, int3
         if (cudaFuncSetAttribute(tail_c5_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kC5StageBytes) != cudaSuccess)
             return DGCNN_ERR_CUDA;
-        tail_c5_fwd<<<grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st>>>(pooled, B, k, d.L1, w5, b5, h1,
+        DGCNN_LAUNCH(tail_c5_fwd, grid_for(B * d.L1, kC5Pairs, 4), 256, kC5StageBytes, st, pooled, B, k, d.L1, w5, b5, h1,
                                                                                  arg);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
@@ -979,15 +995,15 @@ extern "C" int dgcnn_tail_fwd_loss(const float* pooled, int64_t num_graphs, int3
     if (smem6 > 48 * 1024 &&
         cudaFuncSetAttribute(tail_c6_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6) != cudaSuccess)
         return DGCNN_ERR_CUDA;
-    tail_c6_fwd<<<grid_for(B, 1, 4), 256, smem6, st>>>(h1, B, d.L1, w6, b6, h2);
+    DGCNN_LAUNCH(tail_c6_fwd, grid_for(B, 1, 4), 256, smem6, st, h1, B, d.L1, w6, b6, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int kchunk = (int)ceil_div(ceil_div(d.D1, kFc1Splits), 16) * 16;
     const int splits = (int)ceil_div(d.D1, kchunk);
     dim3 g1((unsigned)ceil_div(kFc, kGemmBN), (unsigned)ceil_div(B, kGemmBM), (unsigned)splits);
-    gemm_f32<false, false, false><<<g1, 256, 0, st>>>(h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
+    DGCNN_LAUNCH((gemm_f32<false, false, false>), g1, 256, 0, st, h2, d.D1, wf1, d.D1, slabs, (int)B, kFc, d.D1, kchunk,
                                                       nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    tail_head_kernel<<<grid_for(B, 4, 4), 128, 0, st>>>(slabs, splits, B, num_classes, bf1, wf2, bf2, y, training,
+    DGCNN_LAUNCH(tail_head_kernel, grid_for(B, 4, 4), 128, 0, st, slabs, splits, B, num_classes, bf1, wf2, bf2, y, training,
                                                         seed, rng_offset, h3, keep, logp, dlogit, dz3, per_graph);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
@@ -1073,28 +1089,28 @@ static int tail_bwd_impl(const float* dlogp, const float* pooled, int64_t num_gr
     };
 
     if (!after_loss) {
-        tail_fc2_bwd_rows<<<grid_for(B, 8, 4), 256, 0, st>>>(dlogp, logp, keep, B, num_classes, wf2, dlogit, dz3);
+        DGCNN_LAUNCH(tail_fc2_bwd_rows, grid_for(B, 8, 4), 256, 0, st, dlogp, logp, keep, B, num_classes, wf2, dlogit, dz3);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     if (!fork(0)) return DGCNN_ERR_CUDA;
-    tail_fc2_bwd_params<<<(num_classes * kFc + num_classes + kFc + 31) / 32 + (after_loss ? 1 : 0), 256, 0, sw>>>(
+    DGCNN_LAUNCH(tail_fc2_bwd_params, (num_classes * kFc + num_classes + kFc + 31) / 32 + (after_loss ? 1 : 0), 256, 0, sw, 
         dlogit, h3, dz3, B, num_classes, dwf2, dbf2, dbf1, after_loss ? per_graph : nullptr, stats_after_loss,
         rng_offset);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dz2 = (dz3 Wf1) * (h2 > 0):  [B,128] x [128,D1]
     dim3 ga((unsigned)ceil_div(d.D1, kGemmBN), (unsigned)ceil_div(B, kGemmBM), 1);
-    gemm_f32<false, true, true><<<ga, 256, 0, st>>>(dz3, kFc, wf1, d.D1, dz2, (int)B, d.D1, kFc, kFc, h2);
+    DGCNN_LAUNCH((gemm_f32<false, true, true>), ga, 256, 0, st, dz3, kFc, wf1, d.D1, dz2, (int)B, d.D1, kFc, kFc, h2);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // dWf1 = dz3^T h2:  [128,B] x [B,D1]
     {   // split over the batch, slabs summed in order
         const int kchunk = (int)ceil_div(ceil_div(B, kDwSplits), 16) * 16;
         const int splits = (int)ceil_div(B, kchunk);
         dim3 gb((unsigned)ceil_div(d.D1, kGemmBN), (unsigned)ceil_div(kFc, kGemmBM), (unsigned)splits);
-        gemm_f32<true, true, false><<<gb, 256, 0, sw>>>(dz3, kFc, h2, d.D1, slabw, kFc, d.D1, (int)B, kchunk,
+        DGCNN_LAUNCH((gemm_f32<true, true, false>), gb, 256, 0, sw, dz3, kFc, h2, d.D1, slabw, kFc, d.D1, (int)B, kchunk,
                                                         nullptr);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         const int total = kFc * d.D1;
-        tail_reduce_partials<<<(total + 31) / 32, 256, 0, sw>>>(slabw, splits, total, total, dwf1, dwf1);
+        DGCNN_LAUNCH(tail_reduce_partials, (total + 31) / 32, 256, 0, sw, slabw, splits, total, total, dwf1, dwf1);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     const size_t smem_in = sizeof(float) * (kC6 * kK6 * kC5 + kC6 * (d.L2 + 2 * (kK6 - 1) + 8) + kC5 * d.L1);
@@ -1105,27 +1121,27 @@ static int tail_bwd_impl(const float* dlogp, const float* pooled, int64_t num_gr
                              (int)smem_in) != cudaSuccess)
         return DGCNN_ERR_CUDA;
     if (!fork(1)) return DGCNN_ERR_CUDA;             // dz2 is ready
-    tail_c6_bwd_input<<<grid_for(B, 1, 4), 256, smem_in, st>>>(dz2, B, d.L1, w6, dh1);
+    DGCNN_LAUNCH(tail_c6_bwd_input, grid_for(B, 1, 4), 256, smem_in, st, dz2, B, d.L1, w6, dh1);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int parts6 = grid_for(B, 1, 2);
-    tail_c6_bwd_weight<<<parts6, 256, smem_w, sw>>>(dz2, h1, B, d.L1, part6);
+    DGCNN_LAUNCH(tail_c6_bwd_weight, parts6, 256, smem_w, sw, dz2, h1, B, d.L1, part6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int n6 = kC6 * kC5 * kK6;
-    tail_reduce_partials<<<(n6 + kC6 + 31) / 32, 256, 0, sw>>>(part6, parts6, n6 + kC6, n6, dw6, db6);
+    DGCNN_LAUNCH(tail_reduce_partials, (n6 + kC6 + 31) / 32, 256, 0, sw, part6, parts6, n6 + kC6, n6, dw6, db6);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (!to_h1) {
         if (!fork(2)) return DGCNN_ERR_CUDA;             // dh1 is ready
-        tail_c5_bwd_input<<<grid_for(B * d.L1, 32, 8), 256, 0, st>>>(dh1, arg, B, k, d.L1, w5, dpooled);
+        DGCNN_LAUNCH(tail_c5_bwd_input, grid_for(B * d.L1, 32, 8), 256, 0, st, dh1, arg, B, k, d.L1, w5, dpooled);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         const size_t smem5 = sizeof(float) * (kC5Pairs * kC5Row + 2 * kC5Pairs * kC5);
         if (cudaFuncSetAttribute(tail_c5_bwd_weight, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem5) != cudaSuccess)
             return DGCNN_ERR_CUDA;
         const int parts5 = grid_for(B * d.L1, kC5Pairs, 2);
-        tail_c5_bwd_weight<<<parts5, 256, smem5, sw>>>(dh1, arg, pooled, B, k, d.L1, part5);
+        DGCNN_LAUNCH(tail_c5_bwd_weight, parts5, 256, smem5, sw, dh1, arg, pooled, B, k, d.L1, part5);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         const int n5 = kC5 * kKW;
-        tail_reduce_partials<<<(n5 + kC5 + 31) / 32, 256, 0, sw>>>(part5, parts5, n5 + kC5, n5, dw5, db5);
+        DGCNN_LAUNCH(tail_reduce_partials, (n5 + kC5 + 31) / 32, 256, 0, sw, part5, parts5, n5 + kC5, n5, dw5, db5);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     if (side) {
@@ -1200,7 +1216,7 @@ extern "C" int dgcnn_project_rows(const float* x, int64_t ldx, int32_t cin, cons
     if (!x || !weight || !h) return DGCNN_ERR_INVALID_ARGUMENT;
     dim3 grid(1, (unsigned)ceil_div(num_nodes, kGemmBM), 1);
     const int kchunk = (int)ceil_div(cin, 16) * 16;
-    gemm_f32<false, false, false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    DGCNN_LAUNCH((gemm_f32<false, false, false>), grid, 256, 0, static_cast<cudaStream_t>(stream), 
         x, ldx, weight, cin, h, (int)num_nodes, 32, cin, kchunk, nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
@@ -1213,10 +1229,10 @@ extern "C" int dgcnn_adam_step(float* params, const float* grads, float* exp_avg
     if (n == 0) return DGCNN_OK;
     if (!params || !grads || !exp_avg || !exp_avg_sq) return DGCNN_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    adam_flat<<<grid_for(n, 256, 4), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1,
+    DGCNN_LAUNCH(adam_flat, grid_for(n, 256, 4), 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1,
                                                    beta2, eps, grad_scale);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    adam_bump<<<1, 1, 0, st>>>(step);
+    DGCNN_LAUNCH(adam_bump, 1, 1, 0, st, step);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }
@@ -1225,7 +1241,7 @@ extern "C" int dgcnn_nll_sum(const float* logp, const int64_t* y, int64_t num_gr
                              float grad_scale, float* stats, float* dlogp, void* stream) {
     if (num_graphs < 0 || num_classes < 1 || !stats) return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_graphs > 0 && (!logp || !y)) return DGCNN_ERR_INVALID_ARGUMENT;
-    nll_sum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(logp, y, num_graphs, num_classes,
+    DGCNN_LAUNCH(nll_sum_kernel, 1, 1024, 0, static_cast<cudaStream_t>(stream), logp, y, num_graphs, num_classes,
                                                                      grad_scale, stats, dlogp);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;

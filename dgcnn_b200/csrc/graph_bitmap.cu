@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(1024)
 k0b_offsets(const int32_t* __restrict__ gptr, int num_graphs, int max_nodes,
             int32_t* __restrict__ bmoff, int32_t* __restrict__ fgoff, int32_t* __restrict__ gflags,
             int32_t* __restrict__ gflags_t, const int32_t* __restrict__ gorder, int4* __restrict__ gdesc) {
+    DGCNN_PDL_WAIT();
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -105,6 +106,7 @@ k0b_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
          uint32_t* __restrict__ bitmap0, uint32_t* __restrict__ bitmap1,
          int32_t* __restrict__ gflags0, int32_t* __restrict__ gflags1,
          const int32_t* gate_word, int gate_mask, int only_second) {
+    DGCNN_PDL_WAIT();
     const bool second = only_second || blockIdx.y != 0;
     if (second && gate_word && !(*gate_word & gate_mask)) return;
     const int32_t* __restrict__ rowptr = second ? rowptr1 : rowptr0;
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(256)
 k0b_fragments(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ bmoff,
               const int4* __restrict__ gdesc, int num_graphs, int max_nodes,
               uint32_t* __restrict__ fragmap) {
+    DGCNN_PDL_WAIT();
     const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
     for (int q = blockIdx.x; q < num_graphs; q += gridDim.x) {
         const int4 d = gdesc[q];                     // {graph, first node, nodes, fgoff}
@@ -276,25 +279,25 @@ int dgcnn_build_bitmaps_impl(const int32_t* rowptr, const int32_t* col,
             cudaMemsetAsync(bitmap_t, 0, sizeof(uint32_t) * (size_t)need, st) != cudaSuccess)
             return DGCNN_ERR_CUDA;
     }
-    k0b_offsets<<<1, 1024, 0, st>>>(gptr, (int)num_graphs, (int)max_nodes, bmoff,
+    DGCNN_LAUNCH(k0b_offsets, 1, 1024, 0, st, gptr, (int)num_graphs, (int)max_nodes, bmoff,
                                     fragmap ? fgoff : nullptr, gflags, gflags_t, gorder,
                                     reinterpret_cast<int4*>(gdesc));
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (num_nodes > 0 && lazy) {
         if (transposed) {                            // (returns at once unless K0 raised the gate)
-            k0b_fill<<<dim3((unsigned)grid_for(num_nodes, 8, 8), 1), 256, 0, st>>>(
+            DGCNN_LAUNCH(k0b_fill, dim3((unsigned)grid_for(num_nodes, 8, 8), 1), 256, 0, st, 
                 rowptr, col, rowptr_t, col_t, gptr, batch, batch32, (int)num_graphs, num_nodes, (int)max_nodes,
                 bmoff, bitmap, bitmap_t, gflags, gflags_t, gate_word, gate_mask, 1);
             DGCNN_RETURN_IF_LAUNCH_FAILED();
         }
     } else if (num_nodes > 0) {
         dim3 grid((unsigned)grid_for(num_nodes, 8, 8), transposed ? 2 : 1);
-        k0b_fill<<<grid, 256, 0, st>>>(rowptr, col, rowptr_t, col_t, gptr, batch, batch32, (int)num_graphs,
+        DGCNN_LAUNCH(k0b_fill, grid, 256, 0, st, rowptr, col, rowptr_t, col_t, gptr, batch, batch32, (int)num_graphs,
                                        num_nodes, (int)max_nodes, bmoff, bitmap, bitmap_t, gflags,
                                        gflags_t, gate_word, gate_mask, 0);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         if (fragmap && gdesc) {
-            k0b_fragments<<<dim3((unsigned)grid_for(num_graphs, 1, 8), 4), 256, 0, st>>>(
+            DGCNN_LAUNCH(k0b_fragments, dim3((unsigned)grid_for(num_graphs, 1, 8), 4), 256, 0, st, 
                 bitmap, bmoff, reinterpret_cast<const int4*>(gdesc), (int)num_graphs, (int)max_nodes,
                 fragmap);
             DGCNN_RETURN_IF_LAUNCH_FAILED();

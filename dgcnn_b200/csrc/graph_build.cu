@@ -94,6 +94,7 @@ __device__ __forceinline__ void graph_ptr_body(const void* __restrict__ batch, b
 __global__ void __launch_bounds__(256)
 k0_graph_ptr(const void* __restrict__ batch, bool i32, int64_t n, int64_t num_graphs,
              int32_t* __restrict__ gptr, int32_t* status) {
+    DGCNN_PDL_WAIT();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride)
         graph_ptr_body(batch, i32, n, num_graphs, gptr, status, i);
@@ -128,6 +129,7 @@ struct GenericArgs {
 
 __global__ void __launch_bounds__(kScanThreads)
 k0_generic(GenericArgs a) {
+    DGCNN_PDL_WAIT();
     __shared__ int red[kScanThreads / 32];
     __shared__ int carry_s;
     if (!(*a.gate & 1)) return;
@@ -310,6 +312,7 @@ k0_fast_build(const void* __restrict__ src, const void* __restrict__ dst, int64_
               int32_t* __restrict__ rowptr, int32_t* __restrict__ col,
               int32_t* __restrict__ rowptr_t, int32_t* __restrict__ col_t,
               int32_t* __restrict__ gptr, int32_t* flags, int32_t* status) {
+    DGCNN_PDL_WAIT();
     __shared__ unsigned long long red[2][8];
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,6 +383,7 @@ __global__ void __launch_bounds__(1024)
 k0_finalize(int64_t n, const int32_t* __restrict__ rowptr, float* __restrict__ dis, int32_t* flags,
             int check_fingerprints, const int32_t* __restrict__ gptr, int num_graphs,
             int32_t* __restrict__ gorder) {
+    DGCNN_PDL_WAIT();
     __shared__ int sizes[kMaxOrderGraphs];
     if (blockIdx.x == 0 && threadIdx.x == 0 && check_fingerprints) {
         const unsigned long long* fp = reinterpret_cast<const unsigned long long*>(flags + 2);
@@ -427,6 +431,7 @@ k0_finalize(int64_t n, const int32_t* __restrict__ rowptr, float* __restrict__ d
 __global__ void __launch_bounds__(256)
 k0_fast_verify(const void* __restrict__ src, const void* __restrict__ dst, bool i32, int64_t e0, int64_t n,
                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int32_t* flags) {
+    DGCNN_PDL_WAIT();
     if (*flags & 1) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,7 +462,7 @@ extern "C" int dgcnn_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t 
         return DGCNN_ERR_INVALID_ARGUMENT;
     if (num_nodes >= INT32_MAX) return DGCNN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    k0_graph_ptr<<<grid_for(num_nodes + 1, 256, 8), 256, 0, st>>>(batch, false, num_nodes, num_graphs, gptr,
+    DGCNN_LAUNCH(k0_graph_ptr, grid_for(num_nodes + 1, 256, 8), 256, 0, st, batch, false, num_nodes, num_graphs, gptr,
                                                                  status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
@@ -492,11 +497,11 @@ static int build_graph_impl(const void* edge_index, bool i32, int64_t num_edges,
 
     // fast path (sorted + symmetric input), verified on the device
     int64_t work = e0 + 1 > n + 1 ? e0 + 1 : n + 1;
-    k0_fast_build<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, e0, batch, i32, n, num_graphs, rowptr,
+    DGCNN_LAUNCH(k0_fast_build, grid_for(work, 256, 8), 256, 0, st, src, dst, e0, batch, i32, n, num_graphs, rowptr,
                                                           col, rowptr_t, col_t, gptr, w.flags, status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (exact_verify) {
-        k0_fast_verify<<<grid_for(work, 256, 8), 256, 0, st>>>(src, dst, i32, e0, n, rowptr, col, w.flags);
+        DGCNN_LAUNCH(k0_fast_verify, grid_for(work, 256, 8), 256, 0, st, src, dst, i32, e0, n, rowptr, col, w.flags);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     int fin_grid = grid_for(n + 1, 1024, 1);
@@ -504,7 +509,7 @@ static int build_graph_impl(const void* edge_index, bool i32, int64_t num_edges,
         const int want = (int)((num_graphs + 15) / 16 < 32 ? (num_graphs + 15) / 16 : 32);
         if (fin_grid < want) fin_grid = want;
     }
-    k0_finalize<<<fin_grid, 1024, 0, st>>>(n, rowptr, dis, w.flags, exact_verify ? 0 : 1, gptr,
+    DGCNN_LAUNCH(k0_finalize, fin_grid, 1024, 0, st, n, rowptr, dis, w.flags, exact_verify ? 0 : 1, gptr,
                                            gorder ? (int)num_graphs : 0, gorder);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
 

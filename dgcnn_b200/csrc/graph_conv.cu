@@ -68,6 +68,7 @@ __device__ __forceinline__ void load_matrix(const AggParams& p, float* smat, flo
 // channel-parallel: lane l owns input channels l, l+32, ... (CPL of them)
 template <int CPL>
 __global__ void __launch_bounds__(kConvThreads) gc_aggregate_chan(AggParams p) {
+    DGCNN_PDL_WAIT();
     extern __shared__ float smem[];
     float* smat = smem;
     float* sbias = smem + p.fin * p.fout;
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kConvThreads) gc_aggregate_chan(AggParams p) {
 // neighbours instead of the channels and combine with warp-shuffle partial sums
 template <int FINP>
 __global__ void __launch_bounds__(kConvThreads) gc_aggregate_edge(AggParams p) {
+    DGCNN_PDL_WAIT();
     extern __shared__ float smem[];
     float* smat = smem;
     float* sbias = smem + p.fin * p.fout;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(kConvThreads) gc_aggregate_edge(AggParams p) {
 constexpr int kVecRows = 4;      // rows per warp
 
 __global__ void __launch_bounds__(kConvThreads) gc_aggregate_vec32(AggParams p) {
+    DGCNN_PDL_WAIT();
     extern __shared__ float smem[];
     float* smat = smem;                    // [32][32]: smat[k*32 + c], zero for c >= fout
     float* sbias = smem + 32 * 32;
@@ -329,6 +332,7 @@ struct StagedParams {
 };
 
 __global__ void __launch_bounds__(kStagedThreads) gc_aggregate_staged(StagedParams sp) {
+    DGCNN_PDL_WAIT();
     extern __shared__ __align__(16) float smem[];
     const AggParams& p = sp.a;
     float* smat = smem;                    // [32][32]
@@ -435,7 +439,7 @@ static int launch_aggregate(const AggParams& p, cudaStream_t st) {
         // one task (four rows) per warp whenever the device can hold them: the rows of a batch are
         // independent latency chains
         const int grid_v = grid_for((p.n + kVecRows - 1) / kVecRows, kConvThreads / 32, 16);
-        gc_aggregate_vec32<<<grid_v, kConvThreads, smem_v, st>>>(p);
+        DGCNN_LAUNCH(gc_aggregate_vec32, grid_v, kConvThreads, smem_v, st, p);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
         return DGCNN_OK;
     }
@@ -447,7 +451,7 @@ static int launch_aggregate(const AggParams& p, cudaStream_t st) {
             cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                  (int)smem) != cudaSuccess)                                   \
             return DGCNN_ERR_CUDA;                                                            \
-        KERNEL<<<grid, kConvThreads, smem, st>>>(p);                                          \
+        DGCNN_LAUNCH(KERNEL, grid, kConvThreads, smem, st, p);                                          \
     } while (0)
     if (p.fin <= 1) DGCNN_LAUNCH_AGG(gc_aggregate_edge<1>);
     else if (p.fin <= 2) DGCNN_LAUNCH_AGG(gc_aggregate_edge<2>);
@@ -483,13 +487,13 @@ static int launch_aggregate_graphs(const AggParams& p0, const int32_t* gptr, con
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)DGCNN_NUM_SMS * per_sm;
     if (grid > num_graphs) grid = num_graphs;
-    gc_aggregate_staged<<<(unsigned)grid, kStagedThreads, smem, st>>>(sp);
+    DGCNN_LAUNCH(gc_aggregate_staged, (unsigned)grid, kStagedThreads, smem, st, sp);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (max_nodes <= 0 || max_nodes > cap) {                     // someone may not have fitted
         AggParams pb = p0;
         pb.gptr = gptr; pb.num_graphs = (int)num_graphs; pb.big_rows = cap;
         const size_t smem_v = pb.out ? sizeof(float) * (32 * 32 + 32) : 0;
-        gc_aggregate_vec32<<<DGCNN_NUM_SMS * 4, kConvThreads, smem_v, st>>>(pb);
+        DGCNN_LAUNCH(gc_aggregate_vec32, DGCNN_NUM_SMS * 4, kConvThreads, smem_v, st, pb);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     return DGCNN_OK;
@@ -500,6 +504,7 @@ static int launch_aggregate_graphs(const AggParams& p0, const int32_t* gptr, con
 __global__ void __launch_bounds__(256)
 gc_bwd_dpre(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy,
             int cout, int64_t n, int act, float* __restrict__ dpre, float* __restrict__ db_part) {
+    DGCNN_PDL_WAIT();
     __shared__ float red[256];
     const int c = threadIdx.x;
     const int rows_per_block = blockDim.y;
@@ -530,6 +535,7 @@ gc_bwd_dpre(const float* __restrict__ dy, int64_t lddy, const float* __restrict_
 // gradients are bit-reproducible).  Block = 32 outputs x 8 part lanes.
 __global__ void __launch_bounds__(256)
 gc_reduce_parts(const float* __restrict__ part, int parts, int total, float* __restrict__ out) {
+    DGCNN_PDL_WAIT();
     __shared__ float red[8][33];
     const int ox = threadIdx.x & 31, py = threadIdx.x >> 5;
     const int o = blockIdx.x * 32 + ox;
@@ -559,6 +565,7 @@ constexpr int kDwRows = 32;
 __global__ void __launch_bounds__(256)
 gc_bwd_dw(const float* __restrict__ dh, const float* __restrict__ x, int64_t ldx, int cin, int cout,
           int64_t n, float* __restrict__ dw_part) {
+    DGCNN_PDL_WAIT();
     extern __shared__ float smem[];
     float* sdh = smem;                   // [kDwRows][cout]
     float* sx = smem + kDwRows * cout;   // [kDwRows][cin]
@@ -713,10 +720,10 @@ extern "C" int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* 
     // A: dpre, db (per-CTA partial sums, added in CTA order)
     int cx = (int)next_pow2((uint32_t)cout);
     dim3 block_a(cx, 256 / cx);
-    gc_bwd_dpre<<<w.grid_a, block_a, 0, st>>>(dy, lddy, y, ldy, cout, n, act, w.dpre, db ? w.db_part : nullptr);
+    DGCNN_LAUNCH(gc_bwd_dpre, w.grid_a, block_a, 0, st, dy, lddy, y, ldy, cout, n, act, w.dpre, db ? w.db_part : nullptr);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (db) {
-        gc_reduce_parts<<<(cout + 31) / 32, 256, 0, st>>>(w.db_part, w.grid_a, cout, db);
+        DGCNN_LAUNCH(gc_reduce_parts, (cout + 31) / 32, 256, 0, st, w.db_part, w.grid_a, cout, db);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
 
@@ -733,9 +740,9 @@ extern "C" int dgcnn_graph_conv_bwd(const float* dy, int64_t lddy, const float* 
     // C: dw = dh^T x (per-CTA partial products, added in CTA order)
     dim3 grid_c((unsigned)w.grid_c, (unsigned)ceil_div(cin * cout, 1024));
     size_t smem_c = sizeof(float) * kDwRows * (size_t)(cin + cout);
-    gc_bwd_dw<<<grid_c, 256, smem_c, st>>>(w.dh, x, ldx, cin, cout, n, w.dw_part);
+    DGCNN_LAUNCH(gc_bwd_dw, grid_c, 256, smem_c, st, w.dh, x, ldx, cin, cout, n, w.dw_part);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    gc_reduce_parts<<<(cin * cout + 31) / 32, 256, 0, st>>>(w.dw_part, w.grid_c, cin * cout, dw);
+    DGCNN_LAUNCH(gc_reduce_parts, (cin * cout + 31) / 32, 256, 0, st, w.dw_part, w.grid_c, cin * cout, dw);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

@@ -112,6 +112,7 @@ __device__ __forceinline__ void aggregate32(const float* __restrict__ in, float*
 }
 
 __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_fwd_kernel(StackFwdParams p) {
+    DGCNN_PDL_WAIT();
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_graph;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -366,7 +367,7 @@ int dgcnn_stack_fwd_fma(const float* x, int64_t ldx, int32_t num_features, const
         per_sm = 1;
     int64_t grid = (int64_t)per_sm * DGCNN_NUM_SMS;
     if (grid > num_graphs) grid = num_graphs;
-    stack_fwd_kernel<<<(unsigned)grid, threads, smem, st>>>(p);
+    DGCNN_LAUNCH(stack_fwd_kernel, (unsigned)grid, threads, smem, st, p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

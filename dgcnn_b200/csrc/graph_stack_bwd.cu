@@ -89,6 +89,7 @@ __device__ __forceinline__ float reduce_rows(const float* red, int nwarps, int c
 }
 
 __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_bwd_kernel(StackBwdParams p) {
+    DGCNN_PDL_WAIT();
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kStackMaxThreads, 2) stack_bwd_kernel(StackBwd
 // grads[o] = sum over CTAs, in CTA order
 __global__ void __launch_bounds__(256)
 stack_bwd_reduce(const float* __restrict__ partials, int parts, int total, float* __restrict__ grads) {
+    DGCNN_PDL_WAIT();
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= total) return;
     float s = 0.f;
@@ -432,9 +434,9 @@ extern "C" int dgcnn_stack_bwd(const float* dpooled, const int32_t* perm, int32_
         return DGCNN_ERR_CUDA;
     int grid = stack_bwd_grid(p.f, p.nmax, threads, smem, num_graphs);
     if (grid > 8 * DGCNN_NUM_SMS) grid = 8 * DGCNN_NUM_SMS;
-    stack_bwd_kernel<<<grid, threads, smem, st>>>(p);
+    DGCNN_LAUNCH(stack_bwd_kernel, grid, threads, smem, st, p);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
-    stack_bwd_reduce<<<(G.total + 255) / 256, 256, 0, st>>>(p.partials, grid, G.total, grads);
+    DGCNN_LAUNCH(stack_bwd_reduce, (G.total + 255) / 256, 256, 0, st, p.partials, grid, G.total, grads);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

@@ -867,6 +867,7 @@ __device__ __forceinline__ void bwd_process_graph(const StackBwdMmaParams& p, co
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdMmaParams p) {
+    DGCNN_PDL_WAIT();
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ PlanEntry s_plan[kMaxTeams];
     __shared__ int s_count;
@@ -980,6 +981,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
 __global__ void __launch_bounds__(256)
 stack_bwd_reduce_graphs(const float* __restrict__ partials, int parts, int total,
                         float* __restrict__ grads) {
+    DGCNN_PDL_WAIT();
     __shared__ float red[8][33];
     const int ox = threadIdx.x & 31, gy = threadIdx.x >> 5;
     const int o = blockIdx.x * 32 + ox;
@@ -1097,18 +1099,19 @@ int dgcnn_stack_bwd_mma(const float* dpooled, const int32_t* perm, int32_t k, co
         return DGCNN_ERR_CUDA;
     if (p.pairs) {
         cudaLaunchConfig_t cfg{};
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1] = pdl_attribute();
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kBwdThreads);
-        cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         if (cudaLaunchKernelEx(&cfg, stack_bwd_mma_kernel, p) != cudaSuccess) return DGCNN_ERR_CUDA;
     } else {
-        stack_bwd_mma_kernel<<<(unsigned)grid, kBwdThreads, smem, st>>>(p);
+        DGCNN_LAUNCH(stack_bwd_mma_kernel, (unsigned)grid, kBwdThreads, smem, st, p);
     }
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     const int total = grad_offsets_m(f, conv5).total;
-    stack_bwd_reduce_graphs<<<(total + 31) / 32, 256, 0, st>>>(p.partials, (int)grid, total, grads);
+    DGCNN_LAUNCH(stack_bwd_reduce_graphs, (total + 31) / 32, 256, 0, st, p.partials, (int)grid, total, grads);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

@@ -830,6 +830,7 @@ __device__ __forceinline__ void process_graph(const StackFwdParams& p, Team& tm,
 // The CTA's graphs and their teams: plan_pass() in graph_mma.cuh.
 template <bool LAZY>
 __global__ void __launch_bounds__(kFwdThreads, 1) stack_fwd_mma_kernel(StackFwdParams p) {
+    DGCNN_PDL_WAIT();
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ PlanEntry s_plan[kMaxTeams];
     __shared__ int s_count;
@@ -1106,15 +1107,16 @@ static int stack_fwd_impl(const float* x, int64_t ldx, int32_t num_features,
         grid += grid & 1;
         if (grid > DGCNN_NUM_SMS) grid = DGCNN_NUM_SMS;
         cudaLaunchConfig_t cfg{};
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1] = pdl_attribute();
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFwdThreads);
-        cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         if (cudaLaunchKernelEx(&cfg, kernel, p) != cudaSuccess) return DGCNN_ERR_CUDA;
     } else {
         if (grid > num_graphs) grid = num_graphs;
-        kernel<<<(unsigned)grid, kFwdThreads, smem, st>>>(p);
+        DGCNN_LAUNCH(kernel, (unsigned)grid, kFwdThreads, smem, st, p);
     }
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;

@@ -89,6 +89,7 @@ sp_fwd_kernel(const float* __restrict__ x, int64_t ldx, int d,
                               const int32_t* __restrict__ gptr, int64_t num_graphs, int k,
                               float* __restrict__ out, int32_t* __restrict__ perm,
                               uint64_t* __restrict__ workspace, uint32_t smem_cap) {
+    DGCNN_PDL_WAIT();
     extern __shared__ uint64_t sbuf[];
     __shared__ uint32_t hist[264];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -151,6 +152,7 @@ sp_fwd_kernel(const float* __restrict__ x, int64_t ldx, int d,
 
 __global__ void __launch_bounds__(256)
 sp_bwd_zero(float* __restrict__ dx, int64_t lddx, int d, int64_t n) {
+    DGCNN_PDL_WAIT();
     int64_t total = n * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -163,6 +165,7 @@ sp_bwd_zero(float* __restrict__ dx, int64_t lddx, int d, int64_t n) {
 __global__ void __launch_bounds__(256)
 sp_bwd_scatter(const float* __restrict__ dout, const int32_t* __restrict__ perm, int64_t rows, int d,
                float* __restrict__ dx, int64_t lddx, int64_t n) {
+    DGCNN_PDL_WAIT();
     const int lane = threadIdx.x & 31;
     int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
@@ -214,7 +217,7 @@ extern "C" int dgcnn_sort_pool_fwd(const float* x, int64_t ldx, int32_t d, const
                              (int)smem) != cudaSuccess)
         return DGCNN_ERR_CUDA;
     int grid = (int)(num_graphs < 8 * DGCNN_NUM_SMS ? num_graphs : 8 * DGCNN_NUM_SMS);
-    sp_fwd_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+    DGCNN_LAUNCH(sp_fwd_kernel, grid, threads, smem, static_cast<cudaStream_t>(stream), 
         x, ldx, d, gptr, num_graphs, k, out, perm, reinterpret_cast<uint64_t*>(aligned), cap);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
@@ -232,13 +235,13 @@ extern "C" int dgcnn_sort_pool_bwd(const float* dout, const int32_t* perm, int64
         if (cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)num_nodes * d, st) != cudaSuccess)
             return DGCNN_ERR_CUDA;
     } else {
-        sp_bwd_zero<<<grid_for(num_nodes * d, 256, 8), 256, 0, st>>>(dx, lddx, d, num_nodes);
+        DGCNN_LAUNCH(sp_bwd_zero, grid_for(num_nodes * d, 256, 8), 256, 0, st, dx, lddx, d, num_nodes);
         DGCNN_RETURN_IF_LAUNCH_FAILED();
     }
     if (num_graphs == 0) return DGCNN_OK;
     if (!dout || !perm) return DGCNN_ERR_INVALID_ARGUMENT;
     int64_t rows = num_graphs * k;
-    sp_bwd_scatter<<<grid_for(rows, 8, 8), 256, 0, st>>>(dout, perm, rows, d, dx, lddx, num_nodes);
+    DGCNN_LAUNCH(sp_bwd_scatter, grid_for(rows, 8, 8), 256, 0, st, dout, perm, rows, d, dx, lddx, num_nodes);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     return DGCNN_OK;
 }

@@ -48,6 +48,7 @@ static bool fuse_conv5_enabled() {
 // caller last cleared it -- a bad batch in the middle of an epoch is not lost (one tiny launch
 // in place of the memset that used to clear the word).
 __global__ void step_status_begin(int32_t* status) {
+    DGCNN_PDL_WAIT();
     status[1] |= status[0] & ~DGCNN_GRAPH_GENERIC;
     status[0] = 0;
 }
@@ -313,7 +314,7 @@ extern "C" int dgcnn_train_step(const float* x, int64_t ldx, const void* edge_in
     Arena a{reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255), 0};
     const StepBuffers s = carve(a, N, E, B, num_features, k, num_classes, max_nodes, false);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    step_status_begin<<<1, 1, 0, st>>>(graph_status);
+    DGCNN_LAUNCH(step_status_begin, 1, 1, 0, st, graph_status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     if (index_is_i32)
         DGCNN_TRY(dgcnn_build_graph_i32(static_cast<const int32_t*>(edge_index), E,
@@ -356,7 +357,7 @@ extern "C" int dgcnn_train_step_resident(const dgcnn_dataset* dataset, const int
         s.col_t = s.col;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    step_status_begin<<<1, 1, 0, st>>>(graph_status);
+    DGCNN_LAUNCH(step_status_begin, 1, 1, 0, st, graph_status);
     DGCNN_RETURN_IF_LAUNCH_FAILED();
     // K0b's outputs are gathered too when the data set carries them and every graph of the batch
     // owns a bitmap (max_nodes <= 1024); otherwise K0b runs on the gathered CSR

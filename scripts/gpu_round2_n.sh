@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round 2, call N: programmatic dependent launch on every kernel of the library (A/B against DGCNN_PDL=0)
+set -u
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-.}"
+D=gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=20 --tb=short -p no:cacheprovider > $D/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> $D/pytest_gpu.log
+tail -5 $D/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $D/smoke.log 2>&1; echo "smoke exit $?" >> $D/smoke.log; tail -2 $D/smoke.log
+for pdl in 1 0 1 0; do
+  DGCNN_PDL=$pdl timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > $D/bench_collab_pdl$pdl.json 2> $D/bench_collab_pdl$pdl.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_collab_pdl$pdl.json").read().strip().splitlines()[-1])
+h=d["hot_path_fwd"]; r=d.get("e2e_resident_dataset") or {}
+print("PDL=$pdl collab ms/step", round(d["ms_per_step"],4), "value", round(d["value"]), "fwd us", round(h["us"],1), "k0", round(h["graph_build_us"],1), "resident", r.get("device_step_us"), r.get("value"), "e2e", round(d["e2e"]["value"]))
+PY
+done
+DGCNN_PDL=1 timeout 600 python scripts/ks_vs_largest.py 0 492 2>&1 | tail -2

@@ -531,6 +531,46 @@ def test_graphs_beyond_one_cta_are_split_over_a_cta_pair(big_sizes, small):
     assert ops.LAUNCHES.get("train_step", 0) - before == 21
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_batches_through_the_split_plan(seed):
+    """Fuzz of the per-CTA plan (graph_mma.cuh: split set, rounds, toy grids): random batch sizes on
+    both sides of the SM count with a random number of graphs beyond one CTA's shared memory.  The
+    conv5-fused kernels against the unfused sequence (same permutation and x_cat bit for bit, loss and
+    gradients to fp32 rounding), and the cluster launch against the plain one where the plain one can
+    hold the batch."""
+    from dgcnn_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.RandomState(100 + seed)
+    small = int(rng.choice([1, 5, 40, 140, 160, 330]))
+    nbig = int(rng.choice([0, 1, 2, 9, 14]))
+    hi = 512 if seed % 2 else 432
+    big = tuple(int(v) for v in rng.randint(300, hi + 1, size=nbig))
+    cfg = CONFIGS["collab"]
+    batch = collab_batch_with_big_graphs(big, small, seed=200 + seed)
+    mx = int((batch.ptr[1:] - batch.ptr[:-1]).max())
+    torch.manual_seed(seed)
+    model = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    data = batch.to(DEV)
+    assert ops.conv5_fusable(cfg.num_features, mx)
+    st_f, gr_f, perm_f, keep_f, xcat_f = step_kernels(model, data, cfg.k, True, training=False)
+    st_u, gr_u, perm_u, keep_u, xcat_u = step_kernels(model, data, cfg.k, False, training=False)
+    assert torch.equal(perm_f, perm_u) and torch.equal(xcat_f, xcat_u)
+    assert abs(float(st_f[0]) - float(st_u[0])) <= 1e-4 * max(1.0, abs(float(st_u[0])))
+    for pname, a, b_ in zip(PARAM_NAMES, gr_f, gr_u):
+        scale = max(1e-3, float(b_.abs().max()))
+        assert (a.reshape(-1) - b_.reshape(-1)).abs().max().item() <= 2e-3 * scale, pname
+    if mx <= 432:
+        try:
+            lib.dgcnn_stack_fwd_configure(0, 80)
+            st_p, gr_p, perm_p, _, xcat_p = step_kernels(model, data, cfg.k, True, training=False)
+        finally:
+            lib.dgcnn_stack_fwd_configure(-1, 80)
+        assert torch.equal(perm_p, perm_f) and torch.equal(xcat_p, xcat_f) and torch.equal(st_p, st_f)
+        for pname, a, b_ in zip(PARAM_NAMES, gr_p, gr_f):
+            scale = max(1e-3, float(b_.abs().max()))
+            assert (a - b_).abs().max().item() <= 2e-5 * scale, pname
+
+
 @pytest.mark.parametrize("name,count", [("collab", 512), ("proteins", 128), ("collab", 3)])
 def test_backward_cluster_split_matches_the_plain_launch(name, count):
     """KSB launched as clusters of two CTAs (largest graphs split over a pair: each CTA takes half of

@@ -317,15 +317,15 @@ k0_fast_build(const void* __restrict__ src, const void* __restrict__ dst, int64_
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long f0 = 0ull, f1 = 0ull;
-    for (int64_t e = tid; e <= e0; e += stride) {
-        int64_t s = n, d = 0;
-        if (e < e0) {
-            s = ld_idx(src, e, i32);
-            d = ld_idx(dst, e, i32);
+    // One edge list position: its column, the fingerprint, sortedness against the previous edge
+    // (ps, pd; -1 before the first edge) and the row pointers it opens.  has == false is the
+    // sentinel position e == e0 that closes the last rows.
+    auto position = [&](int64_t e, bool has, int64_t s, int64_t d, int64_t ps, int64_t pd) {
+        if (has) {
             if ((uint64_t)s >= (uint64_t)n || (uint64_t)d >= (uint64_t)n) {
                 if (status) atomicOr(status, DGCNN_GRAPH_BAD_EDGE);
                 atomicOr(flags, 1);
-                continue;
+                return;
             }
             col[e] = (int32_t)d;
             if (col_t) col_t[e] = (int32_t)d;
@@ -338,13 +338,8 @@ k0_fast_build(const void* __restrict__ src, const void* __restrict__ dst, int64_
             const unsigned long long m1 = pair_mix(lo, hi, 0x165667B1u, 0xD3A2646Du);
             if (s < d) { f0 += m0; f1 += m1; } else if (s > d) { f0 -= m0; f1 -= m1; }
         }
-        int64_t ps = -1, pd = -1;
-        if (e > 0) {
-            ps = ld_idx(src, e - 1, i32);
-            pd = ld_idx(dst, e - 1, i32);
-            if ((uint64_t)ps >= (uint64_t)n) { atomicOr(flags, 1); continue; }
-        }
-        if (e < e0 && !(ps < s || (ps == s && pd < d))) atomicOr(flags, 1);   // not strictly sorted
+        if (e > 0 && (uint64_t)ps >= (uint64_t)n) { atomicOr(flags, 1); return; }
+        if (has && !(ps < s || (ps == s && pd < d))) atomicOr(flags, 1);   // not strictly sorted
         if (ps < s) {                                  // e opens row s (and any edge-free rows before it)
             rowptr[s] = (int32_t)e;
             if (rowptr_t) rowptr_t[s] = (int32_t)e;
@@ -354,6 +349,33 @@ k0_fast_build(const void* __restrict__ src, const void* __restrict__ dst, int64_
                 if (rowptr_t) rowptr_t[r] = (int32_t)e;
             }
         }
+    };
+    // Two consecutive positions per thread and step: one 16-byte (int32 input: 8-byte) load per
+    // index row instead of two loads, the second position's predecessor comes from registers, and
+    // both positions' loads are in flight together (the pass is bound by instructions and load
+    // latency, not by bandwidth: profiles/r01_k0_fast_build.md).
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & (i32 ? 7 : 15)) == 0;
+    for (int64_t p = tid; 2 * p <= e0; p += stride) {
+        const int64_t e = 2 * p;
+        const bool has_a = e < e0, has_b = e + 1 < e0;
+        int64_t sa = n, da = 0, sb = n, db = 0;
+        if (vec && has_b) {
+            if (i32) {
+                const int2 sv = reinterpret_cast<const int2*>(src)[p], dv = reinterpret_cast<const int2*>(dst)[p];
+                sa = sv.x; sb = sv.y; da = dv.x; db = dv.y;
+            } else {
+                const longlong2 sv = reinterpret_cast<const longlong2*>(src)[p];
+                const longlong2 dv = reinterpret_cast<const longlong2*>(dst)[p];
+                sa = sv.x; sb = sv.y; da = dv.x; db = dv.y;
+            }
+        } else {
+            if (has_a) { sa = ld_idx(src, e, i32); da = ld_idx(dst, e, i32); }
+            if (has_b) { sb = ld_idx(src, e + 1, i32); db = ld_idx(dst, e + 1, i32); }
+        }
+        int64_t ps = -1, pd = -1;
+        if (e > 0) { ps = ld_idx(src, e - 1, i32); pd = ld_idx(dst, e - 1, i32); }
+        position(e, has_a, sa, da, ps, pd);
+        if (e + 1 <= e0) position(e + 1, has_b, sb, db, sa, da);
     }
     // block-level sums of the fingerprints, one atomic pair per CTA
 #pragma unroll

@@ -234,8 +234,11 @@ int dgcnn_sort_pool_bwd(const float* dout, const int32_t* perm, int64_t num_grap
  * One CTA per graph; adjacency, features and sort keys stay in shared memory
  * (see dgcnn_b200/csrc/graph_stack_mma.cu and graph_stack.cu for the two variants).  Needs the size of the largest graph
  * (`max_nodes`, known on the host from the batch's ptr): graphs must fit the
- * shared-memory budget, which dgcnn_stack_fwd_supported() reports (1/0, pure host
- * arithmetic).  When it returns 0 use K1 x 4 + K2.
+ * shared-memory budget, which dgcnn_stack_fwd_supported() reports (1/0; host arithmetic
+ * plus, once per process, an occupancy query: a graph that does not fit ONE CTA is split over
+ * the two CTAs of a cluster when the device can co-schedule all pairs -- see
+ * dgcnn_stack_fwd_configure -- which lifts the limit from 560 to 608 nodes at F <= 8).
+ * When it returns 0 use K1 x 4 + K2.
  * w1 [32,F], w2/w3 [32,32], w4 [1,32] row-major; biases may be NULL.
  * ------------------------------------------------------------------------ */
 int dgcnn_stack_fwd_supported(int32_t num_features, int64_t max_nodes);
@@ -250,7 +253,11 @@ void dgcnn_stack_fwd_set_trace(int64_t* device_buffer);
  * pairs: 1 clusters (default when the device can co-schedule all pairs), 0 plain launch,
  * -1 probe again (also re-reads DGCNN_KS_PAIRS / DGCNN_KS_SPLIT_PCT); split_pct > 0: split a
  * graph whose cost exceeds this percentage of one SM's fair share of the batch (default 80).
- * Results are bit-identical either way (tests/test_gpu_headline.py). */
+ * Graphs that do not fit one CTA's shared memory are split regardless of the threshold (the
+ * *_supported functions answer for the current setting).  The setting also applies to the
+ * backward kernel (dgcnn_stack_bwd / dgcnn_stack_bwd_conv5: each CTA of a pair takes half of the
+ * row tiles, gradient rows cross through L2).  Forward results are bit-identical either way, the
+ * backward's parameter gradients equal up to fp32 summation order (tests/test_gpu_headline.py). */
 void dgcnn_stack_fwd_configure(int32_t pairs, int32_t split_pct);
 size_t dgcnn_stack_fwd_workspace_bytes(void);
 int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
@@ -276,7 +283,7 @@ int dgcnn_stack_fwd(const float* x, int64_t ldx, int32_t num_features,
  * `pooled`.  `pooled` may be NULL: the [B, k*97] SortPooling output is then never written
  * (-26 MB per COLLAB batch) and dgcnn_tail_fwd is called with pooled == NULL.
  * Tensor-core variant only; dgcnn_stack_fwd_conv5_supported: the graphs need 64 bytes more
- * shared memory per node than for dgcnn_stack_fwd. */
+ * shared memory per node than for dgcnn_stack_fwd (480 nodes in one CTA, 512 as a CTA pair). */
 int dgcnn_stack_fwd_conv5_supported(int32_t num_features, int64_t max_nodes);
 int dgcnn_stack_fwd_conv5(const float* x, int64_t ldx, int32_t num_features,
                           const int32_t* rowptr, const int32_t* col, const float* dis,

@@ -740,7 +740,9 @@ def main():
             import numpy as np
             from dgcnn_b200.synth import make_graphs
             ds_graphs = []
-            for i in range(RING):                         # the same graphs as host_batches[i]
+            # the same graphs as host_batches[i], then more up to nine steps per epoch: COLLAB's
+            # training fold (train.py:89-95, 4500 of 5000 graphs) is nine batches of 512
+            for i in range(max(RING, 9 if args.workload in ("collab", "proteins", "mutag") else RING)):
                 ds_graphs += make_graphs(cfg, cfg.batch_size, seed=324 + 1000 * rank + i)
             ds = dg.DeviceDataset(ds_graphs, dev, num_classes=cfg.num_classes)
             bs = cfg.batch_size
@@ -770,7 +772,7 @@ def main():
             gen = torch.Generator().manual_seed(324)
             drv.train_epoch(trainer, ds, all_ids, bs, gen)
             torch.cuda.synchronize()
-            epochs = max(3, e2e_steps // RING)
+            epochs = max(3, e2e_steps // max(1, len(ds) // bs))
             t0 = time.perf_counter()
             for _ in range(epochs):
                 ep_loss, ep_acc = drv.train_epoch(trainer, ds, all_ids, bs, gen)

@@ -330,6 +330,19 @@ class DeviceDataset:
         from .dp import shard_ids
         return shard_ids(np.asarray(ids, dtype=np.int64), self.nodes, self.edges, world_size, rank)
 
+    def ids_to_device_pinned(self, ids) -> torch.Tensor:
+        """int32 copy of ``ids`` on the device through a pinned staging buffer that is allocated once
+        and reused (a whole epoch's shuffled ids in one transfer).  The caller must have synchronised
+        with the previous use of the returned tensor (driver.train_epoch reads the epoch's statistics
+        before the next epoch starts)."""
+        count = int(len(ids))
+        if getattr(self, "_ids_pinned", None) is None or self._ids_pinned.numel() < count:
+            self._ids_pinned = torch.empty(max(count, 1024), dtype=torch.int32).pin_memory()
+            self._ids_device = torch.empty(self._ids_pinned.numel(), dtype=torch.int32, device=self.device)
+        self._ids_pinned[:count].copy_(torch.from_numpy(np.ascontiguousarray(ids)).to(torch.int32))
+        self._ids_device[:count].copy_(self._ids_pinned[:count], non_blocking=True)
+        return self._ids_device[:count]
+
     def ids_to_device(self, ids) -> torch.Tensor:
         t = ids if isinstance(ids, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32))
         return t.to(dtype=torch.int32).to(self.device, non_blocking=True)

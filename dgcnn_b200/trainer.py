@@ -73,6 +73,8 @@ class FusedTrainer:
         # the one-by-one Python sequence below, which is also the fallback)
         self.native = os.environ.get("DGCNN_NATIVE_STEP", "1") != "0"
         self._arena = None
+        self._resident_checked = None                 # (F, k, C) the data set was checked against
+        self._fusable_cache = {}                      # (F, largest graph, fusion switch) -> conv5 fused
         # [0] flags of the last step, [1] sticky OR of the error flags of the earlier ones
         self._graph_status = torch.zeros(2, dtype=torch.int32, device=dev)
         # multi-GPU: gradients are summed by the fused peer-memory all-reduce + Adam kernel when
@@ -110,12 +112,19 @@ class FusedTrainer:
                              "several GPUs; the ranks' shards need not hold the same number of graphs")
         return int(local_graphs)
 
-    def check_status(self) -> None:
-        """Host-syncing check of the device status words (call once per epoch): a gradient
-        exchange that timed out leaves the parameters untouched and raises here; bad input flags
-        (BAD_EDGE / BAD_BATCH / fp16 RANGE) accumulate across steps until cleared."""
-        gs = self._graph_status.tolist()
-        comm, graph = int(self.comm_status.item()), int(gs[0]) | int(gs[1])
+    def status_words(self) -> torch.Tensor:
+        """[comm_status, graph_status[0], graph_status[1]] as one float32 device tensor (flags are
+        small integers), for callers that fold the check into a host read they do anyway."""
+        return torch.cat([self.comm_status.reshape(-1)[:1], self._graph_status.reshape(-1)[:2]]).float()
+
+    def check_status(self, values=None) -> None:
+        """Check of the device status words (call once per epoch; host-syncing unless ``values`` =
+        status_words() already on the host): a gradient exchange that timed out leaves the
+        parameters untouched and raises here; bad input flags (BAD_EDGE / BAD_BATCH / fp16 RANGE)
+        accumulate across steps until cleared."""
+        if values is None:
+            values = self.status_words().tolist()
+        comm, graph = int(values[0]), int(values[1]) | int(values[2])
         if comm:
             raise RuntimeError("FusedTrainer: the peer-memory gradient exchange timed out (a rank is gone or "
                                "stuck); parameters were NOT updated by the affected steps")
@@ -205,35 +214,40 @@ class FusedTrainer:
                 self.stats[1] = (logp.argmax(1) == data.y).sum()
         return self._finish(global_batch, world)
 
-    def resident_supported(self, dataset, ids) -> bool:
+    def resident_supported(self, dataset, ids, max_nodes: Optional[int] = None) -> bool:
         """Can the one-call fused step run this batch of a DeviceDataset (every graph must fit the
-        fused kernels)?  Otherwise use ``step_autograd(dataset.batch(ids))``."""
-        mx = dataset.plan(ids)[2]
+        fused kernels)?  Otherwise use ``step_autograd(dataset.batch(ids))``.  ``max_nodes``: the
+        batch's largest graph when the caller already knows it."""
+        mx = int(max_nodes) if max_nodes is not None else dataset.plan(ids)[2]
         f = dataset.num_features
         return (ops.stack_fwd_supported(f, mx) and ops.stack_bwd_supported(f, mx)
                 and self.model.classifier_2.out_features <= 32)
 
     def step_resident(self, dataset, ids, ids_device: Optional[torch.Tensor] = None,
-                      global_batch: Optional[int] = None) -> torch.Tensor:
+                      global_batch: Optional[int] = None, plan=None) -> torch.Tensor:
         """One optimisation step on the graphs ``ids`` of a ``DeviceDataset``:
         dgcnn_collate gathers the batch from the resident data set, so neither the host
         collate (train.py:108-109) nor the host-to-device copy (train.py:36) nor K0 runs.
         Bit-identical to ``step()`` on the host-collated batch of the same graphs.  Returns
-        the device tensor [sum of NLL, number of correct predictions]."""
+        the device tensor [sum of NLL, number of correct predictions].  ``plan``: (nodes, edges,
+        largest graph) of the batch when the caller computed them already (driver.train_epoch does,
+        for the whole epoch at once); ``ids_device``: the ids already on the device."""
         import ctypes
         from . import _lib
         m = self.model
         lib = _lib.load_library()
-        n, e, mx = dataset.plan(ids)
+        n, e, mx = plan if plan is not None else dataset.plan(ids)
         b, f = int(len(ids)), dataset.num_features
         k, c = m.sort_pool.k, m.classifier_2.out_features
         world = self._world()
         global_batch = self._global_batch(b, global_batch, world)
         if dataset.device != self.flat.device:
             raise RuntimeError("FusedTrainer.step_resident: data set and model live on different devices")
-        if self.num_params != int(lib.dgcnn_train_step_num_params(f, k, c)):
-            raise RuntimeError("FusedTrainer.step_resident: the model does not match the data set "
-                               "(num_features / k / num_classes)")
+        if self._resident_checked != (f, k, c):
+            if self.num_params != int(lib.dgcnn_train_step_num_params(f, k, c)):
+                raise RuntimeError("FusedTrainer.step_resident: the model does not match the data set "
+                                   "(num_features / k / num_classes)")
+            self._resident_checked = (f, k, c)
         if world > 1 and self.exchange is None:
             raise RuntimeError("FusedTrainer.step_resident: multi-GPU needs the peer-memory exchange "
                                "(DGCNN_ALLREDUCE=p2p)")
@@ -262,7 +276,10 @@ class FusedTrainer:
         _lib.check(rc, "train_step_resident")
         # n1_gather + KS + 5 tail fwd + NLL + 12 tail bwd + 2 KSB + 2 Adam; with conv5 fused into KS / KSB
         #  the tail loses its conv5 forward kernel and three backward ones
-        launches = (16 if ops.conv5_fusable(f, mx) else 20) + (0 if b <= 1024 else 1)
+        fused = self._fusable_cache.get((f, mx, ops.FUSE_CONV5))
+        if fused is None:
+            fused = self._fusable_cache[(f, mx, ops.FUSE_CONV5)] = bool(ops.conv5_fusable(f, mx))
+        launches = (16 if fused else 20) + (0 if b <= 1024 else 1)
         ops.LAUNCHES["train_step_resident"] = ops.LAUNCHES.get("train_step_resident", 0) + launches
         return self.stats
 

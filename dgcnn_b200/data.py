@@ -339,7 +339,7 @@ class DeviceDataset:
         if getattr(self, "_ids_pinned", None) is None or self._ids_pinned.numel() < count:
             self._ids_pinned = torch.empty(max(count, 1024), dtype=torch.int32).pin_memory()
             self._ids_device = torch.empty(self._ids_pinned.numel(), dtype=torch.int32, device=self.device)
-        self._ids_pinned[:count].copy_(torch.from_numpy(np.ascontiguousarray(ids)).to(torch.int32))
+        self._ids_pinned.numpy()[:count] = np.asarray(ids)   # (casts to int32 in place)
         self._ids_device[:count].copy_(self._ids_pinned[:count], non_blocking=True)
         return self._ids_device[:count]
 

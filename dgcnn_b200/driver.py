@@ -138,6 +138,17 @@ class EpochStats:
         return loss, float(h[:, 1].sum()) / float(g.sum()) * 100.0
 
 
+def epoch_plan(order: np.ndarray, nodes: np.ndarray, edges: np.ndarray, batch_size: int):
+    """(first position, nodes, edges, largest graph) of every batch of an epoch that walks the graph
+    ids ``order`` in steps of ``batch_size`` (last batch short): ``DeviceDataset.plan`` for all
+    batches in one vectorised pass over the per-graph tables."""
+    order = np.asarray(order, dtype=np.int64)
+    starts = np.arange(0, order.size, int(batch_size))
+    nn, ne = np.asarray(nodes)[order], np.asarray(edges)[order]
+    return (starts, np.add.reduceat(nn, starts).astype(np.int64), np.add.reduceat(ne, starts).astype(np.int64),
+            np.maximum.reduceat(nn, starts).astype(np.int64))
+
+
 def train_epoch(trainer: FusedTrainer, ds: DeviceDataset, ids: np.ndarray, batch_size: int,
                 generator: torch.Generator) -> Tuple[float, float]:
     """train.py:27-47.  The host side of a step is kept below the device time of the fused step
@@ -150,11 +161,7 @@ def train_epoch(trainer: FusedTrainer, ds: DeviceDataset, ids: np.ndarray, batch
     if ids.min() < 0 or ids.max() >= ds.num_graphs:
         raise IndexError("train_epoch: graph id outside the data set")
     order = ids[torch.randperm(ids.size, generator=generator).numpy()]   # (= epoch_batches(shuffle=True))
-    starts = np.arange(0, order.size, batch_size)
-    nn, ne = ds.nodes[order], ds.edges[order]
-    n_b = np.add.reduceat(nn, starts)
-    e_b = np.add.reduceat(ne, starts)
-    mx_b = np.maximum.reduceat(nn, starts)
+    starts, n_b, e_b, mx_b = epoch_plan(order, ds.nodes, ds.edges, batch_size)
     ids_dev = ds.ids_to_device_pinned(order)                  # one H2D per epoch (reused pinned buffer)
     st = EpochStats(ds.device, len(starts))
     fits = {}                                                 # largest graph -> fused step possible

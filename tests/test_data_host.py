@@ -283,3 +283,37 @@ def test_resident_loader_iterates_like_the_reference_dataloader():
     assert sum(rec2.seen, []) == ids[torch.randperm(23, generator=g2).numpy()].tolist()
     with pytest.raises(ValueError):
         dd.ResidentLoader(rec, ids, batch_size=0)
+
+
+def test_epoch_plan_equals_the_per_batch_sums():
+    """driver.epoch_plan (one vectorised pass for a whole epoch) against the per-batch arithmetic of
+    DeviceDataset.plan: nodes, edges and the largest graph of every batch, short last batch included;
+    the batches are the ones epoch_batches yields for the same permutation."""
+    rng = np.random.RandomState(3)
+    nodes = rng.randint(1, 500, size=1037).astype(np.int64)
+    edges = (nodes * rng.randint(0, 30, size=nodes.size)).astype(np.int64)
+    for batch_size in (1, 7, 512, 1037, 5000):
+        gen = torch.Generator().manual_seed(batch_size)
+        ids = np.arange(nodes.size, dtype=np.int64)
+        order = ids[torch.randperm(ids.size, generator=gen).numpy()]
+        starts, n_b, e_b, mx_b = driver.epoch_plan(order, nodes, edges, batch_size)
+        gen = torch.Generator().manual_seed(batch_size)
+        batches = list(dd.epoch_batches(ids, batch_size, True, gen))
+        assert len(batches) == len(starts)
+        for i, b in enumerate(batches):
+            np.testing.assert_array_equal(b, order[starts[i]:starts[i] + batch_size])
+            assert (int(n_b[i]), int(e_b[i]), int(mx_b[i])) == \
+                (int(nodes[b].sum()), int(edges[b].sum()), int(nodes[b].max()))
+
+
+def test_epoch_stats_reproduce_the_reference_running_means():
+    """EpochStats (train.py:33, 44-45): mean of the per-batch MEAN losses and accuracy over all
+    samples, from per-step [sum of NLL, #correct] pairs; unequal last batch."""
+    st = driver.EpochStats(torch.device("cpu"), steps=2)
+    sums = [(10.0, 3.0, 8), (4.0, 5.0, 8), (1.5, 1.0, 3)]          # more steps than announced: grows
+    for s, c, g in sums:
+        st.add(torch.tensor([s, c, 99.0]), g)
+    loss, acc = st.result()
+    assert abs(loss - (10.0 / 8 + 4.0 / 8 + 1.5 / 3) / 3) < 1e-12
+    assert abs(acc - 9.0 / 19 * 100.0) < 1e-12
+    assert driver.EpochStats(torch.device("cpu")).result() == (0.0, 0.0)

@@ -60,6 +60,8 @@ SIGNATURES = {
                                                              c_int32, c_int64]),
     "dgcnn_train_step_resident": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, c_int32,
                                             c_int32, c_int64, c_int32] + _STEP_TAIL),
+    "dgcnn_train_step_resident_graphed": (c_int32, [_DATASET_P, c_void_p, c_int64, c_int64, c_int64, c_int32,
+                                            c_int32, c_int64, c_int32] + _STEP_TAIL),
     "dgcnn_abi_version": (c_int32, []),
     "dgcnn_status_string": (c_char_p, [c_int32]),
     "dgcnn_build_graph_workspace_bytes": (c_size_t, [c_int64, c_int64]),
@@ -184,6 +186,7 @@ SIGNATURES = {
                                        c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "dgcnn_train_step_configure": (None, [c_int32]),
     "dgcnn_train_step_configure_maps": (None, [c_int32]),
+    "dgcnn_train_step_graph_counts": (None, [c_void_p]),
     "dgcnn_train_step_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32, c_int32,
                                                     c_int64]),
     "dgcnn_train_step_num_params": (c_int64, [c_int32, c_int32, c_int32]),

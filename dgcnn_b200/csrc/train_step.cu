@@ -374,3 +374,89 @@ extern "C" int dgcnn_train_step_resident(const dgcnn_dataset* dataset, const int
     return step_after_build(t, s, s.x_batch, F, nullptr, s.batch32, s.y_batch, maps);
 }
 #undef DGCNN_TRY
+
+// The resident step replayed as a CUDA graph (the product loop, driver.train_epoch): every call
+// stream-captures the step -- host work only -- and UPDATES the executable graph of the previous
+// call in place (cudaGraphExecUpdate: same topology, new kernel arguments and grids), then launches
+// it.  The device runs the step without the gaps of 16 eagerly launched kernels and their
+// side-stream events (233 us -> the captured step's time); a change of topology (conv5 fusion on /
+// off, more than 1024 graphs) re-instantiates.  The first call on a device runs eagerly: it
+// creates what must not be created under capture (side stream, function attributes, probes).
+namespace {
+struct StepGraph { cudaGraphExec_t exec = nullptr; bool warmed = false; };
+StepGraph g_step_graph[64];
+int64_t g_step_graph_counts[4] = {0, 0, 0, 0};        // updated in place, instantiated, eager, capture failed
+}  // namespace
+
+// debug: how the graph-replayed steps of this process were launched
+// {updated in place, newly instantiated, run eagerly, capture failed}
+extern "C" void dgcnn_train_step_graph_counts(int64_t* out4) {
+    for (int i = 0; i < 4; ++i) out4[i] = g_step_graph_counts[i];
+}
+
+extern "C" int dgcnn_train_step_resident_graphed(const dgcnn_dataset* dataset, const int32_t* ids,
+                                                 int64_t num_nodes, int64_t num_edges, int64_t num_graphs,
+                                                 int32_t k, int32_t num_classes, int64_t max_nodes, int32_t norm,
+                                                 float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                                                 int64_t* step, float lr, float beta1, float beta2, float eps,
+                                                 int64_t global_batch, int32_t training, uint64_t seed,
+                                                 int64_t* rng_offset, void* const* exchange, int32_t world,
+                                                 int32_t rank, int64_t* epoch, int32_t* comm_status,
+                                                 int32_t* graph_status, void* workspace, size_t workspace_bytes,
+                                                 void* stream) {
+    auto plain = [&]() {
+        return dgcnn_train_step_resident(dataset, ids, num_nodes, num_edges, num_graphs, k, num_classes, max_nodes,
+                                         norm, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps,
+                                         global_batch, training, seed, rng_offset, exchange, world, rank, epoch,
+                                         comm_status, graph_status, workspace, workspace_bytes, stream);
+    };
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || st == nullptr ||
+        cudaStreamIsCapturing(st, &capturing) != cudaSuccess || capturing != cudaStreamCaptureStatusNone) {
+        ++g_step_graph_counts[2];
+        return plain();                                   // (legacy stream / already inside a capture)
+    }
+    StepGraph& sg = g_step_graph[dev];
+    if (!sg.warmed) {
+        sg.warmed = true;
+        ++g_step_graph_counts[2];
+        return plain();
+    }
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        ++g_step_graph_counts[3];
+        return plain();
+    }
+    const int rc = plain();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ended = cudaStreamEndCapture(st, &graph);
+    if (rc != DGCNN_OK || ended != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        ++g_step_graph_counts[3];
+        return rc != DGCNN_OK ? rc : DGCNN_ERR_CUDA;
+    }
+    bool updated = sg.exec != nullptr;
+    if (sg.exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(sg.exec, graph, &info) != cudaSuccess) {
+            cudaGetLastError();                           // topology changed: build a new executable
+            cudaGraphExecDestroy(sg.exec);
+            sg.exec = nullptr;
+            updated = false;
+        }
+    }
+    if (!sg.exec && cudaGraphInstantiate(&sg.exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        sg.exec = nullptr;
+        cudaGraphDestroy(graph);
+        return plain();
+    }
+    cudaGraphDestroy(graph);
+    ++g_step_graph_counts[updated ? 0 : 1];
+    if (cudaGraphLaunch(sg.exec, st) != cudaSuccess) return DGCNN_ERR_CUDA;
+    return DGCNN_OK;
+}
+

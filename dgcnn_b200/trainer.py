@@ -223,15 +223,25 @@ class FusedTrainer:
         return (ops.stack_fwd_supported(f, mx) and ops.stack_bwd_supported(f, mx)
                 and self.model.classifier_2.out_features <= 32)
 
+    def graph_stream(self) -> torch.cuda.Stream:
+        """A stream of the trainer's own for graph-replayed steps (CUDA graphs cannot be captured on
+        the legacy default stream)."""
+        if getattr(self, "_graph_stream", None) is None:
+            with torch.cuda.device(self.flat.device):
+                self._graph_stream = torch.cuda.Stream()
+        return self._graph_stream
+
     def step_resident(self, dataset, ids, ids_device: Optional[torch.Tensor] = None,
-                      global_batch: Optional[int] = None, plan=None) -> torch.Tensor:
+                      global_batch: Optional[int] = None, plan=None, graphed: bool = False) -> torch.Tensor:
         """One optimisation step on the graphs ``ids`` of a ``DeviceDataset``:
         dgcnn_collate gathers the batch from the resident data set, so neither the host
         collate (train.py:108-109) nor the host-to-device copy (train.py:36) nor K0 runs.
         Bit-identical to ``step()`` on the host-collated batch of the same graphs.  Returns
         the device tensor [sum of NLL, number of correct predictions].  ``plan``: (nodes, edges,
         largest graph) of the batch when the caller computed them already (driver.train_epoch does,
-        for the whole epoch at once); ``ids_device``: the ids already on the device."""
+        for the whole epoch at once); ``ids_device``: the ids already on the device; ``graphed``:
+        replay the step as a CUDA graph that is updated in place from call to call
+        (dgcnn_train_step_resident_graphed; needs a non-default current stream, see graph_stream())."""
         import ctypes
         from . import _lib
         m = self.model
@@ -263,7 +273,8 @@ class FusedTrainer:
             table = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p_)) for p_ in self.exchange.ptrs])
             epoch, rank = self.exchange.epoch.data_ptr(), self.exchange.rank
         with torch.cuda.device(self.flat.device):
-            rc = lib.dgcnn_train_step_resident(
+            entry = lib.dgcnn_train_step_resident_graphed if graphed else lib.dgcnn_train_step_resident
+            rc = entry(
                 dataset.c_struct, ids_device.data_ptr(), n, e, b, k, c, mx, int(m.conv1.norm),
                 self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                 self.step_count.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, int(global_batch),

@@ -631,6 +631,22 @@ int dgcnn_train_step_resident(const dgcnn_dataset* dataset, const int32_t* ids, 
                               uint64_t seed, int64_t* rng_offset, void* const* exchange, int32_t world,
                               int32_t rank, int64_t* epoch, int32_t* comm_status, int32_t* graph_status,
                               void* workspace, size_t workspace_bytes, void* stream);
+/* The same step replayed as a CUDA graph: each call captures the launch sequence (host work only),
+ * updates the executable graph kept from the previous call in place (cudaGraphExecUpdate) and launches
+ * it -- the product loop's way of running the step without eager-launch gaps (train.py:35-45 once per
+ * batch; driver.train_epoch).  Same arguments, same results bit for bit; `stream` must be a real
+ * (non-legacy) stream that is not being captured, else the call degrades to dgcnn_train_step_resident.
+ * The first call per device runs eagerly. */
+int dgcnn_train_step_resident_graphed(const dgcnn_dataset* dataset, const int32_t* ids, int64_t num_nodes,
+                              int64_t num_edges, int64_t num_graphs, int32_t k, int32_t num_classes,
+                              int64_t max_nodes, int32_t norm, float* params, float* grads,
+                              float* exp_avg, float* exp_avg_sq, int64_t* step, float lr, float beta1,
+                              float beta2, float eps, int64_t global_batch, int32_t training,
+                              uint64_t seed, int64_t* rng_offset, void* const* exchange, int32_t world,
+                              int32_t rank, int64_t* epoch, int32_t* comm_status, int32_t* graph_status,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* debug: {updated in place, newly instantiated, run eagerly, capture failed} calls of the above */
+void dgcnn_train_step_graph_counts(int64_t* out4);
 
 #ifdef __cplusplus
 }

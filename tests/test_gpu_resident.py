@@ -356,3 +356,46 @@ def test_driver_epoch_falls_back_for_graphs_beyond_the_fused_kernels():
     assert abs(loss - total / 4) <= 1e-4 * max(1.0, abs(total / 4))
     for (n_, p_), (_, q_) in zip(model.named_parameters(), ref_model.named_parameters()):
         assert (p_ - q_).abs().max().item() <= 5e-5, n_
+
+
+def test_graph_replayed_resident_step_is_bit_identical_to_the_eager_one():
+    """dgcnn_train_step_resident_graphed (the step captured on every call, the executable graph
+    updated in place, then launched) against the eagerly launched resident step: statistics and
+    parameters bit for bit over batches of changing size -- including a change of topology (a batch
+    whose largest graph takes the conv5 fusion away re-instantiates the graph) -- and the library's
+    own counters say that the graph path really ran."""
+    cfg = CONFIGS["collab"]
+    graphs = make_graphs(cfg, 160, seed=12)
+    ds = dg.DeviceDataset(graphs, DEV, num_classes=cfg.num_classes)
+    rng = np.random.RandomState(0)
+    batches = [np.sort(rng.choice(len(graphs), size=sz, replace=False)) for sz in (64, 17, 100, 64, 3)]
+    torch.manual_seed(2)
+    base = dg.Model(cfg.num_features, cfg.num_classes, cfg.k).to(DEV).train()
+    lib = _lib.load_library()
+    before = (ctypes.c_int64 * 4)()
+    lib.dgcnn_train_step_graph_counts(ctypes.cast(before, ctypes.c_void_p))
+    results = {}
+    for graphed in (False, True):
+        tr = dg.FusedTrainer(copy.deepcopy(base))
+        stream = tr.graph_stream() if graphed else torch.cuda.current_stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        stats = []
+        with torch.cuda.stream(stream):
+            for step, ids in enumerate(batches):
+                if step == 3:
+                    ops.set_fuse_conv5(False)                 # another launch sequence: new topology
+                try:
+                    stats.append(tr.step_resident(ds, ids, graphed=graphed).clone())
+                finally:
+                    ops.set_fuse_conv5(True)
+            tr.check_status()
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        results[graphed] = (stats, tr.flat.clone())
+    for a, b_ in zip(results[False][0], results[True][0]):
+        assert torch.equal(a, b_)
+    assert torch.equal(results[False][1], results[True][1])
+    after = (ctypes.c_int64 * 4)()
+    lib.dgcnn_train_step_graph_counts(ctypes.cast(after, ctypes.c_void_p))
+    updated, instantiated, eager, failed = (int(after[i] - before[i]) for i in range(4))
+    assert failed == 0 and updated + instantiated >= 4 and instantiated >= 1

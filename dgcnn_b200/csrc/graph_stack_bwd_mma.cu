@@ -1,6 +1,6 @@
 // Tensor-core version of the fused backward (autograd of model.py:28-35, train.py:40),
-// the mirror image of graph_stack_mma.cu.  One TEAM (1, 2 or 4 quads of a 512-thread CTA)
-// per graph; per layer l = 4..1:
+// the mirror image of graph_stack_mma.cu.  One TEAM of warps per graph (the per-CTA plan of
+// graph_mma.cuh: up to eight graphs of a 640-thread CTA run concurrently); per layer l = 4..1:
 //
 //   dpre = dy * (1 - y^2)            row-local, db += column sums
 //   dh   = c_i * (A_hat^T . r dpre)  mma.sync: A^T from the bitmap (exact 0/1 fp16),
@@ -12,9 +12,19 @@
 // the largest pooled gradient it receives (exact to apply and to undo) before anything is
 // split into fp16 hi/lo pairs; a graph whose pooled gradient is all zero is skipped.
 //
-// Determinism without float atomics and without a fixed graph->CTA assignment: every graph
-// writes ITS OWN parameter-gradient vector to HBM; a second kernel sums the B vectors in
-// graph order.  (B x 2.2k floats = 4.5 MB on COLLAB-synth bs512.)
+// A graph that the plan SPLITS over the two CTAs of a cluster (large graphs; mandatory beyond one
+// CTA's shared memory): each CTA takes half of the 16-row tiles -- the column-indexed planes are
+// built whole in both, dh / adjacency / parameter-gradient sums only for the own rows, the
+// gradient rows G cross through L2 between two alternating buffers under ONE cluster barrier per
+// layer (bwd_process_graph).
+//
+// SURVEY 8f N2 (dh1 != null): the backward of conv5 + ReLU + MaxPool1d is fused in -- dz planes
+// from d(h1) / arg (the graph's slab staged once in shared memory), dz W5 added where a layer's
+// input gradient is assembled (dz_w5_tile), dW5 / db5 in the dW tile loop.
+//
+// Determinism without float atomics: the plan is a pure function of the graph sizes, a CTA adds
+// its teams' parameter-gradient vectors in team order and writes ONE partial vector to HBM; a
+// second kernel sums the CTAs' vectors in CTA order.  (148 x 3.8k floats = 2.2 MB.)
 #include "graph_mma.cuh"
 
 namespace dgcnn {

@@ -22,8 +22,17 @@
 //               then an fp32 FMA projection F -> 32.  F > 8: project first (FMA), aggregate
 //               on the tensor cores.
 //   layer 4     32 -> 1: v = c_i (x_3 . w4) is emitted by layer 3's epilogue; one MMA column.
-//   SortPool    64-bit (key, index) composites, rank sort (n <= 256) or bitonic; the k winners
+//   SortPool    64-bit (key, index) composites, rank sort (n <= 640) or bitonic; the k winners
 //               are copied row by row (one warp per row) from x_cat (L2 hits) into `pooled`.
+//   conv5       SURVEY 8f N2 (h1 != null): z[node][16] = W5 x_cat[node] + b5 accumulated in the layer
+//               epilogues (project16), ReLU + pair maximum on the k winners; `pooled` optional.
+//   clusters    the kernel is launched as clusters of two CTAs; the plan (graph_mma.cuh) SPLITS
+//               the largest graphs over a pair -- mandatorily those that do not fit one CTA's
+//               shared memory: each CTA owns half of the row tiles and pushes its rows into the
+//               peer's planes with DSMEM bulk copies + mbarrier transactions (pair_exchange).
+//   lazy maps   stack_fwd_mma_kernel<true> (the one-call training step): no K0b maps -- every team
+//               expands its graph's CSR rows into the fragment-major map itself and exports it
+//               for the backward kernel (phase 0 of process_graph).
 //
 // mma.sync (register fragments) is used on purpose, not tcgen05: the operands are generated
 // in registers from a bitmap for graphs of ~30-500 nodes; tcgen05 needs shared-memory operand

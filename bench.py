@@ -17,6 +17,14 @@ single gradient all-reduce when N > 1, Adam.  Prints ONE JSON line on rank 0.
 `roofline`   the dominant kernel, timed alone with CUDA events, against MEASURED_PEAKS
 `cpu_baseline` / `--impl reference`   the CPU oracle restatement of the reference's
              path (PyG itself is not installable here), timed on this host's cores
+
+N > 1 (torchrun, one rank per GPU): weak scaling, 512 graphs per rank and step; `--shards balanced`
+(default) deals a global batch of 512 N graphs with dp.balanced_shards.  The ranks' timed steps
+are queued behind a device-side rendezvous right after the host barrier; `first_timed_step_ms` /
+`ms_per_step_after_first` show what start skew is left, `per_rank` each rank's own view,
+`params_equal_across_ranks` / `comm_status_per_rank` that the replicas stayed identical;
+`--trace-exchange FILE` records the exchange kernel's %globaltimer timeline per step and rank.
+Other BASELINE configs: `--workload dd|powerlaw|proteins|mutag`.
 """
 from __future__ import annotations
 

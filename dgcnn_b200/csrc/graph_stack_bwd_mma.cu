@@ -93,7 +93,10 @@ __host__ __device__ inline BwdShared bwd_shared_layout(int f, bool conv5 = false
     L.w4 = o; o += kHid * 4;
     L.w5t = o; o += conv5 ? 2 * 104 * kW5TPad * 2 : 0;   // W5^T hi/lo planes [plane][column i][channel]
     L.w5x = o; o += conv5 ? (kC5b + 4) * 4 : 0;          // W5[:, 96] fp32, then max_i sum_c |W5[c][i]|
-    L.acc = o; o += al16(grad_offsets_m(f, conv5).total * 4);   // the CTA's running parameter-gradient sum
+    L.acc = o;                                           // (the CTA's running parameter-gradient sum lives in
+                                                         //  its slot of `partials` in HBM / L2: 15 KB more
+                                                         //  shared memory for the graphs -- one team more per
+                                                         //  pass, and a second pass costs a whole ~50 us chain)
     L.total = o;
     return L;
 }
@@ -885,8 +888,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
     const bool conv5 = p.dh1 != nullptr;
     const BwdShared SL = bwd_shared_layout(f, conv5);
     const int gtotal = grad_offsets_m(f, conv5).total;
-    float* cta_acc = reinterpret_cast<float*>(smraw + SL.acc);
-    for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) cta_acc[idx] = 0.f;
+    float* out = p.partials + (int64_t)blockIdx.x * gtotal;      // this CTA's partial vector (running sum)
     // A_hat^T: the forward bitmap when K0 proved the batch symmetric, else the transposed one
     const bool use_t = p.status && (*p.status & DGCNN_GRAPH_GENERIC) && p.bitmap_t;
     const uint32_t* gbm = use_t ? p.bitmap_t : p.bitmap;
@@ -947,7 +949,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
         }
         __syncthreads();                             // the plan (and, first time, the weights)
         const int count = s_count;
-        if (count == 0) break;
+        if (count == 0) {
+            if (pass == 0)                           // a CTA without graphs still owns a row of the reduction
+                for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) out[idx] = 0.f;
+            break;
+        }
         int mine = -1;
         for (int j = 0; j < count; ++j)
             if (warp_id >= s_plan[j].warp0 && warp_id < s_plan[j].warp0 + s_plan[j].nwarps) mine = j;
@@ -970,19 +976,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) stack_bwd_mma_kernel(StackBwdM
             }
         }
         __syncthreads();                             // every team's vector is complete
-        // fixed order (pass by pass, team by team) on a static plan: bit-reproducible sums
-        for (int j = 0; j < count; ++j) {
-            const PlanEntry& e = s_plan[j];
-            if (e.n > p.nmax) continue;
-            const int np = max(16, (e.n + 15) & ~15);
-            const float* sacc = reinterpret_cast<const float*>(team_base + e.smem_off +
-                                                               bwd_team_layout(f, np, conv5, e.pad != 0).sacc);
-            for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) cta_acc[idx] += sacc[idx];
+        // fixed order (pass by pass, team by team) on a static plan: bit-reproducible sums.  Every
+        // thread owns the same elements in every pass, so the running sum needs no barrier of its own.
+        for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) {
+            float a = pass == 0 ? 0.f : out[idx];
+            for (int j = 0; j < count; ++j) {
+                const PlanEntry& e = s_plan[j];
+                if (e.n > p.nmax) continue;
+                const int np = max(16, (e.n + 15) & ~15);
+                const float* sacc = reinterpret_cast<const float*>(team_base + e.smem_off +
+                                                                   bwd_team_layout(f, np, conv5, e.pad != 0).sacc);
+                a += sacc[idx];
+            }
+            out[idx] = a;
         }
-        next += count;                               // (the next pass syncs before it re-carves)
+        next += count;
+        __syncthreads();                             // s_plan and the teams' vectors are free for the next pass
     }
-    float* out = p.partials + (int64_t)blockIdx.x * gtotal;
-    for (int idx = threadIdx.x; idx < gtotal; idx += kBwdThreads) out[idx] = cta_acc[idx];
 }
 
 // grads[o] = sum over graphs (deterministic: fixed partition, fixed order).  Block =

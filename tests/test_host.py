@@ -246,3 +246,19 @@ def test_resident_entry_points_validate_before_touching_cuda():
     assert lib.dgcnn_train_step_resident(None, None, 1, 0, 1, 30, 2, 1, 0, None, None, None, None, None,
                                          1e-3, 0.9, 0.999, 1e-8, 1, 0, 0, None, None, 1, 0, None, None, None,
                                          None, 0, None) == INVALID
+
+
+def test_bench_reads_the_kernel_traffic_from_the_committed_profile(tmp_path, monkeypatch):
+    """bench.py's roofline.traffic comes from profiles/r02_stack_fwd_mma.md (an ncu --set full
+    summary), not from a constant: the parser on the committed file and on a hand-made one."""
+    import bench
+    got = bench.ks_traffic_from_profile()
+    assert got is not None and 100_000 < got < 200_000_000
+    fake = tmp_path / "ks.md"
+    fake.write_text("| metric | value | unit |\n|---|---:|---|\n| gpu__time_duration.sum | 32.4 | us |\n"
+                    "| dram__bytes_read.sum | 1.5 | Mbyte |\n| dram__bytes_write.sum | 250.0 | Kbyte |\n"
+                    "| dram__bytes_read.sum | 9.0 | Mbyte |\n")
+    monkeypatch.setattr(bench, "KS_PROFILE", str(fake))
+    assert bench.ks_traffic_from_profile() == 1_750_000
+    monkeypatch.setattr(bench, "KS_PROFILE", str(tmp_path / "missing.md"))
+    assert bench.ks_traffic_from_profile() is None
